@@ -1,0 +1,150 @@
+/* samurai_b200 -- C ABI of the B200-native implementation of samurai's per-time-step hot path.
+ *
+ * samurai (hpc-maths/samurai v0.33.0) is a header-only C++ library with no plugin/FFI layer; its "boundary" is its
+ * public C++ API.  This header is what a `<samurai/...>` header set binds to: every entry point
+ * names the reference interface it replaces (paths relative to the reference's include/samurai/).
+ *
+ * Conventions: plain C types, opaque handles, every call returns 0 on success and non-zero on failure with the
+ * message available from smr_last_error().  Errors the reference raises as C++ exceptions (std::out_of_range from
+ * LevelCellArray::get_interval, level_cell_array.hpp:671-724; std::invalid_argument from attach_bc,
+ * field/field_base.hpp:306-315) are reported with the codes below so the C++ side can re-throw the same type.
+ * One host thread per process drives one GPU; work is asynchronous on one CUDA stream and the calls that return
+ * data to the host synchronise it.  There is NO CPU fallback: compute entry points fail with SMR_ERR_CUDA when no
+ * device is available.  Host-only entry points (mesh construction and queries) work without a GPU.
+ */
+#ifndef SAMURAI_B200_H
+#define SAMURAI_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C"
+{
+#endif
+
+    typedef uint64_t smr_mesh_t;
+    typedef uint64_t smr_field_t;
+
+    enum
+    {
+        SMR_OK               = 0,
+        SMR_ERR_INVALID      = 1, /* std::invalid_argument */
+        SMR_ERR_OUT_OF_RANGE = 2, /* std::out_of_range     */
+        SMR_ERR_CUDA         = 3, /* CUDA runtime failure / no device */
+        SMR_ERR_INTERNAL     = 4
+    };
+
+    /* mesh_id_t of MRMesh (mr/mesh.hpp:25-34) */
+    enum
+    {
+        SMR_MESH_CELLS            = 0,
+        SMR_MESH_CELLS_AND_GHOSTS = 1,
+        SMR_MESH_PROJ_CELLS       = 2,
+        SMR_MESH_UNION_CELLS      = 3,
+        SMR_MESH_REFERENCE        = 4
+    };
+
+    /* mesh_config<dim, prediction_stencil_radius> (mesh_config.hpp:20-432) after parse_args() */
+    typedef struct
+    {
+        int32_t dim;                /* 1, 2 or 3                                                   */
+        int32_t min_level;          /* mesh_config::min_level                                      */
+        int32_t max_level;          /* mesh_config::max_level                                      */
+        int32_t pred_radius;        /* template parameter prediction_stencil_radius: 0 or 1        */
+        int32_t max_stencil_radius; /* mesh_config::max_stencil_radius (only 1 is implemented)     */
+        int32_t graduation_width;   /* mesh_config::graduation_width                               */
+        int32_t n_cells0[3];        /* box size in level-0 cells: length / scaling_factor          */
+        double origin[3];           /* Box::min_corner                                             */
+        double scaling_factor;      /* LevelCellArray::scaling_factor (box.hpp:280-, approximate_box) */
+    } smr_mesh_config;
+
+    /* one x-interval of a sub-mesh: LevelCellArray entry (interval.hpp:50-64) flattened with its (y, z) */
+    typedef struct
+    {
+        int32_t y, z;
+        int32_t start, end; /* [start, end) */
+        int64_t offset;     /* storage offset of cell `start` (= Interval::index + start)          */
+    } smr_interval;
+
+    /* ---- runtime (samurai.hpp:22-114 initialize/finalize) ------------------------------------------------------ */
+    int smr_init(int device);  /* device < 0: host-only mode (no CUDA context is created)            */
+    int smr_finalize(void);
+    const char* smr_last_error(void);
+    int smr_device_available(void);
+    int smr_set_stream(void* cuda_stream); /* run on an existing cudaStream_t (e.g. torch's current stream) */
+    int smr_synchronize(void);
+
+    /* ---- mesh: samurai::mra::make_mesh(box, cfg) / MRMesh(ca, cfg) (mr/mesh.hpp:481-529, mesh.hpp:326-412) ------ */
+    int smr_mesh_create_uniform(const smr_mesh_config* cfg, int level, smr_mesh_t* out); /* start_level = level */
+    int smr_mesh_create_from_intervals(const smr_mesh_config* cfg, const int32_t* levels, const smr_interval* ivl, int64_t n, smr_mesh_t* out);
+    int smr_mesh_destroy(smr_mesh_t m);
+    int smr_mesh_config_get(smr_mesh_t m, smr_mesh_config* out);
+    /* mesh.nb_cells(mesh_id) / nb_cells(level, mesh_id) (mesh.hpp:541-558); level < 0: all levels */
+    int smr_mesh_nb_cells(smr_mesh_t m, int mesh_id, int level, int64_t* out);
+    int smr_mesh_nb_intervals(smr_mesh_t m, int mesh_id, int level, int64_t* out);
+    /* for_each_interval(mesh[mesh_id][level]) order (algorithm.hpp:75-132); `out` has room for nb_intervals */
+    int smr_mesh_get_intervals(smr_mesh_t m, int mesh_id, int level, smr_interval* out);
+    int smr_mesh_generation(smr_mesh_t m, uint64_t* out); /* bumped by every adaptation that changes the mesh */
+    /* mesh.get_index(level, i, j, k) (mesh.hpp:772-789): -1 in *out and SMR_ERR_OUT_OF_RANGE when absent */
+    int smr_mesh_get_index(smr_mesh_t m, int level, int i, int j, int k, int64_t* out);
+
+    /* host half of the adaptation on its own: update_cell_array_from_tag + make_graduation + MRMesh(new_ca, mesh)
+     * (algorithm/graduation.hpp:743-842, 573-726; mr/adapt.hpp:363-380).  `tags` is reference-sized (CellFlag bits,
+     * cell_flag.hpp:11-17).  Fields on the mesh are NOT transferred: resize them.  Works without a GPU. */
+    int smr_mesh_update_from_tags(smr_mesh_t m, const uint8_t* tags, int64_t n, int* unchanged);
+
+    /* ---- fields: make_scalar_field<double>(name, mesh) (field/scalar_field.hpp:171-215) ------------------------- */
+    int smr_field_create(smr_mesh_t m, const char* name, smr_field_t* out);
+    int smr_field_destroy(smr_field_t f);
+    int smr_field_resize(smr_field_t f);                 /* Field::resize() (field/access_base.hpp:105-115) */
+    int smr_field_fill(smr_field_t f, double v);         /* Field::fill */
+    int smr_field_size(smr_field_t f, int64_t* out);     /* nb_cells(reference) */
+    int smr_field_upload(smr_field_t f, const double* host, int64_t n);   /* host -> device, n == size */
+    int smr_field_download(smr_field_t f, double* host, int64_t n);       /* device -> host, synchronises */
+    int smr_field_swap(smr_field_t a, smr_field_t b);    /* std::swap(u.array(), v.array()) */
+    /* make_bc<Dirichlet<1>>(u, v) / make_bc<Neumann<1>>(u, v), constant value, Everywhere (bc/bc.hpp:751-815) */
+    enum
+    {
+        SMR_BCTYPE_DIRICHLET = 0, /* bc/dirichlet.hpp:19-30 */
+        SMR_BCTYPE_NEUMANN   = 1  /* bc/neumann.hpp:19-35   */
+    };
+
+    int smr_field_set_bc(smr_field_t f, int bc_type, double value);
+
+    /* ---- hot path ------------------------------------------------------------------------------------------------ */
+    /* update_ghost_mr(field) (algorithm/update_ghost_mr.hpp:260-270 -> :194-237) */
+    int smr_update_ghost_mr(smr_field_t f);
+    /* unp1 = u - dt * upwind(a, u)  (stencil_field.hpp:83-179 through field_base.hpp:230-242) */
+    int smr_fv_upwind(smr_field_t unp1, smr_field_t u, const double* a, double dt);
+    /* unp1 = u - dt * upwind_scalar_burgers(k, u)  (stencil_field.hpp:184-249) */
+    int smr_fv_upwind_burgers(smr_field_t unp1, smr_field_t u, const double* k, double dt);
+
+    /* make_MRAdapt(fields...)(mra_config) (mr/adapt.hpp:148-195, 277-389): adapts the mesh IN PLACE and transfers
+     * `fields`; any other field living on the mesh must be smr_field_resize()d by the caller, as in the reference.
+     * *n_iterations receives the number of harten iterations executed. */
+    int smr_adapt(const smr_field_t* fields, int n_fields, double epsilon, double regularity, int* n_iterations);
+    /* one harten iteration (mr/adapt.hpp:277-389); *unchanged = 1 when the mesh was already at its fixed point */
+    int smr_adapt_iteration(const smr_field_t* fields, int n_fields, double epsilon, double regularity, int ite, int* unchanged);
+    /* detail and tag arrays of the last harten iteration, reference-sized, as they were BEFORE the mesh update;
+     * n must equal the reference size of the mesh that iteration ran on (smr_adapt_last_size) */
+    int smr_adapt_last_size(smr_mesh_t m, int64_t* out);
+    int smr_adapt_last_tags(smr_mesh_t m, uint8_t* host, int64_t n);
+    int smr_adapt_last_detail(smr_mesh_t m, double* host, int64_t n);
+
+    /* ---- instrumentation (timers.hpp: "mesh adaptation", "ghost update", ...) ------------------------------------ */
+    typedef struct
+    {
+        uint64_t kernel_launches; /* kernels of this library launched since the last reset                          */
+        uint64_t h2d_bytes;
+        uint64_t d2h_bytes;
+        double host_mesh_seconds;  /* update_cell_array_from_tag + make_graduation + sub-mesh construction          */
+        double host_batch_seconds; /* set-algebra traversal into index batches                                      */
+        uint64_t mesh_rebuilds;
+    } smr_stats;
+
+    int smr_stats_get(smr_stats* out);
+    int smr_stats_reset(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

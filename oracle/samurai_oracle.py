@@ -1,0 +1,854 @@
+"""CPU oracle: a numpy restatement of samurai's per-time-step hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing in the product (`samurai_b200/`) may import
+this module; only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s
+cpu_baseline / `--impl reference` legs do, and only as the checker / baseline.
+
+It is deliberately a DIFFERENT implementation from the product's host code:
+cell sets are sorted arrays of packed integer keys (one key per cell) instead
+of interval lists, so a bug in the product's interval algebra cannot hide
+behind a shared implementation.  Floating-point work is plain numpy fp64
+element-wise arithmetic (no FMA, IEEE round-to-nearest), written in the
+reference's operation order so results are bit-comparable.
+
+Parity pin: `tests/test_oracle_golden.py` checks this oracle against the
+reference's golden HDF5 files (advection_2d, prediction radius 0 and 1, initial
+and final meshes + fields) -- see tests/golden/make_golden.py.
+
+Reference (hpc-maths/samurai v0.33.0, paths relative to include/samurai/):
+  mesh construction      mesh.hpp:326-341,426-439,894-911,1160-1262  mr/mesh.hpp:222-455
+  ghost update           algorithm/update_ghost_mr.hpp:194-237
+  outer ghosts / BC      algorithm/update_outer_ghost.hpp:20-432  bc/apply_field_bc.hpp:14-466
+  projection/prediction  numeric/projection.hpp:22-64  numeric/prediction.hpp:22-361
+  detail / tags          mr/operators.hpp:29-89,139-533  mr/criteria.hpp:19-113  mr/adapt.hpp:148-389
+  mesh from tags         algorithm/graduation.hpp:245-330,573-842
+  field transfer         algorithm/update_fields.hpp:27-54
+  FV operators           stencil_field.hpp:16-243
+Supported scope: non-periodic box domains, scalar fp64 fields, ghost width 1
+(max_stencil_radius = 1, prediction radius 0 or 1), Dirichlet<1>/Neumann<1>
+constant BCs -- exactly what BASELINE.json's configs use.
+"""
+from __future__ import annotations
+
+import itertools
+from dataclasses import dataclass, field as dc_field
+
+import numpy as np
+
+# ----------------------------------------------------------------------------
+# packed cell keys
+# ----------------------------------------------------------------------------
+BITS = 21
+BIAS = 1 << 20
+MASK = (1 << BITS) - 1
+
+KEEP, COARSEN, REFINE = 1, 2, 4  # cell_flag.hpp:11-17
+
+EMPTY = np.zeros(0, dtype=np.int64)
+
+
+def pack(coords: np.ndarray) -> np.ndarray:
+    """coords [N, dim] (x, y[, z]) -> keys sorted by (z, y, x) when sorted."""
+    coords = np.asarray(coords, dtype=np.int64)
+    key = np.zeros(coords.shape[0], dtype=np.int64)
+    for d in range(coords.shape[1]):
+        key |= (coords[:, d] + BIAS) << (BITS * d)
+    return key
+
+
+def unpack(keys: np.ndarray, dim: int) -> np.ndarray:
+    out = np.empty((keys.shape[0], dim), dtype=np.int64)
+    for d in range(dim):
+        out[:, d] = ((keys >> (BITS * d)) & MASK) - BIAS
+    return out
+
+
+def shift_key(direction) -> int:
+    s = 0
+    for d, v in enumerate(direction):
+        s += int(v) << (BITS * d)
+    return s
+
+
+def translate(s: np.ndarray, direction) -> np.ndarray:
+    return s + shift_key(direction)
+
+
+def union(*sets):
+    sets = [s for s in sets if s.size]
+    if not sets:
+        return EMPTY
+    if len(sets) == 1:
+        return sets[0]
+    return np.unique(np.concatenate(sets))
+
+
+def inter(a, b):
+    if a.size == 0 or b.size == 0:
+        return EMPTY
+    return np.intersect1d(a, b, assume_unique=True)
+
+
+def diff(a, b):
+    if a.size == 0 or b.size == 0:
+        return a
+    return np.setdiff1d(a, b, assume_unique=True)
+
+
+def coarsen(s: np.ndarray, shift: int, dim: int) -> np.ndarray:
+    """`.on(level - shift)`: interval >> shift (interval.hpp:227-233)."""
+    if shift == 0 or s.size == 0:
+        return s
+    return np.unique(pack(unpack(s, dim) >> shift))
+
+
+def refine(s: np.ndarray, shift: int, dim: int) -> np.ndarray:
+    """`.on(level + shift)`: every cell -> its 2^(shift*dim) descendants."""
+    if shift == 0 or s.size == 0:
+        return s
+    c = unpack(s, dim) << shift
+    n = 1 << shift
+    parts = []
+    for off in itertools.product(range(n), repeat=dim):
+        parts.append(pack(c + np.array(off, dtype=np.int64)))
+    return np.sort(np.concatenate(parts))
+
+
+def expand(s: np.ndarray, w: int, dim: int) -> np.ndarray:
+    """Box expansion by w cells in every dimension (subset/expansion.hpp)."""
+    if w == 0 or s.size == 0:
+        return s
+    parts = [translate(s, off) for off in itertools.product(range(-w, w + 1), repeat=dim)]
+    return np.unique(np.concatenate(parts))
+
+
+def box_cells(lo, hi) -> np.ndarray:
+    """All cells with lo[d] <= c[d] < hi[d]."""
+    axes = [np.arange(lo[d], hi[d], dtype=np.int64) for d in range(len(lo))]
+    grids = np.meshgrid(*axes, indexing="ij")
+    coords = np.stack([g.ravel() for g in grids], axis=1)
+    return np.sort(pack(coords))
+
+
+def cartesian_directions(dim):
+    """for_each_cartesian_direction order (stencil.hpp:299-335): +e_d, -e_d."""
+    out = []
+    for d in range(dim):
+        for sgn in (1, -1):
+            v = [0] * dim
+            v[d] = sgn
+            out.append(tuple(v))
+    return out
+
+
+def diagonal_directions(dim):
+    """for_each_diagonal_direction (stencil.hpp:337-349): static_nested_loop<dim,-1,2>, x fastest."""
+    out = []
+    for rev in itertools.product((-1, 0, 1), repeat=dim):
+        v = tuple(reversed(rev))  # last dim outermost, x innermost
+        if sum(abs(c) for c in v) > 1:
+            out.append(v)
+    return out
+
+
+# ----------------------------------------------------------------------------
+# mesh
+# ----------------------------------------------------------------------------
+@dataclass
+class MeshConfig:
+    dim: int = 2
+    min_level: int = 4
+    max_level: int = 10
+    pred_radius: int = 1  # mesh_config<dim, prediction_stencil_radius>
+    max_stencil_radius: int = 1
+    graduation_width: int = 1
+    n_cells0: tuple = None  # domain size in level-0 cells per dim (default 1 each)
+    origin: tuple = None
+    scaling: float = 1.0
+
+    def __post_init__(self):
+        if self.n_cells0 is None:
+            self.n_cells0 = (1,) * self.dim
+        if self.origin is None:
+            self.origin = (0.0,) * self.dim
+        assert self.max_stencil_radius == 1, "oracle restates ghost width 1 only"
+        assert self.pred_radius in (0, 1)
+
+    @property
+    def ghost_width(self):
+        return max(self.max_stencil_radius, self.pred_radius)  # mesh_config.hpp:395
+
+    def cell_length(self, level):
+        return self.scaling / (1 << level)  # cell.hpp:16-20
+
+
+class Mesh:
+    """MRMesh restatement: cells / cells_and_ghosts / proj_cells / union / reference."""
+
+    def __init__(self, cfg: MeshConfig, cells: dict):
+        self.cfg = cfg
+        dim = cfg.dim
+        L = cfg.max_level
+        nlev = L + 3
+        self.nlev = nlev
+        self.cells = [EMPTY] * nlev
+        for l, s in cells.items():
+            self.cells[l] = np.asarray(s, dtype=np.int64)
+        self._build()
+
+    # domain pyramid (mesh.hpp:1207-1228): the box at every level 0..max_level, kept implicit
+    def in_domain(self, level, keys):
+        if level > self.cfg.max_level:
+            return np.zeros(keys.size, dtype=bool)
+        c = unpack(keys, self.cfg.dim)
+        ok = np.ones(keys.size, dtype=bool)
+        for d in range(self.cfg.dim):
+            ok &= (c[:, d] >= 0) & (c[:, d] < (self.cfg.n_cells0[d] << level))
+        return ok
+
+    def domain_inter(self, level, s):
+        return s[self.in_domain(level, s)] if s.size else s
+
+    def domain_diff(self, level, s):
+        return s[~self.in_domain(level, s)] if s.size else s
+
+    def expanded_domain_inter(self, level, s, w):
+        """s ∩ expand(domain[level], w)."""
+        if s.size == 0:
+            return s
+        c = unpack(s, self.cfg.dim)
+        ok = np.ones(s.size, dtype=bool)
+        for d in range(self.cfg.dim):
+            ok &= (c[:, d] >= -w) & (c[:, d] < (self.cfg.n_cells0[d] << level) + w)
+        return s[ok]
+
+    def corner_cell(self, level, direction):
+        """Mesh_base::construct_corners (mesh.hpp:914-997) `.on(level)`: the domain's corner cell(s) for a
+        diagonal direction = domain \\ U_{d: dir[d]!=0} translate(domain, -dir[d] e_d), here for a box."""
+        dim = self.cfg.dim
+        axes = []
+        for d in range(dim):
+            n = self.cfg.n_cells0[d] << level
+            if direction[d] > 0:
+                axes.append(np.array([n - 1], dtype=np.int64))
+            elif direction[d] < 0:
+                axes.append(np.array([0], dtype=np.int64))
+            else:
+                axes.append(np.arange(n, dtype=np.int64))
+        grids = np.meshgrid(*axes, indexing="ij")
+        return np.sort(pack(np.stack([g.ravel() for g in grids], axis=1)))
+
+    @staticmethod
+    def uniform(cfg: MeshConfig, level=None):
+        level = cfg.max_level if level is None else level
+        dim = cfg.dim
+        return Mesh(cfg, {level: box_cells([0] * dim, [n << level for n in cfg.n_cells0])})
+
+    def _build(self):
+        cfg, dim, nlev = self.cfg, self.cfg.dim, self.nlev
+        L = cfg.max_level
+        msr, pr = cfg.max_stencil_radius, cfg.pred_radius
+        # construct_union (mesh.hpp:1231-1262)
+        self.union = [EMPTY] * nlev
+        for l in range(L, 0, -1):
+            self.union[l - 1] = coarsen(union(self.cells[l], self.union[l]), 1, dim)
+        # cells_and_ghosts (mr/mesh.hpp:240-253)
+        self.cag = [expand(self.cells[l], msr, dim) for l in range(nlev)]
+        cl = [self.cag[l] for l in range(nlev)]
+        self.proj = [EMPTY] * nlev
+        if cfg.max_level != cfg.min_level:
+            # prediction ghosts one and two levels below (mr/mesh.hpp:329-359)
+            for l in range(nlev):
+                if self.cells[l].size == 0 or l == 0:
+                    continue
+                s1 = self.expanded_domain_inter(l - 1, expand(coarsen(self.cag[l], 1, dim), pr, dim), pr)
+                cl[l - 1] = union(cl[l - 1], s1)
+                if l - 1 > 0:
+                    s2 = expand(coarsen(self.cells[l], 2, dim), pr, dim)
+                    cl[l - 2] = union(cl[l - 2], s2)
+            ref = list(cl)
+            # children of projected ghosts, coarse -> fine cascade (mr/mesh.hpp:415-452);
+            # for_each_level re-evaluates max_level() every iteration and skips empty levels
+            nonempty = [l for l in range(nlev) if ref[l].size]
+            l = nonempty[0] if nonempty else nlev
+            while l < nlev - 1 and l <= max(k for k in range(nlev) if ref[k].size):
+                if ref[l].size:
+                    e = inter(ref[l], self.union[l])
+                    if e.size:
+                        cl[l + 1] = union(cl[l + 1], refine(e, 1, dim))
+                    ref[l + 1] = cl[l + 1]
+                    self.proj[l] = e
+                l += 1
+        self.ref = cl
+        # renumbering (mesh.hpp:894-911, cell_array.hpp:484-493): level asc, then (z, y, x)
+        self.start = np.zeros(nlev + 1, dtype=np.int64)
+        for l in range(nlev):
+            self.start[l + 1] = self.start[l] + self.ref[l].size
+        self.nref = int(self.start[-1])
+
+    # storage offsets ---------------------------------------------------------
+    def index(self, level, keys, strict=True):
+        ref = self.ref[level]
+        pos = np.searchsorted(ref, keys)
+        ok = (pos < ref.size)
+        ok[ok] &= ref[pos[ok]] == keys[ok]
+        if strict:
+            if not ok.all():
+                bad = unpack(np.asarray(keys)[~ok][:5], self.cfg.dim)
+                raise IndexError(f"cells not in reference mesh at level {level}: {bad.tolist()}")
+            return self.start[level] + pos
+        return np.where(ok, self.start[level] + pos, -1)
+
+    def contains(self, level, keys):
+        ref = self.ref[level]
+        pos = np.searchsorted(ref, keys)
+        ok = pos < ref.size
+        ok[ok] &= ref[pos[ok]] == keys[ok]
+        return ok
+
+    def nb_cells(self):
+        return int(sum(c.size for c in self.cells))
+
+    def leaf_levels(self):
+        return [l for l in range(self.nlev) if self.cells[l].size]
+
+    def same_cells(self, other_cells):
+        for l in range(self.nlev):
+            o = other_cells[l] if l < len(other_cells) else EMPTY
+            if self.cells[l].size != o.size or not np.array_equal(self.cells[l], o):
+                return False
+        return True
+
+    def leaf_table(self):
+        """(level, coords[N,dim], storage index) for every leaf, in for_each_cell order."""
+        lv, co, ix = [], [], []
+        for l in self.leaf_levels():
+            k = self.cells[l]
+            lv.append(np.full(k.size, l, dtype=np.int64))
+            co.append(unpack(k, self.cfg.dim))
+            ix.append(self.index(l, k))
+        return np.concatenate(lv), np.concatenate(co), np.concatenate(ix)
+
+    def cell_centers(self, level, keys):
+        c = unpack(keys, self.cfg.dim)
+        h = self.cfg.cell_length(level)
+        return np.array(self.cfg.origin)[None, :] + h * (c + 0.5)  # cell.hpp:131-134
+
+
+# ----------------------------------------------------------------------------
+# boundary conditions
+# ----------------------------------------------------------------------------
+@dataclass
+class Bc:
+    kind: str = "dirichlet"  # or "neumann"
+    value: float = 0.0
+
+
+# ----------------------------------------------------------------------------
+# numerics
+# ----------------------------------------------------------------------------
+def interp_coeffs(radius, sign):
+    """numeric/prediction.hpp:22-40."""
+    if radius == 0:
+        return np.array([1.0])
+    assert radius == 1
+    return np.array([sign / 8.0, 1.0, -sign / 8.0])
+
+
+def _children_offsets(dim):
+    """static_nested_loop<dim-1,0,2> rows x (2i, 2i+1): x fastest, then y, then z."""
+    out = []
+    for rev in itertools.product((0, 1), repeat=dim):
+        out.append(tuple(reversed(rev)))
+    return out
+
+
+def _stencil_offsets(dim, r):
+    """static_nested_loop<dim,-r,r+1>: last dim outermost, x innermost."""
+    out = []
+    for rev in itertools.product(range(-r, r + 1), repeat=dim):
+        out.append(tuple(reversed(rev)))
+    return out
+
+
+def projection(mesh: Mesh, f, coarse_level, coarse_keys):
+    """projection_op_ (numeric/projection.hpp:22-64): sum rows of (f[2i] + f[2i+1]), * 1/2^dim."""
+    dim = mesh.cfg.dim
+    if coarse_keys.size == 0:
+        return
+    c = unpack(coarse_keys, dim)
+    total = np.zeros(coarse_keys.size)
+    rows = [tuple(reversed(r)) for r in itertools.product((0, 1), repeat=dim - 1)] if dim > 1 else [()]
+    for row in rows:
+        k0 = pack(2 * c + np.array((0,) + row, dtype=np.int64))
+        i0 = mesh.index(coarse_level + 1, k0)
+        i1 = mesh.index(coarse_level + 1, k0 + 1)
+        total = total + (f[i0] + f[i1])
+    inv = 1.0 / float(1 << dim)
+    f[mesh.index(coarse_level, coarse_keys)] = total * inv
+
+
+def predict_values(mesh: Mesh, fsrc, src_mesh: Mesh, fine_level, fine_keys):
+    """prediction_op (numeric/prediction.hpp:286-361 and :149-257): value of fine cells from level-1."""
+    dim = mesh.cfg.dim
+    r = mesh.cfg.pred_radius
+    cf = unpack(fine_keys, dim)
+    cc = cf >> 1
+    if r == 0:
+        return fsrc[src_mesh.index(fine_level - 1, pack(cc))].copy()
+    par = cf & 1  # 0 even -> interp_coeffs(+1), 1 odd -> interp_coeffs(-1)
+    cpair = np.stack([interp_coeffs(r, 1.0), interp_coeffs(r, -1.0)])  # [2, 3]
+    val = np.zeros(fine_keys.size)
+    for st in _stencil_offsets(dim, r):
+        src = fsrc[src_mesh.index(fine_level - 1, pack(cc + np.array(st, dtype=np.int64)))]
+        coeff = np.ones(fine_keys.size)
+        for d in range(dim):  # coeff *= c_x, then c_y, then c_z
+            coeff = coeff * cpair[par[:, d], st[d] + r]
+        val = val + src * coeff
+    return val
+
+
+def compute_detail(mesh: Mesh, f, detail, level, coarse_keys):
+    """compute_detail_op (mr/operators.hpp:146-175, 226-358, 360-533)."""
+    dim = mesh.cfg.dim
+    r = mesh.cfg.pred_radius
+    if coarse_keys.size == 0:
+        return
+    c = unpack(coarse_keys, dim)
+    ce, co = interp_coeffs(r, 1.0), interp_coeffs(r, -1.0)
+    cpair = [ce, co]
+    children = _children_offsets(dim)
+    idx_child = [mesh.index(level + 1, pack(2 * c + np.array(ch, dtype=np.int64))) for ch in children]
+    d = [f[i].copy() for i in idx_child]
+    if r == 0:
+        src = f[mesh.index(level, coarse_keys)]
+        for k in range(len(children)):
+            d[k] = d[k] - src
+    else:
+        for st in _stencil_offsets(dim, r):
+            src = f[mesh.index(level, pack(c + np.array(st, dtype=np.int64)))]
+            for k, ch in enumerate(children):
+                coeff = cpair[ch[0]][st[0] + r]
+                for dd in range(1, dim):  # (c_x * c_y) * c_z
+                    coeff = coeff * cpair[ch[dd]][st[dd] + r]
+                d[k] = d[k] - coeff * src
+    for k in range(len(children)):
+        detail[idx_child[k]] = d[k]
+
+
+# ----------------------------------------------------------------------------
+# ghost update
+# ----------------------------------------------------------------------------
+def update_outer_ghosts(mesh: Mesh, f, bc: Bc, level):
+    """algorithm/update_outer_ghost.hpp:338-432 for ghost width 1."""
+    cfg, dim = mesh.cfg, mesh.cfg.dim
+    L, lmin = cfg.max_level, cfg.min_level
+    if dim > 1 and lmin <= level <= L:
+        for direction in diagonal_directions(dim):
+            corner = mesh.corner_cell(level, direction)
+            # update_outer_corners_by_polynomial_extrapolation, stencil size 2:
+            # u[corner + direction] = u[corner]   (bc/polynomial_extrapolation.hpp:63-66)
+            cc = inter(mesh.cells[level], corner)
+            if cc.size:
+                f[mesh.index(level, translate(cc, direction))] = f[mesh.index(level, cc)]
+            # project_corner_below (update_outer_ghost.hpp:267-336)
+            if level > 0:
+                for delta_l in (1, 2):
+                    proj_level = level - delta_l
+                    fine_outer = inter(translate(corner, direction), mesh.ref[level])
+                    ghosts = inter(coarsen(fine_outer, delta_l, dim), mesh.ref[proj_level])
+                    if ghosts.size:
+                        g = unpack(ghosts, dim)
+                        add = np.array([((1 << delta_l) - 1) if direction[d] == -1 else 0 for d in range(dim)], dtype=np.int64)
+                        child = pack((g << delta_l) + add)
+                        ok = mesh.contains(level, child)
+                        if ok.any():
+                            f[mesh.index(proj_level, ghosts[ok])] = f[mesh.index(level, child[ok])]
+                    if proj_level == 0:
+                        break
+    for direction in cartesian_directions(dim):
+        if level < L:
+            _project_bc(mesh, f, level, direction)
+        if level >= lmin:
+            _apply_field_bc(mesh, f, bc, level, direction)
+        if lmin <= level < L:
+            _predict_bc(mesh, f, level + 1, direction)
+
+
+def _project_bc(mesh: Mesh, f, level, direction):
+    """project_bc, layer 1 (update_outer_ghost.hpp:20-152)."""
+    dim = mesh.cfg.dim
+    outside = mesh.domain_diff(level, translate(mesh.union[level], direction))
+    ghosts = inter(outside, mesh.ref[level])
+    if ghosts.size == 0:
+        return
+    gi = mesh.index(level, ghosts)
+    total = np.zeros(ghosts.size)
+    count = np.zeros(ghosts.size, dtype=np.int64)
+    g = unpack(ghosts, dim)
+    for dl in (1, 2):
+        todo = count == 0
+        if not todo.any():
+            break
+        n = 1 << dl
+        # children traversed row by row: (z, y) outer, x inner
+        for rev in itertools.product(range(n), repeat=dim):
+            off = np.array(tuple(reversed(rev)), dtype=np.int64)
+            ck = pack((g[todo] << dl) + off)
+            ok = mesh.contains(level + dl, ck)
+            if ok.any():
+                sel = np.flatnonzero(todo)[ok]
+                total[sel] = total[sel] + f[mesh.index(level + dl, ck[ok])]
+                count[sel] += 1
+    has = count > 0
+    out = np.zeros(ghosts.size)  # field = 0 first (update_outer_ghost.hpp:77)
+    out[has] = total[has] / count[has]
+    f[gi] = out
+
+
+def _bdry_leaves(mesh: Mesh, level, direction):
+    """leaves at `level` whose neighbour in `direction` is outside the domain (boundary.hpp:6-33)."""
+    k = mesh.cells[level]
+    return k[~mesh.in_domain(level, translate(k, direction))] if k.size else k
+
+
+def _apply_field_bc(mesh: Mesh, f, bc: Bc, level, direction):
+    """apply_field_bc (bc/apply_field_bc.hpp:53-101); DirichletImpl<1>, NeumannImpl<1>."""
+    cells = _bdry_leaves(mesh, level, direction)
+    if cells.size == 0:
+        return
+    ci = mesh.index(level, cells)
+    gi = mesh.index(level, translate(cells, direction))
+    if bc.kind == "dirichlet":
+        f[gi] = 2 * bc.value - f[ci]  # bc/dirichlet.hpp:29
+    elif bc.kind == "neumann":
+        dx = mesh.cfg.cell_length(level)
+        f[gi] = dx * bc.value + f[ci]  # bc/neumann.hpp:27-28
+    else:
+        raise ValueError(bc.kind)
+
+
+def _predict_bc(mesh: Mesh, f, pred_level, direction):
+    """predict_bc (update_outer_ghost.hpp:194-262): copy parent BC ghost into its children."""
+    dim = mesh.cfg.dim
+    bc_ghosts = mesh.domain_diff(pred_level - 1, translate(_bdry_leaves(mesh, pred_level - 1, direction), direction))
+    fine = inter(refine(bc_ghosts, 1, dim), mesh.ref[pred_level])
+    if fine.size == 0:
+        return
+    parent = pack(unpack(fine, dim) >> 1)
+    f[mesh.index(pred_level, fine)] = f[mesh.index(pred_level - 1, parent)]
+
+
+def projection_set(mesh: Mesh, level):
+    """cells of proj_cells[level-1] with a child in reference[level] (update_ghost_mr.hpp:219)."""
+    dim = mesh.cfg.dim
+    return inter(coarsen(mesh.ref[level], 1, dim), mesh.proj[level - 1])
+
+
+def prediction_set(mesh: Mesh, level):
+    """update_ghost_mr.hpp:226-228."""
+    dim = mesh.cfg.dim
+    pred_ghosts = diff(mesh.ref[level], union(mesh.cells[level], mesh.proj[level]))
+    e = mesh.domain_inter(level, pred_ghosts)
+    if e.size == 0:
+        return e
+    parent = pack(unpack(e, dim) >> 1)
+    return e[mesh.contains(level - 1, parent)]
+
+
+def update_ghost_mr(mesh: Mesh, f, bc: Bc):
+    """update_ghost_mr_aggregated (algorithm/update_ghost_mr.hpp:194-237), serial, non-periodic."""
+    L = mesh.cfg.max_level
+    for level in range(L, -1, -1):
+        update_outer_ghosts(mesh, f, bc, level)
+        if level > 0:
+            projection(mesh, f, level - 1, projection_set(mesh, level))
+    for level in range(1, L + 1):
+        e = prediction_set(mesh, level)
+        if e.size:
+            f[mesh.index(level, e)] = predict_values(mesh, f, mesh, level, e)
+
+
+# ----------------------------------------------------------------------------
+# MR adaptation
+# ----------------------------------------------------------------------------
+def detail_set(mesh: Mesh, level):
+    """mr/adapt.hpp:312-315."""
+    dim = mesh.cfg.dim
+    below = union(coarsen(mesh.cells[level + 1], 1, dim), coarsen(mesh.cells[level + 2], 2, dim) if level + 2 < mesh.nlev else EMPTY)
+    return inter(mesh.ref[level], below)
+
+
+def tag_set(mesh: Mesh, level):
+    """coarse cells (level-1) having a leaf child at `level` (mr/adapt.hpp:333, 351)."""
+    dim = mesh.cfg.dim
+    return inter(mesh.ref[level - 1], coarsen(mesh.cells[level], 1, dim))
+
+
+def mr_criteria(mesh: Mesh, detail, tag, level, eps, regularity):
+    """mr_criteria_op (mr/criteria.hpp:19-113), fine level = `level`, coarse = level-1."""
+    cfg, dim = mesh.cfg, mesh.cfg.dim
+    coarse = tag_set(mesh, level)
+    if coarse.size == 0:
+        return
+    exponent = dim * (cfg.max_level - level)
+    eps_l = eps / (1 << exponent)  # mr/adapt.hpp:328-329
+    reg = regularity + dim
+    fine_eps = pow(2.0, reg) * eps_l
+    coarse_eps = fine_eps / (1 << dim)
+    c = unpack(coarse, dim)
+    ci = mesh.index(level - 1, coarse)
+    fi = [mesh.index(level, pack(2 * c + np.array(ch, dtype=np.int64))) for ch in _children_offsets(dim)]
+    if level > cfg.min_level:
+        cond = ~(np.abs(detail[ci]) > coarse_eps)
+        for i in fi:
+            cond &= ~(np.abs(detail[i]) > eps_l)
+        for i in fi:
+            tag[i[cond]] = COARSEN
+    if level < cfg.max_level:
+        for i in fi:
+            tag[i] |= (np.abs(detail[i]) > fine_eps).astype(np.uint8) * np.uint8(REFINE)
+
+
+def maximum(mesh: Mesh, tag, level):
+    """maximum_op (mr/operators.hpp:29-89) on parents (level-1) of leaves at `level`."""
+    dim = mesh.cfg.dim
+    coarse = tag_set(mesh, level)
+    if coarse.size == 0:
+        return
+    c = unpack(coarse, dim)
+    ci = mesh.index(level - 1, coarse)
+    fi = [mesh.index(level, pack(2 * c + np.array(ch, dtype=np.int64))) for ch in _children_offsets(dim)]
+    any_keep = np.zeros(coarse.size, dtype=bool)
+    all_coarsen = np.ones(coarse.size, dtype=bool)
+    for i in fi:
+        any_keep |= (tag[i] & KEEP) != 0
+        all_coarsen &= (tag[i] & COARSEN) != 0
+    for i in fi:
+        tag[i[any_keep]] |= KEEP
+    tag[ci[any_keep]] |= KEEP
+    m2 = ~any_keep & all_coarsen
+    tag[ci[m2]] |= KEEP
+    m3 = ~any_keep & ~all_coarsen
+    for i in fi:
+        tag[i[m3]] &= np.uint8(0xFF & ~COARSEN)
+
+
+def update_cell_array_from_tag(mesh: Mesh, tag):
+    """algorithm/graduation.hpp:743-842 (set semantics)."""
+    cfg, dim, nlev = mesh.cfg, mesh.cfg.dim, mesh.nlev
+    add = [[] for _ in range(nlev)]
+    rem = [[] for _ in range(nlev)]
+    for l in mesh.leaf_levels():
+        k = mesh.cells[l]
+        t = tag[mesh.index(l, k)]
+        ref_ = ((t & REFINE) != 0) & (l < cfg.max_level)
+        coa = ~ref_ & ((t & COARSEN) != 0) & ((t & KEEP) == 0) & (l > cfg.min_level)
+        if ref_.any():
+            rem[l].append(k[ref_])
+            add[l + 1].append(refine(k[ref_], 1, dim))
+        if coa.any():
+            rem[l].append(k[coa])
+            c = unpack(k[coa], dim)
+            even = ((c & 1) == 0).all(axis=1)
+            if even.any():
+                add[l - 1].append(np.unique(pack(c[even] >> 1)))
+    new = [EMPTY] * nlev
+    for l in range(cfg.min_level, cfg.max_level + 1):
+        s = union(mesh.cells[l], *add[l])
+        r = union(*rem[l]) if rem[l] else EMPTY
+        new[l] = diff(s, r)
+    return new
+
+
+def make_graduation(cfg: MeshConfig, ca):
+    """make_graduation (algorithm/graduation.hpp:573-726) for max_stencil_radius == 1, serial, non-periodic."""
+    dim = cfg.dim
+    w = cfg.graduation_width
+    nlev = len(ca)
+    ca = list(ca)
+    while True:
+        levels = [l for l in range(nlev) if ca[l].size]
+        if not levels:
+            return ca
+        lo, hi = levels[0], levels[-1]
+        out = [[] for _ in range(nlev)]
+        for fine in range(hi, lo + 1, -1):  # fine_level = max_level ... min_level+2
+            if ca[fine].size == 0:
+                continue
+            proj = coarsen(expand(ca[fine], 2 * w, dim), 2, dim)
+            coarse_level = fine - 2
+            while True:
+                if proj.size:
+                    r = inter(proj, ca[coarse_level])
+                    if r.size:
+                        out[coarse_level].append(r)
+                if coarse_level == lo or proj.size == 0:
+                    break
+                proj = coarsen(proj, 1, dim)
+                coarse_level -= 1
+        if not any(out):
+            return ca
+        rem = [union(*o) if o else EMPTY for o in out]
+        # new_ca[level] = (ca[level] U children(remove[level-1])) \ remove[level]  (graduation.hpp:706-716)
+        new = [diff(union(ca[l], refine(rem[l - 1], 1, dim) if l > 0 and rem[l - 1].size else EMPTY), rem[l]) for l in range(nlev)]
+        changed = any(new[l].size != ca[l].size or not np.array_equal(new[l], ca[l]) for l in range(nlev))
+        ca = new
+        if not changed:
+            return ca
+
+
+def update_fields(old: Mesh, new: Mesh, f):
+    """update_fields (algorithm/update_fields.hpp:27-54,101-127): copy, project, predict onto the new mesh."""
+    cfg, dim = old.cfg, old.cfg.dim
+    g = np.zeros(new.nref)
+    for l in range(cfg.min_level, cfg.max_level + 1):
+        s = inter(old.ref[l], new.cells[l])
+        if s.size:
+            g[new.index(l, s)] = f[old.index(l, s)]
+    for l in range(cfg.min_level + 1, cfg.max_level + 1):
+        sc = inter(coarsen(old.cells[l], 1, dim), new.cells[l - 1])
+        if sc.size:
+            c = unpack(sc, dim)
+            total = np.zeros(sc.size)
+            rows = [tuple(reversed(r)) for r in itertools.product((0, 1), repeat=dim - 1)] if dim > 1 else [()]
+            for row in rows:
+                k0 = pack(2 * c + np.array((0,) + row, dtype=np.int64))
+                total = total + (f[old.index(l, k0)] + f[old.index(l, k0 + 1)])
+            g[new.index(l - 1, sc)] = total * (1.0 / float(1 << dim))
+        # set_refine = (new cells[l] ∩ old cells[l-1]).on(l-1): each coarse cell writes ALL 2^dim children
+        sr = inter(coarsen(new.cells[l], 1, dim), old.cells[l - 1])
+        if sr.size:
+            fine = refine(sr, 1, dim)
+            g[new.index(l, fine)] = predict_values(new, f, old, l, fine)
+    return g
+
+
+@dataclass
+class AdaptStats:
+    iterations: int = 0
+    changed: bool = False
+
+
+def adapt(mesh: Mesh, f, bc: Bc, eps=1e-4, regularity=1.0, trace=None):
+    """Adapt::operator() + harten (mr/adapt.hpp:148-195, 277-389). Returns (mesh, field)."""
+    cfg = mesh.cfg
+    lmin, L = cfg.min_level, cfg.max_level
+    if lmin == L:
+        return mesh, f
+    for ite in range(L - lmin):
+        detail = np.zeros(mesh.nref)
+        tag = np.zeros(mesh.nref, dtype=np.uint8)
+        for l in mesh.leaf_levels():
+            tag[mesh.index(l, mesh.cells[l])] = KEEP
+        update_ghost_mr(mesh, f, bc)
+        for level in range(max(lmin - 1, 0), L - ite):
+            compute_detail(mesh, f, detail, level, detail_set(mesh, level))
+        for level in range(lmin, L - ite + 1):
+            mr_criteria(mesh, detail, tag, level, eps, regularity)
+        for level in range(L, 0, -1):
+            maximum(mesh, tag, level)
+        if trace is not None:
+            trace.append(dict(ite=ite, mesh=mesh, field=f.copy(), detail=detail, tag=tag.copy()))
+        new_ca = update_cell_array_from_tag(mesh, tag)
+        new_ca = make_graduation(cfg, new_ca)
+        if mesh.same_cells(new_ca):
+            break
+        new_mesh = Mesh(cfg, {l: new_ca[l] for l in range(len(new_ca)) if new_ca[l].size})
+        f = update_fields(mesh, new_mesh, f)
+        mesh = new_mesh
+    return mesh, f
+
+
+# ----------------------------------------------------------------------------
+# FV operators (field-expression path)
+# ----------------------------------------------------------------------------
+def _upwind_flux(a, ul, ur):
+    return (0.5 * a) * (ul + ur) + (0.5 * abs(a)) * (ul - ur)  # stencil_field.hpp:92-97
+
+
+def _burgers_flux(a, ul, ur):
+    """upwind_scalar_burgers_op::flux (stencil_field.hpp:193-217)."""
+    out = np.zeros_like(ul)
+    mask1 = (a * ul) < (a * ur)
+    mask2 = (ul * ur) > 0.0
+    mn = np.minimum(np.abs(ul), np.abs(ur))
+    mx = np.maximum(np.abs(ul), np.abs(ur))
+    m = mask1 & mask2
+    out[m] = 0.5 * mn[m] * mn[m]
+    m = ~mask1
+    out[m] = 0.5 * mx[m] * mx[m]
+    return out
+
+
+def fv_step(mesh: Mesh, u, a, dt, scheme="upwind"):
+    """unp1 = u - dt * upwind(a, u) over the leaves (field_base.hpp:230-242, stencil_field.hpp:30-54).
+
+    Non-leaf entries of the result are NaN: the reference leaves them unspecified
+    (`unp1.resize()` + swap), so nothing downstream may depend on them.
+    """
+    dim = mesh.cfg.dim
+    flux = _upwind_flux if scheme == "upwind" else _burgers_flux
+    unp1 = np.full(mesh.nref, np.nan)
+    for l in mesh.leaf_levels():
+        k = mesh.cells[l]
+        ic = mesh.index(l, k)
+        uc = u[ic]
+        dx = mesh.cfg.cell_length(l)
+        acc = None
+        for d in range(dim):
+            e = [0] * dim
+            e[d] = 1
+            um = u[mesh.index(l, translate(k, [-v for v in e]))]
+            up = u[mesh.index(l, translate(k, e))]
+            lo = flux(a[d], um, uc)
+            hi = flux(a[d], uc, up)
+            acc = (-lo + hi) if acc is None else ((acc + -lo) + hi)
+        unp1[ic] = uc - dt * (acc / dx)
+    return unp1
+
+
+# ----------------------------------------------------------------------------
+# demo drivers
+# ----------------------------------------------------------------------------
+def init_disc(mesh: Mesh, center, radius):
+    """advection_2d.cpp:23-45 / advection_3d.cpp:32-45: 1 inside the ball, else 0."""
+    u = np.zeros(mesh.nref)
+    for l in mesh.leaf_levels():
+        k = mesh.cells[l]
+        x = mesh.cell_centers(l, k)
+        r2 = None
+        for d in range(mesh.cfg.dim):
+            t = (x[:, d] - center[d]) * (x[:, d] - center[d])
+            r2 = t if r2 is None else r2 + t
+        u[mesh.index(l, k)] = np.where(r2 <= radius * radius, 1.0, 0.0)
+    return u
+
+
+def run_advection(cfg: MeshConfig, Tf, eps=2e-4, regularity=1.0, a=None, cfl=0.5, center=None, radius=0.2,
+                  max_steps=None, on_step=None):
+    """demos/FiniteVolume/advection_2d.cpp:61-155 (and advection_3d.cpp). Returns dict with init and final state."""
+    dim = cfg.dim
+    a = [1.0] * dim if a is None else list(a)
+    center = [0.3] * dim if center is None else center
+    bc = Bc("dirichlet", 0.0)
+    mesh = Mesh.uniform(cfg)
+    u = init_disc(mesh, center, radius)
+    dt = cfl * cfg.cell_length(cfg.max_level)
+    mesh, u = adapt(mesh, u, bc, eps, regularity)
+    init_state = (mesh, u.copy())
+    t, nt = 0.0, 0
+    while t != Tf:
+        mesh, u = adapt(mesh, u, bc, eps, regularity)
+        t += dt
+        if t > Tf:
+            dt += Tf - t
+            t = Tf
+        update_ghost_mr(mesh, u, bc)
+        u = fv_step(mesh, u, a, dt)
+        nt += 1
+        if on_step is not None:
+            on_step(nt, mesh, u)
+        if max_steps is not None and nt >= max_steps:
+            break
+    return dict(init=init_state, final=(mesh, u), steps=nt)

@@ -1,0 +1,445 @@
+"""samurai_b200 -- Python binding (ctypes) of the C ABI in include/samurai_b200.h.
+
+The names mirror samurai's C++ API for the hot path (MRMesh / make_scalar_field / make_bc / make_MRAdapt /
+update_ghost_mr / upwind), so the parity tests read like the reference's demos (demos/FiniteVolume/advection_2d.cpp).
+There is no CPU fallback: compute calls raise when the CUDA library or a device is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsamurai_b200.so")
+
+CELLS, CELLS_AND_GHOSTS, PROJ_CELLS, UNION_CELLS, REFERENCE = range(5)
+DIRICHLET, NEUMANN = 0, 1
+KEEP, COARSEN, REFINE = 1, 2, 4
+
+
+class SamuraiError(RuntimeError):
+    pass
+
+
+class MeshConfigC(C.Structure):
+    _fields_ = [
+        ("dim", C.c_int32),
+        ("min_level", C.c_int32),
+        ("max_level", C.c_int32),
+        ("pred_radius", C.c_int32),
+        ("max_stencil_radius", C.c_int32),
+        ("graduation_width", C.c_int32),
+        ("n_cells0", C.c_int32 * 3),
+        ("origin", C.c_double * 3),
+        ("scaling_factor", C.c_double),
+    ]
+
+
+class IntervalC(C.Structure):
+    _fields_ = [("y", C.c_int32), ("z", C.c_int32), ("start", C.c_int32), ("end", C.c_int32), ("offset", C.c_int64)]
+
+
+INTERVAL_DTYPE = np.dtype([("y", "<i4"), ("z", "<i4"), ("start", "<i4"), ("end", "<i4"), ("offset", "<i8")])
+
+
+class StatsC(C.Structure):
+    _fields_ = [
+        ("kernel_launches", C.c_uint64),
+        ("h2d_bytes", C.c_uint64),
+        ("d2h_bytes", C.c_uint64),
+        ("host_mesh_seconds", C.c_double),
+        ("host_batch_seconds", C.c_double),
+        ("mesh_rebuilds", C.c_uint64),
+    ]
+
+
+# every symbol include/samurai_b200.h declares: (name, argtypes)
+_u64, _i64, _i32, _dbl, _vp = C.c_uint64, C.c_int64, C.c_int, C.c_double, C.c_void_p
+_P = C.POINTER
+SYMBOLS = {
+    "smr_init": [_i32],
+    "smr_finalize": [],
+    "smr_last_error": [],
+    "smr_device_available": [],
+    "smr_set_stream": [_vp],
+    "smr_synchronize": [],
+    "smr_mesh_create_uniform": [_P(MeshConfigC), _i32, _P(_u64)],
+    "smr_mesh_create_from_intervals": [_P(MeshConfigC), _vp, _vp, _i64, _P(_u64)],
+    "smr_mesh_destroy": [_u64],
+    "smr_mesh_config_get": [_u64, _P(MeshConfigC)],
+    "smr_mesh_nb_cells": [_u64, _i32, _i32, _P(_i64)],
+    "smr_mesh_nb_intervals": [_u64, _i32, _i32, _P(_i64)],
+    "smr_mesh_get_intervals": [_u64, _i32, _i32, _vp],
+    "smr_mesh_generation": [_u64, _P(_u64)],
+    "smr_mesh_get_index": [_u64, _i32, _i32, _i32, _i32, _P(_i64)],
+    "smr_mesh_update_from_tags": [_u64, _vp, _i64, _P(_i32)],
+    "smr_field_create": [_u64, C.c_char_p, _P(_u64)],
+    "smr_field_destroy": [_u64],
+    "smr_field_resize": [_u64],
+    "smr_field_fill": [_u64, _dbl],
+    "smr_field_size": [_u64, _P(_i64)],
+    "smr_field_upload": [_u64, _vp, _i64],
+    "smr_field_download": [_u64, _vp, _i64],
+    "smr_field_swap": [_u64, _u64],
+    "smr_field_set_bc": [_u64, _i32, _dbl],
+    "smr_update_ghost_mr": [_u64],
+    "smr_fv_upwind": [_u64, _u64, _vp, _dbl],
+    "smr_fv_upwind_burgers": [_u64, _u64, _vp, _dbl],
+    "smr_adapt": [_vp, _i32, _dbl, _dbl, _P(_i32)],
+    "smr_adapt_iteration": [_vp, _i32, _dbl, _dbl, _i32, _P(_i32)],
+    "smr_adapt_last_size": [_u64, _P(_i64)],
+    "smr_adapt_last_tags": [_u64, _vp, _i64],
+    "smr_adapt_last_detail": [_u64, _vp, _i64],
+    "smr_stats_get": [_P(StatsC)],
+    "smr_stats_reset": [],
+}
+
+_lib = None
+_initialized = None
+
+
+def load_library():
+    """Load libsamurai_b200.so (built in-tree by __graft_entry__.build()). Fails loudly when it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SamuraiError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` (no CPU fallback exists)")
+    lib = C.CDLL(LIB_PATH)
+    for name, argtypes in SYMBOLS.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = C.c_char_p if name == "smr_last_error" else C.c_int
+    _lib = lib
+    return lib
+
+
+def _check(rc):
+    if rc != 0:
+        msg = load_library().smr_last_error().decode()
+        if rc == 2:
+            raise IndexError(msg)  # std::out_of_range
+        if rc == 1:
+            raise ValueError(msg)  # std::invalid_argument
+        raise SamuraiError(msg)
+
+
+def initialize(device=None):
+    """samurai::initialize (samurai.hpp:22-98). device=None: cuda:0 when visible, otherwise host-only mode."""
+    global _initialized
+    lib = load_library()
+    if device is None:
+        rc = lib.smr_init(0)
+        if rc != 0:
+            _check(lib.smr_init(-1))
+            _initialized = -1
+            return False
+        _initialized = 0
+        return True
+    _check(lib.smr_init(device))
+    _initialized = device
+    return device >= 0
+
+
+def finalize():
+    _check(load_library().smr_finalize())
+
+
+def device_available():
+    return bool(load_library().smr_device_available())
+
+
+def synchronize():
+    _check(load_library().smr_synchronize())
+
+
+def set_stream(ptr):
+    _check(load_library().smr_set_stream(C.c_void_p(ptr)))
+
+
+def stats(reset=False):
+    s = StatsC()
+    load_library().smr_stats_get(C.byref(s))
+    if reset:
+        load_library().smr_stats_reset()
+    return {k: getattr(s, k) for k, _ in StatsC._fields_}
+
+
+class mesh_config:
+    """samurai::mesh_config<dim, prediction_stencil_radius> fluent builder (mesh_config.hpp:20-432)."""
+
+    def __init__(self, dim, prediction_stencil_radius=1):
+        self.dim = dim
+        self.pred_radius = prediction_stencil_radius
+        self._min_level = 0
+        self._max_level = 6
+        self._max_stencil_radius = 1
+        self._graduation_width = 1
+        self._disable_minimal_ghost_width = False
+
+    def min_level(self, v):
+        self._min_level = v
+        return self
+
+    def max_level(self, v):
+        self._max_level = v
+        return self
+
+    def max_stencil_size(self, size):
+        self._max_stencil_radius = size // 2 + (size % 2)
+        return self
+
+    def max_stencil_radius(self, r):
+        self._max_stencil_radius = r
+        return self
+
+    def graduation_width(self, w):
+        self._graduation_width = w
+        return self
+
+    def disable_minimal_ghost_width(self):
+        self._disable_minimal_ghost_width = True
+        return self
+
+    def to_c(self, box_min, box_max):
+        msr = self._max_stencil_radius
+        if not self._disable_minimal_ghost_width:
+            msr = max(msr, 2)  # mesh_config.hpp:388-393
+        c = MeshConfigC()
+        c.dim, c.min_level, c.max_level = self.dim, self._min_level, self._max_level
+        c.pred_radius, c.max_stencil_radius, c.graduation_width = self.pred_radius, msr, self._graduation_width
+        lengths = [float(box_max[d]) - float(box_min[d]) for d in range(self.dim)]
+        # approximate_box (box.hpp:280-360) for boxes whose lengths are integer multiples of the smallest one
+        scaling = min(lengths)
+        for d in range(3):
+            if d < self.dim:
+                n = lengths[d] / scaling
+                if abs(n - round(n)) > 1e-12:
+                    raise ValueError("box lengths must be integer multiples of the smallest length")
+                c.n_cells0[d] = int(round(n))
+                c.origin[d] = float(box_min[d])
+            else:
+                c.n_cells0[d] = 1
+                c.origin[d] = 0.0
+        c.scaling_factor = scaling
+        return c
+
+
+class MRMesh:
+    """samurai::MRMesh (mr/mesh.hpp:74-122); make_mesh(box, cfg) starts uniform at max_level (mr/mesh.hpp:510-518)."""
+
+    def __init__(self, handle, cfg_c):
+        self._h = handle
+        self.cfg = cfg_c
+
+    @staticmethod
+    def make_mesh(box_min, box_max, config: mesh_config, start_level=None):
+        lib = load_library()
+        c = config.to_c(box_min, box_max)
+        h = C.c_uint64()
+        _check(lib.smr_mesh_create_uniform(C.byref(c), c.max_level if start_level is None else start_level, C.byref(h)))
+        return MRMesh(h.value, c)
+
+    @staticmethod
+    def from_intervals(box_min, box_max, config: mesh_config, levels, intervals):
+        lib = load_library()
+        c = config.to_c(box_min, box_max)
+        levels = np.ascontiguousarray(levels, dtype=np.int32)
+        intervals = np.ascontiguousarray(intervals, dtype=INTERVAL_DTYPE)
+        h = C.c_uint64()
+        _check(lib.smr_mesh_create_from_intervals(C.byref(c), levels.ctypes.data, intervals.ctypes.data, len(levels), C.byref(h)))
+        return MRMesh(h.value, c)
+
+    @property
+    def dim(self):
+        return self.cfg.dim
+
+    def min_level(self):
+        return self.cfg.min_level
+
+    def max_level(self):
+        return self.cfg.max_level
+
+    def cell_length(self, level):
+        return self.cfg.scaling_factor / (1 << level)
+
+    def min_cell_length(self):
+        return self.cell_length(self.cfg.max_level)
+
+    def nb_cells(self, mesh_id=CELLS, level=-1):
+        out = C.c_int64()
+        _check(load_library().smr_mesh_nb_cells(self._h, mesh_id, level, C.byref(out)))
+        return out.value
+
+    def generation(self):
+        out = C.c_uint64()
+        _check(load_library().smr_mesh_generation(self._h, C.byref(out)))
+        return out.value
+
+    def intervals(self, mesh_id, level):
+        lib = load_library()
+        n = C.c_int64()
+        _check(lib.smr_mesh_nb_intervals(self._h, mesh_id, level, C.byref(n)))
+        out = np.zeros(n.value, dtype=INTERVAL_DTYPE)
+        if n.value:
+            _check(lib.smr_mesh_get_intervals(self._h, mesh_id, level, out.ctypes.data))
+        return out
+
+    def get_index(self, level, i, j=0, k=0):
+        out = C.c_int64()
+        _check(load_library().smr_mesh_get_index(self._h, level, i, j, k, C.byref(out)))
+        return out.value
+
+    def update_from_tags(self, tags):
+        tags = np.ascontiguousarray(tags, dtype=np.uint8)
+        unchanged = C.c_int()
+        _check(load_library().smr_mesh_update_from_tags(self._h, tags.ctypes.data, tags.size, C.byref(unchanged)))
+        return bool(unchanged.value)
+
+    def cell_table(self, mesh_id=CELLS):
+        """(level, coords[N,dim], storage offset) per cell in for_each_cell order."""
+        lv, co, off = [], [], []
+        for level in range(self.cfg.max_level + 3):
+            iv = self.intervals(mesh_id, level)
+            if iv.size == 0:
+                continue
+            n = (iv["end"] - iv["start"]).astype(np.int64)
+            tot = int(n.sum())
+            rep = np.repeat(np.arange(iv.size), n)
+            k = np.arange(tot) - np.repeat(np.cumsum(n) - n, n)
+            x = iv["start"][rep] + k
+            cols = [x, iv["y"][rep], iv["z"][rep]][: self.cfg.dim]
+            co.append(np.stack(cols, axis=1).astype(np.int64))
+            off.append(iv["offset"][rep] + k)
+            lv.append(np.full(tot, level, dtype=np.int64))
+        if not lv:
+            return np.zeros(0, np.int64), np.zeros((0, self.cfg.dim), np.int64), np.zeros(0, np.int64)
+        return np.concatenate(lv), np.concatenate(co), np.concatenate(off)
+
+    def destroy(self):
+        if self._h:
+            _check(load_library().smr_mesh_destroy(self._h))
+            self._h = 0
+
+
+class ScalarField:
+    """samurai::ScalarField<mesh_t, double> (field/scalar_field.hpp), device resident."""
+
+    def __init__(self, name, mesh: MRMesh):
+        h = C.c_uint64()
+        _check(load_library().smr_field_create(mesh._h, name.encode(), C.byref(h)))
+        self._h = h.value
+        self.name = name
+        self.mesh = mesh
+
+    def size(self):
+        out = C.c_int64()
+        _check(load_library().smr_field_size(self._h, C.byref(out)))
+        return out.value
+
+    def resize(self):
+        _check(load_library().smr_field_resize(self._h))
+
+    def fill(self, v):
+        _check(load_library().smr_field_fill(self._h, float(v)))
+
+    def upload(self, host):
+        host = np.ascontiguousarray(host, dtype=np.float64)
+        _check(load_library().smr_field_upload(self._h, host.ctypes.data, host.size))
+
+    def download(self, out=None):
+        n = self.size()
+        if out is None:
+            out = np.empty(n, dtype=np.float64)
+        _check(load_library().smr_field_download(self._h, out.ctypes.data, n))
+        return out
+
+    def destroy(self):
+        if self._h:
+            _check(load_library().smr_field_destroy(self._h))
+            self._h = 0
+
+
+def make_scalar_field(name, mesh):
+    return ScalarField(name, mesh)
+
+
+def make_bc(field: ScalarField, kind, value):
+    """samurai::make_bc<Dirichlet<1>>(u, v) / make_bc<Neumann<1>>(u, v) (bc/bc.hpp:751-815)."""
+    _check(load_library().smr_field_set_bc(field._h, kind, float(value)))
+
+
+def swap(a: ScalarField, b: ScalarField):
+    """std::swap(u.array(), unp1.array())."""
+    _check(load_library().smr_field_swap(a._h, b._h))
+
+
+def update_ghost_mr(field: ScalarField):
+    _check(load_library().smr_update_ghost_mr(field._h))
+
+
+def upwind_step(unp1: ScalarField, u: ScalarField, a, dt):
+    """unp1 = u - dt * samurai::upwind(a, u)."""
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    _check(load_library().smr_fv_upwind(unp1._h, u._h, a.ctypes.data, float(dt)))
+
+
+def upwind_scalar_burgers_step(unp1: ScalarField, u: ScalarField, k, dt):
+    """unp1 = u - dt * samurai::upwind_scalar_burgers(k, u)."""
+    k = np.ascontiguousarray(k, dtype=np.float64)
+    _check(load_library().smr_fv_upwind_burgers(unp1._h, u._h, k.ctypes.data, float(dt)))
+
+
+class mra_config:
+    """samurai::mra_config (mr/config.hpp:10-68)."""
+
+    def __init__(self):
+        self._eps, self._reg = 1e-4, 1.0
+
+    def epsilon(self, v):
+        self._eps = v
+        return self
+
+    def regularity(self, v):
+        self._reg = v
+        return self
+
+
+class MRAdapt:
+    """samurai::make_MRAdapt(fields...) (mr/adapt.hpp:391-397)."""
+
+    def __init__(self, *fields):
+        self.fields = fields
+        self._arr = (C.c_uint64 * len(fields))(*[f._h for f in fields])
+
+    def __call__(self, cfg: mra_config):
+        n = C.c_int()
+        _check(load_library().smr_adapt(self._arr, len(self.fields), cfg._eps, cfg._reg, C.byref(n)))
+        return n.value
+
+    def iteration(self, cfg: mra_config, ite):
+        unchanged = C.c_int()
+        _check(load_library().smr_adapt_iteration(self._arr, len(self.fields), cfg._eps, cfg._reg, ite, C.byref(unchanged)))
+        return bool(unchanged.value)
+
+    def last_tags(self):
+        mesh = self.fields[0].mesh
+        n = C.c_int64()
+        _check(load_library().smr_adapt_last_size(mesh._h, C.byref(n)))
+        out = np.empty(n.value, dtype=np.uint8)
+        _check(load_library().smr_adapt_last_tags(mesh._h, out.ctypes.data, out.size))
+        return out
+
+    def last_detail(self):
+        mesh = self.fields[0].mesh
+        n = C.c_int64()
+        _check(load_library().smr_adapt_last_size(mesh._h, C.byref(n)))
+        out = np.empty(n.value * len(self.fields), dtype=np.float64)
+        _check(load_library().smr_adapt_last_detail(mesh._h, out.ctypes.data, out.size))
+        return out
+
+
+def make_MRAdapt(*fields):
+    return MRAdapt(*fields)

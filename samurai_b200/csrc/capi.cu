@@ -1,0 +1,1149 @@
+// C ABI of samurai_b200 (include/samurai_b200.h): host mesh/plan management + kernel launches on one CUDA stream.
+// No CPU fallback: every compute entry point requires a device and fails loudly otherwise.
+#include "../../include/samurai_b200.h"
+#include "batches.hpp"
+#include "kernels.cuh"
+
+#include <chrono>
+#include <cmath>
+#include <memory>
+#include <string>
+#include <unordered_map>
+
+namespace smr
+{
+    struct CudaError : std::runtime_error
+    {
+        using std::runtime_error::runtime_error;
+    };
+
+#define SMR_CUDA(call)                                                                                                    \
+    do                                                                                                                    \
+    {                                                                                                                     \
+        cudaError_t e_ = (call);                                                                                          \
+        if (e_ != cudaSuccess)                                                                                            \
+        {                                                                                                                 \
+            throw CudaError(std::string(#call) + ": " + cudaGetErrorString(e_));                                         \
+        }                                                                                                                 \
+    } while (0)
+
+    struct DevBuf
+    {
+        void* p    = nullptr;
+        size_t cap = 0;
+
+        void ensure(size_t bytes)
+        {
+            if (bytes > cap)
+            {
+                release();
+                size_t want = bytes + bytes / 4 + 4096;
+                SMR_CUDA(cudaMalloc(&p, want));
+                cap = want;
+            }
+        }
+
+        void release()
+        {
+            if (p)
+            {
+                cudaFree(p);
+            }
+            p   = nullptr;
+            cap = 0;
+        }
+
+        ~DevBuf()
+        {
+            release();
+        }
+
+        DevBuf()                         = default;
+        DevBuf(const DevBuf&)            = delete;
+        DevBuf& operator=(const DevBuf&) = delete;
+
+        void swap(DevBuf& o)
+        {
+            std::swap(p, o.p);
+            std::swap(cap, o.cap);
+        }
+    };
+
+    struct PinnedBuf
+    {
+        void* p    = nullptr;
+        size_t cap = 0;
+
+        void ensure(size_t bytes)
+        {
+            if (bytes > cap)
+            {
+                if (p)
+                {
+                    cudaFreeHost(p);
+                }
+                size_t want = bytes + bytes / 4 + 4096;
+                SMR_CUDA(cudaHostAlloc(&p, want, cudaHostAllocDefault));
+                cap = want;
+            }
+        }
+
+        ~PinnedBuf()
+        {
+            if (p)
+            {
+                cudaFreeHost(p);
+            }
+        }
+    };
+
+    struct FieldObj;
+
+    struct MeshObj
+    {
+        Mesh mesh;
+        MeshPlan plan;
+        bool plan_ready = false;
+        DevBuf d_arena;
+        PinnedBuf h_arena;
+        DevBuf d_detail, d_tag;
+        PinnedBuf h_tag;
+        int64_t last_size   = 0;
+        int last_ncomp      = 0;
+        std::vector<FieldObj*> fields;
+    };
+
+    struct FieldObj
+    {
+        MeshObj* mesh = nullptr;
+        std::string name;
+        DevBuf data;
+        int64_t n    = 0;
+        int bc_type  = -1;
+        double bc_value = 0;
+    };
+
+    struct Ctx
+    {
+        bool device         = false;
+        int dev             = -1;
+        cudaStream_t stream = nullptr;
+        std::string err;
+        smr_stats stats{};
+        uint64_t next_id = 1;
+        std::unordered_map<uint64_t, std::unique_ptr<MeshObj>> meshes;
+        std::unordered_map<uint64_t, std::unique_ptr<FieldObj>> fields;
+    };
+
+    static Ctx g;
+
+    static double now()
+    {
+        return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    }
+
+    static void require_device()
+    {
+        if (!g.device)
+        {
+            throw CudaError("no CUDA device: samurai_b200 has no CPU fallback for compute entry points (call smr_init(device >= 0))");
+        }
+    }
+
+    static MeshObj& get_mesh(smr_mesh_t h)
+    {
+        auto it = g.meshes.find(h);
+        if (it == g.meshes.end())
+        {
+            throw std::invalid_argument("invalid mesh handle");
+        }
+        return *it->second;
+    }
+
+    static FieldObj& get_field(smr_field_t h)
+    {
+        auto it = g.fields.find(h);
+        if (it == g.fields.end())
+        {
+            throw std::invalid_argument("invalid field handle");
+        }
+        return *it->second;
+    }
+
+    static void config_to_mesh_cfg(const smr_mesh_config* c, MeshConfig& out)
+    {
+        if (!c)
+        {
+            throw std::invalid_argument("null mesh config");
+        }
+        if (c->dim < 1 || c->dim > 3)
+        {
+            throw std::invalid_argument("dim must be 1, 2 or 3");
+        }
+        if (c->max_level < c->min_level)
+        {
+            throw std::invalid_argument("Max level must be greater than min level."); // mesh_config.hpp:383-386
+        }
+        if (c->max_level + 3 > SMR_MAX_LEVELS)
+        {
+            throw std::invalid_argument("max_level too large (max_refinement_level is 20, samurai_config.hpp:50)");
+        }
+        if (c->max_stencil_radius != 1)
+        {
+            throw std::invalid_argument("only max_stencil_radius == 1 (ghost width 1) is implemented");
+        }
+        if (c->pred_radius < 0 || c->pred_radius > 1)
+        {
+            throw std::invalid_argument("prediction_stencil_radius must be 0 or 1 (update_outer_ghost.hpp:341)");
+        }
+        out.dim                = c->dim;
+        out.min_level          = c->min_level;
+        out.max_level          = c->max_level;
+        out.pred_radius        = c->pred_radius;
+        out.max_stencil_radius = c->max_stencil_radius;
+        out.graduation_width   = c->graduation_width;
+        for (int d = 0; d < 3; ++d)
+        {
+            out.n0[d]     = d < c->dim ? c->n_cells0[d] : 1;
+            out.origin[d] = d < c->dim ? c->origin[d] : 0.0;
+            if (out.n0[d] < 1)
+            {
+                throw std::invalid_argument("n_cells0 must be >= 1");
+            }
+        }
+        out.scaling = c->scaling_factor;
+    }
+
+    // ---------------------------------------------------------------------------------------------------------
+    // plan upload and launches
+    // ---------------------------------------------------------------------------------------------------------
+    static void upload_arena(const Arena& a, DevBuf& d, PinnedBuf& h)
+    {
+        if (a.bytes.empty())
+        {
+            return;
+        }
+        d.ensure(a.bytes.size());
+        h.ensure(a.bytes.size());
+        std::memcpy(h.p, a.bytes.data(), a.bytes.size());
+        SMR_CUDA(cudaMemcpyAsync(d.p, h.p, a.bytes.size(), cudaMemcpyHostToDevice, g.stream));
+        g.stats.h2d_bytes += a.bytes.size();
+    }
+
+    static void ensure_plan(MeshObj& mo)
+    {
+        if (mo.plan_ready)
+        {
+            return;
+        }
+        const double t0 = now();
+        build_plan(mo.mesh, mo.plan);
+        g.stats.host_batch_seconds += now() - t0;
+        // the previous arena may still be in use by queued kernels: stream-ordered, so a sync is needed before reuse
+        SMR_CUDA(cudaStreamSynchronize(g.stream));
+        upload_arena(mo.plan.arena, mo.d_arena, mo.h_arena);
+        mo.plan_ready = true;
+    }
+
+    template <class Item, class Op>
+    static void launch(const void* arena, const Batch& b, const Op& op)
+    {
+        if (b.empty())
+        {
+            return;
+        }
+        const char* base = static_cast<const char*>(arena);
+        BatchView<Item> v{reinterpret_cast<const Item*>(base + b.items),
+                          reinterpret_cast<const int64_t*>(base + b.prefix),
+                          reinterpret_cast<const int32_t*>(base + b.cta_first),
+                          b.n_cells};
+        batch_kernel<Item, Op><<<b.n_ctas, SMR_CTA_THREADS, 0, g.stream>>>(v, op);
+        SMR_CUDA(cudaGetLastError());
+        ++g.stats.kernel_launches;
+    }
+
+    static void launch_bc(const void* arena, const Batch& b, double* f, int bc_type, double bc_value)
+    {
+        if (b.empty())
+        {
+            return;
+        }
+        const char* base = static_cast<const char*>(arena);
+        bc_kernel<<<b.n_ctas, SMR_CTA_THREADS, 0, g.stream>>>(reinterpret_cast<const smr_item_bc*>(base + b.items),
+                                                              reinterpret_cast<const int64_t*>(base + b.aux),
+                                                              b.n_items,
+                                                              f,
+                                                              bc_type,
+                                                              bc_value);
+        SMR_CUDA(cudaGetLastError());
+        ++g.stats.kernel_launches;
+    }
+
+    template <template <int> class OpT, class Item, class... Args>
+    static void launch_dim(int dim, const void* arena, const Batch& b, Args... args)
+    {
+        switch (dim)
+        {
+            case 1:
+                launch<Item>(arena, b, OpT<1>{args...});
+                break;
+            case 2:
+                launch<Item>(arena, b, OpT<2>{args...});
+                break;
+            default:
+                launch<Item>(arena, b, OpT<3>{args...});
+                break;
+        }
+    }
+
+    template <int D>
+    using PredOp0 = PredOp<D, 0>;
+    template <int D>
+    using PredOp1 = PredOp<D, 1>;
+    template <int D>
+    using DetailOp0 = DetailOp<D, 0>;
+    template <int D>
+    using DetailOp1 = DetailOp<D, 1>;
+    template <int D>
+    using UpwindOp = FvOp<D, false>;
+    template <int D>
+    using BurgersOp = FvOp<D, true>;
+
+    static void launch_pred(int dim, int radius, const void* arena, const Batch& b, const double* src, double* dst)
+    {
+        if (radius == 0)
+        {
+            launch_dim<PredOp0, smr_item_pred>(dim, arena, b, src, dst);
+        }
+        else
+        {
+            launch_dim<PredOp1, smr_item_pred>(dim, arena, b, src, dst);
+        }
+    }
+
+    static void check_field_ready(FieldObj& f)
+    {
+        if (f.n != f.mesh->mesh.nref || f.data.p == nullptr)
+        {
+            throw std::invalid_argument("field '" + f.name + "' is not sized for its mesh: call smr_field_resize() after the mesh changed");
+        }
+    }
+
+    static void do_update_ghost(FieldObj& f)
+    {
+        MeshObj& mo = *f.mesh;
+        check_field_ready(f);
+        if (f.bc_type < 0)
+        {
+            throw std::invalid_argument("field '" + f.name + "' has no boundary condition attached (make_bc)");
+        }
+        ensure_plan(mo);
+        const MeshConfig& cfg = mo.mesh.cfg;
+        double* u             = static_cast<double*>(f.data.p);
+        const void* arena     = mo.d_arena.p;
+        for (int level = cfg.max_level; level >= 0; --level)
+        {
+            const GhostPhase& ph = mo.plan.down[level];
+            launch_bc(arena, ph.bc1, u, f.bc_type, f.bc_value);
+            launch_bc(arena, ph.bc2, u, f.bc_type, f.bc_value);
+            launch_dim<ProjOp, smr_item_proj>(cfg.dim, arena, ph.proj, static_cast<const double*>(u), u);
+        }
+        for (int level = 1; level <= cfg.max_level; ++level)
+        {
+            launch_pred(cfg.dim, cfg.pred_radius, arena, mo.plan.pred[level], u, u);
+        }
+    }
+
+    static void do_fv(FieldObj& out, FieldObj& in, const double* a, double dt, bool burgers)
+    {
+        require_device();
+        if (out.mesh != in.mesh)
+        {
+            throw std::invalid_argument("fields live on different meshes");
+        }
+        if (&out == &in)
+        {
+            throw std::invalid_argument("output field must differ from input field");
+        }
+        MeshObj& mo = *in.mesh;
+        check_field_ready(in);
+        check_field_ready(out);
+        ensure_plan(mo);
+        const MeshConfig& cfg = mo.mesh.cfg;
+        if (burgers && cfg.dim != 2)
+        {
+            throw std::invalid_argument("upwind_scalar_burgers is only defined in 2D (stencil_field.hpp:219-243)");
+        }
+        FvParams p;
+        for (int d = 0; d < 3; ++d)
+        {
+            const double ad = d < cfg.dim ? a[d] : 0.0;
+            p.a[d]          = ad;
+            p.half_a[d]     = .5 * ad;
+            p.half_abs_a[d] = .5 * std::abs(ad);
+        }
+        p.dt = dt;
+        for (int l = 0; l < SMR_MAX_LEVELS; ++l)
+        {
+            p.dx[l] = cfg.cell_length(l);
+        }
+        const double* u = static_cast<const double*>(in.data.p);
+        double* o       = static_cast<double*>(out.data.p);
+        if (burgers)
+        {
+            launch_dim<BurgersOp, smr_item_fv>(cfg.dim, mo.d_arena.p, mo.plan.fv, u, o, p);
+        }
+        else
+        {
+            launch_dim<UpwindOp, smr_item_fv>(cfg.dim, mo.d_arena.p, mo.plan.fv, u, o, p);
+        }
+    }
+
+    // one harten iteration; returns true when the mesh is unchanged
+    static bool do_harten(std::vector<FieldObj*>& fields, double eps, double regularity, int ite)
+    {
+        require_device();
+        MeshObj& mo           = *fields[0]->mesh;
+        const MeshConfig& cfg = mo.mesh.cfg;
+        const int dim = cfg.dim, L = cfg.max_level, lmin = cfg.min_level;
+        const int ncomp = static_cast<int>(fields.size());
+        for (auto* f : fields)
+        {
+            if (f->mesh != &mo)
+            {
+                throw std::invalid_argument("all adapted fields must live on the same mesh");
+            }
+            check_field_ready(*f);
+        }
+        ensure_plan(mo);
+        const int64_t n = mo.mesh.nref;
+        mo.d_detail.ensure(static_cast<size_t>(n) * sizeof(double) * ncomp);
+        mo.d_tag.ensure(static_cast<size_t>(n));
+        SMR_CUDA(cudaMemsetAsync(mo.d_detail.p, 0, static_cast<size_t>(n) * sizeof(double) * ncomp, g.stream));
+        SMR_CUDA(cudaMemsetAsync(mo.d_tag.p, 0, static_cast<size_t>(n), g.stream));
+        uint8_t* tag      = static_cast<uint8_t*>(mo.d_tag.p);
+        double* detail    = static_cast<double*>(mo.d_detail.p);
+        const void* arena = mo.d_arena.p;
+        launch<smr_item_fv>(arena, mo.plan.fv, KeepLeavesOp{tag});
+        for (auto* f : fields)
+        {
+            do_update_ghost(*f);
+        }
+        for (int level = std::max(lmin - 1, 0); level < L - ite; ++level)
+        {
+            for (int c = 0; c < ncomp; ++c)
+            {
+                const double* u = static_cast<const double*>(fields[c]->data.p);
+                if (cfg.pred_radius == 0)
+                {
+                    launch_dim<DetailOp0, smr_item_detail>(dim, arena, mo.plan.detail[level], u, detail + c * n);
+                }
+                else
+                {
+                    launch_dim<DetailOp1, smr_item_detail>(dim, arena, mo.plan.detail[level], u, detail + c * n);
+                }
+            }
+        }
+        TagParams tp;
+        tp.min_level = lmin;
+        tp.max_level = L;
+        for (int l = 0; l < SMR_MAX_LEVELS; ++l)
+        {
+            const int exponent = dim * (L - l);
+            if (l > L || exponent >= 31)
+            {
+                tp.eps[l] = tp.fine_eps[l] = tp.coarse_eps[l] = 0;
+                continue;
+            }
+            const double eps_l = eps / (1 << exponent);          // mr/adapt.hpp:328-329
+            const double reg   = regularity + dim;               // mr/adapt.hpp:331
+            tp.eps[l]          = eps_l;
+            tp.fine_eps[l]     = std::pow(2.0, reg) * eps_l;     // mr/criteria.hpp:31
+            tp.coarse_eps[l]   = tp.fine_eps[l] / (1 << dim);    // mr/criteria.hpp:32
+        }
+        if (dim * (L - lmin) >= 31)
+        {
+            throw std::invalid_argument("dim*(max_level-min_level) >= 31 overflows the reference's `1 << exponent` (mr/adapt.hpp:328)");
+        }
+        for (int level = std::max(lmin, 1); level <= L - ite; ++level)
+        {
+            switch (dim)
+            {
+                case 1:
+                    launch<smr_item_tag>(arena, mo.plan.tag[level], CriteriaOp<1>{detail, tag, tp, ncomp, n});
+                    break;
+                case 2:
+                    launch<smr_item_tag>(arena, mo.plan.tag[level], CriteriaOp<2>{detail, tag, tp, ncomp, n});
+                    break;
+                default:
+                    launch<smr_item_tag>(arena, mo.plan.tag[level], CriteriaOp<3>{detail, tag, tp, ncomp, n});
+                    break;
+            }
+        }
+        for (int level = L; level >= 1; --level)
+        {
+            launch_dim<MaximumOp, smr_item_tag>(dim, arena, mo.plan.tag[level], tag);
+        }
+        mo.h_tag.ensure(static_cast<size_t>(n));
+        SMR_CUDA(cudaMemcpyAsync(mo.h_tag.p, tag, static_cast<size_t>(n), cudaMemcpyDeviceToHost, g.stream));
+        SMR_CUDA(cudaStreamSynchronize(g.stream));
+        g.stats.d2h_bytes += static_cast<uint64_t>(n);
+        mo.last_size  = n;
+        mo.last_ncomp = ncomp;
+
+        // host: new leaves from tags, graduation, fixed-point test (mr/adapt.hpp:360-379)
+        double t0    = now();
+        CellArray ca = cells_from_tags(mo.mesh, static_cast<const uint8_t*>(mo.h_tag.p));
+        make_graduation(cfg, ca);
+        const bool same = same_cells(ca, mo.mesh.cells);
+        if (same)
+        {
+            g.stats.host_mesh_seconds += now() - t0;
+            return true;
+        }
+        auto new_mesh = std::make_unique<Mesh>();
+        new_mesh->generation = mo.mesh.generation;
+        new_mesh->init_from_cells(cfg, std::move(ca));
+        g.stats.host_mesh_seconds += now() - t0;
+        ++g.stats.mesh_rebuilds;
+
+        // update_fields (algorithm/update_fields.hpp:27-54,101-127)
+        t0 = now();
+        TransferPlan tpn;
+        build_transfer(mo.mesh, *new_mesh, tpn);
+        g.stats.host_batch_seconds += now() - t0;
+        DevBuf d_tr;
+        PinnedBuf h_tr;
+        upload_arena(tpn.arena, d_tr, h_tr);
+        const int64_t nn = new_mesh->nref;
+        std::vector<std::unique_ptr<DevBuf>> fresh;
+        for (auto* f : fields)
+        {
+            auto nb = std::make_unique<DevBuf>();
+            nb->ensure(static_cast<size_t>(nn) * sizeof(double));
+            SMR_CUDA(cudaMemsetAsync(nb->p, 0, static_cast<size_t>(nn) * sizeof(double), g.stream));
+            const double* src = static_cast<const double*>(f->data.p);
+            double* dst       = static_cast<double*>(nb->p);
+            launch<smr_item_copy>(d_tr.p, tpn.copy, CopyOp{src, dst});
+            launch_dim<ProjOp, smr_item_proj>(dim, d_tr.p, tpn.proj, src, dst);
+            launch_pred(dim, cfg.pred_radius, d_tr.p, tpn.pred, src, dst);
+            fresh.push_back(std::move(nb));
+        }
+        SMR_CUDA(cudaStreamSynchronize(g.stream)); // transfer arena and old buffers are released below
+        for (size_t i = 0; i < fields.size(); ++i)
+        {
+            fields[i]->data.swap(*fresh[i]);
+            fields[i]->n = nn;
+        }
+        mo.mesh       = std::move(*new_mesh);
+        mo.plan_ready = false;
+        return false;
+    }
+
+    template <class F>
+    static int guarded(F&& f)
+    {
+        try
+        {
+            f();
+            return SMR_OK;
+        }
+        catch (const std::out_of_range& e)
+        {
+            g.err = e.what();
+            return SMR_ERR_OUT_OF_RANGE;
+        }
+        catch (const std::invalid_argument& e)
+        {
+            g.err = e.what();
+            return SMR_ERR_INVALID;
+        }
+        catch (const CudaError& e)
+        {
+            g.err = e.what();
+            return SMR_ERR_CUDA;
+        }
+        catch (const std::exception& e)
+        {
+            g.err = e.what();
+            return SMR_ERR_INTERNAL;
+        }
+    }
+} // namespace smr
+
+using namespace smr;
+
+extern "C"
+{
+    int smr_init(int device)
+    {
+        return guarded(
+            [&]
+            {
+                if (device < 0)
+                {
+                    g.device = false;
+                    return;
+                }
+                int n = 0;
+                if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0)
+                {
+                    g.device = false;
+                    throw CudaError("no CUDA device visible");
+                }
+                if (device >= n)
+                {
+                    throw CudaError("device index out of range");
+                }
+                SMR_CUDA(cudaSetDevice(device));
+                g.dev    = device;
+                g.stream = nullptr; // legacy default stream unless smr_set_stream() is called
+                g.device = true;
+            });
+    }
+
+    int smr_finalize(void)
+    {
+        return guarded(
+            [&]
+            {
+                if (g.device)
+                {
+                    cudaStreamSynchronize(g.stream);
+                }
+                g.fields.clear();
+                g.meshes.clear();
+            });
+    }
+
+    const char* smr_last_error(void)
+    {
+        return g.err.c_str();
+    }
+
+    int smr_device_available(void)
+    {
+        return g.device ? 1 : 0;
+    }
+
+    int smr_set_stream(void* s)
+    {
+        return guarded(
+            [&]
+            {
+                require_device();
+                SMR_CUDA(cudaStreamSynchronize(g.stream));
+                g.stream = static_cast<cudaStream_t>(s);
+            });
+    }
+
+    int smr_synchronize(void)
+    {
+        return guarded(
+            [&]
+            {
+                require_device();
+                SMR_CUDA(cudaStreamSynchronize(g.stream));
+            });
+    }
+
+    int smr_mesh_create_uniform(const smr_mesh_config* cfg, int level, smr_mesh_t* out)
+    {
+        return guarded(
+            [&]
+            {
+                MeshConfig c;
+                config_to_mesh_cfg(cfg, c);
+                if (level < 0 || level > c.max_level)
+                {
+                    throw std::invalid_argument("start level out of range");
+                }
+                const double t0 = now();
+                auto mo         = std::make_unique<MeshObj>();
+                mo->mesh.init_uniform(c, level);
+                g.stats.host_mesh_seconds += now() - t0;
+                *out = g.next_id++;
+                g.meshes[*out] = std::move(mo);
+            });
+    }
+
+    int smr_mesh_create_from_intervals(const smr_mesh_config* cfg, const int32_t* levels, const smr_interval* ivl, int64_t n, smr_mesh_t* out)
+    {
+        return guarded(
+            [&]
+            {
+                MeshConfig c;
+                config_to_mesh_cfg(cfg, c);
+                const int nlev = Mesh::levels_for(c);
+                std::vector<SetBuilder> b(nlev);
+                for (int64_t i = 0; i < n; ++i)
+                {
+                    if (levels[i] < 0 || levels[i] > c.max_level)
+                    {
+                        throw std::invalid_argument("interval level out of range");
+                    }
+                    b[levels[i]].add(mk_key(c.dim > 1 ? ivl[i].y : 0, c.dim > 2 ? ivl[i].z : 0), ivl[i].start, ivl[i].end);
+                }
+                CellArray ca(nlev);
+                for (int l = 0; l < nlev; ++l)
+                {
+                    ca[l] = b[l].build();
+                }
+                const double t0 = now();
+                auto mo         = std::make_unique<MeshObj>();
+                mo->mesh.init_from_cells(c, std::move(ca));
+                g.stats.host_mesh_seconds += now() - t0;
+                *out = g.next_id++;
+                g.meshes[*out] = std::move(mo);
+            });
+    }
+
+    int smr_mesh_destroy(smr_mesh_t m)
+    {
+        return guarded(
+            [&]
+            {
+                MeshObj& mo = get_mesh(m);
+                if (!mo.fields.empty())
+                {
+                    throw std::invalid_argument("mesh still has fields attached");
+                }
+                if (g.device)
+                {
+                    cudaStreamSynchronize(g.stream);
+                }
+                g.meshes.erase(m);
+            });
+    }
+
+    int smr_mesh_config_get(smr_mesh_t m, smr_mesh_config* out)
+    {
+        return guarded(
+            [&]
+            {
+                const MeshConfig& c     = get_mesh(m).mesh.cfg;
+                out->dim                = c.dim;
+                out->min_level          = c.min_level;
+                out->max_level          = c.max_level;
+                out->pred_radius        = c.pred_radius;
+                out->max_stencil_radius = c.max_stencil_radius;
+                out->graduation_width   = c.graduation_width;
+                for (int d = 0; d < 3; ++d)
+                {
+                    out->n_cells0[d] = c.n0[d];
+                    out->origin[d]   = c.origin[d];
+                }
+                out->scaling_factor = c.scaling;
+            });
+    }
+
+    static void check_mesh_id(int id)
+    {
+        if (id < 0 || id > 4)
+        {
+            throw std::invalid_argument("invalid mesh id");
+        }
+    }
+
+    int smr_mesh_nb_cells(smr_mesh_t m, int mesh_id, int level, int64_t* out)
+    {
+        return guarded(
+            [&]
+            {
+                const Mesh& mesh = get_mesh(m).mesh;
+                check_mesh_id(mesh_id);
+                const CellArray& ca = mesh.sub(mesh_id);
+                int64_t n           = 0;
+                for (int l = 0; l < mesh.nlev; ++l)
+                {
+                    if (level < 0 || level == l)
+                    {
+                        n += ca[l].n_cells();
+                    }
+                }
+                *out = n;
+            });
+    }
+
+    int smr_mesh_nb_intervals(smr_mesh_t m, int mesh_id, int level, int64_t* out)
+    {
+        return guarded(
+            [&]
+            {
+                const Mesh& mesh = get_mesh(m).mesh;
+                check_mesh_id(mesh_id);
+                const CellArray& ca = mesh.sub(mesh_id);
+                int64_t n           = 0;
+                for (int l = 0; l < mesh.nlev; ++l)
+                {
+                    if (level < 0 || level == l)
+                    {
+                        n += static_cast<int64_t>(ca[l].n_intervals());
+                    }
+                }
+                *out = n;
+            });
+    }
+
+    int smr_mesh_get_intervals(smr_mesh_t m, int mesh_id, int level, smr_interval* out)
+    {
+        return guarded(
+            [&]
+            {
+                const Mesh& mesh = get_mesh(m).mesh;
+                check_mesh_id(mesh_id);
+                if (level < 0 || level >= mesh.nlev)
+                {
+                    throw std::invalid_argument("level out of range");
+                }
+                LevelSet s = mesh.sub(mesh_id)[level];
+                if (s.off.size() != s.xs.size())
+                {
+                    // union cells are not necessarily inside the reference mesh: report -1 offsets
+                    s.off.assign(s.xs.size(), -1);
+                }
+                size_t k = 0;
+                for (size_t r = 0; r < s.rows(); ++r)
+                {
+                    for (int q = s.ptr[r]; q < s.ptr[r + 1]; ++q)
+                    {
+                        out[k++] = {key_y(s.key[r]), key_z(s.key[r]), s.xs[q], s.xe[q], s.off[q]};
+                    }
+                }
+            });
+    }
+
+    int smr_mesh_generation(smr_mesh_t m, uint64_t* out)
+    {
+        return guarded(
+            [&]
+            {
+                *out = get_mesh(m).mesh.generation;
+            });
+    }
+
+    int smr_mesh_get_index(smr_mesh_t m, int level, int i, int j, int k, int64_t* out)
+    {
+        return guarded(
+            [&]
+            {
+                const Mesh& mesh = get_mesh(m).mesh;
+                *out             = -1;
+                if (level < 0 || level >= mesh.nlev)
+                {
+                    throw std::out_of_range("level out of range");
+                }
+                const int64_t o = mesh.ref[level].offset_of(mk_key(mesh.cfg.dim > 1 ? j : 0, mesh.cfg.dim > 2 ? k : 0), i, i);
+                if (o < 0)
+                {
+                    missing("get_index", level, i, j, k);
+                }
+                *out = o;
+            });
+    }
+
+    int smr_field_create(smr_mesh_t m, const char* name, smr_field_t* out)
+    {
+        return guarded(
+            [&]
+            {
+                MeshObj& mo = get_mesh(m);
+                auto f      = std::make_unique<FieldObj>();
+                f->mesh     = &mo;
+                f->name     = name ? name : "";
+                mo.fields.push_back(f.get());
+                *out           = g.next_id++;
+                g.fields[*out] = std::move(f);
+            });
+    }
+
+    int smr_field_destroy(smr_field_t fh)
+    {
+        return guarded(
+            [&]
+            {
+                FieldObj& f = get_field(fh);
+                if (g.device)
+                {
+                    cudaStreamSynchronize(g.stream);
+                }
+                auto& v = f.mesh->fields;
+                v.erase(std::remove(v.begin(), v.end(), &f), v.end());
+                g.fields.erase(fh);
+            });
+    }
+
+    int smr_field_resize(smr_field_t fh)
+    {
+        return guarded(
+            [&]
+            {
+                require_device();
+                FieldObj& f     = get_field(fh);
+                const int64_t n = f.mesh->mesh.nref;
+                if (static_cast<size_t>(n) * sizeof(double) > f.data.cap)
+                {
+                    SMR_CUDA(cudaStreamSynchronize(g.stream));
+                }
+                f.data.ensure(static_cast<size_t>(n) * sizeof(double));
+                f.n = n;
+            });
+    }
+
+    int smr_field_fill(smr_field_t fh, double v)
+    {
+        return guarded(
+            [&]
+            {
+                require_device();
+                FieldObj& f = get_field(fh);
+                check_field_ready(f);
+                if (v == 0.0)
+                {
+                    SMR_CUDA(cudaMemsetAsync(f.data.p, 0, static_cast<size_t>(f.n) * sizeof(double), g.stream));
+                }
+                else
+                {
+                    std::vector<double> h(static_cast<size_t>(f.n), v);
+                    SMR_CUDA(cudaMemcpyAsync(f.data.p, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+                    SMR_CUDA(cudaStreamSynchronize(g.stream));
+                }
+            });
+    }
+
+    int smr_field_size(smr_field_t fh, int64_t* out)
+    {
+        return guarded(
+            [&]
+            {
+                *out = get_field(fh).mesh->mesh.nref;
+            });
+    }
+
+    int smr_field_upload(smr_field_t fh, const double* host, int64_t n)
+    {
+        return guarded(
+            [&]
+            {
+                require_device();
+                FieldObj& f = get_field(fh);
+                check_field_ready(f);
+                if (n != f.n)
+                {
+                    throw std::invalid_argument("upload size does not match the field size");
+                }
+                SMR_CUDA(cudaMemcpyAsync(f.data.p, host, static_cast<size_t>(n) * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+                g.stats.h2d_bytes += static_cast<uint64_t>(n) * sizeof(double);
+            });
+    }
+
+    int smr_field_download(smr_field_t fh, double* host, int64_t n)
+    {
+        return guarded(
+            [&]
+            {
+                require_device();
+                FieldObj& f = get_field(fh);
+                check_field_ready(f);
+                if (n != f.n)
+                {
+                    throw std::invalid_argument("download size does not match the field size");
+                }
+                SMR_CUDA(cudaMemcpyAsync(host, f.data.p, static_cast<size_t>(n) * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+                SMR_CUDA(cudaStreamSynchronize(g.stream));
+                g.stats.d2h_bytes += static_cast<uint64_t>(n) * sizeof(double);
+            });
+    }
+
+    int smr_field_swap(smr_field_t ah, smr_field_t bh)
+    {
+        return guarded(
+            [&]
+            {
+                FieldObj& a = get_field(ah);
+                FieldObj& b = get_field(bh);
+                if (a.mesh != b.mesh)
+                {
+                    throw std::invalid_argument("fields live on different meshes");
+                }
+                a.data.swap(b.data);
+                std::swap(a.n, b.n);
+            });
+    }
+
+    int smr_field_set_bc(smr_field_t fh, int bc_type, double value)
+    {
+        return guarded(
+            [&]
+            {
+                FieldObj& f = get_field(fh);
+                if (bc_type != SMR_BCTYPE_DIRICHLET && bc_type != SMR_BCTYPE_NEUMANN)
+                {
+                    throw std::invalid_argument("unknown boundary condition type");
+                }
+                f.bc_type  = bc_type;
+                f.bc_value = value;
+            });
+    }
+
+    int smr_update_ghost_mr(smr_field_t fh)
+    {
+        return guarded(
+            [&]
+            {
+                require_device();
+                do_update_ghost(get_field(fh));
+            });
+    }
+
+    int smr_fv_upwind(smr_field_t out, smr_field_t in, const double* a, double dt)
+    {
+        return guarded(
+            [&]
+            {
+                do_fv(get_field(out), get_field(in), a, dt, false);
+            });
+    }
+
+    int smr_fv_upwind_burgers(smr_field_t out, smr_field_t in, const double* k, double dt)
+    {
+        return guarded(
+            [&]
+            {
+                do_fv(get_field(out), get_field(in), k, dt, true);
+            });
+    }
+
+    static std::vector<FieldObj*> collect_fields(const smr_field_t* fields, int n)
+    {
+        if (n < 1 || n > 8)
+        {
+            throw std::invalid_argument("make_MRAdapt needs between 1 and 8 fields");
+        }
+        std::vector<FieldObj*> v;
+        for (int i = 0; i < n; ++i)
+        {
+            v.push_back(&get_field(fields[i]));
+        }
+        return v;
+    }
+
+    int smr_adapt_iteration(const smr_field_t* fields, int n_fields, double epsilon, double regularity, int ite, int* unchanged)
+    {
+        return guarded(
+            [&]
+            {
+                auto v     = collect_fields(fields, n_fields);
+                *unchanged = do_harten(v, epsilon, regularity, ite) ? 1 : 0;
+            });
+    }
+
+    int smr_adapt(const smr_field_t* fields, int n_fields, double epsilon, double regularity, int* n_iterations)
+    {
+        return guarded(
+            [&]
+            {
+                auto v                = collect_fields(fields, n_fields);
+                const MeshConfig& cfg = v[0]->mesh->mesh.cfg;
+                int done              = 0;
+                if (cfg.min_level != cfg.max_level)
+                {
+                    for (int ite = 0; ite < cfg.max_level - cfg.min_level; ++ite)
+                    {
+                        ++done;
+                        if (do_harten(v, epsilon, regularity, ite))
+                        {
+                            break;
+                        }
+                    }
+                }
+                if (n_iterations)
+                {
+                    *n_iterations = done;
+                }
+            });
+    }
+
+    int smr_mesh_update_from_tags(smr_mesh_t m, const uint8_t* tags, int64_t n, int* unchanged)
+    {
+        return guarded(
+            [&]
+            {
+                MeshObj& mo = get_mesh(m);
+                if (n != mo.mesh.nref)
+                {
+                    throw std::invalid_argument("tag array size does not match nb_cells(reference)");
+                }
+                const double t0 = now();
+                CellArray ca    = cells_from_tags(mo.mesh, tags);
+                make_graduation(mo.mesh.cfg, ca);
+                const bool same = same_cells(ca, mo.mesh.cells);
+                *unchanged      = same ? 1 : 0;
+                if (!same)
+                {
+                    if (g.device)
+                    {
+                        SMR_CUDA(cudaStreamSynchronize(g.stream));
+                    }
+                    Mesh nm;
+                    nm.generation = mo.mesh.generation;
+                    nm.init_from_cells(mo.mesh.cfg, std::move(ca));
+                    mo.mesh       = std::move(nm);
+                    mo.plan_ready = false;
+                    ++g.stats.mesh_rebuilds;
+                }
+                g.stats.host_mesh_seconds += now() - t0;
+            });
+    }
+
+    int smr_adapt_last_size(smr_mesh_t m, int64_t* out)
+    {
+        return guarded(
+            [&]
+            {
+                *out = get_mesh(m).last_size;
+            });
+    }
+
+    int smr_adapt_last_tags(smr_mesh_t m, uint8_t* host, int64_t n)
+    {
+        return guarded(
+            [&]
+            {
+                MeshObj& mo = get_mesh(m);
+                if (n != mo.last_size || n == 0)
+                {
+                    throw std::invalid_argument("size does not match the last adaptation's reference size");
+                }
+                std::memcpy(host, mo.h_tag.p, static_cast<size_t>(n));
+            });
+    }
+
+    int smr_adapt_last_detail(smr_mesh_t m, double* host, int64_t n)
+    {
+        return guarded(
+            [&]
+            {
+                require_device();
+                MeshObj& mo = get_mesh(m);
+                if (n != mo.last_size * mo.last_ncomp || n == 0)
+                {
+                    throw std::invalid_argument("size does not match the last adaptation's reference size x n_fields");
+                }
+                SMR_CUDA(cudaMemcpyAsync(host, mo.d_detail.p, static_cast<size_t>(n) * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+                SMR_CUDA(cudaStreamSynchronize(g.stream));
+            });
+    }
+
+    int smr_stats_get(smr_stats* out)
+    {
+        *out = g.stats;
+        return SMR_OK;
+    }
+
+    int smr_stats_reset(void)
+    {
+        g.stats = smr_stats{};
+        return SMR_OK;
+    }
+}

@@ -1,0 +1,90 @@
+/* Work-item records shared by the host batch builders and the CUDA kernels.
+ *
+ * A batch is the host-side traversal of one set-algebra subset of the reference, flattened into
+ * records that carry precomputed storage offsets, so the kernels never search the mesh.  One record = one x-interval
+ * of the subset; `n` = number of output cells it produces.  Batches also carry an exclusive prefix sum of `n` and,
+ * per CTA of SMR_CTA_CELLS output cells, the index of the first record that CTA touches.
+ */
+#ifndef SAMURAI_B200_ITEMS_H
+#define SAMURAI_B200_ITEMS_H
+#include <stdint.h>
+
+#include "../../include/samurai_b200.h"
+
+#define SMR_CTA_THREADS 256
+#define SMR_CELLS_PER_THREAD 4
+#define SMR_CTA_CELLS (SMR_CTA_THREADS * SMR_CELLS_PER_THREAD)
+#define SMR_MAX_LEVELS 24
+
+/* leaf interval for the FV field-expression kernels (stencil_field.hpp) */
+typedef struct
+{
+    int64_t c;      /* offset of first cell in its own row (i-1 / i+1 are c-1 / c+1) */
+    int64_t ym, yp; /* same x, rows j-1 / j+1 */
+    int64_t zm, zp; /* same x, rows k-1 / k+1 (3D) */
+    int32_t n;
+    int32_t level;
+} smr_item_fv;
+
+/* coarse interval filled by projection (numeric/projection.hpp:22-64) */
+typedef struct
+{
+    int64_t dst;    /* coarse offset */
+    int64_t src[4]; /* fine offset of x = 2*start in rows (2y+cy, 2z+cz), index cy + 2*cz */
+    int32_t n;
+    int32_t pad;
+} smr_item_proj;
+
+/* fine interval filled by prediction (numeric/prediction.hpp:259-361, 149-257) */
+typedef struct
+{
+    int64_t dst;    /* fine offset of x = start */
+    int64_t src[9]; /* coarse offset of x = start>>1 in rows (y>>1 + ry - 1, z>>1 + rz - 1), index ry + 3*rz */
+    int32_t n;
+    int32_t par; /* bit0: start & 1, bit1: y & 1, bit2: z & 1 */
+} smr_item_pred;
+
+/* coarse interval whose 2^dim children get a detail (mr/operators.hpp:139-533) */
+typedef struct
+{
+    int64_t coarse[9]; /* offset of x = start in rows (y + ry - 1, z + rz - 1), index ry + 3*rz */
+    int64_t fine[4];   /* offset of x = 2*start in rows (2y+cy, 2z+cz), index cy + 2*cz */
+    int32_t n;
+    int32_t pad;
+} smr_item_detail;
+
+/* coarse interval for the tagging criteria and the keep propagation (mr/criteria.hpp, mr/operators.hpp:29-89) */
+typedef struct
+{
+    int64_t coarse;
+    int64_t fine[4];
+    int32_t n;
+    int32_t level; /* level of the children */
+} smr_item_tag;
+
+typedef struct
+{
+    int64_t dst;
+    int64_t src;
+    int32_t n;
+    int32_t pad;
+} smr_item_copy;
+
+/* one boundary ghost cell (algorithm/update_outer_ghost.hpp, bc/apply_field_bc.hpp) */
+enum
+{
+    SMR_BC_COPY  = 0, /* f[dst] = f[src[0]]                            corner extrapolation / projection, predict_bc */
+    SMR_BC_VALUE = 1, /* Dirichlet: 2*v - f[src[0]] ; Neumann: coef*v + f[src[0]]   (coef = dx)                     */
+    SMR_BC_AVG   = 2  /* f[dst] = (0 + f[src[0]] + ... ) / n_src ; 0 if n_src == 0   project_bc                     */
+};
+
+typedef struct
+{
+    int64_t dst;
+    double coef;
+    int32_t kind;
+    int32_t n_src;
+    int64_t src_first; /* index into the batch's int64 source-offset array */
+} smr_item_bc;
+
+#endif

@@ -1,0 +1,26 @@
+"""Regenerate tests/golden/*.npz from the reference's own golden HDF5 files.
+
+Run in the build container (needs /root/reference):  python tests/golden/make_golden.py
+Source: /root/reference/tests/reference/finite_volume/test_finite_volume_advection_2d_*.h5, the files
+samurai's pytest suite compares the advection_2d demo against (tests/test_demo_finite_volume.py:55-72,
+run with --Tf 0.01; tolerance rel 1e-14 / abs 1e-7, tests/conftest.py:121-122).
+Each .npz holds, per leaf cell in for_each_cell order: level (int8), idx (int32 [N,2]), u (float64).
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", "..", "oracle"))
+import h5mini  # noqa: E402
+
+REF = "/root/reference/tests/reference/finite_volume/"
+BASE = "test_finite_volume_advection_2d_finite-volume-advection-2d-0.01_"
+
+if __name__ == "__main__":
+    for name in ("pred_0_init", "pred_0", "pred_1_init", "pred_1"):
+        level, idx, fields = h5mini.read_samurai_mesh(REF + BASE + name + ".h5")
+        out = os.path.join(HERE, "advection_2d_" + name + ".npz")
+        np.savez_compressed(out, level=level.astype(np.int8), idx=idx.astype(np.int32), u=fields["u"])
+        print(out, len(level), os.path.getsize(out))
