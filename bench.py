@@ -1,0 +1,435 @@
+#!/usr/bin/env python
+"""bench.py -- samurai hot path on B200: cell-updates/s per FV step incl. ghost update + MR detail/tagging.
+
+Workload (BASELINE.json configs[1]): demos/FiniteVolume/advection_2d.cpp scaled to max_level=14 (min_level 4,
+eps 2e-4, prediction radius 1, Dirichlet 0, disc r=0.2 at (0.3,0.3), a=(1,1), cfl 0.5). One "step" is one pass of
+the demo's time loop:  MRadaptation(cfg) -> update_ghost_mr(u) -> unp1 = u - dt*upwind(a,u) -> swap.
+One cell-update = one leaf cell advanced one step (nb_cells(mesh_id_t::cells), the reference benchmarks' counter).
+
+  value   device-resident loop: fields live in HBM, K steps timed with CUDA events (includes the host-side mesh work
+          the GPU waits for; the split device / host-mesh / host-batch is reported next to it)
+  e2e     same K steps through the public API with HOST buffers: u uploaded from pinned memory and unp1 read back
+          every step
+  roofline  dominant kernel family of the timed loop (CUDA-event time per launch, measured in a separate profiled
+          pass), algorithmic bytes from DESIGN.md; plus `uniform_sweep`: the FV kernel on a uniform level-13 mesh
+          (BASELINE.json configs[4]) where the HBM roofline is the physically meaningful bound
+  cpu_baseline  the numpy oracle ("port") on host cores, a bounded sample of the same adapted mesh
+
+`--impl reference` times the oracle port alone (no GPU code on the path).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "cell-updates/s per FV step (incl. ghost+MR detail)"
+UNIT = "cell-updates/s"
+
+# algorithmic bytes per output cell of each kernel family (DESIGN.md "Kernels"), fp64 scalar field
+def alg_bytes_per_cell(family, dim):
+    nchild = 1 << dim
+    return {
+        "fv": 16.0,                          # read u, write unp1
+        "projection": 8.0 * (nchild + 1),    # 2^dim children read, 1 coarse write
+        "prediction": 8.0 * (1 + 1.0 / nchild),  # 1 fine write + its parent read once
+        "detail": 8.0 * (1 + 2 * nchild),    # coarse read once, children read, details written
+        "criteria": 8.0 * (nchild + 1) + 2.0 * nchild,  # detail reads + tag read/write
+        "maximum": 2.0 * nchild + 2.0,       # tag bytes r/w
+        "bc": 24.0,                          # 1 read + 1 write + item record amortised
+        "copy": 16.0,
+        "keep": 1.0,
+        "init": 8.0,
+    }[family]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the numpy oracle port
+# ----------------------------------------------------------------------------------------------------------------------
+def oracle_adapted_state(so, min_level, max_level, eps, start_level=8):
+    """Adapted advection_2d state built by the oracle alone (bottom-up: uniform start_level, refine to max_level)."""
+    cfg = so.MeshConfig(dim=2, min_level=min_level, max_level=max_level, pred_radius=1)
+    bc = so.Bc("dirichlet", 0.0)
+    mesh = so.Mesh.uniform(cfg, level=min(start_level, max_level))
+    u = so.init_disc(mesh, [0.3, 0.3], 0.2)
+    for _ in range(max_level - min_level + 2):
+        before = mesh
+        mesh, u = so.adapt(mesh, u, bc, eps, 1.0)
+        # re-impose the exact initial condition on the refined leaves (sharp disc)
+        u = so.init_disc(mesh, [0.3, 0.3], 0.2)
+        if mesh is before:
+            break
+    return cfg, bc, mesh, u
+
+
+def oracle_steps(so, cfg, bc, mesh, u, n_steps, dt):
+    """n_steps of the demo loop on the oracle; returns (cell_updates, seconds, mesh, u)."""
+    cells = 0
+    t0 = time.perf_counter()
+    for _ in range(n_steps):
+        mesh, u = so.adapt(mesh, u, bc, ARGS.eps, 1.0)
+        so.update_ghost_mr(mesh, u, bc)
+        u = so.fv_step(mesh, u, [1.0, 1.0], dt)
+        cells += mesh.nb_cells()
+    return cells, time.perf_counter() - t0, mesh, u
+
+
+def run_reference(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import samurai_oracle as so
+
+    # bounded sample: the numpy port advances ~9e4 cell-updates/s and the adapted mesh holds ~1.2e5 * 2^(L-12) leaves,
+    # so pick the largest max_level <= the product's whose (steps + warmup) fit in ~150 s of CPU work
+    sample_level = min(args.max_level, args.ref_max_level)
+    while sample_level > args.min_level + 2 and (args.steps + args.warmup) * 1.3 * 2.0 ** (sample_level - 12) > 150.0:
+        sample_level -= 1
+    cfg, bc, mesh, u = oracle_adapted_state(so, args.min_level, sample_level, args.eps)
+    dt = 0.5 * cfg.cell_length(sample_level)
+    _, _, mesh, u = oracle_steps(so, cfg, bc, mesh, u, args.warmup, dt)
+    cells, secs, mesh, u = oracle_steps(so, cfg, bc, mesh, u, args.steps, dt)
+    value = cells / secs
+    sample = (f"{args.steps} steps of advection_2d on the oracle's own adapted mesh, levels {args.min_level}-{sample_level} "
+              f"({mesh.nb_cells()} leaves); numpy port, 1 thread")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"advection_2d min_level={args.min_level} max_level={sample_level} eps={args.eps} (CPU sample of the max_level={args.max_level} case)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# product arm
+# ----------------------------------------------------------------------------------------------------------------------
+class Sim:
+    """The advection_2d demo (demos/FiniteVolume/advection_2d.cpp:61-155) on the C ABI."""
+
+    def __init__(self, sb, args, dim=2):
+        self.sb = sb
+        self.dim = dim
+        cfg = sb.mesh_config(dim, 1).min_level(args.min_level).max_level(args.max_level).max_stencil_size(2).disable_minimal_ghost_width()
+        self.mesh = sb.MRMesh.make_mesh([0.0] * dim, [1.0] * dim, cfg)
+        self.u = sb.make_scalar_field("u", self.mesh)
+        self.u.resize()
+        self.u.init_ball([0.3] * dim, 0.2)
+        sb.make_bc(self.u, sb.DIRICHLET, 0.0)
+        self.unp1 = sb.make_scalar_field("unp1", self.mesh)
+        self.adapt = sb.make_MRAdapt(self.u)
+        self.mra = sb.mra_config().epsilon(args.eps)
+        self.a = [1.0] * dim
+        self.dt = 0.5 * self.mesh.min_cell_length()
+
+    def step(self):
+        sb = self.sb
+        self.adapt(self.mra)
+        sb.update_ghost_mr(self.u)
+        self.unp1.resize()
+        sb.upwind_step(self.unp1, self.u, self.a, self.dt)
+        sb.swap(self.u, self.unp1)
+        return self.mesh.nb_cells()
+
+
+def uniform_sweep(sb, torch, level, iters=20):
+    """BASELINE.json configs[4]: uniform-level upwind sweep, the shape where HBM bandwidth is the bound."""
+    cfg = sb.mesh_config(2, 1).min_level(level).max_level(level).max_stencil_size(2).disable_minimal_ghost_width()
+    mesh = sb.MRMesh.make_mesh([0.0, 0.0], [1.0, 1.0], cfg)
+    u = sb.make_scalar_field("u", mesh)
+    u.resize()
+    u.fill(0.0)
+    u.init_ball([0.3, 0.3], 0.2)
+    sb.make_bc(u, sb.DIRICHLET, 0.0)
+    v = sb.make_scalar_field("v", mesh)
+    v.resize()
+    sb.update_ghost_mr(u)
+    n = mesh.nb_cells()
+    dt = 0.5 * mesh.min_cell_length()
+    for _ in range(3):
+        sb.upwind_step(v, u, [1.0, 1.0], dt)
+        sb.swap(u, v)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        sb.upwind_step(v, u, [1.0, 1.0], dt)
+        sb.swap(u, v)
+    e1.record()
+    torch.cuda.synchronize()
+    secs = e0.elapsed_time(e1) * 1e-3 / iters
+    # ghost update on the same mesh (BC only on a uniform mesh)
+    e0.record()
+    for _ in range(iters):
+        sb.update_ghost_mr(u)
+    e1.record()
+    torch.cuda.synchronize()
+    gsecs = e0.elapsed_time(e1) * 1e-3 / iters
+    u.destroy()
+    v.destroy()
+    mesh.destroy()
+    return n, secs, gsecs
+
+
+def run_product(args):
+    import torch
+    import torch.distributed as dist
+
+    rank, local_rank, world = dist_env()
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    import __graft_entry__
+
+    if not os.path.exists(__graft_entry__.LIB):
+        __graft_entry__.build()
+    import samurai_b200 as sb
+
+    if not sb.initialize(local_rank):
+        raise SystemExit("no CUDA device: bench.py has no CPU fallback for the product arm")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_file):
+        peak_gbs, peak_src = json.load(open(peaks_file))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak_gbs, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+
+    t0 = time.perf_counter()
+    sim = Sim(sb, args)
+    sim.adapt(sim.mra)  # the demo's initial MRadaptation (from the uniform max_level mesh)
+    sb.synchronize()
+    init_secs = time.perf_counter() - t0
+
+    for _ in range(args.warmup):
+        sim.step()
+
+    # ---- timed, device-resident ------------------------------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    sb.stats(reset=True)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    cells = 0
+    for _ in range(args.steps):
+        cells += sim.step()
+    e1.record()
+    barrier()
+    secs = e0.elapsed_time(e1) * 1e-3
+    st = sb.stats()
+    clocks = sampler.stop()
+    leaves_now, ref_now = sim.mesh.nb_cells(), sim.mesh.nb_cells(sb.REFERENCE)
+
+    # ---- e2e: host buffers in, host buffers out, every step --------------------------------------------------------
+    host = sim.u.download()
+    pinned = torch.empty(int(ref_now * 1.5) + 1024, dtype=torch.float64).pin_memory().numpy()
+    pinned[: host.size] = host
+    n_host = host.size
+    sb.stats(reset=True)
+    barrier()
+    e0.record()
+    e2e_cells = 0
+    for _ in range(args.steps):
+        sim.u.upload(pinned[:n_host])
+        e2e_cells += sim.step()
+        n_host = sim.u.size()
+        if n_host > pinned.size:
+            pinned = torch.empty(int(n_host * 1.5), dtype=torch.float64).pin_memory().numpy()
+        sim.u.download(pinned[:n_host])
+    e1.record()
+    barrier()
+    e2e_secs = e0.elapsed_time(e1) * 1e-3
+    st_e2e = sb.stats()
+
+    # ---- max over ranks --------------------------------------------------------------------------------------------
+    if world > 1:
+        t = torch.tensor([secs, e2e_secs], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        c = torch.tensor([cells, e2e_cells], device="cuda", dtype=torch.float64)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        secs, e2e_secs = t.tolist()
+        cells, e2e_cells = c.tolist()
+
+    line = None
+    if rank == 0:
+        # ---- per-family profile pass (separate from the timed region: every launch is synchronised) ----------------
+        sb.profile_enable(True)
+        for _ in range(2):
+            sim.step()
+        prof = sb.profile_get()
+        sb.profile_enable(False)
+        fam_time = {k: v[1] for k, v in prof.items() if v[0]}
+        total_prof = sum(fam_time.values()) or 1.0
+        dom = max(fam_time, key=fam_time.get)
+        n_l, s_l, c_l = prof[dom]
+        achieved = alg_bytes_per_cell(dom, 2) * c_l / s_l / 1e9
+        families = {k: {"launches": v[0], "us_per_launch": 1e6 * v[1] / v[0], "cells_per_launch": v[2] / v[0],
+                        "share": v[1] / total_prof, "GBps": alg_bytes_per_cell(k, 2) * v[2] / v[1] / 1e9} for k, v in prof.items() if v[0]}
+
+        # ---- uniform sweep (configs[4]) -----------------------------------------------------------------------------
+        sweep = None
+        if args.sweep_level > 0:
+            n_u, s_u, g_u = uniform_sweep(sb, torch, args.sweep_level)
+            sweep = {"workload": f"uniform 2D level {args.sweep_level} upwind sweep, {n_u} cells, working set {16 * n_u / 1e6:.0f} MB > L2",
+                     "cell_updates_per_s": n_u / s_u, "ms_per_sweep": 1e3 * s_u, "bound": "hbm", "achieved": 16.0 * n_u / s_u / 1e9,
+                     "peak": peak_gbs, "unit": "GB/s", "frac": 16.0 * n_u / s_u / 1e9 / peak_gbs, "ghost_update_ms": 1e3 * g_u}
+
+        # ---- cpu baseline: oracle port on a bounded sample of the same state ----------------------------------------
+        cpu = None
+        if not args.no_cpu_baseline:
+            cpu = cpu_baseline_from_state(sb, sim, args)
+
+        line = {
+            "metric": METRIC, "value": cells / secs, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"advection_2d min_level={args.min_level} max_level={args.max_level} eps={args.eps} pred_radius=1 Dirichlet(0) "
+                                   f"disc r=0.2@(0.3,0.3), a=(1,1), cfl=0.5; one step = MRadaptation + update_ghost_mr + upwind + swap",
+                       "leaves": leaves_now, "reference_cells": ref_now, "parallelism": f"replicas x{world}" if world > 1 else "single GPU",
+                       "l2_policy": "every kernel is launched once per mesh state; between timed steps the mesh and all index batches change; "
+                                    "the uniform sweep uses a working set > L2"},
+            "split_ms_per_step": {"device": 1e3 * st["device_seconds"] / args.steps, "host_mesh": 1e3 * st["host_mesh_seconds"] / args.steps,
+                                  "host_batches": 1e3 * st["host_batch_seconds"] / args.steps},
+            "device_only_value": cells / world / st["device_seconds"] if st["device_seconds"] > 0 else None,
+            "gpu_launches": int(st["kernel_launches"]),
+            "initial_adaptation_s": init_secs,
+            "e2e": {"value": e2e_cells / e2e_secs, "unit": UNIT, "h2d_bytes_per_step": int(st_e2e["h2d_bytes"] / args.steps),
+                    "d2h_bytes_per_step": int(st_e2e["d2h_bytes"] / args.steps), "ms_per_step": 1e3 * e2e_secs / args.steps},
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
+                         "traffic": None, "peak_source": peak_src, "share_of_device_time": fam_time[dom] / total_prof,
+                         "note": "adapted-mesh step: ~1e6 cells spread over ~100 dependent launches, launch-latency bound; see uniform_sweep for the HBM-bound shape"},
+            "kernel_families": families,
+            "uniform_sweep": sweep,
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_baseline_from_state(sb, sim, args):
+    """Oracle port timed on the product's current adapted mesh (same leaves, same field): a bounded sample of the
+    same workload, and a full-size parity check of the step at the same time."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import samurai_oracle as so
+
+    lv, co, off = sim.mesh.cell_table(sb.CELLS)
+    pu = sim.u.download()
+    cfg = so.MeshConfig(dim=2, min_level=args.min_level, max_level=args.max_level, pred_radius=1)
+    cells = {int(l): np.sort(so.pack(co[lv == l])) for l in np.unique(lv)}
+    omesh = so.Mesh(cfg, cells)
+    ou = np.zeros(omesh.nref)
+    olv, oco, oix = omesh.leaf_table()
+    # both tables are in for_each_cell order
+    assert np.array_equal(olv, lv) and np.array_equal(oco, co)
+    ou[oix] = pu[off]
+    bc = so.Bc("dirichlet", 0.0)
+    n_steps = args.cpu_steps
+    cells_done, secs, omesh, ou = oracle_steps(so, cfg, bc, omesh, ou, n_steps, sim.dt)
+    # parity at full size: advance the product by the same steps and compare
+    for _ in range(n_steps):
+        sim.step()
+    lv2, co2, off2 = sim.mesh.cell_table(sb.CELLS)
+    olv, oco, oix = omesh.leaf_table()
+    same_mesh = bool(np.array_equal(olv, lv2) and np.array_equal(oco, co2))
+    pu2 = sim.u.download()
+    err = float(np.max(np.abs(pu2[off2] - ou[oix]) / np.maximum(np.abs(ou[oix]), 1.0))) if same_mesh else None
+    return {"value": cells_done / secs, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"{n_steps} steps on the same adapted mesh ({omesh.nb_cells()} leaves), numpy oracle, 1 thread",
+            "parity_mesh_identical": same_mesh, "parity_max_rel_err": err}
+
+
+def main():
+    global ARGS
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--min-level", type=int, default=4)
+    ap.add_argument("--max-level", type=int, default=14)
+    ap.add_argument("--eps", type=float, default=2e-4)
+    ap.add_argument("--sweep-level", type=int, default=13)
+    ap.add_argument("--cpu-steps", type=int, default=2)
+    ap.add_argument("--ref-max-level", type=int, default=14, help="largest max_level the CPU reference arm samples")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ARGS = ap.parse_args()
+    if ARGS.impl == "reference":
+        run_reference(ARGS)
+    else:
+        run_product(ARGS)
+
+
+if __name__ == "__main__":
+    main()

@@ -139,10 +139,22 @@ extern "C"
         double host_mesh_seconds;  /* update_cell_array_from_tag + make_graduation + sub-mesh construction          */
         double host_batch_seconds; /* set-algebra traversal into index batches                                      */
         uint64_t mesh_rebuilds;
+        double device_seconds;     /* CUDA-event time of every stretch of device work (kernels + async copies)      */
     } smr_stats;
 
-    int smr_stats_get(smr_stats* out);
+    int smr_stats_get(smr_stats* out); /* synchronises the stream to resolve device_seconds */
     int smr_stats_reset(void);
+
+    /* per-kernel-family profile: when enabled every launch is bracketed by CUDA events and synchronised (slow; never
+     * enable it inside a timed region).  family = SMR_FAM_* of csrc/items.h: 0 fv, 1 projection, 2 prediction,
+     * 3 detail, 4 criteria, 5 maximum, 6 bc, 7 copy, 8 keep, 9 init. */
+    int smr_profile_enable(int on);
+    int smr_profile_get(int family, uint64_t* launches, double* seconds, uint64_t* cells);
+
+    /* the demos' initial condition as a device kernel over the leaves: u = inside where |center(cell) - c|^2 <= r^2,
+     * else outside (only written when overwrite_outside != 0)
+     * (demos/FiniteVolume/advection_2d.cpp:23-45, advection_3d.cpp:32-45, scalar_burgers_2d.cpp:20-50) */
+    int smr_field_init_ball(smr_field_t f, const double* center, double radius, double inside, double outside, int overwrite_outside);
 
 #ifdef __cplusplus
 }

@@ -52,6 +52,7 @@ class StatsC(C.Structure):
         ("host_mesh_seconds", C.c_double),
         ("host_batch_seconds", C.c_double),
         ("mesh_rebuilds", C.c_uint64),
+        ("device_seconds", C.c_double),
     ]
 
 
@@ -94,7 +95,12 @@ SYMBOLS = {
     "smr_adapt_last_detail": [_u64, _vp, _i64],
     "smr_stats_get": [_P(StatsC)],
     "smr_stats_reset": [],
+    "smr_profile_enable": [_i32],
+    "smr_profile_get": [_i32, _P(_u64), _P(_dbl), _P(_u64)],
+    "smr_field_init_ball": [_u64, _vp, _dbl, _dbl, _dbl, _i32],
 }
+
+FAMILIES = ["fv", "projection", "prediction", "detail", "criteria", "maximum", "bc", "copy", "keep", "init"]
 
 _lib = None
 _initialized = None
@@ -165,6 +171,20 @@ def stats(reset=False):
     if reset:
         load_library().smr_stats_reset()
     return {k: getattr(s, k) for k, _ in StatsC._fields_}
+
+
+def profile_enable(on=True):
+    _check(load_library().smr_profile_enable(1 if on else 0))
+
+
+def profile_get():
+    """{family: (launches, seconds, cells)} accumulated since profile_enable()."""
+    out = {}
+    for i, name in enumerate(FAMILIES):
+        n, s, c = C.c_uint64(), C.c_double(), C.c_uint64()
+        _check(load_library().smr_profile_get(i, C.byref(n), C.byref(s), C.byref(c)))
+        out[name] = (n.value, s.value, c.value)
+    return out
 
 
 class mesh_config:
@@ -355,6 +375,11 @@ class ScalarField:
             out = np.empty(n, dtype=np.float64)
         _check(load_library().smr_field_download(self._h, out.ctypes.data, n))
         return out
+
+    def init_ball(self, center, radius, inside=1.0, outside=0.0, overwrite_outside=True):
+        """The demos' init(): 1 inside the disc/ball, 0 outside, evaluated at the leaf centres on the device."""
+        c = np.ascontiguousarray(list(center) + [0.0] * (3 - len(center)), dtype=np.float64)
+        _check(load_library().smr_field_init_ball(self._h, c.ctypes.data, float(radius), float(inside), float(outside), int(overwrite_outside)))
 
     def destroy(self):
         if self._h:

@@ -169,6 +169,10 @@ namespace smr
                     }
                     it.n     = e - s;
                     it.level = l;
+                    it.x     = s;
+                    it.y     = y;
+                    it.z     = z;
+                    it.pad   = 0;
                     out.push_back(it);
                 }
             }

@@ -131,6 +131,13 @@ namespace smr
         std::string err;
         smr_stats stats{};
         uint64_t next_id = 1;
+        bool profile     = false;
+        double prof_seconds[SMR_FAM_COUNT]  = {};
+        uint64_t prof_launches[SMR_FAM_COUNT] = {};
+        uint64_t prof_cells[SMR_FAM_COUNT]  = {};
+        cudaEvent_t prof_a = nullptr, prof_b = nullptr;
+        std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending; // device-time sections not yet resolved
+        std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pool;
         std::unordered_map<uint64_t, std::unique_ptr<MeshObj>> meshes;
         std::unordered_map<uint64_t, std::unique_ptr<FieldObj>> fields;
     };
@@ -147,6 +154,92 @@ namespace smr
         if (!g.device)
         {
             throw CudaError("no CUDA device: samurai_b200 has no CPU fallback for compute entry points (call smr_init(device >= 0))");
+        }
+    }
+
+    // ---- device-time sections: event pairs around every contiguous stretch of device work -----------------------
+    struct Section
+    {
+        std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
+
+        Section()
+        {
+            if (!g.device)
+            {
+                return;
+            }
+            if (g.pool.empty())
+            {
+                SMR_CUDA(cudaEventCreate(&ev.first));
+                SMR_CUDA(cudaEventCreate(&ev.second));
+            }
+            else
+            {
+                ev = g.pool.back();
+                g.pool.pop_back();
+            }
+            SMR_CUDA(cudaEventRecord(ev.first, g.stream));
+        }
+
+        void close()
+        {
+            if (ev.first)
+            {
+                cudaEventRecord(ev.second, g.stream);
+                g.pending.push_back(ev);
+                ev.first = nullptr;
+            }
+        }
+
+        ~Section()
+        {
+            close();
+        }
+    };
+
+    static void resolve_sections()
+    {
+        if (!g.device || g.pending.empty())
+        {
+            return;
+        }
+        cudaStreamSynchronize(g.stream);
+        for (auto& p : g.pending)
+        {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, p.first, p.second) == cudaSuccess)
+            {
+                g.stats.device_seconds += ms * 1e-3;
+            }
+            g.pool.push_back(p);
+        }
+        g.pending.clear();
+    }
+
+    static void prof_begin()
+    {
+        if (g.profile)
+        {
+            if (!g.prof_a)
+            {
+                SMR_CUDA(cudaEventCreate(&g.prof_a));
+                SMR_CUDA(cudaEventCreate(&g.prof_b));
+            }
+            SMR_CUDA(cudaEventRecord(g.prof_a, g.stream));
+        }
+    }
+
+    static void prof_end(int fam, int64_t cells)
+    {
+        if (g.profile)
+        {
+            SMR_CUDA(cudaEventRecord(g.prof_b, g.stream));
+            SMR_CUDA(cudaEventSynchronize(g.prof_b));
+            float ms = 0;
+            SMR_CUDA(cudaEventElapsedTime(&ms, g.prof_a, g.prof_b));
+            g.prof_seconds[fam] += ms * 1e-3;
+            g.prof_launches[fam] += 1;
+            g.prof_cells[fam] += static_cast<uint64_t>(cells);
         }
     }
 
@@ -246,12 +339,13 @@ namespace smr
     }
 
     template <class Item, class Op>
-    static void launch(const void* arena, const Batch& b, const Op& op)
+    static void launch(int fam, const void* arena, const Batch& b, const Op& op)
     {
         if (b.empty())
         {
             return;
         }
+        prof_begin();
         const char* base = static_cast<const char*>(arena);
         BatchView<Item> v{reinterpret_cast<const Item*>(base + b.items),
                           reinterpret_cast<const int64_t*>(base + b.prefix),
@@ -260,6 +354,7 @@ namespace smr
         batch_kernel<Item, Op><<<b.n_ctas, SMR_CTA_THREADS, 0, g.stream>>>(v, op);
         SMR_CUDA(cudaGetLastError());
         ++g.stats.kernel_launches;
+        prof_end(fam, b.n_cells);
     }
 
     static void launch_bc(const void* arena, const Batch& b, double* f, int bc_type, double bc_value)
@@ -269,6 +364,7 @@ namespace smr
             return;
         }
         const char* base = static_cast<const char*>(arena);
+        prof_begin();
         bc_kernel<<<b.n_ctas, SMR_CTA_THREADS, 0, g.stream>>>(reinterpret_cast<const smr_item_bc*>(base + b.items),
                                                               reinterpret_cast<const int64_t*>(base + b.aux),
                                                               b.n_items,
@@ -277,21 +373,22 @@ namespace smr
                                                               bc_value);
         SMR_CUDA(cudaGetLastError());
         ++g.stats.kernel_launches;
+        prof_end(SMR_FAM_BC, b.n_items);
     }
 
     template <template <int> class OpT, class Item, class... Args>
-    static void launch_dim(int dim, const void* arena, const Batch& b, Args... args)
+    static void launch_dim(int fam, int dim, const void* arena, const Batch& b, Args... args)
     {
         switch (dim)
         {
             case 1:
-                launch<Item>(arena, b, OpT<1>{args...});
+                launch<Item>(fam, arena, b, OpT<1>{args...});
                 break;
             case 2:
-                launch<Item>(arena, b, OpT<2>{args...});
+                launch<Item>(fam, arena, b, OpT<2>{args...});
                 break;
             default:
-                launch<Item>(arena, b, OpT<3>{args...});
+                launch<Item>(fam, arena, b, OpT<3>{args...});
                 break;
         }
     }
@@ -313,11 +410,11 @@ namespace smr
     {
         if (radius == 0)
         {
-            launch_dim<PredOp0, smr_item_pred>(dim, arena, b, src, dst);
+            launch_dim<PredOp0, smr_item_pred>(SMR_FAM_PRED, dim, arena, b, src, dst);
         }
         else
         {
-            launch_dim<PredOp1, smr_item_pred>(dim, arena, b, src, dst);
+            launch_dim<PredOp1, smr_item_pred>(SMR_FAM_PRED, dim, arena, b, src, dst);
         }
     }
 
@@ -346,7 +443,7 @@ namespace smr
             const GhostPhase& ph = mo.plan.down[level];
             launch_bc(arena, ph.bc1, u, f.bc_type, f.bc_value);
             launch_bc(arena, ph.bc2, u, f.bc_type, f.bc_value);
-            launch_dim<ProjOp, smr_item_proj>(cfg.dim, arena, ph.proj, static_cast<const double*>(u), u);
+            launch_dim<ProjOp, smr_item_proj>(SMR_FAM_PROJ, cfg.dim, arena, ph.proj, static_cast<const double*>(u), u);
         }
         for (int level = 1; level <= cfg.max_level; ++level)
         {
@@ -369,6 +466,7 @@ namespace smr
         check_field_ready(in);
         check_field_ready(out);
         ensure_plan(mo);
+        Section sec;
         const MeshConfig& cfg = mo.mesh.cfg;
         if (burgers && cfg.dim != 2)
         {
@@ -391,11 +489,11 @@ namespace smr
         double* o       = static_cast<double*>(out.data.p);
         if (burgers)
         {
-            launch_dim<BurgersOp, smr_item_fv>(cfg.dim, mo.d_arena.p, mo.plan.fv, u, o, p);
+            launch_dim<BurgersOp, smr_item_fv>(SMR_FAM_FV, cfg.dim, mo.d_arena.p, mo.plan.fv, u, o, p);
         }
         else
         {
-            launch_dim<UpwindOp, smr_item_fv>(cfg.dim, mo.d_arena.p, mo.plan.fv, u, o, p);
+            launch_dim<UpwindOp, smr_item_fv>(SMR_FAM_FV, cfg.dim, mo.d_arena.p, mo.plan.fv, u, o, p);
         }
     }
 
@@ -416,6 +514,7 @@ namespace smr
             check_field_ready(*f);
         }
         ensure_plan(mo);
+        Section sec1;
         const int64_t n = mo.mesh.nref;
         mo.d_detail.ensure(static_cast<size_t>(n) * sizeof(double) * ncomp);
         mo.d_tag.ensure(static_cast<size_t>(n));
@@ -424,7 +523,7 @@ namespace smr
         uint8_t* tag      = static_cast<uint8_t*>(mo.d_tag.p);
         double* detail    = static_cast<double*>(mo.d_detail.p);
         const void* arena = mo.d_arena.p;
-        launch<smr_item_fv>(arena, mo.plan.fv, KeepLeavesOp{tag});
+        launch<smr_item_fv>(SMR_FAM_KEEP, arena, mo.plan.fv, KeepLeavesOp{tag});
         for (auto* f : fields)
         {
             do_update_ghost(*f);
@@ -436,11 +535,11 @@ namespace smr
                 const double* u = static_cast<const double*>(fields[c]->data.p);
                 if (cfg.pred_radius == 0)
                 {
-                    launch_dim<DetailOp0, smr_item_detail>(dim, arena, mo.plan.detail[level], u, detail + c * n);
+                    launch_dim<DetailOp0, smr_item_detail>(SMR_FAM_DETAIL, dim, arena, mo.plan.detail[level], u, detail + c * n);
                 }
                 else
                 {
-                    launch_dim<DetailOp1, smr_item_detail>(dim, arena, mo.plan.detail[level], u, detail + c * n);
+                    launch_dim<DetailOp1, smr_item_detail>(SMR_FAM_DETAIL, dim, arena, mo.plan.detail[level], u, detail + c * n);
                 }
             }
         }
@@ -470,22 +569,23 @@ namespace smr
             switch (dim)
             {
                 case 1:
-                    launch<smr_item_tag>(arena, mo.plan.tag[level], CriteriaOp<1>{detail, tag, tp, ncomp, n});
+                    launch<smr_item_tag>(SMR_FAM_CRITERIA, arena, mo.plan.tag[level], CriteriaOp<1>{detail, tag, tp, ncomp, n});
                     break;
                 case 2:
-                    launch<smr_item_tag>(arena, mo.plan.tag[level], CriteriaOp<2>{detail, tag, tp, ncomp, n});
+                    launch<smr_item_tag>(SMR_FAM_CRITERIA, arena, mo.plan.tag[level], CriteriaOp<2>{detail, tag, tp, ncomp, n});
                     break;
                 default:
-                    launch<smr_item_tag>(arena, mo.plan.tag[level], CriteriaOp<3>{detail, tag, tp, ncomp, n});
+                    launch<smr_item_tag>(SMR_FAM_CRITERIA, arena, mo.plan.tag[level], CriteriaOp<3>{detail, tag, tp, ncomp, n});
                     break;
             }
         }
         for (int level = L; level >= 1; --level)
         {
-            launch_dim<MaximumOp, smr_item_tag>(dim, arena, mo.plan.tag[level], tag);
+            launch_dim<MaximumOp, smr_item_tag>(SMR_FAM_MAXIMUM, dim, arena, mo.plan.tag[level], tag);
         }
         mo.h_tag.ensure(static_cast<size_t>(n));
         SMR_CUDA(cudaMemcpyAsync(mo.h_tag.p, tag, static_cast<size_t>(n), cudaMemcpyDeviceToHost, g.stream));
+        sec1.close();
         SMR_CUDA(cudaStreamSynchronize(g.stream));
         g.stats.d2h_bytes += static_cast<uint64_t>(n);
         mo.last_size  = n;
@@ -514,6 +614,7 @@ namespace smr
         g.stats.host_batch_seconds += now() - t0;
         DevBuf d_tr;
         PinnedBuf h_tr;
+        Section sec2;
         upload_arena(tpn.arena, d_tr, h_tr);
         const int64_t nn = new_mesh->nref;
         std::vector<std::unique_ptr<DevBuf>> fresh;
@@ -524,11 +625,12 @@ namespace smr
             SMR_CUDA(cudaMemsetAsync(nb->p, 0, static_cast<size_t>(nn) * sizeof(double), g.stream));
             const double* src = static_cast<const double*>(f->data.p);
             double* dst       = static_cast<double*>(nb->p);
-            launch<smr_item_copy>(d_tr.p, tpn.copy, CopyOp{src, dst});
-            launch_dim<ProjOp, smr_item_proj>(dim, d_tr.p, tpn.proj, src, dst);
+            launch<smr_item_copy>(SMR_FAM_COPY, d_tr.p, tpn.copy, CopyOp{src, dst});
+            launch_dim<ProjOp, smr_item_proj>(SMR_FAM_PROJ, dim, d_tr.p, tpn.proj, src, dst);
             launch_pred(dim, cfg.pred_radius, d_tr.p, tpn.pred, src, dst);
             fresh.push_back(std::move(nb));
         }
+        sec2.close();
         SMR_CUDA(cudaStreamSynchronize(g.stream)); // transfer arena and old buffers are released below
         for (size_t i = 0; i < fields.size(); ++i)
         {
@@ -992,7 +1094,10 @@ extern "C"
             [&]
             {
                 require_device();
-                do_update_ghost(get_field(fh));
+                FieldObj& f = get_field(fh);
+                ensure_plan(*f.mesh);
+                Section sec;
+                do_update_ghost(f);
             });
     }
 
@@ -1137,13 +1242,91 @@ extern "C"
 
     int smr_stats_get(smr_stats* out)
     {
-        *out = g.stats;
-        return SMR_OK;
+        return guarded(
+            [&]
+            {
+                resolve_sections();
+                *out = g.stats;
+            });
     }
 
     int smr_stats_reset(void)
     {
-        g.stats = smr_stats{};
+        return guarded(
+            [&]
+            {
+                resolve_sections();
+                g.stats = smr_stats{};
+            });
+    }
+
+    int smr_profile_enable(int on)
+    {
+        g.profile = on != 0;
+        for (int f = 0; f < SMR_FAM_COUNT; ++f)
+        {
+            g.prof_seconds[f]  = 0;
+            g.prof_launches[f] = 0;
+            g.prof_cells[f]    = 0;
+        }
         return SMR_OK;
+    }
+
+    int smr_profile_get(int family, uint64_t* launches, double* seconds, uint64_t* cells)
+    {
+        return guarded(
+            [&]
+            {
+                if (family < 0 || family >= SMR_FAM_COUNT)
+                {
+                    throw std::invalid_argument("invalid kernel family");
+                }
+                *launches = g.prof_launches[family];
+                *seconds  = g.prof_seconds[family];
+                *cells    = g.prof_cells[family];
+            });
+    }
+
+    int smr_field_init_ball(smr_field_t fh, const double* center, double radius, double inside, double outside, int overwrite_outside)
+    {
+        return guarded(
+            [&]
+            {
+                require_device();
+                FieldObj& f = get_field(fh);
+                check_field_ready(f);
+                MeshObj& mo = *f.mesh;
+                ensure_plan(mo);
+                Section sec;
+                const MeshConfig& cfg = mo.mesh.cfg;
+                double* u             = static_cast<double*>(f.data.p);
+                auto run              = [&](auto op)
+                {
+                    op.u = u;
+                    for (int d = 0; d < 3; ++d)
+                    {
+                        op.origin[d] = cfg.origin[d];
+                        op.center[d] = d < cfg.dim ? center[d] : 0.0;
+                    }
+                    op.scaling           = cfg.scaling;
+                    op.radius            = radius;
+                    op.inside            = inside;
+                    op.outside           = outside;
+                    op.overwrite_outside = overwrite_outside != 0;
+                    launch<smr_item_fv>(SMR_FAM_INIT, mo.d_arena.p, mo.plan.fv, op);
+                };
+                switch (cfg.dim)
+                {
+                    case 1:
+                        run(InitBallOp<1>{});
+                        break;
+                    case 2:
+                        run(InitBallOp<2>{});
+                        break;
+                    default:
+                        run(InitBallOp<3>{});
+                        break;
+                }
+            });
     }
 }

@@ -16,6 +16,22 @@
 #define SMR_CTA_CELLS (SMR_CTA_THREADS * SMR_CELLS_PER_THREAD)
 #define SMR_MAX_LEVELS 24
 
+/* kernel families, for the per-family profile (smr_profile_get) */
+enum
+{
+    SMR_FAM_FV = 0,
+    SMR_FAM_PROJ,
+    SMR_FAM_PRED,
+    SMR_FAM_DETAIL,
+    SMR_FAM_CRITERIA,
+    SMR_FAM_MAXIMUM,
+    SMR_FAM_BC,
+    SMR_FAM_COPY,
+    SMR_FAM_KEEP,
+    SMR_FAM_INIT,
+    SMR_FAM_COUNT
+};
+
 /* leaf interval for the FV field-expression kernels (stencil_field.hpp) */
 typedef struct
 {
@@ -24,6 +40,8 @@ typedef struct
     int64_t zm, zp; /* same x, rows k-1 / k+1 (3D) */
     int32_t n;
     int32_t level;
+    int32_t x, y, z; /* integer coordinates of the first cell (cell.hpp:32-77) */
+    int32_t pad;
 } smr_item_fv;
 
 /* coarse interval filled by projection (numeric/projection.hpp:22-64) */

@@ -417,6 +417,43 @@ namespace smr
         }
     };
 
+    // u[cell] = (|center - c|^2 <= r^2) ? inside : outside   -- the demos' initial condition
+    // (demos/FiniteVolume/advection_2d.cpp:23-45, advection_3d.cpp:32-45, scalar_burgers_2d.cpp:20-50)
+    template <int DIM>
+    struct InitBallOp
+    {
+        double* __restrict__ u;
+        double origin[3];
+        double scaling;
+        double center[3];
+        double radius;
+        double inside;
+        bool overwrite_outside;
+        double outside;
+
+        __device__ __forceinline__ void operator()(const smr_item_fv& it, int k) const
+        {
+            const double length = scaling / static_cast<double>(1 << it.level); // cell.hpp:16-20
+            const int idx[3]    = {it.x + k, it.y, it.z};
+            double r2           = 0.0;
+#pragma unroll
+            for (int d = 0; d < DIM; ++d)
+            {
+                const double c = origin[d] + length * (idx[d] + 0.5); // Cell::center, cell.hpp:131-134
+                const double t = (c - center[d]) * (c - center[d]);
+                r2             = d == 0 ? t : r2 + t;
+            }
+            if (r2 <= radius * radius)
+            {
+                u[it.c + k] = inside;
+            }
+            else if (overwrite_outside)
+            {
+                u[it.c + k] = outside;
+            }
+        }
+    };
+
     struct CopyOp
     {
         const double* __restrict__ src;
