@@ -140,6 +140,7 @@ extern "C"
         double host_batch_seconds; /* set-algebra traversal into index batches                                      */
         uint64_t mesh_rebuilds;
         double device_seconds;     /* CUDA-event time of every stretch of device work (kernels + async copies)      */
+        uint64_t ghost_updates_skipped; /* smr_update_ghost_mr calls answered by the ghosts_updated flag            */
     } smr_stats;
 
     int smr_stats_get(smr_stats* out); /* synchronises the stream to resolve device_seconds */
@@ -150,6 +151,10 @@ extern "C"
      * 3 detail, 4 criteria, 5 maximum, 6 bc, 7 copy, 8 keep, 9 init. */
     int smr_profile_enable(int on);
     int smr_profile_get(int family, uint64_t* launches, double* seconds, uint64_t* cells);
+
+    /* host-side profiling aid: rebuild the sub-meshes and the index batches of the current leaves `reps` times
+     * (no device work) and report the mean seconds of each stage */
+    int smr_debug_host_rebuild(smr_mesh_t m, int reps, double* mesh_seconds, double* plan_seconds, int64_t* arena_bytes);
 
     /* the demos' initial condition as a device kernel over the leaves: u = inside where |center(cell) - c|^2 <= r^2,
      * else outside (only written when overwrite_outside != 0)

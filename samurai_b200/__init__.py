@@ -53,6 +53,7 @@ class StatsC(C.Structure):
         ("host_batch_seconds", C.c_double),
         ("mesh_rebuilds", C.c_uint64),
         ("device_seconds", C.c_double),
+        ("ghost_updates_skipped", C.c_uint64),
     ]
 
 
@@ -95,6 +96,7 @@ SYMBOLS = {
     "smr_adapt_last_detail": [_u64, _vp, _i64],
     "smr_stats_get": [_P(StatsC)],
     "smr_stats_reset": [],
+    "smr_debug_host_rebuild": [_u64, _i32, _P(_dbl), _P(_dbl), _P(_i64)],
     "smr_profile_enable": [_i32],
     "smr_profile_get": [_i32, _P(_u64), _P(_dbl), _P(_u64)],
     "smr_field_init_ball": [_u64, _vp, _dbl, _dbl, _dbl, _i32],
@@ -311,6 +313,11 @@ class MRMesh:
         out = C.c_int64()
         _check(load_library().smr_mesh_get_index(self._h, level, i, j, k, C.byref(out)))
         return out.value
+
+    def debug_host_rebuild(self, reps=3):
+        a, b, n = C.c_double(), C.c_double(), C.c_int64()
+        _check(load_library().smr_debug_host_rebuild(self._h, reps, C.byref(a), C.byref(b), C.byref(n)))
+        return a.value, b.value, n.value
 
     def update_from_tags(self, tags):
         tags = np.ascontiguousarray(tags, dtype=np.uint8)

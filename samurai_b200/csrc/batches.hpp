@@ -11,8 +11,14 @@
 #include "items.h"
 #include "mesh.hpp"
 
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <new>
 #include <string>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 namespace smr
 {
@@ -43,51 +49,156 @@ namespace smr
         }
     };
 
+    // Host staging buffer for all batches of one plan.  Allocation goes through alloc_fn/free_fn so the C ABI can make
+    // it pinned memory (one cudaMemcpyAsync uploads the whole plan without an intermediate copy).
     struct Arena
     {
-        std::vector<uint8_t> bytes;
+        uint8_t* p  = nullptr;
+        size_t cap  = 0;
+        size_t size = 0;
 
-        template <class T>
-        int64_t push(const T* p, size_t n)
+        static inline void* (*alloc_fn)(size_t) = nullptr;
+        static inline void (*free_fn)(void*)    = nullptr;
+
+        Arena()                        = default;
+        Arena(const Arena&)            = delete;
+        Arena& operator=(const Arena&) = delete;
+
+        ~Arena()
         {
-            size_t off = (bytes.size() + 15) & ~size_t(15);
-            bytes.resize(off + n * sizeof(T));
-            if (n)
-            {
-                std::memcpy(bytes.data() + off, p, n * sizeof(T));
-            }
-            return static_cast<int64_t>(off);
+            release();
         }
 
-        template <class T>
-        int64_t push(const std::vector<T>& v)
+        void release()
         {
-            return push(v.data(), v.size());
+            if (p)
+            {
+                if (free_fn)
+                {
+                    free_fn(p);
+                }
+                else
+                {
+                    std::free(p);
+                }
+            }
+            p   = nullptr;
+            cap = 0;
+        }
+
+        void clear()
+        {
+            size = 0;
+        }
+
+        // layout pass: reserve `bytes` (16-byte aligned) and return their offset
+        size_t take(size_t bytes)
+        {
+            size             = (size + 15) & ~size_t(15);
+            const size_t off = size;
+            size += bytes;
+            return off;
+        }
+
+        // after the layout pass: make sure the memory exists
+        void commit()
+        {
+            if (size > cap)
+            {
+                release();
+                cap = size + size / 4 + 4096;
+                p   = static_cast<uint8_t*>(alloc_fn ? alloc_fn(cap) : std::malloc(cap));
+                if (!p)
+                {
+                    throw std::bad_alloc();
+                }
+            }
         }
     };
 
+    // A batch waiting to be laid out and written: the concatenation of `parts` (per-level record vectors).
     template <class Item>
-    inline Batch finish_batch(Arena& arena, int kind, const std::vector<Item>& items, int level = -1)
+    struct Pending
     {
-        Batch b;
-        b.kind    = kind;
-        b.level   = level;
-        b.n_items = static_cast<int>(items.size());
-        if (items.empty())
+        Batch* out = nullptr;
+        int kind   = -1;
+        int level  = -1;
+        std::vector<const std::vector<Item>*> parts;
+        std::vector<int64_t>* cum = nullptr; // optional per-part cumulative output-cell counts
+        bool inclusive            = false;
+    };
+
+    template <class Item>
+    inline void layout_batch(Pending<Item>& pd, Arena& arena)
+    {
+        Batch& b  = *pd.out;
+        b         = Batch();
+        b.kind    = pd.kind;
+        b.level   = pd.level;
+        size_t n  = 0;
+        int64_t c = 0;
+        if (pd.cum)
         {
-            return b;
+            pd.cum->assign(pd.parts.size() + 1, 0);
         }
-        std::vector<int64_t> prefix(items.size() + 1);
-        int64_t acc = 0;
-        for (size_t i = 0; i < items.size(); ++i)
+        for (size_t k = 0; k < pd.parts.size(); ++k)
         {
-            prefix[i] = acc;
-            acc += items[i].n;
+            if (pd.cum && !pd.inclusive)
+            {
+                (*pd.cum)[k] = c;
+            }
+            for (const Item& it : *pd.parts[k])
+            {
+                c += it.n;
+            }
+            n += pd.parts[k]->size();
+            if (pd.cum && pd.inclusive)
+            {
+                (*pd.cum)[k] = c;
+            }
         }
-        prefix[items.size()] = acc;
-        b.n_cells            = acc;
-        b.n_ctas             = static_cast<int>((acc + SMR_CTA_CELLS - 1) / SMR_CTA_CELLS);
-        std::vector<int32_t> first(b.n_ctas + 1);
+        if (pd.cum)
+        {
+            (*pd.cum)[pd.parts.size()] = c;
+        }
+        b.n_items = static_cast<int>(n);
+        if (n == 0)
+        {
+            return;
+        }
+        b.n_cells   = c;
+        b.n_ctas    = static_cast<int>((c + SMR_CTA_CELLS - 1) / SMR_CTA_CELLS);
+        b.items     = static_cast<int64_t>(arena.take(n * sizeof(Item)));
+        b.prefix    = static_cast<int64_t>(arena.take((n + 1) * sizeof(int64_t)));
+        b.cta_first = static_cast<int64_t>(arena.take((static_cast<size_t>(b.n_ctas) + 1) * sizeof(int32_t)));
+    }
+
+    template <class Item>
+    inline void fill_batch(const Pending<Item>& pd, Arena& arena)
+    {
+        const Batch& b = *pd.out;
+        if (b.n_items == 0)
+        {
+            return;
+        }
+        Item* items     = reinterpret_cast<Item*>(arena.p + b.items);
+        int64_t* prefix = reinterpret_cast<int64_t*>(arena.p + b.prefix);
+        int32_t* first  = reinterpret_cast<int32_t*>(arena.p + b.cta_first);
+        size_t i        = 0;
+        int64_t acc     = 0;
+        for (const auto* part : pd.parts)
+        {
+            if (!part->empty())
+            {
+                std::memcpy(items + i, part->data(), part->size() * sizeof(Item));
+            }
+            for (const Item& it : *part)
+            {
+                prefix[i++] = acc;
+                acc += it.n;
+            }
+        }
+        prefix[i] = acc;
         size_t it = 0;
         for (int c = 0; c < b.n_ctas; ++c)
         {
@@ -99,27 +210,45 @@ namespace smr
             first[c] = static_cast<int32_t>(it);
         }
         first[b.n_ctas] = b.n_items - 1;
-        b.items         = arena.push(items);
-        b.prefix        = arena.push(prefix);
-        b.cta_first     = arena.push(first);
-        return b;
     }
 
-    inline Batch finish_bc_batch(Arena& arena, const std::vector<smr_item_bc>& items, const std::vector<int64_t>& srcs, int level)
+    struct PendingBc
     {
-        Batch b;
+        Batch* out = nullptr;
+        int level  = -1;
+        const std::vector<smr_item_bc>* items = nullptr;
+        const std::vector<int64_t>* srcs      = nullptr;
+    };
+
+    inline void layout_bc(PendingBc& pd, Arena& arena)
+    {
+        Batch& b  = *pd.out;
+        b         = Batch();
         b.kind    = B_BC;
-        b.level   = level;
-        b.n_items = static_cast<int>(items.size());
-        if (items.empty())
+        b.level   = pd.level;
+        b.n_items = static_cast<int>(pd.items->size());
+        if (b.n_items == 0)
         {
-            return b;
+            return;
         }
         b.n_cells = b.n_items;
         b.n_ctas  = (b.n_items + SMR_CTA_THREADS - 1) / SMR_CTA_THREADS;
-        b.items   = arena.push(items);
-        b.aux     = arena.push(srcs);
-        return b;
+        b.items   = static_cast<int64_t>(arena.take(pd.items->size() * sizeof(smr_item_bc)));
+        b.aux     = static_cast<int64_t>(arena.take(pd.srcs->size() * sizeof(int64_t)));
+    }
+
+    inline void fill_bc(const PendingBc& pd, Arena& arena)
+    {
+        const Batch& b = *pd.out;
+        if (b.n_items == 0)
+        {
+            return;
+        }
+        std::memcpy(arena.p + b.items, pd.items->data(), pd.items->size() * sizeof(smr_item_bc));
+        if (!pd.srcs->empty())
+        {
+            std::memcpy(arena.p + b.aux, pd.srcs->data(), pd.srcs->size() * sizeof(int64_t));
+        }
     }
 
     [[noreturn]] inline void missing(const char* what, int level, int x, int y, int z)
@@ -138,43 +267,64 @@ namespace smr
         return o;
     }
 
+    // probe-based variant: rows are visited in increasing key order and x in increasing order inside a row
+    inline int64_t need(Probe& p, const char* what, int level, int y, int z, int x, int x_last)
+    {
+        const int64_t o = p.offset(x, x_last);
+        if (o < 0)
+        {
+            missing(what, level, x, y, z);
+        }
+        return o;
+    }
+
     // ---------------------------------------------------------------------------------------------------------
     // per-interval item builders
     // ---------------------------------------------------------------------------------------------------------
-    inline void fv_items(const Mesh& m, std::vector<smr_item_fv>& out)
+    inline void fv_items(const Mesh& m, int l, std::vector<smr_item_fv>& out)
     {
         const int dim = m.cfg.dim;
-        for (int l = 0; l < m.nlev; ++l)
+        const LevelSet& c   = m.cells[l];
+        const LevelSet& ref = m.ref[l];
+        Probe pc(ref), pym(ref), pyp(ref), pzm(ref), pzp(ref);
+        out.reserve(out.size() + c.n_intervals());
+        for (size_t r = 0; r < c.rows(); ++r)
         {
-            const LevelSet& c   = m.cells[l];
-            const LevelSet& ref = m.ref[l];
-            for (size_t r = 0; r < c.rows(); ++r)
+            const int y = key_y(c.key[r]), z = key_z(c.key[r]);
+            pc.seek(c.key[r]);
+            if (dim > 1)
             {
-                const int y = key_y(c.key[r]), z = key_z(c.key[r]);
-                for (int q = c.ptr[r]; q < c.ptr[r + 1]; ++q)
+                pym.seek(mk_key(y - 1, z));
+                pyp.seek(mk_key(y + 1, z));
+            }
+            if (dim > 2)
+            {
+                pzm.seek(mk_key(y, z - 1));
+                pzp.seek(mk_key(y, z + 1));
+            }
+            for (int q = c.ptr[r]; q < c.ptr[r + 1]; ++q)
+            {
+                const int s = c.xs[q], e = c.xe[q];
+                smr_item_fv it;
+                it.c  = need(pc, "fv x", l, y, z, s - 1, e) + 1;
+                it.ym = it.yp = it.zm = it.zp = it.c;
+                if (dim > 1)
                 {
-                    const int s = c.xs[q], e = c.xe[q];
-                    smr_item_fv it;
-                    it.c  = need(ref, "fv x", l, y, z, s - 1, e) + 1;
-                    it.ym = it.yp = it.zm = it.zp = it.c;
-                    if (dim > 1)
-                    {
-                        it.ym = need(ref, "fv y-1", l, y - 1, z, s, e - 1);
-                        it.yp = need(ref, "fv y+1", l, y + 1, z, s, e - 1);
-                    }
-                    if (dim > 2)
-                    {
-                        it.zm = need(ref, "fv z-1", l, y, z - 1, s, e - 1);
-                        it.zp = need(ref, "fv z+1", l, y, z + 1, s, e - 1);
-                    }
-                    it.n     = e - s;
-                    it.level = l;
-                    it.x     = s;
-                    it.y     = y;
-                    it.z     = z;
-                    it.pad   = 0;
-                    out.push_back(it);
+                    it.ym = need(pym, "fv y-1", l, y - 1, z, s, e - 1);
+                    it.yp = need(pyp, "fv y+1", l, y + 1, z, s, e - 1);
                 }
+                if (dim > 2)
+                {
+                    it.zm = need(pzm, "fv z-1", l, y, z - 1, s, e - 1);
+                    it.zp = need(pzp, "fv z+1", l, y, z + 1, s, e - 1);
+                }
+                it.n     = e - s;
+                it.level = l;
+                it.x     = s;
+                it.y     = y;
+                it.z     = z;
+                it.pad   = 0;
+                out.push_back(it);
             }
         }
     }
@@ -182,21 +332,35 @@ namespace smr
     // coarse set `cs` at level lc (dst offsets from dst_ref) <- children rows in src_ref (level lc+1)
     inline void proj_items(int dim, const LevelSet& cs, int lc, const LevelSet& dst_ref, const LevelSet& src_ref, std::vector<smr_item_proj>& out)
     {
+        Probe pd(dst_ref);
+        Probe ps[4] = {Probe(src_ref), Probe(src_ref), Probe(src_ref), Probe(src_ref)};
+        const int ny = dim > 1 ? 2 : 1, nz = dim > 2 ? 2 : 1;
+        out.reserve(out.size() + cs.n_intervals());
         for (size_t r = 0; r < cs.rows(); ++r)
         {
             const int y = key_y(cs.key[r]), z = key_z(cs.key[r]);
+            pd.seek(cs.key[r]);
+            for (int cz = 0; cz < nz; ++cz)
+            {
+                for (int cy = 0; cy < ny; ++cy)
+                {
+                    ps[cy + 2 * cz].seek(mk_key(dim > 1 ? 2 * y + cy : 0, dim > 2 ? 2 * z + cz : 0));
+                }
+            }
             for (int q = cs.ptr[r]; q < cs.ptr[r + 1]; ++q)
             {
                 const int s = cs.xs[q], e = cs.xe[q];
                 smr_item_proj it;
-                it.dst = need(dst_ref, "projection dst", lc, y, z, s, e - 1);
-                for (int cz = 0; cz < 2; ++cz)
+                it.dst = need(pd, "projection dst", lc, y, z, s, e - 1);
+                for (int k = 0; k < 4; ++k)
                 {
-                    for (int cy = 0; cy < 2; ++cy)
+                    it.src[k] = 0;
+                }
+                for (int cz = 0; cz < nz; ++cz)
+                {
+                    for (int cy = 0; cy < ny; ++cy)
                     {
-                        const bool used = (dim > 1 || cy == 0) && (dim > 2 || cz == 0);
-                        it.src[cy + 2 * cz] = used ? need(src_ref, "projection src", lc + 1, dim > 1 ? 2 * y + cy : 0, dim > 2 ? 2 * z + cz : 0, 2 * s, 2 * e - 1)
-                                                   : 0;
+                        it.src[cy + 2 * cz] = need(ps[cy + 2 * cz], "projection src", lc + 1, 2 * y + cy, 2 * z + cz, 2 * s, 2 * e - 1);
                     }
                 }
                 it.n   = e - s;
@@ -206,27 +370,74 @@ namespace smr
         }
     }
 
-    // fine interval [s, e) at level lf, row (y, z): predicted from src_ref (level lf-1)
-    inline void pred_item(int dim, int radius, int lf, int y, int z, int s, int e, int64_t dst, const LevelSet& src_ref, std::vector<smr_item_pred>& out)
+    // Fine set `fs` at level lf (must carry .off = destination offsets) predicted from src_ref (level lf-1).
+    struct PredBuilder
     {
-        smr_item_pred it;
-        it.dst = dst;
-        it.n   = e - s;
-        it.par = (s & 1) | ((dim > 1 ? (y & 1) : 0) << 1) | ((dim > 2 ? (z & 1) : 0) << 2);
-        const int yc = y >> 1, zc = z >> 1, sc = s >> 1, ec = (e - 1) >> 1;
-        const int ry_ = dim > 1 ? radius : 0, rz_ = dim > 2 ? radius : 0;
-        for (int k = 0; k < 9; ++k)
+        int dim, radius, lf;
+        Probe p[9];
+        int ry_, rz_;
+
+        PredBuilder(int dim_, int radius_, int lf_, const LevelSet& src_ref)
+            : dim(dim_)
+            , radius(radius_)
+            , lf(lf_)
         {
-            it.src[k] = 0;
-        }
-        for (int rz = -rz_; rz <= rz_; ++rz)
-        {
-            for (int ry = -ry_; ry <= ry_; ++ry)
+            for (auto& x : p)
             {
-                it.src[(ry + 1) + 3 * (rz + 1)] = need(src_ref, "prediction src", lf - 1, yc + ry, zc + rz, sc - radius, ec + radius) + radius;
+                x = Probe(src_ref);
+            }
+            ry_ = dim > 1 ? radius : 0;
+            rz_ = dim > 2 ? radius : 0;
+        }
+
+        void seek_row(int y, int z)
+        {
+            const int yc = y >> 1, zc = z >> 1;
+            for (int rz = -rz_; rz <= rz_; ++rz)
+            {
+                for (int ry = -ry_; ry <= ry_; ++ry)
+                {
+                    p[(ry + 1) + 3 * (rz + 1)].seek(mk_key(yc + ry, zc + rz));
+                }
             }
         }
-        out.push_back(it);
+
+        void add(int y, int z, int s, int e, int64_t dst, std::vector<smr_item_pred>& out)
+        {
+            smr_item_pred it;
+            it.dst = dst;
+            it.n   = e - s;
+            it.par = (s & 1) | ((dim > 1 ? (y & 1) : 0) << 1) | ((dim > 2 ? (z & 1) : 0) << 2);
+            const int sc = s >> 1, ec = (e - 1) >> 1;
+            for (int k = 0; k < 9; ++k)
+            {
+                it.src[k] = 0;
+            }
+            for (int rz = -rz_; rz <= rz_; ++rz)
+            {
+                for (int ry = -ry_; ry <= ry_; ++ry)
+                {
+                    const int k = (ry + 1) + 3 * (rz + 1);
+                    it.src[k]   = need(p[k], "prediction src", lf - 1, (y >> 1) + ry, (z >> 1) + rz, sc - radius, ec + radius) + radius;
+                }
+            }
+            out.push_back(it);
+        }
+    };
+
+    inline void pred_items(int dim, int radius, int lf, const LevelSet& fs, const LevelSet& src_ref, std::vector<smr_item_pred>& out)
+    {
+        PredBuilder pb(dim, radius, lf, src_ref);
+        out.reserve(out.size() + fs.n_intervals());
+        for (size_t r = 0; r < fs.rows(); ++r)
+        {
+            const int y = key_y(fs.key[r]), z = key_z(fs.key[r]);
+            pb.seek_row(y, z);
+            for (int q = fs.ptr[r]; q < fs.ptr[r + 1]; ++q)
+            {
+                pb.add(y, z, fs.xs[q], fs.xe[q], fs.off[q], out);
+            }
+        }
     }
 
     inline void detail_items(const Mesh& m, int level, const LevelSet& cs, std::vector<smr_item_detail>& out)
@@ -235,9 +446,34 @@ namespace smr
         const LevelSet& rc = m.ref[level];
         const LevelSet& rf = m.ref[level + 1];
         const int ry_ = dim > 1 ? radius : 0, rz_ = dim > 2 ? radius : 0;
+        const int ny = dim > 1 ? 2 : 1, nz = dim > 2 ? 2 : 1;
+        Probe pc[9], pf[4];
+        for (auto& x : pc)
+        {
+            x = Probe(rc);
+        }
+        for (auto& x : pf)
+        {
+            x = Probe(rf);
+        }
+        out.reserve(out.size() + cs.n_intervals());
         for (size_t r = 0; r < cs.rows(); ++r)
         {
             const int y = key_y(cs.key[r]), z = key_z(cs.key[r]);
+            for (int rz = -rz_; rz <= rz_; ++rz)
+            {
+                for (int ry = -ry_; ry <= ry_; ++ry)
+                {
+                    pc[(ry + 1) + 3 * (rz + 1)].seek(mk_key(y + ry, z + rz));
+                }
+            }
+            for (int cz = 0; cz < nz; ++cz)
+            {
+                for (int cy = 0; cy < ny; ++cy)
+                {
+                    pf[cy + 2 * cz].seek(mk_key(dim > 1 ? 2 * y + cy : 0, dim > 2 ? 2 * z + cz : 0));
+                }
+            }
             for (int q = cs.ptr[r]; q < cs.ptr[r + 1]; ++q)
             {
                 const int s = cs.xs[q], e = cs.xe[q];
@@ -247,14 +483,15 @@ namespace smr
                 {
                     for (int ry = -ry_; ry <= ry_; ++ry)
                     {
-                        it.coarse[(ry + 1) + 3 * (rz + 1)] = need(rc, "detail coarse", level, y + ry, z + rz, s - radius, e - 1 + radius) + radius;
+                        const int k  = (ry + 1) + 3 * (rz + 1);
+                        it.coarse[k] = need(pc[k], "detail coarse", level, y + ry, z + rz, s - radius, e - 1 + radius) + radius;
                     }
                 }
-                for (int cz = 0; cz < (dim > 2 ? 2 : 1); ++cz)
+                for (int cz = 0; cz < nz; ++cz)
                 {
-                    for (int cy = 0; cy < (dim > 1 ? 2 : 1); ++cy)
+                    for (int cy = 0; cy < ny; ++cy)
                     {
-                        it.fine[cy + 2 * cz] = need(rf, "detail fine", level + 1, dim > 1 ? 2 * y + cy : 0, dim > 2 ? 2 * z + cz : 0, 2 * s, 2 * e - 1);
+                        it.fine[cy + 2 * cz] = need(pf[cy + 2 * cz], "detail fine", level + 1, 2 * y + cy, 2 * z + cz, 2 * s, 2 * e - 1);
                     }
                 }
                 it.n = e - s;
@@ -268,20 +505,35 @@ namespace smr
         const int dim = m.cfg.dim;
         const LevelSet& rc = m.ref[fine_level - 1];
         const LevelSet& rf = m.ref[fine_level];
+        const int ny = dim > 1 ? 2 : 1, nz = dim > 2 ? 2 : 1;
+        Probe pc(rc), pf[4];
+        for (auto& x : pf)
+        {
+            x = Probe(rf);
+        }
+        out.reserve(out.size() + cs.n_intervals());
         for (size_t r = 0; r < cs.rows(); ++r)
         {
             const int y = key_y(cs.key[r]), z = key_z(cs.key[r]);
+            pc.seek(cs.key[r]);
+            for (int cz = 0; cz < nz; ++cz)
+            {
+                for (int cy = 0; cy < ny; ++cy)
+                {
+                    pf[cy + 2 * cz].seek(mk_key(dim > 1 ? 2 * y + cy : 0, dim > 2 ? 2 * z + cz : 0));
+                }
+            }
             for (int q = cs.ptr[r]; q < cs.ptr[r + 1]; ++q)
             {
                 const int s = cs.xs[q], e = cs.xe[q];
                 smr_item_tag it;
                 std::memset(&it, 0, sizeof(it));
-                it.coarse = need(rc, "tag coarse", fine_level - 1, y, z, s, e - 1);
-                for (int cz = 0; cz < (dim > 2 ? 2 : 1); ++cz)
+                it.coarse = need(pc, "tag coarse", fine_level - 1, y, z, s, e - 1);
+                for (int cz = 0; cz < nz; ++cz)
                 {
-                    for (int cy = 0; cy < (dim > 1 ? 2 : 1); ++cy)
+                    for (int cy = 0; cy < ny; ++cy)
                     {
-                        it.fine[cy + 2 * cz] = need(rf, "tag fine", fine_level, dim > 1 ? 2 * y + cy : 0, dim > 2 ? 2 * z + cz : 0, 2 * s, 2 * e - 1);
+                        it.fine[cy + 2 * cz] = need(pf[cy + 2 * cz], "tag fine", fine_level, 2 * y + cy, 2 * z + cz, 2 * s, 2 * e - 1);
                     }
                 }
                 it.n     = e - s;
@@ -337,21 +589,33 @@ namespace smr
     // ---------------------------------------------------------------------------------------------------------
     // the per-mesh plan
     // ---------------------------------------------------------------------------------------------------------
+    // Top-down sweep of update_ghost_mr, one fused launch per level (update_ghost_mr.hpp:204-222).  The reference
+    // runs, per level: corner extrapolation, project_corner_below, then per direction project_bc / apply_field_bc /
+    // predict_bc, then the projection to level-1.  Dependencies allow regrouping without changing any value:
+    //   * apply_field_bc reads leaves only; predict_bc(level+1) copies the ghost apply_field_bc(level) just wrote, so
+    //     both become direct "value" records sourced from the leaf (same arithmetic, same result);
+    //   * project_bc(level) reads outside ghosts of level+1/+2 written by earlier (finer) phases;
+    //   * project_corner_below(level+1) only feeds project_corner_below(level) and the corner ghost it writes at
+    //     `level` is overwritten by the corner extrapolation of `level` when that exists, so its records are folded
+    //     into phase `level` with the overwritten ones dropped;
+    //   * the projection chain never reads an outside ghost, so it shares the launch.
     struct GhostPhase
     {
-        Batch bc1;  // corner extrapolation + project_bc + apply_field_bc         (level)
-        Batch bc2;  // project_corner_below + predict_bc                           (level)
+        Batch bc;   // extrapolated corners(level) + corner copies from level+1 + project_bc(level) + BC values(level, level+1 children)
         Batch proj; // projection level -> level-1
     };
 
     struct MeshPlan
     {
         Arena arena;
-        Batch fv;                      // all leaves
-        std::vector<GhostPhase> down;  // indexed by level (top-down sweep uses L..0)
-        std::vector<Batch> pred;       // indexed by level (bottom-up sweep 1..L)
-        std::vector<Batch> detail;     // indexed by coarse level
-        std::vector<Batch> tag;        // indexed by fine level
+        Batch fv;                     // all leaves, level ascending
+        std::vector<GhostPhase> down; // indexed by level (top-down sweep uses L..0)
+        std::vector<Batch> pred;      // indexed by level (bottom-up sweep 1..L)
+        Batch detail;                 // all coarse levels, ascending
+        std::vector<int64_t> detail_cum; // detail_cum[k] = output cells of detail records with coarse level < k
+        Batch tag_all;                // criteria: all fine levels, ascending
+        std::vector<int64_t> tag_cum; // tag_cum[k] = output cells of tag records with fine level <= k
+        std::vector<Batch> tag;       // per fine level, for the sequential keep propagation
         double build_seconds = 0;
     };
 
@@ -441,134 +705,186 @@ namespace smr
         }
     }
 
-    inline void build_ghost_phase(const Mesh& m, int level, Arena& arena, GhostPhase& ph)
+    struct PhaseItems
     {
-        const MeshConfig& cfg = m.cfg;
-        const int dim = cfg.dim, L = cfg.max_level, lmin = cfg.min_level;
-        BcBuilder g1, g2;
-        const LevelSet& ref = m.ref[level];
-        if (ref.empty() && (level == 0 || m.ref[level - 1].empty()))
+        BcBuilder bc;
+        std::vector<smr_item_proj> proj;
+    };
+
+    // project_corner_below(src_level) (update_outer_ghost.hpp:267-336): copies of the corner ghost of src_level into
+    // the corner ghosts one (dl = 1) and two (dl = 2) levels below, where the corner-most child exists
+    template <class F>
+    inline void corner_below(const Mesh& m, int src_level, const Dir& d, F&& emit)
+    {
+        const int dim = m.cfg.dim;
+        if (src_level <= 0)
         {
             return;
         }
-        if (dim > 1 && level >= lmin && level <= L)
+        const LevelSet& ref       = m.ref[src_level];
+        const LevelSet corner     = corner_cells(m, src_level, d);
+        const LevelSet fine_outer = set_inter(translate(corner, d.v[0], d.v[1], d.v[2]), ref);
+        for (int dl = 1; dl <= 2; ++dl)
+        {
+            const int pl = src_level - dl;
+            LevelSet ghosts = set_inter(coarsen(fine_outer, dl, dim), m.ref[pl]);
+            const int add   = (1 << dl) - 1;
+            for_each_cell(ghosts,
+                          [&](int x, int y, int z)
+                          {
+                              const int cx = (x << dl) + (d.v[0] == -1 ? add : 0);
+                              const int cy = dim > 1 ? (y << dl) + (d.v[1] == -1 ? add : 0) : 0;
+                              const int cz = dim > 2 ? (z << dl) + (d.v[2] == -1 ? add : 0) : 0;
+                              const int64_t src = ref.offset_of(mk_key(cy, cz), cx, cx);
+                              if (src >= 0)
+                              {
+                                  emit(pl, need(m.ref[pl], "corner below", pl, y, z, x, x), src);
+                              }
+                          });
+            if (pl == 0)
+            {
+                break;
+            }
+        }
+    }
+
+    inline void build_ghost_phase(const Mesh& m, int level, PhaseItems& out)
+    {
+        const MeshConfig& cfg = m.cfg;
+        const int dim = cfg.dim, L = cfg.max_level, lmin = cfg.min_level;
+        BcBuilder& g          = out.bc;
+        const LevelSet& ref   = m.ref[level];
+        const bool have_below = level > 0 && !m.ref[level - 1].empty();
+        if (ref.empty() && !have_below)
+        {
+            return;
+        }
+        std::vector<int64_t> extrap_dst;
+        if (dim > 1)
         {
             for (const Dir& d : diagonal_directions(dim))
             {
-                const LevelSet corner = corner_cells(m, level, d);
-                // update_outer_corners_by_polynomial_extrapolation, ghost width 1: u[c + d] = u[c]
-                LevelSet cc = set_inter(m.cells[level], corner);
-                for_each_cell(cc,
-                              [&](int x, int y, int z)
-                              {
-                                  g1.copy(need(ref, "corner ghost", level, y + d.v[1], z + d.v[2], x + d.v[0], x + d.v[0]),
-                                          need(ref, "corner cell", level, y, z, x, x));
-                              });
-                // project_corner_below
-                if (level > 0)
+                if (level >= lmin && level <= L && !ref.empty())
                 {
-                    const LevelSet fine_outer = set_inter(translate(corner, d.v[0], d.v[1], d.v[2]), ref);
-                    for (int dl = 1; dl <= 2; ++dl)
-                    {
-                        const int pl = level - dl;
-                        LevelSet ghosts = set_inter(coarsen(fine_outer, dl, dim), m.ref[pl]);
-                        const int add   = (1 << dl) - 1;
-                        for_each_cell(ghosts,
-                                      [&](int x, int y, int z)
-                                      {
-                                          const int cx = (x << dl) + (d.v[0] == -1 ? add : 0);
-                                          const int cy = dim > 1 ? (y << dl) + (d.v[1] == -1 ? add : 0) : 0;
-                                          const int cz = dim > 2 ? (z << dl) + (d.v[2] == -1 ? add : 0) : 0;
-                                          const int64_t src = ref.offset_of(mk_key(cy, cz), cx, cx);
-                                          if (src >= 0)
-                                          {
-                                              g2.copy(need(m.ref[pl], "corner below", pl, y, z, x, x), src);
-                                          }
-                                      });
-                        if (pl == 0)
-                        {
-                            break;
-                        }
-                    }
+                    // update_outer_corners_by_polynomial_extrapolation, ghost width 1: u[c + d] = u[c]
+                    LevelSet cc = set_inter(m.cells[level], corner_cells(m, level, d));
+                    for_each_cell(cc,
+                                  [&](int x, int y, int z)
+                                  {
+                                      const int64_t dst = need(ref, "corner ghost", level, y + d.v[1], z + d.v[2], x + d.v[0], x + d.v[0]);
+                                      g.copy(dst, need(ref, "corner cell", level, y, z, x, x));
+                                      extrap_dst.push_back(dst);
+                                  });
+                }
+            }
+            std::sort(extrap_dst.begin(), extrap_dst.end());
+            for (const Dir& d : diagonal_directions(dim))
+            {
+                // records of project_corner_below(level + 1): written in this phase, after phase level+1 produced their source
+                if (level + 1 >= lmin && level + 1 <= L)
+                {
+                    corner_below(m,
+                                 level + 1,
+                                 d,
+                                 [&](int pl, int64_t dst, int64_t src)
+                                 {
+                                     if (pl == level && std::binary_search(extrap_dst.begin(), extrap_dst.end(), dst))
+                                     {
+                                         return; // overwritten by the extrapolation of this level before anything reads it
+                                     }
+                                     g.copy(dst, src);
+                                 });
                 }
             }
         }
         for (const Dir& d : cartesian_directions(dim))
         {
-            if (level < L)
+            if (level < L && !ref.empty())
             {
                 // project_bc, layer 1
                 LevelSet ghosts = set_inter(m.outside_domain(translate(m.uni[level], d.v[0], d.v[1], d.v[2]), level), ref);
-                for_each_cell(ghosts,
-                              [&](int x, int y, int z)
-                              {
-                                  g1.begin_avg(need(ref, "project_bc ghost", level, y, z, x, x));
-                                  for (int dl = 1; dl <= 2; ++dl)
-                                  {
-                                      const LevelSet& rf = m.ref[level + dl];
-                                      const int n        = 1 << dl;
-                                      for (int cz = 0; cz < (dim > 2 ? n : 1); ++cz)
-                                      {
-                                          for (int cy = 0; cy < (dim > 1 ? n : 1); ++cy)
-                                          {
-                                              for (int cx = 0; cx < n; ++cx)
-                                              {
-                                                  const int64_t o = rf.offset_of(mk_key(dim > 1 ? (y << dl) + cy : 0, dim > 2 ? (z << dl) + cz : 0),
-                                                                                 (x << dl) + cx,
-                                                                                 (x << dl) + cx);
-                                                  if (o >= 0)
-                                                  {
-                                                      g1.add_src(o);
-                                                  }
-                                              }
-                                          }
-                                      }
-                                      if (g1.items.back().n_src > 0)
-                                      {
-                                          break;
-                                      }
-                                  }
-                              });
-            }
-            LevelSet bl;
-            if (level >= lmin)
-            {
-                bl = boundary_leaves(m, level, d);
-                const double dx = cfg.cell_length(level);
-                for_each_cell(bl,
-                              [&](int x, int y, int z)
-                              {
-                                  g1.value(need(ref, "bc ghost", level, y + d.v[1], z + d.v[2], x + d.v[0], x + d.v[0]),
-                                           need(ref, "bc cell", level, y, z, x, x),
-                                           dx);
-                              });
-            }
-            if (level >= lmin && level < L && !bl.empty())
-            {
-                // predict_bc(level + 1): children of the BC ghosts present in reference[level+1]
-                LevelSet fine = set_inter(refine(translate(bl, d.v[0], d.v[1], d.v[2]), 1, dim), m.ref[level + 1]);
-                locate(fine, m.ref[level + 1]);
-                for (size_t r = 0; r < fine.rows(); ++r)
+                locate(ghosts, ref);
+                for (size_t r = 0; r < ghosts.rows(); ++r)
                 {
-                    const int y = key_y(fine.key[r]), z = key_z(fine.key[r]);
-                    for (int q = fine.ptr[r]; q < fine.ptr[r + 1]; ++q)
+                    const int y = key_y(ghosts.key[r]), z = key_z(ghosts.key[r]);
+                    for (int q = ghosts.ptr[r]; q < ghosts.ptr[r + 1]; ++q)
                     {
-                        for (int x = fine.xs[q]; x < fine.xe[q]; ++x)
+                        for (int x = ghosts.xs[q]; x < ghosts.xe[q]; ++x)
                         {
-                            g2.copy(fine.off[q] + (x - fine.xs[q]), need(ref, "predict_bc parent", level, y >> 1, z >> 1, x >> 1, x >> 1));
+                            g.begin_avg(ghosts.off[q] + (x - ghosts.xs[q]));
+                            for (int dl = 1; dl <= 2; ++dl)
+                            {
+                                const LevelSet& rf = m.ref[level + dl];
+                                const int n        = 1 << dl;
+                                for (int cz = 0; cz < (dim > 2 ? n : 1); ++cz)
+                                {
+                                    for (int cy = 0; cy < (dim > 1 ? n : 1); ++cy)
+                                    {
+                                        const int row = rf.find_row(mk_key(dim > 1 ? (y << dl) + cy : 0, dim > 2 ? (z << dl) + cz : 0));
+                                        if (row < 0)
+                                        {
+                                            continue;
+                                        }
+                                        for (int cx = 0; cx < n; ++cx)
+                                        {
+                                            const int i = rf.find_ivl(row, (x << dl) + cx);
+                                            if (i >= 0)
+                                            {
+                                                g.add_src(rf.off[i] + ((x << dl) + cx - rf.xs[i]));
+                                            }
+                                        }
+                                    }
+                                }
+                                if (g.items.back().n_src > 0)
+                                {
+                                    break;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            if (level >= lmin && !ref.empty())
+            {
+                // apply_field_bc(level) and, folded in, predict_bc(level + 1)
+                LevelSet bl     = boundary_leaves(m, level, d);
+                const double dx = cfg.cell_length(level);
+                locate(bl, ref);
+                LevelSet gh = translate(bl, d.v[0], d.v[1], d.v[2]);
+                locate(gh, ref);
+                for (size_t q = 0; q < bl.xs.size(); ++q)
+                {
+                    for (int k = 0; k < bl.xe[q] - bl.xs[q]; ++k)
+                    {
+                        g.value(gh.off[q] + k, bl.off[q] + k, dx);
+                    }
+                }
+                if (level < L && !bl.empty())
+                {
+                    LevelSet fine = set_inter(refine(gh, 1, dim), m.ref[level + 1]);
+                    locate(fine, m.ref[level + 1]);
+                    Probe pl(bl);
+                    for (size_t r = 0; r < fine.rows(); ++r)
+                    {
+                        const int y = key_y(fine.key[r]), z = key_z(fine.key[r]);
+                        // the leaf behind the parent ghost: parent - d
+                        pl.seek(mk_key((y >> 1) - d.v[1], (z >> 1) - d.v[2]));
+                        for (int q = fine.ptr[r]; q < fine.ptr[r + 1]; ++q)
+                        {
+                            for (int x = fine.xs[q]; x < fine.xe[q]; ++x)
+                            {
+                                const int lx = (x >> 1) - d.v[0];
+                                g.value(fine.off[q] + (x - fine.xs[q]), need(pl, "predict_bc leaf", level, (y >> 1) - d.v[1], (z >> 1) - d.v[2], lx, lx), dx);
+                            }
                         }
                     }
                 }
             }
         }
-        ph.bc1 = finish_bc_batch(arena, g1.items, g1.srcs, level);
-        ph.bc2 = finish_bc_batch(arena, g2.items, g2.srcs, level);
-        if (level > 0)
+        if (level > 0 && !ref.empty())
         {
             LevelSet ps = set_inter(coarsen(ref, 1, dim), m.proj[level - 1]);
-            std::vector<smr_item_proj> items;
-            proj_items(dim, ps, level - 1, m.ref[level - 1], ref, items);
-            ph.proj = finish_batch(arena, B_PROJ, items, level);
+            proj_items(dim, ps, level - 1, m.ref[level - 1], ref, out.proj);
         }
     }
 
@@ -607,54 +923,161 @@ namespace smr
     {
         const MeshConfig& cfg = m.cfg;
         const int dim = cfg.dim, L = cfg.max_level, lmin = cfg.min_level;
-        plan.arena.bytes.clear();
+        const int nlev = m.nlev;
+        plan.arena.clear();
+        std::vector<std::vector<smr_item_fv>> fv(nlev);
+        std::vector<PhaseItems> phases(nlev);
+        std::vector<std::vector<smr_item_pred>> pred(nlev);
+        std::vector<std::vector<smr_item_detail>> detail(nlev);
+        std::vector<std::vector<smr_item_tag>> tag(nlev);
+        std::string error;
+#ifdef SMR_PLAN_TIMING
+        const double tt0 = omp_get_wtime();
+        std::vector<double> task_t(5 * nlev, 0.0);
+#endif
+        // one task per (kind, level): levels are independent once the mesh exists
+        const int ntasks = 5 * nlev;
+#pragma omp parallel for schedule(dynamic, 1)
+        for (int t = ntasks - 1; t >= 0; --t)
         {
-            std::vector<smr_item_fv> items;
-            fv_items(m, items);
-            plan.fv = finish_batch(plan.arena, B_FV, items);
-        }
-        plan.down.assign(m.nlev, GhostPhase());
-        plan.pred.assign(m.nlev, Batch());
-        plan.detail.assign(m.nlev, Batch());
-        plan.tag.assign(m.nlev, Batch());
-        for (int level = L; level >= 0; --level)
-        {
-            build_ghost_phase(m, level, plan.arena, plan.down[level]);
-        }
-        for (int level = 1; level <= L; ++level)
-        {
-            LevelSet ps = prediction_set(m, level);
-            if (ps.empty())
+            const int kind = t / nlev, level = t % nlev;
+#ifdef SMR_PLAN_TIMING
+            const double tk0 = omp_get_wtime();
+#endif
+            try
             {
-                continue;
-            }
-            locate(ps, m.ref[level]);
-            std::vector<smr_item_pred> items;
-            for (size_t r = 0; r < ps.rows(); ++r)
-            {
-                const int y = key_y(ps.key[r]), z = key_z(ps.key[r]);
-                for (int q = ps.ptr[r]; q < ps.ptr[r + 1]; ++q)
+                switch (kind)
                 {
-                    pred_item(dim, cfg.pred_radius, level, y, z, ps.xs[q], ps.xe[q], ps.off[q], m.ref[level - 1], items);
+                    case 4:
+                        if (!m.cells[level].empty())
+                        {
+                            fv_items(m, level, fv[level]);
+                        }
+                        break;
+                    case 3:
+                        if (level <= L)
+                        {
+                            build_ghost_phase(m, level, phases[level]);
+                        }
+                        break;
+                    case 2:
+                        if (level >= 1 && level <= L)
+                        {
+                            LevelSet ps = prediction_set(m, level);
+                            if (!ps.empty())
+                            {
+                                locate(ps, m.ref[level]);
+                                pred_items(dim, cfg.pred_radius, level, ps, m.ref[level - 1], pred[level]);
+                            }
+                        }
+                        break;
+                    case 1:
+                        if (lmin != L && level >= std::max(lmin - 1, 0) && level < L)
+                        {
+                            detail_items(m, level, detail_set(m, level), detail[level]);
+                        }
+                        break;
+                    default:
+                        if (lmin != L && level >= std::max(lmin, 1) && level <= L)
+                        {
+                            tag_items(m, level, tag_set(m, level), tag[level]);
+                        }
+                        break;
                 }
             }
-            plan.pred[level] = finish_batch(plan.arena, B_PRED, items, level);
+            catch (const std::exception& e)
+            {
+#pragma omp critical
+                error = e.what();
+            }
+#ifdef SMR_PLAN_TIMING
+            task_t[t] = omp_get_wtime() - tk0;
+#endif
         }
-        if (lmin != L)
+        if (!error.empty())
         {
-            for (int level = std::max(lmin - 1, 0); level < L; ++level)
+            throw std::out_of_range(error);
+        }
+#ifdef SMR_PLAN_TIMING
+        const double tt1 = omp_get_wtime();
+        for (int t = 0; t < ntasks; ++t)
+        {
+            if (task_t[t] > 2e-4)
             {
-                std::vector<smr_item_detail> items;
-                detail_items(m, level, detail_set(m, level), items);
-                plan.detail[level] = finish_batch(plan.arena, B_DETAIL, items, level);
-            }
-            for (int level = std::max(lmin, 1); level <= L; ++level)
-            {
-                std::vector<smr_item_tag> items;
-                tag_items(m, level, tag_set(m, level), items);
-                plan.tag[level] = finish_batch(plan.arena, B_TAG, items, level);
+                std::printf("  task kind %d level %d: %.2f ms\n", t / nlev, t % nlev, task_t[t] * 1e3);
             }
         }
+#endif
+        plan.down.assign(nlev, GhostPhase());
+        plan.pred.assign(nlev, Batch());
+        plan.tag.assign(nlev, Batch());
+        // layout (serial, cheap) then fill (parallel) straight into the staging arena
+        Pending<smr_item_fv> p_fv{&plan.fv, B_FV, -1, {}, nullptr, false};
+        Pending<smr_item_detail> p_detail{&plan.detail, B_DETAIL, -1, {}, &plan.detail_cum, false};
+        Pending<smr_item_tag> p_tag_all{&plan.tag_all, B_TAG, -1, {}, &plan.tag_cum, true};
+        std::vector<Pending<smr_item_proj>> p_proj(nlev);
+        std::vector<Pending<smr_item_pred>> p_pred(nlev);
+        std::vector<Pending<smr_item_tag>> p_tag(nlev);
+        std::vector<PendingBc> p_bc(nlev);
+        for (int l = 0; l < nlev; ++l)
+        {
+            p_fv.parts.push_back(&fv[l]);
+            p_detail.parts.push_back(&detail[l]);
+            p_tag_all.parts.push_back(&tag[l]);
+            p_proj[l] = Pending<smr_item_proj>{&plan.down[l].proj, B_PROJ, l, {&phases[l].proj}, nullptr, false};
+            p_pred[l] = Pending<smr_item_pred>{&plan.pred[l], B_PRED, l, {&pred[l]}, nullptr, false};
+            p_tag[l]  = Pending<smr_item_tag>{&plan.tag[l], B_TAG, l, {&tag[l]}, nullptr, false};
+            p_bc[l]   = PendingBc{&plan.down[l].bc, l, &phases[l].bc.items, &phases[l].bc.srcs};
+        }
+        layout_batch(p_fv, plan.arena);
+        layout_batch(p_detail, plan.arena);
+        layout_batch(p_tag_all, plan.arena);
+        for (int l = 0; l < nlev; ++l)
+        {
+            layout_batch(p_proj[l], plan.arena);
+            layout_batch(p_pred[l], plan.arena);
+            layout_batch(p_tag[l], plan.arena);
+            layout_bc(p_bc[l], plan.arena);
+        }
+        plan.arena.commit();
+#pragma omp parallel for schedule(dynamic, 1)
+        for (int t = 0; t < 3 + 4 * nlev; ++t)
+        {
+            if (t == 0)
+            {
+                fill_batch(p_fv, plan.arena);
+            }
+            else if (t == 1)
+            {
+                fill_batch(p_detail, plan.arena);
+            }
+            else if (t == 2)
+            {
+                fill_batch(p_tag_all, plan.arena);
+            }
+            else
+            {
+                const int l = (t - 3) / 4;
+                switch ((t - 3) % 4)
+                {
+                    case 0:
+                        fill_batch(p_proj[l], plan.arena);
+                        break;
+                    case 1:
+                        fill_batch(p_pred[l], plan.arena);
+                        break;
+                    case 2:
+                        fill_batch(p_tag[l], plan.arena);
+                        break;
+                    default:
+                        fill_bc(p_bc[l], plan.arena);
+                        break;
+                }
+            }
+        }
+#ifdef SMR_PLAN_TIMING
+        std::printf("  build_plan: tasks %.2f ms, serial finish %.2f ms\n", (tt1 - tt0) * 1e3, (omp_get_wtime() - tt1) * 1e3);
+#endif
     }
 
     // old mesh -> new mesh field transfer (update_fields): copy, projection, prediction batches
@@ -668,50 +1091,81 @@ namespace smr
     {
         const MeshConfig& cfg = old_m.cfg;
         const int dim = cfg.dim;
-        tp.arena.bytes.clear();
-        std::vector<smr_item_copy> copies;
-        std::vector<smr_item_proj> projs;
-        std::vector<smr_item_pred> preds;
-        for (int l = cfg.min_level; l <= cfg.max_level; ++l)
+        const int nlev = old_m.nlev;
+        tp.arena.clear();
+        std::vector<std::vector<smr_item_copy>> copies(nlev);
+        std::vector<std::vector<smr_item_proj>> projs(nlev);
+        std::vector<std::vector<smr_item_pred>> preds(nlev);
+        std::string error;
+#pragma omp parallel for schedule(dynamic, 1)
+        for (int t = 2 * nlev - 1; t >= 0; --t)
         {
-            LevelSet s = set_inter(old_m.ref[l], new_m.cells[l]);
-            if (s.empty())
+            const int kind = t / nlev, l = t % nlev;
+            if (l < cfg.min_level || l > cfg.max_level)
             {
                 continue;
             }
-            LevelSet so = s;
-            locate(s, new_m.ref[l]);
-            locate(so, old_m.ref[l]);
-            for (size_t q = 0; q < s.xs.size(); ++q)
+            try
             {
-                copies.push_back({s.off[q], so.off[q], s.xe[q] - s.xs[q], 0});
-            }
-        }
-        for (int l = cfg.min_level + 1; l <= cfg.max_level; ++l)
-        {
-            LevelSet sc = set_inter(coarsen(old_m.cells[l], 1, dim), new_m.cells[l - 1]);
-            proj_items(dim, sc, l - 1, new_m.ref[l - 1], old_m.ref[l], projs);
-            LevelSet sr = set_inter(coarsen(new_m.cells[l], 1, dim), old_m.cells[l - 1]);
-            for (size_t r = 0; r < sr.rows(); ++r)
-            {
-                const int y = key_y(sr.key[r]), z = key_z(sr.key[r]);
-                for (int q = sr.ptr[r]; q < sr.ptr[r + 1]; ++q)
+                if (kind == 0)
                 {
-                    const int s = sr.xs[q], e = sr.xe[q];
-                    for (int cz = 0; cz < (dim > 2 ? 2 : 1); ++cz)
+                    LevelSet s = set_inter(old_m.ref[l], new_m.cells[l]);
+                    if (!s.empty())
                     {
-                        for (int cy = 0; cy < (dim > 1 ? 2 : 1); ++cy)
+                        LevelSet so = s;
+                        locate(s, new_m.ref[l]);
+                        locate(so, old_m.ref[l]);
+                        for (size_t q = 0; q < s.xs.size(); ++q)
                         {
-                            const int fy = dim > 1 ? 2 * y + cy : 0, fz = dim > 2 ? 2 * z + cz : 0;
-                            const int64_t dst = need(new_m.ref[l], "update_fields prediction dst", l, fy, fz, 2 * s, 2 * e - 1);
-                            pred_item(dim, cfg.pred_radius, l, fy, fz, 2 * s, 2 * e, dst, old_m.ref[l - 1], preds);
+                            copies[l].push_back({s.off[q], so.off[q], s.xe[q] - s.xs[q], 0});
                         }
                     }
                 }
+                else if (l > cfg.min_level)
+                {
+                    LevelSet sc = set_inter(coarsen(old_m.cells[l], 1, dim), new_m.cells[l - 1]);
+                    proj_items(dim, sc, l - 1, new_m.ref[l - 1], old_m.ref[l], projs[l]);
+                    // set_refine = (new cells[l] ∩ old cells[l-1]).on(l-1); every coarse cell fills all its children
+                    LevelSet sr = set_inter(coarsen(new_m.cells[l], 1, dim), old_m.cells[l - 1]);
+                    if (!sr.empty())
+                    {
+                        LevelSet fine = refine(sr, 1, dim);
+                        locate(fine, new_m.ref[l]);
+                        pred_items(dim, cfg.pred_radius, l, fine, old_m.ref[l - 1], preds[l]);
+                    }
+                }
+            }
+            catch (const std::exception& e)
+            {
+#pragma omp critical
+                error = e.what();
             }
         }
-        tp.copy = finish_batch(tp.arena, B_COPY, copies);
-        tp.proj = finish_batch(tp.arena, B_PROJ, projs);
-        tp.pred = finish_batch(tp.arena, B_PRED, preds);
+        if (!error.empty())
+        {
+            throw std::out_of_range(error);
+        }
+        Pending<smr_item_copy> p_copy{&tp.copy, B_COPY, -1, {}, nullptr, false};
+        Pending<smr_item_proj> p_proj{&tp.proj, B_PROJ, -1, {}, nullptr, false};
+        Pending<smr_item_pred> p_pred{&tp.pred, B_PRED, -1, {}, nullptr, false};
+        for (int l = 0; l < nlev; ++l)
+        {
+            p_copy.parts.push_back(&copies[l]);
+            p_proj.parts.push_back(&projs[l]);
+            p_pred.parts.push_back(&preds[l]);
+        }
+        layout_batch(p_copy, tp.arena);
+        layout_batch(p_proj, tp.arena);
+        layout_batch(p_pred, tp.arena);
+        tp.arena.commit();
+#pragma omp parallel sections
+        {
+#pragma omp section
+            fill_batch(p_copy, tp.arena);
+#pragma omp section
+            fill_batch(p_proj, tp.arena);
+#pragma omp section
+            fill_batch(p_pred, tp.arena);
+        }
     }
 } // namespace smr

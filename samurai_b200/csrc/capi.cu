@@ -105,11 +105,11 @@ namespace smr
         MeshPlan plan;
         bool plan_ready = false;
         DevBuf d_arena;
-        PinnedBuf h_arena;
         DevBuf d_detail, d_tag;
         PinnedBuf h_tag;
         int64_t last_size   = 0;
         int last_ncomp      = 0;
+        bool graduated      = false; // true once the leaves are known to be a fixed point of make_graduation
         std::vector<FieldObj*> fields;
     };
 
@@ -118,9 +118,11 @@ namespace smr
         MeshObj* mesh = nullptr;
         std::string name;
         DevBuf data;
+        DevBuf spare; // second buffer reused by the field transfer so adaptation never calls cudaMalloc in steady state
         int64_t n    = 0;
         int bc_type  = -1;
         double bc_value = 0;
+        bool ghosts_valid = false; // Field::ghosts_updated() (field/field_base.hpp:264-274)
     };
 
     struct Ctx
@@ -138,6 +140,8 @@ namespace smr
         cudaEvent_t prof_a = nullptr, prof_b = nullptr;
         std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending; // device-time sections not yet resolved
         std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pool;
+        DevBuf d_transfer;
+        TransferPlan transfer; // reused so its pinned arena is allocated once
         std::unordered_map<uint64_t, std::unique_ptr<MeshObj>> meshes;
         std::unordered_map<uint64_t, std::unique_ptr<FieldObj>> fields;
     };
@@ -310,17 +314,31 @@ namespace smr
     // ---------------------------------------------------------------------------------------------------------
     // plan upload and launches
     // ---------------------------------------------------------------------------------------------------------
-    static void upload_arena(const Arena& a, DevBuf& d, PinnedBuf& h)
+    static void* pinned_alloc(size_t n)
     {
-        if (a.bytes.empty())
+        void* p = nullptr;
+        if (cudaHostAlloc(&p, n, cudaHostAllocDefault) != cudaSuccess)
+        {
+            return nullptr;
+        }
+        return p;
+    }
+
+    static void pinned_free(void* p)
+    {
+        cudaFreeHost(p);
+    }
+
+    // the arena is pinned host memory (Arena::alloc_fn): one async copy moves the whole plan
+    static void upload_arena(const Arena& a, DevBuf& d)
+    {
+        if (a.size == 0)
         {
             return;
         }
-        d.ensure(a.bytes.size());
-        h.ensure(a.bytes.size());
-        std::memcpy(h.p, a.bytes.data(), a.bytes.size());
-        SMR_CUDA(cudaMemcpyAsync(d.p, h.p, a.bytes.size(), cudaMemcpyHostToDevice, g.stream));
-        g.stats.h2d_bytes += a.bytes.size();
+        d.ensure(a.size);
+        SMR_CUDA(cudaMemcpyAsync(d.p, a.p, a.size, cudaMemcpyHostToDevice, g.stream));
+        g.stats.h2d_bytes += a.size;
     }
 
     static void ensure_plan(MeshObj& mo)
@@ -334,61 +352,88 @@ namespace smr
         g.stats.host_batch_seconds += now() - t0;
         // the previous arena may still be in use by queued kernels: stream-ordered, so a sync is needed before reuse
         SMR_CUDA(cudaStreamSynchronize(g.stream));
-        upload_arena(mo.plan.arena, mo.d_arena, mo.h_arena);
+        upload_arena(mo.plan.arena, mo.d_arena);
         mo.plan_ready = true;
     }
 
-    template <class Item, class Op>
-    static void launch(int fam, const void* arena, const Batch& b, const Op& op)
+    template <class Item>
+    static BatchView<Item> view_of(const void* arena, const Batch& b, int64_t n_cells)
     {
-        if (b.empty())
-        {
-            return;
-        }
-        prof_begin();
         const char* base = static_cast<const char*>(arena);
-        BatchView<Item> v{reinterpret_cast<const Item*>(base + b.items),
-                          reinterpret_cast<const int64_t*>(base + b.prefix),
-                          reinterpret_cast<const int32_t*>(base + b.cta_first),
-                          b.n_cells};
-        batch_kernel<Item, Op><<<b.n_ctas, SMR_CTA_THREADS, 0, g.stream>>>(v, op);
-        SMR_CUDA(cudaGetLastError());
-        ++g.stats.kernel_launches;
-        prof_end(fam, b.n_cells);
+        return BatchView<Item>{reinterpret_cast<const Item*>(base + b.items),
+                               reinterpret_cast<const int64_t*>(base + b.prefix),
+                               reinterpret_cast<const int32_t*>(base + b.cta_first),
+                               n_cells};
     }
 
-    static void launch_bc(const void* arena, const Batch& b, double* f, int bc_type, double bc_value)
+    // launch the first `limit` output cells of a batch (limit < 0: all of it)
+    template <class Item, class Op>
+    static void launch(int fam, const void* arena, const Batch& b, const Op& op, int64_t limit = -1)
     {
-        if (b.empty())
+        const int64_t n_cells = limit < 0 ? b.n_cells : std::min(limit, b.n_cells);
+        if (b.empty() || n_cells <= 0)
+        {
+            return;
+        }
+        prof_begin();
+        const int n_ctas = static_cast<int>((n_cells + SMR_CTA_CELLS - 1) / SMR_CTA_CELLS);
+        batch_kernel<Item, Op><<<n_ctas, SMR_CTA_THREADS, 0, g.stream>>>(view_of<Item>(arena, b, n_cells), op);
+        SMR_CUDA(cudaGetLastError());
+        ++g.stats.kernel_launches;
+        prof_end(fam, n_cells);
+    }
+
+    static void launch_ghost_phase(int dim, const void* arena, const GhostPhase& ph, double* f, int bc_type, double bc_value)
+    {
+        if (ph.bc.empty() && ph.proj.empty())
         {
             return;
         }
         const char* base = static_cast<const char*>(arena);
+        BcView bc{nullptr, nullptr, 0, bc_type, bc_value};
+        if (!ph.bc.empty())
+        {
+            bc.items = reinterpret_cast<const smr_item_bc*>(base + ph.bc.items);
+            bc.srcs  = reinterpret_cast<const int64_t*>(base + ph.bc.aux);
+            bc.n     = ph.bc.n_items;
+        }
+        BatchView<smr_item_proj> pv{nullptr, nullptr, nullptr, 0};
+        if (!ph.proj.empty())
+        {
+            pv = view_of<smr_item_proj>(arena, ph.proj, ph.proj.n_cells);
+        }
+        const int grid = ph.bc.n_ctas + ph.proj.n_ctas;
         prof_begin();
-        bc_kernel<<<b.n_ctas, SMR_CTA_THREADS, 0, g.stream>>>(reinterpret_cast<const smr_item_bc*>(base + b.items),
-                                                              reinterpret_cast<const int64_t*>(base + b.aux),
-                                                              b.n_items,
-                                                              f,
-                                                              bc_type,
-                                                              bc_value);
+        switch (dim)
+        {
+            case 1:
+                ghost_phase_kernel<1><<<grid, SMR_CTA_THREADS, 0, g.stream>>>(bc, ph.bc.n_ctas, pv, f);
+                break;
+            case 2:
+                ghost_phase_kernel<2><<<grid, SMR_CTA_THREADS, 0, g.stream>>>(bc, ph.bc.n_ctas, pv, f);
+                break;
+            default:
+                ghost_phase_kernel<3><<<grid, SMR_CTA_THREADS, 0, g.stream>>>(bc, ph.bc.n_ctas, pv, f);
+                break;
+        }
         SMR_CUDA(cudaGetLastError());
         ++g.stats.kernel_launches;
-        prof_end(SMR_FAM_BC, b.n_items);
+        prof_end(ph.proj.n_cells >= ph.bc.n_items ? SMR_FAM_PROJ : SMR_FAM_BC, ph.proj.n_cells + ph.bc.n_items);
     }
 
     template <template <int> class OpT, class Item, class... Args>
-    static void launch_dim(int fam, int dim, const void* arena, const Batch& b, Args... args)
+    static void launch_dim(int fam, int dim, const void* arena, const Batch& b, int64_t limit, Args... args)
     {
         switch (dim)
         {
             case 1:
-                launch<Item>(fam, arena, b, OpT<1>{args...});
+                launch<Item>(fam, arena, b, OpT<1>{args...}, limit);
                 break;
             case 2:
-                launch<Item>(fam, arena, b, OpT<2>{args...});
+                launch<Item>(fam, arena, b, OpT<2>{args...}, limit);
                 break;
             default:
-                launch<Item>(fam, arena, b, OpT<3>{args...});
+                launch<Item>(fam, arena, b, OpT<3>{args...}, limit);
                 break;
         }
     }
@@ -410,11 +455,11 @@ namespace smr
     {
         if (radius == 0)
         {
-            launch_dim<PredOp0, smr_item_pred>(SMR_FAM_PRED, dim, arena, b, src, dst);
+            launch_dim<PredOp0, smr_item_pred>(SMR_FAM_PRED, dim, arena, b, -1, src, dst);
         }
         else
         {
-            launch_dim<PredOp1, smr_item_pred>(SMR_FAM_PRED, dim, arena, b, src, dst);
+            launch_dim<PredOp1, smr_item_pred>(SMR_FAM_PRED, dim, arena, b, -1, src, dst);
         }
     }
 
@@ -440,15 +485,13 @@ namespace smr
         const void* arena     = mo.d_arena.p;
         for (int level = cfg.max_level; level >= 0; --level)
         {
-            const GhostPhase& ph = mo.plan.down[level];
-            launch_bc(arena, ph.bc1, u, f.bc_type, f.bc_value);
-            launch_bc(arena, ph.bc2, u, f.bc_type, f.bc_value);
-            launch_dim<ProjOp, smr_item_proj>(SMR_FAM_PROJ, cfg.dim, arena, ph.proj, static_cast<const double*>(u), u);
+            launch_ghost_phase(cfg.dim, arena, mo.plan.down[level], u, f.bc_type, f.bc_value);
         }
         for (int level = 1; level <= cfg.max_level; ++level)
         {
             launch_pred(cfg.dim, cfg.pred_radius, arena, mo.plan.pred[level], u, u);
         }
+        f.ghosts_valid = true;
     }
 
     static void do_fv(FieldObj& out, FieldObj& in, const double* a, double dt, bool burgers)
@@ -487,13 +530,14 @@ namespace smr
         }
         const double* u = static_cast<const double*>(in.data.p);
         double* o       = static_cast<double*>(out.data.p);
+        out.ghosts_valid = false;
         if (burgers)
         {
-            launch_dim<BurgersOp, smr_item_fv>(SMR_FAM_FV, cfg.dim, mo.d_arena.p, mo.plan.fv, u, o, p);
+            launch_dim<BurgersOp, smr_item_fv>(SMR_FAM_FV, cfg.dim, mo.d_arena.p, mo.plan.fv, -1, u, o, p);
         }
         else
         {
-            launch_dim<UpwindOp, smr_item_fv>(SMR_FAM_FV, cfg.dim, mo.d_arena.p, mo.plan.fv, u, o, p);
+            launch_dim<UpwindOp, smr_item_fv>(SMR_FAM_FV, cfg.dim, mo.d_arena.p, mo.plan.fv, -1, u, o, p);
         }
     }
 
@@ -528,18 +572,19 @@ namespace smr
         {
             do_update_ghost(*f);
         }
-        for (int level = std::max(lmin - 1, 0); level < L - ite; ++level)
         {
+            // detail for every coarse level < L - ite in one launch (levels are independent: mr/adapt.hpp:310-317)
+            const int64_t limit = mo.plan.detail_cum[std::max(std::min(L - ite, mo.mesh.nlev), 0)];
             for (int c = 0; c < ncomp; ++c)
             {
                 const double* u = static_cast<const double*>(fields[c]->data.p);
                 if (cfg.pred_radius == 0)
                 {
-                    launch_dim<DetailOp0, smr_item_detail>(SMR_FAM_DETAIL, dim, arena, mo.plan.detail[level], u, detail + c * n);
+                    launch_dim<DetailOp0, smr_item_detail>(SMR_FAM_DETAIL, dim, arena, mo.plan.detail, limit, u, detail + c * n);
                 }
                 else
                 {
-                    launch_dim<DetailOp1, smr_item_detail>(SMR_FAM_DETAIL, dim, arena, mo.plan.detail[level], u, detail + c * n);
+                    launch_dim<DetailOp1, smr_item_detail>(SMR_FAM_DETAIL, dim, arena, mo.plan.detail, limit, u, detail + c * n);
                 }
             }
         }
@@ -564,24 +609,25 @@ namespace smr
         {
             throw std::invalid_argument("dim*(max_level-min_level) >= 31 overflows the reference's `1 << exponent` (mr/adapt.hpp:328)");
         }
-        for (int level = std::max(lmin, 1); level <= L - ite; ++level)
         {
+            // criteria for every fine level <= L - ite in one launch (disjoint tag writes, detail is read-only)
+            const int64_t limit = (L - ite) >= 0 ? mo.plan.tag_cum[L - ite] : 0;
             switch (dim)
             {
                 case 1:
-                    launch<smr_item_tag>(SMR_FAM_CRITERIA, arena, mo.plan.tag[level], CriteriaOp<1>{detail, tag, tp, ncomp, n});
+                    launch<smr_item_tag>(SMR_FAM_CRITERIA, arena, mo.plan.tag_all, CriteriaOp<1>{detail, tag, tp, ncomp, n}, limit);
                     break;
                 case 2:
-                    launch<smr_item_tag>(SMR_FAM_CRITERIA, arena, mo.plan.tag[level], CriteriaOp<2>{detail, tag, tp, ncomp, n});
+                    launch<smr_item_tag>(SMR_FAM_CRITERIA, arena, mo.plan.tag_all, CriteriaOp<2>{detail, tag, tp, ncomp, n}, limit);
                     break;
                 default:
-                    launch<smr_item_tag>(SMR_FAM_CRITERIA, arena, mo.plan.tag[level], CriteriaOp<3>{detail, tag, tp, ncomp, n});
+                    launch<smr_item_tag>(SMR_FAM_CRITERIA, arena, mo.plan.tag_all, CriteriaOp<3>{detail, tag, tp, ncomp, n}, limit);
                     break;
             }
         }
         for (int level = L; level >= 1; --level)
         {
-            launch_dim<MaximumOp, smr_item_tag>(SMR_FAM_MAXIMUM, dim, arena, mo.plan.tag[level], tag);
+            launch_dim<MaximumOp, smr_item_tag>(SMR_FAM_MAXIMUM, dim, arena, mo.plan.tag[level], -1, tag);
         }
         mo.h_tag.ensure(static_cast<size_t>(n));
         SMR_CUDA(cudaMemcpyAsync(mo.h_tag.p, tag, static_cast<size_t>(n), cudaMemcpyDeviceToHost, g.stream));
@@ -594,8 +640,15 @@ namespace smr
         // host: new leaves from tags, graduation, fixed-point test (mr/adapt.hpp:360-379)
         double t0    = now();
         CellArray ca = cells_from_tags(mo.mesh, static_cast<const uint8_t*>(mo.h_tag.p));
-        make_graduation(cfg, ca);
-        const bool same = same_cells(ca, mo.mesh.cells);
+        // every mesh held here came out of make_graduation (or is uniform), and make_graduation leaves a graduated
+        // cell array untouched, so it only has to run when the tags changed something
+        bool same = same_cells(ca, mo.mesh.cells);
+        if (!same || !mo.graduated)
+        {
+            make_graduation(cfg, ca);
+            same = same_cells(ca, mo.mesh.cells);
+        }
+        mo.graduated = true;
         if (same)
         {
             g.stats.host_mesh_seconds += now() - t0;
@@ -609,33 +662,34 @@ namespace smr
 
         // update_fields (algorithm/update_fields.hpp:27-54,101-127)
         t0 = now();
-        TransferPlan tpn;
+        TransferPlan& tpn = g.transfer;
+        SMR_CUDA(cudaStreamSynchronize(g.stream)); // the previous transfer upload must have left the staging arena
         build_transfer(mo.mesh, *new_mesh, tpn);
         g.stats.host_batch_seconds += now() - t0;
-        DevBuf d_tr;
-        PinnedBuf h_tr;
-        Section sec2;
-        upload_arena(tpn.arena, d_tr, h_tr);
+        DevBuf& d_tr = g.d_transfer;
         const int64_t nn = new_mesh->nref;
-        std::vector<std::unique_ptr<DevBuf>> fresh;
         for (auto* f : fields)
         {
-            auto nb = std::make_unique<DevBuf>();
-            nb->ensure(static_cast<size_t>(nn) * sizeof(double));
+            f->spare.ensure(static_cast<size_t>(nn) * sizeof(double));
+        }
+        Section sec2;
+        upload_arena(tpn.arena, d_tr);
+        for (auto* f : fields)
+        {
+            DevBuf* nb = &f->spare;
             SMR_CUDA(cudaMemsetAsync(nb->p, 0, static_cast<size_t>(nn) * sizeof(double), g.stream));
             const double* src = static_cast<const double*>(f->data.p);
             double* dst       = static_cast<double*>(nb->p);
             launch<smr_item_copy>(SMR_FAM_COPY, d_tr.p, tpn.copy, CopyOp{src, dst});
-            launch_dim<ProjOp, smr_item_proj>(SMR_FAM_PROJ, dim, d_tr.p, tpn.proj, src, dst);
+            launch_dim<ProjOp, smr_item_proj>(SMR_FAM_PROJ, dim, d_tr.p, tpn.proj, -1, src, dst);
             launch_pred(dim, cfg.pred_radius, d_tr.p, tpn.pred, src, dst);
-            fresh.push_back(std::move(nb));
         }
         sec2.close();
-        SMR_CUDA(cudaStreamSynchronize(g.stream)); // transfer arena and old buffers are released below
         for (size_t i = 0; i < fields.size(); ++i)
         {
-            fields[i]->data.swap(*fresh[i]);
-            fields[i]->n = nn;
+            fields[i]->data.swap(fields[i]->spare);
+            fields[i]->n            = nn;
+            fields[i]->ghosts_valid = false;
         }
         mo.mesh       = std::move(*new_mesh);
         mo.plan_ready = false;
@@ -698,6 +752,8 @@ extern "C"
                     throw CudaError("device index out of range");
                 }
                 SMR_CUDA(cudaSetDevice(device));
+                Arena::alloc_fn = pinned_alloc;
+                Arena::free_fn  = pinned_free;
                 g.dev    = device;
                 g.stream = nullptr; // legacy default stream unless smr_set_stream() is called
                 g.device = true;
@@ -763,6 +819,7 @@ extern "C"
                 const double t0 = now();
                 auto mo         = std::make_unique<MeshObj>();
                 mo->mesh.init_uniform(c, level);
+                mo->graduated = true; // a uniform mesh is trivially graduated
                 g.stats.host_mesh_seconds += now() - t0;
                 *out = g.next_id++;
                 g.meshes[*out] = std::move(mo);
@@ -988,6 +1045,10 @@ extern "C"
                     SMR_CUDA(cudaStreamSynchronize(g.stream));
                 }
                 f.data.ensure(static_cast<size_t>(n) * sizeof(double));
+                if (f.n != n)
+                {
+                    f.ghosts_valid = false;
+                }
                 f.n = n;
             });
     }
@@ -1000,6 +1061,7 @@ extern "C"
                 require_device();
                 FieldObj& f = get_field(fh);
                 check_field_ready(f);
+                f.ghosts_valid = false;
                 if (v == 0.0)
                 {
                     SMR_CUDA(cudaMemsetAsync(f.data.p, 0, static_cast<size_t>(f.n) * sizeof(double), g.stream));
@@ -1034,6 +1096,7 @@ extern "C"
                 {
                     throw std::invalid_argument("upload size does not match the field size");
                 }
+                f.ghosts_valid = false;
                 SMR_CUDA(cudaMemcpyAsync(f.data.p, host, static_cast<size_t>(n) * sizeof(double), cudaMemcpyHostToDevice, g.stream));
                 g.stats.h2d_bytes += static_cast<uint64_t>(n) * sizeof(double);
             });
@@ -1070,6 +1133,7 @@ extern "C"
                 }
                 a.data.swap(b.data);
                 std::swap(a.n, b.n);
+                std::swap(a.ghosts_valid, b.ghosts_valid);
             });
     }
 
@@ -1095,6 +1159,13 @@ extern "C"
             {
                 require_device();
                 FieldObj& f = get_field(fh);
+                if (f.ghosts_valid && f.n == f.mesh->mesh.nref)
+                {
+                    // the ghosts are a pure function of the leaves (and of cells no phase writes, which are unchanged):
+                    // recomputing them would store the same bits (update_ghost_mr_if_needed, update_ghost_mr.hpp:242-249)
+                    ++g.stats.ghost_updates_skipped;
+                    return;
+                }
                 ensure_plan(*f.mesh);
                 Section sec;
                 do_update_ghost(f);
@@ -1184,6 +1255,7 @@ extern "C"
                 make_graduation(mo.mesh.cfg, ca);
                 const bool same = same_cells(ca, mo.mesh.cells);
                 *unchanged      = same ? 1 : 0;
+                mo.graduated    = true;
                 if (!same)
                 {
                     if (g.device)
@@ -1198,6 +1270,31 @@ extern "C"
                     ++g.stats.mesh_rebuilds;
                 }
                 g.stats.host_mesh_seconds += now() - t0;
+            });
+    }
+
+    int smr_debug_host_rebuild(smr_mesh_t m, int reps, double* mesh_seconds, double* plan_seconds, int64_t* arena_bytes)
+    {
+        return guarded(
+            [&]
+            {
+                MeshObj& mo = get_mesh(m);
+                double tm = 0, tp = 0;
+                for (int r = 0; r < reps; ++r)
+                {
+                    CellArray ca = mo.mesh.cells;
+                    double t0    = now();
+                    Mesh nm;
+                    nm.init_from_cells(mo.mesh.cfg, std::move(ca));
+                    tm += now() - t0;
+                    t0 = now();
+                    MeshPlan plan;
+                    build_plan(nm, plan);
+                    tp += now() - t0;
+                    *arena_bytes = static_cast<int64_t>(plan.arena.size);
+                }
+                *mesh_seconds = tm / reps;
+                *plan_seconds = tp / reps;
             });
     }
 
@@ -1298,6 +1395,7 @@ extern "C"
                 MeshObj& mo = *f.mesh;
                 ensure_plan(mo);
                 Section sec;
+                f.ghosts_valid        = false;
                 const MeshConfig& cfg = mo.mesh.cfg;
                 double* u             = static_cast<double*>(f.data.p);
                 auto run              = [&](auto op)

@@ -168,6 +168,92 @@ namespace smr
         }
     };
 
+    // Moving lookup into a LevelSet for queries that arrive in (mostly) non-decreasing (row key, x) order: the row is
+    // found by galloping from the previous hit, the interval by advancing a cursor.  Amortised O(1) per query where a
+    // fresh find_row/find_ivl pair costs two binary searches.
+    struct Probe
+    {
+        const LevelSet* s = nullptr;
+        size_t hint       = 0;
+        int row           = -1;
+        int q = 0, qe = 0;
+
+        Probe() = default;
+
+        explicit Probe(const LevelSet& ls)
+            : s(&ls)
+        {
+        }
+
+        bool seek(int64_t k)
+        {
+            const size_t n = s->key.size();
+            size_t lo, hi;
+            if (hint < n && s->key[hint] <= k)
+            {
+                if (s->key[hint] == k)
+                {
+                    lo = hi = hint;
+                }
+                else
+                {
+                    size_t step = 1;
+                    lo          = hint;
+                    while (lo + step < n && s->key[lo + step] < k)
+                    {
+                        lo += step;
+                        step <<= 1;
+                    }
+                    hi = std::min(n, lo + step + 1);
+                    lo = static_cast<size_t>(std::lower_bound(s->key.begin() + static_cast<std::ptrdiff_t>(lo), s->key.begin() + static_cast<std::ptrdiff_t>(hi), k)
+                                             - s->key.begin());
+                }
+            }
+            else
+            {
+                lo = static_cast<size_t>(std::lower_bound(s->key.begin(), s->key.end(), k) - s->key.begin());
+            }
+            if (lo < n && s->key[lo] == k)
+            {
+                hint = lo;
+                row  = static_cast<int>(lo);
+                q    = s->ptr[lo];
+                qe   = s->ptr[lo + 1];
+                return true;
+            }
+            hint = std::min(lo, n ? n - 1 : 0);
+            row  = -1;
+            return false;
+        }
+
+        // storage offset of x when [x, x_last] lies inside one interval of the current row, else -1
+        int64_t offset(int x, int x_last)
+        {
+            if (row < 0)
+            {
+                return -1;
+            }
+            if (q > s->ptr[row] && s->xs[q > qe - 1 ? qe - 1 : q] > x)
+            {
+                q = s->ptr[row]; // query went backwards: restart the row
+            }
+            while (q < qe && s->xe[q] <= x)
+            {
+                ++q;
+            }
+            if (q >= qe || s->xs[q] > x || x_last >= s->xe[q])
+            {
+                return -1;
+            }
+            return s->off[q] + (x - s->xs[q]);
+        }
+
+        bool contains(int x)
+        {
+            return offset(x, x) >= 0;
+        }
+    };
+
     // ------------------------------------------------------------------------------------------------
     // row-level merges on sorted disjoint interval lists
     // ------------------------------------------------------------------------------------------------

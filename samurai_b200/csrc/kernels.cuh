@@ -23,18 +23,19 @@ namespace smr
         int64_t n_cells;
     };
 
+    // body of one CTA of a batch: output cells [cta * SMR_CTA_CELLS, (cta + 1) * SMR_CTA_CELLS) ∩ [0, n_cells)
     template <class Item, class Op>
-    __global__ void __launch_bounds__(SMR_CTA_THREADS) batch_kernel(BatchView<Item> b, Op op)
+    __device__ __forceinline__ void run_batch_cta(const BatchView<Item>& b, const Op& op, int cta)
     {
         __shared__ int64_t s_prefix[SMR_CTA_CELLS + 2];
-        const int first = b.cta_first[blockIdx.x];
-        const int nloc  = b.cta_first[blockIdx.x + 1] - first + 1;
+        const int first = b.cta_first[cta];
+        const int nloc  = b.cta_first[cta + 1] - first + 1;
         for (int i = threadIdx.x; i <= nloc; i += SMR_CTA_THREADS)
         {
             s_prefix[i] = b.prefix[first + i];
         }
         __syncthreads();
-        const int64_t base = static_cast<int64_t>(blockIdx.x) * SMR_CTA_CELLS;
+        const int64_t base = static_cast<int64_t>(cta) * SMR_CTA_CELLS;
 #pragma unroll
         for (int k = 0; k < SMR_CELLS_PER_THREAD; ++k)
         {
@@ -57,6 +58,12 @@ namespace smr
                 op(b.items[first + lo], static_cast<int>(g - s_prefix[lo]));
             }
         }
+    }
+
+    template <class Item, class Op>
+    __global__ void __launch_bounds__(SMR_CTA_THREADS) batch_kernel(BatchView<Item> b, Op op)
+    {
+        run_batch_cta(b, op, blockIdx.x);
     }
 
     // ------------------------------------------------------------------------------------------------------------
@@ -134,8 +141,8 @@ namespace smr
     template <int DIM>
     struct ProjOp
     {
-        const double* __restrict__ src;
-        double* __restrict__ dst;
+        const double* src; // may alias dst (ghost update projects inside one field)
+        double* dst;
 
         __device__ __forceinline__ void operator()(const smr_item_proj& it, int k) const
         {
@@ -163,8 +170,8 @@ namespace smr
     template <int DIM, int RADIUS>
     struct PredOp
     {
-        const double* __restrict__ src;
-        double* __restrict__ dst;
+        const double* src; // may alias dst (ghost update predicts inside one field)
+        double* dst;
 
         __device__ __forceinline__ void operator()(const smr_item_pred& it, int k) const
         {
@@ -468,29 +475,36 @@ namespace smr
     // ------------------------------------------------------------------------------------------------------------
     // boundary ghosts: one thread per ghost cell (update_outer_ghost.hpp, bc/dirichlet.hpp:29, bc/neumann.hpp:27-28)
     // ------------------------------------------------------------------------------------------------------------
-    __global__ void __launch_bounds__(SMR_CTA_THREADS)
-        bc_kernel(const smr_item_bc* __restrict__ items, const int64_t* __restrict__ srcs, int n, double* __restrict__ f, int bc_type, double bc_value)
+    struct BcView
     {
-        const int i = blockIdx.x * SMR_CTA_THREADS + threadIdx.x;
-        if (i >= n)
+        const smr_item_bc* items;
+        const int64_t* srcs;
+        int n;
+        int bc_type;
+        double bc_value;
+    };
+
+    __device__ __forceinline__ void run_bc(const BcView& v, double* __restrict__ f, int i)
+    {
+        if (i >= v.n)
         {
             return;
         }
-        const smr_item_bc it = items[i];
-        const int64_t* s     = srcs + it.src_first;
+        const smr_item_bc it = v.items[i];
+        const int64_t* s     = v.srcs + it.src_first;
         if (it.kind == SMR_BC_COPY)
         {
             f[it.dst] = f[s[0]];
         }
         else if (it.kind == SMR_BC_VALUE)
         {
-            if (bc_type == SMR_BCTYPE_DIRICHLET)
+            if (v.bc_type == SMR_BCTYPE_DIRICHLET)
             {
-                f[it.dst] = 2 * bc_value - f[s[0]];
+                f[it.dst] = 2 * v.bc_value - f[s[0]];
             }
             else
             {
-                f[it.dst] = it.coef * bc_value + f[s[0]];
+                f[it.dst] = it.coef * v.bc_value + f[s[0]];
             }
         }
         else
@@ -505,6 +519,21 @@ namespace smr
                 sum /= it.n_src;
             }
             f[it.dst] = sum;
+        }
+    }
+
+    // One level of the top-down ghost sweep in a single launch: CTAs [0, bc_ctas) fill the outside ghosts of the level,
+    // the remaining CTAs run the projection level -> level-1.  The two halves never touch the same cells (batches.hpp).
+    template <int DIM>
+    __global__ void __launch_bounds__(SMR_CTA_THREADS) ghost_phase_kernel(BcView bc, int bc_ctas, BatchView<smr_item_proj> pv, double* __restrict__ f)
+    {
+        if (static_cast<int>(blockIdx.x) < bc_ctas)
+        {
+            run_bc(bc, f, blockIdx.x * SMR_CTA_THREADS + threadIdx.x);
+        }
+        else
+        {
+            run_batch_cta(pv, ProjOp<DIM>{f, f}, static_cast<int>(blockIdx.x) - bc_ctas);
         }
     }
 } // namespace smr

@@ -181,31 +181,50 @@ namespace smr
                 c.off.clear();
             }
             uni.assign(nlev, LevelSet());
-            for (int l = L; l >= 1; --l)
-            {
-                uni[l - 1] = coarsen(set_union(cells[l], uni[l]), 1, dim);
-            }
             cag.assign(nlev, LevelSet());
-            for (int l = 0; l < nlev; ++l)
-            {
-                cag[l] = expand(cells[l], msr, dim);
-            }
-            ref = cag;
             proj.assign(nlev, LevelSet());
-            if (cfg.max_level != cfg.min_level)
+            const bool multi = cfg.max_level != cfg.min_level;
+            std::vector<LevelSet> add1(nlev), add2(nlev); // prediction ghosts sent one / two levels down (mr/mesh.hpp:329-359)
+            // levels are independent here; the union pyramid (a serial cascade) runs as one more task next to them
+#pragma omp parallel for schedule(dynamic, 1)
+            for (int t = nlev; t >= 0; --t)
             {
-                for (int l = 1; l < nlev; ++l)
+                if (t == nlev)
                 {
-                    if (cells[l].empty())
+                    for (int l = L; l >= 1; --l)
                     {
-                        continue;
+                        uni[l - 1] = coarsen(set_union(cells[l], uni[l]), 1, dim);
                     }
-                    ref[l - 1] = set_union(ref[l - 1], in_domain(expand(coarsen(cag[l], 1, dim), pr, dim), l - 1, pr));
+                    continue;
+                }
+                const int l = t;
+                cag[l]      = expand(cells[l], msr, dim);
+                if (multi && l >= 1 && !cells[l].empty())
+                {
+                    add1[l] = in_domain(expand(coarsen(cag[l], 1, dim), pr, dim), l - 1, pr);
                     if (l - 1 > 0)
                     {
-                        ref[l - 2] = set_union(ref[l - 2], expand(coarsen(cells[l], 2, dim), pr, dim));
+                        add2[l] = expand(coarsen(cells[l], 2, dim), pr, dim);
                     }
                 }
+            }
+            ref.assign(nlev, LevelSet());
+#pragma omp parallel for schedule(dynamic, 1)
+            for (int l = nlev - 1; l >= 0; --l)
+            {
+                LevelSet r = cag[l];
+                if (l + 1 < nlev && !add1[l + 1].empty())
+                {
+                    r = set_union(r, add1[l + 1]);
+                }
+                if (l + 2 < nlev && !add2[l + 2].empty())
+                {
+                    r = set_union(r, add2[l + 2]);
+                }
+                ref[l] = std::move(r);
+            }
+            if (multi)
+            {
                 int l = 0;
                 while (l < nlev && ref[l].empty())
                 {
@@ -253,11 +272,15 @@ namespace smr
             level_start[nlev] = counter;
             nref              = counter;
             nleaves           = 0;
-            for (int l = 0; l < nlev; ++l)
+#pragma omp parallel for schedule(dynamic, 1)
+            for (int l = nlev - 1; l >= 0; --l)
             {
                 locate(cells[l], ref[l]);
                 locate(cag[l], ref[l]);
                 locate(proj[l], ref[l]);
+            }
+            for (int l = 0; l < nlev; ++l)
+            {
                 nleaves += cells[l].n_cells();
             }
             ++generation;
@@ -387,6 +410,9 @@ namespace smr
             }
             std::vector<LevelSet> out(nlev);
             bool any = false;
+            // every fine level contributes independently to the coarser levels it overlaps
+            std::vector<std::vector<LevelSet>> contrib(nlev, std::vector<LevelSet>(nlev));
+#pragma omp parallel for schedule(dynamic, 1)
             for (int fine = hi; fine > lo + 1; --fine)
             {
                 if (ca[fine].empty())
@@ -398,18 +424,24 @@ namespace smr
                 {
                     if (!p.empty())
                     {
-                        LevelSet r = set_inter(p, ca[cl]);
-                        if (!r.empty())
-                        {
-                            out[cl] = set_union(out[cl], r);
-                            any     = true;
-                        }
+                        contrib[fine][cl] = set_inter(p, ca[cl]);
                     }
                     if (cl == lo || p.empty())
                     {
                         break;
                     }
                     p = coarsen(p, 1, dim);
+                }
+            }
+            for (int cl = lo; cl <= hi; ++cl)
+            {
+                for (int fine = hi; fine > cl + 1; --fine)
+                {
+                    if (!contrib[fine][cl].empty())
+                    {
+                        out[cl] = set_union(out[cl], contrib[fine][cl]);
+                        any     = true;
+                    }
                 }
             }
             if (!any)
