@@ -308,8 +308,11 @@ namespace smr
     {
         const int dim = m.cfg.dim;
         CellArray out(m.nlev);
-        std::vector<SetBuilder> add(m.nlev), rem(m.nlev);
-        for (int l = 0; l < m.nlev; ++l)
+        // add[l][k]: cells created at level l by the scan of level l+1 (k = 0, parents) or l-1 (k = 1, children)
+        std::vector<std::array<SetBuilder, 2>> add(m.nlev + 1);
+        std::vector<SetBuilder> rem(m.nlev);
+#pragma omp parallel for schedule(dynamic, 1)
+        for (int l = m.nlev - 1; l >= 0; --l)
         {
             const LevelSet& c = m.cells[l];
             for (size_t r = 0; r < c.rows(); ++r)
@@ -331,7 +334,7 @@ namespace smr
                             {
                                 for (int cy = 0; cy < (dim > 1 ? 2 : 1); ++cy)
                                 {
-                                    add[l + 1].add(mk_key(dim > 1 ? 2 * y + cy : 0, dim > 2 ? 2 * z + cz : 0), 2 * run_start, 2 * x_end);
+                                    add[l + 1][1].add(mk_key(dim > 1 ? 2 * y + cy : 0, dim > 2 ? 2 * z + cz : 0), 2 * run_start, 2 * x_end);
                                 }
                             }
                         }
@@ -343,7 +346,7 @@ namespace smr
                                 // parent added once, through the even child (graduation.hpp:806-809)
                                 const int ps = (run_start + 1) >> 1; // first even x >= run_start, halved
                                 const int pe = ((x_end - 1) >> 1) + 1;
-                                add[l - 1].add(mk_key(y >> 1, z >> 1), ps, pe);
+                                add[l - 1][0].add(mk_key(y >> 1, z >> 1), ps, pe);
                             }
                         }
                     };
@@ -370,13 +373,17 @@ namespace smr
                 }
             }
         }
-        for (int l = m.cfg.min_level; l <= m.cfg.max_level; ++l)
+#pragma omp parallel for schedule(dynamic, 1)
+        for (int l = m.cfg.max_level; l >= m.cfg.min_level; --l)
         {
             LevelSet s = m.cells[l];
             s.off.clear();
-            if (!add[l].empty())
+            for (int k = 0; k < 2; ++k)
             {
-                s = set_union(s, add[l].build());
+                if (!add[l][k].empty())
+                {
+                    s = set_union(s, add[l][k].build());
+                }
             }
             if (!rem[l].empty())
             {
@@ -419,7 +426,10 @@ namespace smr
                 {
                     continue;
                 }
-                LevelSet p = coarsen(expand(ca[fine], 2 * w, dim), 2, dim);
+                // expand(X, 2w).on(fine-2) == expand(X.on(fine-1), w).on(fine-2): 2w is even and coarse cells are aligned on
+                // multiples of 4, so the halo test x in [4c-2w, 4c+3+2w] is exactly (x>>1) in [2c-w, 2c+1+w]; coarsening
+                // first halves the rows the expansion has to merge
+                LevelSet p = coarsen(expand(coarsen(ca[fine], 1, dim), w, dim), 1, dim);
                 for (int cl = fine - 2;; --cl)
                 {
                     if (!p.empty())

@@ -1,0 +1,88 @@
+"""Host half of the product (C ABI, no GPU needed) against the oracle: sub-meshes and storage numbering bit-exact,
+update_cell_array_from_tag + make_graduation + mesh rebuild driven by the oracle's tag arrays."""
+import numpy as np
+import pytest
+
+import parity_utils as pu
+
+sb, so = pu.sb, pu.so
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _init(lib):
+    lib.initialize(-1)
+
+
+@pytest.mark.parametrize("dim,lmin,lmax,pred", [(1, 1, 6, 1), (2, 2, 6, 0), (2, 2, 6, 1), (2, 4, 8, 1), (3, 1, 4, 0), (3, 1, 4, 1)])
+def test_uniform_mesh_matches_oracle(dim, lmin, lmax, pred):
+    pm = sb.MRMesh.make_mesh([0.0] * dim, [1.0] * dim, pu.product_cfg(dim, lmin, lmax, pred))
+    om = so.Mesh.uniform(pu.oracle_cfg(dim, lmin, lmax, pred))
+    pu.assert_same_mesh(pm, om)
+    assert pm.nb_cells(sb.CELLS) == (1 << (dim * lmax))
+    pm.destroy()
+
+
+def test_single_level_mesh_has_no_projection_cells():
+    pm = sb.MRMesh.make_mesh([0.0, 0.0], [1.0, 1.0], pu.product_cfg(2, 5, 5, 1))
+    om = so.Mesh.uniform(pu.oracle_cfg(2, 5, 5, 1))
+    pu.assert_same_mesh(pm, om)
+    assert pm.nb_cells(sb.PROJ_CELLS) == 0
+    assert pm.nb_cells(sb.REFERENCE) == (32 + 2) ** 2
+    pm.destroy()
+
+
+@pytest.mark.parametrize("dim,lmin,lmax,pred,steps", [(2, 2, 7, 1, 4), (2, 2, 7, 0, 4), (3, 1, 5, 1, 3)])
+def test_adaptation_host_path_matches_oracle(dim, lmin, lmax, pred, steps):
+    """Every harten iteration of the oracle's advection run: feed its tag array to the product's host path and require
+    the same graduated mesh (all sub-meshes + offsets), including the fixed-point detection."""
+    ocfg = pu.oracle_cfg(dim, lmin, lmax, pred)
+    bc = so.Bc()
+    om = so.Mesh.uniform(ocfg)
+    ou = so.init_disc(om, [0.3] * dim, 0.2)
+    pm = sb.MRMesh.make_mesh([0.0] * dim, [1.0] * dim, pu.product_cfg(dim, lmin, lmax, pred))
+    n_checked = 0
+    for _ in range(steps):
+        trace = []
+        om2, ou2 = so.adapt(om, ou, bc, 2e-4, 1.0, trace=trace)
+        for k, t in enumerate(trace):
+            pu.assert_same_mesh(pm, t["mesh"])
+            gen = pm.generation()
+            unchanged = pm.update_from_tags(t["tag"])
+            last = k == len(trace) - 1
+            if unchanged:
+                assert last and pm.generation() == gen
+            n_checked += 1
+        pu.assert_same_mesh(pm, om2)
+        om, ou = om2, ou2
+        so.update_ghost_mr(om, ou, bc)
+        ou = so.fv_step(om, ou, [1.0] * dim, 0.5 * ocfg.cell_length(lmax))
+    assert n_checked >= steps
+    pm.destroy()
+
+
+def test_from_intervals_roundtrip_and_get_index():
+    ocfg = pu.oracle_cfg(2, 2, 6, 1)
+    om = so.Mesh.uniform(ocfg)
+    ou = so.init_disc(om, [0.3, 0.3], 0.2)
+    om, ou = so.adapt(om, ou, so.Bc(), 2e-4, 1.0)
+    lv, co, ix = om.leaf_table()
+    iv = np.zeros(lv.size, dtype=sb.INTERVAL_DTYPE)
+    iv["start"], iv["end"], iv["y"] = co[:, 0], co[:, 0] + 1, co[:, 1]
+    pm = sb.MRMesh.from_intervals([0, 0], [1, 1], pu.product_cfg(2, 2, 6, 1), lv.astype(np.int32), iv)
+    pu.assert_same_mesh(pm, om)
+    # get_index == oracle index for a few leaves; missing cells raise like LevelCellArray::get_interval
+    for k in (0, lv.size // 2, lv.size - 1):
+        assert pm.get_index(int(lv[k]), int(co[k, 0]), int(co[k, 1])) == ix[k]
+    with pytest.raises(IndexError):
+        pm.get_index(6, 1000, 1000)
+    # leaf table order == for_each_cell order
+    plv, pco, poff = pm.cell_table(sb.CELLS)
+    assert np.array_equal(plv, lv) and np.array_equal(pco, co) and np.array_equal(poff, ix)
+    pm.destroy()
+
+
+def test_invalid_configs_raise():
+    with pytest.raises(ValueError):
+        sb.MRMesh.make_mesh([0, 0], [1, 1], sb.mesh_config(2, 1).min_level(5).max_level(3).disable_minimal_ghost_width())
+    with pytest.raises(ValueError):  # ghost width 2 is not implemented: must fail loudly, not silently differ
+        sb.MRMesh.make_mesh([0, 0], [1, 1], sb.mesh_config(2, 1).min_level(2).max_level(4))

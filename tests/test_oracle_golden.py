@@ -1,0 +1,83 @@
+"""Pins the oracle (oracle/samurai_oracle.py) on the reference's OWN golden files.
+
+tests/golden/advection_2d_pred_{0,1}{,_init}.npz are the datasets of
+/root/reference/tests/reference/finite_volume/test_finite_volume_advection_2d_*.h5 (converted by
+tests/golden/make_golden.py): the outputs of samurai's finite-volume-advection-2d demo run with --Tf 0.01 that samurai's
+pytest suite compares against (tests/test_demo_finite_volume.py:55-72, rel 1e-14 / abs 1e-7).  The full pipeline is
+exercised: uniform level-10 mesh -> MRadaptation -> 21 x (MRadaptation, update_ghost_mr, upwind) for prediction radius
+0 and 1.  Mesh: exact.  Field: the reference's own tolerance (we observe <= 4.5e-16 absolute).
+"""
+import os
+
+import numpy as np
+import pytest
+
+import samurai_oracle as so
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _check(mesh, u, name):
+    g = np.load(os.path.join(GOLD, name))
+    lv, co, ix = mesh.leaf_table()
+    assert lv.size == g["level"].size, f"{name}: {lv.size} leaves vs golden {g['level'].size}"
+    assert np.array_equal(lv, g["level"].astype(np.int64)), f"{name}: levels differ"
+    assert np.array_equal(co, g["idx"].astype(np.int64)), f"{name}: cell indices differ (mesh not identical)"
+    ref = g["u"]
+    got = u[ix]
+    # reference tolerance: pytest.approx(rel=1e-14, abs=1e-7) (tests/conftest.py:121-122); we require far tighter
+    assert np.max(np.abs(got - ref)) <= 1e-14, f"{name}: max abs diff {np.max(np.abs(got - ref)):.3e}"
+
+
+@pytest.mark.parametrize("pred", [0, 1])
+def test_oracle_matches_reference_golden(pred):
+    cfg = so.MeshConfig(dim=2, min_level=4, max_level=10, pred_radius=pred)
+    res = so.run_advection(cfg, Tf=0.01, eps=2e-4)
+    assert res["steps"] == 21
+    _check(*res["init"], f"advection_2d_pred_{pred}_init.npz")
+    _check(*res["final"], f"advection_2d_pred_{pred}.npz")
+
+
+def test_projection_prediction_exactness():
+    """reference tests/test_projection_prediction_roundtrip.cpp: projection is the exact mean of the children and the
+    order-1 prediction reproduces polynomials of per-axis degree <= 2 exactly (up to rounding)."""
+    cfg = so.MeshConfig(dim=2, min_level=2, max_level=5, pred_radius=1)
+    # two-level mesh: left half at level 4, right half at level 5
+    c4 = so.box_cells([0, 0], [8, 16])
+    c5 = so.box_cells([16, 0], [32, 32])
+    mesh = so.Mesh(cfg, {4: c4, 5: c5})
+    f = np.zeros(mesh.nref)
+
+    def poly(level, keys):
+        x = mesh.cell_centers(level, keys)
+        h = cfg.cell_length(level)
+        # cell average of 1 + 2x + 3y + x^2 over the cell (exact): x^2 average = xc^2 + h^2/12
+        return 1 + 2 * x[:, 0] + 3 * x[:, 1] + x[:, 0] ** 2 + h * h / 12 + 0.5 * x[:, 0] * x[:, 1]
+
+    for l in range(mesh.nlev):
+        if mesh.ref[l].size:
+            f[mesh.index(l, mesh.ref[l])] = poly(l, mesh.ref[l])
+    exact = f.copy()
+    # projection of level 5 onto its parents
+    parents = so.coarsen(c5, 1, 2)
+    f[mesh.index(4, parents)] = -1
+    so.projection(mesh, f, 4, parents)
+    assert np.max(np.abs(f[mesh.index(4, parents)] - exact[mesh.index(4, parents)])) < 1e-13
+    # prediction of interior level-5 cells from level 4 (parents with a full neighbourhood in the reference mesh)
+    inner = so.box_cells([18, 2], [30, 30])
+    pred = so.predict_values(mesh, exact, mesh, 5, inner)
+    assert np.max(np.abs(pred - exact[mesh.index(5, inner)])) < 1e-12
+
+
+def test_upwind_constant_and_linear():
+    """reference tests/test_fv_operators.cpp:87-226: upwind convection of a constant is 0, of a linear field is a.grad."""
+    cfg = so.MeshConfig(dim=2, min_level=5, max_level=5)
+    mesh = so.Mesh.uniform(cfg)
+    u = np.zeros(mesh.nref)
+    x = mesh.cell_centers(5, mesh.ref[5])
+    u[mesh.index(5, mesh.ref[5])] = 2 * x[:, 0] - 3 * x[:, 1] + 1
+    a = [1.0, 0.5]
+    out = so.fv_step(mesh, u, a, dt=1.0)
+    leaves = mesh.index(5, mesh.cells[5])
+    # unp1 = u - dt * (a . grad u) = u - (2*1 - 3*0.5)
+    assert np.max(np.abs(out[leaves] - (u[leaves] - 0.5))) < 1e-11
