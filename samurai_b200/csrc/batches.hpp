@@ -39,6 +39,7 @@ namespace smr
         int n_items     = 0;
         int n_ctas      = 0;
         int64_t n_cells = 0;
+        int cta_units   = SMR_CTA_CELLS; // output units per CTA (256 x the kernel's units per thread)
         // byte offsets into the arena
         int64_t items = -1, prefix = -1, cta_first = -1, aux = -1;
         int level     = -1;
@@ -126,6 +127,7 @@ namespace smr
         std::vector<const std::vector<Item>*> parts;
         std::vector<int64_t>* cum = nullptr; // optional per-part cumulative output-cell counts
         bool inclusive            = false;
+        int cta_units             = SMR_CTA_CELLS;
     };
 
     template <class Item>
@@ -167,7 +169,8 @@ namespace smr
             return;
         }
         b.n_cells   = c;
-        b.n_ctas    = static_cast<int>((c + SMR_CTA_CELLS - 1) / SMR_CTA_CELLS);
+        b.cta_units = pd.cta_units;
+        b.n_ctas    = static_cast<int>((c + pd.cta_units - 1) / pd.cta_units);
         b.items     = static_cast<int64_t>(arena.take(n * sizeof(Item)));
         b.prefix    = static_cast<int64_t>(arena.take((n + 1) * sizeof(int64_t)));
         b.cta_first = static_cast<int64_t>(arena.take((static_cast<size_t>(b.n_ctas) + 1) * sizeof(int32_t)));
@@ -202,7 +205,7 @@ namespace smr
         size_t it = 0;
         for (int c = 0; c < b.n_ctas; ++c)
         {
-            const int64_t g = static_cast<int64_t>(c) * SMR_CTA_CELLS;
+            const int64_t g = static_cast<int64_t>(c) * b.cta_units;
             while (prefix[it + 1] <= g)
             {
                 ++it;
@@ -326,6 +329,180 @@ namespace smr
                 it.pad   = 0;
                 out.push_back(it);
             }
+        }
+    }
+
+    // Leaves of level l split for the FV kernels: strips of SMR_STRIP_ROWS consecutive rows sharing an x-range, and the
+    // single-row remainder.  Every leaf cell lands in exactly one of the two lists.
+    inline void fv_split_items(const Mesh& m, int l, std::vector<smr_item_fvstrip>& strips, std::vector<smr_item_fv>& singles)
+    {
+        constexpr int R = SMR_STRIP_ROWS;
+        const int dim   = m.cfg.dim;
+        const LevelSet& c   = m.cells[l];
+        const LevelSet& ref = m.ref[l];
+        if (dim < 2)
+        {
+            fv_items(m, l, singles);
+            return;
+        }
+        Probe prow[R + 2], pzm[R], pzp[R];
+        for (auto& x : prow)
+        {
+            x = Probe(ref);
+        }
+        for (int r = 0; r < R; ++r)
+        {
+            pzm[r] = Probe(ref);
+            pzp[r] = Probe(ref);
+        }
+        Probe ps_c(ref), ps_ym(ref), ps_yp(ref), ps_zm(ref), ps_zp(ref);
+        std::vector<std::pair<int, int>> common, tmp;
+        auto single = [&](int y, int z, int s, int e)
+        {
+            smr_item_fv it;
+            ps_c.seek(mk_key(y, z));
+            ps_ym.seek(mk_key(y - 1, z));
+            ps_yp.seek(mk_key(y + 1, z));
+            it.c  = need(ps_c, "fv x", l, y, z, s - 1, e) + 1;
+            it.ym = need(ps_ym, "fv y-1", l, y - 1, z, s, e - 1);
+            it.yp = need(ps_yp, "fv y+1", l, y + 1, z, s, e - 1);
+            it.zm = it.zp = it.c;
+            if (dim > 2)
+            {
+                ps_zm.seek(mk_key(y, z - 1));
+                ps_zp.seek(mk_key(y, z + 1));
+                it.zm = need(ps_zm, "fv z-1", l, y, z - 1, s, e - 1);
+                it.zp = need(ps_zp, "fv z+1", l, y, z + 1, s, e - 1);
+            }
+            it.n     = e - s;
+            it.level = l;
+            it.x     = s;
+            it.y     = y;
+            it.z     = z;
+            it.pad   = 0;
+            singles.push_back(it);
+        };
+        size_t r0 = 0;
+        const size_t nrows = c.rows();
+        while (r0 < nrows)
+        {
+            const int y0 = key_y(c.key[r0]), z0 = key_z(c.key[r0]);
+            bool group = r0 + R <= nrows;
+            for (int r = 1; group && r < R; ++r)
+            {
+                group = c.key[r0 + r] == mk_key(y0 + r, z0);
+            }
+            if (!group)
+            {
+                for (int q = c.ptr[r0]; q < c.ptr[r0 + 1]; ++q)
+                {
+                    single(y0, z0, c.xs[q], c.xe[q]);
+                }
+                ++r0;
+                continue;
+            }
+            // x-ranges common to the R rows
+            common.clear();
+            for (int q = c.ptr[r0]; q < c.ptr[r0 + 1]; ++q)
+            {
+                common.emplace_back(c.xs[q], c.xe[q]);
+            }
+            for (int r = 1; r < R && !common.empty(); ++r)
+            {
+                tmp.clear();
+                size_t i = 0;
+                int q    = c.ptr[r0 + r];
+                const int qe = c.ptr[r0 + r + 1];
+                while (i < common.size() && q < qe)
+                {
+                    const int s = std::max(common[i].first, c.xs[q]), e = std::min(common[i].second, c.xe[q]);
+                    if (s < e)
+                    {
+                        tmp.emplace_back(s, e);
+                    }
+                    if (common[i].second < c.xe[q])
+                    {
+                        ++i;
+                    }
+                    else
+                    {
+                        ++q;
+                    }
+                }
+                common.swap(tmp);
+            }
+            // strips shorter than 8 columns are not worth a record: leave them to the single-row path
+            tmp.clear();
+            for (auto& iv : common)
+            {
+                if (iv.second - iv.first >= 8)
+                {
+                    tmp.push_back(iv);
+                }
+            }
+            common.swap(tmp);
+            for (int r = 0; r < R + 2; ++r)
+            {
+                prow[r].seek(mk_key(y0 - 1 + r, z0));
+            }
+            if (dim > 2)
+            {
+                for (int r = 0; r < R; ++r)
+                {
+                    pzm[r].seek(mk_key(y0 + r, z0 - 1));
+                    pzp[r].seek(mk_key(y0 + r, z0 + 1));
+                }
+            }
+            for (auto& iv : common)
+            {
+                const int s = iv.first, e = iv.second;
+                smr_item_fvstrip it;
+                std::memset(&it, 0, sizeof(it));
+                it.row[0]     = need(prow[0], "fv strip y-1", l, y0 - 1, z0, s, e - 1);
+                it.row[R + 1] = need(prow[R + 1], "fv strip y+R", l, y0 + R, z0, s, e - 1);
+                for (int r = 0; r < R; ++r)
+                {
+                    it.row[r + 1] = need(prow[r + 1], "fv strip x", l, y0 + r, z0, s - 1, e) + 1;
+                    if (dim > 2)
+                    {
+                        it.zm[r] = need(pzm[r], "fv strip z-1", l, y0 + r, z0 - 1, s, e - 1);
+                        it.zp[r] = need(pzp[r], "fv strip z+1", l, y0 + r, z0 + 1, s, e - 1);
+                    }
+                }
+                it.n     = e - s;
+                it.level = l;
+                strips.push_back(it);
+            }
+            // remainder of every row
+            for (int r = 0; r < R; ++r)
+            {
+                size_t i = 0;
+                for (int q = c.ptr[r0 + r]; q < c.ptr[r0 + r + 1]; ++q)
+                {
+                    int s = c.xs[q];
+                    const int e = c.xe[q];
+                    while (i < common.size() && common[i].second <= s)
+                    {
+                        ++i;
+                    }
+                    size_t j = i;
+                    while (s < e)
+                    {
+                        if (j >= common.size() || common[j].first >= e)
+                        {
+                            single(y0 + r, z0, s, e);
+                            break;
+                        }
+                        if (common[j].first > s)
+                        {
+                            single(y0 + r, z0, s, common[j].first);
+                        }
+                        s = std::max(s, common[j].second);
+                        ++j;
+                    }
+                }
+            }
+            r0 += R;
         }
     }
 
@@ -608,7 +785,9 @@ namespace smr
     struct MeshPlan
     {
         Arena arena;
-        Batch fv;                     // all leaves, level ascending
+        Batch fv;                     // all leaves, level ascending (initialisation, keep tags)
+        Batch fv_strip, fv_single;    // the same leaves split for the FV kernels (strips of rows + remainder)
+        int64_t fv_strip_cells = 0;
         std::vector<GhostPhase> down; // indexed by level (top-down sweep uses L..0)
         std::vector<Batch> pred;      // indexed by level (bottom-up sweep 1..L)
         Batch detail;                 // all coarse levels, ascending
@@ -925,7 +1104,8 @@ namespace smr
         const int dim = cfg.dim, L = cfg.max_level, lmin = cfg.min_level;
         const int nlev = m.nlev;
         plan.arena.clear();
-        std::vector<std::vector<smr_item_fv>> fv(nlev);
+        std::vector<std::vector<smr_item_fv>> fv(nlev), fv_single(nlev);
+        std::vector<std::vector<smr_item_fvstrip>> fv_strip(nlev);
         std::vector<PhaseItems> phases(nlev);
         std::vector<std::vector<smr_item_pred>> pred(nlev);
         std::vector<std::vector<smr_item_detail>> detail(nlev);
@@ -933,10 +1113,10 @@ namespace smr
         std::string error;
 #ifdef SMR_PLAN_TIMING
         const double tt0 = omp_get_wtime();
-        std::vector<double> task_t(5 * nlev, 0.0);
+        std::vector<double> task_t(6 * nlev, 0.0);
 #endif
         // one task per (kind, level): levels are independent once the mesh exists
-        const int ntasks = 5 * nlev;
+        const int ntasks = 6 * nlev;
 #pragma omp parallel for schedule(dynamic, 1)
         for (int t = ntasks - 1; t >= 0; --t)
         {
@@ -948,6 +1128,12 @@ namespace smr
             {
                 switch (kind)
                 {
+                    case 5:
+                        if (!m.cells[level].empty())
+                        {
+                            fv_split_items(m, level, fv_strip[level], fv_single[level]);
+                        }
+                        break;
                     case 4:
                         if (!m.cells[level].empty())
                         {
@@ -1013,6 +1199,8 @@ namespace smr
         plan.tag.assign(nlev, Batch());
         // layout (serial, cheap) then fill (parallel) straight into the staging arena
         Pending<smr_item_fv> p_fv{&plan.fv, B_FV, -1, {}, nullptr, false};
+        Pending<smr_item_fv> p_fv_single{&plan.fv_single, B_FV, -1, {}, nullptr, false};
+        Pending<smr_item_fvstrip> p_fv_strip{&plan.fv_strip, B_FV, -1, {}, nullptr, false, SMR_CTA_THREADS};
         Pending<smr_item_detail> p_detail{&plan.detail, B_DETAIL, -1, {}, &plan.detail_cum, false};
         Pending<smr_item_tag> p_tag_all{&plan.tag_all, B_TAG, -1, {}, &plan.tag_cum, true};
         std::vector<Pending<smr_item_proj>> p_proj(nlev);
@@ -1022,6 +1210,8 @@ namespace smr
         for (int l = 0; l < nlev; ++l)
         {
             p_fv.parts.push_back(&fv[l]);
+            p_fv_single.parts.push_back(&fv_single[l]);
+            p_fv_strip.parts.push_back(&fv_strip[l]);
             p_detail.parts.push_back(&detail[l]);
             p_tag_all.parts.push_back(&tag[l]);
             p_proj[l] = Pending<smr_item_proj>{&plan.down[l].proj, B_PROJ, l, {&phases[l].proj}, nullptr, false};
@@ -1030,6 +1220,9 @@ namespace smr
             p_bc[l]   = PendingBc{&plan.down[l].bc, l, &phases[l].bc.items, &phases[l].bc.srcs};
         }
         layout_batch(p_fv, plan.arena);
+        layout_batch(p_fv_single, plan.arena);
+        layout_batch(p_fv_strip, plan.arena);
+        plan.fv_strip_cells = plan.fv_strip.n_cells * SMR_STRIP_ROWS;
         layout_batch(p_detail, plan.arena);
         layout_batch(p_tag_all, plan.arena);
         for (int l = 0; l < nlev; ++l)
@@ -1041,9 +1234,17 @@ namespace smr
         }
         plan.arena.commit();
 #pragma omp parallel for schedule(dynamic, 1)
-        for (int t = 0; t < 3 + 4 * nlev; ++t)
+        for (int t = -2; t < 3 + 4 * nlev; ++t)
         {
-            if (t == 0)
+            if (t == -2)
+            {
+                fill_batch(p_fv_single, plan.arena);
+            }
+            else if (t == -1)
+            {
+                fill_batch(p_fv_strip, plan.arena);
+            }
+            else if (t == 0)
             {
                 fill_batch(p_fv, plan.arena);
             }

@@ -376,7 +376,11 @@ namespace smr
             return;
         }
         prof_begin();
-        const int n_ctas = static_cast<int>((n_cells + SMR_CTA_CELLS - 1) / SMR_CTA_CELLS);
+        if (b.cta_units != SMR_CTA_THREADS * Op::units_per_thread)
+        {
+            throw std::logic_error("batch laid out for a different CTA size than its kernel");
+        }
+        const int n_ctas = static_cast<int>((n_cells + b.cta_units - 1) / b.cta_units);
         batch_kernel<Item, Op><<<n_ctas, SMR_CTA_THREADS, 0, g.stream>>>(view_of<Item>(arena, b, n_cells), op);
         SMR_CUDA(cudaGetLastError());
         ++g.stats.kernel_launches;
@@ -450,6 +454,10 @@ namespace smr
     using UpwindOp = FvOp<D, false>;
     template <int D>
     using BurgersOp = FvOp<D, true>;
+    template <int D>
+    using UpwindStripOp = FvStripOp<D, false>;
+    template <int D>
+    using BurgersStripOp = FvStripOp<D, true>;
 
     static void launch_pred(int dim, int radius, const void* arena, const Batch& b, const double* src, double* dst)
     {
@@ -524,20 +532,38 @@ namespace smr
             p.half_abs_a[d] = .5 * std::abs(ad);
         }
         p.dt = dt;
+        // dx = scaling / 2^level: when `scaling` is a power of two so is dx, and dividing by it equals multiplying by
+        // its (exact) inverse for every finite operand, which spares the fp64 division sequence
+        int exp2      = 0;
+        p.exact_inv   = (std::frexp(cfg.scaling, &exp2) == 0.5) ? 1 : 0;
         for (int l = 0; l < SMR_MAX_LEVELS; ++l)
         {
-            p.dx[l] = cfg.cell_length(l);
+            p.dx[l]     = cfg.cell_length(l);
+            p.inv_dx[l] = 1.0 / p.dx[l];
         }
         const double* u = static_cast<const double*>(in.data.p);
         double* o       = static_cast<double*>(out.data.p);
         out.ghosts_valid = false;
+        if (g.profile && cfg.dim > 1)
+        {
+            g.prof_cells[SMR_FAM_FV] += static_cast<uint64_t>(mo.plan.fv_strip.n_cells) * (SMR_STRIP_ROWS - 1); // a strip unit = R cells
+        }
+        // strips of rows first (the bulk on uniform / smooth regions), then the single-row remainder
         if (burgers)
         {
-            launch_dim<BurgersOp, smr_item_fv>(SMR_FAM_FV, cfg.dim, mo.d_arena.p, mo.plan.fv, -1, u, o, p);
+            if (cfg.dim > 1)
+            {
+                launch_dim<BurgersStripOp, smr_item_fvstrip>(SMR_FAM_FV, cfg.dim, mo.d_arena.p, mo.plan.fv_strip, -1, u, o, p);
+            }
+            launch_dim<BurgersOp, smr_item_fv>(SMR_FAM_FV, cfg.dim, mo.d_arena.p, mo.plan.fv_single, -1, u, o, p);
         }
         else
         {
-            launch_dim<UpwindOp, smr_item_fv>(SMR_FAM_FV, cfg.dim, mo.d_arena.p, mo.plan.fv, -1, u, o, p);
+            if (cfg.dim > 1)
+            {
+                launch_dim<UpwindStripOp, smr_item_fvstrip>(SMR_FAM_FV, cfg.dim, mo.d_arena.p, mo.plan.fv_strip, -1, u, o, p);
+            }
+            launch_dim<UpwindOp, smr_item_fv>(SMR_FAM_FV, cfg.dim, mo.d_arena.p, mo.plan.fv_single, -1, u, o, p);
         }
     }
 

@@ -44,6 +44,18 @@ typedef struct
     int32_t pad;
 } smr_item_fv;
 
+/* SMR_STRIP_ROWS consecutive leaf rows (same z, y0 .. y0+R-1) sharing the x-range [start, start+n): one thread walks
+ * one column of the strip, so every value of the strip is fetched from L2 once instead of three times */
+#define SMR_STRIP_ROWS 4
+typedef struct
+{
+    int64_t row[SMR_STRIP_ROWS + 2]; /* offset of x = start in rows y0-1, y0, ..., y0+R */
+    int64_t zm[SMR_STRIP_ROWS];      /* 3D: same x, plane k-1, rows y0 .. y0+R-1 */
+    int64_t zp[SMR_STRIP_ROWS];
+    int32_t n; /* columns */
+    int32_t level;
+} smr_item_fvstrip;
+
 /* coarse interval filled by projection (numeric/projection.hpp:22-64) */
 typedef struct
 {

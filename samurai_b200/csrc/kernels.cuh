@@ -10,6 +10,10 @@
 #pragma once
 #include "items.h"
 
+#ifndef STRIP_MIN_BLOCKS
+#define STRIP_MIN_BLOCKS 6
+#endif
+
 #include <cuda_runtime.h>
 
 namespace smr
@@ -23,24 +27,73 @@ namespace smr
         int64_t n_cells;
     };
 
-    // body of one CTA of a batch: output cells [cta * SMR_CTA_CELLS, (cta + 1) * SMR_CTA_CELLS) ∩ [0, n_cells)
+    // body of one CTA of a batch: output units [cta * U, (cta + 1) * U) ∩ [0, n_cells), U = 256 * Op::units_per_thread
     template <class Item, class Op>
     __device__ __forceinline__ void run_batch_cta(const BatchView<Item>& b, const Op& op, int cta)
     {
-        __shared__ int64_t s_prefix[SMR_CTA_CELLS + 2];
-        const int first = b.cta_first[cta];
-        const int nloc  = b.cta_first[cta + 1] - first + 1;
+        constexpr int UPT   = Op::units_per_thread;
+        constexpr int UNITS = SMR_CTA_THREADS * UPT;
+        __shared__ int32_t s_prefix[UNITS + 2];
+        const int first    = b.cta_first[cta];
+        const int nloc     = b.cta_first[cta + 1] - first + 1;
+        const int64_t base = static_cast<int64_t>(cta) * UNITS;
+        const int64_t left = b.n_cells - base; // output units from `base` to the end of the batch
+        if (nloc == 1)
+        {
+            // the whole CTA lies inside one record (long intervals: uniform or nearly uniform levels): no staging,
+            // no search, the record is read once and every access is base pointer + small immediate
+            const Item it = b.items[first];
+            const int k0  = static_cast<int>(base - b.prefix[first]) + threadIdx.x;
+            if (left >= UNITS)
+            {
+                if constexpr (Op::two_phase)
+                {
+                    // __restrict__ on functor members does not let the compiler move loads above earlier stores, so ops
+                    // that are worth it expose load()/finish(): all loads first, then the arithmetic and the stores
+                    typename Op::Vals v[UPT];
+#pragma unroll
+                    for (int k = 0; k < UPT; ++k)
+                    {
+                        v[k] = op.load(it, k0 + k * SMR_CTA_THREADS);
+                    }
+#pragma unroll
+                    for (int k = 0; k < UPT; ++k)
+                    {
+                        op.finish(it, k0 + k * SMR_CTA_THREADS, v[k]);
+                    }
+                }
+                else
+                {
+#pragma unroll
+                    for (int k = 0; k < UPT; ++k)
+                    {
+                        op(it, k0 + k * SMR_CTA_THREADS);
+                    }
+                }
+                return;
+            }
+#pragma unroll
+            for (int k = 0; k < UPT; ++k)
+            {
+                if (static_cast<int64_t>(threadIdx.x) + k * SMR_CTA_THREADS < left)
+                {
+                    op(it, k0 + k * SMR_CTA_THREADS);
+                }
+            }
+            return;
+        }
+        // prefix relative to the CTA's first output unit: fits 32 bits (a record holds < 2^31 cells)
         for (int i = threadIdx.x; i <= nloc; i += SMR_CTA_THREADS)
         {
-            s_prefix[i] = b.prefix[first + i];
+            const int64_t rel = b.prefix[first + i] - base;
+            s_prefix[i]       = rel > 2 * UNITS ? 2 * UNITS : static_cast<int32_t>(rel < -2147483647LL ? -2147483647LL : rel);
         }
         __syncthreads();
-        const int64_t base = static_cast<int64_t>(cta) * SMR_CTA_CELLS;
 #pragma unroll
-        for (int k = 0; k < SMR_CELLS_PER_THREAD; ++k)
+        for (int k = 0; k < UPT; ++k)
         {
-            const int64_t g = base + threadIdx.x + k * SMR_CTA_THREADS;
-            if (g < b.n_cells)
+            const int g = threadIdx.x + k * SMR_CTA_THREADS;
+            if (g < left)
             {
                 int lo = 0, hi = nloc - 1;
                 while (lo < hi)
@@ -55,13 +108,13 @@ namespace smr
                         hi = mid - 1;
                     }
                 }
-                op(b.items[first + lo], static_cast<int>(g - s_prefix[lo]));
+                op(b.items[first + lo], g - s_prefix[lo]);
             }
         }
     }
 
     template <class Item, class Op>
-    __global__ void __launch_bounds__(SMR_CTA_THREADS) batch_kernel(BatchView<Item> b, Op op)
+    __global__ void __launch_bounds__(SMR_CTA_THREADS, Op::min_blocks) batch_kernel(BatchView<Item> b, Op op)
     {
         run_batch_cta(b, op, blockIdx.x);
     }
@@ -76,6 +129,8 @@ namespace smr
         double a[3];
         double dt;
         double dx[SMR_MAX_LEVELS];
+        double inv_dx[SMR_MAX_LEVELS]; // 1/dx, used when dx is a power of two (x / dx == x * (1/dx) bit for bit)
+        int exact_inv;
     };
 
     __device__ __forceinline__ double upwind_flux(double ha, double haa, double ul, double ur)
@@ -118,20 +173,107 @@ namespace smr
             return upwind_flux(p.half_a[d], p.half_abs_a[d], ul, ur);
         }
 
-        __device__ __forceinline__ void operator()(const smr_item_fv& it, int k) const
+        static constexpr bool two_phase = true;
+        static constexpr int min_blocks = 1;
+        static constexpr int units_per_thread = SMR_CELLS_PER_THREAD;
+
+        struct Vals
         {
+            double c, xm, xp, ym, yp, zm, zp;
+        };
+
+        __device__ __forceinline__ Vals load(const smr_item_fv& it, int k) const
+        {
+            Vals v;
             const double* c = u + it.c + k;
-            const double uc = c[0];
-            double acc      = -flux(0, c[-1], uc) + flux(0, uc, c[1]);
+            v.c             = c[0];
+            v.xm            = c[-1];
+            v.xp            = c[1];
+            v.ym = v.yp = v.zm = v.zp = 0.0;
             if (DIM > 1)
             {
-                acc = (acc + -flux(1, u[it.ym + k], uc)) + flux(1, uc, u[it.yp + k]);
+                v.ym = u[it.ym + k];
+                v.yp = u[it.yp + k];
             }
             if (DIM > 2)
             {
-                acc = (acc + -flux(2, u[it.zm + k], uc)) + flux(2, uc, u[it.zp + k]);
+                v.zm = u[it.zm + k];
+                v.zp = u[it.zp + k];
             }
-            out[it.c + k] = uc - p.dt * (acc / p.dx[it.level]);
+            return v;
+        }
+
+        __device__ __forceinline__ void finish(const smr_item_fv& it, int k, const Vals& v) const
+        {
+            const double uc = v.c;
+            double acc      = -flux(0, v.xm, uc) + flux(0, uc, v.xp);
+            if (DIM > 1)
+            {
+                acc = (acc + -flux(1, v.ym, uc)) + flux(1, uc, v.yp);
+            }
+            if (DIM > 2)
+            {
+                acc = (acc + -flux(2, v.zm, uc)) + flux(2, uc, v.zp);
+            }
+            const double div = p.exact_inv ? acc * p.inv_dx[it.level] : acc / p.dx[it.level];
+            out[it.c + k]    = uc - p.dt * div;
+        }
+
+        __device__ __forceinline__ void operator()(const smr_item_fv& it, int k) const
+        {
+            finish(it, k, load(it, k));
+        }
+    };
+
+    // Strip form of the same expression: the thread owns column k of SMR_STRIP_ROWS consecutive rows and keeps the column in
+    // registers, so a row is read from L2 once (as itself) instead of three times (as itself and as the j-1 / j+1
+    // neighbour of the rows around it).  Per cell the arithmetic is exactly FvOp's.
+    template <int DIM, bool BURGERS>
+    struct FvStripOp
+    {
+        static constexpr bool two_phase = false;
+        static constexpr int min_blocks = STRIP_MIN_BLOCKS;
+        static constexpr int units_per_thread = 1; // one column of the strip per thread, 256 x R cells per CTA
+
+        const double* __restrict__ u;
+        double* __restrict__ out;
+        FvParams p;
+
+        __device__ __forceinline__ double flux(int d, double ul, double ur) const
+        {
+            if (BURGERS)
+            {
+                return burgers_flux(p.a[d], ul, ur);
+            }
+            return upwind_flux(p.half_a[d], p.half_abs_a[d], ul, ur);
+        }
+
+        __device__ __forceinline__ void operator()(const smr_item_fvstrip& it, int k) const
+        {
+            constexpr int R = SMR_STRIP_ROWS;
+            // the column (the only loads that go to L2/DRAM) is fetched up front; the i-1 / i+1 values are L1 hits on lines
+            // the neighbouring lanes just brought in and are read row by row to keep the register footprint small
+            double v[R + 2];
+#pragma unroll
+            for (int r = 0; r < R + 2; ++r)
+            {
+                v[r] = u[it.row[r] + k];
+            }
+            const double inv = p.inv_dx[it.level], dx = p.dx[it.level];
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+            {
+                const double* c = u + it.row[r + 1] + k;
+                const double uc = v[r + 1];
+                double acc      = -flux(0, c[-1], uc) + flux(0, uc, c[1]);
+                acc             = (acc + -flux(1, v[r], uc)) + flux(1, uc, v[r + 2]);
+                if (DIM > 2)
+                {
+                    acc = (acc + -flux(2, u[it.zm[r] + k], uc)) + flux(2, uc, u[it.zp[r] + k]);
+                }
+                const double div       = p.exact_inv ? acc * inv : acc / dx;
+                out[it.row[r + 1] + k] = uc - p.dt * div;
+            }
         }
     };
 
@@ -141,6 +283,10 @@ namespace smr
     template <int DIM>
     struct ProjOp
     {
+        static constexpr bool two_phase = false;
+        static constexpr int min_blocks = 1;
+        static constexpr int units_per_thread = SMR_CELLS_PER_THREAD;
+
         const double* src; // may alias dst (ghost update projects inside one field)
         double* dst;
 
@@ -170,6 +316,10 @@ namespace smr
     template <int DIM, int RADIUS>
     struct PredOp
     {
+        static constexpr bool two_phase = false;
+        static constexpr int min_blocks = 1;
+        static constexpr int units_per_thread = SMR_CELLS_PER_THREAD;
+
         const double* src; // may alias dst (ghost update predicts inside one field)
         double* dst;
 
@@ -218,6 +368,10 @@ namespace smr
     template <int DIM, int RADIUS>
     struct DetailOp
     {
+        static constexpr bool two_phase = false;
+        static constexpr int min_blocks = 1;
+        static constexpr int units_per_thread = SMR_CELLS_PER_THREAD;
+
         const double* __restrict__ f;
         double* __restrict__ detail;
 
@@ -302,6 +456,10 @@ namespace smr
     template <int DIM>
     struct CriteriaOp
     {
+        static constexpr bool two_phase = false;
+        static constexpr int min_blocks = 1;
+        static constexpr int units_per_thread = SMR_CELLS_PER_THREAD;
+
         const double* __restrict__ detail; // ncomp arrays of `stride` entries (one per adapted field)
         uint8_t* __restrict__ tag;
         TagParams p;
@@ -374,6 +532,10 @@ namespace smr
     template <int DIM>
     struct MaximumOp
     {
+        static constexpr bool two_phase = false;
+        static constexpr int min_blocks = 1;
+        static constexpr int units_per_thread = SMR_CELLS_PER_THREAD;
+
         uint8_t* __restrict__ tag;
 
         __device__ __forceinline__ void operator()(const smr_item_tag& it, int k) const
@@ -416,6 +578,10 @@ namespace smr
     // tag[leaf] = keep (mr/adapt.hpp:286-290), driven by the FV leaf batch
     struct KeepLeavesOp
     {
+        static constexpr bool two_phase = false;
+        static constexpr int min_blocks = 1;
+        static constexpr int units_per_thread = SMR_CELLS_PER_THREAD;
+
         uint8_t* __restrict__ tag;
 
         __device__ __forceinline__ void operator()(const smr_item_fv& it, int k) const
@@ -429,6 +595,10 @@ namespace smr
     template <int DIM>
     struct InitBallOp
     {
+        static constexpr bool two_phase = false;
+        static constexpr int min_blocks = 1;
+        static constexpr int units_per_thread = SMR_CELLS_PER_THREAD;
+
         double* __restrict__ u;
         double origin[3];
         double scaling;
@@ -463,6 +633,10 @@ namespace smr
 
     struct CopyOp
     {
+        static constexpr bool two_phase = false;
+        static constexpr int min_blocks = 1;
+        static constexpr int units_per_thread = SMR_CELLS_PER_THREAD;
+
         const double* __restrict__ src;
         double* __restrict__ dst;
 
