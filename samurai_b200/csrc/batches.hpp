@@ -1200,7 +1200,7 @@ namespace smr
         // layout (serial, cheap) then fill (parallel) straight into the staging arena
         Pending<smr_item_fv> p_fv{&plan.fv, B_FV, -1, {}, nullptr, false};
         Pending<smr_item_fv> p_fv_single{&plan.fv_single, B_FV, -1, {}, nullptr, false};
-        Pending<smr_item_fvstrip> p_fv_strip{&plan.fv_strip, B_FV, -1, {}, nullptr, false, SMR_CTA_THREADS};
+        Pending<smr_item_fvstrip> p_fv_strip{&plan.fv_strip, B_FV, -1, {}, nullptr, false, SMR_CTA_THREADS * STRIP_UPT};
         Pending<smr_item_detail> p_detail{&plan.detail, B_DETAIL, -1, {}, &plan.detail_cum, false};
         Pending<smr_item_tag> p_tag_all{&plan.tag_all, B_TAG, -1, {}, &plan.tag_cum, true};
         std::vector<Pending<smr_item_proj>> p_proj(nlev);

@@ -47,6 +47,9 @@ typedef struct
 /* SMR_STRIP_ROWS consecutive leaf rows (same z, y0 .. y0+R-1) sharing the x-range [start, start+n): one thread walks
  * one column of the strip, so every value of the strip is fetched from L2 once instead of three times */
 #define SMR_STRIP_ROWS 4
+#ifndef STRIP_UPT
+#define STRIP_UPT 4 /* strip columns per thread (measured best on B200 with 6 CTAs/SM) */
+#endif
 typedef struct
 {
     int64_t row[SMR_STRIP_ROWS + 2]; /* offset of x = start in rows y0-1, y0, ..., y0+R */

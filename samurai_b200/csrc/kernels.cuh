@@ -10,6 +10,9 @@
 #pragma once
 #include "items.h"
 
+#ifndef STRIP_UPT
+#define STRIP_UPT 4
+#endif
 #ifndef STRIP_MIN_BLOCKS
 #define STRIP_MIN_BLOCKS 6
 #endif
@@ -233,7 +236,7 @@ namespace smr
     {
         static constexpr bool two_phase = false;
         static constexpr int min_blocks = STRIP_MIN_BLOCKS;
-        static constexpr int units_per_thread = 1; // one column of the strip per thread, 256 x R cells per CTA
+        static constexpr int units_per_thread = STRIP_UPT;
 
         const double* __restrict__ u;
         double* __restrict__ out;
