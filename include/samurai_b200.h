@@ -130,6 +130,21 @@ extern "C"
     int smr_adapt_last_tags(smr_mesh_t m, uint8_t* host, int64_t n);
     int smr_adapt_last_detail(smr_mesh_t m, double* host, int64_t n);
 
+    /* ---- multi-GPU: one process per GPU (reference: Boost.MPI domain decomposition, mesh.hpp:1032-1408 and the
+     * exchange_subdomains_merged rounds of algorithm/update_ghost_mr.hpp:125-187) ---------------------------------------
+     * Every rank holds the same global mesh; the domain is cut into `world` leaf-balanced slabs along the last axis
+     * and each rank computes the records whose output row lies in its slab.  Halo values are stored straight into the
+     * peers' field copies by the producing kernels (CUDA IPC mappings over NVLink) and a flag barrier separates the
+     * phases; tags are replicated so all ranks derive the same new mesh with no host communication.
+     * Call order: smr_init -> smr_mg_init -> exchange the 64-byte handles out of band -> smr_mg_connect. */
+    int smr_mg_init(int rank, int world, uint64_t pool_bytes); /* pool holds every field/detail/tag buffer */
+    int smr_mg_get_handle(void* out64);                        /* cudaIpcMemHandle_t of this rank's pool */
+    int smr_mg_connect(const void* handles);                   /* world x 64 bytes, indexed by rank */
+    int smr_mg_broadcast(smr_field_t f);                       /* make every rank's copy of f complete (before a download) */
+    /* re-cut the slabs from the current leaves (load_balancing/strategies/sfc.hpp role; uniform weights) */
+    int smr_mg_rebalance(const smr_field_t* fields, int n_fields);
+    int smr_mg_leaf_owners(smr_mesh_t m, int32_t* out, int64_t n); /* owner rank of every leaf, for_each_cell order */
+
     /* ---- instrumentation (timers.hpp: "mesh adaptation", "ghost update", ...) ------------------------------------ */
     typedef struct
     {

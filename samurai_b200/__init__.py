@@ -96,6 +96,12 @@ SYMBOLS = {
     "smr_adapt_last_detail": [_u64, _vp, _i64],
     "smr_stats_get": [_P(StatsC)],
     "smr_stats_reset": [],
+    "smr_mg_init": [_i32, _i32, _u64],
+    "smr_mg_get_handle": [_vp],
+    "smr_mg_connect": [_vp],
+    "smr_mg_broadcast": [_u64],
+    "smr_mg_rebalance": [_vp, _i32],
+    "smr_mg_leaf_owners": [_u64, _vp, _i64],
     "smr_debug_host_rebuild": [_u64, _i32, _P(_dbl), _P(_dbl), _P(_i64)],
     "smr_profile_enable": [_i32],
     "smr_profile_get": [_i32, _P(_u64), _P(_dbl), _P(_u64)],
@@ -149,6 +155,46 @@ def initialize(device=None):
     _check(lib.smr_init(device))
     _initialized = device
     return device >= 0
+
+
+def initialize_multi(rank, world, device=None, pool_bytes=8 << 30, exchange=None):
+    """One process per GPU. `exchange(bytes) -> list[bytes]` all-gathers the 64-byte IPC handles (rank order);
+    by default torch.distributed.all_gather_object is used. device < 0: host-only (partition logic without a GPU)."""
+    lib = load_library()
+    dev = rank if device is None else device
+    have = initialize(dev)
+    _check(lib.smr_mg_init(rank, world, pool_bytes if have else 0))
+    if have and world > 1:
+        buf = C.create_string_buffer(64)
+        _check(lib.smr_mg_get_handle(buf))
+        if exchange is None:
+            import torch.distributed as dist
+
+            def exchange(b):
+                out = [None] * world
+                dist.all_gather_object(out, b)
+                return out
+
+        allh = b"".join(exchange(buf.raw))
+        assert len(allh) == 64 * world
+        _check(lib.smr_mg_connect(allh))
+    return have
+
+
+def mg_broadcast(field):
+    _check(load_library().smr_mg_broadcast(field._h))
+
+
+def mg_rebalance(*fields):
+    arr = (C.c_uint64 * len(fields))(*[f._h for f in fields])
+    _check(load_library().smr_mg_rebalance(arr, len(fields)))
+
+
+def mg_leaf_owners(mesh):
+    n = mesh.nb_cells(CELLS)
+    out = np.empty(n, dtype=np.int32)
+    _check(load_library().smr_mg_leaf_owners(mesh._h, out.ctypes.data, n))
+    return out
 
 
 def finalize():

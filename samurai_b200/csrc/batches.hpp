@@ -254,6 +254,135 @@ namespace smr
         }
     }
 
+    // Multi-GPU ownership: the domain is cut into `world` slabs along the last axis (y in 2D, z in 3D) at positions that
+    // balance the leaf count; a record belongs to the rank whose slab contains the centre of its output row, and its
+    // outputs are also stored (over NVLink, by the producing thread) on every peer whose slab comes within `margin`
+    // cells of the row.  All ranks hold the same global mesh, so every rank derives the same cuts with no negotiation.
+    // Replaces the reference's MPI subdomains + interface sets (mesh.hpp:1032-1408, update_ghost_mr.hpp:63-187).
+    struct PlanFilter
+    {
+        int rank = 0, world = 1;
+        int dim = 2, L = 0;
+        int margin = 8; // cells of the record's level: stencil reach (<= 2) + strip height (4) + slack
+        std::vector<int64_t> cut2; // world + 1 cut positions in half cells of level L along the slab axis
+
+        bool active() const
+        {
+            return world > 1;
+        }
+
+        unsigned mask_all() const
+        {
+            return active() ? (((1u << world) - 1u) & ~(1u << rank)) : 0u;
+        }
+
+        int axis_coord(int y, int z) const
+        {
+            return dim > 2 ? z : y;
+        }
+
+        // centre of row j (level l) in half cells of level L, clamped into the domain
+        int64_t center2(int level, int j) const
+        {
+            const int sh = L - level;
+            int64_t c    = 2 * static_cast<int64_t>(j) + 1;
+            c            = sh >= 0 ? (c << sh) : (c >> (-sh));
+            return std::min(std::max<int64_t>(c, 1), cut2.back() - 1);
+        }
+
+        int owner(int level, int j) const
+        {
+            if (!active())
+            {
+                return 0;
+            }
+            const int64_t c = center2(level, j);
+            int r           = 0;
+            while (r + 1 < world && cut2[r + 1] <= c)
+            {
+                ++r;
+            }
+            return r;
+        }
+
+        bool owns(int level, int y, int z) const
+        {
+            return !active() || owner(level, axis_coord(y, z)) == rank;
+        }
+
+        // peers whose slab intersects rows [j - margin, j + rows + margin) of level l
+        unsigned mask(int level, int y, int z, int rows = 1) const
+        {
+            if (!active())
+            {
+                return 0;
+            }
+            const int j      = axis_coord(y, z);
+            const int sh     = L - level;
+            int64_t lo       = 2 * (static_cast<int64_t>(j) - margin);
+            int64_t hi       = 2 * (static_cast<int64_t>(j) + rows + margin);
+            lo               = sh >= 0 ? (lo << sh) : (lo >> (-sh));
+            hi               = sh >= 0 ? (hi << sh) : ((hi >> (-sh)) + 1);
+            unsigned m       = 0;
+            for (int r = 0; r < world; ++r)
+            {
+                if (r != rank && cut2[r] < hi && cut2[r + 1] > lo)
+                {
+                    m |= 1u << r;
+                }
+            }
+            return m;
+        }
+
+        // leaf-balanced cuts for mesh `m` (uniform weight per leaf, like load_balancing/weight.hpp:21)
+        void compute_cuts(const Mesh& m)
+        {
+            dim = m.cfg.dim;
+            L   = m.cfg.max_level;
+            const int axis   = dim > 2 ? 2 : 1;
+            const int64_t nL = static_cast<int64_t>(m.cfg.n0[axis]) << L;
+            cut2.assign(world + 1, 0);
+            cut2[world] = 2 * nL;
+            if (!active())
+            {
+                return;
+            }
+            std::vector<int64_t> w(static_cast<size_t>(nL), 0);
+            int64_t total = 0;
+            for (int l = 0; l < m.nlev; ++l)
+            {
+                const LevelSet& c = m.cells[l];
+                const int sh      = L - l;
+                for (size_t r = 0; r < c.rows(); ++r)
+                {
+                    const int j = axis_coord(key_y(c.key[r]), key_z(c.key[r]));
+                    int64_t n   = 0;
+                    for (int q = c.ptr[r]; q < c.ptr[r + 1]; ++q)
+                    {
+                        n += c.xe[q] - c.xs[q];
+                    }
+                    const int64_t bin = std::min(std::max<int64_t>(((2 * static_cast<int64_t>(j) + 1) << sh) >> 1, 0), nL - 1);
+                    w[static_cast<size_t>(bin)] += n;
+                    total += n;
+                }
+            }
+            int64_t acc = 0;
+            int k       = 1;
+            for (int64_t b = 0; b < nL && k < world; ++b)
+            {
+                acc += w[static_cast<size_t>(b)];
+                while (k < world && acc * world >= total * k)
+                {
+                    cut2[k++] = 2 * (b + 1);
+                }
+            }
+            for (; k < world; ++k)
+            {
+                cut2[k] = 2 * nL;
+            }
+        }
+    };
+
     [[noreturn]] inline void missing(const char* what, int level, int x, int y, int z)
     {
         throw std::out_of_range(std::string("interval not found in the reference mesh (") + what + ") at level " + std::to_string(level)
@@ -284,7 +413,7 @@ namespace smr
     // ---------------------------------------------------------------------------------------------------------
     // per-interval item builders
     // ---------------------------------------------------------------------------------------------------------
-    inline void fv_items(const Mesh& m, int l, std::vector<smr_item_fv>& out)
+    inline void fv_items(const Mesh& m, int l, const PlanFilter& flt, std::vector<smr_item_fv>& out)
     {
         const int dim = m.cfg.dim;
         const LevelSet& c   = m.cells[l];
@@ -294,6 +423,11 @@ namespace smr
         for (size_t r = 0; r < c.rows(); ++r)
         {
             const int y = key_y(c.key[r]), z = key_z(c.key[r]);
+            if (!flt.owns(l, y, z))
+            {
+                continue;
+            }
+            const int mask = static_cast<int>(flt.mask(l, y, z));
             pc.seek(c.key[r]);
             if (dim > 1)
             {
@@ -326,7 +460,7 @@ namespace smr
                 it.x     = s;
                 it.y     = y;
                 it.z     = z;
-                it.pad   = 0;
+                it.mask  = mask;
                 out.push_back(it);
             }
         }
@@ -334,7 +468,7 @@ namespace smr
 
     // Leaves of level l split for the FV kernels: strips of SMR_STRIP_ROWS consecutive rows sharing an x-range, and the
     // single-row remainder.  Every leaf cell lands in exactly one of the two lists.
-    inline void fv_split_items(const Mesh& m, int l, std::vector<smr_item_fvstrip>& strips, std::vector<smr_item_fv>& singles)
+    inline void fv_split_items(const Mesh& m, int l, const PlanFilter& flt, std::vector<smr_item_fvstrip>& strips, std::vector<smr_item_fv>& singles)
     {
         constexpr int R = SMR_STRIP_ROWS;
         const int dim   = m.cfg.dim;
@@ -342,7 +476,7 @@ namespace smr
         const LevelSet& ref = m.ref[l];
         if (dim < 2)
         {
-            fv_items(m, l, singles);
+            fv_items(m, l, flt, singles);
             return;
         }
         Probe prow[R + 2], pzm[R], pzp[R];
@@ -359,6 +493,10 @@ namespace smr
         std::vector<std::pair<int, int>> common, tmp;
         auto single = [&](int y, int z, int s, int e)
         {
+            if (!flt.owns(l, y, z))
+            {
+                return;
+            }
             smr_item_fv it;
             ps_c.seek(mk_key(y, z));
             ps_ym.seek(mk_key(y - 1, z));
@@ -379,7 +517,7 @@ namespace smr
             it.x     = s;
             it.y     = y;
             it.z     = z;
-            it.pad   = 0;
+            it.mask  = static_cast<int>(flt.mask(l, y, z));
             singles.push_back(it);
         };
         size_t r0 = 0;
@@ -453,8 +591,13 @@ namespace smr
                     pzp[r].seek(mk_key(y0 + r, z0 + 1));
                 }
             }
+            const bool own_strip = flt.owns(l, y0, z0);
             for (auto& iv : common)
             {
+                if (!own_strip)
+                {
+                    break;
+                }
                 const int s = iv.first, e = iv.second;
                 smr_item_fvstrip it;
                 std::memset(&it, 0, sizeof(it));
@@ -471,6 +614,7 @@ namespace smr
                 }
                 it.n     = e - s;
                 it.level = l;
+                it.mask  = static_cast<int>(flt.dim > 2 ? flt.mask(l, y0, z0) : flt.mask(l, y0, z0, R));
                 strips.push_back(it);
             }
             // remainder of every row
@@ -507,7 +651,7 @@ namespace smr
     }
 
     // coarse set `cs` at level lc (dst offsets from dst_ref) <- children rows in src_ref (level lc+1)
-    inline void proj_items(int dim, const LevelSet& cs, int lc, const LevelSet& dst_ref, const LevelSet& src_ref, std::vector<smr_item_proj>& out)
+    inline void proj_items(int dim, const LevelSet& cs, int lc, const LevelSet& dst_ref, const LevelSet& src_ref, const PlanFilter& flt, std::vector<smr_item_proj>& out)
     {
         Probe pd(dst_ref);
         Probe ps[4] = {Probe(src_ref), Probe(src_ref), Probe(src_ref), Probe(src_ref)};
@@ -516,6 +660,11 @@ namespace smr
         for (size_t r = 0; r < cs.rows(); ++r)
         {
             const int y = key_y(cs.key[r]), z = key_z(cs.key[r]);
+            if (!flt.owns(lc, y, z))
+            {
+                continue;
+            }
+            const int mask = static_cast<int>(flt.mask(lc, y, z));
             pd.seek(cs.key[r]);
             for (int cz = 0; cz < nz; ++cz)
             {
@@ -540,8 +689,8 @@ namespace smr
                         it.src[cy + 2 * cz] = need(ps[cy + 2 * cz], "projection src", lc + 1, 2 * y + cy, 2 * z + cz, 2 * s, 2 * e - 1);
                     }
                 }
-                it.n   = e - s;
-                it.pad = 0;
+                it.n    = e - s;
+                it.mask = mask;
                 out.push_back(it);
             }
         }
@@ -579,12 +728,12 @@ namespace smr
             }
         }
 
-        void add(int y, int z, int s, int e, int64_t dst, std::vector<smr_item_pred>& out)
+        void add(int y, int z, int s, int e, int64_t dst, unsigned mask, std::vector<smr_item_pred>& out)
         {
             smr_item_pred it;
             it.dst = dst;
             it.n   = e - s;
-            it.par = (s & 1) | ((dim > 1 ? (y & 1) : 0) << 1) | ((dim > 2 ? (z & 1) : 0) << 2);
+            it.par = (s & 1) | ((dim > 1 ? (y & 1) : 0) << 1) | ((dim > 2 ? (z & 1) : 0) << 2) | static_cast<int>(mask << 8);
             const int sc = s >> 1, ec = (e - 1) >> 1;
             for (int k = 0; k < 9; ++k)
             {
@@ -602,22 +751,27 @@ namespace smr
         }
     };
 
-    inline void pred_items(int dim, int radius, int lf, const LevelSet& fs, const LevelSet& src_ref, std::vector<smr_item_pred>& out)
+    inline void pred_items(int dim, int radius, int lf, const LevelSet& fs, const LevelSet& src_ref, const PlanFilter& flt, std::vector<smr_item_pred>& out)
     {
         PredBuilder pb(dim, radius, lf, src_ref);
         out.reserve(out.size() + fs.n_intervals());
         for (size_t r = 0; r < fs.rows(); ++r)
         {
             const int y = key_y(fs.key[r]), z = key_z(fs.key[r]);
+            if (!flt.owns(lf, y, z))
+            {
+                continue;
+            }
+            const unsigned mask = flt.mask(lf, y, z);
             pb.seek_row(y, z);
             for (int q = fs.ptr[r]; q < fs.ptr[r + 1]; ++q)
             {
-                pb.add(y, z, fs.xs[q], fs.xe[q], fs.off[q], out);
+                pb.add(y, z, fs.xs[q], fs.xe[q], fs.off[q], mask, out);
             }
         }
     }
 
-    inline void detail_items(const Mesh& m, int level, const LevelSet& cs, std::vector<smr_item_detail>& out)
+    inline void detail_items(const Mesh& m, int level, const LevelSet& cs, const PlanFilter& flt, std::vector<smr_item_detail>& out)
     {
         const int dim = m.cfg.dim, radius = m.cfg.pred_radius;
         const LevelSet& rc = m.ref[level];
@@ -637,6 +791,11 @@ namespace smr
         for (size_t r = 0; r < cs.rows(); ++r)
         {
             const int y = key_y(cs.key[r]), z = key_z(cs.key[r]);
+            if (!flt.owns(level, y, z))
+            {
+                continue;
+            }
+            const int mask = static_cast<int>(flt.mask(level, y, z));
             for (int rz = -rz_; rz <= rz_; ++rz)
             {
                 for (int ry = -ry_; ry <= ry_; ++ry)
@@ -671,13 +830,14 @@ namespace smr
                         it.fine[cy + 2 * cz] = need(pf[cy + 2 * cz], "detail fine", level + 1, 2 * y + cy, 2 * z + cz, 2 * s, 2 * e - 1);
                     }
                 }
-                it.n = e - s;
+                it.n    = e - s;
+                it.mask = mask;
                 out.push_back(it);
             }
         }
     }
 
-    inline void tag_items(const Mesh& m, int fine_level, const LevelSet& cs, std::vector<smr_item_tag>& out)
+    inline void tag_items(const Mesh& m, int fine_level, const LevelSet& cs, const PlanFilter& flt, std::vector<smr_item_tag>& out)
     {
         const int dim = m.cfg.dim;
         const LevelSet& rc = m.ref[fine_level - 1];
@@ -692,6 +852,10 @@ namespace smr
         for (size_t r = 0; r < cs.rows(); ++r)
         {
             const int y = key_y(cs.key[r]), z = key_z(cs.key[r]);
+            if (!flt.owns(fine_level - 1, y, z))
+            {
+                continue;
+            }
             pc.seek(cs.key[r]);
             for (int cz = 0; cz < nz; ++cz)
             {
@@ -714,7 +878,7 @@ namespace smr
                     }
                 }
                 it.n     = e - s;
-                it.level = fine_level;
+                it.level = fine_level | static_cast<int>(flt.mask_all() << 8); // tags are replicated on every rank
                 out.push_back(it);
             }
         }
@@ -804,22 +968,40 @@ namespace smr
 
         std::vector<smr_item_bc> items;
         std::vector<int64_t> srcs;
+        const PlanFilter* flt = nullptr;
+        int cur_mask          = 0;
+
+        // select the row of the ghost cells about to be emitted; false when another rank owns it
+        bool target(int level, int y, int z)
+        {
+            if (flt == nullptr || !flt->active())
+            {
+                cur_mask = 0;
+                return true;
+            }
+            if (!flt->owns(level, y, z))
+            {
+                return false;
+            }
+            cur_mask = static_cast<int>(flt->mask(level, y, z) << 8);
+            return true;
+        }
 
         void copy(int64_t dst, int64_t src)
         {
-            items.push_back({dst, 0.0, SMR_BC_COPY, 1, static_cast<int64_t>(srcs.size())});
+            items.push_back({dst, 0.0, SMR_BC_COPY | cur_mask, 1, static_cast<int64_t>(srcs.size())});
             srcs.push_back(src);
         }
 
         void value(int64_t dst, int64_t src, double coef)
         {
-            items.push_back({dst, coef, SMR_BC_VALUE, 1, static_cast<int64_t>(srcs.size())});
+            items.push_back({dst, coef, SMR_BC_VALUE | cur_mask, 1, static_cast<int64_t>(srcs.size())});
             srcs.push_back(src);
         }
 
         void begin_avg(int64_t dst)
         {
-            items.push_back({dst, 0.0, SMR_BC_AVG, 0, static_cast<int64_t>(srcs.size())});
+            items.push_back({dst, 0.0, SMR_BC_AVG | cur_mask, 0, static_cast<int64_t>(srcs.size())});
         }
 
         void add_src(int64_t src)
@@ -917,7 +1099,7 @@ namespace smr
                               const int64_t src = ref.offset_of(mk_key(cy, cz), cx, cx);
                               if (src >= 0)
                               {
-                                  emit(pl, need(m.ref[pl], "corner below", pl, y, z, x, x), src);
+                                  emit(pl, y, z, need(m.ref[pl], "corner below", pl, y, z, x, x), src);
                               }
                           });
             if (pl == 0)
@@ -927,11 +1109,12 @@ namespace smr
         }
     }
 
-    inline void build_ghost_phase(const Mesh& m, int level, PhaseItems& out)
+    inline void build_ghost_phase(const Mesh& m, int level, const PlanFilter& flt, PhaseItems& out)
     {
         const MeshConfig& cfg = m.cfg;
         const int dim = cfg.dim, L = cfg.max_level, lmin = cfg.min_level;
         BcBuilder& g          = out.bc;
+        g.flt                 = &flt;
         const LevelSet& ref   = m.ref[level];
         const bool have_below = level > 0 && !m.ref[level - 1].empty();
         if (ref.empty() && !have_below)
@@ -951,8 +1134,11 @@ namespace smr
                                   [&](int x, int y, int z)
                                   {
                                       const int64_t dst = need(ref, "corner ghost", level, y + d.v[1], z + d.v[2], x + d.v[0], x + d.v[0]);
-                                      g.copy(dst, need(ref, "corner cell", level, y, z, x, x));
                                       extrap_dst.push_back(dst);
+                                      if (g.target(level, y + d.v[1], z + d.v[2]))
+                                      {
+                                          g.copy(dst, need(ref, "corner cell", level, y, z, x, x));
+                                      }
                                   });
                 }
             }
@@ -965,13 +1151,16 @@ namespace smr
                     corner_below(m,
                                  level + 1,
                                  d,
-                                 [&](int pl, int64_t dst, int64_t src)
+                                 [&](int pl, int y, int z, int64_t dst, int64_t src)
                                  {
                                      if (pl == level && std::binary_search(extrap_dst.begin(), extrap_dst.end(), dst))
                                      {
                                          return; // overwritten by the extrapolation of this level before anything reads it
                                      }
-                                     g.copy(dst, src);
+                                     if (g.target(pl, y, z))
+                                     {
+                                         g.copy(dst, src);
+                                     }
                                  });
                 }
             }
@@ -986,6 +1175,10 @@ namespace smr
                 for (size_t r = 0; r < ghosts.rows(); ++r)
                 {
                     const int y = key_y(ghosts.key[r]), z = key_z(ghosts.key[r]);
+                    if (!g.target(level, y, z))
+                    {
+                        continue;
+                    }
                     for (int q = ghosts.ptr[r]; q < ghosts.ptr[r + 1]; ++q)
                     {
                         for (int x = ghosts.xs[q]; x < ghosts.xe[q]; ++x)
@@ -1031,11 +1224,18 @@ namespace smr
                 locate(bl, ref);
                 LevelSet gh = translate(bl, d.v[0], d.v[1], d.v[2]);
                 locate(gh, ref);
-                for (size_t q = 0; q < bl.xs.size(); ++q)
+                for (size_t r = 0; r < gh.rows(); ++r)
                 {
-                    for (int k = 0; k < bl.xe[q] - bl.xs[q]; ++k)
+                    if (!g.target(level, key_y(gh.key[r]), key_z(gh.key[r])))
                     {
-                        g.value(gh.off[q] + k, bl.off[q] + k, dx);
+                        continue;
+                    }
+                    for (int q = gh.ptr[r]; q < gh.ptr[r + 1]; ++q)
+                    {
+                        for (int k = 0; k < gh.xe[q] - gh.xs[q]; ++k)
+                        {
+                            g.value(gh.off[q] + k, bl.off[q] + k, dx);
+                        }
                     }
                 }
                 if (level < L && !bl.empty())
@@ -1046,6 +1246,10 @@ namespace smr
                     for (size_t r = 0; r < fine.rows(); ++r)
                     {
                         const int y = key_y(fine.key[r]), z = key_z(fine.key[r]);
+                        if (!g.target(level + 1, y, z))
+                        {
+                            continue;
+                        }
                         // the leaf behind the parent ghost: parent - d
                         pl.seek(mk_key((y >> 1) - d.v[1], (z >> 1) - d.v[2]));
                         for (int q = fine.ptr[r]; q < fine.ptr[r + 1]; ++q)
@@ -1063,7 +1267,7 @@ namespace smr
         if (level > 0 && !ref.empty())
         {
             LevelSet ps = set_inter(coarsen(ref, 1, dim), m.proj[level - 1]);
-            proj_items(dim, ps, level - 1, m.ref[level - 1], ref, out.proj);
+            proj_items(dim, ps, level - 1, m.ref[level - 1], ref, flt, out.proj);
         }
     }
 
@@ -1098,7 +1302,7 @@ namespace smr
         return set_inter(m.ref[fine_level - 1], coarsen(m.cells[fine_level], 1, m.cfg.dim));
     }
 
-    inline void build_plan(const Mesh& m, MeshPlan& plan)
+    inline void build_plan(const Mesh& m, MeshPlan& plan, const PlanFilter& flt = PlanFilter())
     {
         const MeshConfig& cfg = m.cfg;
         const int dim = cfg.dim, L = cfg.max_level, lmin = cfg.min_level;
@@ -1131,19 +1335,19 @@ namespace smr
                     case 5:
                         if (!m.cells[level].empty())
                         {
-                            fv_split_items(m, level, fv_strip[level], fv_single[level]);
+                            fv_split_items(m, level, flt, fv_strip[level], fv_single[level]);
                         }
                         break;
                     case 4:
                         if (!m.cells[level].empty())
                         {
-                            fv_items(m, level, fv[level]);
+                            fv_items(m, level, flt, fv[level]);
                         }
                         break;
                     case 3:
                         if (level <= L)
                         {
-                            build_ghost_phase(m, level, phases[level]);
+                            build_ghost_phase(m, level, flt, phases[level]);
                         }
                         break;
                     case 2:
@@ -1153,20 +1357,20 @@ namespace smr
                             if (!ps.empty())
                             {
                                 locate(ps, m.ref[level]);
-                                pred_items(dim, cfg.pred_radius, level, ps, m.ref[level - 1], pred[level]);
+                                pred_items(dim, cfg.pred_radius, level, ps, m.ref[level - 1], flt, pred[level]);
                             }
                         }
                         break;
                     case 1:
                         if (lmin != L && level >= std::max(lmin - 1, 0) && level < L)
                         {
-                            detail_items(m, level, detail_set(m, level), detail[level]);
+                            detail_items(m, level, detail_set(m, level), flt, detail[level]);
                         }
                         break;
                     default:
                         if (lmin != L && level >= std::max(lmin, 1) && level <= L)
                         {
-                            tag_items(m, level, tag_set(m, level), tag[level]);
+                            tag_items(m, level, tag_set(m, level), flt, tag[level]);
                         }
                         break;
                 }
@@ -1288,7 +1492,7 @@ namespace smr
         Batch copy, proj, pred;
     };
 
-    inline void build_transfer(const Mesh& old_m, const Mesh& new_m, TransferPlan& tp)
+    inline void build_transfer(const Mesh& old_m, const Mesh& new_m, TransferPlan& tp, const PlanFilter& flt = PlanFilter())
     {
         const MeshConfig& cfg = old_m.cfg;
         const int dim = cfg.dim;
@@ -1316,23 +1520,32 @@ namespace smr
                         LevelSet so = s;
                         locate(s, new_m.ref[l]);
                         locate(so, old_m.ref[l]);
-                        for (size_t q = 0; q < s.xs.size(); ++q)
+                        for (size_t r = 0; r < s.rows(); ++r)
                         {
-                            copies[l].push_back({s.off[q], so.off[q], s.xe[q] - s.xs[q], 0});
+                            const int y = key_y(s.key[r]), z = key_z(s.key[r]);
+                            if (!flt.owns(l, y, z))
+                            {
+                                continue;
+                            }
+                            const int mask = static_cast<int>(flt.mask(l, y, z));
+                            for (int q = s.ptr[r]; q < s.ptr[r + 1]; ++q)
+                            {
+                                copies[l].push_back({s.off[q], so.off[q], s.xe[q] - s.xs[q], mask});
+                            }
                         }
                     }
                 }
                 else if (l > cfg.min_level)
                 {
                     LevelSet sc = set_inter(coarsen(old_m.cells[l], 1, dim), new_m.cells[l - 1]);
-                    proj_items(dim, sc, l - 1, new_m.ref[l - 1], old_m.ref[l], projs[l]);
+                    proj_items(dim, sc, l - 1, new_m.ref[l - 1], old_m.ref[l], flt, projs[l]);
                     // set_refine = (new cells[l] ∩ old cells[l-1]).on(l-1); every coarse cell fills all its children
                     LevelSet sr = set_inter(coarsen(new_m.cells[l], 1, dim), old_m.cells[l - 1]);
                     if (!sr.empty())
                     {
                         LevelSet fine = refine(sr, 1, dim);
                         locate(fine, new_m.ref[l]);
-                        pred_items(dim, cfg.pred_radius, l, fine, old_m.ref[l - 1], preds[l]);
+                        pred_items(dim, cfg.pred_radius, l, fine, old_m.ref[l - 1], flt, preds[l]);
                     }
                 }
             }
@@ -1368,5 +1581,35 @@ namespace smr
 #pragma omp section
             fill_batch(p_pred, tp.arena);
         }
+    }
+
+    // Records that re-store every reference cell this rank owns to ALL peers (CopyOp with src == dst): after it every
+    // rank holds the complete field, which is what a re-cut of the slabs (and a host download) needs.
+    inline void build_broadcast(const Mesh& m, const PlanFilter& flt, TransferPlan& tp)
+    {
+        tp.arena.clear();
+        std::vector<std::vector<smr_item_copy>> copies(1);
+        const int mask = static_cast<int>(flt.mask_all());
+        for (int l = 0; l < m.nlev; ++l)
+        {
+            const LevelSet& r = m.ref[l];
+            for (size_t row = 0; row < r.rows(); ++row)
+            {
+                if (!flt.owns(l, key_y(r.key[row]), key_z(r.key[row])))
+                {
+                    continue;
+                }
+                for (int q = r.ptr[row]; q < r.ptr[row + 1]; ++q)
+                {
+                    copies[0].push_back({r.off[q], r.off[q], r.xe[q] - r.xs[q], mask});
+                }
+            }
+        }
+        Pending<smr_item_copy> p_copy{&tp.copy, B_COPY, -1, {&copies[0]}, nullptr, false};
+        tp.proj = Batch();
+        tp.pred = Batch();
+        layout_batch(p_copy, tp.arena);
+        tp.arena.commit();
+        fill_batch(p_copy, tp.arena);
     }
 } // namespace smr

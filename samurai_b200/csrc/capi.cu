@@ -27,10 +27,70 @@ namespace smr
         }                                                                                                                 \
     } while (0)
 
+    // Per-rank device pool for every buffer peers write into (fields, detail, tags).  All ranks issue the same sequence of
+    // allocations with the same sizes, so a buffer sits at the same pool offset on every rank and one address delta per
+    // peer reaches all of them (kernels.cuh: PeerTable).  First fit, deterministic.
+    struct Pool
+    {
+        char* base  = nullptr;
+        size_t size = 0;
+        std::vector<std::pair<size_t, size_t>> free_list; // (offset, bytes), sorted by offset
+
+        void init(char* b, size_t n, size_t reserved)
+        {
+            base = b;
+            size = n;
+            free_list.assign(1, {reserved, n - reserved});
+        }
+
+        void* alloc(size_t n)
+        {
+            n = (n + 255) & ~size_t(255);
+            for (size_t i = 0; i < free_list.size(); ++i)
+            {
+                if (free_list[i].second >= n)
+                {
+                    const size_t off = free_list[i].first;
+                    free_list[i].first += n;
+                    free_list[i].second -= n;
+                    if (free_list[i].second == 0)
+                    {
+                        free_list.erase(free_list.begin() + static_cast<std::ptrdiff_t>(i));
+                    }
+                    return base + off;
+                }
+            }
+            return nullptr;
+        }
+
+        void release(void* p, size_t n)
+        {
+            n                = (n + 255) & ~size_t(255);
+            const size_t off = static_cast<size_t>(static_cast<char*>(p) - base);
+            auto it          = std::lower_bound(free_list.begin(), free_list.end(), std::make_pair(off, size_t(0)));
+            it               = free_list.insert(it, {off, n});
+            if (it + 1 != free_list.end() && it->first + it->second == (it + 1)->first)
+            {
+                it->second += (it + 1)->second;
+                free_list.erase(it + 1);
+            }
+            if (it != free_list.begin() && (it - 1)->first + (it - 1)->second == it->first)
+            {
+                (it - 1)->second += it->second;
+                free_list.erase(it);
+            }
+        }
+    };
+
+    static Pool g_pool;
+    static bool g_pool_on = false;
+
     struct DevBuf
     {
-        void* p    = nullptr;
-        size_t cap = 0;
+        void* p     = nullptr;
+        size_t cap  = 0;
+        bool shared = false; // peers store into it: must live in the pool when running multi-GPU
+        bool pooled = false;
 
         void ensure(size_t bytes)
         {
@@ -38,7 +98,21 @@ namespace smr
             {
                 release();
                 size_t want = bytes + bytes / 4 + 4096;
-                SMR_CUDA(cudaMalloc(&p, want));
+                if (shared && g_pool_on)
+                {
+                    want = (want + 255) & ~size_t(255);
+                    p    = g_pool.alloc(want);
+                    if (!p)
+                    {
+                        throw CudaError("multi-GPU pool exhausted: pass a larger pool_bytes to smr_mg_init");
+                    }
+                    pooled = true;
+                }
+                else
+                {
+                    SMR_CUDA(cudaMalloc(&p, want));
+                    pooled = false;
+                }
                 cap = want;
             }
         }
@@ -47,7 +121,14 @@ namespace smr
         {
             if (p)
             {
-                cudaFree(p);
+                if (pooled)
+                {
+                    g_pool.release(p, cap);
+                }
+                else
+                {
+                    cudaFree(p);
+                }
             }
             p   = nullptr;
             cap = 0;
@@ -66,6 +147,7 @@ namespace smr
         {
             std::swap(p, o.p);
             std::swap(cap, o.cap);
+            std::swap(pooled, o.pooled);
         }
     };
 
@@ -106,6 +188,13 @@ namespace smr
         bool plan_ready = false;
         DevBuf d_arena;
         DevBuf d_detail, d_tag;
+        PlanFilter filter; // multi-GPU slab ownership for this mesh (identity when world == 1)
+
+        MeshObj()
+        {
+            d_detail.shared = true;
+            d_tag.shared    = true;
+        }
         PinnedBuf h_tag;
         int64_t last_size   = 0;
         int last_ncomp      = 0;
@@ -123,6 +212,12 @@ namespace smr
         int bc_type  = -1;
         double bc_value = 0;
         bool ghosts_valid = false; // Field::ghosts_updated() (field/field_base.hpp:264-274)
+
+        FieldObj()
+        {
+            data.shared  = true;
+            spare.shared = true;
+        }
     };
 
     struct Ctx
@@ -142,6 +237,13 @@ namespace smr
         std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pool;
         DevBuf d_transfer;
         TransferPlan transfer; // reused so its pinned arena is allocated once
+        // multi-GPU
+        int mg_rank = 0, mg_world = 1;
+        void* mg_pool            = nullptr;
+        size_t mg_pool_bytes     = 0;
+        unsigned long long epoch = 0;
+        void* mg_peer_base[SMR_MAX_RANKS] = {};
+        bool mg_connected        = false;
         std::unordered_map<uint64_t, std::unique_ptr<MeshObj>> meshes;
         std::unordered_map<uint64_t, std::unique_ptr<FieldObj>> fields;
     };
@@ -247,6 +349,31 @@ namespace smr
         }
     }
 
+    // cross-GPU phase barrier: queued after every launch whose outputs a peer may read (and after local memsets/copies of
+    // buffers a peer may write next)
+    static void mg_barrier()
+    {
+        if (g.mg_world > 1 && g.mg_connected)
+        {
+            mg_barrier_kernel<<<1, 32, 0, g.stream>>>(++g.epoch);
+            SMR_CUDA(cudaGetLastError());
+            ++g.stats.kernel_launches;
+        }
+    }
+
+    static void mg_check_error()
+    {
+        if (g.mg_world > 1 && g.mg_connected)
+        {
+            unsigned long long err = 0;
+            SMR_CUDA(cudaMemcpy(&err, static_cast<char*>(g.mg_pool) + 1024, sizeof(err), cudaMemcpyDeviceToHost));
+            if (err != 0)
+            {
+                throw CudaError("multi-GPU barrier timed out at epoch " + std::to_string(err) + " (a peer stopped)");
+            }
+        }
+    }
+
     static MeshObj& get_mesh(smr_mesh_t h)
     {
         auto it = g.meshes.find(h);
@@ -348,7 +475,19 @@ namespace smr
             return;
         }
         const double t0 = now();
-        build_plan(mo.mesh, mo.plan);
+        if (mo.filter.world != g.mg_world || mo.filter.cut2.empty())
+        {
+            mo.filter.rank  = g.mg_rank;
+            mo.filter.world = g.mg_world;
+            mo.filter.compute_cuts(mo.mesh);
+        }
+        else
+        {
+            // keep the cuts across adaptations (data only lives near its owner): re-cut with smr_mg_rebalance
+            mo.filter.dim = mo.mesh.cfg.dim;
+            mo.filter.L   = mo.mesh.cfg.max_level;
+        }
+        build_plan(mo.mesh, mo.plan, mo.filter);
         g.stats.host_batch_seconds += now() - t0;
         // the previous arena may still be in use by queued kernels: stream-ordered, so a sync is needed before reuse
         SMR_CUDA(cudaStreamSynchronize(g.stream));
@@ -373,6 +512,7 @@ namespace smr
         const int64_t n_cells = limit < 0 ? b.n_cells : std::min(limit, b.n_cells);
         if (b.empty() || n_cells <= 0)
         {
+            mg_barrier(); // every rank queues the same number of barriers whatever its share of the records
             return;
         }
         prof_begin();
@@ -385,12 +525,14 @@ namespace smr
         SMR_CUDA(cudaGetLastError());
         ++g.stats.kernel_launches;
         prof_end(fam, n_cells);
+        mg_barrier();
     }
 
     static void launch_ghost_phase(int dim, const void* arena, const GhostPhase& ph, double* f, int bc_type, double bc_value)
     {
         if (ph.bc.empty() && ph.proj.empty())
         {
+            mg_barrier();
             return;
         }
         const char* base = static_cast<const char*>(arena);
@@ -423,6 +565,7 @@ namespace smr
         SMR_CUDA(cudaGetLastError());
         ++g.stats.kernel_launches;
         prof_end(ph.proj.n_cells >= ph.bc.n_items ? SMR_FAM_PROJ : SMR_FAM_BC, ph.proj.n_cells + ph.bc.n_items);
+        mg_barrier();
     }
 
     template <template <int> class OpT, class Item, class... Args>
@@ -593,7 +736,8 @@ namespace smr
         uint8_t* tag      = static_cast<uint8_t*>(mo.d_tag.p);
         double* detail    = static_cast<double*>(mo.d_detail.p);
         const void* arena = mo.d_arena.p;
-        launch<smr_item_fv>(SMR_FAM_KEEP, arena, mo.plan.fv, KeepLeavesOp{tag});
+        mg_barrier(); // local memsets done everywhere before any peer stores a tag
+        launch<smr_item_fv>(SMR_FAM_KEEP, arena, mo.plan.fv, KeepLeavesOp{tag, mo.filter.mask_all()});
         for (auto* f : fields)
         {
             do_update_ghost(*f);
@@ -690,7 +834,7 @@ namespace smr
         t0 = now();
         TransferPlan& tpn = g.transfer;
         SMR_CUDA(cudaStreamSynchronize(g.stream)); // the previous transfer upload must have left the staging arena
-        build_transfer(mo.mesh, *new_mesh, tpn);
+        build_transfer(mo.mesh, *new_mesh, tpn, mo.filter);
         g.stats.host_batch_seconds += now() - t0;
         DevBuf& d_tr = g.d_transfer;
         const int64_t nn = new_mesh->nref;
@@ -704,6 +848,7 @@ namespace smr
         {
             DevBuf* nb = &f->spare;
             SMR_CUDA(cudaMemsetAsync(nb->p, 0, static_cast<size_t>(nn) * sizeof(double), g.stream));
+            mg_barrier();
             const double* src = static_cast<const double*>(f->data.p);
             double* dst       = static_cast<double*>(nb->p);
             launch<smr_item_copy>(SMR_FAM_COPY, d_tr.p, tpn.copy, CopyOp{src, dst});
@@ -1088,14 +1233,17 @@ extern "C"
                 FieldObj& f = get_field(fh);
                 check_field_ready(f);
                 f.ghosts_valid = false;
+                mg_barrier();
                 if (v == 0.0)
                 {
                     SMR_CUDA(cudaMemsetAsync(f.data.p, 0, static_cast<size_t>(f.n) * sizeof(double), g.stream));
+                    mg_barrier();
                 }
                 else
                 {
                     std::vector<double> h(static_cast<size_t>(f.n), v);
                     SMR_CUDA(cudaMemcpyAsync(f.data.p, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+                    mg_barrier();
                     SMR_CUDA(cudaStreamSynchronize(g.stream));
                 }
             });
@@ -1123,7 +1271,9 @@ extern "C"
                     throw std::invalid_argument("upload size does not match the field size");
                 }
                 f.ghosts_valid = false;
+                mg_barrier(); // nobody is still storing into this buffer
                 SMR_CUDA(cudaMemcpyAsync(f.data.p, host, static_cast<size_t>(n) * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+                mg_barrier();
                 g.stats.h2d_bytes += static_cast<uint64_t>(n) * sizeof(double);
             });
     }
@@ -1296,6 +1446,180 @@ extern "C"
                     ++g.stats.mesh_rebuilds;
                 }
                 g.stats.host_mesh_seconds += now() - t0;
+            });
+    }
+
+    // ---------------------------------------------------------------------------------------------------------------
+    // multi-GPU (one process per GPU; peers reached through CUDA IPC mappings of each rank's pool)
+    // ---------------------------------------------------------------------------------------------------------------
+    int smr_mg_init(int rank, int world, uint64_t pool_bytes)
+    {
+        return guarded(
+            [&]
+            {
+                if (world < 1 || world > SMR_MAX_RANKS || rank < 0 || rank >= world)
+                {
+                    throw std::invalid_argument("smr_mg_init: need 0 <= rank < world <= 8");
+                }
+                if (!g.meshes.empty() || !g.fields.empty())
+                {
+                    throw std::invalid_argument("smr_mg_init must be called before any mesh or field exists");
+                }
+                g.mg_rank      = rank;
+                g.mg_world     = world;
+                g.mg_connected = false;
+                if (world > 1 && g.device)
+                {
+                    if (pool_bytes < (1u << 20))
+                    {
+                        throw std::invalid_argument("smr_mg_init: pool_bytes too small");
+                    }
+                    SMR_CUDA(cudaMalloc(&g.mg_pool, pool_bytes));
+                    SMR_CUDA(cudaMemset(g.mg_pool, 0, 4096));
+                    g.mg_pool_bytes = pool_bytes;
+                    g_pool.init(static_cast<char*>(g.mg_pool), pool_bytes, 4096);
+                    g_pool_on = true;
+                }
+            });
+    }
+
+    int smr_mg_get_handle(void* out64)
+    {
+        return guarded(
+            [&]
+            {
+                require_device();
+                if (!g.mg_pool)
+                {
+                    throw std::invalid_argument("smr_mg_get_handle: no pool (world == 1?)");
+                }
+                static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+                cudaIpcMemHandle_t h;
+                SMR_CUDA(cudaIpcGetMemHandle(&h, g.mg_pool));
+                std::memcpy(out64, &h, 64);
+            });
+    }
+
+    int smr_mg_connect(const void* handles)
+    {
+        return guarded(
+            [&]
+            {
+                require_device();
+                if (g.mg_world < 2)
+                {
+                    return;
+                }
+                PeerTable t{};
+                t.rank  = g.mg_rank;
+                t.world = g.mg_world;
+                t.flags = static_cast<unsigned long long*>(g.mg_pool);
+                t.error = reinterpret_cast<unsigned long long*>(static_cast<char*>(g.mg_pool) + 1024);
+                for (int p = 0; p < g.mg_world; ++p)
+                {
+                    if (p == g.mg_rank)
+                    {
+                        g.mg_peer_base[p] = g.mg_pool;
+                    }
+                    else
+                    {
+                        cudaIpcMemHandle_t h;
+                        std::memcpy(&h, static_cast<const char*>(handles) + 64 * p, 64);
+                        SMR_CUDA(cudaIpcOpenMemHandle(&g.mg_peer_base[p], h, cudaIpcMemLazyEnablePeerAccess));
+                    }
+                    t.delta[p] = static_cast<long long>(static_cast<char*>(g.mg_peer_base[p]) - static_cast<char*>(g.mg_pool));
+                }
+                SMR_CUDA(cudaMemcpyToSymbol(g_peers, &t, sizeof(t)));
+                g.mg_connected = true;
+            });
+    }
+
+    // every rank re-stores the reference cells it owns into all peers: afterwards each rank holds the complete field
+    static void do_broadcast(FieldObj& f)
+    {
+        MeshObj& mo = *f.mesh;
+        check_field_ready(f);
+        ensure_plan(mo);
+        if (g.mg_world < 2)
+        {
+            return;
+        }
+        SMR_CUDA(cudaStreamSynchronize(g.stream));
+        build_broadcast(mo.mesh, mo.filter, g.transfer);
+        upload_arena(g.transfer.arena, g.d_transfer);
+        double* u = static_cast<double*>(f.data.p);
+        launch<smr_item_copy>(SMR_FAM_COPY, g.d_transfer.p, g.transfer.copy, CopyOp{u, u});
+    }
+
+    int smr_mg_broadcast(smr_field_t fh)
+    {
+        return guarded(
+            [&]
+            {
+                require_device();
+                do_broadcast(get_field(fh));
+                SMR_CUDA(cudaStreamSynchronize(g.stream));
+                mg_check_error();
+            });
+    }
+
+    int smr_mg_rebalance(const smr_field_t* fields, int n_fields)
+    {
+        return guarded(
+            [&]
+            {
+                require_device();
+                if (n_fields < 1)
+                {
+                    throw std::invalid_argument("smr_mg_rebalance needs at least one field");
+                }
+                MeshObj& mo = *get_field(fields[0]).mesh;
+                for (int i = 0; i < n_fields; ++i)
+                {
+                    do_broadcast(get_field(fields[i]));
+                }
+                SMR_CUDA(cudaStreamSynchronize(g.stream));
+                mg_check_error();
+                mo.filter.rank  = g.mg_rank;
+                mo.filter.world = g.mg_world;
+                mo.filter.compute_cuts(mo.mesh);
+                mo.plan_ready = false;
+            });
+    }
+
+    int smr_mg_leaf_owners(smr_mesh_t m, int32_t* out, int64_t n)
+    {
+        return guarded(
+            [&]
+            {
+                MeshObj& mo = get_mesh(m);
+                if (n != mo.mesh.nleaves)
+                {
+                    throw std::invalid_argument("smr_mg_leaf_owners: n must equal nb_cells(cells)");
+                }
+                PlanFilter flt = mo.filter;
+                if (flt.world != g.mg_world || flt.cut2.empty())
+                {
+                    flt.rank  = g.mg_rank;
+                    flt.world = g.mg_world;
+                    flt.compute_cuts(mo.mesh);
+                }
+                int64_t k = 0;
+                for (int l = 0; l < mo.mesh.nlev; ++l)
+                {
+                    const LevelSet& c = mo.mesh.cells[l];
+                    for (size_t r = 0; r < c.rows(); ++r)
+                    {
+                        const int o = flt.owner(l, flt.axis_coord(key_y(c.key[r]), key_z(c.key[r])));
+                        for (int q = c.ptr[r]; q < c.ptr[r + 1]; ++q)
+                        {
+                            for (int x = c.xs[q]; x < c.xe[q]; ++x)
+                            {
+                                out[k++] = o;
+                            }
+                        }
+                    }
+                }
             });
     }
 

@@ -15,6 +15,7 @@
 #define SMR_CELLS_PER_THREAD 4
 #define SMR_CTA_CELLS (SMR_CTA_THREADS * SMR_CELLS_PER_THREAD)
 #define SMR_MAX_LEVELS 24
+#define SMR_MAX_RANKS 8
 
 /* kernel families, for the per-family profile (smr_profile_get) */
 enum
@@ -41,7 +42,7 @@ typedef struct
     int32_t n;
     int32_t level;
     int32_t x, y, z; /* integer coordinates of the first cell (cell.hpp:32-77) */
-    int32_t pad;
+    int32_t mask;    /* multi-GPU: peers that also receive this record's outputs (bit p = rank p) */
 } smr_item_fv;
 
 /* SMR_STRIP_ROWS consecutive leaf rows (same z, y0 .. y0+R-1) sharing the x-range [start, start+n): one thread walks
@@ -57,6 +58,8 @@ typedef struct
     int64_t zp[SMR_STRIP_ROWS];
     int32_t n; /* columns */
     int32_t level;
+    int32_t mask;
+    int32_t pad;
 } smr_item_fvstrip;
 
 /* coarse interval filled by projection (numeric/projection.hpp:22-64) */
@@ -65,7 +68,7 @@ typedef struct
     int64_t dst;    /* coarse offset */
     int64_t src[4]; /* fine offset of x = 2*start in rows (2y+cy, 2z+cz), index cy + 2*cz */
     int32_t n;
-    int32_t pad;
+    int32_t mask;
 } smr_item_proj;
 
 /* fine interval filled by prediction (numeric/prediction.hpp:259-361, 149-257) */
@@ -74,7 +77,7 @@ typedef struct
     int64_t dst;    /* fine offset of x = start */
     int64_t src[9]; /* coarse offset of x = start>>1 in rows (y>>1 + ry - 1, z>>1 + rz - 1), index ry + 3*rz */
     int32_t n;
-    int32_t par; /* bit0: start & 1, bit1: y & 1, bit2: z & 1 */
+    int32_t par; /* bit0: start & 1, bit1: y & 1, bit2: z & 1; bits 8-15: multi-GPU peer mask */
 } smr_item_pred;
 
 /* coarse interval whose 2^dim children get a detail (mr/operators.hpp:139-533) */
@@ -83,7 +86,7 @@ typedef struct
     int64_t coarse[9]; /* offset of x = start in rows (y + ry - 1, z + rz - 1), index ry + 3*rz */
     int64_t fine[4];   /* offset of x = 2*start in rows (2y+cy, 2z+cz), index cy + 2*cz */
     int32_t n;
-    int32_t pad;
+    int32_t mask;
 } smr_item_detail;
 
 /* coarse interval for the tagging criteria and the keep propagation (mr/criteria.hpp, mr/operators.hpp:29-89) */
@@ -92,7 +95,7 @@ typedef struct
     int64_t coarse;
     int64_t fine[4];
     int32_t n;
-    int32_t level; /* level of the children */
+    int32_t level; /* bits 0-7: level of the children; bits 8-15: multi-GPU peer mask */
 } smr_item_tag;
 
 typedef struct
@@ -100,7 +103,7 @@ typedef struct
     int64_t dst;
     int64_t src;
     int32_t n;
-    int32_t pad;
+    int32_t mask;
 } smr_item_copy;
 
 /* one boundary ghost cell (algorithm/update_outer_ghost.hpp, bc/apply_field_bc.hpp) */
@@ -115,7 +118,7 @@ typedef struct
 {
     int64_t dst;
     double coef;
-    int32_t kind;
+    int32_t kind; /* bits 0-7: SMR_BC_*; bits 8-15: multi-GPU peer mask */
     int32_t n_src;
     int64_t src_first; /* index into the batch's int64 source-offset array */
 } smr_item_bc;

@@ -21,6 +21,63 @@
 
 namespace smr
 {
+    // ------------------------------------------------------------------------------------------------------------
+    // multi-GPU: every buffer kernels write lives in a per-rank pool mapped into all peers (CUDA IPC) at the same
+    // offsets, so the address of a cell in peer p's copy is the local address + delta[p].  A record's mask says which
+    // peers need its outputs (their slab, widened by the stencil reach, contains the record): the producing thread
+    // stores there directly over NVLink, fused into the kernel -- no pack / send / unpack pass.
+    // ------------------------------------------------------------------------------------------------------------
+    struct PeerTable
+    {
+        long long delta[SMR_MAX_RANKS]; // peer pool base - local pool base, bytes
+        unsigned long long* flags;      // local barrier flags, one per rank
+        unsigned long long* error;      // set when a barrier times out
+        int rank, world;
+    };
+
+    __constant__ PeerTable g_peers;
+
+    template <class T>
+    __device__ __forceinline__ void mstore(T* addr, T v, unsigned mask)
+    {
+        *addr = v;
+        if (mask)
+        {
+#pragma unroll
+            for (int p = 0; p < SMR_MAX_RANKS; ++p)
+            {
+                if ((mask >> p) & 1u)
+                {
+                    *reinterpret_cast<T*>(reinterpret_cast<char*>(addr) + g_peers.delta[p]) = v;
+                }
+            }
+        }
+    }
+
+    // all ranks have finished everything queued before this kernel (and their peer stores have landed) once it returns
+    __global__ void mg_barrier_kernel(unsigned long long epoch)
+    {
+        const int t = threadIdx.x;
+        if (t < g_peers.world && t != g_peers.rank)
+        {
+            __threadfence_system();
+            volatile unsigned long long* remote = reinterpret_cast<volatile unsigned long long*>(
+                reinterpret_cast<char*>(g_peers.flags) + g_peers.delta[t]);
+            remote[g_peers.rank] = epoch;
+            __threadfence_system();
+            volatile unsigned long long* mine = g_peers.flags;
+            long long spins                   = 0;
+            while (mine[t] < epoch)
+            {
+                if (++spins > 400000000LL) // ~ a second: a peer died; fail loudly instead of hanging the GPU
+                {
+                    *g_peers.error = epoch;
+                    break;
+                }
+            }
+        }
+    }
+
     template <class Item>
     struct BatchView
     {
@@ -219,7 +276,7 @@ namespace smr
                 acc = (acc + -flux(2, v.zm, uc)) + flux(2, uc, v.zp);
             }
             const double div = p.exact_inv ? acc * p.inv_dx[it.level] : acc / p.dx[it.level];
-            out[it.c + k]    = uc - p.dt * div;
+            mstore(out + it.c + k, uc - p.dt * div, static_cast<unsigned>(it.mask));
         }
 
         __device__ __forceinline__ void operator()(const smr_item_fv& it, int k) const
@@ -275,7 +332,7 @@ namespace smr
                     acc = (acc + -flux(2, u[it.zm[r] + k], uc)) + flux(2, uc, u[it.zp[r] + k]);
                 }
                 const double div       = p.exact_inv ? acc * inv : acc / dx;
-                out[it.row[r + 1] + k] = uc - p.dt * div;
+                mstore(out + it.row[r + 1] + k, uc - p.dt * div, static_cast<unsigned>(it.mask));
             }
         }
     };
@@ -302,7 +359,7 @@ namespace smr
                 const double* s = src + it.src[r] + 2 * k;
                 sum += s[0] + s[1];
             }
-            dst[it.dst + k] = sum * (1.0 / static_cast<double>(1 << DIM));
+            mstore(dst + it.dst + k, sum * (1.0 / static_cast<double>(1 << DIM)), static_cast<unsigned>(it.mask));
         }
     };
 
@@ -331,7 +388,7 @@ namespace smr
             const int ic = ((it.par & 1) + k) >> 1;
             if (RADIUS == 0)
             {
-                dst[it.dst + k] = src[it.src[4] + ic];
+                mstore(dst + it.dst + k, src[it.src[4] + ic], static_cast<unsigned>(it.par) >> 8);
                 return;
             }
             const int px = (it.par ^ k) & 1;
@@ -361,7 +418,7 @@ namespace smr
                     }
                 }
             }
-            dst[it.dst + k] = val;
+            mstore(dst + it.dst + k, val, static_cast<unsigned>(it.par) >> 8);
         }
     };
 
@@ -439,8 +496,8 @@ namespace smr
             for (int r = 0; r < NR; ++r)
             {
                 double* o = detail + it.fine[r] + 2 * k;
-                o[0]      = d[r][0];
-                o[1]      = d[r][1];
+                mstore(o, d[r][0], static_cast<unsigned>(it.mask));
+                mstore(o + 1, d[r][1], static_cast<unsigned>(it.mask));
             }
         }
     };
@@ -472,8 +529,9 @@ namespace smr
         __device__ __forceinline__ void operator()(const smr_item_tag& it, int k) const
         {
             constexpr int NR = 1 << (DIM - 1);
-            const int fl     = it.level;
-            bool coarsen_ok  = fl > p.min_level;
+            const int fl        = it.level & 0xff;
+            const unsigned mask = static_cast<unsigned>(it.level) >> 8;
+            bool coarsen_ok     = fl > p.min_level;
             bool refine[NR][2];
 #pragma unroll
             for (int r = 0; r < NR; ++r)
@@ -510,8 +568,8 @@ namespace smr
 #pragma unroll
                 for (int r = 0; r < NR; ++r)
                 {
-                    tag[it.fine[r] + 2 * k]     = 2;
-                    tag[it.fine[r] + 2 * k + 1] = 2;
+                    mstore(tag + it.fine[r] + 2 * k, static_cast<uint8_t>(2), mask);
+                    mstore(tag + it.fine[r] + 2 * k + 1, static_cast<uint8_t>(2), mask);
                 }
             }
             if (fl < p.max_level)
@@ -524,7 +582,9 @@ namespace smr
                     {
                         if (refine[r][x])
                         {
-                            tag[it.fine[r] + 2 * k + x] |= 4;
+                            uint8_t* t = tag + it.fine[r] + 2 * k + x;
+                            // the coarsen store above (if any) went to the same peers, so the local value is theirs too
+                            mstore(t, static_cast<uint8_t>((coarsen_ok ? 2 : *t) | 4), mask);
                         }
                     }
                 }
@@ -543,36 +603,39 @@ namespace smr
 
         __device__ __forceinline__ void operator()(const smr_item_tag& it, int k) const
         {
-            constexpr int NR = 1 << (DIM - 1);
+            constexpr int NR    = 1 << (DIM - 1);
+            const unsigned mask = static_cast<unsigned>(it.level) >> 8;
+            uint8_t t[NR][2];
             uint8_t any = 0, all = 0xff;
 #pragma unroll
             for (int r = 0; r < NR; ++r)
             {
-                const uint8_t a = tag[it.fine[r] + 2 * k], b = tag[it.fine[r] + 2 * k + 1];
-                any |= a | b;
-                all &= a & b;
+                t[r][0] = tag[it.fine[r] + 2 * k];
+                t[r][1] = tag[it.fine[r] + 2 * k + 1];
+                any |= t[r][0] | t[r][1];
+                all &= t[r][0] & t[r][1];
             }
             if (any & 1)
             {
 #pragma unroll
                 for (int r = 0; r < NR; ++r)
                 {
-                    tag[it.fine[r] + 2 * k] |= 1;
-                    tag[it.fine[r] + 2 * k + 1] |= 1;
+                    mstore(tag + it.fine[r] + 2 * k, static_cast<uint8_t>(t[r][0] | 1), mask);
+                    mstore(tag + it.fine[r] + 2 * k + 1, static_cast<uint8_t>(t[r][1] | 1), mask);
                 }
-                tag[it.coarse + k] |= 1;
+                mstore(tag + it.coarse + k, static_cast<uint8_t>(tag[it.coarse + k] | 1), mask);
             }
             else if (all & 2)
             {
-                tag[it.coarse + k] |= 1;
+                mstore(tag + it.coarse + k, static_cast<uint8_t>(tag[it.coarse + k] | 1), mask);
             }
             else
             {
 #pragma unroll
                 for (int r = 0; r < NR; ++r)
                 {
-                    tag[it.fine[r] + 2 * k] &= static_cast<uint8_t>(~2);
-                    tag[it.fine[r] + 2 * k + 1] &= static_cast<uint8_t>(~2);
+                    mstore(tag + it.fine[r] + 2 * k, static_cast<uint8_t>(t[r][0] & ~2), mask);
+                    mstore(tag + it.fine[r] + 2 * k + 1, static_cast<uint8_t>(t[r][1] & ~2), mask);
                 }
             }
         }
@@ -586,10 +649,11 @@ namespace smr
         static constexpr int units_per_thread = SMR_CELLS_PER_THREAD;
 
         uint8_t* __restrict__ tag;
+        unsigned mask_all; // tags are replicated on every rank
 
         __device__ __forceinline__ void operator()(const smr_item_fv& it, int k) const
         {
-            tag[it.c + k] = 1;
+            mstore(tag + it.c + k, static_cast<uint8_t>(1), mask_all);
         }
     };
 
@@ -625,11 +689,11 @@ namespace smr
             }
             if (r2 <= radius * radius)
             {
-                u[it.c + k] = inside;
+                mstore(u + it.c + k, inside, static_cast<unsigned>(it.mask));
             }
             else if (overwrite_outside)
             {
-                u[it.c + k] = outside;
+                mstore(u + it.c + k, outside, static_cast<unsigned>(it.mask));
             }
         }
     };
@@ -645,7 +709,7 @@ namespace smr
 
         __device__ __forceinline__ void operator()(const smr_item_copy& it, int k) const
         {
-            dst[it.dst + k] = src[it.src + k];
+            mstore(dst + it.dst + k, src[it.src + k], static_cast<unsigned>(it.mask));
         }
     };
 
@@ -661,7 +725,7 @@ namespace smr
         double bc_value;
     };
 
-    __device__ __forceinline__ void run_bc(const BcView& v, double* __restrict__ f, int i)
+    __device__ __forceinline__ void run_bc(const BcView& v, double* f, int i)
     {
         if (i >= v.n)
         {
@@ -669,19 +733,21 @@ namespace smr
         }
         const smr_item_bc it = v.items[i];
         const int64_t* s     = v.srcs + it.src_first;
-        if (it.kind == SMR_BC_COPY)
+        const int kind       = it.kind & 0xff;
+        const unsigned mask  = static_cast<unsigned>(it.kind) >> 8;
+        if (kind == SMR_BC_COPY)
         {
-            f[it.dst] = f[s[0]];
+            mstore(f + it.dst, f[s[0]], mask);
         }
-        else if (it.kind == SMR_BC_VALUE)
+        else if (kind == SMR_BC_VALUE)
         {
             if (v.bc_type == SMR_BCTYPE_DIRICHLET)
             {
-                f[it.dst] = 2 * v.bc_value - f[s[0]];
+                mstore(f + it.dst, 2 * v.bc_value - f[s[0]], mask);
             }
             else
             {
-                f[it.dst] = it.coef * v.bc_value + f[s[0]];
+                mstore(f + it.dst, it.coef * v.bc_value + f[s[0]], mask);
             }
         }
         else
@@ -695,7 +761,7 @@ namespace smr
             {
                 sum /= it.n_src;
             }
-            f[it.dst] = sum;
+            mstore(f + it.dst, sum, mask);
         }
     }
 

@@ -1,0 +1,127 @@
+"""Multi-rank worker (run under torchrun). Modes:
+  gpu   : one process per GPU; the advection loop on N GPUs must equal the oracle (== the 1-GPU result) bit for bit:
+          meshes identical on every rank, leaf values gathered from their owners identical to the oracle's.
+  host  : gloo, no GPU; the slab partition derived independently by every rank is the same and is a partition.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+
+def main():
+    mode = sys.argv[1]
+    dim = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+    lmin, lmax = (2, 7) if dim == 2 else (1, 5)
+    if len(sys.argv) > 4:
+        lmin, lmax = int(sys.argv[3]), int(sys.argv[4])
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    if mode == "gpu":
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        dist.init_process_group("gloo")
+    import parity_utils as pu
+    sb, so = pu.sb, pu.so
+
+    def gather(obj):
+        out = [None] * world
+        dist.all_gather_object(out, obj)
+        return out
+
+    have = sb.initialize_multi(rank, world, device=local if mode == "gpu" else -1, pool_bytes=1 << 30)
+    assert have == (mode == "gpu")
+    pmesh = sb.MRMesh.make_mesh([0.0] * dim, [1.0] * dim, pu.product_cfg(dim, lmin, lmax, 1))
+    ocfg = pu.oracle_cfg(dim, lmin, lmax, 1)
+    bc = so.Bc("dirichlet", 0.0)
+    omesh = so.Mesh.uniform(ocfg)
+    ou = so.init_disc(omesh, [0.3] * dim, 0.2)
+
+    def check_partition():
+        owners = sb.mg_leaf_owners(pmesh)
+        allo = gather(owners)
+        for o in allo:
+            assert np.array_equal(o, allo[0]), "ranks disagree on the partition"
+        assert owners.min() >= 0 and owners.max() < world
+        counts = np.bincount(owners, minlength=world)
+        return owners, counts
+
+    if mode == "host":
+        owners, counts = check_partition()
+        assert counts.sum() == pmesh.nb_cells()
+        # uniform mesh: slabs balanced to within one row of cells
+        assert counts.max() - counts.min() <= (1 << (lmax * (dim - 1))), counts
+        # drive the mesh with the oracle's tags: still identical and a partition on every rank
+        omesh2, ou2 = so.adapt(omesh, ou, bc, 2e-4, 1.0, trace=(trace := []))
+        for t in trace:
+            pmesh.update_from_tags(t["tag"])
+        pu.assert_same_mesh(pmesh, omesh2)
+        owners, counts = check_partition()
+        assert counts.sum() == omesh2.nb_cells()
+        if rank == 0:
+            print("host partition OK", counts.tolist())
+        dist.barrier()
+        dist.destroy_process_group()
+        return
+
+    u = sb.make_scalar_field("u", pmesh)
+    u.resize()
+    u.upload(ou)
+    sb.make_bc(u, sb.DIRICHLET, 0.0)
+    unp1 = sb.make_scalar_field("unp1", pmesh)
+    adapt = sb.make_MRAdapt(u)
+    mcfg = sb.mra_config().epsilon(2e-4)
+    a = [1.0] * dim
+    dt = (0.5 if dim == 2 else 0.25) * pmesh.min_cell_length()
+
+    def check(tag):
+        pu.assert_same_mesh(pmesh, omesh)
+        owners, counts = check_partition()
+        _, _, leaf_idx = omesh.leaf_table()
+        mine = u.download()[leaf_idx]
+        parts = gather((owners == rank, mine[owners == rank]))
+        full = np.empty(leaf_idx.size)
+        for m, v in parts:
+            full[m] = v
+        err = pu.max_rel_err(full, ou[leaf_idx])
+        assert err == 0.0, f"{tag}: N-GPU result differs from the oracle, max rel err {err:.3e}"
+        # after a broadcast every rank holds the complete field
+        sb.mg_broadcast(u)
+        allv = u.download()[leaf_idx]
+        assert np.array_equal(allv, ou[leaf_idx]), f"{tag}: broadcast copy incomplete on rank {rank}"
+        if rank == 0:
+            print(f"{tag}: leaves {omesh.nb_cells()} per-rank {counts.tolist()} OK", flush=True)
+
+    adapt(mcfg)
+    omesh, ou = so.adapt(omesh, ou, bc, 2e-4, 1.0)
+    check("initial adaptation")
+    sb.mg_rebalance(u)
+    for it in range(4):
+        adapt(mcfg)
+        omesh, ou = so.adapt(omesh, ou, bc, 2e-4, 1.0)
+        sb.update_ghost_mr(u)
+        so.update_ghost_mr(omesh, ou, bc)
+        unp1.resize()
+        sb.upwind_step(unp1, u, a, dt)
+        ou = so.fv_step(omesh, ou, a, dt)
+        sb.swap(u, unp1)
+        check(f"step {it}")
+        if it == 1:
+            sb.mg_rebalance(u)
+    st = sb.stats()
+    if rank == 0:
+        print("multi-GPU parity OK; launches", st["kernel_launches"], flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
