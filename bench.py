@@ -30,6 +30,11 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# torchrun pins OMP_NUM_THREADS=1; the host-side mesh/batch construction is OpenMP-parallel, so give every rank its share
+_world = int(os.environ.get("WORLD_SIZE", 1))
+if _world > 1:
+    os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // _world))
+
 METRIC = "cell-updates/s per FV step (incl. ghost+MR detail)"
 UNIT = "cell-updates/s"
 
@@ -249,7 +254,15 @@ def run_product(args):
         __graft_entry__.build()
     import samurai_b200 as sb
 
-    if not sb.initialize(local_rank):
+    if world > 1:
+        # every field / detail / tag buffer lives in a per-rank pool mapped into the peers: size it for the uniform
+        # max_level start mesh (reference cells ~ 4/3 * 4^L; u, its transfer twin, unp1, detail, tags) with slack
+        nref0 = int(4 ** args.max_level * 1.35)
+        pool = int(nref0 * (8 * 4 + 1) * 1.6) + (1 << 28)
+        ok = sb.initialize_multi(rank, world, device=local_rank, pool_bytes=pool)
+    else:
+        ok = sb.initialize(local_rank)
+    if not ok:
         raise SystemExit("no CUDA device: bench.py has no CPU fallback for the product arm")
 
     def barrier():
@@ -268,9 +281,13 @@ def run_product(args):
     sim.adapt(sim.mra)  # the demo's initial MRadaptation (from the uniform max_level mesh)
     sb.synchronize()
     init_secs = time.perf_counter() - t0
+    if world > 1:
+        sb.mg_rebalance(sim.u)  # the start mesh was cut into equal slabs; re-cut for the adapted leaves
 
     for _ in range(args.warmup):
         sim.step()
+    if world > 1:
+        sb.mg_rebalance(sim.u)
 
     # ---- timed, device-resident ------------------------------------------------------------------------------------
     sampler = ClockSampler(local_rank)
@@ -290,6 +307,8 @@ def run_product(args):
     leaves_now, ref_now = sim.mesh.nb_cells(), sim.mesh.nb_cells(sb.REFERENCE)
 
     # ---- e2e: host buffers in, host buffers out, every step --------------------------------------------------------
+    if world > 1:
+        sb.mg_broadcast(sim.u)
     host = sim.u.download()
     pinned = torch.empty(int(ref_now * 1.5) + 1024, dtype=torch.float64).pin_memory().numpy()
     pinned[: host.size] = host
@@ -304,6 +323,8 @@ def run_product(args):
         n_host = sim.u.size()
         if n_host > pinned.size:
             pinned = torch.empty(int(n_host * 1.5), dtype=torch.float64).pin_memory().numpy()
+        if world > 1:
+            sb.mg_broadcast(sim.u)  # the host copy must be the complete field on every rank
         sim.u.download(pinned[:n_host])
     e1.record()
     barrier()
@@ -314,13 +335,29 @@ def run_product(args):
     if world > 1:
         t = torch.tensor([secs, e2e_secs], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        c = torch.tensor([cells, e2e_cells], device="cuda", dtype=torch.float64)
-        dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        secs, e2e_secs = t.tolist()
-        cells, e2e_cells = c.tolist()
+        secs, e2e_secs = t.tolist()  # cells / e2e_cells already count the GLOBAL leaves (every rank holds the whole mesh)
 
     line = None
-    if rank == 0:
+    if rank == 0 and world > 1:
+        line = {
+            "metric": METRIC, "value": cells / secs, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"advection_2d min_level={args.min_level} max_level={args.max_level} eps={args.eps} pred_radius=1 Dirichlet(0) "
+                                   f"disc r=0.2@(0.3,0.3), a=(1,1), cfl=0.5; one step = MRadaptation + update_ghost_mr + upwind + swap",
+                       "leaves": leaves_now, "reference_cells": ref_now,
+                       "parallelism": f"{world} leaf-balanced slabs (one per GPU), halo values stored into the peers by the producing kernels over "
+                                      f"NVLink (CUDA IPC), flag barrier per phase, tags replicated; same global problem as N=1"},
+            "split_ms_per_step": {"device": 1e3 * st["device_seconds"] / args.steps, "host_mesh": 1e3 * st["host_mesh_seconds"] / args.steps,
+                                  "host_batches": 1e3 * st["host_batch_seconds"] / args.steps},
+            "gpu_launches": int(st["kernel_launches"]),
+            "initial_adaptation_s": init_secs,
+            "e2e": {"value": e2e_cells / e2e_secs, "unit": UNIT, "h2d_bytes_per_step": int(st_e2e["h2d_bytes"] / args.steps),
+                    "d2h_bytes_per_step": int(st_e2e["d2h_bytes"] / args.steps), "ms_per_step": 1e3 * e2e_secs / args.steps},
+            "roofline": None, "cpu_baseline": None, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    elif rank == 0:
         # ---- per-family profile pass (separate from the timed region: every launch is synchronised) ----------------
         sb.profile_enable(True)
         for _ in range(2):
