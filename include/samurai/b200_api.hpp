@@ -1,0 +1,1267 @@
+// samurai's public C++ API for the per-time-step hot path, bound to libsamurai_b200.so (include/samurai_b200.h).
+//
+// Source-compatible with what the reference's FV demos use (demos/FiniteVolume/advection_2d.cpp, advection_3d.cpp,
+// scalar_burgers_2d.cpp compile unchanged against this include directory): samurai::initialize/finalize/app/SAMURAI_PARSE,
+// Box, mesh_config, mra::make_mesh / make_empty_mesh, MRMesh, make_scalar_field, for_each_cell, make_bc<Dirichlet<1>>,
+// make_MRAdapt, mra_config, update_ghost_mr, upwind, upwind_scalar_burgers, `unp1 = u - dt * op(a, u)`, save/dump.
+// Fields are device resident; host accessors (u[cell]) work on a mirror with dirty tracking.  Expressions other than the
+// recognised FV step forms do not compile: nothing silently runs on the CPU.
+// Reference interfaces replaced: see the file:line notes on every declaration (paths relative to include/samurai/).
+#pragma once
+#include "../samurai_b200.h"
+
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <filesystem>
+#include <fstream>
+#include <functional>
+#include <iostream>
+#include <limits>
+#include <map>
+#include <memory>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+#include <fmt/format.h>
+#include <xtensor/containers/xfixed.hpp>
+
+// ---------------------------------------------------------------------------------------------------------------------
+// command line (the subset of CLI11 the demos touch through samurai::app)
+// ---------------------------------------------------------------------------------------------------------------------
+namespace CLI
+{
+    class Option
+    {
+      public:
+
+        Option* capture_default_str()
+        {
+            return this;
+        }
+
+        Option* group(const std::string&)
+        {
+            return this;
+        }
+
+        std::string name, description;
+        std::function<std::size_t(const std::vector<std::string>&, std::size_t)> parse; // consumes values, returns count
+    };
+
+    class App
+    {
+      public:
+
+        template <class T>
+        Option* add_option(const std::string& name, T& var, const std::string& desc = "")
+        {
+            auto it = m_options.find(name);
+            if (it == m_options.end())
+            {
+                it = m_options.emplace(name, std::make_unique<Option>()).first;
+            }
+            Option* o      = it->second.get();
+            o->name        = name;
+            o->description = desc;
+            o->parse       = [&var](const std::vector<std::string>& args, std::size_t i) -> std::size_t
+            {
+                return read(var, args, i);
+            };
+            return o;
+        }
+
+        Option* add_flag(const std::string& name, bool& var, const std::string& desc = "")
+        {
+            Option* o = add_option(name, var, desc);
+            o->parse  = [&var](const std::vector<std::string>&, std::size_t) -> std::size_t
+            {
+                var = true;
+                return 0;
+            };
+            return o;
+        }
+
+        void parse(int argc, char** argv)
+        {
+            std::vector<std::string> args(argv + 1, argv + argc);
+            for (std::size_t i = 0; i < args.size();)
+            {
+                std::string key = args[i], inline_val;
+                auto eq         = key.find('=');
+                if (eq != std::string::npos)
+                {
+                    inline_val = key.substr(eq + 1);
+                    key        = key.substr(0, eq);
+                }
+                if (key == "-h" || key == "--help")
+                {
+                    for (auto& kv : m_options)
+                    {
+                        std::cout << "  " << kv.first << "  " << kv.second->description << "\n";
+                    }
+                    std::exit(0);
+                }
+                auto it = m_options.find(key);
+                if (it == m_options.end())
+                {
+                    throw std::invalid_argument("The following argument was not expected: " + key);
+                }
+                if (!inline_val.empty())
+                {
+                    std::vector<std::string> one{inline_val};
+                    it->second->parse(one, 0);
+                    ++i;
+                }
+                else
+                {
+                    i += 1 + it->second->parse(args, i + 1);
+                }
+            }
+        }
+
+        std::string description;
+
+      private:
+
+        template <class T>
+        static void read_one(T& v, const std::string& s)
+        {
+            if constexpr (std::is_same_v<T, std::string>)
+            {
+                v = s;
+            }
+            else if constexpr (std::is_same_v<T, std::filesystem::path>)
+            {
+                v = std::filesystem::path(s);
+            }
+            else if constexpr (std::is_same_v<T, bool>)
+            {
+                v = (s == "1" || s == "true" || s == "on");
+            }
+            else if constexpr (std::is_floating_point_v<T>)
+            {
+                v = static_cast<T>(std::stod(s));
+            }
+            else
+            {
+                v = static_cast<T>(std::stoll(s));
+            }
+        }
+
+        template <class T>
+        static std::size_t read(T& var, const std::vector<std::string>& args, std::size_t i)
+        {
+            if (i >= args.size())
+            {
+                throw std::invalid_argument("missing value for an option");
+            }
+            read_one(var, args[i]);
+            return 1;
+        }
+
+        template <class T, std::size_t N>
+        static std::size_t read(std::array<T, N>& var, const std::vector<std::string>& args, std::size_t i)
+        {
+            std::size_t n = 0;
+            while (n < N && i + n < args.size() && !(args[i + n].size() > 1 && args[i + n][0] == '-' && args[i + n][1] == '-'))
+            {
+                read_one(var[n], args[i + n]);
+                ++n;
+            }
+            return n;
+        }
+
+        template <class T, std::size_t N>
+        static std::size_t read(xt::xtensor_fixed<T, xt::xshape<N>>& var, const std::vector<std::string>& args, std::size_t i)
+        {
+            std::size_t n = 0;
+            while (n < N && i + n < args.size() && !(args[i + n].size() > 1 && args[i + n][0] == '-' && args[i + n][1] == '-'))
+            {
+                read_one(var[n], args[i + n]);
+                ++n;
+            }
+            return n;
+        }
+
+        std::map<std::string, std::unique_ptr<Option>> m_options;
+    };
+}
+
+namespace samurai
+{
+    namespace fs = std::filesystem;
+
+    namespace b200
+    {
+        inline void check(int rc)
+        {
+            if (rc == SMR_OK)
+            {
+                return;
+            }
+            const std::string msg = smr_last_error();
+            if (rc == SMR_ERR_INVALID)
+            {
+                throw std::invalid_argument(msg);
+            }
+            if (rc == SMR_ERR_OUT_OF_RANGE)
+            {
+                throw std::out_of_range(msg);
+            }
+            throw std::runtime_error(msg);
+        }
+    }
+
+    // ---- arguments.hpp:11-89 -------------------------------------------------------------------------------------------
+    namespace args
+    {
+        inline std::size_t min_level        = std::numeric_limits<std::size_t>::max();
+        inline std::size_t max_level        = std::numeric_limits<std::size_t>::max();
+        inline std::size_t start_level      = std::numeric_limits<std::size_t>::max();
+        inline std::size_t graduation_width = std::numeric_limits<std::size_t>::max();
+        inline int max_stencil_radius       = std::numeric_limits<int>::max();
+        inline double epsilon               = std::numeric_limits<double>::infinity();
+        inline double regularity            = std::numeric_limits<double>::infinity();
+        inline bool timers                  = false;
+    }
+
+    // ---- samurai.hpp:22-114 --------------------------------------------------------------------------------------------
+    inline CLI::App app;
+
+    inline CLI::App& initialize(const std::string& description, int& /*argc*/, char**& /*argv*/)
+    {
+        app.description = description;
+        app.add_option("--min-level", args::min_level, "The minimum level of the mesh");
+        app.add_option("--max-level", args::max_level, "The maximum level of the mesh");
+        app.add_option("--start-level", args::start_level, "Start level of AMR");
+        app.add_option("--graduation-width", args::graduation_width, "The graduation width of the mesh");
+        app.add_option("--max-stencil-radius", args::max_stencil_radius, "The maximum number of neighbour in each direction");
+        app.add_option("--mr-eps", args::epsilon, "The epsilon used by the multiresolution to adapt the mesh");
+        app.add_option("--mr-reg", args::regularity, "The regularity criteria used by the multiresolution to adapt the mesh");
+        app.add_flag("--timers", args::timers, "Print timers at the end of the program");
+        int device = 0;
+        if (const char* e = std::getenv("SAMURAI_B200_DEVICE"))
+        {
+            device = std::atoi(e);
+        }
+        b200::check(smr_init(device));
+        return app;
+    }
+
+    inline CLI::App& initialize(int& argc, char**& argv)
+    {
+        return initialize("SAMURAI", argc, argv);
+    }
+
+    inline void finalize()
+    {
+        if (args::timers)
+        {
+            smr_stats st;
+            smr_stats_get(&st);
+            std::cout << "samurai_b200 timers: device " << st.device_seconds << " s, host mesh " << st.host_mesh_seconds << " s, host batches "
+                      << st.host_batch_seconds << " s, kernel launches " << st.kernel_launches << std::endl;
+        }
+        b200::check(smr_finalize());
+    }
+
+#define SAMURAI_PARSE(argc, argv)                \
+    try                                          \
+    {                                            \
+        samurai::app.parse(argc, argv);          \
+    }                                            \
+    catch (const std::exception& e)              \
+    {                                            \
+        std::cerr << e.what() << std::endl;      \
+        return 1;                                \
+    }
+
+    // ---- box.hpp -------------------------------------------------------------------------------------------------------
+    template <class value_t, std::size_t dim_>
+    class Box
+    {
+      public:
+
+        static constexpr std::size_t dim = dim_;
+        using point_t                    = xt::xtensor_fixed<value_t, xt::xshape<dim>>;
+
+        Box() = default;
+
+        template <class P1, class P2>
+        Box(const P1& min_corner, const P2& max_corner)
+        {
+            for (std::size_t d = 0; d < dim; ++d)
+            {
+                m_min[d] = min_corner[d];
+                m_max[d] = max_corner[d];
+            }
+        }
+
+        const point_t& min_corner() const
+        {
+            return m_min;
+        }
+
+        const point_t& max_corner() const
+        {
+            return m_max;
+        }
+
+        point_t length() const
+        {
+            point_t l;
+            for (std::size_t d = 0; d < dim; ++d)
+            {
+                l[d] = m_max[d] - m_min[d];
+            }
+            return l;
+        }
+
+      private:
+
+        point_t m_min, m_max;
+    };
+
+    // ---- mesh_config.hpp:20-432 ----------------------------------------------------------------------------------------
+    struct default_interval_t
+    {
+    };
+
+    template <std::size_t dim_, int prediction_stencil_radius_ = 1, std::size_t max_refinement_level_ = 20, class interval_t_ = default_interval_t>
+    class mesh_config
+    {
+      public:
+
+        static constexpr std::size_t dim                  = dim_;
+        static constexpr int prediction_stencil_radius    = prediction_stencil_radius_;
+        static constexpr std::size_t max_refinement_level = max_refinement_level_;
+
+        auto& max_stencil_radius(int r)
+        {
+            m_max_stencil_radius = r;
+            return *this;
+        }
+
+        int max_stencil_radius() const
+        {
+            return m_max_stencil_radius;
+        }
+
+        auto& max_stencil_size(int s)
+        {
+            m_max_stencil_radius = s / 2 + (s % 2);
+            return *this;
+        }
+
+        auto& graduation_width(std::size_t w)
+        {
+            m_graduation_width = w;
+            return *this;
+        }
+
+        std::size_t graduation_width() const
+        {
+            return m_graduation_width;
+        }
+
+        int ghost_width() const
+        {
+            return m_ghost_width;
+        }
+
+        auto& min_level(std::size_t l)
+        {
+            m_min_level = l;
+            return *this;
+        }
+
+        std::size_t min_level() const
+        {
+            return m_min_level;
+        }
+
+        auto& max_level(std::size_t l)
+        {
+            m_max_level = l;
+            return *this;
+        }
+
+        std::size_t max_level() const
+        {
+            return m_max_level;
+        }
+
+        auto& start_level(std::size_t l)
+        {
+            m_start_level = l;
+            return *this;
+        }
+
+        std::size_t& start_level()
+        {
+            return m_start_level;
+        }
+
+        std::size_t start_level() const
+        {
+            return m_start_level;
+        }
+
+        auto& approx_box_tol(double t)
+        {
+            m_approx_box_tol = t;
+            return *this;
+        }
+
+        auto& scaling_factor(double s)
+        {
+            m_scaling_factor = s;
+            return *this;
+        }
+
+        double scaling_factor() const
+        {
+            return m_scaling_factor;
+        }
+
+        auto& disable_args_parse()
+        {
+            m_disable_args_parse = true;
+            return *this;
+        }
+
+        auto& disable_minimal_ghost_width()
+        {
+            m_disable_minimal_ghost_width = true;
+            return *this;
+        }
+
+        void parse_args() // mesh_config.hpp:358-396
+        {
+            if (!m_disable_args_parse)
+            {
+                if (args::max_stencil_radius != std::numeric_limits<int>::max())
+                {
+                    m_max_stencil_radius = args::max_stencil_radius;
+                }
+                if (args::graduation_width != std::numeric_limits<std::size_t>::max())
+                {
+                    m_graduation_width = args::graduation_width;
+                }
+                if (args::min_level != std::numeric_limits<std::size_t>::max())
+                {
+                    m_min_level = args::min_level;
+                }
+                if (args::max_level != std::numeric_limits<std::size_t>::max())
+                {
+                    m_max_level = args::max_level;
+                }
+                if (args::start_level != std::numeric_limits<std::size_t>::max())
+                {
+                    m_start_level = args::start_level;
+                }
+                if (m_max_level < m_min_level)
+                {
+                    throw std::invalid_argument("Max level must be greater than min level.");
+                }
+            }
+            if (!m_disable_minimal_ghost_width)
+            {
+                m_max_stencil_radius = std::max(m_max_stencil_radius, 2);
+            }
+            m_ghost_width = std::max(m_max_stencil_radius, static_cast<int>(prediction_stencil_radius));
+        }
+
+      private:
+
+        int m_max_stencil_radius       = 1;
+        std::size_t m_graduation_width = 1;
+        int m_ghost_width              = 1;
+        std::size_t m_min_level        = 0;
+        std::size_t m_max_level        = 6;
+        std::size_t m_start_level      = 6;
+        double m_approx_box_tol        = 0.05;
+        double m_scaling_factor        = 0;
+        bool m_disable_args_parse          = false;
+        bool m_disable_minimal_ghost_width = false;
+    };
+
+    // ---- mr/mesh.hpp:25-34 ---------------------------------------------------------------------------------------------
+    enum class MRMeshId
+    {
+        cells            = 0,
+        cells_and_ghosts = 1,
+        proj_cells       = 2,
+        union_cells      = 3,
+        reference        = 4,
+        count            = 5,
+        all_cells        = reference
+    };
+
+    // ---- interval.hpp:50-64, cell.hpp:32-77 ------------------------------------------------------------------------------
+    struct Interval
+    {
+        int start = 0, end = 0, step = 1;
+        long long index = 0; // storage index: value of cell x lives at index + x
+
+        std::size_t size() const
+        {
+            return static_cast<std::size_t>(end - start);
+        }
+    };
+
+    template <std::size_t dim_>
+    struct Cell
+    {
+        static constexpr std::size_t dim = dim_;
+        using coords_t                   = xt::xtensor_fixed<double, xt::xshape<dim>>;
+
+        std::size_t level = 0;
+        xt::xtensor_fixed<int, xt::xshape<dim>> indices;
+        long long index = 0;
+        double length   = 0;
+        coords_t origin_point;
+
+        coords_t center() const // cell.hpp:131-134
+        {
+            coords_t c;
+            for (std::size_t d = 0; d < dim; ++d)
+            {
+                c[d] = origin_point[d] + length * (indices[d] + 0.5);
+            }
+            return c;
+        }
+
+        double center(std::size_t d) const
+        {
+            return origin_point[d] + length * (indices[d] + 0.5);
+        }
+
+        coords_t corner() const
+        {
+            coords_t c;
+            for (std::size_t d = 0; d < dim; ++d)
+            {
+                c[d] = origin_point[d] + length * indices[d];
+            }
+            return c;
+        }
+    };
+
+    // ---- mr/mesh.hpp:74-122, mesh.hpp ------------------------------------------------------------------------------------
+    template <class Config>
+    class MRMesh
+    {
+      public:
+
+        using config_t                   = Config;
+        using mesh_id_t                  = MRMeshId;
+        using cell_t                     = Cell<Config::dim>;
+        static constexpr std::size_t dim = Config::dim;
+
+        MRMesh() = default;
+
+        MRMesh(const Box<double, dim>& b, const Config& cfg)
+            : m_cfg(cfg)
+        {
+            smr_mesh_config c{};
+            c.dim                = static_cast<int32_t>(dim);
+            c.min_level          = static_cast<int32_t>(cfg.min_level());
+            c.max_level          = static_cast<int32_t>(cfg.max_level());
+            c.pred_radius        = Config::prediction_stencil_radius;
+            c.max_stencil_radius = cfg.max_stencil_radius();
+            c.graduation_width   = static_cast<int32_t>(cfg.graduation_width());
+            // approximate_box (box.hpp:280-360) for boxes whose edge lengths are integer multiples of the smallest one
+            const auto len = b.length();
+            double s       = cfg.scaling_factor();
+            if (s <= 0)
+            {
+                s = len[0];
+                for (std::size_t d = 1; d < dim; ++d)
+                {
+                    s = std::min(s, len[d]);
+                }
+            }
+            for (std::size_t d = 0; d < 3; ++d)
+            {
+                if (d < dim)
+                {
+                    const double n = len[d] / s;
+                    if (std::abs(n - std::round(n)) > 1e-12)
+                    {
+                        throw std::invalid_argument("box edge lengths must be integer multiples of the cell length at level 0");
+                    }
+                    c.n_cells0[d] = static_cast<int32_t>(std::lround(n));
+                    c.origin[d]   = b.min_corner()[d];
+                }
+                else
+                {
+                    c.n_cells0[d] = 1;
+                    c.origin[d]   = 0;
+                }
+            }
+            c.scaling_factor = s;
+            m_c              = c;
+            smr_mesh_t h     = 0;
+            b200::check(smr_mesh_create_uniform(&c, static_cast<int>(cfg.start_level()), &h));
+            m_owner = std::make_shared<Owner>();
+            m_owner->h = h;
+        }
+
+        // Copies share the library mesh (the demos copy a mesh to iterate over it, scalar_burgers_2d.cpp:23);
+        // `mesh = samurai::mra::make_mesh(box, config);` (advection_2d.cpp:107) rebinds this object, and the fields that
+        // point at it follow.
+        MRMesh(const MRMesh&)                = default;
+        MRMesh& operator=(const MRMesh&)     = default;
+        MRMesh(MRMesh&&) noexcept            = default;
+        MRMesh& operator=(MRMesh&&) noexcept = default;
+
+        smr_mesh_t handle() const
+        {
+            return m_owner ? m_owner->h : 0;
+        }
+
+        std::size_t min_level() const
+        {
+            return m_cfg.min_level();
+        }
+
+        std::size_t max_level() const
+        {
+            return m_cfg.max_level();
+        }
+
+        double scaling_factor() const
+        {
+            return m_c.scaling_factor;
+        }
+
+        double cell_length(std::size_t level) const
+        {
+            return m_c.scaling_factor / static_cast<double>(1 << level);
+        }
+
+        double min_cell_length() const
+        {
+            return cell_length(max_level());
+        }
+
+        std::size_t nb_cells(mesh_id_t id = mesh_id_t::cells) const
+        {
+            int64_t n = 0;
+            b200::check(smr_mesh_nb_cells(handle(), static_cast<int>(id), -1, &n));
+            return static_cast<std::size_t>(n);
+        }
+
+        std::size_t nb_cells(std::size_t level, mesh_id_t id = mesh_id_t::cells) const
+        {
+            int64_t n = 0;
+            b200::check(smr_mesh_nb_cells(handle(), static_cast<int>(id), static_cast<int>(level), &n));
+            return static_cast<std::size_t>(n);
+        }
+
+        std::vector<smr_interval> intervals(mesh_id_t id, std::size_t level) const
+        {
+            int64_t n = 0;
+            b200::check(smr_mesh_nb_intervals(handle(), static_cast<int>(id), static_cast<int>(level), &n));
+            std::vector<smr_interval> v(static_cast<std::size_t>(n));
+            if (n)
+            {
+                b200::check(smr_mesh_get_intervals(handle(), static_cast<int>(id), static_cast<int>(level), v.data()));
+            }
+            return v;
+        }
+
+        const smr_mesh_config& c_config() const
+        {
+            return m_c;
+        }
+
+      private:
+
+        struct Owner
+        {
+            smr_mesh_t h = 0;
+
+            ~Owner()
+            {
+                // refused while fields are still attached; whatever is left is reclaimed by smr_finalize()
+                if (h)
+                {
+                    smr_mesh_destroy(h);
+                }
+            }
+        };
+
+        std::shared_ptr<Owner> m_owner;
+        Config m_cfg;
+        smr_mesh_config m_c{};
+    };
+
+    namespace mra
+    {
+        template <class mesh_config_t>
+        auto make_empty_mesh(const mesh_config_t&)
+        {
+            return MRMesh<mesh_config_t>();
+        }
+
+        template <class mesh_config_t>
+        auto make_mesh(const Box<double, mesh_config_t::dim>& b, const mesh_config_t& cfg) // mr/mesh.hpp:510-518
+        {
+            auto mesh_cfg = cfg;
+            mesh_cfg.parse_args();
+            mesh_cfg.start_level() = mesh_cfg.max_level();
+            return MRMesh<mesh_config_t>(b, mesh_cfg);
+        }
+    }
+
+    // ---- algorithm.hpp:53-363 ------------------------------------------------------------------------------------------
+    template <class Mesh, class Func>
+    void for_each_interval(const Mesh& mesh, Func&& f) // f(level, interval, index)  (leaves)
+    {
+        for (std::size_t level = 0; level <= mesh.max_level(); ++level)
+        {
+            for (const auto& iv : mesh.intervals(MRMeshId::cells, level))
+            {
+                Interval i{iv.start, iv.end, 1, static_cast<long long>(iv.offset) - iv.start};
+                xt::xtensor_fixed<int, xt::xshape<(Mesh::dim > 1 ? Mesh::dim - 1 : 1)>> index;
+                index[0] = iv.y;
+                if constexpr (Mesh::dim > 2)
+                {
+                    index[1] = iv.z;
+                }
+                f(level, i, index);
+            }
+        }
+    }
+
+    template <class Mesh, class Func>
+    void for_each_cell(const Mesh& mesh, Func&& f)
+    {
+        typename Mesh::cell_t cell;
+        for (std::size_t d = 0; d < Mesh::dim; ++d)
+        {
+            cell.origin_point[d] = mesh.c_config().origin[d];
+        }
+        for (std::size_t level = 0; level <= mesh.max_level(); ++level)
+        {
+            cell.level  = level;
+            cell.length = mesh.cell_length(level);
+            for (const auto& iv : mesh.intervals(MRMeshId::cells, level))
+            {
+                if constexpr (Mesh::dim > 1)
+                {
+                    cell.indices[1] = iv.y;
+                }
+                if constexpr (Mesh::dim > 2)
+                {
+                    cell.indices[2] = iv.z;
+                }
+                for (int x = iv.start; x < iv.end; ++x)
+                {
+                    cell.indices[0] = x;
+                    cell.index      = iv.offset + (x - iv.start);
+                    f(cell);
+                }
+            }
+        }
+    }
+
+    // ---- field/scalar_field.hpp ------------------------------------------------------------------------------------------
+    // Storage = what `u.array()` returns: std::swap(u.array(), unp1.array()) exchanges the device buffers (advection_2d.cpp:146)
+    struct FieldStorage
+    {
+        smr_field_t handle = 0;
+        std::vector<double> host; // mirror for u[cell]
+        bool host_valid  = false; // mirror equals the device copy
+        bool host_dirty  = false; // mirror was written and not uploaded yet
+    };
+
+    struct Dirichlet1Tag
+    {
+    };
+
+    template <std::size_t order = 1>
+    struct Dirichlet
+    {
+        static constexpr int type = SMR_BCTYPE_DIRICHLET;
+        static_assert(order == 1, "only Dirichlet<1> is implemented on the device path");
+    };
+
+    template <std::size_t order = 1>
+    struct Neumann
+    {
+        static constexpr int type = SMR_BCTYPE_NEUMANN;
+        static_assert(order == 1, "only Neumann<1> is implemented on the device path");
+    };
+
+    template <class A, class Field>
+    struct upwind_expr
+    {
+        A a;
+        const Field* u;
+        bool burgers;
+    };
+
+    template <class A, class Field>
+    struct scaled_upwind_expr
+    {
+        double dt;
+        upwind_expr<A, Field> op;
+    };
+
+    template <class A, class Field>
+    struct fv_step_expr
+    {
+        const Field* u;
+        scaled_upwind_expr<A, Field> rhs;
+    };
+
+    template <class mesh_t_, class value_t = double>
+    class ScalarField
+    {
+      public:
+
+        using mesh_t                     = mesh_t_;
+        using cell_t                     = typename mesh_t::cell_t;
+        static constexpr std::size_t dim = mesh_t::dim;
+        static constexpr bool on_device  = std::is_same_v<value_t, double>;
+
+        ScalarField(std::string name, mesh_t& mesh)
+            : m_name(std::move(name))
+            , p_mesh(&mesh)
+        {
+        }
+
+        ScalarField(const ScalarField&)            = delete;
+        ScalarField& operator=(const ScalarField&) = delete;
+
+        ScalarField(ScalarField&& o) noexcept
+            : m_name(std::move(o.m_name))
+            , p_mesh(o.p_mesh)
+            , m_storage(std::move(o.m_storage))
+            , m_plain(std::move(o.m_plain))
+            , m_bc_type(o.m_bc_type)
+            , m_bc_value(o.m_bc_value)
+        {
+            o.m_storage.handle = 0;
+        }
+
+        ~ScalarField()
+        {
+            if (m_storage.handle)
+            {
+                smr_field_destroy(m_storage.handle);
+            }
+        }
+
+        const std::string& name() const
+        {
+            return m_name;
+        }
+
+        mesh_t& mesh()
+        {
+            return *p_mesh;
+        }
+
+        const mesh_t& mesh() const
+        {
+            return *p_mesh;
+        }
+
+        FieldStorage& array()
+        {
+            return m_storage;
+        }
+
+        std::size_t size() const
+        {
+            return p_mesh->nb_cells(MRMeshId::reference);
+        }
+
+        void resize() // field/access_base.hpp:105-115
+        {
+            if constexpr (on_device)
+            {
+                push_host();
+                b200::check(smr_field_resize(handle()));
+                m_storage.host_valid = false;
+            }
+            else
+            {
+                m_plain.resize(size());
+            }
+        }
+
+        void fill(value_t v)
+        {
+            if constexpr (on_device)
+            {
+                b200::check(smr_field_resize(handle()));
+                b200::check(smr_field_fill(handle(), v));
+                m_storage.host_valid = false;
+                m_storage.host_dirty = false;
+            }
+            else
+            {
+                m_plain.assign(size(), v);
+            }
+        }
+
+        // host access: u[cell]
+        value_t& operator[](const cell_t& cell)
+        {
+            if constexpr (on_device)
+            {
+                pull_host();
+                m_storage.host_dirty = true;
+                return m_storage.host[static_cast<std::size_t>(cell.index)];
+            }
+            else
+            {
+                if (m_plain.size() != size())
+                {
+                    m_plain.resize(size());
+                }
+                return m_plain[static_cast<std::size_t>(cell.index)];
+            }
+        }
+
+        value_t operator[](const cell_t& cell) const
+        {
+            if constexpr (on_device)
+            {
+                const_cast<ScalarField*>(this)->pull_host();
+                return m_storage.host[static_cast<std::size_t>(cell.index)];
+            }
+            else
+            {
+                return m_plain[static_cast<std::size_t>(cell.index)];
+            }
+        }
+
+        // device handle with pending host writes flushed and the boundary condition attached
+        smr_field_t device() const
+        {
+            auto* self = const_cast<ScalarField*>(this);
+            self->push_host();
+            if (m_bc_type >= 0)
+            {
+                b200::check(smr_field_set_bc(self->handle(), m_bc_type, m_bc_value));
+            }
+            return self->handle();
+        }
+
+        void device_written()
+        {
+            m_storage.host_valid = false;
+            m_storage.host_dirty = false;
+        }
+
+        void attach_bc(int type, double value)
+        {
+            m_bc_type  = type;
+            m_bc_value = value;
+        }
+
+        // `unp1 = u - dt * upwind(a, u)`  (field/field_base.hpp:230-242 + stencil_field.hpp)
+        template <class A>
+        ScalarField& operator=(const fv_step_expr<A, ScalarField>& e)
+        {
+            static_assert(on_device, "FV expressions need a double field");
+            if (e.u != e.rhs.op.u)
+            {
+                throw std::invalid_argument("only `u - dt * op(a, u)` with the same field u is recognised on the device path");
+            }
+            double a[3] = {0, 0, 0};
+            for (std::size_t d = 0; d < dim; ++d)
+            {
+                a[d] = e.rhs.op.a[d];
+            }
+            const smr_field_t in = e.u->device();
+            b200::check(smr_field_resize(handle()));
+            if (e.rhs.op.burgers)
+            {
+                b200::check(smr_fv_upwind_burgers(handle(), in, a, e.rhs.dt));
+            }
+            else
+            {
+                b200::check(smr_fv_upwind(handle(), in, a, e.rhs.dt));
+            }
+            device_written();
+            return *this;
+        }
+
+        std::vector<double> leaf_values() const
+        {
+            const_cast<ScalarField*>(this)->pull_host();
+            return m_storage.host;
+        }
+
+      private:
+
+        smr_field_t handle()
+        {
+            if (!m_storage.handle)
+            {
+                if (!p_mesh->handle())
+                {
+                    throw std::runtime_error("field '" + m_name + "' used before its mesh was built");
+                }
+                b200::check(smr_field_create(p_mesh->handle(), m_name.c_str(), &m_storage.handle));
+            }
+            return m_storage.handle;
+        }
+
+        void pull_host()
+        {
+            const std::size_t n = size();
+            if (!m_storage.host_valid || m_storage.host.size() != n)
+            {
+                int64_t fs_ = 0;
+                b200::check(smr_field_resize(handle()));
+                b200::check(smr_field_size(handle(), &fs_));
+                m_storage.host.resize(n);
+                b200::check(smr_field_download(handle(), m_storage.host.data(), static_cast<int64_t>(n)));
+                m_storage.host_valid = true;
+                m_storage.host_dirty = false;
+            }
+        }
+
+        void push_host()
+        {
+            if (m_storage.host_dirty)
+            {
+                b200::check(smr_field_upload(handle(), m_storage.host.data(), static_cast<int64_t>(m_storage.host.size())));
+                b200::check(smr_synchronize());
+                m_storage.host_dirty = false;
+                m_storage.host_valid = true;
+            }
+        }
+
+        std::string m_name;
+        mesh_t* p_mesh;
+        FieldStorage m_storage;
+        std::vector<value_t> m_plain; // non-double fields are host-only (e.g. the `level` field the demos save)
+        int m_bc_type     = -1;
+        double m_bc_value = 0;
+    };
+
+    template <class value_t, class mesh_t>
+    auto make_scalar_field(const std::string& name, mesh_t& mesh) // field/scalar_field.hpp:171-215
+    {
+        return ScalarField<mesh_t, value_t>(name, mesh);
+    }
+
+    // field/swap.hpp:14-18
+    template <class mesh_t, class T>
+    void swap(ScalarField<mesh_t, T>& a, ScalarField<mesh_t, T>& b)
+    {
+        std::swap(a.array(), b.array());
+    }
+
+    // ---- bc/bc.hpp:751-815 -----------------------------------------------------------------------------------------------
+    template <class BcType, class Field>
+    void make_bc(Field& u, double value)
+    {
+        u.attach_bc(BcType::type, value);
+    }
+
+    // ---- stencil_field.hpp:175-179, 245-249 ------------------------------------------------------------------------------
+    template <class A, class Field>
+    auto upwind(const A& a, const Field& u)
+    {
+        return upwind_expr<A, Field>{a, &u, false};
+    }
+
+    template <class A, class Field>
+    auto upwind_scalar_burgers(const A& k, const Field& u)
+    {
+        return upwind_expr<A, Field>{k, &u, true};
+    }
+
+    template <class A, class Field>
+    auto operator*(double dt, const upwind_expr<A, Field>& op)
+    {
+        return scaled_upwind_expr<A, Field>{dt, op};
+    }
+
+    template <class A, class mesh_t>
+    auto operator-(const ScalarField<mesh_t, double>& u, const scaled_upwind_expr<A, ScalarField<mesh_t, double>>& rhs)
+    {
+        return fv_step_expr<A, ScalarField<mesh_t, double>>{&u, rhs};
+    }
+
+    // ---- algorithm/update_ghost_mr.hpp:260-270 ---------------------------------------------------------------------------
+    template <class Field>
+    void update_ghost_mr(Field& u)
+    {
+        b200::check(smr_update_ghost_mr(u.device()));
+        u.device_written();
+    }
+
+    // ---- mr/config.hpp:10-68 -----------------------------------------------------------------------------------------------
+    class mra_config
+    {
+      public:
+
+        mra_config& epsilon(double e)
+        {
+            m_eps = e;
+            return *this;
+        }
+
+        double epsilon() const
+        {
+            return m_eps;
+        }
+
+        mra_config& regularity(double r)
+        {
+            m_reg = r;
+            return *this;
+        }
+
+        double regularity() const
+        {
+            return m_reg;
+        }
+
+        mra_config& relative_detail(bool b)
+        {
+            if (b)
+            {
+                throw std::invalid_argument("relative_detail is not implemented on the device path");
+            }
+            return *this;
+        }
+
+        void parse_args()
+        {
+            if (std::isfinite(args::epsilon))
+            {
+                m_eps = args::epsilon;
+            }
+            if (std::isfinite(args::regularity))
+            {
+                m_reg = args::regularity;
+            }
+        }
+
+      private:
+
+        double m_eps = 1e-4, m_reg = 1.;
+    };
+
+    // ---- mr/adapt.hpp:391-397 ----------------------------------------------------------------------------------------------
+    template <class... Fields>
+    class Adapt
+    {
+      public:
+
+        explicit Adapt(Fields&... fields)
+            : m_fields{&fields...}
+        {
+        }
+
+        void operator()(mra_config& cfg)
+        {
+            cfg.parse_args();
+            call(cfg.epsilon(), cfg.regularity(), std::index_sequence_for<Fields...>{});
+        }
+
+        void operator()(double eps, double regularity)
+        {
+            call(eps, regularity, std::index_sequence_for<Fields...>{});
+        }
+
+      private:
+
+        template <std::size_t... I>
+        void call(double eps, double reg, std::index_sequence<I...>)
+        {
+            smr_field_t h[] = {std::get<I>(m_fields)->device()...};
+            int it          = 0;
+            b200::check(smr_adapt(h, static_cast<int>(sizeof...(Fields)), eps, reg, &it));
+            (std::get<I>(m_fields)->device_written(), ...);
+        }
+
+        std::tuple<Fields*...> m_fields;
+    };
+
+    template <class... Fields>
+    auto make_MRAdapt(Fields&... fields)
+    {
+        return Adapt<Fields...>(fields...);
+    }
+
+    // ---- io/hdf5.hpp, io/restart.hpp -----------------------------------------------------------------------------------
+    // No HDF5 library in this environment: save() writes <name>.csv (level, cell indices, centre, one column per field) in
+    // for_each_cell order -- the information of /mesh + /mesh/fields/* of the reference's .h5 -- next to a <name>.txt summary.
+    namespace detail
+    {
+        template <class Mesh>
+        void write_header(std::ostream& os, const Mesh&)
+        {
+            os << "level";
+            for (std::size_t d = 0; d < Mesh::dim; ++d)
+            {
+                os << "," << "ijk"[d];
+            }
+        }
+    }
+
+    template <class T>
+    concept mesh_like = requires(const T& m) { m.c_config(); };
+
+    template <class Mesh, class... Fields>
+        requires mesh_like<Mesh>
+    void save(const fs::path& path, const std::string& filename, const Mesh& mesh, const Fields&... fields)
+    {
+        fs::create_directories(path);
+        std::ofstream os(path / (filename + ".csv"));
+        os.precision(17);
+        detail::write_header(os, mesh);
+        ((os << "," << fields.name()), ...);
+        os << "\n";
+        for_each_cell(mesh,
+                      [&](const auto& cell)
+                      {
+                          os << cell.level;
+                          for (std::size_t d = 0; d < Mesh::dim; ++d)
+                          {
+                              os << "," << cell.indices[d];
+                          }
+                          ((os << "," << fields[cell]), ...);
+                          os << "\n";
+                      });
+    }
+
+    template <class Mesh, class... Fields>
+        requires mesh_like<Mesh>
+    void dump(const fs::path& path, const std::string& filename, const Mesh& mesh, const Fields&... fields)
+    {
+        save(path, filename, mesh, fields...);
+    }
+
+    template <class Mesh, class... Fields>
+    void load(const fs::path&, Mesh&, Fields&...)
+    {
+        throw std::runtime_error("samurai::load (HDF5 restart files) is not available in samurai_b200");
+    }
+
+    template <class Mesh, class... Fields>
+    void load(const std::string&, Mesh&, Fields&...)
+    {
+        throw std::runtime_error("samurai::load (HDF5 restart files) is not available in samurai_b200");
+    }
+} // namespace samurai
