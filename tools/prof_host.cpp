@@ -1,3 +1,4 @@
+// Host-side profiling harness: g++ -O2 -std=c++17 -fopenmp -I. -o /tmp/prof_host tools/prof_host.cpp
 #include "samurai_b200/csrc/batches.hpp"
 #include <chrono>
 #include <cstdio>
@@ -12,19 +13,10 @@ int main(int argc, char** argv){
   for(int64_t i=0;i<n;++i) b[d[5*i]].add(mk_key(d[5*i+1],0), d[5*i+3], d[5*i+4]);
   CellArray ca(nlev); for(int l=0;l<nlev;++l) ca[l]=b[l].build();
   Mesh m; m.init_from_cells(c, CellArray(ca));
-  int reps=5; double t0;
-  for(int l=0;l<nlev;++l) if(!m.cells[l].empty()) printf("level %d: leaves %ld ivl %zu rows %zu | ref cells %ld ivl %zu\n", l, (long)m.cells[l].n_cells(), m.cells[l].n_intervals(), m.cells[l].rows(), (long)m.ref[l].n_cells(), m.ref[l].n_intervals());
+  int reps=10; double t0;
   t0=now(); for(int r=0;r<reps;++r){ Mesh x; x.init_from_cells(c, CellArray(ca)); } printf("mesh build %.2f ms\n",(now()-t0)/reps*1e3);
-  { t0=now(); for(int r=0;r<reps;++r){ for(int l=0;l<nlev;++l){ std::vector<smr_item_fv> it; if(!m.cells[l].empty()) fv_items(m,l,it);} } printf("fv items %.2f ms\n",(now()-t0)/reps*1e3); }
-  { t0=now(); for(int r=0;r<reps;++r){ for(int l=c.max_level;l>=0;--l){ PhaseItems ph; build_ghost_phase(m,l,ph);} } printf("ghost phases %.2f ms\n",(now()-t0)/reps*1e3); }
-  { int l=c.max_level; t0=now(); for(int r=0;r<reps;++r){ PhaseItems ph; build_ghost_phase(m,l,ph);} printf("  ghost phase L %.2f ms\n",(now()-t0)/reps*1e3); }
-  { t0=now(); for(int r=0;r<reps;++r){ for(int l=1;l<=c.max_level;++l){ LevelSet ps=prediction_set(m,l);} } printf("prediction sets %.2f ms\n",(now()-t0)/reps*1e3); }
-  { t0=now(); for(int r=0;r<reps;++r){ for(int l=1;l<=c.max_level;++l){ LevelSet ps=prediction_set(m,l); if(ps.empty())continue; locate(ps,m.ref[l]); std::vector<smr_item_pred> items; pred_items(2,1,l,ps,m.ref[l-1],items);} } printf("prediction sets+items %.2f ms\n",(now()-t0)/reps*1e3); }
-  { t0=now(); for(int r=0;r<reps;++r){ for(int l=3;l<c.max_level;++l){ LevelSet s=detail_set(m,l);} } printf("detail sets %.2f ms\n",(now()-t0)/reps*1e3); }
-  { t0=now(); for(int r=0;r<reps;++r){ for(int l=3;l<c.max_level;++l){ std::vector<smr_item_detail> items; detail_items(m,l,detail_set(m,l),items);} } printf("detail sets+items %.2f ms\n",(now()-t0)/reps*1e3); }
-  { t0=now(); for(int r=0;r<reps;++r){ for(int l=4;l<=c.max_level;++l){ std::vector<smr_item_tag> items; tag_items(m,l,tag_set(m,l),items);} } printf("tag sets+items %.2f ms\n",(now()-t0)/reps*1e3); }
-  { t0=now(); for(int r=0;r<reps;++r){ MeshPlan p; build_plan(m,p);} printf("build_plan total %.2f ms\n",(now()-t0)/reps*1e3); }
+  { MeshPlan p; build_plan(m,p); t0=now(); for(int r=0;r<reps;++r){ build_plan(m,p);} printf("build_plan %.2f ms (arena %.1f MB)\n",(now()-t0)/reps*1e3, p.arena.size/1e6); }
   { std::vector<uint8_t> tag(m.nref,1); t0=now(); for(int r=0;r<reps;++r){ CellArray x=cells_from_tags(m,tag.data()); } printf("cells_from_tags %.2f ms\n",(now()-t0)/reps*1e3);
     t0=now(); for(int r=0;r<reps;++r){ CellArray x=m.cells; make_graduation(c,x);} printf("graduation %.2f ms\n",(now()-t0)/reps*1e3); }
-  { Mesh m2; m2.init_from_cells(c, CellArray(ca)); t0=now(); for(int r=0;r<reps;++r){ TransferPlan tp; build_transfer(m,m2,tp);} printf("transfer (same mesh) %.2f ms\n",(now()-t0)/reps*1e3); }
+  { Mesh m2; m2.init_from_cells(c, CellArray(ca)); TransferPlan tp; build_transfer(m,m2,tp); t0=now(); for(int r=0;r<reps;++r){ build_transfer(m,m2,tp);} printf("transfer %.2f ms\n",(now()-t0)/reps*1e3); }
 }
