@@ -118,6 +118,20 @@ extern "C"
     /* unp1 = u - dt * upwind_scalar_burgers(k, u)  (stencil_field.hpp:184-249) */
     int smr_fv_upwind_burgers(smr_field_t unp1, smr_field_t u, const double* k, double dt);
 
+    /* flux-based linear homogeneous schemes, explicit application: out = S(u) with out.fill(0) first
+     * (schemes/fv/FV_scheme.hpp:202-238, flux_based/explicit_flux_based_scheme__lin_hom.hpp:233-319).  Ghosts of `u` are
+     * updated first if needed (update_ghost_mr_if_needed).  Uniform-level meshes only for now: a mesh with a level jump is
+     * rejected with SMR_ERR_INVALID rather than approximated. */
+    enum
+    {
+        SMR_SCHEME_CONVECTION_UPWIND = 0, /* make_convection_upwind<Field>(velocity), operators/convection_lin.hpp:15-89; params = velocity[dim] */
+        SMR_SCHEME_DIFFUSION_ORDER2  = 1  /* make_diffusion_order2<Field>(K),         operators/diffusion.hpp:123-175;     params = K[dim]        */
+    };
+
+    int smr_scheme_apply(smr_field_t out, smr_field_t u, int kind, const double* params);
+    /* out = a * x + b * y over the leaves: the field-expression tail `unp1 = u - dt * scheme(u)` is (1, u, -dt, rhs) */
+    int smr_field_lincomb(smr_field_t out, double a, smr_field_t x, double b, smr_field_t y);
+
     /* make_MRAdapt(fields...)(mra_config) (mr/adapt.hpp:148-195, 277-389): adapts the mesh IN PLACE and transfers
      * `fields`; any other field living on the mesh must be smr_field_resize()d by the caller, as in the reference.
      * *n_iterations receives the number of harten iterations executed. */

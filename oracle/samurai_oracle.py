@@ -809,6 +809,90 @@ def fv_step(mesh: Mesh, u, a, dt, scheme="upwind"):
 
 
 # ----------------------------------------------------------------------------
+# flux-based linear homogeneous schemes (uniform-level meshes)
+# ----------------------------------------------------------------------------
+def convection_upwind_coeffs(velocity):
+    """make_convection_upwind<Field>(velocity) (schemes/fv/operators/convection_lin.hpp:15-89): flux coeffs {left, right}."""
+    def fn(d, h):
+        v = float(velocity[d])
+        return (v, 0.0) if v >= 0 else (0.0, v)
+    return fn
+
+
+def diffusion_order2_coeffs(K):
+    """make_diffusion_order2<Field>(K) (schemes/fv/operators/diffusion.hpp:123-175)."""
+    def fn(d, h):
+        left, right = -1 / h, 1 / h
+        left *= -float(K[d])
+        right *= -float(K[d])
+        return (left, right)
+    return fn
+
+
+def flux_linhom_apply(mesh: Mesh, u, coeff_fn):
+    """Explicit<FluxBasedScheme<LinearHomogeneous>>::apply, sequential context
+    (flux_based/explicit_flux_based_scheme__lin_hom.hpp:39-119, 233-319; coefficient loop
+    flux_based_scheme__lin_hom.hpp:74-229; interfaces interface.hpp:35-110, 440-509), restated literally: for every
+    direction, the same-level interface intervals in for_each_interval order, each applying
+    `out[left] += lc[c]*in[st_c]; out[right] += rc[c]*in[st_c]` for c = 0, 1, then the boundary interfaces.
+    Only meshes whose leaves sit on one level (no level jump) are supported here."""
+    dim = mesh.cfg.dim
+    levels = mesh.leaf_levels()
+    assert len(levels) == 1, "oracle flux path: uniform-level meshes only"
+    level = levels[0]
+    h = mesh.cfg.cell_length(level)
+    out = np.zeros(mesh.nref)
+    cells = mesh.cells[level]
+    c = unpack(cells, dim)
+    factor = pow(h, dim - 1) / pow(h, dim)  # h_factor (flux_based_scheme__lin_hom.hpp:62-67)
+    for d in range(dim):
+        e = [0] * dim
+        e[d] = 1
+        fc = coeff_fn(d, h)
+        lc = (factor * fc[0], factor * fc[1])
+        rc = (-lc[0], -lc[1])
+        # interface set: cells ∩ translate(cells, -dir), traversed row by row (rows = all coords but x)
+        has_next = np.isin(translate(cells, e), cells)
+        left_all = cells[has_next]
+        if dim == 1:
+            groups = [left_all]
+        else:
+            lcoords = unpack(left_all, dim)
+            rowkey = np.zeros(left_all.size, dtype=np.int64)
+            for dd in range(dim - 1, 0, -1):
+                rowkey = rowkey * (1 << 21) + (lcoords[:, dd] + BIAS)
+            order = np.argsort(rowkey, kind="stable")
+            left_sorted = left_all[order]
+            rk = rowkey[order]
+            bounds = np.flatnonzero(np.diff(rk)) + 1
+            groups = np.split(left_sorted, bounds)
+        for left in groups:
+            if left.size == 0:
+                continue
+            li = mesh.index(level, left)
+            ri = mesh.index(level, translate(left, e))
+            st = (li, ri)  # stencil cells {0, +dir} = (left cell, right cell)
+            for cc in range(2):
+                out[li] = out[li] + lc[cc] * u[st[cc]]
+                out[ri] = out[ri] + rc[cc] * u[st[cc]]
+        # boundary interfaces: direction, then opposite direction
+        bd = cells[~mesh.in_domain(level, translate(cells, e))]
+        if bd.size:
+            bi = mesh.index(level, bd)
+            st = (bi, mesh.index(level, translate(bd, e)))
+            for cc in range(2):
+                out[bi] = out[bi] + lc[cc] * u[st[cc]]
+        me = [-v for v in e]
+        bd = cells[~mesh.in_domain(level, translate(cells, me))]
+        if bd.size:
+            bi = mesh.index(level, bd)
+            st = (mesh.index(level, translate(bd, me)), bi)
+            for cc in range(2):
+                out[bi] = out[bi] + (-lc[cc]) * u[st[cc]]
+    return out
+
+
+# ----------------------------------------------------------------------------
 # demo drivers
 # ----------------------------------------------------------------------------
 def init_disc(mesh: Mesh, center, radius):

@@ -89,6 +89,8 @@ SYMBOLS = {
     "smr_update_ghost_mr": [_u64],
     "smr_fv_upwind": [_u64, _u64, _vp, _dbl],
     "smr_fv_upwind_burgers": [_u64, _u64, _vp, _dbl],
+    "smr_scheme_apply": [_u64, _u64, _i32, _vp],
+    "smr_field_lincomb": [_u64, _dbl, _u64, _dbl, _u64],
     "smr_adapt": [_vp, _i32, _dbl, _dbl, _P(_i32)],
     "smr_adapt_iteration": [_vp, _i32, _dbl, _dbl, _i32, _P(_i32)],
     "smr_adapt_last_size": [_u64, _P(_i64)],
@@ -468,6 +470,39 @@ def upwind_scalar_burgers_step(unp1: ScalarField, u: ScalarField, k, dt):
     """unp1 = u - dt * samurai::upwind_scalar_burgers(k, u)."""
     k = np.ascontiguousarray(k, dtype=np.float64)
     _check(load_library().smr_fv_upwind_burgers(unp1._h, u._h, k.ctypes.data, float(dt)))
+
+
+CONVECTION_UPWIND, DIFFUSION_ORDER2 = 0, 1
+
+
+class FluxScheme:
+    """A flux-based linear homogeneous scheme object: `rhs = scheme(u)` / `scheme.apply(out, u)` (schemes/fv/FV_scheme.hpp:202-238)."""
+
+    def __init__(self, kind, params, name):
+        self.kind, self.params, self.name = kind, np.ascontiguousarray(params, dtype=np.float64), name
+
+    def apply(self, out: ScalarField, u: ScalarField):
+        _check(load_library().smr_scheme_apply(out._h, u._h, self.kind, self.params.ctypes.data))
+
+    def __call__(self, u: ScalarField):
+        out = ScalarField(f"{self.name}({u.name})", u.mesh)
+        self.apply(out, u)
+        return out
+
+
+def make_convection_upwind(velocity):
+    """samurai::make_convection_upwind<Field>(velocity) (schemes/fv/operators/convection_lin.hpp:15-89)."""
+    return FluxScheme(CONVECTION_UPWIND, velocity, "convection")
+
+
+def make_diffusion_order2(K):
+    """samurai::make_diffusion_order2<Field>(K) (schemes/fv/operators/diffusion.hpp:123-175)."""
+    return FluxScheme(DIFFUSION_ORDER2, K, "diffusion")
+
+
+def lincomb(out: ScalarField, a, x: ScalarField, b, y: ScalarField):
+    """out = a*x + b*y on the leaves; `unp1 = u - dt * scheme(u)` is lincomb(unp1, 1, u, -dt, rhs)."""
+    _check(load_library().smr_field_lincomb(out._h, float(a), x._h, float(b), y._h))
 
 
 class mra_config:

@@ -1366,6 +1366,112 @@ extern "C"
             });
     }
 
+    int smr_scheme_apply(smr_field_t outh, smr_field_t inh, int kind, const double* params)
+    {
+        return guarded(
+            [&]
+            {
+                require_device();
+                FieldObj& out = get_field(outh);
+                FieldObj& in  = get_field(inh);
+                if (out.mesh != in.mesh || &out == &in)
+                {
+                    throw std::invalid_argument("scheme output must be a different field on the same mesh");
+                }
+                MeshObj& mo = *in.mesh;
+                check_field_ready(in);
+                const MeshConfig& cfg = mo.mesh.cfg;
+                const int level       = mo.mesh.min_leaf_level();
+                if (level != mo.mesh.max_leaf_level())
+                {
+                    throw std::invalid_argument("flux-based schemes are implemented for uniform-level meshes only (level jumps: next round)");
+                }
+                if (kind != SMR_SCHEME_CONVECTION_UPWIND && kind != SMR_SCHEME_DIFFUSION_ORDER2)
+                {
+                    throw std::invalid_argument("unknown scheme kind");
+                }
+                // update_ghosts_if_needed (schemes/fv/FV_scheme.hpp:187-197)
+                if (!in.ghosts_valid)
+                {
+                    ensure_plan(mo);
+                    do_update_ghost(in);
+                }
+                ensure_plan(mo);
+                if (static_cast<size_t>(mo.mesh.nref) * sizeof(double) > out.data.cap)
+                {
+                    SMR_CUDA(cudaStreamSynchronize(g.stream));
+                }
+                out.data.ensure(static_cast<size_t>(mo.mesh.nref) * sizeof(double));
+                out.n = mo.mesh.nref;
+                Section sec;
+                out.ghosts_valid = false;
+                mg_barrier();
+                SMR_CUDA(cudaMemsetAsync(out.data.p, 0, static_cast<size_t>(out.n) * sizeof(double), g.stream)); // output.fill(0)
+                mg_barrier();
+                FluxParams p;
+                const double h      = cfg.cell_length(level);
+                const double factor = std::pow(h, cfg.dim - 1) / std::pow(h, cfg.dim); // h_factor, lin_hom.hpp:62-67
+                for (int d = 0; d < 3; ++d)
+                {
+                    double left = 0, right = 0;
+                    if (d < cfg.dim)
+                    {
+                        if (kind == SMR_SCHEME_CONVECTION_UPWIND) // operators/convection_lin.hpp:31-72
+                        {
+                            const double v = params[d];
+                            left           = v >= 0 ? v : 0.0;
+                            right          = v >= 0 ? 0.0 : v;
+                        }
+                        else // operators/diffusion.hpp:143-170
+                        {
+                            left  = -1 / h;
+                            right = 1 / h;
+                            left *= -params[d];
+                            right *= -params[d];
+                        }
+                    }
+                    p.lc[d][0] = factor * left;
+                    p.lc[d][1] = factor * right;
+                    p.n[d]     = cfg.n0[d] << level;
+                }
+                const double* u = static_cast<const double*>(in.data.p);
+                double* o       = static_cast<double*>(out.data.p);
+                launch_dim<FluxLinHomOp, smr_item_fv>(SMR_FAM_FV, cfg.dim, mo.d_arena.p, mo.plan.fv, -1, u, o, p);
+            });
+    }
+
+    int smr_field_lincomb(smr_field_t outh, double a, smr_field_t xh, double b, smr_field_t yh)
+    {
+        return guarded(
+            [&]
+            {
+                require_device();
+                FieldObj& out = get_field(outh);
+                FieldObj& x   = get_field(xh);
+                FieldObj& y   = get_field(yh);
+                if (out.mesh != x.mesh || out.mesh != y.mesh)
+                {
+                    throw std::invalid_argument("fields live on different meshes");
+                }
+                MeshObj& mo = *x.mesh;
+                check_field_ready(x);
+                check_field_ready(y);
+                ensure_plan(mo);
+                if (static_cast<size_t>(mo.mesh.nref) * sizeof(double) > out.data.cap)
+                {
+                    SMR_CUDA(cudaStreamSynchronize(g.stream));
+                }
+                out.data.ensure(static_cast<size_t>(mo.mesh.nref) * sizeof(double));
+                out.n = mo.mesh.nref;
+                Section sec;
+                out.ghosts_valid = false;
+                launch<smr_item_fv>(SMR_FAM_FV,
+                                    mo.d_arena.p,
+                                    mo.plan.fv,
+                                    LinCombOp{static_cast<const double*>(x.data.p), static_cast<const double*>(y.data.p), static_cast<double*>(out.data.p), a, b, a == 1.0});
+            });
+    }
+
     static std::vector<FieldObj*> collect_fields(const smr_field_t* fields, int n)
     {
         if (n < 1 || n > 8)

@@ -338,6 +338,84 @@ namespace smr
     };
 
     // ------------------------------------------------------------------------------------------------------------
+    // Flux-based linear homogeneous schemes on a uniform-level mesh: out = S(u) for stencil-2 conservative fluxes
+    // (make_convection_upwind, make_diffusion_order2).  The reference scatters `out[left] += lc[c]*u[st_c]`,
+    // `out[right] += rc[c]*u[st_c]` interface interval by interface interval, then the boundary interfaces
+    // (flux_based/explicit_flux_based_scheme__lin_hom.hpp:39-119, 233-319); a cell therefore receives, per direction,
+    // the four products {lc0*u_c, lc1*u_+, rc0*u_-, rc1*u_c} in an order that depends only on whether it touches the low
+    // or the high boundary and on the direction (x: both sides come from ONE interface interval; y/z: the lower row's
+    // interval is visited before the cell's own).  This gather adds them in exactly that order.
+    // ------------------------------------------------------------------------------------------------------------
+    struct FluxParams
+    {
+        double lc[3][2]; // left-cell coefficients factor * flux_coeffs, per direction
+        int n[3];        // domain size in cells at the mesh level
+    };
+
+    template <int DIM>
+    struct FluxLinHomOp
+    {
+        static constexpr bool two_phase = false;
+        static constexpr int min_blocks = 1;
+        static constexpr int units_per_thread = SMR_CELLS_PER_THREAD;
+
+        const double* __restrict__ u;
+        double* __restrict__ out;
+        FluxParams p;
+
+        __device__ __forceinline__ void operator()(const smr_item_fv& it, int k) const
+        {
+            const double* c = u + it.c + k;
+            const double uc = c[0];
+            const int idx[3] = {it.x + k, it.y, it.z};
+            double acc = 0.0;
+#pragma unroll
+            for (int d = 0; d < DIM; ++d)
+            {
+                const double um = d == 0 ? c[-1] : (d == 1 ? u[it.ym + k] : u[it.zm + k]);
+                const double up = d == 0 ? c[1] : (d == 1 ? u[it.yp + k] : u[it.zp + k]);
+                const double tLc = p.lc[d][0] * uc, tLp = p.lc[d][1] * up;
+                const double tRm = (-p.lc[d][0]) * um, tRc = (-p.lc[d][1]) * uc;
+                const bool low = idx[d] == 0, high = idx[d] == p.n[d] - 1;
+                if (low)
+                {
+                    acc = (((acc + tLc) + tLp) + tRm) + tRc;
+                }
+                else if (d == 0 && !high)
+                {
+                    acc = (((acc + tLc) + tRm) + tLp) + tRc;
+                }
+                else
+                {
+                    acc = (((acc + tRm) + tRc) + tLc) + tLp;
+                }
+            }
+            mstore(out + it.c + k, acc, static_cast<unsigned>(it.mask));
+        }
+    };
+
+    // out = a * x + b * y on the leaves (the field-expression tail `u - dt * S(u)` is a = 1, b = -dt)
+    struct LinCombOp
+    {
+        static constexpr bool two_phase = false;
+        static constexpr int min_blocks = 1;
+        static constexpr int units_per_thread = SMR_CELLS_PER_THREAD;
+
+        const double* x;
+        const double* y;
+        double* out;
+        double a, b;
+        bool a_is_one;
+
+        __device__ __forceinline__ void operator()(const smr_item_fv& it, int k) const
+        {
+            const int64_t i = it.c + k;
+            const double v  = a_is_one ? x[i] + b * y[i] : a * x[i] + b * y[i];
+            mstore(out + i, v, static_cast<unsigned>(it.mask));
+        }
+    };
+
+    // ------------------------------------------------------------------------------------------------------------
     // projection (numeric/projection.hpp:22-64)
     // ------------------------------------------------------------------------------------------------------------
     template <int DIM>
