@@ -227,6 +227,19 @@ def uniform_sweep(sb, torch, level, iters=20):
     e1.record()
     torch.cuda.synchronize()
     secs = e0.elapsed_time(e1) * 1e-3 / iters
+    # heat/diffusion sweep (make_diffusion_order2, explicit): rhs = S(u) then unp1 = u - dt * rhs, the reference's unfused form
+    rhs = sb.make_scalar_field("rhs", mesh)
+    diff = sb.make_diffusion_order2([1.0, 1.0])
+    for _ in range(3):
+        diff.apply(rhs, u)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        diff.apply(rhs, u)
+    e1.record()
+    torch.cuda.synchronize()
+    dsecs = e0.elapsed_time(e1) * 1e-3 / iters
+    rhs.destroy()
     # ghost update on the same mesh (BC only on a uniform mesh)
     e0.record()
     for _ in range(iters):
@@ -237,7 +250,7 @@ def uniform_sweep(sb, torch, level, iters=20):
     u.destroy()
     v.destroy()
     mesh.destroy()
-    return n, secs, gsecs
+    return n, secs, gsecs, dsecs
 
 
 def run_product(args):
@@ -375,10 +388,12 @@ def run_product(args):
         # ---- uniform sweep (configs[4]) -----------------------------------------------------------------------------
         sweep = None
         if args.sweep_level > 0:
-            n_u, s_u, g_u = uniform_sweep(sb, torch, args.sweep_level)
+            n_u, s_u, g_u, d_u = uniform_sweep(sb, torch, args.sweep_level)
             sweep = {"workload": f"uniform 2D level {args.sweep_level} upwind sweep, {n_u} cells, working set {16 * n_u / 1e6:.0f} MB > L2",
                      "cell_updates_per_s": n_u / s_u, "ms_per_sweep": 1e3 * s_u, "bound": "hbm", "achieved": 16.0 * n_u / s_u / 1e9,
-                     "peak": peak_gbs, "unit": "GB/s", "frac": 16.0 * n_u / s_u / 1e9 / peak_gbs, "ghost_update_ms": 1e3 * g_u}
+                     "peak": peak_gbs, "unit": "GB/s", "frac": 16.0 * n_u / s_u / 1e9 / peak_gbs, "ghost_update_ms": 1e3 * g_u,
+                     "diffusion_order2": {"ms_per_apply": 1e3 * d_u, "note": "rhs = make_diffusion_order2(K)(u): fill(0) + gather, 8 B zero-fill + 8 B read + 8 B write per cell",
+                                          "achieved": 24.0 * n_u / d_u / 1e9, "frac": 24.0 * n_u / d_u / 1e9 / peak_gbs}}
 
         # ---- cpu baseline: oracle port on a bounded sample of the same state ----------------------------------------
         cpu = None

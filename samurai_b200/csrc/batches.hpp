@@ -615,6 +615,9 @@ namespace smr
                 it.n     = e - s;
                 it.level = l;
                 it.mask  = static_cast<int>(flt.dim > 2 ? flt.mask(l, y0, z0) : flt.mask(l, y0, z0, R));
+                it.x     = s;
+                it.y     = y0;
+                it.z     = z0;
                 strips.push_back(it);
             }
             // remainder of every row

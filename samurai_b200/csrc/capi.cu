@@ -1436,7 +1436,19 @@ extern "C"
                 }
                 const double* u = static_cast<const double*>(in.data.p);
                 double* o       = static_cast<double*>(out.data.p);
-                launch_dim<FluxLinHomOp, smr_item_fv>(SMR_FAM_FV, cfg.dim, mo.d_arena.p, mo.plan.fv, -1, u, o, p);
+                if (cfg.dim > 1)
+                {
+                    if (g.profile)
+                    {
+                        g.prof_cells[SMR_FAM_FV] += static_cast<uint64_t>(mo.plan.fv_strip.n_cells) * (SMR_STRIP_ROWS - 1);
+                    }
+                    launch_dim<FluxLinHomStripOp, smr_item_fvstrip>(SMR_FAM_FV, cfg.dim, mo.d_arena.p, mo.plan.fv_strip, -1, u, o, p);
+                    launch_dim<FluxLinHomOp, smr_item_fv>(SMR_FAM_FV, cfg.dim, mo.d_arena.p, mo.plan.fv_single, -1, u, o, p);
+                }
+                else
+                {
+                    launch_dim<FluxLinHomOp, smr_item_fv>(SMR_FAM_FV, cfg.dim, mo.d_arena.p, mo.plan.fv, -1, u, o, p);
+                }
             });
     }
 

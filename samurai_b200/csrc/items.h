@@ -59,7 +59,7 @@ typedef struct
     int32_t n; /* columns */
     int32_t level;
     int32_t mask;
-    int32_t pad;
+    int32_t x, y, z; /* coordinates of the first cell of the first row */
 } smr_item_fvstrip;
 
 /* coarse interval filled by projection (numeric/projection.hpp:22-64) */

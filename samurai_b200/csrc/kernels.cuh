@@ -394,6 +394,58 @@ namespace smr
         }
     };
 
+    // strip form (see FvStripOp): the column of SMR_STRIP_ROWS rows lives in registers
+    template <int DIM>
+    struct FluxLinHomStripOp
+    {
+        static constexpr bool two_phase = false;
+        static constexpr int min_blocks = STRIP_MIN_BLOCKS;
+        static constexpr int units_per_thread = STRIP_UPT;
+
+        const double* __restrict__ u;
+        double* __restrict__ out;
+        FluxParams p;
+
+        __device__ __forceinline__ double dir_terms(double acc, int d, int idx, double um, double uc, double up) const
+        {
+            const double tLc = p.lc[d][0] * uc, tLp = p.lc[d][1] * up;
+            const double tRm = (-p.lc[d][0]) * um, tRc = (-p.lc[d][1]) * uc;
+            if (idx == 0)
+            {
+                return (((acc + tLc) + tLp) + tRm) + tRc;
+            }
+            if (d == 0 && idx != p.n[0] - 1)
+            {
+                return (((acc + tLc) + tRm) + tLp) + tRc;
+            }
+            return (((acc + tRm) + tRc) + tLc) + tLp;
+        }
+
+        __device__ __forceinline__ void operator()(const smr_item_fvstrip& it, int k) const
+        {
+            constexpr int R = SMR_STRIP_ROWS;
+            double v[R + 2];
+#pragma unroll
+            for (int r = 0; r < R + 2; ++r)
+            {
+                v[r] = u[it.row[r] + k];
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+            {
+                const double* c = u + it.row[r + 1] + k;
+                const double uc = v[r + 1];
+                double acc      = dir_terms(0.0, 0, it.x + k, c[-1], uc, c[1]);
+                acc             = dir_terms(acc, 1, it.y + r, v[r], uc, v[r + 2]);
+                if (DIM > 2)
+                {
+                    acc = dir_terms(acc, 2, it.z, u[it.zm[r] + k], uc, u[it.zp[r] + k]);
+                }
+                mstore(out + it.row[r + 1] + k, acc, static_cast<unsigned>(it.mask));
+            }
+        }
+    };
+
     // out = a * x + b * y on the leaves (the field-expression tail `u - dt * S(u)` is a = 1, b = -dt)
     struct LinCombOp
     {
