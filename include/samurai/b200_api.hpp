@@ -1138,11 +1138,13 @@ namespace samurai
 
         mra_config& relative_detail(bool b)
         {
-            if (b)
-            {
-                throw std::invalid_argument("relative_detail is not implemented on the device path");
-            }
+            m_rel = b;
             return *this;
+        }
+
+        bool relative_detail() const
+        {
+            return m_rel;
         }
 
         void parse_args()
@@ -1160,6 +1162,7 @@ namespace samurai
       private:
 
         double m_eps = 1e-4, m_reg = 1.;
+        bool m_rel   = false;
     };
 
     // ---- mr/adapt.hpp:391-397 ----------------------------------------------------------------------------------------------
@@ -1176,22 +1179,22 @@ namespace samurai
         void operator()(mra_config& cfg)
         {
             cfg.parse_args();
-            call(cfg.epsilon(), cfg.regularity(), std::index_sequence_for<Fields...>{});
+            call(cfg.epsilon(), cfg.regularity(), cfg.relative_detail(), std::index_sequence_for<Fields...>{});
         }
 
         void operator()(double eps, double regularity)
         {
-            call(eps, regularity, std::index_sequence_for<Fields...>{});
+            call(eps, regularity, false, std::index_sequence_for<Fields...>{});
         }
 
       private:
 
         template <std::size_t... I>
-        void call(double eps, double reg, std::index_sequence<I...>)
+        void call(double eps, double reg, bool rel, std::index_sequence<I...>)
         {
             smr_field_t h[] = {std::get<I>(m_fields)->device()...};
             int it          = 0;
-            b200::check(smr_adapt(h, static_cast<int>(sizeof...(Fields)), eps, reg, &it));
+            b200::check(smr_adapt_ex(h, static_cast<int>(sizeof...(Fields)), eps, reg, rel ? 1 : 0, &it));
             (std::get<I>(m_fields)->device_written(), ...);
         }
 

@@ -136,6 +136,8 @@ extern "C"
      * `fields`; any other field living on the mesh must be smr_field_resize()d by the caller, as in the reference.
      * *n_iterations receives the number of harten iterations executed. */
     int smr_adapt(const smr_field_t* fields, int n_fields, double epsilon, double regularity, int* n_iterations);
+    /* same with mra_config::relative_detail (mr/config.hpp, mr/rel_detail.hpp:73-112): details divided by max_leaves |f| */
+    int smr_adapt_ex(const smr_field_t* fields, int n_fields, double epsilon, double regularity, int relative_detail, int* n_iterations);
     /* one harten iteration (mr/adapt.hpp:277-389); *unchanged = 1 when the mesh was already at its fixed point */
     int smr_adapt_iteration(const smr_field_t* fields, int n_fields, double epsilon, double regularity, int ite, int* unchanged);
     /* detail and tag arrays of the last harten iteration, reference-sized, as they were BEFORE the mesh update;

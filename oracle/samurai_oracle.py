@@ -730,7 +730,17 @@ class AdaptStats:
     changed: bool = False
 
 
-def adapt(mesh: Mesh, f, bc: Bc, eps=1e-4, regularity=1.0, trace=None):
+def compute_relative_detail(mesh: Mesh, f, detail):
+    """compute_relative_detail (mr/rel_detail.hpp:73-112): detail *= 1 / max_leaves |f| over the whole array."""
+    m = np.finfo(np.float64).tiny  # std::numeric_limits<double>::min()
+    for l in mesh.leaf_levels():
+        m = max(m, float(np.max(np.abs(f[mesh.index(l, mesh.cells[l])]))))
+    if m < np.finfo(np.float64).eps:
+        m = 1.0
+    detail *= 1.0 / m
+
+
+def adapt(mesh: Mesh, f, bc: Bc, eps=1e-4, regularity=1.0, trace=None, relative_detail=False):
     """Adapt::operator() + harten (mr/adapt.hpp:148-195, 277-389). Returns (mesh, field)."""
     cfg = mesh.cfg
     lmin, L = cfg.min_level, cfg.max_level
@@ -744,6 +754,8 @@ def adapt(mesh: Mesh, f, bc: Bc, eps=1e-4, regularity=1.0, trace=None):
         update_ghost_mr(mesh, f, bc)
         for level in range(max(lmin - 1, 0), L - ite):
             compute_detail(mesh, f, detail, level, detail_set(mesh, level))
+        if relative_detail:
+            compute_relative_detail(mesh, f, detail)
         for level in range(lmin, L - ite + 1):
             mr_criteria(mesh, detail, tag, level, eps, regularity)
         for level in range(L, 0, -1):

@@ -92,6 +92,7 @@ SYMBOLS = {
     "smr_scheme_apply": [_u64, _u64, _i32, _vp],
     "smr_field_lincomb": [_u64, _dbl, _u64, _dbl, _u64],
     "smr_adapt": [_vp, _i32, _dbl, _dbl, _P(_i32)],
+    "smr_adapt_ex": [_vp, _i32, _dbl, _dbl, _i32, _P(_i32)],
     "smr_adapt_iteration": [_vp, _i32, _dbl, _dbl, _i32, _P(_i32)],
     "smr_adapt_last_size": [_u64, _P(_i64)],
     "smr_adapt_last_tags": [_u64, _vp, _i64],
@@ -509,7 +510,11 @@ class mra_config:
     """samurai::mra_config (mr/config.hpp:10-68)."""
 
     def __init__(self):
-        self._eps, self._reg = 1e-4, 1.0
+        self._eps, self._reg, self._rel = 1e-4, 1.0, False
+
+    def relative_detail(self, v=True):
+        self._rel = bool(v)
+        return self
 
     def epsilon(self, v):
         self._eps = v
@@ -529,7 +534,7 @@ class MRAdapt:
 
     def __call__(self, cfg: mra_config):
         n = C.c_int()
-        _check(load_library().smr_adapt(self._arr, len(self.fields), cfg._eps, cfg._reg, C.byref(n)))
+        _check(load_library().smr_adapt_ex(self._arr, len(self.fields), cfg._eps, cfg._reg, int(cfg._rel), C.byref(n)))
         return n.value
 
     def iteration(self, cfg: mra_config, ite):

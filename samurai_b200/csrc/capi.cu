@@ -187,13 +187,14 @@ namespace smr
         MeshPlan plan;
         bool plan_ready = false;
         DevBuf d_arena;
-        DevBuf d_detail, d_tag;
+        DevBuf d_detail, d_tag, d_relmax;
         PlanFilter filter; // multi-GPU slab ownership for this mesh (identity when world == 1)
 
         MeshObj()
         {
             d_detail.shared = true;
             d_tag.shared    = true;
+            d_relmax.shared = true;
         }
         PinnedBuf h_tag;
         int64_t last_size   = 0;
@@ -711,7 +712,7 @@ namespace smr
     }
 
     // one harten iteration; returns true when the mesh is unchanged
-    static bool do_harten(std::vector<FieldObj*>& fields, double eps, double regularity, int ite)
+    static bool do_harten(std::vector<FieldObj*>& fields, double eps, double regularity, int ite, bool relative_detail = false)
     {
         require_device();
         MeshObj& mo           = *fields[0]->mesh;
@@ -756,6 +757,31 @@ namespace smr
                 {
                     launch_dim<DetailOp1, smr_item_detail>(SMR_FAM_DETAIL, dim, arena, mo.plan.detail, limit, u, detail + c * n);
                 }
+            }
+        }
+        if (relative_detail)
+        {
+            // compute_relative_detail (mr/rel_detail.hpp:73-112), one component per adapted field
+            mo.d_relmax.ensure(sizeof(unsigned long long) * SMR_MAX_RANKS * 8);
+            unsigned long long* slots = static_cast<unsigned long long*>(mo.d_relmax.p);
+            mg_barrier();
+            SMR_CUDA(cudaMemsetAsync(slots, 0, sizeof(unsigned long long) * SMR_MAX_RANKS * 8, g.stream));
+            mg_barrier();
+            for (int c = 0; c < ncomp; ++c)
+            {
+                launch<smr_item_fv>(SMR_FAM_DETAIL, arena, mo.plan.fv, AbsMaxOp{static_cast<const double*>(fields[c]->data.p), slots + c * SMR_MAX_RANKS + g.mg_rank});
+                if (g.mg_world > 1 && g.mg_connected)
+                {
+                    publish_slot_kernel<<<1, 32, 0, g.stream>>>(slots + c * SMR_MAX_RANKS);
+                    SMR_CUDA(cudaGetLastError());
+                    ++g.stats.kernel_launches;
+                    mg_barrier();
+                }
+                const int grid = static_cast<int>(std::min<int64_t>((n + SMR_CTA_THREADS - 1) / SMR_CTA_THREADS, 148 * 16));
+                scale_detail_kernel<<<grid, SMR_CTA_THREADS, 0, g.stream>>>(detail + c * n, n, slots + c * SMR_MAX_RANKS, g.mg_world);
+                SMR_CUDA(cudaGetLastError());
+                ++g.stats.kernel_launches;
+                mg_barrier();
             }
         }
         TagParams tp;
@@ -1510,6 +1536,11 @@ extern "C"
 
     int smr_adapt(const smr_field_t* fields, int n_fields, double epsilon, double regularity, int* n_iterations)
     {
+        return smr_adapt_ex(fields, n_fields, epsilon, regularity, 0, n_iterations);
+    }
+
+    int smr_adapt_ex(const smr_field_t* fields, int n_fields, double epsilon, double regularity, int relative_detail, int* n_iterations)
+    {
         return guarded(
             [&]
             {
@@ -1521,7 +1552,7 @@ extern "C"
                     for (int ite = 0; ite < cfg.max_level - cfg.min_level; ++ite)
                     {
                         ++done;
-                        if (do_harten(v, epsilon, regularity, ite))
+                        if (do_harten(v, epsilon, regularity, ite, relative_detail != 0))
                         {
                             break;
                         }

@@ -771,6 +771,60 @@ namespace smr
         }
     };
 
+    // ------------------------------------------------------------------------------------------------------------
+    // relative detail (mr/rel_detail.hpp:73-112): max over the leaves of |f| (max is order independent, so the parallel
+    // reduction is bit-identical to the reference's loop), then detail *= 1/max over the whole array.
+    // Non-negative doubles order like their bit patterns, so the reduction is an integer atomicMax.
+    // ------------------------------------------------------------------------------------------------------------
+    struct AbsMaxOp
+    {
+        static constexpr bool two_phase = false;
+        static constexpr int min_blocks = 1;
+        static constexpr int units_per_thread = SMR_CELLS_PER_THREAD;
+
+        const double* __restrict__ f;
+        unsigned long long* slot; // this rank's slot
+
+        __device__ __forceinline__ void operator()(const smr_item_fv& it, int k) const
+        {
+            const unsigned long long v = static_cast<unsigned long long>(__double_as_longlong(fabs(f[it.c + k])));
+            if (v > *reinterpret_cast<volatile unsigned long long*>(slot))
+            {
+                atomicMax(slot, v);
+            }
+        }
+    };
+
+    // publish this rank's slot into every peer's table (multi-GPU), one thread per peer
+    __global__ void publish_slot_kernel(unsigned long long* slots)
+    {
+        const int p = threadIdx.x;
+        if (p < g_peers.world && p != g_peers.rank)
+        {
+            unsigned long long* remote = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(slots) + g_peers.delta[p]);
+            remote[g_peers.rank]       = slots[g_peers.rank];
+        }
+    }
+
+    __global__ void __launch_bounds__(SMR_CTA_THREADS) scale_detail_kernel(double* __restrict__ detail, int64_t n, const unsigned long long* slots, int world)
+    {
+        unsigned long long mbits = static_cast<unsigned long long>(__double_as_longlong(2.2250738585072014e-308)); // DBL_MIN
+        for (int r = 0; r < world; ++r)
+        {
+            mbits = slots[r] > mbits ? slots[r] : mbits;
+        }
+        double m = __longlong_as_double(static_cast<long long>(mbits));
+        if (m < 2.220446049250313e-16) // DBL_EPSILON
+        {
+            m = 1.0;
+        }
+        const double inv = 1. / m;
+        for (int64_t i = static_cast<int64_t>(blockIdx.x) * SMR_CTA_THREADS + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * SMR_CTA_THREADS)
+        {
+            detail[i] *= inv;
+        }
+    }
+
     // tag[leaf] = keep (mr/adapt.hpp:286-290), driven by the FV leaf batch
     struct KeepLeavesOp
     {

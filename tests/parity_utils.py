@@ -76,7 +76,7 @@ def assert_fields_close(a, b, what, tol=REL_TOL, finite_only=False):
 
 
 def run_advection_parity(dim=2, min_level=2, max_level=6, pred_radius=1, steps=3, eps=2e-4, regularity=1.0, device=0, verbose=False,
-                         scheme="upwind"):
+                         scheme="upwind", relative_detail=False, amplitude=1.0):
     """demos/FiniteVolume/advection_2d.cpp time loop on the GPU, checked against the oracle at every step:
     meshes bit-identical (cells + all ghosts + storage offsets), fields within 1e-12 relative."""
     if not sb.initialize(device):
@@ -85,7 +85,7 @@ def run_advection_parity(dim=2, min_level=2, max_level=6, pred_radius=1, steps=3
     bc = so.Bc("dirichlet", 0.0)
     omesh = so.Mesh.uniform(ocfg)
     center, radius = [0.3] * dim, 0.2
-    ou = so.init_disc(omesh, center, radius)
+    ou = so.init_disc(omesh, center, radius) * amplitude
 
     pmesh = sb.MRMesh.make_mesh([0.0] * dim, [1.0] * dim, product_cfg(dim, min_level, max_level, pred_radius))
     assert_same_mesh(pmesh, omesh)
@@ -95,7 +95,7 @@ def run_advection_parity(dim=2, min_level=2, max_level=6, pred_radius=1, steps=3
     sb.make_bc(u, sb.DIRICHLET, 0.0)
     unp1 = sb.make_scalar_field("unp1", pmesh)
     adapt = sb.make_MRAdapt(u)
-    mcfg = sb.mra_config().epsilon(eps).regularity(regularity)
+    mcfg = sb.mra_config().epsilon(eps).regularity(regularity).relative_detail(relative_detail)
     a = [1.0] * dim
     dt = 0.5 * pmesh.min_cell_length() if dim == 2 else 0.25 * pmesh.min_cell_length()
 
@@ -108,11 +108,11 @@ def run_advection_parity(dim=2, min_level=2, max_level=6, pred_radius=1, steps=3
             print(f"{tag}: leaves {omesh.nb_cells()} ref {omesh.nref} max rel err {err:.2e}")
 
     adapt(mcfg)
-    omesh, ou = so.adapt(omesh, ou, bc, eps, regularity)
+    omesh, ou = so.adapt(omesh, ou, bc, eps, regularity, relative_detail=relative_detail)
     check("initial adaptation")
     for it in range(steps):
         adapt(mcfg)
-        omesh, ou = so.adapt(omesh, ou, bc, eps, regularity)
+        omesh, ou = so.adapt(omesh, ou, bc, eps, regularity, relative_detail=relative_detail)
         sb.update_ghost_mr(u)
         so.update_ghost_mr(omesh, ou, bc)
         # after the ghost update every reference cell the oracle defines must agree

@@ -16,3 +16,9 @@ def test_advection_loop_matches_oracle(gpu, dim, lmin, lmax, pred, steps):
 
 def test_burgers_loop_matches_oracle(gpu):
     pu.run_advection_parity(dim=2, min_level=2, max_level=7, pred_radius=1, steps=4, scheme="burgers")
+
+
+def test_relative_detail_matches_oracle(gpu):
+    """mra_config().relative_detail(true) (mr/rel_detail.hpp:73-112): details normalised by max_leaves |u|; with an
+    amplitude of 37.5 the absolute and relative criteria give different meshes, so the path is really exercised."""
+    pu.run_advection_parity(dim=2, min_level=2, max_level=7, pred_radius=1, steps=3, relative_detail=True, amplitude=37.5)
