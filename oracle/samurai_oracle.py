@@ -33,6 +33,8 @@ from __future__ import annotations
 import itertools
 from dataclasses import dataclass, field as dc_field
 
+import math
+
 import numpy as np
 
 # ----------------------------------------------------------------------------
@@ -841,66 +843,207 @@ def diffusion_order2_coeffs(K):
     return fn
 
 
+def _runs(keys, dim):
+    """Split sorted cell keys into x-intervals (runs of consecutive x in one row), in for_each_interval order."""
+    if keys.size == 0:
+        return []
+    brk = np.flatnonzero(np.diff(keys) != 1) + 1
+    return np.split(keys, brk)
+
+
 def flux_linhom_apply(mesh: Mesh, u, coeff_fn):
-    """Explicit<FluxBasedScheme<LinearHomogeneous>>::apply, sequential context
-    (flux_based/explicit_flux_based_scheme__lin_hom.hpp:39-119, 233-319; coefficient loop
-    flux_based_scheme__lin_hom.hpp:74-229; interfaces interface.hpp:35-110, 440-509), restated literally: for every
-    direction, the same-level interface intervals in for_each_interval order, each applying
-    `out[left] += lc[c]*in[st_c]; out[right] += rc[c]*in[st_c]` for c = 0, 1, then the boundary interfaces.
-    Only meshes whose leaves sit on one level (no level jump) are supported here."""
-    dim = mesh.cfg.dim
-    levels = mesh.leaf_levels()
-    assert len(levels) == 1, "oracle flux path: uniform-level meshes only"
-    level = levels[0]
-    h = mesh.cfg.cell_length(level)
+    """Explicit<FluxBasedScheme<LinearHomogeneous>>::apply in its sequential context, restated literally
+    (flux_based/explicit_flux_based_scheme__lin_hom.hpp:39-119, 233-319; coefficient / level loop
+    flux_based_scheme__lin_hom.hpp:74-229; interface sets interface.hpp:35-110, 125-306, 440-509).
+    For every direction: same-level interface intervals of every level, then per level the two level-jump orientations,
+    then the boundary interfaces; every interval applies, for c = 0, 1:  out[left] += lc[c]*in[st_c]; out[right] += rc[c]*in[st_c]
+    (coarse side of a jump: lc*in[2ii] + lc*in[2ii+1])."""
+    cfg, dim = mesh.cfg, mesh.cfg.dim
     out = np.zeros(mesh.nref)
-    cells = mesh.cells[level]
-    c = unpack(cells, dim)
-    factor = pow(h, dim - 1) / pow(h, dim)  # h_factor (flux_based_scheme__lin_hom.hpp:62-67)
+    leaf_lv = mesh.leaf_levels()
+    lo = max(cfg.min_level, leaf_lv[0] - 1)
+    hi = min(cfg.max_level, leaf_lv[-1] + 1)
+
+    def hfac(h_face, h_cell):
+        return pow(h_face, dim - 1) / pow(h_cell, dim)
+
     for d in range(dim):
         e = [0] * dim
         e[d] = 1
-        fc = coeff_fn(d, h)
-        lc = (factor * fc[0], factor * fc[1])
-        rc = (-lc[0], -lc[1])
-        # interface set: cells ∩ translate(cells, -dir), traversed row by row (rows = all coords but x)
-        has_next = np.isin(translate(cells, e), cells)
-        left_all = cells[has_next]
-        if dim == 1:
-            groups = [left_all]
-        else:
-            lcoords = unpack(left_all, dim)
-            rowkey = np.zeros(left_all.size, dtype=np.int64)
-            for dd in range(dim - 1, 0, -1):
-                rowkey = rowkey * (1 << 21) + (lcoords[:, dd] + BIAS)
-            order = np.argsort(rowkey, kind="stable")
-            left_sorted = left_all[order]
-            rk = rowkey[order]
-            bounds = np.flatnonzero(np.diff(rk)) + 1
-            groups = np.split(left_sorted, bounds)
-        for left in groups:
-            if left.size == 0:
-                continue
-            li = mesh.index(level, left)
-            ri = mesh.index(level, translate(left, e))
-            st = (li, ri)  # stencil cells {0, +dir} = (left cell, right cell)
-            for cc in range(2):
-                out[li] = out[li] + lc[cc] * u[st[cc]]
-                out[ri] = out[ri] + rc[cc] * u[st[cc]]
-        # boundary interfaces: direction, then opposite direction
-        bd = cells[~mesh.in_domain(level, translate(cells, e))]
-        if bd.size:
-            bi = mesh.index(level, bd)
-            st = (bi, mesh.index(level, translate(bd, e)))
-            for cc in range(2):
-                out[bi] = out[bi] + lc[cc] * u[st[cc]]
         me = [-v for v in e]
-        bd = cells[~mesh.in_domain(level, translate(cells, me))]
-        if bd.size:
-            bi = mesh.index(level, bd)
-            st = (mesh.index(level, translate(bd, me)), bi)
-            for cc in range(2):
-                out[bi] = out[bi] + (-lc[cc]) * u[st[cc]]
+        # ---- same level
+        for level in range(lo, hi + 1):
+            cells = mesh.cells[level]
+            if cells.size == 0:
+                continue
+            h = cfg.cell_length(level)
+            fc = coeff_fn(d, h)
+            f = hfac(h, h)
+            lc = (f * fc[0], f * fc[1])
+            rc = (-lc[0], -lc[1])
+            iface = cells[np.isin(translate(cells, e), cells)]
+            for run in _runs(iface, dim):
+                li = mesh.index(level, run)
+                ri = mesh.index(level, translate(run, e))
+                st = (li, ri)
+                for cc in range(2):
+                    out[li] = out[li] + lc[cc] * u[st[cc]]
+                    out[ri] = out[ri] + rc[cc] * u[st[cc]]
+        # ---- level jumps level -> level+1
+        for level in range(lo, hi):
+            coarse, fine = mesh.cells[level], mesh.cells[level + 1]
+            if coarse.size == 0 or fine.size == 0:
+                continue
+            h_l, h_f = cfg.cell_length(level), cfg.cell_length(level + 1)
+            fc = coeff_fn(d, h_f)  # flux computed at level+1
+            rcoarse = refine(coarse, 1, dim)
+            # orientation A: coarse on the left, fine on the right
+            lcA = tuple(hfac(h_f, h_l) * v for v in fc)
+            rcA = tuple(-hfac(h_f, h_f) * v for v in fc)
+            ghosts = inter(rcoarse, translate(fine, me))
+            for run in _runs(ghosts, dim):
+                st = (mesh.index(level + 1, run), mesh.index(level + 1, translate(run, e)))
+                right = st[1]
+                if run.size == 1 or d == 0:
+                    left = mesh.index(level, pack(unpack(run, dim) >> 1))
+                    for cc in range(2):
+                        out[left] = out[left] + lcA[cc] * u[st[cc]]
+                        out[right] = out[right] + rcA[cc] * u[st[cc]]
+                else:
+                    assert run.size % 2 == 0
+                    left = mesh.index(level, pack(unpack(run[0::2], dim) >> 1))
+                    for cc in range(2):
+                        out[left] = out[left] + (lcA[cc] * u[st[cc][0::2]] + lcA[cc] * u[st[cc][1::2]])
+                        out[right] = out[right] + rcA[cc] * u[st[cc]]
+            # orientation B: fine on the left, coarse on the right; stencil {-dir, 0} around the ghost child
+            lcB = tuple(hfac(h_f, h_f) * v for v in fc)
+            rcB = tuple(-hfac(h_f, h_l) * v for v in fc)
+            ghosts = inter(rcoarse, translate(fine, e))
+            for run in _runs(ghosts, dim):
+                st = (mesh.index(level + 1, translate(run, me)), mesh.index(level + 1, run))
+                left = st[0]
+                if run.size == 1 or d == 0:
+                    right = mesh.index(level, pack(unpack(run, dim) >> 1))
+                    for cc in range(2):
+                        out[left] = out[left] + lcB[cc] * u[st[cc]]
+                        out[right] = out[right] + rcB[cc] * u[st[cc]]
+                else:
+                    assert run.size % 2 == 0
+                    right = mesh.index(level, pack(unpack(run[0::2], dim) >> 1))
+                    for cc in range(2):
+                        out[left] = out[left] + lcB[cc] * u[st[cc]]
+                        out[right] = out[right] + (rcB[cc] * u[st[cc][0::2]] + rcB[cc] * u[st[cc][1::2]])
+        # ---- boundary interfaces: per level, direction then opposite direction
+        for level in leaf_lv:
+            cells = mesh.cells[level]
+            h = cfg.cell_length(level)
+            fc = coeff_fn(d, h)
+            f = hfac(h, h)
+            bc_ = (f * fc[0], f * fc[1])
+            bd = cells[~mesh.in_domain(level, translate(cells, e))]
+            for run in _runs(bd, dim):
+                bi = mesh.index(level, run)
+                st = (bi, mesh.index(level, translate(run, e)))
+                for cc in range(2):
+                    out[bi] = out[bi] + bc_[cc] * u[st[cc]]
+            bd = cells[~mesh.in_domain(level, translate(cells, me))]
+            for run in _runs(bd, dim):
+                bi = mesh.index(level, run)
+                st = (mesh.index(level, translate(run, me)), bi)
+                for cc in range(2):
+                    out[bi] = out[bi] + (-bc_[cc]) * u[st[cc]]
+    return out
+
+
+def burgers_upwind_flux(scale=1.0):
+    """`scale * make_convection_upwind<Field>()` for a scalar field (schemes/fv/operators/convection_nonlin.hpp:24-76;
+    scalar factor: flux_based/algebraic_operators.hpp:38-46): v = .5*(uL+uR); flux = (v >= 0 ? uL*uL : uR*uR) [* scale]."""
+    def fn(ul, ur):
+        v = 0.5 * (ul + ur)
+        f = np.where(v >= 0, ul * ul, ur * ur)
+        return f * scale if scale != 1 else f
+    return fn
+
+
+def flux_nonlin_apply(mesh: Mesh, u, flux_fn):
+    """Explicit<FluxBasedScheme<NonLinear>>::apply with finer_level_flux disabled, sequential order
+    (flux_based/explicit_flux_based_scheme__nonlin.hpp:35-85; flux_based_scheme__nonlin.hpp:334-364 interior,
+    :366-402 boundary, :407-520 level loop and factors; fluxes[1] = -fluxes[0]: flux_definition.hpp:125-136).
+    Per interface cell, in interval order: out[left] += flux*left_factor, then out[right] += (-flux)*right_factor."""
+    cfg, dim = mesh.cfg, mesh.cfg.dim
+    out = np.zeros(mesh.nref)
+    leaf_lv = mesh.leaf_levels()
+    lo = max(cfg.min_level, leaf_lv[0] - 1)
+    hi = min(cfg.max_level, leaf_lv[-1] + 1)
+
+    def hfac(h_face, h_cell):
+        return pow(h_face, dim - 1) / pow(h_cell, dim)
+
+    def scatter(run_left, run_right, st0, st1, lf, rf):
+        # sequential per-cell accumulation (several fine cells may hit the same coarse cell: np.add.at keeps order)
+        fl = flux_fn(u[st0], u[st1])
+        a = fl * lf
+        b = (-fl) * rf
+        for k in range(run_left.size):
+            out[run_left[k]] = out[run_left[k]] + a[k]
+            out[run_right[k]] = out[run_right[k]] + b[k]
+
+    for d in range(dim):
+        e = [0] * dim
+        e[d] = 1
+        me = [-v for v in e]
+        for level in range(lo, hi + 1):
+            cells = mesh.cells[level]
+            if cells.size == 0:
+                continue
+            h = cfg.cell_length(level)
+            f = hfac(h, h)
+            iface = cells[np.isin(translate(cells, e), cells)]
+            for run in _runs(iface, dim):
+                li = mesh.index(level, run)
+                ri = mesh.index(level, translate(run, e))
+                scatter(li, ri, li, ri, f, f)
+        for level in range(lo, hi):
+            coarse, fine = mesh.cells[level], mesh.cells[level + 1]
+            if coarse.size == 0 or fine.size == 0:
+                continue
+            h_l, h_f = cfg.cell_length(level), cfg.cell_length(level + 1)
+            rcoarse = refine(coarse, 1, dim)
+            ghosts = inter(rcoarse, translate(fine, me))
+            for run in _runs(ghosts, dim):
+                st0 = mesh.index(level + 1, run)
+                st1 = mesh.index(level + 1, translate(run, e))
+                left = mesh.index(level, pack(unpack(run, dim) >> 1))
+                scatter(left, st1, st0, st1, hfac(h_f, h_l), hfac(h_f, h_f))
+            ghosts = inter(rcoarse, translate(fine, e))
+            for run in _runs(ghosts, dim):
+                st0 = mesh.index(level + 1, translate(run, me))
+                st1 = mesh.index(level + 1, run)
+                right = mesh.index(level, pack(unpack(run, dim) >> 1))
+                scatter(st0, right, st0, st1, hfac(h_f, h_f), hfac(h_f, h_l))
+        for level in leaf_lv:
+            cells = mesh.cells[level]
+            h = cfg.cell_length(level)
+            f = hfac(h, h)
+            bd = cells[~mesh.in_domain(level, translate(cells, e))]
+            for run in _runs(bd, dim):
+                bi = mesh.index(level, run)
+                fl = flux_fn(u[bi], u[mesh.index(level, translate(run, e))])
+                out[bi] = out[bi] + fl * f
+            bd = cells[~mesh.in_domain(level, translate(cells, me))]
+            for run in _runs(bd, dim):
+                bi = mesh.index(level, run)
+                fl = flux_fn(u[mesh.index(level, translate(run, me))], u[bi])
+                out[bi] = out[bi] + (-fl) * f  # flux_values[1] *= -(-factor)
+    return out
+
+
+def lincomb_leaves(mesh: Mesh, a, x, b, y):
+    """`unp1 = a*x + b*y` over the leaves (field expression, field_base.hpp:230-242); other entries NaN."""
+    out = np.full(mesh.nref, np.nan)
+    for l in mesh.leaf_levels():
+        i = mesh.index(l, mesh.cells[l])
+        out[i] = a * x[i] + b * y[i] if a != 1.0 else x[i] + b * y[i]
     return out
 
 
@@ -942,6 +1085,52 @@ def run_advection(cfg: MeshConfig, Tf, eps=2e-4, regularity=1.0, a=None, cfl=0.5
             t = Tf
         update_ghost_mr(mesh, u, bc)
         u = fv_step(mesh, u, a, dt)
+        nt += 1
+        if on_step is not None:
+            on_step(nt, mesh, u)
+        if max_steps is not None and nt >= max_steps:
+            break
+    return dict(init=init_state, final=(mesh, u), steps=nt)
+
+
+def heat_exact(x, t, K=1.0):
+    """demos/FiniteVolume/heat.cpp:14-24."""
+    r = np.ones(x.shape[0])
+    for d in range(x.shape[1]):
+        r = r * (1 / (2 * math.sqrt(math.pi * K * t)) * np.exp(-x[:, d] * x[:, d] / (4 * K * t)))
+    return r
+
+
+def run_heat(cfg: MeshConfig, Tf=0.1, K=1.0, cfl=0.95, eps=1e-4, regularity=1.0, max_steps=None, on_step=None):
+    """demos/FiniteVolume/heat.cpp:112-236 with --explicit --init-sol=dirac: u0 = exact(t0 = 1e-2), Neumann(0),
+    dt = cfl dx^2 / (2^dim K), per step MRadaptation then unp1 = u - dt * diff(u) (diff = make_diffusion_order2)."""
+    dim = cfg.dim
+    bc = Bc("neumann", 0.0)
+    mesh = Mesh.uniform(cfg)
+    t = 1e-2
+    u = np.zeros(mesh.nref)
+    L = cfg.max_level
+    u[mesh.index(L, mesh.cells[L])] = heat_exact(mesh.cell_centers(L, mesh.cells[L]), t, K)
+    dx = cfg.cell_length(L)
+    dt = cfl * (dx * dx) / (pow(2, dim) * K)
+    coeffs = diffusion_order2_coeffs([K] * dim)
+    mesh, u = adapt(mesh, u, bc, eps, regularity)
+    init_state = (mesh, u.copy())
+    nt = 0
+    while t != Tf:
+        t += dt
+        if t > Tf:
+            dt += Tf - t
+            t = Tf
+        mesh, u = adapt(mesh, u, bc, eps, regularity)
+        update_ghost_mr(mesh, u, bc)
+        rhs = flux_linhom_apply(mesh, u, coeffs)
+        # unp1 = u - dt * diff(u)  (xtensor: dt * rhs evaluated per element, then subtracted)
+        unp1 = np.full(mesh.nref, np.nan)
+        for l in mesh.leaf_levels():
+            i = mesh.index(l, mesh.cells[l])
+            unp1[i] = u[i] - dt * rhs[i]
+        u = unp1
         nt += 1
         if on_step is not None:
             on_step(nt, mesh, u)

@@ -24,3 +24,16 @@ if __name__ == "__main__":
         out = os.path.join(HERE, "advection_2d_" + name + ".npz")
         np.savez_compressed(out, level=level.astype(np.int8), idx=idx.astype(np.int32), u=fields["u"])
         print(out, len(level), os.path.getsize(out))
+    # heat.cpp --explicit --init-sol=dirac --Tf=0.1 --min-level=3 --max-level=6 on [-4, 4]^2 (tests/test_demo_finite_volume.py:99-116):
+    # flux-based diffusion (make_diffusion_order2) across level jumps, Neumann(0), MR adaptation every step
+    h5 = h5mini.H5File(REF + "test_finite_volume_demo_heat_explicit.h5")
+    pts = h5.read("/mesh/points")
+    conn = h5.read("/mesh/connectivity").reshape(-1, 4).astype(np.int64)
+    lo = pts[conn].min(axis=1)[:, :2]
+    level = h5.read("/mesh/fields/level").astype(np.int64)
+    length = 8.0 / (1 << level)
+    idx = np.rint((lo + 4.0) / length[:, None]).astype(np.int64)
+    assert np.allclose(pts[conn].max(axis=1)[:, 0] - lo[:, 0], length)
+    out = os.path.join(HERE, "heat_explicit.npz")
+    np.savez_compressed(out, level=level.astype(np.int8), idx=idx.astype(np.int32), u=h5.read("/mesh/fields/u"))
+    print(out, len(level), os.path.getsize(out))

@@ -81,3 +81,39 @@ def test_upwind_constant_and_linear():
     leaves = mesh.index(5, mesh.cells[5])
     # unp1 = u - dt * (a . grad u) = u - (2*1 - 3*0.5)
     assert np.max(np.abs(out[leaves] - (u[leaves] - 0.5))) < 1e-11
+
+
+def test_oracle_matches_reference_heat_golden():
+    """Pins the flux-based path (a8/a10: make_diffusion_order2 across level jumps, Neumann(0), adaptation every step)
+    on the reference's own golden: demos/FiniteVolume/heat.cpp --explicit --init-sol=dirac --Tf=0.1 --min-level=3
+    --max-level=6 (tests/test_demo_finite_volume.py:99-116) -> test_finite_volume_demo_heat_explicit.h5."""
+    cfg = so.MeshConfig(dim=2, min_level=3, max_level=6, pred_radius=1, origin=(-4.0, -4.0), scaling=8.0)
+    res = so.run_heat(cfg)
+    assert res["steps"] == 25
+    mesh, u = res["final"]
+    g = np.load(os.path.join(GOLD, "heat_explicit.npz"))
+    lv, co, ix = mesh.leaf_table()
+    assert np.array_equal(lv, g["level"].astype(np.int64)) and np.array_equal(co, g["idx"].astype(np.int64)), "mesh not identical"
+    assert np.max(np.abs(u[ix] - g["u"])) <= 1e-15  # observed 2.2e-19 (max |u| = 0.77)
+
+
+@pytest.mark.parametrize("dim,lo,hi", [(1, 2, 6), (2, 2, 6), (3, 2, 5)])
+def test_flux_schemes_on_adapted_meshes(dim, lo, hi):
+    """reference tests/test_fv_operators.cpp:953-1128 (two-level mesh): every flux operator returns 0 on a constant field
+    including across level jumps; the conservative form telescopes (sum of h^dim * out = boundary fluxes only)."""
+    cfg = so.MeshConfig(dim=dim, min_level=lo, max_level=hi, pred_radius=1)
+    mesh = so.Mesh.uniform(cfg)
+    bc = so.Bc("dirichlet", 0.0)
+    mesh, u = so.adapt(mesh, so.init_disc(mesh, [0.3] * dim, 0.2), bc, eps=2e-4)
+    assert len(mesh.leaf_levels()) > 1
+    const = np.full(mesh.nref, 1.5)
+    leaves = np.concatenate([mesh.index(l, mesh.cells[l]) for l in mesh.leaf_levels()])
+    vol = np.concatenate([np.full(mesh.cells[l].size, cfg.cell_length(l) ** dim) for l in mesh.leaf_levels()])
+    so.update_ghost_mr(mesh, u, bc)
+    for out in (so.flux_linhom_apply(mesh, const, so.convection_upwind_coeffs([1.0, -0.5, 0.25][:dim])),
+                so.flux_linhom_apply(mesh, const, so.diffusion_order2_coeffs([1.0, 2.0, 0.5][:dim]))):
+        assert np.max(np.abs(out[leaves])) == 0.0
+    # the disc does not touch the boundary: u = 0 there, so all boundary fluxes vanish and the interior telescopes
+    for out in (so.flux_linhom_apply(mesh, u, so.diffusion_order2_coeffs([1.0] * dim)),
+                so.flux_nonlin_apply(mesh, u, so.burgers_upwind_flux(0.5))):
+        assert abs(np.sum(out[leaves] * vol)) < 1e-12 * max(1.0, np.max(np.abs(out[leaves])))
