@@ -118,17 +118,21 @@ extern "C"
     /* unp1 = u - dt * upwind_scalar_burgers(k, u)  (stencil_field.hpp:184-249) */
     int smr_fv_upwind_burgers(smr_field_t unp1, smr_field_t u, const double* k, double dt);
 
-    /* flux-based linear homogeneous schemes, explicit application: out = S(u) with out.fill(0) first
-     * (schemes/fv/FV_scheme.hpp:202-238, flux_based/explicit_flux_based_scheme__lin_hom.hpp:233-319).  Ghosts of `u` are
-     * updated first if needed (update_ghost_mr_if_needed).  Uniform-level meshes only for now: a mesh with a level jump is
-     * rejected with SMR_ERR_INVALID rather than approximated. */
+    /* flux-based schemes, explicit application: out = S(u) with out.fill(0) first (schemes/fv/FV_scheme.hpp:202-238;
+     * linear homogeneous: flux_based/explicit_flux_based_scheme__lin_hom.hpp:39-119,233-319 + flux_based_scheme__lin_hom.hpp:74-229;
+     * non-linear: explicit_flux_based_scheme__nonlin.hpp:35-85 + flux_based_scheme__nonlin.hpp:334-520; interfaces incl.
+     * level jumps and boundaries: interface.hpp:35-306,440-509).  Ghosts of `u` are updated first if needed
+     * (update_ghost_mr_if_needed).  `scale` is the scalar of `scale * scheme` (flux_based/algebraic_operators.hpp:7-82), 1 for none.
+     * Every cell accumulates its contributions in the order of the reference's sequential scatter loops. */
     enum
     {
         SMR_SCHEME_CONVECTION_UPWIND = 0, /* make_convection_upwind<Field>(velocity), operators/convection_lin.hpp:15-89; params = velocity[dim] */
-        SMR_SCHEME_DIFFUSION_ORDER2  = 1  /* make_diffusion_order2<Field>(K),         operators/diffusion.hpp:123-175;     params = K[dim]        */
+        SMR_SCHEME_DIFFUSION_ORDER2  = 1, /* make_diffusion_order2<Field>(K),         operators/diffusion.hpp:123-175;     params = K[dim]        */
+        SMR_SCHEME_CONVECTION_UPWIND_NONLINEAR = 2 /* make_convection_upwind<Field>() on a scalar field (Burgers, flux u*u upwinded by the
+                                                      mean velocity), operators/convection_nonlin.hpp:24-76; params unused */
     };
 
-    int smr_scheme_apply(smr_field_t out, smr_field_t u, int kind, const double* params);
+    int smr_scheme_apply(smr_field_t out, smr_field_t u, int kind, const double* params, double scale);
     /* out = a * x + b * y over the leaves: the field-expression tail `unp1 = u - dt * scheme(u)` is (1, u, -dt, rhs) */
     int smr_field_lincomb(smr_field_t out, double a, smr_field_t x, double b, smr_field_t y);
 

@@ -89,7 +89,7 @@ SYMBOLS = {
     "smr_update_ghost_mr": [_u64],
     "smr_fv_upwind": [_u64, _u64, _vp, _dbl],
     "smr_fv_upwind_burgers": [_u64, _u64, _vp, _dbl],
-    "smr_scheme_apply": [_u64, _u64, _i32, _vp],
+    "smr_scheme_apply": [_u64, _u64, _i32, _vp, _dbl],
     "smr_field_lincomb": [_u64, _dbl, _u64, _dbl, _u64],
     "smr_adapt": [_vp, _i32, _dbl, _dbl, _P(_i32)],
     "smr_adapt_ex": [_vp, _i32, _dbl, _dbl, _i32, _P(_i32)],
@@ -473,17 +473,21 @@ def upwind_scalar_burgers_step(unp1: ScalarField, u: ScalarField, k, dt):
     _check(load_library().smr_fv_upwind_burgers(unp1._h, u._h, k.ctypes.data, float(dt)))
 
 
-CONVECTION_UPWIND, DIFFUSION_ORDER2 = 0, 1
+CONVECTION_UPWIND, DIFFUSION_ORDER2, CONVECTION_UPWIND_NONLINEAR = 0, 1, 2
 
 
 class FluxScheme:
-    """A flux-based linear homogeneous scheme object: `rhs = scheme(u)` / `scheme.apply(out, u)` (schemes/fv/FV_scheme.hpp:202-238)."""
+    """A flux-based scheme object: `rhs = scheme(u)` / `scheme.apply(out, u)` (schemes/fv/FV_scheme.hpp:202-238);
+    `scalar * scheme` scales the flux (flux_based/algebraic_operators.hpp:7-82)."""
 
-    def __init__(self, kind, params, name):
-        self.kind, self.params, self.name = kind, np.ascontiguousarray(params, dtype=np.float64), name
+    def __init__(self, kind, params, name, scale=1.0):
+        self.kind, self.params, self.name, self.scale = kind, np.ascontiguousarray(params, dtype=np.float64), name, float(scale)
 
     def apply(self, out: ScalarField, u: ScalarField):
-        _check(load_library().smr_scheme_apply(out._h, u._h, self.kind, self.params.ctypes.data))
+        _check(load_library().smr_scheme_apply(out._h, u._h, self.kind, self.params.ctypes.data, self.scale))
+
+    def __rmul__(self, scalar):
+        return FluxScheme(self.kind, self.params, f"{scalar} * {self.name}", self.scale * float(scalar))
 
     def __call__(self, u: ScalarField):
         out = ScalarField(f"{self.name}({u.name})", u.mesh)
@@ -491,8 +495,11 @@ class FluxScheme:
         return out
 
 
-def make_convection_upwind(velocity):
-    """samurai::make_convection_upwind<Field>(velocity) (schemes/fv/operators/convection_lin.hpp:15-89)."""
+def make_convection_upwind(velocity=None):
+    """samurai::make_convection_upwind<Field>(velocity) (schemes/fv/operators/convection_lin.hpp:15-89); without a velocity
+    the non-linear Burgers form make_convection_upwind<Field>() (operators/convection_nonlin.hpp:24-76, scalar fields)."""
+    if velocity is None:
+        return FluxScheme(CONVECTION_UPWIND_NONLINEAR, [0.0, 0.0, 0.0], "convection(u)")
     return FluxScheme(CONVECTION_UPWIND, velocity, "convection")
 
 

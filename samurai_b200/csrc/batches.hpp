@@ -654,6 +654,298 @@ namespace smr
     }
 
     // coarse set `cs` at level lc (dst offsets from dst_ref) <- children rows in src_ref (level lc+1)
+    // ---------------------------------------------------------------------------------------------------------
+    // flux-based schemes on multi-level meshes: the reference enumerates interfaces (interface.hpp:35-306, 440-509) and
+    // scatters both sides' contributions; here every leaf gathers its own contributions, so the host classifies what
+    // lies across each face of each leaf (same-level leaf / coarser leaf / finer leaves / boundary) and cuts the leaf
+    // intervals where a transverse classification changes.
+    // ---------------------------------------------------------------------------------------------------------
+    inline void flux_items(const Mesh& m, int l, const PlanFilter& flt, std::vector<smr_item_flux>& out, std::vector<int64_t>& aux)
+    {
+        const int dim        = m.cfg.dim;
+        const LevelSet& c    = m.cells[l];
+        const LevelSet& ref  = m.ref[l];
+        const LevelSet* cc   = l > 0 ? &m.cells[l - 1] : nullptr;
+        const LevelSet* cf   = l + 1 < m.nlev ? &m.cells[l + 1] : nullptr;
+        const LevelSet* rf   = l + 1 < m.nlev ? &m.ref[l + 1] : nullptr;
+        const int nfaces     = 2 * dim;
+        int nl[3];
+        for (int d = 0; d < 3; ++d)
+        {
+            nl[d] = m.cfg.n0[d] << l;
+        }
+        struct Seg
+        {
+            int a, b, kind;
+        };
+        std::vector<Seg> segs[6];
+        std::vector<int> cuts;
+        auto has = [](const LevelSet* s, int y, int z, int x)
+        {
+            return s != nullptr && s->contains(mk_key(y, z), x);
+        };
+        out.reserve(out.size() + c.n_intervals());
+        for (size_t r = 0; r < c.rows(); ++r)
+        {
+            const int y = key_y(c.key[r]), z = key_z(c.key[r]);
+            if (!flt.owns(l, y, z))
+            {
+                continue;
+            }
+            const int mask = static_cast<int>(flt.mask(l, y, z));
+            const int py = dim > 1 ? (y >> 1) : 0, pz = dim > 2 ? (z >> 1) : 0; // parent row
+            auto cy_ = [&](int a) { return dim > 1 ? 2 * y + a : 0; };             // child rows
+            auto cz_ = [&](int a) { return dim > 2 ? 2 * z + a : 0; };
+            for (int q = c.ptr[r]; q < c.ptr[r + 1]; ++q)
+            {
+                const int s = c.xs[q], e = c.xe[q];
+                cuts.clear();
+                cuts.push_back(s);
+                cuts.push_back(e);
+                for (int f = 2; f < nfaces; ++f)
+                {
+                    segs[f].clear();
+                    const int d = f >> 1, sgn = (f & 1) ? 1 : -1;
+                    const int yy = y + (d == 1 ? sgn : 0), zz = z + (d == 2 ? sgn : 0);
+                    const int j = d == 1 ? yy : zz;
+                    if (j < 0 || j >= nl[d])
+                    {
+                        segs[f].push_back({s, e, SMR_FACE_BDRY});
+                        continue;
+                    }
+                    const int rS = c.find_row(mk_key(yy, zz));
+                    const int rC = cc ? cc->find_row(mk_key(yy >> 1, dim > 2 ? (zz >> 1) : 0)) : -1;
+                    // the child row of the neighbour position that touches this leaf
+                    const int fy = d == 1 ? 2 * yy + (sgn < 0 ? 1 : 0) : 2 * yy;
+                    const int fz = dim > 2 ? (d == 2 ? 2 * zz + (sgn < 0 ? 1 : 0) : 2 * zz) : 0;
+                    const int rF = cf ? cf->find_row(mk_key(fy, fz)) : -1;
+                    int pos = s;
+                    while (pos < e)
+                    {
+                        int i, end, kind;
+                        if (rS >= 0 && (i = c.find_ivl(rS, pos)) >= 0)
+                        {
+                            end  = std::min(e, c.xe[i]);
+                            kind = SMR_FACE_SAME;
+                        }
+                        else if (rC >= 0 && (i = cc->find_ivl(rC, pos >> 1)) >= 0)
+                        {
+                            end  = std::min(e, 2 * cc->xe[i]);
+                            kind = SMR_FACE_COARSE;
+                        }
+                        else if (rF >= 0 && (i = cf->find_ivl(rF, 2 * pos)) >= 0)
+                        {
+                            end  = std::min(e, (cf->xe[i] + 1) >> 1);
+                            kind = SMR_FACE_FINE;
+                        }
+                        else
+                        {
+                            missing("flux: neighbour leaf", l, pos, yy, zz);
+                        }
+                        segs[f].push_back({pos, end, kind});
+                        cuts.push_back(end);
+                        pos = end;
+                    }
+                }
+                std::sort(cuts.begin(), cuts.end());
+                cuts.erase(std::unique(cuts.begin(), cuts.end()), cuts.end());
+                size_t cur[6] = {0, 0, 0, 0, 0, 0};
+                for (size_t ci = 0; ci + 1 < cuts.size(); ++ci)
+                {
+                    const int a = cuts[ci], b = cuts[ci + 1];
+                    int kinds  = 0;
+                    bool any_fine = false;
+                    // x faces
+                    int kx[2];
+                    if (a > s)
+                    {
+                        kx[0] = SMR_FACE_SAME;
+                    }
+                    else if (a == 0)
+                    {
+                        kx[0] = SMR_FACE_BDRY;
+                    }
+                    else if (has(cc, py, pz, (a - 1) >> 1))
+                    {
+                        kx[0] = SMR_FACE_COARSE;
+                    }
+                    else if (has(cf, cy_(0), cz_(0), 2 * a - 1))
+                    {
+                        kx[0] = SMR_FACE_FINE;
+                    }
+                    else
+                    {
+                        missing("flux: x- neighbour leaf", l, a - 1, y, z);
+                    }
+                    if (b < e)
+                    {
+                        kx[1] = SMR_FACE_SAME;
+                    }
+                    else if (b == nl[0])
+                    {
+                        kx[1] = SMR_FACE_BDRY;
+                    }
+                    else if (has(cc, py, pz, b >> 1))
+                    {
+                        kx[1] = SMR_FACE_COARSE;
+                    }
+                    else if (has(cf, cy_(0), cz_(0), 2 * b))
+                    {
+                        kx[1] = SMR_FACE_FINE;
+                    }
+                    else
+                    {
+                        missing("flux: x+ neighbour leaf", l, b, y, z);
+                    }
+                    kinds |= kx[0] | (kx[1] << 2);
+                    any_fine = kx[0] == SMR_FACE_FINE || kx[1] == SMR_FACE_FINE;
+                    for (int f = 2; f < nfaces; ++f)
+                    {
+                        while (segs[f][cur[f]].b <= a)
+                        {
+                            ++cur[f];
+                        }
+                        const int kind = segs[f][cur[f]].kind;
+                        kinds |= kind << (2 * f);
+                        any_fine = any_fine || kind == SMR_FACE_FINE;
+                    }
+                    smr_item_flux it;
+                    it.c = ref.offset_of(c.key[r], a - 1, b);
+                    if (it.c < 0)
+                    {
+                        missing("flux x", l, a - 1, y, z);
+                    }
+                    it.c += 1;
+                    for (int k = 0; k < 4; ++k)
+                    {
+                        it.nb[k] = it.c;
+                    }
+                    for (int f = 2; f < nfaces; ++f)
+                    {
+                        const int d = f >> 1, sgn = (f & 1) ? 1 : -1;
+                        it.nb[f - 2] = need(ref, "flux transverse row", l, y + (d == 1 ? sgn : 0), z + (d == 2 ? sgn : 0), a, b - 1);
+                    }
+                    it.fine = 0;
+                    if (any_fine)
+                    {
+                        it.fine = static_cast<int64_t>(aux.size());
+                        aux.resize(aux.size() + SMR_FLUX_AUX_SLOTS, 0);
+                        int64_t* fx = aux.data() + it.fine;
+                        const int nr = 1 << (dim - 1);
+                        for (int side = 0; side < 2; ++side)
+                        {
+                            if (kx[side] == SMR_FACE_FINE)
+                            {
+                                // stencil cells at level+1: x-: {fine 2a-1, ghost 2a}; x+: {ghost 2b-1, fine 2b}
+                                const int x0 = side == 0 ? 2 * a - 1 : 2 * b - 1;
+                                for (int rr = 0; rr < nr; ++rr)
+                                {
+                                    fx[side * 4 + rr] = need(*rf, "flux fine x rows", l + 1, cy_(rr & 1), cz_(rr >> 1), x0, x0 + 1);
+                                }
+                            }
+                        }
+                        for (int f = 2; f < nfaces; ++f)
+                        {
+                            if (((kinds >> (2 * f)) & 3) != SMR_FACE_FINE)
+                            {
+                                continue;
+                            }
+                            const int d = f >> 1, sgn = (f & 1) ? 1 : -1;
+                            const int base = d == 1 ? 2 * y : 2 * z;
+                            const int fine_row  = sgn < 0 ? base - 1 : base + 2;
+                            const int ghost_row = sgn < 0 ? base : base + 1;
+                            const int st_row[2] = {sgn < 0 ? fine_row : ghost_row, sgn < 0 ? ghost_row : fine_row};
+                            const int nb_other  = dim > 2 ? 2 : 1;
+                            for (int bb = 0; bb < nb_other; ++bb)
+                            {
+                                for (int st = 0; st < 2; ++st)
+                                {
+                                    const int ry = d == 1 ? st_row[st] : cy_(bb);
+                                    const int rz = d == 2 ? st_row[st] : cz_(bb);
+                                    fx[f * 4 + 2 * bb + st] = need(*rf, "flux fine transverse rows", l + 1, ry, rz, 2 * a, 2 * b - 1);
+                                }
+                            }
+                        }
+                    }
+                    it.n     = b - a;
+                    it.level = l;
+                    it.kinds = kinds;
+                    it.mask  = mask;
+                    out.push_back(it);
+                }
+            }
+        }
+    }
+
+    // batches for the flux-based schemes on multi-level meshes, built on first use for a mesh (flux schemes only)
+    struct FluxPlan
+    {
+        Arena arena;
+        Batch items;
+        bool ready = false;
+    };
+
+    inline void build_flux_plan(const Mesh& m, FluxPlan& plan, const PlanFilter& flt = PlanFilter())
+    {
+        const int nlev = m.nlev;
+        std::vector<std::vector<smr_item_flux>> items(nlev);
+        std::vector<std::vector<int64_t>> aux(nlev);
+        std::string error;
+#pragma omp parallel for schedule(dynamic, 1)
+        for (int l = nlev - 1; l >= 0; --l)
+        {
+            try
+            {
+                if (!m.cells[l].empty())
+                {
+                    flux_items(m, l, flt, items[l], aux[l]);
+                }
+            }
+            catch (const std::exception& e)
+            {
+#pragma omp critical
+                error = e.what();
+            }
+        }
+        if (!error.empty())
+        {
+            throw std::out_of_range(error);
+        }
+        // per-level aux indices -> indices into the concatenated aux array
+        int64_t base = 0;
+        for (int l = 0; l < nlev; ++l)
+        {
+            if (base != 0)
+            {
+                for (smr_item_flux& it : items[l])
+                {
+                    it.fine += base;
+                }
+            }
+            base += static_cast<int64_t>(aux[l].size());
+        }
+        plan.arena.clear();
+        Pending<smr_item_flux> pd{&plan.items, B_FV, -1, {}, nullptr, false};
+        for (int l = 0; l < nlev; ++l)
+        {
+            pd.parts.push_back(&items[l]);
+        }
+        layout_batch(pd, plan.arena);
+        plan.items.aux = static_cast<int64_t>(plan.arena.take(static_cast<size_t>(std::max<int64_t>(base, 1)) * sizeof(int64_t)));
+        plan.arena.commit();
+        fill_batch(pd, plan.arena);
+        int64_t* dst = reinterpret_cast<int64_t*>(plan.arena.p + plan.items.aux);
+        for (int l = 0; l < nlev; ++l)
+        {
+            if (!aux[l].empty())
+            {
+                std::memcpy(dst, aux[l].data(), aux[l].size() * sizeof(int64_t));
+                dst += aux[l].size();
+            }
+        }
+        plan.ready = true;
+    }
+
     inline void proj_items(int dim, const LevelSet& cs, int lc, const LevelSet& dst_ref, const LevelSet& src_ref, const PlanFilter& flt, std::vector<smr_item_proj>& out)
     {
         Probe pd(dst_ref);

@@ -187,6 +187,14 @@ namespace smr
         MeshPlan plan;
         bool plan_ready = false;
         DevBuf d_arena;
+        FluxPlan flux; // flux-based schemes on multi-level meshes, built on first use
+        DevBuf d_flux, d_fluxtab;
+
+        void invalidate_plans()
+        {
+            plan_ready = false;
+            flux.ready = false;
+        }
         DevBuf d_detail, d_tag, d_relmax;
         PlanFilter filter; // multi-GPU slab ownership for this mesh (identity when world == 1)
 
@@ -889,8 +897,55 @@ namespace smr
             fields[i]->ghosts_valid = false;
         }
         mo.mesh       = std::move(*new_mesh);
-        mo.plan_ready = false;
+        mo.invalidate_plans();
         return false;
+    }
+
+    // flux coefficients {left, right} of direction d for cells of size h
+    static void scheme_coeffs(int kind, const double* params, double scale, int d, double h, double fc[2])
+    {
+        if (kind == SMR_SCHEME_CONVECTION_UPWIND) // operators/convection_lin.hpp:31-72
+        {
+            const double v = params[d];
+            fc[0]          = v >= 0 ? v : 0.0;
+            fc[1]          = v >= 0 ? 0.0 : v;
+        }
+        else // operators/diffusion.hpp:143-170
+        {
+            fc[0] = -1 / h;
+            fc[1] = 1 / h;
+            fc[0] *= -params[d];
+            fc[1] *= -params[d];
+        }
+        if (scale != 1) // scalar * scheme: flux_based/algebraic_operators.hpp:20-28
+        {
+            fc[0] *= scale;
+            fc[1] *= scale;
+        }
+    }
+
+    static double h_factor(int dim, double h_face, double h_cell) // flux_based_scheme__lin_hom.hpp:62-67
+    {
+        return std::pow(h_face, dim - 1) / std::pow(h_cell, dim);
+    }
+
+    template <int NONLIN>
+    static void launch_flux_general(int dim, MeshObj& mo, const double* u, double* o, double scale)
+    {
+        const int64_t* aux = reinterpret_cast<const int64_t*>(static_cast<const char*>(mo.d_flux.p) + mo.flux.items.aux);
+        const double* tab  = static_cast<const double*>(mo.d_fluxtab.p);
+        switch (dim)
+        {
+            case 1:
+                launch<smr_item_flux>(SMR_FAM_FV, mo.d_flux.p, mo.flux.items, FluxGenOp<1, NONLIN>{u, o, aux, tab, scale});
+                break;
+            case 2:
+                launch<smr_item_flux>(SMR_FAM_FV, mo.d_flux.p, mo.flux.items, FluxGenOp<2, NONLIN>{u, o, aux, tab, scale});
+                break;
+            default:
+                launch<smr_item_flux>(SMR_FAM_FV, mo.d_flux.p, mo.flux.items, FluxGenOp<3, NONLIN>{u, o, aux, tab, scale});
+                break;
+        }
     }
 
     template <class F>
@@ -1392,7 +1447,7 @@ extern "C"
             });
     }
 
-    int smr_scheme_apply(smr_field_t outh, smr_field_t inh, int kind, const double* params)
+    int smr_scheme_apply(smr_field_t outh, smr_field_t inh, int kind, const double* params, double scale)
     {
         return guarded(
             [&]
@@ -1407,22 +1462,28 @@ extern "C"
                 MeshObj& mo = *in.mesh;
                 check_field_ready(in);
                 const MeshConfig& cfg = mo.mesh.cfg;
-                const int level       = mo.mesh.min_leaf_level();
-                if (level != mo.mesh.max_leaf_level())
-                {
-                    throw std::invalid_argument("flux-based schemes are implemented for uniform-level meshes only (level jumps: next round)");
-                }
-                if (kind != SMR_SCHEME_CONVECTION_UPWIND && kind != SMR_SCHEME_DIFFUSION_ORDER2)
+                if (kind != SMR_SCHEME_CONVECTION_UPWIND && kind != SMR_SCHEME_DIFFUSION_ORDER2 && kind != SMR_SCHEME_CONVECTION_UPWIND_NONLINEAR)
                 {
                     throw std::invalid_argument("unknown scheme kind");
                 }
+                const bool nonlin = kind == SMR_SCHEME_CONVECTION_UPWIND_NONLINEAR;
+                static const bool force_general = std::getenv("SMR_FLUX_GENERAL") != nullptr;
+                const int level    = mo.mesh.min_leaf_level();
+                const bool general = nonlin || force_general || level != mo.mesh.max_leaf_level();
                 // update_ghosts_if_needed (schemes/fv/FV_scheme.hpp:187-197)
+                ensure_plan(mo);
                 if (!in.ghosts_valid)
                 {
-                    ensure_plan(mo);
                     do_update_ghost(in);
                 }
-                ensure_plan(mo);
+                if (general && !mo.flux.ready)
+                {
+                    const double t0 = now();
+                    build_flux_plan(mo.mesh, mo.flux, mo.filter);
+                    g.stats.host_batch_seconds += now() - t0;
+                    SMR_CUDA(cudaStreamSynchronize(g.stream));
+                    upload_arena(mo.flux.arena, mo.d_flux);
+                }
                 if (static_cast<size_t>(mo.mesh.nref) * sizeof(double) > out.data.cap)
                 {
                     SMR_CUDA(cudaStreamSynchronize(g.stream));
@@ -1434,34 +1495,61 @@ extern "C"
                 mg_barrier();
                 SMR_CUDA(cudaMemsetAsync(out.data.p, 0, static_cast<size_t>(out.n) * sizeof(double), g.stream)); // output.fill(0)
                 mg_barrier();
-                FluxParams p;
-                const double h      = cfg.cell_length(level);
-                const double factor = std::pow(h, cfg.dim - 1) / std::pow(h, cfg.dim); // h_factor, lin_hom.hpp:62-67
-                for (int d = 0; d < 3; ++d)
-                {
-                    double left = 0, right = 0;
-                    if (d < cfg.dim)
-                    {
-                        if (kind == SMR_SCHEME_CONVECTION_UPWIND) // operators/convection_lin.hpp:31-72
-                        {
-                            const double v = params[d];
-                            left           = v >= 0 ? v : 0.0;
-                            right          = v >= 0 ? 0.0 : v;
-                        }
-                        else // operators/diffusion.hpp:143-170
-                        {
-                            left  = -1 / h;
-                            right = 1 / h;
-                            left *= -params[d];
-                            right *= -params[d];
-                        }
-                    }
-                    p.lc[d][0] = factor * left;
-                    p.lc[d][1] = factor * right;
-                    p.n[d]     = cfg.n0[d] << level;
-                }
                 const double* u = static_cast<const double*>(in.data.p);
                 double* o       = static_cast<double*>(out.data.p);
+                if (general)
+                {
+                    // coefficient tables per level (flux_based_scheme__lin_hom.hpp:94-165, __nonlin.hpp:434-505)
+                    static thread_local std::vector<double> tab;
+                    tab.assign(2 * SMR_MAX_LEVELS * 6, 0.0);
+                    for (int l = 0; l <= cfg.max_level && l < SMR_MAX_LEVELS; ++l)
+                    {
+                        const double h = cfg.cell_length(l), hf = cfg.cell_length(l + 1);
+                        double* cs     = tab.data() + l * 6;
+                        double* cj     = tab.data() + (SMR_MAX_LEVELS + l) * 6;
+                        if (nonlin)
+                        {
+                            cs[0] = h_factor(cfg.dim, h, h);
+                            cj[0] = h_factor(cfg.dim, hf, h);
+                            continue;
+                        }
+                        for (int d = 0; d < cfg.dim; ++d)
+                        {
+                            double fc[2];
+                            scheme_coeffs(kind, params, scale, d, h, fc);
+                            cs[2 * d]     = h_factor(cfg.dim, h, h) * fc[0];
+                            cs[2 * d + 1] = h_factor(cfg.dim, h, h) * fc[1];
+                            scheme_coeffs(kind, params, scale, d, hf, fc); // flux computed at level + 1
+                            cj[2 * d]     = h_factor(cfg.dim, hf, h) * fc[0];
+                            cj[2 * d + 1] = h_factor(cfg.dim, hf, h) * fc[1];
+                        }
+                    }
+                    mo.d_fluxtab.ensure(tab.size() * sizeof(double));
+                    SMR_CUDA(cudaMemcpyAsync(mo.d_fluxtab.p, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+                    if (nonlin)
+                    {
+                        launch_flux_general<1>(cfg.dim, mo, u, o, scale);
+                    }
+                    else
+                    {
+                        launch_flux_general<0>(cfg.dim, mo, u, o, scale);
+                    }
+                    return;
+                }
+                FluxParams p;
+                const double h      = cfg.cell_length(level);
+                const double factor = h_factor(cfg.dim, h, h);
+                for (int d = 0; d < 3; ++d)
+                {
+                    double fc[2] = {0, 0};
+                    if (d < cfg.dim)
+                    {
+                        scheme_coeffs(kind, params, scale, d, h, fc);
+                    }
+                    p.lc[d][0] = factor * fc[0];
+                    p.lc[d][1] = factor * fc[1];
+                    p.n[d]     = cfg.n0[d] << level;
+                }
                 if (cfg.dim > 1)
                 {
                     if (g.profile)
@@ -1591,7 +1679,7 @@ extern "C"
                     nm.generation = mo.mesh.generation;
                     nm.init_from_cells(mo.mesh.cfg, std::move(ca));
                     mo.mesh       = std::move(nm);
-                    mo.plan_ready = false;
+                    mo.invalidate_plans();
                     ++g.stats.mesh_rebuilds;
                 }
                 g.stats.host_mesh_seconds += now() - t0;
@@ -1732,7 +1820,7 @@ extern "C"
                 mo.filter.rank  = g.mg_rank;
                 mo.filter.world = g.mg_world;
                 mo.filter.compute_cuts(mo.mesh);
-                mo.plan_ready = false;
+                mo.invalidate_plans();
             });
     }
 

@@ -62,6 +62,30 @@ typedef struct
     int32_t x, y, z; /* coordinates of the first cell of the first row */
 } smr_item_fvstrip;
 
+/* leaf sub-interval for the flux-based schemes on multi-level meshes (schemes/fv/flux_based/, interface.hpp): all cells
+ * of the record see the same kind of neighbour across each transverse face; the x faces only matter for the first
+ * (x-) and last (x+) cell, interior x faces are same-level by construction */
+enum
+{
+    SMR_FACE_SAME   = 0, /* same-level leaf                      interface.hpp:35-110  */
+    SMR_FACE_COARSE = 1, /* coarser leaf: this cell is the fine side of a jump, the stencil uses the ghost at its own level */
+    SMR_FACE_FINE   = 2, /* finer leaves: this cell is the coarse side, contributions come from level+1 rows (aux offsets) */
+    SMR_FACE_BDRY   = 3  /* domain boundary                      boundary.hpp:6-33     */
+};
+#define SMR_FLUX_AUX_SLOTS 24 /* 6 faces x 4 level+1 row offsets */
+typedef struct
+{
+    int64_t c;     /* offset of the first cell in its own row */
+    int64_t nb[4]; /* same x in rows y-1, y+1, z-1, z+1 of the cell's own level */
+    int64_t fine;  /* first of this record's SMR_FLUX_AUX_SLOTS entries in the batch's aux array (only if a face is FINE):
+                      x faces: [face*4 + cy + 2*cz] = offset of stencil cell 0 in child row (2y+cy, 2z+cz);
+                      y/z faces: [face*4 + 2*b + st] = offset of x = 2*start in stencil row st of the b-th child row */
+    int32_t n;
+    int32_t level;
+    int32_t kinds; /* 2 bits per face, face = 2*d + (plus side) */
+    int32_t mask;
+} smr_item_flux;
+
 /* coarse interval filled by projection (numeric/projection.hpp:22-64) */
 typedef struct
 {

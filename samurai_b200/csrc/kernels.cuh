@@ -446,6 +446,137 @@ namespace smr
         }
     };
 
+    // Flux-based schemes on multi-level meshes, gather form.  The reference scatters, per direction: same-level
+    // interfaces (all levels), then per level the jumps "coarse | fine" (A) and "fine | coarse" (B), then the boundary
+    // interfaces in direction and opposite direction (flux_based_scheme__lin_hom.hpp:74-229, __nonlin.hpp:407-520).
+    // For one cell that fixes the order of the terms of each side by the kind of neighbour across the face:
+    //            minus side  plus side
+    //   same        1           1        (x direction, linear: interleaved c = 0 left/right, c = 1 left/right; else minus first)
+    //   coarse      2 (A)       2.5 (B)  cell = fine side, stencil = its own-level ghost inside the coarse leaf
+    //   fine        3.5 (B)     3 (A)    cell = coarse side, one contribution per level+1 interface interval
+    //   boundary    4.5         4
+    // `tab` = [2][SMR_MAX_LEVELS][3][2] doubles: same-level left-cell coefficients h_factor(h,h)*coeffs(h) of the cell's
+    // level, then the coarse-side jump coefficients h_factor(h_{l+1},h_l)*coeffs(h_{l+1}); right-cell coefficients are
+    // their negatives.  Non-linear schemes keep the two factors in [.][l][0][0].
+    template <int DIM, int NONLIN>
+    struct FluxGenOp
+    {
+        static constexpr bool two_phase = false;
+        static constexpr int min_blocks = 1;
+        static constexpr int units_per_thread = SMR_CELLS_PER_THREAD;
+
+        const double* __restrict__ u;
+        double* __restrict__ out;
+        const int64_t* __restrict__ aux;
+        const double* __restrict__ tab;
+        double scale;
+
+        // scale * make_convection_upwind<Field>() on a scalar field (operators/convection_nonlin.hpp:63-76,
+        // flux_based/algebraic_operators.hpp:38-46)
+        __device__ __forceinline__ double nflux(double ul, double ur) const
+        {
+            const double v = 0.5 * (ul + ur);
+            const double f = v >= 0 ? ul * ul : ur * ur;
+            return scale != 1 ? f * scale : f;
+        }
+
+        __device__ __forceinline__ double side(double acc, const smr_item_flux& it, int k, int d, int plus, int kind, const double* c,
+                                               const double* cs, const double* cj) const
+        {
+            const double uc = c[0];
+            const double sg = plus ? 1.0 : -1.0; // right-cell coefficients / fluxes[1] are exact negations
+            if (kind != SMR_FACE_FINE)
+            {
+                const double un = d == 0 ? c[plus ? 1 : -1] : u[it.nb[2 * (d - 1) + plus] + k];
+                if (NONLIN)
+                {
+                    const double f = plus ? nflux(uc, un) : nflux(un, uc);
+                    return acc + (sg * f) * cs[0];
+                }
+                const double s0 = plus ? uc : un, s1 = plus ? un : uc; // stencil {left cell, right cell}
+                return (acc + (sg * cs[2 * d]) * s0) + (sg * cs[2 * d + 1]) * s1;
+            }
+            const int64_t* fx = aux + it.fine + (2 * d + plus) * 4;
+            if (d == 0)
+            {
+#pragma unroll
+                for (int r = 0; r < (1 << (DIM - 1)); ++r)
+                {
+                    const double s0 = u[fx[r]], s1 = u[fx[r] + 1];
+                    if (NONLIN)
+                    {
+                        acc = acc + (sg * nflux(s0, s1)) * cj[0];
+                    }
+                    else
+                    {
+                        acc = acc + (sg * cj[0]) * s0;
+                        acc = acc + (sg * cj[1]) * s1;
+                    }
+                }
+                return acc;
+            }
+#pragma unroll
+            for (int b = 0; b < (DIM > 2 ? 2 : 1); ++b)
+            {
+                const double* r0 = u + fx[2 * b] + 2 * k;
+                const double* r1 = u + fx[2 * b + 1] + 2 * k;
+                if (NONLIN)
+                {
+                    acc = acc + (sg * nflux(r0[0], r1[0])) * cj[0];
+                    acc = acc + (sg * nflux(r0[1], r1[1])) * cj[0];
+                }
+                else
+                {
+                    const double a0 = sg * cj[2 * d], a1 = sg * cj[2 * d + 1];
+                    acc = acc + (a0 * r0[0] + a0 * r0[1]);
+                    acc = acc + (a1 * r1[0] + a1 * r1[1]);
+                }
+            }
+            return acc;
+        }
+
+        __device__ __forceinline__ void operator()(const smr_item_flux& it, int k) const
+        {
+            const double* c  = u + it.c + k;
+            const double* cs = tab + it.level * 6;
+            const double* cj = tab + (SMR_MAX_LEVELS + it.level) * 6;
+            double acc       = 0.0;
+#pragma unroll
+            for (int d = 0; d < DIM; ++d)
+            {
+                int km = (it.kinds >> (4 * d)) & 3, kp = (it.kinds >> (4 * d + 2)) & 3;
+                if (d == 0)
+                {
+                    km = k != 0 ? SMR_FACE_SAME : km;
+                    kp = k != it.n - 1 ? SMR_FACE_SAME : kp;
+                }
+                if (!NONLIN && d == 0 && km == SMR_FACE_SAME && kp == SMR_FACE_SAME)
+                {
+                    // one interface interval holds both x-interfaces of the cell: for c = 0, 1 the left-cell loop runs
+                    // before the right-cell loop (explicit_flux_based_scheme__lin_hom.hpp:63-76)
+                    const double tLc = cs[0] * c[0], tLp = cs[1] * c[1];
+                    const double tRm = (-cs[0]) * c[-1], tRc = (-cs[1]) * c[0];
+                    acc = (((acc + tLc) + tRm) + tLp) + tRc;
+                    continue;
+                }
+                // pass numbers x2: minus {2, 4, 7, 9}, plus {2, 5, 6, 8}
+                const int pm = km == SMR_FACE_SAME ? 2 : (km == SMR_FACE_COARSE ? 4 : (km == SMR_FACE_FINE ? 7 : 9));
+                const int pp = kp == SMR_FACE_SAME ? 2 : (kp == SMR_FACE_COARSE ? 5 : (kp == SMR_FACE_FINE ? 6 : 8));
+                if (pm <= pp)
+                {
+                    acc = side(acc, it, k, d, 0, km, c, cs, cj);
+                    acc = side(acc, it, k, d, 1, kp, c, cs, cj);
+                }
+                else
+                {
+                    acc = side(acc, it, k, d, 1, kp, c, cs, cj);
+                    acc = side(acc, it, k, d, 0, km, c, cs, cj);
+                }
+            }
+            mstore(out + it.c + k, acc, static_cast<unsigned>(it.mask));
+        }
+    };
+
     // out = a * x + b * y on the leaves (the field-expression tail `u - dt * S(u)` is a = 1, b = -dt)
     struct LinCombOp
     {

@@ -1,5 +1,5 @@
-"""Flux-based linear homogeneous schemes (make_convection_upwind, make_diffusion_order2) on uniform-level meshes:
-bit-exact against the oracle's literal restatement of the reference's scatter loops, plus the reference's analytic
+"""Flux-based schemes (make_convection_upwind linear and non-linear, make_diffusion_order2) on uniform-level and adapted
+meshes: bit-exact against the oracle's literal restatement of the reference's scatter loops, plus the reference's analytic
 checks (tests/test_fv_operators.cpp:87-226: diffusion exact on quadratics, convection exact on linear fields, zero on
 constants) and the explicit heat step of demos/FiniteVolume/heat.cpp."""
 import numpy as np
@@ -69,12 +69,106 @@ def test_analytic_exactness(gpu):
     assert np.max(np.abs(c2[inner] - 0.5)) < 1e-10
 
 
-def test_adapted_mesh_is_rejected_not_approximated(gpu):
-    pmesh = sb.MRMesh.make_mesh([0.0, 0.0], [1.0, 1.0], pu.product_cfg(2, 2, 6, 1))
+def _adapted(dim, lo, hi, bc=("dirichlet", 0.0)):
+    """Same adapted mesh on both sides (disc initial condition, one MRadaptation), leaves perturbed with seeded noise."""
+    pmesh = sb.MRMesh.make_mesh([0.0] * dim, [1.0] * dim, pu.product_cfg(dim, lo, hi, 1))
     u = sb.make_scalar_field("u", pmesh)
     u.resize()
-    u.init_ball([0.3, 0.3], 0.2)
-    sb.make_bc(u, sb.DIRICHLET, 0.0)
+    u.init_ball([0.3] * dim, 0.2)
+    sb.make_bc(u, sb.DIRICHLET if bc[0] == "dirichlet" else sb.NEUMANN, bc[1])
     sb.make_MRAdapt(u)(sb.mra_config().epsilon(2e-4))
-    with pytest.raises(ValueError, match="uniform-level"):
-        sb.make_diffusion_order2([1.0, 1.0])(u)
+    omesh = so.Mesh.uniform(pu.oracle_cfg(dim, lo, hi, 1))
+    obc = so.Bc(*bc)
+    omesh, ou = so.adapt(omesh, so.init_disc(omesh, [0.3] * dim, 0.2), obc, eps=2e-4)
+    pu.assert_same_mesh(pmesh, omesh)
+    rng = np.random.default_rng(11)
+    leaves = np.concatenate([omesh.index(l, omesh.cells[l]) for l in omesh.leaf_levels()])
+    ou[leaves] += 0.1 * rng.standard_normal(leaves.size)
+    u.upload(ou)
+    return pmesh, omesh, u, ou, obc, leaves
+
+
+@pytest.mark.parametrize("dim,lo,hi", [(1, 2, 7), (2, 2, 6), (2, 3, 7), (3, 2, 5)])
+@pytest.mark.parametrize("bc", [("dirichlet", 0.3), ("neumann", -0.2)])
+def test_schemes_across_level_jumps_bitwise(gpu, dim, lo, hi, bc):
+    """a8-a10 on adapted meshes: linear homogeneous and non-linear flux schemes, every leaf bit-identical to the oracle's
+    literal restatement of the reference's scatter loops (same-level, both jump orientations, boundary)."""
+    pmesh, omesh, u, ou, obc, leaves = _adapted(dim, lo, hi, bc)
+    assert len(omesh.leaf_levels()) > 1
+    og = ou.copy()
+    so.update_ghost_mr(omesh, og, obc)
+    vel, K = [1.0, -0.5, 0.25][:dim], [1.0, 2.0, 0.5][:dim]
+    cases = [(sb.make_convection_upwind(vel), so.flux_linhom_apply(omesh, og, so.convection_upwind_coeffs(vel))),
+             (sb.make_diffusion_order2(K), so.flux_linhom_apply(omesh, og, so.diffusion_order2_coeffs(K))),
+             (sb.make_convection_upwind(), so.flux_nonlin_apply(omesh, og, so.burgers_upwind_flux())),
+             (0.5 * sb.make_convection_upwind(), so.flux_nonlin_apply(omesh, og, so.burgers_upwind_flux(0.5)))]
+    for scheme, ref in cases:
+        rhs = scheme(u)
+        got = rhs.download()
+        bad = np.flatnonzero(got[leaves] != ref[leaves])
+        assert bad.size == 0, f"{scheme.name}: {bad.size} of {leaves.size} leaves differ, max {np.max(np.abs(got[leaves] - ref[leaves])):.3e}"
+        rhs.destroy()
+    u.destroy()
+    pmesh.destroy()
+
+
+def test_general_kernel_equals_strip_kernel_on_uniform_mesh(gpu, monkeypatch):
+    """the uniform-level fast path (strip kernel) and the general gather kernel give the same bits"""
+    import subprocess, sys, os
+    code = ("import numpy as np, sys; sys.path.insert(0, 'tests'); import parity_utils as pu; sb = pu.sb\n"
+            "assert sb.initialize(0)\n"
+            "m = sb.MRMesh.make_mesh([0.,0.],[1.,1.], pu.product_cfg(2, 6, 6, 1)); u = sb.make_scalar_field('u', m); u.resize()\n"
+            "rng = np.random.default_rng(3); u.upload(rng.standard_normal(m.nb_cells(sb.REFERENCE))); sb.make_bc(u, sb.DIRICHLET, 0.1)\n"
+            "np.save(sys.argv[1], sb.make_diffusion_order2([1., 2.])(u).download())\n")
+    outs = []
+    for env_extra in ({}, {"SMR_FLUX_GENERAL": "1"}):
+        path = f"/tmp/flux_uniform_{len(outs)}.npy"
+        subprocess.run([sys.executable, "-c", code, path], check=True, cwd=pu.ROOT, env={**os.environ, **env_extra})
+        outs.append(np.load(path))
+    omesh = so.Mesh.uniform(pu.oracle_cfg(2, 6, 6, 1))
+    leaves = omesh.index(6, omesh.cells[6])
+    assert np.array_equal(outs[0][leaves], outs[1][leaves])
+
+
+def test_heat_demo_reproduces_reference_golden(gpu):
+    """demos/FiniteVolume/heat.cpp --explicit --init-sol=dirac --Tf=0.1 --min-level=3 --max-level=6 on the GPU against the
+    reference's own golden file (tests/golden/heat_explicit.npz <- test_finite_volume_demo_heat_explicit.h5):
+    mesh identical, field within the reference's tolerance (rel 1e-14 / abs 1e-7; we require 1e-15 absolute)."""
+    import os
+    dim = 2
+    cfg = pu.product_cfg(dim, 3, 6, 1)
+    pmesh = sb.MRMesh.make_mesh([-4.0, -4.0], [4.0, 4.0], cfg)
+    ocfg = so.MeshConfig(dim=2, min_level=3, max_level=6, pred_radius=1, origin=(-4.0, -4.0), scaling=8.0)
+    om = so.Mesh.uniform(ocfg)
+    t = 1e-2
+    f0 = np.zeros(om.nref)
+    f0[om.index(6, om.cells[6])] = so.heat_exact(om.cell_centers(6, om.cells[6]), t)
+    u = sb.make_scalar_field("u", pmesh)
+    u.resize()
+    u.upload(f0)
+    unp1 = sb.make_scalar_field("unp1", pmesh)
+    sb.make_bc(u, sb.NEUMANN, 0.0)
+    sb.make_bc(unp1, sb.NEUMANN, 0.0)
+    diff = sb.make_diffusion_order2([1.0, 1.0])
+    dx = pmesh.cell_length(6)
+    dt = 0.95 * (dx * dx) / (pow(2, dim) * 1.0)
+    adapt = sb.make_MRAdapt(u)
+    mra = sb.mra_config()
+    adapt(mra)
+    Tf, nt = 0.1, 0
+    while t != Tf:
+        t += dt
+        if t > Tf:
+            dt += Tf - t
+            t = Tf
+        adapt(mra)
+        unp1.resize()
+        sb.lincomb(unp1, 1.0, u, -dt, diff(u))
+        sb.swap(u, unp1)
+        nt += 1
+    assert nt == 25
+    g = np.load(os.path.join(pu.ROOT, "tests", "golden", "heat_explicit.npz"))
+    lv, idx, off = pmesh.cell_table(sb.CELLS)
+    assert np.array_equal(lv, g["level"].astype(np.int64)) and np.array_equal(idx[:, :2], g["idx"].astype(np.int64)), "mesh differs"
+    got = u.download()[off]
+    assert np.max(np.abs(got - g["u"])) <= 1e-15
