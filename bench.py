@@ -79,6 +79,13 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def wait_first_sample(self, timeout=8.0):
+        """nvidia-smi's start-up (NVML initialisation) takes ~1 s and stalls CUDA calls of other processes on the same GPU
+        while it lasts: keep it out of the timed region, which then only sees the periodic 200 ms queries."""
+        t0 = time.perf_counter()
+        while self.proc is not None and not self.lines and time.perf_counter() - t0 < timeout:
+            time.sleep(0.05)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -305,6 +312,7 @@ def run_product(args):
     # ---- timed, device-resident ------------------------------------------------------------------------------------
     sampler = ClockSampler(local_rank)
     sampler.start()
+    sampler.wait_first_sample()
     sb.stats(reset=True)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -411,6 +419,9 @@ def run_product(args):
                                     "the uniform sweep uses a working set > L2"},
             "split_ms_per_step": {"device": 1e3 * st["device_seconds"] / args.steps, "host_mesh": 1e3 * st["host_mesh_seconds"] / args.steps,
                                   "host_batches": 1e3 * st["host_batch_seconds"] / args.steps},
+            "host_stages_ms_per_step": dict(zip(("tags_to_leaves", "mesh_equality", "graduation", "sub_meshes", "transfer_batches", "mesh_batches",
+                                                 "wait_device", "release_old_mesh"), [1e3 * v / args.steps for v in st["host_stage_seconds"]])),
+            "harten_iterations_per_step": st["harten_iterations"] / args.steps, "mesh_rebuilds_per_step": st["mesh_rebuilds"] / args.steps,
             "device_only_value": cells / world / st["device_seconds"] if st["device_seconds"] > 0 else None,
             "gpu_launches": int(st["kernel_launches"]),
             "initial_adaptation_s": init_secs,
@@ -466,7 +477,7 @@ def main():
     global ARGS
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--min-level", type=int, default=4)

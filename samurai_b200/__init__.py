@@ -54,6 +54,8 @@ class StatsC(C.Structure):
         ("mesh_rebuilds", C.c_uint64),
         ("device_seconds", C.c_double),
         ("ghost_updates_skipped", C.c_uint64),
+        ("harten_iterations", C.c_uint64),
+        ("host_stage_seconds", C.c_double * 8),
     ]
 
 
@@ -221,7 +223,7 @@ def stats(reset=False):
     load_library().smr_stats_get(C.byref(s))
     if reset:
         load_library().smr_stats_reset()
-    return {k: getattr(s, k) for k, _ in StatsC._fields_}
+    return {k: (list(getattr(s, k)) if k == "host_stage_seconds" else getattr(s, k)) for k, _ in StatsC._fields_}
 
 
 def profile_enable(on=True):

@@ -125,9 +125,11 @@ namespace smr
         int kind   = -1;
         int level  = -1;
         std::vector<const std::vector<Item>*> parts;
-        std::vector<int64_t>* cum = nullptr; // optional per-part cumulative output-cell counts
+        std::vector<int64_t>* cum = nullptr; // optional per-group cumulative output-cell counts
         bool inclusive            = false;
         int cta_units             = SMR_CTA_CELLS;
+        std::vector<int> group;   // group (e.g. level) of every part, non-decreasing; empty: every part is its own group
+        int n_groups = 0;
     };
 
     template <class Item>
@@ -139,29 +141,39 @@ namespace smr
         b.level   = pd.level;
         size_t n  = 0;
         int64_t c = 0;
+        const int ngroups = pd.n_groups > 0 ? pd.n_groups : static_cast<int>(pd.parts.size());
         if (pd.cum)
         {
-            pd.cum->assign(pd.parts.size() + 1, 0);
+            pd.cum->assign(static_cast<size_t>(ngroups) + 1, 0);
         }
+        std::vector<int64_t> per_group(static_cast<size_t>(ngroups), 0);
         for (size_t k = 0; k < pd.parts.size(); ++k)
         {
-            if (pd.cum && !pd.inclusive)
-            {
-                (*pd.cum)[k] = c;
-            }
+            int64_t cp = 0;
             for (const Item& it : *pd.parts[k])
             {
-                c += it.n;
+                cp += it.n;
             }
+            c += cp;
+            per_group[static_cast<size_t>(pd.n_groups > 0 ? pd.group[k] : static_cast<int>(k))] += cp;
             n += pd.parts[k]->size();
-            if (pd.cum && pd.inclusive)
-            {
-                (*pd.cum)[k] = c;
-            }
         }
         if (pd.cum)
         {
-            (*pd.cum)[pd.parts.size()] = c;
+            int64_t acc = 0;
+            for (int gi = 0; gi < ngroups; ++gi)
+            {
+                if (!pd.inclusive)
+                {
+                    (*pd.cum)[static_cast<size_t>(gi)] = acc;
+                }
+                acc += per_group[static_cast<size_t>(gi)];
+                if (pd.inclusive)
+                {
+                    (*pd.cum)[static_cast<size_t>(gi)] = acc;
+                }
+            }
+            (*pd.cum)[static_cast<size_t>(ngroups)] = acc;
         }
         b.n_items = static_cast<int>(n);
         if (n == 0)
@@ -413,14 +425,15 @@ namespace smr
     // ---------------------------------------------------------------------------------------------------------
     // per-interval item builders
     // ---------------------------------------------------------------------------------------------------------
-    inline void fv_items(const Mesh& m, int l, const PlanFilter& flt, std::vector<smr_item_fv>& out)
+    inline void fv_items(const Mesh& m, int l, const PlanFilter& flt, std::vector<smr_item_fv>& out, size_t row_begin = 0, size_t row_end = ~size_t(0))
     {
         const int dim = m.cfg.dim;
         const LevelSet& c   = m.cells[l];
         const LevelSet& ref = m.ref[l];
         Probe pc(ref), pym(ref), pyp(ref), pzm(ref), pzp(ref);
-        out.reserve(out.size() + c.n_intervals());
-        for (size_t r = 0; r < c.rows(); ++r)
+        row_end = std::min(row_end, c.rows());
+        out.reserve(out.size() + static_cast<size_t>(c.ptr[row_end] - c.ptr[row_begin]));
+        for (size_t r = row_begin; r < row_end; ++r)
         {
             const int y = key_y(c.key[r]), z = key_z(c.key[r]);
             if (!flt.owns(l, y, z))
@@ -468,7 +481,8 @@ namespace smr
 
     // Leaves of level l split for the FV kernels: strips of SMR_STRIP_ROWS consecutive rows sharing an x-range, and the
     // single-row remainder.  Every leaf cell lands in exactly one of the two lists.
-    inline void fv_split_items(const Mesh& m, int l, const PlanFilter& flt, std::vector<smr_item_fvstrip>& strips, std::vector<smr_item_fv>& singles)
+    inline void fv_split_items(const Mesh& m, int l, const PlanFilter& flt, std::vector<smr_item_fvstrip>& strips, std::vector<smr_item_fv>& singles,
+                               size_t row_begin = 0, size_t row_end = ~size_t(0))
     {
         constexpr int R = SMR_STRIP_ROWS;
         const int dim   = m.cfg.dim;
@@ -476,7 +490,7 @@ namespace smr
         const LevelSet& ref = m.ref[l];
         if (dim < 2)
         {
-            fv_items(m, l, flt, singles);
+            fv_items(m, l, flt, singles, row_begin, row_end);
             return;
         }
         Probe prow[R + 2], pzm[R], pzp[R];
@@ -520,8 +534,8 @@ namespace smr
             it.mask  = static_cast<int>(flt.mask(l, y, z));
             singles.push_back(it);
         };
-        size_t r0 = 0;
-        const size_t nrows = c.rows();
+        size_t r0 = row_begin;
+        const size_t nrows = std::min(row_end, c.rows());
         while (r0 < nrows)
         {
             const int y0 = key_y(c.key[r0]), z0 = key_z(c.key[r0]);
@@ -660,7 +674,8 @@ namespace smr
     // lies across each face of each leaf (same-level leaf / coarser leaf / finer leaves / boundary) and cuts the leaf
     // intervals where a transverse classification changes.
     // ---------------------------------------------------------------------------------------------------------
-    inline void flux_items(const Mesh& m, int l, const PlanFilter& flt, std::vector<smr_item_flux>& out, std::vector<int64_t>& aux)
+    inline void flux_items(const Mesh& m, int l, const PlanFilter& flt, std::vector<smr_item_flux>& out, std::vector<int64_t>& aux,
+                           size_t row_begin = 0, size_t row_end = ~size_t(0))
     {
         const int dim        = m.cfg.dim;
         const LevelSet& c    = m.cells[l];
@@ -684,8 +699,9 @@ namespace smr
         {
             return s != nullptr && s->contains(mk_key(y, z), x);
         };
-        out.reserve(out.size() + c.n_intervals());
-        for (size_t r = 0; r < c.rows(); ++r)
+        row_end = std::min(row_end, c.rows());
+        out.reserve(out.size() + static_cast<size_t>(c.ptr[row_end] - c.ptr[row_begin]));
+        for (size_t r = row_begin; r < row_end; ++r)
         {
             const int y = key_y(c.key[r]), z = key_z(c.key[r]);
             if (!flt.owns(l, y, z))
@@ -1603,42 +1619,24 @@ namespace smr
         const int dim = cfg.dim, L = cfg.max_level, lmin = cfg.min_level;
         const int nlev = m.nlev;
         plan.arena.clear();
-        std::vector<std::vector<smr_item_fv>> fv(nlev), fv_single(nlev);
-        std::vector<std::vector<smr_item_fvstrip>> fv_strip(nlev);
+        // Two passes of independent tasks.  Pass A, one task per (kind, level): the set algebra of the tag / detail /
+        // prediction subsets and the whole ghost phase of a level.  Pass B, one task per (kind, level, row chunk): the
+        // traversal of a subset (or of the leaves) into records.  Chunks keep the finest levels, which hold most of the
+        // cells, from being the critical path.
         std::vector<PhaseItems> phases(nlev);
-        std::vector<std::vector<smr_item_pred>> pred(nlev);
-        std::vector<std::vector<smr_item_detail>> detail(nlev);
-        std::vector<std::vector<smr_item_tag>> tag(nlev);
+        std::vector<LevelSet> tagset(nlev), detailset(nlev), predset(nlev);
         std::string error;
 #ifdef SMR_PLAN_TIMING
         const double tt0 = omp_get_wtime();
-        std::vector<double> task_t(6 * nlev, 0.0);
 #endif
-        // one task per (kind, level): levels are independent once the mesh exists
-        const int ntasks = 6 * nlev;
 #pragma omp parallel for schedule(dynamic, 1)
-        for (int t = ntasks - 1; t >= 0; --t)
+        for (int t = 4 * nlev - 1; t >= 0; --t)
         {
             const int kind = t / nlev, level = t % nlev;
-#ifdef SMR_PLAN_TIMING
-            const double tk0 = omp_get_wtime();
-#endif
             try
             {
                 switch (kind)
                 {
-                    case 5:
-                        if (!m.cells[level].empty())
-                        {
-                            fv_split_items(m, level, flt, fv_strip[level], fv_single[level]);
-                        }
-                        break;
-                    case 4:
-                        if (!m.cells[level].empty())
-                        {
-                            fv_items(m, level, flt, fv[level]);
-                        }
-                        break;
                     case 3:
                         if (level <= L)
                         {
@@ -1648,24 +1646,23 @@ namespace smr
                     case 2:
                         if (level >= 1 && level <= L)
                         {
-                            LevelSet ps = prediction_set(m, level);
-                            if (!ps.empty())
+                            predset[level] = prediction_set(m, level);
+                            if (!predset[level].empty())
                             {
-                                locate(ps, m.ref[level]);
-                                pred_items(dim, cfg.pred_radius, level, ps, m.ref[level - 1], flt, pred[level]);
+                                locate(predset[level], m.ref[level]);
                             }
                         }
                         break;
                     case 1:
                         if (lmin != L && level >= std::max(lmin - 1, 0) && level < L)
                         {
-                            detail_items(m, level, detail_set(m, level), flt, detail[level]);
+                            detailset[level] = detail_set(m, level);
                         }
                         break;
                     default:
                         if (lmin != L && level >= std::max(lmin, 1) && level <= L)
                         {
-                            tag_items(m, level, tag_set(m, level), flt, tag[level]);
+                            tagset[level] = tag_set(m, level);
                         }
                         break;
                 }
@@ -1675,9 +1672,72 @@ namespace smr
 #pragma omp critical
                 error = e.what();
             }
+        }
+        if (!error.empty())
+        {
+            throw std::out_of_range(error);
+        }
+        struct Chunk
+        {
+            int kind, level;
+            size_t r0, r1;
+            std::vector<smr_item_fv> fv, fv_single;
+            std::vector<smr_item_fvstrip> fv_strip;
+            std::vector<smr_item_pred> pred;
+            std::vector<smr_item_detail> detail;
+            std::vector<smr_item_tag> tag;
+        };
+        std::vector<Chunk> chunks;
+        // chunk lists per kind, levels ascending, so that the concatenation below keeps level order
+        for (int kind = 0; kind < 5; ++kind)
+        {
+            for (int level = 0; level < nlev; ++level)
+            {
+                const LevelSet& src = kind == 0 ? tagset[level] : (kind == 1 ? detailset[level] : (kind == 2 ? predset[level] : m.cells[level]));
+                if (src.empty())
+                {
+                    continue;
+                }
+                const std::vector<size_t> cut = chunk_rows(src, 2500, 16);
+                for (size_t c = 0; c + 1 < cut.size(); ++c)
+                {
+                    chunks.push_back(Chunk{kind, level, cut[c], cut[c + 1], {}, {}, {}, {}, {}, {}});
+                }
+            }
+        }
 #ifdef SMR_PLAN_TIMING
-            task_t[t] = omp_get_wtime() - tk0;
+        const double tt05 = omp_get_wtime();
 #endif
+#pragma omp parallel for schedule(dynamic, 1)
+        for (int t = static_cast<int>(chunks.size()) - 1; t >= 0; --t)
+        {
+            Chunk& ck = chunks[static_cast<size_t>(t)];
+            try
+            {
+                switch (ck.kind)
+                {
+                    case 4:
+                        fv_split_items(m, ck.level, flt, ck.fv_strip, ck.fv_single, ck.r0, ck.r1);
+                        break;
+                    case 3:
+                        fv_items(m, ck.level, flt, ck.fv, ck.r0, ck.r1);
+                        break;
+                    case 2:
+                        pred_items(dim, cfg.pred_radius, ck.level, slice_rows(predset[ck.level], ck.r0, ck.r1, true), m.ref[ck.level - 1], flt, ck.pred);
+                        break;
+                    case 1:
+                        detail_items(m, ck.level, slice_rows(detailset[ck.level], ck.r0, ck.r1), flt, ck.detail);
+                        break;
+                    default:
+                        tag_items(m, ck.level, slice_rows(tagset[ck.level], ck.r0, ck.r1), flt, ck.tag);
+                        break;
+                }
+            }
+            catch (const std::exception& e)
+            {
+#pragma omp critical
+                error = e.what();
+            }
         }
         if (!error.empty())
         {
@@ -1685,13 +1745,7 @@ namespace smr
         }
 #ifdef SMR_PLAN_TIMING
         const double tt1 = omp_get_wtime();
-        for (int t = 0; t < ntasks; ++t)
-        {
-            if (task_t[t] > 2e-4)
-            {
-                std::printf("  task kind %d level %d: %.2f ms\n", t / nlev, t % nlev, task_t[t] * 1e3);
-            }
-        }
+        std::printf("  build_plan: sets+phases %.2f ms, %zu chunks %.2f ms\n", (tt05 - tt0) * 1e3, chunks.size(), (tt1 - tt05) * 1e3);
 #endif
         plan.down.assign(nlev, GhostPhase());
         plan.pred.assign(nlev, Batch());
@@ -1702,21 +1756,42 @@ namespace smr
         Pending<smr_item_fvstrip> p_fv_strip{&plan.fv_strip, B_FV, -1, {}, nullptr, false, SMR_CTA_THREADS * STRIP_UPT};
         Pending<smr_item_detail> p_detail{&plan.detail, B_DETAIL, -1, {}, &plan.detail_cum, false};
         Pending<smr_item_tag> p_tag_all{&plan.tag_all, B_TAG, -1, {}, &plan.tag_cum, true};
+        p_detail.n_groups = p_tag_all.n_groups = nlev; // cumulative counts are indexed by level
         std::vector<Pending<smr_item_proj>> p_proj(nlev);
         std::vector<Pending<smr_item_pred>> p_pred(nlev);
         std::vector<Pending<smr_item_tag>> p_tag(nlev);
         std::vector<PendingBc> p_bc(nlev);
         for (int l = 0; l < nlev; ++l)
         {
-            p_fv.parts.push_back(&fv[l]);
-            p_fv_single.parts.push_back(&fv_single[l]);
-            p_fv_strip.parts.push_back(&fv_strip[l]);
-            p_detail.parts.push_back(&detail[l]);
-            p_tag_all.parts.push_back(&tag[l]);
             p_proj[l] = Pending<smr_item_proj>{&plan.down[l].proj, B_PROJ, l, {&phases[l].proj}, nullptr, false};
-            p_pred[l] = Pending<smr_item_pred>{&plan.pred[l], B_PRED, l, {&pred[l]}, nullptr, false};
-            p_tag[l]  = Pending<smr_item_tag>{&plan.tag[l], B_TAG, l, {&tag[l]}, nullptr, false};
+            p_pred[l] = Pending<smr_item_pred>{&plan.pred[l], B_PRED, l, {}, nullptr, false};
+            p_tag[l]  = Pending<smr_item_tag>{&plan.tag[l], B_TAG, l, {}, nullptr, false};
             p_bc[l]   = PendingBc{&plan.down[l].bc, l, &phases[l].bc.items, &phases[l].bc.srcs};
+        }
+        for (const Chunk& ck : chunks)
+        {
+            switch (ck.kind)
+            {
+                case 4:
+                    p_fv_single.parts.push_back(&ck.fv_single);
+                    p_fv_strip.parts.push_back(&ck.fv_strip);
+                    break;
+                case 3:
+                    p_fv.parts.push_back(&ck.fv);
+                    break;
+                case 2:
+                    p_pred[ck.level].parts.push_back(&ck.pred);
+                    break;
+                case 1:
+                    p_detail.parts.push_back(&ck.detail);
+                    p_detail.group.push_back(ck.level);
+                    break;
+                default:
+                    p_tag_all.parts.push_back(&ck.tag);
+                    p_tag_all.group.push_back(ck.level);
+                    p_tag[ck.level].parts.push_back(&ck.tag);
+                    break;
+            }
         }
         layout_batch(p_fv, plan.arena);
         layout_batch(p_fv_single, plan.arena);

@@ -498,8 +498,11 @@ namespace smr
         }
         build_plan(mo.mesh, mo.plan, mo.filter);
         g.stats.host_batch_seconds += now() - t0;
+        g.stats.host_stage_seconds[5] += now() - t0;
         // the previous arena may still be in use by queued kernels: stream-ordered, so a sync is needed before reuse
+        const double tw = now();
         SMR_CUDA(cudaStreamSynchronize(g.stream));
+        g.stats.host_stage_seconds[6] += now() - tw;
         upload_arena(mo.plan.arena, mo.d_arena);
         mo.plan_ready = true;
     }
@@ -842,15 +845,42 @@ namespace smr
         mo.last_ncomp = ncomp;
 
         // host: new leaves from tags, graduation, fixed-point test (mr/adapt.hpp:360-379)
+        ++g.stats.harten_iterations;
         double t0    = now();
-        CellArray ca = cells_from_tags(mo.mesh, static_cast<const uint8_t*>(mo.h_tag.p));
+        double ts    = t0;
+        auto stage   = [&](int k)
+        {
+            const double t = now();
+            g.stats.host_stage_seconds[k] += t - ts;
+            ts = t;
+        };
+        bool no_tag_changes = false;
+        CellArray ca        = cells_from_tags(mo.mesh, static_cast<const uint8_t*>(mo.h_tag.p), &no_tag_changes);
+        stage(0);
+        if (no_tag_changes && mo.graduated)
+        {
+            // no leaf refined or coarsened, and the leaves are a fixed point of make_graduation: mesh == new_mesh
+            g.stats.host_mesh_seconds += now() - t0;
+            return true;
+        }
+        if (no_tag_changes)
+        {
+            ca = mo.mesh.cells;
+            for (LevelSet& s : ca)
+            {
+                s.off.clear();
+            }
+        }
         // every mesh held here came out of make_graduation (or is uniform), and make_graduation leaves a graduated
         // cell array untouched, so it only has to run when the tags changed something
         bool same = same_cells(ca, mo.mesh.cells);
+        stage(1);
         if (!same || !mo.graduated)
         {
             make_graduation(cfg, ca);
+            stage(2);
             same = same_cells(ca, mo.mesh.cells);
+            stage(1);
         }
         mo.graduated = true;
         if (same)
@@ -861,6 +891,7 @@ namespace smr
         auto new_mesh = std::make_unique<Mesh>();
         new_mesh->generation = mo.mesh.generation;
         new_mesh->init_from_cells(cfg, std::move(ca));
+        stage(3);
         g.stats.host_mesh_seconds += now() - t0;
         ++g.stats.mesh_rebuilds;
 
@@ -868,7 +899,10 @@ namespace smr
         t0 = now();
         TransferPlan& tpn = g.transfer;
         SMR_CUDA(cudaStreamSynchronize(g.stream)); // the previous transfer upload must have left the staging arena
+        ts = now();
+        g.stats.host_stage_seconds[6] += ts - t0;
         build_transfer(mo.mesh, *new_mesh, tpn, mo.filter);
+        stage(4);
         g.stats.host_batch_seconds += now() - t0;
         DevBuf& d_tr = g.d_transfer;
         const int64_t nn = new_mesh->nref;
@@ -896,8 +930,11 @@ namespace smr
             fields[i]->n            = nn;
             fields[i]->ghosts_valid = false;
         }
-        mo.mesh       = std::move(*new_mesh);
+        const double tm = now();
+        mo.mesh         = std::move(*new_mesh);
+        new_mesh.reset();
         mo.invalidate_plans();
+        g.stats.host_stage_seconds[7] += now() - tm;
         return false;
     }
 

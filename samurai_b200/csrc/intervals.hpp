@@ -7,6 +7,7 @@
 // (row key, x_start, x_end, storage offset) is what gets uploaded to the device.
 #pragma once
 #include <algorithm>
+#include <limits>
 #include <cassert>
 #include <cstdint>
 #include <stdexcept>
@@ -353,11 +354,26 @@ namespace smr
             return out;
         }
         size_t i = 0, j = 0;
-        const size_t na = a.rows(), nb = b.rows();
-        out.key.reserve(OP == SetOp::Union ? na + nb : na);
-        out.xs.reserve(a.xs.size() + (OP == SetOp::Union ? b.xs.size() : 0));
-        out.xe.reserve(a.xs.size() + (OP == SetOp::Union ? b.xs.size() : 0));
-        while (i < na || j < nb)
+        size_t na = a.rows(), nb = b.rows();
+        if (OP == SetOp::Inter)
+        {
+            // only the common key range matters: skip straight to it (chunked callers intersect a small set with a big one)
+            i  = static_cast<size_t>(std::lower_bound(a.key.begin(), a.key.end(), b.key.front()) - a.key.begin());
+            j  = static_cast<size_t>(std::lower_bound(b.key.begin(), b.key.end(), a.key.front()) - b.key.begin());
+            na = static_cast<size_t>(std::upper_bound(a.key.begin(), a.key.end(), b.key.back()) - a.key.begin());
+            nb = static_cast<size_t>(std::upper_bound(b.key.begin(), b.key.end(), a.key.back()) - b.key.begin());
+            const size_t guess = std::min(na - std::min(i, na), nb - std::min(j, nb));
+            out.key.reserve(guess);
+            out.xs.reserve(2 * guess);
+            out.xe.reserve(2 * guess);
+        }
+        else
+        {
+            out.key.reserve(OP == SetOp::Union ? na + nb : na);
+            out.xs.reserve(a.xs.size() + (OP == SetOp::Union ? b.xs.size() : 0));
+            out.xe.reserve(a.xs.size() + (OP == SetOp::Union ? b.xs.size() : 0));
+        }
+        while (OP == SetOp::Inter ? (i < na && j < nb) : (i < na || j < nb))
         {
             if (j >= nb || (i < na && a.key[i] < b.key[j]))
             {
@@ -723,6 +739,253 @@ namespace smr
             return out;
         }
     };
+
+    // ------------------------------------------------------------------------------------------------
+    // intra-level parallelism: expand / coarsen / refine / translate / intersection or difference with a fixed set all
+    // distribute over the union of their input, so a large level is cut into row chunks that are processed
+    // independently and whose results are united again (chunk results overlap only near the cuts)
+    // ------------------------------------------------------------------------------------------------
+    inline LevelSet slice_rows(const LevelSet& a, size_t r0, size_t r1, bool with_offsets = false)
+    {
+        LevelSet out;
+        if (r0 >= r1)
+        {
+            return out;
+        }
+        const int q0 = a.ptr[r0], q1 = a.ptr[r1];
+        if (with_offsets && a.off.size() == a.xs.size())
+        {
+            out.off.assign(a.off.begin() + q0, a.off.begin() + q1);
+        }
+        out.key.assign(a.key.begin() + static_cast<std::ptrdiff_t>(r0), a.key.begin() + static_cast<std::ptrdiff_t>(r1));
+        out.xs.assign(a.xs.begin() + q0, a.xs.begin() + q1);
+        out.xe.assign(a.xe.begin() + q0, a.xe.begin() + q1);
+        out.ptr.resize(r1 - r0 + 1);
+        for (size_t r = r0; r <= r1; ++r)
+        {
+            out.ptr[r - r0] = a.ptr[r] - q0;
+        }
+        return out;
+    }
+
+    // row boundaries of at most `max_chunks` chunks holding about `target` intervals each
+    inline std::vector<size_t> chunk_rows(const LevelSet& a, size_t target, size_t max_chunks)
+    {
+        std::vector<size_t> cut{0};
+        const size_t n = a.n_intervals();
+        size_t chunks  = std::min(max_chunks, std::max<size_t>(1, n / std::max<size_t>(target, 1)));
+        for (size_t c = 1; c < chunks; ++c)
+        {
+            const int32_t want = static_cast<int32_t>(n * c / chunks);
+            const size_t r     = static_cast<size_t>(std::lower_bound(a.ptr.begin(), a.ptr.end(), want) - a.ptr.begin());
+            if (r > cut.back() && r < a.rows())
+            {
+                cut.push_back(r);
+            }
+        }
+        cut.push_back(a.rows());
+        return cut;
+    }
+
+    // union of any number of sets: k-way merge over the row keys, runs of rows owned by a single part are copied in bulk
+    inline LevelSet union_all(const std::vector<const LevelSet*>& in)
+    {
+        std::vector<const LevelSet*> parts;
+        for (const LevelSet* p : in)
+        {
+            if (p != nullptr && !p->empty())
+            {
+                parts.push_back(p);
+            }
+        }
+        LevelSet out;
+        if (parts.empty())
+        {
+            return out;
+        }
+        if (parts.size() == 1)
+        {
+            out = *parts[0];
+            out.off.clear();
+            return out;
+        }
+        size_t rows = 0, ivls = 0;
+        for (const LevelSet* p : parts)
+        {
+            rows += p->rows();
+            ivls += p->n_intervals();
+        }
+        out.key.reserve(rows);
+        out.ptr.reserve(rows + 1);
+        out.xs.reserve(ivls);
+        out.xe.reserve(ivls);
+        const size_t np = parts.size();
+        std::vector<size_t> cur(np, 0);
+        std::vector<std::pair<int32_t, int32_t>> tmp;
+        constexpr int64_t INF = std::numeric_limits<int64_t>::max();
+        while (true)
+        {
+            // smallest and second smallest current keys
+            int64_t k1 = INF, k2 = INF;
+            size_t p1 = np;
+            int ties  = 0;
+            for (size_t p = 0; p < np; ++p)
+            {
+                if (cur[p] >= parts[p]->rows())
+                {
+                    continue;
+                }
+                const int64_t k = parts[p]->key[cur[p]];
+                if (k < k1)
+                {
+                    k2 = k1;
+                    k1 = k;
+                    p1 = p;
+                    ties = 1;
+                }
+                else if (k == k1)
+                {
+                    ++ties;
+                }
+                else if (k < k2)
+                {
+                    k2 = k;
+                }
+            }
+            if (p1 == np)
+            {
+                break;
+            }
+            if (ties == 1)
+            {
+                // rows of part p1 with key < k2: bulk copy
+                const LevelSet& a = *parts[p1];
+                const size_t r0   = cur[p1];
+                const size_t r1   = static_cast<size_t>(std::lower_bound(a.key.begin() + static_cast<std::ptrdiff_t>(r0), a.key.end(), k2) - a.key.begin());
+                const int q0 = a.ptr[r0], q1 = a.ptr[r1];
+                const int32_t shift = static_cast<int32_t>(out.xs.size()) - q0;
+                out.key.insert(out.key.end(), a.key.begin() + static_cast<std::ptrdiff_t>(r0), a.key.begin() + static_cast<std::ptrdiff_t>(r1));
+                out.xs.insert(out.xs.end(), a.xs.begin() + q0, a.xs.begin() + q1);
+                out.xe.insert(out.xe.end(), a.xe.begin() + q0, a.xe.begin() + q1);
+                for (size_t r = r0 + 1; r <= r1; ++r)
+                {
+                    out.ptr.push_back(a.ptr[r] + shift);
+                }
+                cur[p1] = r1;
+                continue;
+            }
+            // several parts hold row k1: merge their intervals
+            tmp.clear();
+            for (size_t p = 0; p < np; ++p)
+            {
+                if (cur[p] < parts[p]->rows() && parts[p]->key[cur[p]] == k1)
+                {
+                    const LevelSet& a = *parts[p];
+                    for (int q = a.ptr[cur[p]]; q < a.ptr[cur[p] + 1]; ++q)
+                    {
+                        tmp.emplace_back(a.xs[q], a.xe[q]);
+                    }
+                    ++cur[p];
+                }
+            }
+            std::sort(tmp.begin(), tmp.end());
+            for (auto& iv : tmp)
+            {
+                out.push(k1, iv.first, iv.second);
+            }
+        }
+        return out;
+    }
+
+    inline LevelSet union_all(const std::vector<LevelSet>& in)
+    {
+        std::vector<const LevelSet*> p;
+        p.reserve(in.size());
+        for (const LevelSet& s : in)
+        {
+            p.push_back(&s);
+        }
+        return union_all(p);
+    }
+
+    // f(part) over row chunks of `a` in parallel (no-op inside an enclosing parallel region), results united
+    template <class F>
+    inline LevelSet par_rows(const LevelSet& a, F&& f, size_t target = 3000, size_t max_chunks = 16)
+    {
+        const std::vector<size_t> cut = chunk_rows(a, target, max_chunks);
+        const int n                   = static_cast<int>(cut.size()) - 1;
+        if (n <= 1)
+        {
+            return f(a);
+        }
+        std::vector<LevelSet> res(static_cast<size_t>(n));
+#pragma omp parallel for schedule(dynamic, 1)
+        for (int c = 0; c < n; ++c)
+        {
+            res[static_cast<size_t>(c)] = f(slice_rows(a, cut[static_cast<size_t>(c)], cut[static_cast<size_t>(c) + 1]));
+        }
+        return union_all(res);
+    }
+
+    // a OP b with both operands cut at the same row keys
+    template <SetOp OP>
+    inline LevelSet par_set_op(const LevelSet& a, const LevelSet& b, size_t target = 3000, size_t max_chunks = 16)
+    {
+        const LevelSet& big           = a.n_intervals() >= b.n_intervals() ? a : b;
+        const std::vector<size_t> cut = chunk_rows(big, target, max_chunks);
+        const int n                   = static_cast<int>(cut.size()) - 1;
+        if (n <= 1)
+        {
+            return set_op<OP>(a, b);
+        }
+        std::vector<LevelSet> res(static_cast<size_t>(n));
+        auto row_of = [](const LevelSet& s, int64_t k)
+        {
+            return static_cast<size_t>(std::lower_bound(s.key.begin(), s.key.end(), k) - s.key.begin());
+        };
+#pragma omp parallel for schedule(dynamic, 1)
+        for (int c = 0; c < n; ++c)
+        {
+            const bool first = c == 0, last = c == n - 1;
+            const int64_t klo = first ? 0 : big.key[cut[static_cast<size_t>(c)]];
+            const int64_t khi = last ? 0 : big.key[cut[static_cast<size_t>(c) + 1]];
+            const LevelSet pa = slice_rows(a, first ? 0 : row_of(a, klo), last ? a.rows() : row_of(a, khi));
+            const LevelSet pb = slice_rows(b, first ? 0 : row_of(b, klo), last ? b.rows() : row_of(b, khi));
+            res[static_cast<size_t>(c)] = set_op<OP>(pa, pb);
+        }
+        return union_all(res); // chunk results have disjoint key ranges: pure concatenation
+    }
+
+    inline LevelSet par_union(const LevelSet& a, const LevelSet& b)
+    {
+        if (a.empty())
+        {
+            return b;
+        }
+        if (b.empty())
+        {
+            return a;
+        }
+        return par_set_op<SetOp::Union>(a, b);
+    }
+
+    inline LevelSet par_inter(const LevelSet& a, const LevelSet& b)
+    {
+        if (a.empty() || b.empty())
+        {
+            return LevelSet();
+        }
+        return par_set_op<SetOp::Inter>(a, b);
+    }
+
+    inline LevelSet par_diff(const LevelSet& a, const LevelSet& b)
+    {
+        if (a.empty() || b.empty())
+        {
+            return a;
+        }
+        return par_set_op<SetOp::Diff>(a, b);
+    }
 
     // Fill sub.off from the containing intervals of `ref` (sub must be a subset of ref; both sorted).
     // Mirrors Mesh_base::renumbering (reference mesh.hpp:894-911): every sub-mesh reuses the reference numbering.

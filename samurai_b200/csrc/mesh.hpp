@@ -10,6 +10,10 @@
 //   algorithm/graduation.hpp:245-330,573-726  make_graduation (max_stencil_radius == 1: no boundary rule)
 // Scope: serial (one subdomain == domain), non-periodic box domains.
 #pragma once
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+#include <cstdio>
 #include "intervals.hpp"
 
 #include <array>
@@ -184,30 +188,97 @@ namespace smr
             cag.assign(nlev, LevelSet());
             proj.assign(nlev, LevelSet());
             const bool multi = cfg.max_level != cfg.min_level;
+#ifdef SMR_PLAN_TIMING
+            const double tb0 = omp_get_wtime();
+            std::vector<double> tlev(nlev + 1, 0.0);
+#endif
             std::vector<LevelSet> add1(nlev), add2(nlev); // prediction ghosts sent one / two levels down (mr/mesh.hpp:329-359)
-            // levels are independent here; the union pyramid (a serial cascade) runs as one more task next to them
-#pragma omp parallel for schedule(dynamic, 1)
-            for (int t = nlev; t >= 0; --t)
+            // Tasks: every level cut into row chunks (intervals.hpp, "intra-level parallelism") plus the union pyramid, a
+            // serial cascade that runs next to them.  A chunk yields partial cells_and_ghosts / prediction-ghost sets.
+            struct Task
             {
-                if (t == nlev)
+                int level;
+                size_t r0, r1;
+                LevelSet cag, add1, add2;
+            };
+            std::vector<Task> tasks;
+            std::vector<std::pair<int, int>> level_tasks(nlev, {0, 0});
+            for (int l = 0; l < nlev; ++l)
+            {
+                level_tasks[l].first = static_cast<int>(tasks.size());
+                if (!cells[l].empty())
+                {
+                    const std::vector<size_t> cut = chunk_rows(cells[l], 3000, 16);
+                    for (size_t c = 0; c + 1 < cut.size(); ++c)
+                    {
+                        tasks.push_back(Task{l, cut[c], cut[c + 1], {}, {}, {}});
+                    }
+                }
+                level_tasks[l].second = static_cast<int>(tasks.size());
+            }
+            const int ntasks = static_cast<int>(tasks.size());
+#pragma omp parallel for schedule(dynamic, 1)
+            for (int t = ntasks; t >= 0; --t)
+            {
+#ifdef SMR_PLAN_TIMING
+                const double tl0 = omp_get_wtime();
+#endif
+                if (t == ntasks)
                 {
                     for (int l = L; l >= 1; --l)
                     {
                         uni[l - 1] = coarsen(set_union(cells[l], uni[l]), 1, dim);
                     }
+#ifdef SMR_PLAN_TIMING
+                    tlev[nlev] = omp_get_wtime() - tl0;
+#endif
                     continue;
                 }
-                const int l = t;
-                cag[l]      = expand(cells[l], msr, dim);
-                if (multi && l >= 1 && !cells[l].empty())
+                Task& tk    = tasks[t];
+                const int l = tk.level;
+                const bool whole = tk.r0 == 0 && tk.r1 == cells[l].rows();
+                LevelSet part_storage;
+                if (!whole)
                 {
-                    add1[l] = in_domain(expand(coarsen(cag[l], 1, dim), pr, dim), l - 1, pr);
+                    part_storage = slice_rows(cells[l], tk.r0, tk.r1);
+                }
+                const LevelSet& part = whole ? cells[l] : part_storage;
+                tk.cag               = expand(part, msr, dim);
+                if (multi && l >= 1)
+                {
+                    tk.add1 = in_domain(expand(coarsen(tk.cag, 1, dim), pr, dim), l - 1, pr);
                     if (l - 1 > 0)
                     {
-                        add2[l] = expand(coarsen(cells[l], 2, dim), pr, dim);
+                        tk.add2 = expand(coarsen(part, 2, dim), pr, dim);
                     }
                 }
+#ifdef SMR_PLAN_TIMING
+#pragma omp atomic
+                tlev[l] += omp_get_wtime() - tl0;
+#endif
             }
+#pragma omp parallel for schedule(dynamic, 1)
+            for (int t = 3 * nlev - 1; t >= 0; --t)
+            {
+                const int l = t / 3, what = t % 3;
+                std::vector<const LevelSet*> parts;
+                for (int k = level_tasks[l].first; k < level_tasks[l].second; ++k)
+                {
+                    parts.push_back(what == 0 ? &tasks[k].cag : (what == 1 ? &tasks[k].add1 : &tasks[k].add2));
+                }
+                if (parts.size() == 1)
+                {
+                    LevelSet& src = what == 0 ? tasks[level_tasks[l].first].cag : (what == 1 ? tasks[level_tasks[l].first].add1 : tasks[level_tasks[l].first].add2);
+                    (what == 0 ? cag[l] : (what == 1 ? add1[l] : add2[l])) = std::move(src);
+                }
+                else if (!parts.empty())
+                {
+                    (what == 0 ? cag[l] : (what == 1 ? add1[l] : add2[l])) = union_all(parts);
+                }
+            }
+#ifdef SMR_PLAN_TIMING
+            const double tb1 = omp_get_wtime();
+#endif
             ref.assign(nlev, LevelSet());
 #pragma omp parallel for schedule(dynamic, 1)
             for (int l = nlev - 1; l >= 0; --l)
@@ -223,6 +294,9 @@ namespace smr
                 }
                 ref[l] = std::move(r);
             }
+#ifdef SMR_PLAN_TIMING
+            const double tb2 = omp_get_wtime();
+#endif
             if (multi)
             {
                 int l = 0;
@@ -246,15 +320,22 @@ namespace smr
                 {
                     if (!ref[l].empty())
                     {
-                        proj[l] = set_inter(ref[l], uni[l]);
+                        proj[l] = par_inter(ref[l], uni[l]);
                         if (!proj[l].empty())
                         {
-                            ref[l + 1] = set_union(ref[l + 1], refine(proj[l], 1, dim));
+                            ref[l + 1] = par_union(ref[l + 1], par_rows(proj[l],
+                                                                        [dim](const LevelSet& part)
+                                                                        {
+                                                                            return refine(part, 1, dim);
+                                                                        }));
                         }
                     }
                     ++l;
                 }
             }
+#ifdef SMR_PLAN_TIMING
+            const double tb3 = omp_get_wtime();
+#endif
             // storage numbering: level ascending, then rows (z, y), then x
             level_start.assign(nlev + 1, 0);
             int64_t counter = 0;
@@ -283,6 +364,18 @@ namespace smr
             {
                 nleaves += cells[l].n_cells();
             }
+#ifdef SMR_PLAN_TIMING
+            std::printf("  mesh build: cag/add/union %.2f ms (", (tb1 - tb0) * 1e3);
+            for (int t = 0; t <= nlev; ++t)
+            {
+                if (tlev[t] > 1e-4)
+                {
+                    std::printf(" %d:%.2f", t, tlev[t] * 1e3);
+                }
+            }
+            std::printf(" ), ref union %.2f ms, proj cascade %.2f ms, numbering+locate %.2f ms\n", (tb2 - tb1) * 1e3, (tb3 - tb2) * 1e3,
+                        (omp_get_wtime() - tb3) * 1e3);
+#endif
             ++generation;
         }
     };
@@ -304,18 +397,42 @@ namespace smr
     }
 
     // update_cell_array_from_tag: tags (reference-sized, indexed by storage offset) -> new leaf sets
-    inline CellArray cells_from_tags(const Mesh& m, const uint8_t* tag)
+    // update_cell_array_from_tag: tags (reference-sized, indexed by storage offset) -> new leaf sets.
+    // `*unchanged` (optional) is set when no leaf is refined or coarsened: the result then equals m.cells.
+    inline CellArray cells_from_tags(const Mesh& m, const uint8_t* tag, bool* unchanged = nullptr)
     {
         const int dim = m.cfg.dim;
         CellArray out(m.nlev);
-        // add[l][k]: cells created at level l by the scan of level l+1 (k = 0, parents) or l-1 (k = 1, children)
-        std::vector<std::array<SetBuilder, 2>> add(m.nlev + 1);
-        std::vector<SetBuilder> rem(m.nlev);
-#pragma omp parallel for schedule(dynamic, 1)
-        for (int l = m.nlev - 1; l >= 0; --l)
+        // scan tasks: row chunks of every level; each collects the cells it removes from its level, the children it adds
+        // one level up and the parents it adds one level down
+        struct Task
         {
+            int level;
+            size_t r0, r1;
+            SetBuilder rem, up, down;
+        };
+        std::vector<Task> tasks;
+        std::vector<std::pair<int, int>> level_tasks(m.nlev, {0, 0});
+        for (int l = 0; l < m.nlev; ++l)
+        {
+            level_tasks[l].first = static_cast<int>(tasks.size());
+            if (!m.cells[l].empty())
+            {
+                const std::vector<size_t> cut = chunk_rows(m.cells[l], 2000, 16);
+                for (size_t c = 0; c + 1 < cut.size(); ++c)
+                {
+                    tasks.push_back(Task{l, cut[c], cut[c + 1], {}, {}, {}});
+                }
+            }
+            level_tasks[l].second = static_cast<int>(tasks.size());
+        }
+#pragma omp parallel for schedule(dynamic, 1)
+        for (int t = static_cast<int>(tasks.size()) - 1; t >= 0; --t)
+        {
+            Task& tk          = tasks[static_cast<size_t>(t)];
+            const int l       = tk.level;
             const LevelSet& c = m.cells[l];
-            for (size_t r = 0; r < c.rows(); ++r)
+            for (size_t r = tk.r0; r < tk.r1; ++r)
             {
                 const int y = key_y(c.key[r]), z = key_z(c.key[r]);
                 const bool yz_even = (dim < 2 || (y & 1) == 0) && (dim < 3 || (z & 1) == 0);
@@ -329,24 +446,24 @@ namespace smr
                     {
                         if (run_kind == 1)
                         {
-                            rem[l].add(c.key[r], run_start, x_end);
+                            tk.rem.add(c.key[r], run_start, x_end);
                             for (int cz = 0; cz < (dim > 2 ? 2 : 1); ++cz)
                             {
                                 for (int cy = 0; cy < (dim > 1 ? 2 : 1); ++cy)
                                 {
-                                    add[l + 1][1].add(mk_key(dim > 1 ? 2 * y + cy : 0, dim > 2 ? 2 * z + cz : 0), 2 * run_start, 2 * x_end);
+                                    tk.up.add(mk_key(dim > 1 ? 2 * y + cy : 0, dim > 2 ? 2 * z + cz : 0), 2 * run_start, 2 * x_end);
                                 }
                             }
                         }
                         else if (run_kind == 2)
                         {
-                            rem[l].add(c.key[r], run_start, x_end);
+                            tk.rem.add(c.key[r], run_start, x_end);
                             if (yz_even)
                             {
                                 // parent added once, through the even child (graduation.hpp:806-809)
                                 const int ps = (run_start + 1) >> 1; // first even x >= run_start, halved
                                 const int pe = ((x_end - 1) >> 1) + 1;
-                                add[l - 1][0].add(mk_key(y >> 1, z >> 1), ps, pe);
+                                tk.down.add(mk_key(y >> 1, z >> 1), ps, pe);
                             }
                         }
                     };
@@ -373,23 +490,124 @@ namespace smr
                 }
             }
         }
-#pragma omp parallel for schedule(dynamic, 1)
-        for (int l = m.cfg.max_level; l >= m.cfg.min_level; --l)
+        bool any = false;
+        for (const Task& tk : tasks)
         {
-            LevelSet s = m.cells[l];
-            s.off.clear();
-            for (int k = 0; k < 2; ++k)
+            any = any || !tk.rem.empty();
+        }
+        if (unchanged != nullptr)
+        {
+            *unchanged = !any;
+        }
+        if (!any && unchanged != nullptr)
+        {
+            return out; // the caller asked for the flag: it copies m.cells itself if it still needs them
+        }
+        if (!any)
+        {
+            for (int l = 0; l < m.nlev; ++l)
             {
-                if (!add[l][k].empty())
+                out[l] = m.cells[l];
+                out[l].off.clear();
+            }
+            return out;
+        }
+        // per level: the cells added (from the scans of level-1 and level+1) and removed
+        std::vector<LevelSet> add(m.nlev), rem(m.nlev);
+#pragma omp parallel for schedule(dynamic, 1)
+        for (int k = 2 * m.nlev - 1; k >= 0; --k)
+        {
+            const int l = k >> 1;
+            SetBuilder sb;
+            if (k & 1)
+            {
+                for (int t = level_tasks[l].first; t < level_tasks[l].second; ++t)
                 {
-                    s = set_union(s, add[l][k].build());
+                    sb.v.insert(sb.v.end(), tasks[static_cast<size_t>(t)].rem.v.begin(), tasks[static_cast<size_t>(t)].rem.v.end());
                 }
+                rem[l] = sb.build();
+            }
+            else
+            {
+                if (l > 0)
+                {
+                    for (int t = level_tasks[l - 1].first; t < level_tasks[l - 1].second; ++t)
+                    {
+                        sb.v.insert(sb.v.end(), tasks[static_cast<size_t>(t)].up.v.begin(), tasks[static_cast<size_t>(t)].up.v.end());
+                    }
+                }
+                if (l + 1 < m.nlev)
+                {
+                    for (int t = level_tasks[l + 1].first; t < level_tasks[l + 1].second; ++t)
+                    {
+                        sb.v.insert(sb.v.end(), tasks[static_cast<size_t>(t)].down.v.begin(), tasks[static_cast<size_t>(t)].down.v.end());
+                    }
+                }
+                add[l] = sb.build();
+            }
+        }
+        // new level = (old ∪ added) \ removed, by key-range chunks of the old level
+        struct Piece
+        {
+            int level;
+            int64_t klo, khi;
+            bool first, last;
+            LevelSet res;
+        };
+        std::vector<Piece> pieces;
+        std::vector<std::pair<int, int>> level_pieces(m.nlev, {0, 0});
+        for (int l = 0; l < m.nlev; ++l)
+        {
+            level_pieces[l].first = static_cast<int>(pieces.size());
+            if (l >= m.cfg.min_level && l <= m.cfg.max_level)
+            {
+                const LevelSet& c = m.cells[l];
+                if (c.empty())
+                {
+                    pieces.push_back(Piece{l, 0, 0, true, true, {}});
+                }
+                else
+                {
+                    const std::vector<size_t> cut = chunk_rows(c, 3000, 16);
+                    for (size_t k = 0; k + 1 < cut.size(); ++k)
+                    {
+                        pieces.push_back(Piece{l, c.key[cut[k]], k + 2 < cut.size() ? c.key[cut[k + 1]] : 0, k == 0, k + 2 == cut.size(), {}});
+                    }
+                }
+            }
+            level_pieces[l].second = static_cast<int>(pieces.size());
+        }
+        auto key_slice = [](const LevelSet& s, const Piece& pc)
+        {
+            const size_t r0 = pc.first ? 0 : static_cast<size_t>(std::lower_bound(s.key.begin(), s.key.end(), pc.klo) - s.key.begin());
+            const size_t r1 = pc.last ? s.rows() : static_cast<size_t>(std::lower_bound(s.key.begin(), s.key.end(), pc.khi) - s.key.begin());
+            return slice_rows(s, r0, r1);
+        };
+#pragma omp parallel for schedule(dynamic, 1)
+        for (int k = static_cast<int>(pieces.size()) - 1; k >= 0; --k)
+        {
+            Piece& pc   = pieces[static_cast<size_t>(k)];
+            const int l = pc.level;
+            LevelSet s  = key_slice(m.cells[l], pc);
+            if (!add[l].empty())
+            {
+                s = set_union(s, key_slice(add[l], pc));
             }
             if (!rem[l].empty())
             {
-                s = set_diff(s, rem[l].build());
+                s = set_diff(s, key_slice(rem[l], pc));
             }
-            out[l] = std::move(s);
+            pc.res = std::move(s);
+        }
+#pragma omp parallel for schedule(dynamic, 1)
+        for (int l = m.cfg.max_level; l >= m.cfg.min_level; --l)
+        {
+            std::vector<const LevelSet*> parts;
+            for (int k = level_pieces[l].first; k < level_pieces[l].second; ++k)
+            {
+                parts.push_back(&pieces[static_cast<size_t>(k)].res);
+            }
+            out[l] = union_all(parts);
         }
         return out;
     }
@@ -417,24 +635,41 @@ namespace smr
             }
             std::vector<LevelSet> out(nlev);
             bool any = false;
-            // every fine level contributes independently to the coarser levels it overlaps
-            std::vector<std::vector<LevelSet>> contrib(nlev, std::vector<LevelSet>(nlev));
-#pragma omp parallel for schedule(dynamic, 1)
+            // every row chunk of every fine level contributes independently to the coarser levels it overlaps
+            struct Task
+            {
+                int fine;
+                size_t r0, r1;
+                std::vector<LevelSet> contrib; // indexed by coarse level
+            };
+            std::vector<Task> tasks;
             for (int fine = hi; fine > lo + 1; --fine)
             {
                 if (ca[fine].empty())
                 {
                     continue;
                 }
+                const std::vector<size_t> cut = chunk_rows(ca[fine], 3000, 16);
+                for (size_t c = 0; c + 1 < cut.size(); ++c)
+                {
+                    tasks.push_back(Task{fine, cut[c], cut[c + 1], {}});
+                }
+            }
+#pragma omp parallel for schedule(dynamic, 1)
+            for (int t = 0; t < static_cast<int>(tasks.size()); ++t)
+            {
+                Task& tk       = tasks[static_cast<size_t>(t)];
+                const int fine = tk.fine;
+                tk.contrib.assign(static_cast<size_t>(nlev), LevelSet());
                 // expand(X, 2w).on(fine-2) == expand(X.on(fine-1), w).on(fine-2): 2w is even and coarse cells are aligned on
                 // multiples of 4, so the halo test x in [4c-2w, 4c+3+2w] is exactly (x>>1) in [2c-w, 2c+1+w]; coarsening
                 // first halves the rows the expansion has to merge
-                LevelSet p = coarsen(expand(coarsen(ca[fine], 1, dim), w, dim), 1, dim);
+                LevelSet p = coarsen(expand(coarsen(slice_rows(ca[fine], tk.r0, tk.r1), 1, dim), w, dim), 1, dim);
                 for (int cl = fine - 2;; --cl)
                 {
-                    if (!p.empty())
+                    if (!p.empty() && !ca[cl].empty())
                     {
-                        contrib[fine][cl] = set_inter(p, ca[cl]);
+                        tk.contrib[static_cast<size_t>(cl)] = set_inter(p, ca[cl]);
                     }
                     if (cl == lo || p.empty())
                     {
@@ -443,15 +678,21 @@ namespace smr
                     p = coarsen(p, 1, dim);
                 }
             }
+#pragma omp parallel for schedule(dynamic, 1) reduction(|| : any)
             for (int cl = lo; cl <= hi; ++cl)
             {
-                for (int fine = hi; fine > cl + 1; --fine)
+                std::vector<const LevelSet*> parts;
+                for (const Task& tk : tasks)
                 {
-                    if (!contrib[fine][cl].empty())
+                    if (!tk.contrib.empty() && !tk.contrib[static_cast<size_t>(cl)].empty())
                     {
-                        out[cl] = set_union(out[cl], contrib[fine][cl]);
-                        any     = true;
+                        parts.push_back(&tk.contrib[static_cast<size_t>(cl)]);
                     }
+                }
+                if (!parts.empty())
+                {
+                    out[cl] = union_all(parts);
+                    any     = true;
                 }
             }
             if (!any)
@@ -461,14 +702,18 @@ namespace smr
             ++nit;
             CellArray nca(nlev);
             bool changed = false;
-            for (int l = 0; l < nlev; ++l)
+#pragma omp parallel for schedule(dynamic, 1) reduction(|| : changed)
+            for (int l = nlev - 1; l >= 0; --l)
             {
-                LevelSet s = ca[l];
-                if (l > 0 && !out[l - 1].empty())
+                const bool add = l > 0 && !out[l - 1].empty();
+                const bool rem = !out[l].empty();
+                if (!add && !rem)
                 {
-                    s = set_union(s, refine(out[l - 1], 1, dim));
+                    nca[l] = std::move(ca[l]);
+                    continue;
                 }
-                if (!out[l].empty())
+                LevelSet s = add ? set_union(ca[l], refine(out[l - 1], 1, dim)) : ca[l];
+                if (rem)
                 {
                     s = set_diff(s, out[l]);
                 }
