@@ -380,18 +380,32 @@ def run_product(args):
         print(json.dumps(line), flush=True)
     elif rank == 0:
         # ---- per-family profile pass (separate from the timed region: every launch is synchronised) ----------------
+        # (a) as timed: the fused level wavefront (one cooperative launch per ghost update / harten iteration / transfer)
         sb.profile_enable(True)
-        for _ in range(2):
+        for _ in range(4):
             sim.step()
         prof = sb.profile_get()
+        wf_bytes = sb.profile_bytes("wavefront")
         sb.profile_enable(False)
         fam_time = {k: v[1] for k, v in prof.items() if v[0]}
         total_prof = sum(fam_time.values()) or 1.0
         dom = max(fam_time, key=fam_time.get)
         n_l, s_l, c_l = prof[dom]
-        achieved = alg_bytes_per_cell(dom, 2) * c_l / s_l / 1e9
+        dom_bytes = wf_bytes if dom == "wavefront" else alg_bytes_per_cell(dom, 2) * c_l
+        achieved = dom_bytes / s_l / 1e9
+        fused = {k: {"launches": v[0], "us_per_launch": 1e6 * v[1] / v[0], "units_per_launch": v[2] / v[0], "share": v[1] / total_prof,
+                     "GBps": (wf_bytes if k == "wavefront" else alg_bytes_per_cell(k, 2) * v[2]) / v[1] / 1e9} for k, v in prof.items() if v[0]}
+        # (b) the same steps with one launch per sweep, to see the kernel families separately
+        sb.set_fused(False)
+        sb.profile_enable(True)
+        for _ in range(2):
+            sim.step()
+        prof_u = sb.profile_get()
+        sb.profile_enable(False)
+        sb.set_fused(True)
+        tot_u = sum(v[1] for v in prof_u.values() if v[0]) or 1.0
         families = {k: {"launches": v[0], "us_per_launch": 1e6 * v[1] / v[0], "cells_per_launch": v[2] / v[0],
-                        "share": v[1] / total_prof, "GBps": alg_bytes_per_cell(k, 2) * v[2] / v[1] / 1e9} for k, v in prof.items() if v[0]}
+                        "share": v[1] / tot_u, "GBps": alg_bytes_per_cell(k, 2) * v[2] / v[1] / 1e9} for k, v in prof_u.items() if v[0]}
 
         # ---- uniform sweep (configs[4]) -----------------------------------------------------------------------------
         sweep = None
@@ -429,8 +443,11 @@ def run_product(args):
                     "d2h_bytes_per_step": int(st_e2e["d2h_bytes"] / args.steps), "ms_per_step": 1e3 * e2e_secs / args.steps},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
                          "traffic": None, "peak_source": peak_src, "share_of_device_time": fam_time[dom] / total_prof,
-                         "note": "adapted-mesh step: ~1e6 cells spread over ~100 dependent launches, launch-latency bound; see uniform_sweep for the HBM-bound shape"},
-            "kernel_families": families,
+                         "launches": n_l, "us_per_launch": 1e6 * s_l / n_l, "algorithmic_bytes_per_launch": dom_bytes / n_l,
+                         "note": "adapted-mesh step: ~1e6 cells over ~40 dependent level sweeps per launch (grid barrier between sweeps): latency bound, "
+                                 "the working set lives in L2; see uniform_sweep for the HBM-bound shape"},
+            "kernel_families_fused": fused,
+            "kernel_families_per_sweep_launches": families,
             "uniform_sweep": sweep,
             "cpu_baseline": cpu,
             "clocks": clocks,

@@ -187,9 +187,16 @@ extern "C"
 
     /* per-kernel-family profile: when enabled every launch is bracketed by CUDA events and synchronised (slow; never
      * enable it inside a timed region).  family = SMR_FAM_* of csrc/items.h: 0 fv, 1 projection, 2 prediction,
-     * 3 detail, 4 criteria, 5 maximum, 6 bc, 7 copy, 8 keep, 9 init. */
+     * 3 detail, 4 criteria, 5 maximum, 6 bc, 7 copy, 8 keep, 9 init, 10 fused wavefront. */
     int smr_profile_enable(int on);
     int smr_profile_get(int family, uint64_t* launches, double* seconds, uint64_t* cells);
+    /* algorithmic bytes of the fused launches of a family; 0 for the families whose bytes follow
+     * from `cells` alone.  family 10 = fused level wavefront. */
+    int smr_profile_get_bytes(int family, uint64_t* bytes);
+    /* 1 (default): ghost update, harten iteration and field transfer each run as ONE cooperative launch that walks the
+     * level wavefront with grid-wide barriers; 0: one launch per sweep (same results bit for bit; used to profile the
+     * kernel families separately).  Multi-GPU runs always use the per-sweep launches. */
+    int smr_set_fused(int on);
 
     /* host-side profiling aid: rebuild the sub-meshes and the index batches of the current leaves `reps` times
      * (no device work) and report the mean seconds of each stage */

@@ -110,10 +110,12 @@ SYMBOLS = {
     "smr_debug_host_rebuild": [_u64, _i32, _P(_dbl), _P(_dbl), _P(_i64)],
     "smr_profile_enable": [_i32],
     "smr_profile_get": [_i32, _P(_u64), _P(_dbl), _P(_u64)],
+    "smr_profile_get_bytes": [_i32, _P(_u64)],
+    "smr_set_fused": [_i32],
     "smr_field_init_ball": [_u64, _vp, _dbl, _dbl, _dbl, _i32],
 }
 
-FAMILIES = ["fv", "projection", "prediction", "detail", "criteria", "maximum", "bc", "copy", "keep", "init"]
+FAMILIES = ["fv", "projection", "prediction", "detail", "criteria", "maximum", "bc", "copy", "keep", "init", "wavefront"]
 
 _lib = None
 _initialized = None
@@ -238,6 +240,18 @@ def profile_get():
         _check(load_library().smr_profile_get(i, C.byref(n), C.byref(s), C.byref(c)))
         out[name] = (n.value, s.value, c.value)
     return out
+
+
+def profile_bytes(family="wavefront"):
+    """algorithmic bytes of the fused launches of a family accumulated since profile_enable()."""
+    b = C.c_uint64()
+    _check(load_library().smr_profile_get_bytes(FAMILIES.index(family), C.byref(b)))
+    return b.value
+
+
+def set_fused(on=True):
+    """one cooperative launch per level wavefront (default) or one launch per sweep (same results)."""
+    _check(load_library().smr_set_fused(1 if on else 0))
 
 
 class mesh_config:

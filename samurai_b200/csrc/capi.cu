@@ -246,6 +246,14 @@ namespace smr
         std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pool;
         DevBuf d_transfer;
         TransferPlan transfer; // reused so its pinned arena is allocated once
+        uint64_t prof_bytes[SMR_FAM_COUNT] = {};
+        // fused wavefront: phase / job tables go through a ring of pinned staging slots
+        bool fuse          = true;
+        int wf_grid        = 0;
+        void* wf_host      = nullptr;
+        void* wf_dev       = nullptr;
+        int wf_next        = 0;
+        cudaEvent_t wf_done[16] = {};
         // multi-GPU
         int mg_rank = 0, mg_world = 1;
         void* mg_pool            = nullptr;
@@ -606,6 +614,8 @@ namespace smr
     template <int D>
     using DetailOp1 = DetailOp<D, 1>;
     template <int D>
+    using MaximumOpR = MaximumOp<D, true>;
+    template <int D>
     using UpwindOp = FvOp<D, false>;
     template <int D>
     using BurgersOp = FvOp<D, true>;
@@ -623,6 +633,282 @@ namespace smr
         else
         {
             launch_dim<PredOp1, smr_item_pred>(SMR_FAM_PRED, dim, arena, b, -1, src, dst);
+        }
+    }
+
+    // ---- fused level wavefront (kernels.cuh: wavefront_kernel) -------------------------------------------------------
+    constexpr int WF_SLOTS      = 16;
+    constexpr size_t WF_SLOT_BYTES = 32768;
+
+    struct WfBuilder
+    {
+        std::vector<WfPhase> phases;
+        std::vector<WfJob> jobs;
+        int64_t units = 0;
+        uint64_t bytes = 0;
+        int dim       = 2;
+        bool open     = false;
+
+        void begin_phase()
+        {
+            phases.push_back(WfPhase{static_cast<int32_t>(jobs.size()), 0, 0, 0});
+            open = true;
+        }
+
+        void end_phase()
+        {
+            if (open && phases.back().n_jobs == 0)
+            {
+                phases.pop_back();
+            }
+            open = false;
+        }
+
+        // algorithmic bytes per output unit
+        uint64_t unit_bytes(int op) const
+        {
+            const int c = 1 << dim;
+            switch (op)
+            {
+                case WF_BC:
+                    return 24;
+                case WF_PROJ:
+                    return 8 * (c + 1);
+                case WF_PRED:
+                    return 8 + 8 / c + (8 % c ? 1 : 0);
+                case WF_DETAIL:
+                    return 8 * (1 + 2 * c);
+                case WF_CRITERIA:
+                    return 8 * (c + 1) + 2 * c;
+                case WF_MAXIMUM:
+                    return 2 * c + 2;
+                case WF_KEEP:
+                    return 1;
+                case WF_COPY:
+                    return 16;
+                default:
+                    return 1; // zero fill: per byte
+            }
+        }
+
+        void add(int op, const Batch& b, int field, int64_t limit = -1)
+        {
+            if (b.empty())
+            {
+                return;
+            }
+            WfJob j{};
+            j.op = op;
+            if (op == WF_BC)
+            {
+                j.n_cells = b.n_items;
+                j.n_ctas  = (b.n_items + SMR_CTA_THREADS - 1) / SMR_CTA_THREADS;
+            }
+            else
+            {
+                j.n_cells = limit < 0 ? b.n_cells : std::min(limit, b.n_cells);
+                if (j.n_cells <= 0)
+                {
+                    return;
+                }
+                if (b.cta_units != SMR_CTA_CELLS)
+                {
+                    throw std::logic_error("wavefront job laid out for a different CTA size");
+                }
+                j.n_ctas = static_cast<int32_t>((j.n_cells + SMR_CTA_CELLS - 1) / SMR_CTA_CELLS);
+            }
+            j.items     = b.items;
+            j.prefix    = b.prefix;
+            j.cta_first = b.cta_first;
+            j.aux       = b.aux;
+            j.field     = field;
+            push(j);
+        }
+
+        void add_zero(int op, int64_t nbytes)
+        {
+            if (nbytes <= 0)
+            {
+                return;
+            }
+            WfJob j{};
+            j.op      = op;
+            j.n_cells = nbytes;
+            j.n_ctas  = static_cast<int32_t>((nbytes + SMR_WF_ZERO_BYTES - 1) / SMR_WF_ZERO_BYTES);
+            push(j);
+        }
+
+        void push(const WfJob& j)
+        {
+            jobs.push_back(j);
+            phases.back().n_jobs += 1;
+            phases.back().total_ctas += j.n_ctas;
+            units += j.n_cells;
+            bytes += unit_bytes(j.op) * static_cast<uint64_t>(j.n_cells);
+        }
+    };
+
+    static bool wf_enabled()
+    {
+        return g.fuse && g.mg_world == 1;
+    }
+
+    template <int DIM, int RADIUS>
+    static void wf_launch_t(WfArgs& a, int grid)
+    {
+        void* args[] = {&a};
+        SMR_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(&wavefront_kernel<DIM, RADIUS>), dim3(static_cast<unsigned>(grid)),
+                                             dim3(SMR_CTA_THREADS), args, 0, g.stream));
+    }
+
+    template <int DIM, int RADIUS>
+    static int wf_occupancy()
+    {
+        int per_sm = 0;
+        SMR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wavefront_kernel<DIM, RADIUS>, SMR_CTA_THREADS, 0));
+        return per_sm;
+    }
+
+    // run the phases of `wb` (offsets relative to `arena`) in one cooperative launch
+    static void wf_run(WfBuilder& wb, WfArgs& a, const void* arena, int dim, int radius)
+    {
+        wb.end_phase();
+        if (wb.phases.empty())
+        {
+            return;
+        }
+        if (g.wf_host == nullptr)
+        {
+            SMR_CUDA(cudaMallocHost(&g.wf_host, WF_SLOTS * WF_SLOT_BYTES));
+            SMR_CUDA(cudaMalloc(&g.wf_dev, WF_SLOTS * WF_SLOT_BYTES));
+            for (int i = 0; i < WF_SLOTS; ++i)
+            {
+                SMR_CUDA(cudaEventCreateWithFlags(&g.wf_done[i], cudaEventDisableTiming));
+            }
+            cudaDeviceProp prop;
+            SMR_CUDA(cudaGetDeviceProperties(&prop, g.dev));
+            int per_sm = 2;
+            // the same occupancy holds for every instantiation we launch at this grid size: take the smallest
+            per_sm = std::min(per_sm, std::min(std::min(wf_occupancy<1, 1>(), wf_occupancy<2, 1>()), wf_occupancy<3, 1>()));
+            per_sm = std::min(per_sm, std::min(std::min(wf_occupancy<1, 0>(), wf_occupancy<2, 0>()), wf_occupancy<3, 0>()));
+            if (per_sm < 1)
+            {
+                throw CudaError("wavefront kernel does not fit on an SM");
+            }
+            g.wf_grid = prop.multiProcessorCount * per_sm;
+        }
+        const size_t pbytes = wb.phases.size() * sizeof(WfPhase), jbytes = wb.jobs.size() * sizeof(WfJob);
+        if (pbytes + jbytes > WF_SLOT_BYTES)
+        {
+            throw std::logic_error("wavefront table exceeds its staging slot");
+        }
+        const int slot = g.wf_next;
+        g.wf_next      = (g.wf_next + 1) % WF_SLOTS;
+        SMR_CUDA(cudaEventSynchronize(g.wf_done[slot])); // the launch that last used this slot has consumed it
+        char* h = static_cast<char*>(g.wf_host) + slot * WF_SLOT_BYTES;
+        char* d = static_cast<char*>(g.wf_dev) + slot * WF_SLOT_BYTES;
+        std::memcpy(h, wb.phases.data(), pbytes);
+        std::memcpy(h + pbytes, wb.jobs.data(), jbytes);
+        SMR_CUDA(cudaMemcpyAsync(d, h, pbytes + jbytes, cudaMemcpyHostToDevice, g.stream));
+        a.arena    = static_cast<const char*>(arena);
+        a.phases   = reinterpret_cast<const WfPhase*>(d);
+        a.jobs     = reinterpret_cast<const WfJob*>(d + pbytes);
+        a.n_phases = static_cast<int>(wb.phases.size());
+        int widest = 1;
+        for (const WfPhase& ph : wb.phases)
+        {
+            widest = std::max(widest, ph.total_ctas);
+        }
+        const int grid = std::min(g.wf_grid, widest);
+        prof_begin();
+        switch (dim * 2 + (radius ? 1 : 0))
+        {
+            case 2:
+                wf_launch_t<1, 0>(a, grid);
+                break;
+            case 3:
+                wf_launch_t<1, 1>(a, grid);
+                break;
+            case 4:
+                wf_launch_t<2, 0>(a, grid);
+                break;
+            case 5:
+                wf_launch_t<2, 1>(a, grid);
+                break;
+            case 6:
+                wf_launch_t<3, 0>(a, grid);
+                break;
+            default:
+                wf_launch_t<3, 1>(a, grid);
+                break;
+        }
+        SMR_CUDA(cudaEventRecord(g.wf_done[slot], g.stream));
+        ++g.stats.kernel_launches;
+        if (g.profile)
+        {
+            g.prof_bytes[SMR_FAM_WAVEFRONT] += wb.bytes;
+        }
+        prof_end(SMR_FAM_WAVEFRONT, wb.units);
+    }
+
+    // phases of update_ghost_mr for `fields` (algorithm/update_ghost_mr.hpp:194-237): top-down ghost phases, then the
+    // bottom-up prediction; `extra(i)` lets the caller slip independent jobs into the i-th phase
+    template <class Extra>
+    static void wf_add_ghost_phases(WfBuilder& wb, MeshObj& mo, int nfields, Extra&& extra)
+    {
+        const MeshConfig& cfg = mo.mesh.cfg;
+        int index             = 0;
+        for (int level = cfg.max_level; level >= 0; --level)
+        {
+            const GhostPhase& ph = mo.plan.down[level];
+            if (ph.bc.empty() && ph.proj.empty())
+            {
+                continue;
+            }
+            wb.begin_phase();
+            extra(index++);
+            for (int f = 0; f < nfields; ++f)
+            {
+                wb.add(WF_BC, ph.bc, f);
+                wb.add(WF_PROJ, ph.proj, f);
+            }
+            wb.end_phase();
+        }
+        for (int level = 1; level <= cfg.max_level; ++level)
+        {
+            if (mo.plan.pred[level].empty())
+            {
+                continue;
+            }
+            wb.begin_phase();
+            extra(index++);
+            for (int f = 0; f < nfields; ++f)
+            {
+                wb.add(WF_PRED, mo.plan.pred[level], f);
+            }
+            wb.end_phase();
+        }
+        // phases the caller still owes its extras to
+        for (; index < 2; ++index)
+        {
+            wb.begin_phase();
+            extra(index);
+            wb.end_phase();
+        }
+    }
+
+    static void wf_set_fields(WfArgs& a, const std::vector<FieldObj*>& fields)
+    {
+        if (fields.size() > SMR_WF_MAX_FIELDS)
+        {
+            throw std::invalid_argument("too many fields for one fused launch");
+        }
+        for (size_t i = 0; i < fields.size(); ++i)
+        {
+            a.dst[i]      = static_cast<double*>(fields[i]->data.p);
+            a.src[i]      = a.dst[i];
+            a.bc_type[i]  = fields[i]->bc_type;
+            a.bc_value[i] = fields[i]->bc_value;
         }
     }
 
@@ -646,6 +932,18 @@ namespace smr
         const MeshConfig& cfg = mo.mesh.cfg;
         double* u             = static_cast<double*>(f.data.p);
         const void* arena     = mo.d_arena.p;
+        if (wf_enabled())
+        {
+            WfBuilder wb;
+            wb.dim = cfg.dim;
+            WfArgs a{};
+            std::vector<FieldObj*> one{&f};
+            wf_set_fields(a, one);
+            wf_add_ghost_phases(wb, mo, 1, [](int) {});
+            wf_run(wb, a, arena, cfg.dim, cfg.pred_radius);
+            f.ghosts_valid = true;
+            return;
+        }
         for (int level = cfg.max_level; level >= 0; --level)
         {
             launch_ghost_phase(cfg.dim, arena, mo.plan.down[level], u, f.bc_type, f.bc_value);
@@ -722,6 +1020,34 @@ namespace smr
         }
     }
 
+    // compute_relative_detail (mr/rel_detail.hpp:73-112), one component per adapted field
+    static void relative_detail_pass(MeshObj& mo, std::vector<FieldObj*>& fields, double* detail, int64_t n)
+    {
+        const int ncomp   = static_cast<int>(fields.size());
+        const void* arena = mo.d_arena.p;
+        mo.d_relmax.ensure(sizeof(unsigned long long) * SMR_MAX_RANKS * 8);
+        unsigned long long* slots = static_cast<unsigned long long*>(mo.d_relmax.p);
+        mg_barrier();
+        SMR_CUDA(cudaMemsetAsync(slots, 0, sizeof(unsigned long long) * SMR_MAX_RANKS * 8, g.stream));
+        mg_barrier();
+        for (int c = 0; c < ncomp; ++c)
+        {
+            launch<smr_item_fv>(SMR_FAM_DETAIL, arena, mo.plan.fv, AbsMaxOp{static_cast<const double*>(fields[c]->data.p), slots + c * SMR_MAX_RANKS + g.mg_rank});
+            if (g.mg_world > 1 && g.mg_connected)
+            {
+                publish_slot_kernel<<<1, 32, 0, g.stream>>>(slots + c * SMR_MAX_RANKS);
+                SMR_CUDA(cudaGetLastError());
+                ++g.stats.kernel_launches;
+                mg_barrier();
+            }
+            const int grid = static_cast<int>(std::min<int64_t>((n + SMR_CTA_THREADS - 1) / SMR_CTA_THREADS, 148 * 16));
+            scale_detail_kernel<<<grid, SMR_CTA_THREADS, 0, g.stream>>>(detail + c * n, n, slots + c * SMR_MAX_RANKS, g.mg_world);
+            SMR_CUDA(cudaGetLastError());
+            ++g.stats.kernel_launches;
+            mg_barrier();
+        }
+    }
+
     // one harten iteration; returns true when the mesh is unchanged
     static bool do_harten(std::vector<FieldObj*>& fields, double eps, double regularity, int ite, bool relative_detail = false)
     {
@@ -743,58 +1069,6 @@ namespace smr
         const int64_t n = mo.mesh.nref;
         mo.d_detail.ensure(static_cast<size_t>(n) * sizeof(double) * ncomp);
         mo.d_tag.ensure(static_cast<size_t>(n));
-        SMR_CUDA(cudaMemsetAsync(mo.d_detail.p, 0, static_cast<size_t>(n) * sizeof(double) * ncomp, g.stream));
-        SMR_CUDA(cudaMemsetAsync(mo.d_tag.p, 0, static_cast<size_t>(n), g.stream));
-        uint8_t* tag      = static_cast<uint8_t*>(mo.d_tag.p);
-        double* detail    = static_cast<double*>(mo.d_detail.p);
-        const void* arena = mo.d_arena.p;
-        mg_barrier(); // local memsets done everywhere before any peer stores a tag
-        launch<smr_item_fv>(SMR_FAM_KEEP, arena, mo.plan.fv, KeepLeavesOp{tag, mo.filter.mask_all()});
-        for (auto* f : fields)
-        {
-            do_update_ghost(*f);
-        }
-        {
-            // detail for every coarse level < L - ite in one launch (levels are independent: mr/adapt.hpp:310-317)
-            const int64_t limit = mo.plan.detail_cum[std::max(std::min(L - ite, mo.mesh.nlev), 0)];
-            for (int c = 0; c < ncomp; ++c)
-            {
-                const double* u = static_cast<const double*>(fields[c]->data.p);
-                if (cfg.pred_radius == 0)
-                {
-                    launch_dim<DetailOp0, smr_item_detail>(SMR_FAM_DETAIL, dim, arena, mo.plan.detail, limit, u, detail + c * n);
-                }
-                else
-                {
-                    launch_dim<DetailOp1, smr_item_detail>(SMR_FAM_DETAIL, dim, arena, mo.plan.detail, limit, u, detail + c * n);
-                }
-            }
-        }
-        if (relative_detail)
-        {
-            // compute_relative_detail (mr/rel_detail.hpp:73-112), one component per adapted field
-            mo.d_relmax.ensure(sizeof(unsigned long long) * SMR_MAX_RANKS * 8);
-            unsigned long long* slots = static_cast<unsigned long long*>(mo.d_relmax.p);
-            mg_barrier();
-            SMR_CUDA(cudaMemsetAsync(slots, 0, sizeof(unsigned long long) * SMR_MAX_RANKS * 8, g.stream));
-            mg_barrier();
-            for (int c = 0; c < ncomp; ++c)
-            {
-                launch<smr_item_fv>(SMR_FAM_DETAIL, arena, mo.plan.fv, AbsMaxOp{static_cast<const double*>(fields[c]->data.p), slots + c * SMR_MAX_RANKS + g.mg_rank});
-                if (g.mg_world > 1 && g.mg_connected)
-                {
-                    publish_slot_kernel<<<1, 32, 0, g.stream>>>(slots + c * SMR_MAX_RANKS);
-                    SMR_CUDA(cudaGetLastError());
-                    ++g.stats.kernel_launches;
-                    mg_barrier();
-                }
-                const int grid = static_cast<int>(std::min<int64_t>((n + SMR_CTA_THREADS - 1) / SMR_CTA_THREADS, 148 * 16));
-                scale_detail_kernel<<<grid, SMR_CTA_THREADS, 0, g.stream>>>(detail + c * n, n, slots + c * SMR_MAX_RANKS, g.mg_world);
-                SMR_CUDA(cudaGetLastError());
-                ++g.stats.kernel_launches;
-                mg_barrier();
-            }
-        }
         TagParams tp;
         tp.min_level = lmin;
         tp.max_level = L;
@@ -816,25 +1090,116 @@ namespace smr
         {
             throw std::invalid_argument("dim*(max_level-min_level) >= 31 overflows the reference's `1 << exponent` (mr/adapt.hpp:328)");
         }
+        uint8_t* tag      = static_cast<uint8_t*>(mo.d_tag.p);
+        double* detail    = static_cast<double*>(mo.d_detail.p);
+        const void* arena = mo.d_arena.p;
+        const int64_t detail_limit   = mo.plan.detail_cum[std::max(std::min(L - ite, mo.mesh.nlev), 0)];
+        const int64_t criteria_limit = (L - ite) >= 0 ? mo.plan.tag_cum[L - ite] : 0;
+        if (wf_enabled())
         {
-            // criteria for every fine level <= L - ite in one launch (disjoint tag writes, detail is read-only)
-            const int64_t limit = (L - ite) >= 0 ? mo.plan.tag_cum[L - ite] : 0;
-            switch (dim)
+            // the whole device side of the iteration in one (two with relative detail) cooperative launch:
+            // zero fill | keep tags | ghost wavefront of every field | detail | criteria | keep propagation
+            WfArgs a{};
+            wf_set_fields(a, fields);
+            a.detail   = detail;
+            a.tag      = tag;
+            a.n        = n;
+            a.ncomp    = ncomp;
+            a.mask_all = 0;
+            a.tp       = tp;
+            WfBuilder wb;
+            wb.dim = dim;
+            wf_add_ghost_phases(wb, mo, ncomp,
+                                [&](int index)
+                                {
+                                    if (index == 0)
+                                    {
+                                        wb.add_zero(WF_ZERO_DETAIL, static_cast<int64_t>(n) * static_cast<int64_t>(sizeof(double)) * ncomp);
+                                        wb.add_zero(WF_ZERO_TAG, n);
+                                    }
+                                    else if (index == 1)
+                                    {
+                                        wb.add(WF_KEEP, mo.plan.fv, 0);
+                                    }
+                                });
+            for (auto* f : fields)
             {
-                case 1:
-                    launch<smr_item_tag>(SMR_FAM_CRITERIA, arena, mo.plan.tag_all, CriteriaOp<1>{detail, tag, tp, ncomp, n}, limit);
-                    break;
-                case 2:
-                    launch<smr_item_tag>(SMR_FAM_CRITERIA, arena, mo.plan.tag_all, CriteriaOp<2>{detail, tag, tp, ncomp, n}, limit);
-                    break;
-                default:
-                    launch<smr_item_tag>(SMR_FAM_CRITERIA, arena, mo.plan.tag_all, CriteriaOp<3>{detail, tag, tp, ncomp, n}, limit);
-                    break;
+                f->ghosts_valid = true;
             }
+            wb.begin_phase();
+            for (int c = 0; c < ncomp; ++c)
+            {
+                wb.add(WF_DETAIL, mo.plan.detail, c, detail_limit);
+            }
+            wb.end_phase();
+            if (relative_detail)
+            {
+                wf_run(wb, a, arena, dim, cfg.pred_radius);
+                wb = WfBuilder();
+                wb.dim = dim;
+                relative_detail_pass(mo, fields, detail, n);
+            }
+            wb.begin_phase();
+            wb.add(WF_CRITERIA, mo.plan.tag_all, 0, criteria_limit);
+            wb.end_phase();
+            for (int level = L; level >= 1; --level)
+            {
+                wb.begin_phase();
+                wb.add(WF_MAXIMUM, mo.plan.tag[level], 0);
+                wb.end_phase();
+            }
+            wf_run(wb, a, arena, dim, cfg.pred_radius);
         }
-        for (int level = L; level >= 1; --level)
+        else
         {
-            launch_dim<MaximumOp, smr_item_tag>(SMR_FAM_MAXIMUM, dim, arena, mo.plan.tag[level], -1, tag);
+            SMR_CUDA(cudaMemsetAsync(mo.d_detail.p, 0, static_cast<size_t>(n) * sizeof(double) * ncomp, g.stream));
+            SMR_CUDA(cudaMemsetAsync(mo.d_tag.p, 0, static_cast<size_t>(n), g.stream));
+            mg_barrier(); // local memsets done everywhere before any peer stores a tag
+            launch<smr_item_fv>(SMR_FAM_KEEP, arena, mo.plan.fv, KeepLeavesOp{tag, mo.filter.mask_all()});
+            for (auto* f : fields)
+            {
+                do_update_ghost(*f);
+            }
+            {
+                // detail for every coarse level < L - ite in one launch (levels are independent: mr/adapt.hpp:310-317)
+                const int64_t limit = mo.plan.detail_cum[std::max(std::min(L - ite, mo.mesh.nlev), 0)];
+                for (int c = 0; c < ncomp; ++c)
+                {
+                    const double* u = static_cast<const double*>(fields[c]->data.p);
+                    if (cfg.pred_radius == 0)
+                    {
+                        launch_dim<DetailOp0, smr_item_detail>(SMR_FAM_DETAIL, dim, arena, mo.plan.detail, limit, u, detail + c * n);
+                    }
+                    else
+                    {
+                        launch_dim<DetailOp1, smr_item_detail>(SMR_FAM_DETAIL, dim, arena, mo.plan.detail, limit, u, detail + c * n);
+                    }
+                }
+            }
+            if (relative_detail)
+            {
+                relative_detail_pass(mo, fields, detail, n);
+            }
+            {
+                // criteria for every fine level <= L - ite in one launch (disjoint tag writes, detail is read-only)
+                const int64_t limit = (L - ite) >= 0 ? mo.plan.tag_cum[L - ite] : 0;
+                switch (dim)
+                {
+                    case 1:
+                        launch<smr_item_tag>(SMR_FAM_CRITERIA, arena, mo.plan.tag_all, CriteriaOp<1>{detail, tag, tp, ncomp, n}, limit);
+                        break;
+                    case 2:
+                        launch<smr_item_tag>(SMR_FAM_CRITERIA, arena, mo.plan.tag_all, CriteriaOp<2>{detail, tag, tp, ncomp, n}, limit);
+                        break;
+                    default:
+                        launch<smr_item_tag>(SMR_FAM_CRITERIA, arena, mo.plan.tag_all, CriteriaOp<3>{detail, tag, tp, ncomp, n}, limit);
+                        break;
+                }
+            }
+            for (int level = L; level >= 1; --level)
+            {
+                launch_dim<MaximumOpR, smr_item_tag>(SMR_FAM_MAXIMUM, dim, arena, mo.plan.tag[level], -1, tag);
+            }
         }
         mo.h_tag.ensure(static_cast<size_t>(n));
         SMR_CUDA(cudaMemcpyAsync(mo.h_tag.p, tag, static_cast<size_t>(n), cudaMemcpyDeviceToHost, g.stream));
@@ -912,16 +1277,37 @@ namespace smr
         }
         Section sec2;
         upload_arena(tpn.arena, d_tr);
-        for (auto* f : fields)
+        if (wf_enabled() && fields.size() <= SMR_WF_MAX_FIELDS)
         {
-            DevBuf* nb = &f->spare;
-            SMR_CUDA(cudaMemsetAsync(nb->p, 0, static_cast<size_t>(nn) * sizeof(double), g.stream));
-            mg_barrier();
-            const double* src = static_cast<const double*>(f->data.p);
-            double* dst       = static_cast<double*>(nb->p);
-            launch<smr_item_copy>(SMR_FAM_COPY, d_tr.p, tpn.copy, CopyOp{src, dst});
-            launch_dim<ProjOp, smr_item_proj>(SMR_FAM_PROJ, dim, d_tr.p, tpn.proj, -1, src, dst);
-            launch_pred(dim, cfg.pred_radius, d_tr.p, tpn.pred, src, dst);
+            // copy / projection / prediction of every field: independent jobs of one phase, one launch
+            WfArgs a{};
+            WfBuilder wb;
+            wb.dim = dim;
+            wb.begin_phase();
+            for (size_t i = 0; i < fields.size(); ++i)
+            {
+                SMR_CUDA(cudaMemsetAsync(fields[i]->spare.p, 0, static_cast<size_t>(nn) * sizeof(double), g.stream));
+                a.src[i] = static_cast<const double*>(fields[i]->data.p);
+                a.dst[i] = static_cast<double*>(fields[i]->spare.p);
+                wb.add(WF_COPY, tpn.copy, static_cast<int>(i));
+                wb.add(WF_PROJ, tpn.proj, static_cast<int>(i));
+                wb.add(WF_PRED, tpn.pred, static_cast<int>(i));
+            }
+            wf_run(wb, a, d_tr.p, dim, cfg.pred_radius);
+        }
+        else
+        {
+            for (auto* f : fields)
+            {
+                DevBuf* nb = &f->spare;
+                SMR_CUDA(cudaMemsetAsync(nb->p, 0, static_cast<size_t>(nn) * sizeof(double), g.stream));
+                mg_barrier();
+                const double* src = static_cast<const double*>(f->data.p);
+                double* dst       = static_cast<double*>(nb->p);
+                launch<smr_item_copy>(SMR_FAM_COPY, d_tr.p, tpn.copy, CopyOp{src, dst});
+                launch_dim<ProjOp, smr_item_proj>(SMR_FAM_PROJ, dim, d_tr.p, tpn.proj, -1, src, dst);
+                launch_pred(dim, cfg.pred_radius, d_tr.p, tpn.pred, src, dst);
+            }
         }
         sec2.close();
         for (size_t i = 0; i < fields.size(); ++i)
@@ -1989,7 +2375,27 @@ extern "C"
             g.prof_seconds[f]  = 0;
             g.prof_launches[f] = 0;
             g.prof_cells[f]    = 0;
+            g.prof_bytes[f]    = 0;
         }
+        return SMR_OK;
+    }
+
+    int smr_profile_get_bytes(int family, uint64_t* bytes)
+    {
+        return guarded(
+            [&]
+            {
+                if (family < 0 || family >= SMR_FAM_COUNT)
+                {
+                    throw std::invalid_argument("invalid kernel family");
+                }
+                *bytes = g.prof_bytes[family];
+            });
+    }
+
+    int smr_set_fused(int on)
+    {
+        g.fuse = on != 0;
         return SMR_OK;
     }
 

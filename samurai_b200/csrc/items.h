@@ -30,6 +30,7 @@ enum
     SMR_FAM_COPY,
     SMR_FAM_KEEP,
     SMR_FAM_INIT,
+    SMR_FAM_WAVEFRONT, /* fused level wavefront (ghost update / harten iteration / field transfer in one launch) */
     SMR_FAM_COUNT
 };
 

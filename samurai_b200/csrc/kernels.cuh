@@ -17,6 +17,7 @@
 #define STRIP_MIN_BLOCKS 6
 #endif
 
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 namespace smr
@@ -78,6 +79,19 @@ namespace smr
         }
     }
 
+    // Field pointers of an op: __restrict__ (read-only data path, loads hoisted above stores) when the op runs as its own
+    // launch; plain when it runs inside the fused wavefront kernel, where other phases of the same launch write the arrays
+    template <class T, bool R>
+    struct PtrOf
+    {
+        using type = T* __restrict__;
+    };
+    template <class T>
+    struct PtrOf<T, false>
+    {
+        using type = T*;
+    };
+
     template <class Item>
     struct BatchView
     {
@@ -88,12 +102,12 @@ namespace smr
     };
 
     // body of one CTA of a batch: output units [cta * U, (cta + 1) * U) ∩ [0, n_cells), U = 256 * Op::units_per_thread
+    // `s_prefix`: shared staging for SMR_CTA_THREADS * Op::units_per_thread + 2 entries, owned by the calling kernel
     template <class Item, class Op>
-    __device__ __forceinline__ void run_batch_cta(const BatchView<Item>& b, const Op& op, int cta)
+    __device__ __forceinline__ void run_batch_cta(const BatchView<Item>& b, const Op& op, int cta, int32_t* s_prefix)
     {
         constexpr int UPT   = Op::units_per_thread;
         constexpr int UNITS = SMR_CTA_THREADS * UPT;
-        __shared__ int32_t s_prefix[UNITS + 2];
         const int first    = b.cta_first[cta];
         const int nloc     = b.cta_first[cta + 1] - first + 1;
         const int64_t base = static_cast<int64_t>(cta) * UNITS;
@@ -176,7 +190,8 @@ namespace smr
     template <class Item, class Op>
     __global__ void __launch_bounds__(SMR_CTA_THREADS, Op::min_blocks) batch_kernel(BatchView<Item> b, Op op)
     {
-        run_batch_cta(b, op, blockIdx.x);
+        __shared__ int32_t s_prefix[SMR_CTA_THREADS * Op::units_per_thread + 2];
+        run_batch_cta(b, op, blockIdx.x, s_prefix);
     }
 
     // ------------------------------------------------------------------------------------------------------------
@@ -686,15 +701,15 @@ namespace smr
     // ------------------------------------------------------------------------------------------------------------
     // detail (mr/operators.hpp:146-175, 226-358, 360-533)
     // ------------------------------------------------------------------------------------------------------------
-    template <int DIM, int RADIUS>
+    template <int DIM, int RADIUS, bool RESTRICT = true>
     struct DetailOp
     {
         static constexpr bool two_phase = false;
         static constexpr int min_blocks = 1;
         static constexpr int units_per_thread = SMR_CELLS_PER_THREAD;
 
-        const double* __restrict__ f;
-        double* __restrict__ detail;
+        typename PtrOf<const double, RESTRICT>::type f;
+        typename PtrOf<double, RESTRICT>::type detail;
 
         __device__ __forceinline__ void operator()(const smr_item_detail& it, int k) const
         {
@@ -774,15 +789,15 @@ namespace smr
         int min_level, max_level;
     };
 
-    template <int DIM>
+    template <int DIM, bool RESTRICT = true>
     struct CriteriaOp
     {
         static constexpr bool two_phase = false;
         static constexpr int min_blocks = 1;
         static constexpr int units_per_thread = SMR_CELLS_PER_THREAD;
 
-        const double* __restrict__ detail; // ncomp arrays of `stride` entries (one per adapted field)
-        uint8_t* __restrict__ tag;
+        typename PtrOf<const double, RESTRICT>::type detail; // ncomp arrays of `stride` entries (one per adapted field)
+        typename PtrOf<uint8_t, RESTRICT>::type tag;
         TagParams p;
         int ncomp;
         int64_t stride;
@@ -853,14 +868,14 @@ namespace smr
         }
     };
 
-    template <int DIM>
+    template <int DIM, bool RESTRICT = true>
     struct MaximumOp
     {
         static constexpr bool two_phase = false;
         static constexpr int min_blocks = 1;
         static constexpr int units_per_thread = SMR_CELLS_PER_THREAD;
 
-        uint8_t* __restrict__ tag;
+        typename PtrOf<uint8_t, RESTRICT>::type tag;
 
         __device__ __forceinline__ void operator()(const smr_item_tag& it, int k) const
         {
@@ -957,13 +972,14 @@ namespace smr
     }
 
     // tag[leaf] = keep (mr/adapt.hpp:286-290), driven by the FV leaf batch
-    struct KeepLeavesOp
+    template <bool RESTRICT = true>
+    struct KeepLeavesOpT
     {
         static constexpr bool two_phase = false;
         static constexpr int min_blocks = 1;
         static constexpr int units_per_thread = SMR_CELLS_PER_THREAD;
 
-        uint8_t* __restrict__ tag;
+        typename PtrOf<uint8_t, RESTRICT>::type tag;
         unsigned mask_all; // tags are replicated on every rank
 
         __device__ __forceinline__ void operator()(const smr_item_fv& it, int k) const
@@ -971,6 +987,8 @@ namespace smr
             mstore(tag + it.c + k, static_cast<uint8_t>(1), mask_all);
         }
     };
+
+    using KeepLeavesOp = KeepLeavesOpT<true>;
 
     // u[cell] = (|center - c|^2 <= r^2) ? inside : outside   -- the demos' initial condition
     // (demos/FiniteVolume/advection_2d.cpp:23-45, advection_3d.cpp:32-45, scalar_burgers_2d.cpp:20-50)
@@ -1013,20 +1031,23 @@ namespace smr
         }
     };
 
-    struct CopyOp
+    template <bool RESTRICT = true>
+    struct CopyOpT
     {
         static constexpr bool two_phase = false;
         static constexpr int min_blocks = 1;
         static constexpr int units_per_thread = SMR_CELLS_PER_THREAD;
 
-        const double* __restrict__ src;
-        double* __restrict__ dst;
+        typename PtrOf<const double, RESTRICT>::type src;
+        typename PtrOf<double, RESTRICT>::type dst;
 
         __device__ __forceinline__ void operator()(const smr_item_copy& it, int k) const
         {
             mstore(dst + it.dst + k, src[it.src + k], static_cast<unsigned>(it.mask));
         }
     };
+
+    using CopyOp = CopyOpT<true>;
 
     // ------------------------------------------------------------------------------------------------------------
     // boundary ghosts: one thread per ghost cell (update_outer_ghost.hpp, bc/dirichlet.hpp:29, bc/neumann.hpp:27-28)
@@ -1085,13 +1106,160 @@ namespace smr
     template <int DIM>
     __global__ void __launch_bounds__(SMR_CTA_THREADS) ghost_phase_kernel(BcView bc, int bc_ctas, BatchView<smr_item_proj> pv, double* __restrict__ f)
     {
+        __shared__ int32_t s_prefix[SMR_CTA_CELLS + 2];
         if (static_cast<int>(blockIdx.x) < bc_ctas)
         {
             run_bc(bc, f, blockIdx.x * SMR_CTA_THREADS + threadIdx.x);
         }
         else
         {
-            run_batch_cta(pv, ProjOp<DIM>{f, f}, static_cast<int>(blockIdx.x) - bc_ctas);
+            run_batch_cta(pv, ProjOp<DIM>{f, f}, static_cast<int>(blockIdx.x) - bc_ctas, s_prefix);
+        }
+    }
+
+    // ------------------------------------------------------------------------------------------------------------
+    // Fused level wavefront.  An adapted mesh of ~10^6 cells spreads a ghost update over ~2 (L+1) dependent sweeps of a
+    // few thousand cells each, and a harten iteration adds detail, criteria and L keep-propagation sweeps: as separate
+    // launches the step is bound by launch latency (profiles/r01_summary.md).  Here ONE cooperative launch walks a
+    // table of phases; a phase is a set of independent jobs (each job = one batch), the CTAs of the grid share the
+    // CTA-chunks of all jobs of the phase, and a grid-wide barrier separates phases.  Per-cell arithmetic is the ops'
+    // own operator(): results are bit-identical to the launch-per-sweep path.
+    // ------------------------------------------------------------------------------------------------------------
+    enum
+    {
+        WF_BC = 0,
+        WF_PROJ,
+        WF_PRED,
+        WF_DETAIL,
+        WF_CRITERIA,
+        WF_MAXIMUM,
+        WF_KEEP,
+        WF_ZERO_DETAIL,
+        WF_ZERO_TAG,
+        WF_COPY
+    };
+
+    struct WfJob
+    {
+        int32_t op;
+        int32_t n_ctas;
+        int64_t items, prefix, cta_first, aux; // byte offsets into the arena
+        int64_t n_cells;                       // output units (bc: records; zero: bytes)
+        int32_t field;                         // index into WfArgs::dst / src (detail: component)
+        int32_t pad;
+    };
+
+    struct WfPhase
+    {
+        int32_t first_job, n_jobs, total_ctas, pad;
+    };
+
+    #define SMR_WF_MAX_FIELDS 8
+    #define SMR_WF_ZERO_BYTES 16384 /* bytes cleared by one CTA-chunk of a WF_ZERO_* job */
+
+    struct WfArgs
+    {
+        const char* arena;
+        const WfPhase* phases;
+        const WfJob* jobs;
+        int n_phases;
+        int ncomp;
+        const double* src[SMR_WF_MAX_FIELDS]; // == dst for the ghost update, the old field for update_fields
+        double* dst[SMR_WF_MAX_FIELDS];
+        int bc_type[SMR_WF_MAX_FIELDS];
+        double bc_value[SMR_WF_MAX_FIELDS];
+        double* detail;
+        uint8_t* tag;
+        int64_t n; // reference cells (detail stride)
+        unsigned mask_all;
+        TagParams tp;
+    };
+
+    template <class Item>
+    __device__ __forceinline__ BatchView<Item> wf_view(const char* arena, const WfJob& jb)
+    {
+        return BatchView<Item>{reinterpret_cast<const Item*>(arena + jb.items), reinterpret_cast<const int64_t*>(arena + jb.prefix),
+                               reinterpret_cast<const int32_t*>(arena + jb.cta_first), jb.n_cells};
+    }
+
+    __device__ __forceinline__ void wf_zero(void* base, int64_t bytes, int chunk)
+    {
+        const int64_t lo = static_cast<int64_t>(chunk) * SMR_WF_ZERO_BYTES;
+        const int64_t hi = lo + SMR_WF_ZERO_BYTES < bytes ? lo + SMR_WF_ZERO_BYTES : bytes;
+        char* p          = static_cast<char*>(base);
+        // buffers are 256-byte aligned and chunks are multiples of 16 bytes
+        for (int64_t o = lo + 16 * static_cast<int64_t>(threadIdx.x); o + 16 <= hi; o += 16 * SMR_CTA_THREADS)
+        {
+            *reinterpret_cast<uint4*>(p + o) = make_uint4(0, 0, 0, 0);
+        }
+        const int64_t tail = lo + ((hi - lo) & ~int64_t(15));
+        if (tail + static_cast<int64_t>(threadIdx.x) < hi && threadIdx.x < 16)
+        {
+            p[tail + threadIdx.x] = 0;
+        }
+    }
+
+    template <int DIM, int RADIUS>
+    __global__ void __launch_bounds__(SMR_CTA_THREADS, 2) wavefront_kernel(WfArgs a)
+    {
+        __shared__ int32_t s_prefix[SMR_CTA_CELLS + 2];
+        cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+        for (int p = 0; p < a.n_phases; ++p)
+        {
+            const WfPhase ph = a.phases[p];
+            for (int w = blockIdx.x; w < ph.total_ctas; w += gridDim.x)
+            {
+                int j = ph.first_job, local = w;
+                while (local >= a.jobs[j].n_ctas)
+                {
+                    local -= a.jobs[j].n_ctas;
+                    ++j;
+                }
+                const WfJob jb = a.jobs[j];
+                switch (jb.op)
+                {
+                    case WF_BC:
+                    {
+                        const BcView bc{reinterpret_cast<const smr_item_bc*>(a.arena + jb.items), reinterpret_cast<const int64_t*>(a.arena + jb.aux),
+                                        static_cast<int>(jb.n_cells), a.bc_type[jb.field], a.bc_value[jb.field]};
+                        run_bc(bc, a.dst[jb.field], local * SMR_CTA_THREADS + threadIdx.x);
+                        break;
+                    }
+                    case WF_PROJ:
+                        run_batch_cta(wf_view<smr_item_proj>(a.arena, jb), ProjOp<DIM>{a.src[jb.field], a.dst[jb.field]}, local, s_prefix);
+                        break;
+                    case WF_PRED:
+                        run_batch_cta(wf_view<smr_item_pred>(a.arena, jb), PredOp<DIM, RADIUS>{a.src[jb.field], a.dst[jb.field]}, local, s_prefix);
+                        break;
+                    case WF_DETAIL:
+                        run_batch_cta(wf_view<smr_item_detail>(a.arena, jb), DetailOp<DIM, RADIUS, false>{a.dst[jb.field], a.detail + jb.field * a.n}, local,
+                                      s_prefix);
+                        break;
+                    case WF_CRITERIA:
+                        run_batch_cta(wf_view<smr_item_tag>(a.arena, jb), CriteriaOp<DIM, false>{a.detail, a.tag, a.tp, a.ncomp, a.n}, local, s_prefix);
+                        break;
+                    case WF_MAXIMUM:
+                        run_batch_cta(wf_view<smr_item_tag>(a.arena, jb), MaximumOp<DIM, false>{a.tag}, local, s_prefix);
+                        break;
+                    case WF_KEEP:
+                        run_batch_cta(wf_view<smr_item_fv>(a.arena, jb), KeepLeavesOpT<false>{a.tag, a.mask_all}, local, s_prefix);
+                        break;
+                    case WF_ZERO_DETAIL:
+                        wf_zero(a.detail, jb.n_cells, local);
+                        break;
+                    case WF_ZERO_TAG:
+                        wf_zero(a.tag, jb.n_cells, local);
+                        break;
+                    default: // WF_COPY
+                        run_batch_cta(wf_view<smr_item_copy>(a.arena, jb), CopyOpT<false>{a.src[jb.field], a.dst[jb.field]}, local, s_prefix);
+                        break;
+                }
+                __syncthreads(); // s_prefix is reused by the next chunk
+            }
+            if (p + 1 < a.n_phases)
+            {
+                grid.sync();
+            }
         }
     }
 } // namespace smr

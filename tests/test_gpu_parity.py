@@ -22,3 +22,48 @@ def test_relative_detail_matches_oracle(gpu):
     """mra_config().relative_detail(true) (mr/rel_detail.hpp:73-112): details normalised by max_leaves |u|; with an
     amplitude of 37.5 the absolute and relative criteria give different meshes, so the path is really exercised."""
     pu.run_advection_parity(dim=2, min_level=2, max_level=7, pred_radius=1, steps=3, relative_detail=True, amplitude=37.5)
+
+
+@pytest.mark.parametrize("dim,lmin,lmax,pred", [(1, 2, 8, 1), (2, 2, 7, 1), (2, 3, 7, 0), (3, 1, 4, 1)])
+def test_per_sweep_launches_match_oracle_too(gpu, dim, lmin, lmax, pred):
+    """the default path runs every level wavefront as one cooperative launch (smr_set_fused); the one-launch-per-sweep
+    path must give the same meshes and fields (it is what the multi-GPU runs and the per-family profile use)."""
+    pu.sb.set_fused(False)
+    try:
+        pu.run_advection_parity(dim=dim, min_level=lmin, max_level=lmax, pred_radius=pred, steps=3)
+    finally:
+        pu.sb.set_fused(True)
+
+
+def test_fused_and_per_sweep_paths_are_bit_identical(gpu):
+    """same run twice, fused and per-sweep: every reference cell (leaves AND ghosts) and every tag byte identical"""
+    sb = pu.sb
+    outs = []
+    for fused in (True, False):
+        sb.set_fused(fused)
+        mesh = sb.MRMesh.make_mesh([0.0, 0.0], [1.0, 1.0], pu.product_cfg(2, 3, 9, 1))
+        u = sb.make_scalar_field("u", mesh)
+        u.resize()
+        u.init_ball([0.3, 0.3], 0.2)
+        sb.make_bc(u, sb.NEUMANN, 0.25)
+        unp1 = sb.make_scalar_field("unp1", mesh)
+        adapt = sb.make_MRAdapt(u)
+        mra = sb.mra_config().epsilon(1e-4)
+        adapt(mra)
+        for _ in range(5):
+            adapt(mra)
+            sb.update_ghost_mr(u)
+            unp1.resize()
+            sb.upwind_step(unp1, u, [1.0, 0.5], 0.5 * mesh.min_cell_length())
+            sb.swap(u, unp1)
+        adapt(mra)
+        sb.update_ghost_mr(u)
+        outs.append((mesh.cell_table(sb.REFERENCE), u.download()))
+        u.destroy()
+        unp1.destroy()
+        mesh.destroy()
+    sb.set_fused(True)
+    (ta, fa), (tb, fb) = outs
+    assert all(np.array_equal(x, y) for x, y in zip(ta, tb))
+    leaves_and_ghosts = ta[2]
+    assert np.array_equal(fa[leaves_and_ghosts], fb[leaves_and_ghosts])
