@@ -252,6 +252,8 @@ namespace smr
         int wf_grid        = 0;
         void* wf_host      = nullptr;
         void* wf_dev       = nullptr;
+        unsigned* wf_barrier   = nullptr;
+        unsigned wf_barrier_at = 0;
         int wf_next        = 0;
         cudaEvent_t wf_done[16] = {};
         // multi-GPU
@@ -638,7 +640,8 @@ namespace smr
 
     // ---- fused level wavefront (kernels.cuh: wavefront_kernel) -------------------------------------------------------
     constexpr int WF_SLOTS      = 16;
-    constexpr size_t WF_SLOT_BYTES = 32768;
+    constexpr size_t WF_SLOT_BYTES = 16384; // phase + job tables of one launch (also the kernel's dynamic shared memory bound)
+    constexpr int WF_SERIAL_CTAS   = 1;     // phases of at most this many chunks are run by CTA 0 alone
 
     struct WfBuilder
     {
@@ -715,7 +718,8 @@ namespace smr
                 {
                     throw std::logic_error("wavefront job laid out for a different CTA size");
                 }
-                j.n_ctas = static_cast<int32_t>((j.n_cells + SMR_CTA_CELLS - 1) / SMR_CTA_CELLS);
+                // work items of the kernel are quarter chunks (kernels.cuh: run_batch_sub)
+                j.n_ctas = static_cast<int32_t>((j.n_cells + SMR_CTA_THREADS - 1) / SMR_CTA_THREADS);
             }
             j.items     = b.items;
             j.prefix    = b.prefix;
@@ -754,18 +758,18 @@ namespace smr
     }
 
     template <int DIM, int RADIUS>
-    static void wf_launch_t(WfArgs& a, int grid)
+    static void wf_launch_t(WfArgs& a, int grid, size_t smem)
     {
         void* args[] = {&a};
         SMR_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(&wavefront_kernel<DIM, RADIUS>), dim3(static_cast<unsigned>(grid)),
-                                             dim3(SMR_CTA_THREADS), args, 0, g.stream));
+                                             dim3(SMR_CTA_THREADS), args, smem, g.stream));
     }
 
     template <int DIM, int RADIUS>
     static int wf_occupancy()
     {
         int per_sm = 0;
-        SMR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wavefront_kernel<DIM, RADIUS>, SMR_CTA_THREADS, 0));
+        SMR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wavefront_kernel<DIM, RADIUS>, SMR_CTA_THREADS, WF_SLOT_BYTES));
         return per_sm;
     }
 
@@ -777,10 +781,26 @@ namespace smr
         {
             return;
         }
+        for (WfPhase& ph : wb.phases)
+        {
+            ph.pad = ph.total_ctas <= WF_SERIAL_CTAS ? 1 : 0;
+        }
+        static const bool trace = std::getenv("SMR_WF_TRACE") != nullptr;
+        if (trace)
+        {
+            std::fprintf(stderr, "wavefront: %zu phases, chunks per phase:", wb.phases.size());
+            for (const WfPhase& ph : wb.phases)
+            {
+                std::fprintf(stderr, " %d%s", ph.total_ctas, ph.pad ? "s" : "");
+            }
+            std::fprintf(stderr, "\n");
+        }
         if (g.wf_host == nullptr)
         {
             SMR_CUDA(cudaMallocHost(&g.wf_host, WF_SLOTS * WF_SLOT_BYTES));
             SMR_CUDA(cudaMalloc(&g.wf_dev, WF_SLOTS * WF_SLOT_BYTES));
+            SMR_CUDA(cudaMalloc(&g.wf_barrier, 256));
+            SMR_CUDA(cudaMemset(g.wf_barrier, 0, 256));
             for (int i = 0; i < WF_SLOTS; ++i)
             {
                 SMR_CUDA(cudaEventCreateWithFlags(&g.wf_done[i], cudaEventDisableTiming));
@@ -814,32 +834,51 @@ namespace smr
         a.phases   = reinterpret_cast<const WfPhase*>(d);
         a.jobs     = reinterpret_cast<const WfJob*>(d + pbytes);
         a.n_phases = static_cast<int>(wb.phases.size());
+        a.n_jobs   = static_cast<int>(wb.jobs.size());
         int widest = 1;
         for (const WfPhase& ph : wb.phases)
         {
             widest = std::max(widest, ph.total_ctas);
         }
         const int grid = std::min(g.wf_grid, widest);
+        // the kernel crosses one grid barrier per transition between phases that is not serial -> serial
+        unsigned n_barriers = 0;
+        for (size_t i = 0; i + 1 < wb.phases.size(); ++i)
+        {
+            n_barriers += (wb.phases[i].pad != 0 && wb.phases[i + 1].pad != 0) ? 0u : 1u;
+        }
+        a.barrier      = g.wf_barrier;
+        a.barrier_base = g.wf_barrier_at;
+        g.wf_barrier_at += n_barriers * static_cast<unsigned>(grid); // wraps modulo 2^32 like the device counter
+        static void* d_trace = nullptr;
+        if (trace)
+        {
+            if (d_trace == nullptr)
+            {
+                SMR_CUDA(cudaMalloc(&d_trace, 4096));
+            }
+            a.trace = static_cast<unsigned long long*>(d_trace);
+        }
         prof_begin();
         switch (dim * 2 + (radius ? 1 : 0))
         {
             case 2:
-                wf_launch_t<1, 0>(a, grid);
+                wf_launch_t<1, 0>(a, grid, pbytes + jbytes);
                 break;
             case 3:
-                wf_launch_t<1, 1>(a, grid);
+                wf_launch_t<1, 1>(a, grid, pbytes + jbytes);
                 break;
             case 4:
-                wf_launch_t<2, 0>(a, grid);
+                wf_launch_t<2, 0>(a, grid, pbytes + jbytes);
                 break;
             case 5:
-                wf_launch_t<2, 1>(a, grid);
+                wf_launch_t<2, 1>(a, grid, pbytes + jbytes);
                 break;
             case 6:
-                wf_launch_t<3, 0>(a, grid);
+                wf_launch_t<3, 0>(a, grid, pbytes + jbytes);
                 break;
             default:
-                wf_launch_t<3, 1>(a, grid);
+                wf_launch_t<3, 1>(a, grid, pbytes + jbytes);
                 break;
         }
         SMR_CUDA(cudaEventRecord(g.wf_done[slot], g.stream));
@@ -849,6 +888,18 @@ namespace smr
             g.prof_bytes[SMR_FAM_WAVEFRONT] += wb.bytes;
         }
         prof_end(SMR_FAM_WAVEFRONT, wb.units);
+        if (trace)
+        {
+            std::vector<unsigned long long> t(wb.phases.size() + 1);
+            SMR_CUDA(cudaStreamSynchronize(g.stream));
+            SMR_CUDA(cudaMemcpy(t.data(), d_trace, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+            std::fprintf(stderr, "wavefront: grid %d, total %.1f us, per phase (us):", grid, (t.back() - t.front()) * 1e-3);
+            for (size_t i = 0; i + 1 < t.size(); ++i)
+            {
+                std::fprintf(stderr, " %.1f", (t[i + 1] - t[i]) * 1e-3);
+            }
+            std::fprintf(stderr, "\n");
+        }
     }
 
     // phases of update_ghost_mr for `fields` (algorithm/update_ghost_mr.hpp:194-237): top-down ghost phases, then the

@@ -187,6 +187,51 @@ namespace smr
         }
     }
 
+    // Quarter of a chunk: output units [cta * U + sub * 256, + 256) with ONE unit per thread.  Used by the fused wavefront
+    // kernel, whose phases are latency bound (a few chunks, hundreds of idle CTAs): four CTAs share a chunk instead of one
+    // thread walking four units back to back.
+    template <class Item, class Op>
+    __device__ __forceinline__ void run_batch_sub(const BatchView<Item>& b, const Op& op, int cta, int sub, int32_t* s_prefix)
+    {
+        constexpr int UNITS = SMR_CTA_THREADS * Op::units_per_thread;
+        const int first     = b.cta_first[cta];
+        const int nloc      = b.cta_first[cta + 1] - first + 1;
+        const int64_t base  = static_cast<int64_t>(cta) * UNITS;
+        const int64_t left  = b.n_cells - base;
+        const int g         = sub * SMR_CTA_THREADS + threadIdx.x;
+        if (nloc == 1)
+        {
+            if (g < left)
+            {
+                op(b.items[first], static_cast<int>(base - b.prefix[first]) + g);
+            }
+            return;
+        }
+        for (int i = threadIdx.x; i <= nloc; i += SMR_CTA_THREADS)
+        {
+            const int64_t rel = b.prefix[first + i] - base;
+            s_prefix[i]       = rel > 2 * UNITS ? 2 * UNITS : static_cast<int32_t>(rel < -2147483647LL ? -2147483647LL : rel);
+        }
+        __syncthreads();
+        if (g < left)
+        {
+            int lo = 0, hi = nloc - 1;
+            while (lo < hi)
+            {
+                const int mid = (lo + hi + 1) >> 1;
+                if (s_prefix[mid] <= g)
+                {
+                    lo = mid;
+                }
+                else
+                {
+                    hi = mid - 1;
+                }
+            }
+            op(b.items[first + lo], g - s_prefix[lo]);
+        }
+    }
+
     template <class Item, class Op>
     __global__ void __launch_bounds__(SMR_CTA_THREADS, Op::min_blocks) batch_kernel(BatchView<Item> b, Op op)
     {
@@ -1163,6 +1208,7 @@ namespace smr
         const WfPhase* phases;
         const WfJob* jobs;
         int n_phases;
+        int n_jobs;
         int ncomp;
         const double* src[SMR_WF_MAX_FIELDS]; // == dst for the ghost update, the old field for update_fields
         double* dst[SMR_WF_MAX_FIELDS];
@@ -1172,8 +1218,35 @@ namespace smr
         uint8_t* tag;
         int64_t n; // reference cells (detail stride)
         unsigned mask_all;
+        unsigned* barrier;      // grid barrier counter (monotonic across launches)
+        unsigned barrier_base;  // its value when this launch starts
+        unsigned long long* trace; // optional: CTA 0 stamps %globaltimer at the start of every phase and at the end
         TagParams tp;
     };
+
+    __device__ __forceinline__ unsigned long long wf_now()
+    {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        return t;
+    }
+
+    // Grid-wide barrier of the cooperative launch (all CTAs co-resident): one atomic arrival per CTA on a monotonic
+    // counter, thread 0 spins until the whole grid has arrived.  Lighter than cooperative_groups' grid.sync().
+    __device__ __forceinline__ void wf_grid_barrier(unsigned* counter, unsigned target)
+    {
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            __threadfence();
+            atomicAdd(counter, 1u);
+            while (static_cast<int>(*reinterpret_cast<volatile unsigned*>(counter) - target) < 0)
+            {
+            }
+            __threadfence();
+        }
+        __syncthreads();
+    }
 
     template <class Item>
     __device__ __forceinline__ BatchView<Item> wf_view(const char* arena, const WfJob& jb)
@@ -1200,66 +1273,183 @@ namespace smr
     }
 
     template <int DIM, int RADIUS>
+    __device__ __forceinline__ void wf_chunk(const WfArgs& a, const WfJob& jb, int local, int32_t* s_prefix)
+    {
+        switch (jb.op)
+        {
+            case WF_BC:
+            {
+                const BcView bc{reinterpret_cast<const smr_item_bc*>(a.arena + jb.items), reinterpret_cast<const int64_t*>(a.arena + jb.aux),
+                                static_cast<int>(jb.n_cells), a.bc_type[jb.field], a.bc_value[jb.field]};
+                run_bc(bc, a.dst[jb.field], local * SMR_CTA_THREADS + threadIdx.x);
+                break;
+            }
+            case WF_PROJ:
+                run_batch_sub(wf_view<smr_item_proj>(a.arena, jb), ProjOp<DIM>{a.src[jb.field], a.dst[jb.field]}, local >> 2, local & 3, s_prefix);
+                break;
+            case WF_PRED:
+                run_batch_sub(wf_view<smr_item_pred>(a.arena, jb), PredOp<DIM, RADIUS>{a.src[jb.field], a.dst[jb.field]}, local >> 2, local & 3, s_prefix);
+                break;
+            case WF_DETAIL:
+                run_batch_sub(wf_view<smr_item_detail>(a.arena, jb), DetailOp<DIM, RADIUS, false>{a.dst[jb.field], a.detail + jb.field * a.n}, local >> 2, local & 3, s_prefix);
+                break;
+            case WF_CRITERIA:
+                run_batch_sub(wf_view<smr_item_tag>(a.arena, jb), CriteriaOp<DIM, false>{a.detail, a.tag, a.tp, a.ncomp, a.n}, local >> 2, local & 3, s_prefix);
+                break;
+            case WF_MAXIMUM:
+                run_batch_sub(wf_view<smr_item_tag>(a.arena, jb), MaximumOp<DIM, false>{a.tag}, local >> 2, local & 3, s_prefix);
+                break;
+            case WF_KEEP:
+                run_batch_sub(wf_view<smr_item_fv>(a.arena, jb), KeepLeavesOpT<false>{a.tag, a.mask_all}, local >> 2, local & 3, s_prefix);
+                break;
+            case WF_ZERO_DETAIL:
+                wf_zero(a.detail, jb.n_cells, local);
+                break;
+            case WF_ZERO_TAG:
+                wf_zero(a.tag, jb.n_cells, local);
+                break;
+            default: // WF_COPY
+                run_batch_sub(wf_view<smr_item_copy>(a.arena, jb), CopyOpT<false>{a.src[jb.field], a.dst[jb.field]}, local >> 2, local & 3, s_prefix);
+                break;
+        }
+    }
+
+    __device__ __forceinline__ void wf_prefetch_range(const char* base, int64_t lo, int64_t hi)
+    {
+        lo &= ~int64_t(127);
+        hi = hi - lo > 32768 ? lo + 32768 : hi; // the head of a long record list is enough to start the chunk
+        for (int64_t o = lo + 128 * static_cast<int64_t>(threadIdx.x); o < hi; o += 128 * SMR_CTA_THREADS)
+        {
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(base + o));
+        }
+    }
+
+    // Pull the index data (CTA table, prefix slice, records) of chunk `w` of phase `ph` into L1 while the CTA is about to
+    // wait at the barrier: after the barrier the chunk starts with cache hits instead of a chain of four L2 round trips.
+    // Only the read-only arena is touched, never field data (which the phases in flight are still writing).
+    __device__ __forceinline__ void wf_prefetch(const WfArgs& a, const WfJob* jobs, const WfPhase& ph, int w)
+    {
+        if (w >= ph.total_ctas)
+        {
+            return;
+        }
+        int j = ph.first_job, local = w;
+        while (local >= jobs[j].n_ctas)
+        {
+            local -= jobs[j].n_ctas;
+            ++j;
+        }
+        const WfJob& jb = jobs[j];
+        int isz;
+        switch (jb.op)
+        {
+            case WF_BC:
+                wf_prefetch_range(a.arena + jb.items, static_cast<int64_t>(local) * SMR_CTA_THREADS * sizeof(smr_item_bc),
+                                  static_cast<int64_t>(local + 1) * SMR_CTA_THREADS * sizeof(smr_item_bc));
+                return;
+            case WF_PROJ:
+                isz = sizeof(smr_item_proj);
+                break;
+            case WF_PRED:
+                isz = sizeof(smr_item_pred);
+                break;
+            case WF_DETAIL:
+                isz = sizeof(smr_item_detail);
+                break;
+            case WF_CRITERIA:
+            case WF_MAXIMUM:
+                isz = sizeof(smr_item_tag);
+                break;
+            case WF_KEEP:
+                isz = sizeof(smr_item_fv);
+                break;
+            case WF_COPY:
+                isz = sizeof(smr_item_copy);
+                break;
+            default:
+                return;
+        }
+        const int32_t* cf = reinterpret_cast<const int32_t*>(a.arena + jb.cta_first);
+        const int first = cf[local >> 2], last = cf[(local >> 2) + 1];
+        wf_prefetch_range(a.arena + jb.prefix, static_cast<int64_t>(first) * 8, static_cast<int64_t>(last + 2) * 8);
+        wf_prefetch_range(a.arena + jb.items, static_cast<int64_t>(first) * isz, static_cast<int64_t>(last + 1) * isz);
+    }
+
+    // Dynamic shared memory: the phase and job tables (loaded once).  A phase flagged `serial` (a handful of chunks: the
+    // coarse levels) is run by CTA 0 alone and needs no grid barrier before the next serial phase, only a CTA barrier.
+    template <int DIM, int RADIUS>
     __global__ void __launch_bounds__(SMR_CTA_THREADS, 2) wavefront_kernel(WfArgs a)
     {
         __shared__ int32_t s_prefix[SMR_CTA_CELLS + 2];
-        cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+        extern __shared__ __align__(16) unsigned char s_tab[];
+        unsigned barriers = 0;
+        {
+            // phases and jobs are contiguous in the staging slot
+            const int words        = (a.n_phases * static_cast<int>(sizeof(WfPhase)) + a.n_jobs * static_cast<int>(sizeof(WfJob))) / 4;
+            const uint32_t* src    = reinterpret_cast<const uint32_t*>(a.phases);
+            uint32_t* dst          = reinterpret_cast<uint32_t*>(s_tab);
+            for (int i = threadIdx.x; i < words; i += SMR_CTA_THREADS)
+            {
+                dst[i] = src[i];
+            }
+            __syncthreads();
+        }
+        const WfPhase* phases = reinterpret_cast<const WfPhase*>(s_tab);
+        const WfJob* jobs     = reinterpret_cast<const WfJob*>(s_tab + a.n_phases * sizeof(WfPhase));
         for (int p = 0; p < a.n_phases; ++p)
         {
-            const WfPhase ph = a.phases[p];
-            for (int w = blockIdx.x; w < ph.total_ctas; w += gridDim.x)
+            const WfPhase ph  = phases[p];
+            const bool serial = ph.pad != 0;
+            if (a.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0)
             {
-                int j = ph.first_job, local = w;
-                while (local >= a.jobs[j].n_ctas)
+                a.trace[p] = wf_now();
+            }
+            if (!serial || blockIdx.x == 0)
+            {
+                for (int w = serial ? 0 : blockIdx.x; w < ph.total_ctas; w += serial ? 1 : gridDim.x)
                 {
-                    local -= a.jobs[j].n_ctas;
-                    ++j;
-                }
-                const WfJob jb = a.jobs[j];
-                switch (jb.op)
-                {
-                    case WF_BC:
+                    int j = ph.first_job, local = w;
+                    while (local >= jobs[j].n_ctas)
                     {
-                        const BcView bc{reinterpret_cast<const smr_item_bc*>(a.arena + jb.items), reinterpret_cast<const int64_t*>(a.arena + jb.aux),
-                                        static_cast<int>(jb.n_cells), a.bc_type[jb.field], a.bc_value[jb.field]};
-                        run_bc(bc, a.dst[jb.field], local * SMR_CTA_THREADS + threadIdx.x);
-                        break;
+                        local -= jobs[j].n_ctas;
+                        ++j;
                     }
-                    case WF_PROJ:
-                        run_batch_cta(wf_view<smr_item_proj>(a.arena, jb), ProjOp<DIM>{a.src[jb.field], a.dst[jb.field]}, local, s_prefix);
-                        break;
-                    case WF_PRED:
-                        run_batch_cta(wf_view<smr_item_pred>(a.arena, jb), PredOp<DIM, RADIUS>{a.src[jb.field], a.dst[jb.field]}, local, s_prefix);
-                        break;
-                    case WF_DETAIL:
-                        run_batch_cta(wf_view<smr_item_detail>(a.arena, jb), DetailOp<DIM, RADIUS, false>{a.dst[jb.field], a.detail + jb.field * a.n}, local,
-                                      s_prefix);
-                        break;
-                    case WF_CRITERIA:
-                        run_batch_cta(wf_view<smr_item_tag>(a.arena, jb), CriteriaOp<DIM, false>{a.detail, a.tag, a.tp, a.ncomp, a.n}, local, s_prefix);
-                        break;
-                    case WF_MAXIMUM:
-                        run_batch_cta(wf_view<smr_item_tag>(a.arena, jb), MaximumOp<DIM, false>{a.tag}, local, s_prefix);
-                        break;
-                    case WF_KEEP:
-                        run_batch_cta(wf_view<smr_item_fv>(a.arena, jb), KeepLeavesOpT<false>{a.tag, a.mask_all}, local, s_prefix);
-                        break;
-                    case WF_ZERO_DETAIL:
-                        wf_zero(a.detail, jb.n_cells, local);
-                        break;
-                    case WF_ZERO_TAG:
-                        wf_zero(a.tag, jb.n_cells, local);
-                        break;
-                    default: // WF_COPY
-                        run_batch_cta(wf_view<smr_item_copy>(a.arena, jb), CopyOpT<false>{a.src[jb.field], a.dst[jb.field]}, local, s_prefix);
-                        break;
+                    wf_chunk<DIM, RADIUS>(a, jobs[j], local, s_prefix);
+                    __syncthreads(); // s_prefix is reused by the next chunk
                 }
-                __syncthreads(); // s_prefix is reused by the next chunk
             }
             if (p + 1 < a.n_phases)
             {
-                grid.sync();
+                const WfPhase nx = phases[p + 1];
+                if (nx.pad != 0)
+                {
+                    if (blockIdx.x == 0)
+                    {
+                        for (int w = 0; w < nx.total_ctas; ++w)
+                        {
+                            wf_prefetch(a, jobs, nx, w);
+                        }
+                    }
+                }
+                else
+                {
+                    wf_prefetch(a, jobs, nx, blockIdx.x);
+                }
+                if (serial && phases[p + 1].pad != 0)
+                {
+                    __threadfence(); // CTA 0 runs the next phase too: its own writes, ordered by the CTA barrier above
+                    __syncthreads();
+                }
+                else
+                {
+                    ++barriers;
+                    wf_grid_barrier(a.barrier, a.barrier_base + barriers * gridDim.x);
+                }
             }
+        }
+        if (a.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0)
+        {
+            a.trace[a.n_phases] = wf_now();
         }
     }
 } // namespace smr
