@@ -56,17 +56,37 @@ def alg_bytes_per_cell(family, dim):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe).  NVML is read in-process
+    (nvidia_ml_py, the library nvidia-smi itself uses): an external `nvidia-smi -lms 200` loop was measured to stall this
+    process's CUDA calls by several ms per step.  Falls back to the nvidia-smi loop if NVML cannot be loaded."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, period=0.1):
         self.gpu = gpu_index
+        self.period = period
         self.proc = None
         self.lines = []
+        self.samples = []  # (sm_mhz, sm_max_mhz, reasons bitmask)
+        self.nvml = None
+        self._stop = threading.Event()
+        self.t = None
 
     def start(self):
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.gpu]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else self.gpu
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nvml = pynvml
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -75,18 +95,43 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        while not self._stop.is_set():
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+                rs = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.samples.append((float(sm), float(mx), int(rs)))
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def wait_first_sample(self, timeout=8.0):
-        """nvidia-smi's start-up (NVML initialisation) takes ~1 s and stalls CUDA calls of other processes on the same GPU
-        while it lasts: keep it out of the timed region, which then only sees the periodic 200 ms queries."""
+        """keep the sampler's start-up (NVML initialisation, ~1 s for nvidia-smi) out of the timed region"""
         t0 = time.perf_counter()
-        while self.proc is not None and not self.lines and time.perf_counter() - t0 < timeout:
-            time.sleep(0.05)
+        while not self.lines and not self.samples and time.perf_counter() - t0 < timeout and (self.proc is not None or self.nvml is not None):
+            time.sleep(0.02)
 
     def stop(self):
+        if self.nvml is not None:
+            self._stop.set()
+            self.t.join(timeout=2)
+            n = self.nvml
+            names = (("hw_slowdown", getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8)),
+                     ("hw_thermal_slowdown", getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40)),
+                     ("sw_thermal_slowdown", getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20)),
+                     ("sw_power_cap", getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4)))
+            reasons = sorted({name for _, _, rs in self.samples for name, bit in names if rs & bit})
+            sm = [x[0] for x in self.samples]
+            mx = [x[1] for x in self.samples]
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                    "samples": len(sm), "source": "nvml in-process, %.0f ms period" % (1e3 * self.period)}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.25)
@@ -109,7 +154,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi -lms 200"}
 
 
 def dist_env():
@@ -142,7 +187,7 @@ def oracle_steps(so, cfg, bc, mesh, u, n_steps, dt):
     for _ in range(n_steps):
         mesh, u = so.adapt(mesh, u, bc, ARGS.eps, 1.0)
         so.update_ghost_mr(mesh, u, bc)
-        u = so.fv_step(mesh, u, [1.0, 1.0], dt)
+        u = so.fv_step(mesh, u, [1.0] * cfg.dim, dt)
         cells += mesh.nb_cells()
     return cells, time.perf_counter() - t0, mesh, u
 
@@ -183,7 +228,8 @@ def run_reference(args):
 class Sim:
     """The advection_2d demo (demos/FiniteVolume/advection_2d.cpp:61-155) on the C ABI."""
 
-    def __init__(self, sb, args, dim=2):
+    def __init__(self, sb, args, dim=None):
+        dim = args.dim if dim is None else dim
         self.sb = sb
         self.dim = dim
         cfg = sb.mesh_config(dim, 1).min_level(args.min_level).max_level(args.max_level).max_stencil_size(2).disable_minimal_ghost_width()
@@ -196,7 +242,7 @@ class Sim:
         self.adapt = sb.make_MRAdapt(self.u)
         self.mra = sb.mra_config().epsilon(args.eps)
         self.a = [1.0] * dim
-        self.dt = 0.5 * self.mesh.min_cell_length()
+        self.dt = (0.5 if dim == 2 else 0.25) * self.mesh.min_cell_length()  # advection_2d.cpp:76 / advection_3d.cpp:76
 
     def step(self):
         sb = self.sb
@@ -310,7 +356,7 @@ def run_product(args):
         sb.mg_rebalance(sim.u)
 
     # ---- timed, device-resident ------------------------------------------------------------------------------------
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, period=args.clock_period)
     sampler.start()
     sampler.wait_first_sample()
     sb.stats(reset=True)
@@ -364,8 +410,8 @@ def run_product(args):
             "metric": METRIC, "value": cells / secs, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"advection_2d min_level={args.min_level} max_level={args.max_level} eps={args.eps} pred_radius=1 Dirichlet(0) "
-                                   f"disc r=0.2@(0.3,0.3), a=(1,1), cfl=0.5; one step = MRadaptation + update_ghost_mr + upwind + swap",
+            "config": {"workload": f"advection_{args.dim}d min_level={args.min_level} max_level={args.max_level} eps={args.eps} pred_radius=1 Dirichlet(0) "
+                                   f"ball r=0.2@(0.3,..), a=(1,..), cfl={0.5 if args.dim == 2 else 0.25}; one step = MRadaptation + update_ghost_mr + upwind + swap",
                        "leaves": leaves_now, "reference_cells": ref_now,
                        "parallelism": f"{world} leaf-balanced slabs (one per GPU), halo values stored into the peers by the producing kernels over "
                                       f"NVLink (CUDA IPC), flag barrier per phase, tags replicated; same global problem as N=1"},
@@ -391,10 +437,10 @@ def run_product(args):
         total_prof = sum(fam_time.values()) or 1.0
         dom = max(fam_time, key=fam_time.get)
         n_l, s_l, c_l = prof[dom]
-        dom_bytes = wf_bytes if dom == "wavefront" else alg_bytes_per_cell(dom, 2) * c_l
+        dom_bytes = wf_bytes if dom == "wavefront" else alg_bytes_per_cell(dom, args.dim) * c_l
         achieved = dom_bytes / s_l / 1e9
         fused = {k: {"launches": v[0], "us_per_launch": 1e6 * v[1] / v[0], "units_per_launch": v[2] / v[0], "share": v[1] / total_prof,
-                     "GBps": (wf_bytes if k == "wavefront" else alg_bytes_per_cell(k, 2) * v[2]) / v[1] / 1e9} for k, v in prof.items() if v[0]}
+                     "GBps": (wf_bytes if k == "wavefront" else alg_bytes_per_cell(k, args.dim) * v[2]) / v[1] / 1e9} for k, v in prof.items() if v[0]}
         # (b) the same steps with one launch per sweep, to see the kernel families separately
         sb.set_fused(False)
         sb.profile_enable(True)
@@ -405,7 +451,7 @@ def run_product(args):
         sb.set_fused(True)
         tot_u = sum(v[1] for v in prof_u.values() if v[0]) or 1.0
         families = {k: {"launches": v[0], "us_per_launch": 1e6 * v[1] / v[0], "cells_per_launch": v[2] / v[0],
-                        "share": v[1] / tot_u, "GBps": alg_bytes_per_cell(k, 2) * v[2] / v[1] / 1e9} for k, v in prof_u.items() if v[0]}
+                        "share": v[1] / tot_u, "GBps": alg_bytes_per_cell(k, args.dim) * v[2] / v[1] / 1e9} for k, v in prof_u.items() if v[0]}
 
         # ---- uniform sweep (configs[4]) -----------------------------------------------------------------------------
         sweep = None
@@ -426,8 +472,8 @@ def run_product(args):
             "metric": METRIC, "value": cells / secs, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"advection_2d min_level={args.min_level} max_level={args.max_level} eps={args.eps} pred_radius=1 Dirichlet(0) "
-                                   f"disc r=0.2@(0.3,0.3), a=(1,1), cfl=0.5; one step = MRadaptation + update_ghost_mr + upwind + swap",
+            "config": {"workload": f"advection_{args.dim}d min_level={args.min_level} max_level={args.max_level} eps={args.eps} pred_radius=1 Dirichlet(0) "
+                                   f"ball r=0.2@(0.3,..), a=(1,..), cfl={0.5 if args.dim == 2 else 0.25}; one step = MRadaptation + update_ghost_mr + upwind + swap",
                        "leaves": leaves_now, "reference_cells": ref_now, "parallelism": f"replicas x{world}" if world > 1 else "single GPU",
                        "l2_policy": "every kernel is launched once per mesh state; between timed steps the mesh and all index batches change; "
                                     "the uniform sweep uses a working set > L2"},
@@ -466,7 +512,7 @@ def cpu_baseline_from_state(sb, sim, args):
 
     lv, co, off = sim.mesh.cell_table(sb.CELLS)
     pu = sim.u.download()
-    cfg = so.MeshConfig(dim=2, min_level=args.min_level, max_level=args.max_level, pred_radius=1)
+    cfg = so.MeshConfig(dim=args.dim, min_level=args.min_level, max_level=args.max_level, pred_radius=1)
     cells = {int(l): np.sort(so.pack(co[lv == l])) for l in np.unique(lv)}
     omesh = so.Mesh(cfg, cells)
     ou = np.zeros(omesh.nref)
@@ -497,6 +543,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dim", type=int, default=2, help="2: advection_2d (configs[1], the headline); 3: advection_3d (configs[3])")
     ap.add_argument("--min-level", type=int, default=4)
     ap.add_argument("--max-level", type=int, default=14)
     ap.add_argument("--eps", type=float, default=2e-4)
@@ -504,6 +551,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=2)
     ap.add_argument("--ref-max-level", type=int, default=14, help="largest max_level the CPU reference arm samples")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--clock-period", type=float, default=0.1, help="seconds between NVML clock samples during the timed region")
     ARGS = ap.parse_args()
     if ARGS.impl == "reference":
         run_reference(ARGS)

@@ -825,6 +825,31 @@ namespace samurai
         scaled_upwind_expr<A, Field> rhs;
     };
 
+    // ---- flux-based schemes (schemes/fv/FV_scheme.hpp:202-238, flux_based/flux_based_scheme.hpp) ---------------------------
+    template <class Field>
+    class FluxBasedScheme;
+
+    template <class Field>
+    struct scheme_expr // scheme(u)
+    {
+        FluxBasedScheme<Field> scheme;
+        Field* u;
+    };
+
+    template <class Field>
+    struct scaled_scheme_expr // dt * scheme(u)
+    {
+        double factor;
+        scheme_expr<Field> e;
+    };
+
+    template <class Field>
+    struct scheme_step_expr // v - dt * scheme(u)
+    {
+        const Field* v;
+        scaled_scheme_expr<Field> rhs;
+    };
+
     template <class mesh_t_, class value_t = double>
     class ScalarField
     {
@@ -1001,6 +1026,26 @@ namespace samurai
             return *this;
         }
 
+        // `rhs = scheme(u)` (explicit application, out.fill(0) first: schemes/fv/explicit_FV_scheme.hpp)
+        ScalarField& operator=(const scheme_expr<ScalarField>& e)
+        {
+            static_assert(on_device, "FV schemes need a double field");
+            e.scheme.apply(*this, *e.u);
+            return *this;
+        }
+
+        // `unp1 = v - dt * scheme(u)` (field expression over the leaves, field/field_base.hpp:230-242)
+        ScalarField& operator=(const scheme_step_expr<ScalarField>& e)
+        {
+            static_assert(on_device, "FV schemes need a double field");
+            ScalarField tmp(e.rhs.e.scheme.name() + "(" + e.rhs.e.u->name() + ")", *p_mesh);
+            e.rhs.e.scheme.apply(tmp, *e.rhs.e.u);
+            b200::check(smr_field_resize(handle()));
+            b200::check(smr_field_lincomb(handle(), 1.0, e.v->device(), -e.rhs.factor, tmp.device()));
+            device_written();
+            return *this;
+        }
+
         std::vector<double> leaf_values() const
         {
             const_cast<ScalarField*>(this)->pull_host();
@@ -1099,6 +1144,124 @@ namespace samurai
     auto operator-(const ScalarField<mesh_t, double>& u, const scaled_upwind_expr<A, ScalarField<mesh_t, double>>& rhs)
     {
         return fv_step_expr<A, ScalarField<mesh_t, double>>{&u, rhs};
+    }
+
+    // ---- schemes/fv/operators/{convection_lin,convection_nonlin,diffusion}.hpp ------------------------------------------------
+    template <std::size_t dim>
+    using VelocityVector = xt::xtensor_fixed<double, xt::xshape<dim>>; // operators/convection_lin.hpp:9
+    template <std::size_t dim>
+    using DiffCoeff = xt::xtensor_fixed<double, xt::xshape<dim>>; // operators/diffusion.hpp:111
+
+    template <class Field>
+    class FluxBasedScheme
+    {
+      public:
+
+        using field_t = Field;
+
+        FluxBasedScheme(int kind, const double* params, std::string name)
+            : m_kind(kind)
+            , m_name(std::move(name))
+        {
+            for (std::size_t d = 0; d < Field::dim; ++d)
+            {
+                m_params[d] = params[d];
+            }
+        }
+
+        const std::string& name() const
+        {
+            return m_name;
+        }
+
+        void set_name(const std::string& n)
+        {
+            m_name = n;
+        }
+
+        // scheme(u): usable as `rhs = scheme(u)` and inside `v - dt * scheme(u)`
+        scheme_expr<Field> operator()(Field& u) const
+        {
+            return {*this, &u};
+        }
+
+        // scheme.apply(out, in) (schemes/fv/FV_scheme.hpp:212-238): ghosts of `in` are updated if needed, out.fill(0), then the fluxes
+        void apply(Field& out, Field& in) const
+        {
+            b200::check(smr_scheme_apply(out.device(), in.device(), m_kind, m_params, m_scale));
+            out.device_written();
+            in.device_written(); // its ghosts may just have been updated on the device
+        }
+
+        FluxBasedScheme scaled(double s) const // flux_based/algebraic_operators.hpp:7-82
+        {
+            FluxBasedScheme r(*this);
+            r.m_scale *= s;
+            r.m_name = std::to_string(s) + " * " + m_name;
+            return r;
+        }
+
+      private:
+
+        int m_kind;
+        double m_params[3] = {0, 0, 0};
+        double m_scale     = 1.0;
+        std::string m_name;
+    };
+
+    template <class Field>
+    auto make_convection_upwind(const VelocityVector<Field::dim>& velocity) // operators/convection_lin.hpp:15-89
+    {
+        double v[3] = {0, 0, 0};
+        for (std::size_t d = 0; d < Field::dim; ++d)
+        {
+            v[d] = velocity(d);
+        }
+        return FluxBasedScheme<Field>(SMR_SCHEME_CONVECTION_UPWIND, v, "convection");
+    }
+
+    template <class Field>
+    auto make_convection_upwind() // operators/convection_nonlin.hpp:24-76 (scalar field: Burgers)
+    {
+        const double v[3] = {0, 0, 0};
+        return FluxBasedScheme<Field>(SMR_SCHEME_CONVECTION_UPWIND_NONLINEAR, v, "convection(u)");
+    }
+
+    template <class Field>
+    auto make_diffusion_order2(const DiffCoeff<Field::dim>& K) // operators/diffusion.hpp:123-175
+    {
+        double k[3] = {0, 0, 0};
+        for (std::size_t d = 0; d < Field::dim; ++d)
+        {
+            k[d] = K(d);
+        }
+        return FluxBasedScheme<Field>(SMR_SCHEME_DIFFUSION_ORDER2, k, "diffusion");
+    }
+
+    template <class Field>
+    auto make_diffusion_order2(double k = 1.0) // operators/diffusion.hpp:236-252
+    {
+        DiffCoeff<Field::dim> K;
+        K.fill(k);
+        return make_diffusion_order2<Field>(K);
+    }
+
+    template <class Field>
+    auto operator*(double s, const FluxBasedScheme<Field>& scheme)
+    {
+        return scheme.scaled(s);
+    }
+
+    template <class Field>
+    auto operator*(double dt, const scheme_expr<Field>& e)
+    {
+        return scaled_scheme_expr<Field>{dt, e};
+    }
+
+    template <class mesh_t>
+    auto operator-(const ScalarField<mesh_t, double>& v, const scaled_scheme_expr<ScalarField<mesh_t, double>>& rhs)
+    {
+        return scheme_step_expr<ScalarField<mesh_t, double>>{&v, rhs};
     }
 
     // ---- algorithm/update_ghost_mr.hpp:260-270 ---------------------------------------------------------------------------

@@ -641,6 +641,7 @@ namespace smr
     // ---- fused level wavefront (kernels.cuh: wavefront_kernel) -------------------------------------------------------
     constexpr int WF_SLOTS      = 16;
     constexpr size_t WF_SLOT_BYTES = 16384; // phase + job tables of one launch (also the kernel's dynamic shared memory bound)
+    constexpr int WF_WIDE_FACTOR   = 8;     // phases above this many quarter chunks per CTA of the grid use full chunks
     constexpr int WF_SERIAL_CTAS   = 1;     // phases of at most this many chunks are run by CTA 0 alone
 
     struct WfBuilder
@@ -781,20 +782,6 @@ namespace smr
         {
             return;
         }
-        for (WfPhase& ph : wb.phases)
-        {
-            ph.pad = ph.total_ctas <= WF_SERIAL_CTAS ? 1 : 0;
-        }
-        static const bool trace = std::getenv("SMR_WF_TRACE") != nullptr;
-        if (trace)
-        {
-            std::fprintf(stderr, "wavefront: %zu phases, chunks per phase:", wb.phases.size());
-            for (const WfPhase& ph : wb.phases)
-            {
-                std::fprintf(stderr, " %d%s", ph.total_ctas, ph.pad ? "s" : "");
-            }
-            std::fprintf(stderr, "\n");
-        }
         if (g.wf_host == nullptr)
         {
             SMR_CUDA(cudaMallocHost(&g.wf_host, WF_SLOTS * WF_SLOT_BYTES));
@@ -816,6 +803,36 @@ namespace smr
                 throw CudaError("wavefront kernel does not fit on an SM");
             }
             g.wf_grid = prop.multiProcessorCount * per_sm;
+        }
+        for (WfPhase& ph : wb.phases)
+        {
+            // a phase with far more quarter chunks than CTAs is throughput bound: switch its batch jobs to full chunks
+            if (g.wf_grid > 0 && ph.total_ctas > WF_WIDE_FACTOR * g.wf_grid)
+            {
+                int total = 0;
+                for (int j = ph.first_job; j < ph.first_job + ph.n_jobs; ++j)
+                {
+                    WfJob& jb = wb.jobs[static_cast<size_t>(j)];
+                    if (jb.op != WF_BC && jb.op != WF_ZERO_DETAIL && jb.op != WF_ZERO_TAG)
+                    {
+                        jb.pad    = 1;
+                        jb.n_ctas = static_cast<int32_t>((jb.n_cells + SMR_CTA_CELLS - 1) / SMR_CTA_CELLS);
+                    }
+                    total += jb.n_ctas;
+                }
+                ph.total_ctas = total;
+            }
+            ph.pad = ph.total_ctas <= WF_SERIAL_CTAS ? 1 : 0;
+        }
+        static const bool trace = std::getenv("SMR_WF_TRACE") != nullptr;
+        if (trace)
+        {
+            std::fprintf(stderr, "wavefront: %zu phases, chunks per phase:", wb.phases.size());
+            for (const WfPhase& ph : wb.phases)
+            {
+                std::fprintf(stderr, " %d%s", ph.total_ctas, ph.pad ? "s" : "");
+            }
+            std::fprintf(stderr, "\n");
         }
         const size_t pbytes = wb.phases.size() * sizeof(WfPhase), jbytes = wb.jobs.size() * sizeof(WfJob);
         if (pbytes + jbytes > WF_SLOT_BYTES)

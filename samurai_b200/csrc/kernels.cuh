@@ -1191,7 +1191,7 @@ namespace smr
         int64_t items, prefix, cta_first, aux; // byte offsets into the arena
         int64_t n_cells;                       // output units (bc: records; zero: bytes)
         int32_t field;                         // index into WfArgs::dst / src (detail: component)
-        int32_t pad;
+        int32_t pad;                           // 1: work items are full chunks, 0: quarter chunks
     };
 
     struct WfPhase
@@ -1272,6 +1272,21 @@ namespace smr
         }
     }
 
+    // one work item of a batch job: a full chunk (`wide`: phases with far more work than CTAs, four units per thread keep
+    // more loads in flight) or a quarter chunk (latency-bound phases: one unit per thread, four CTAs share the chunk)
+    template <class Item, class Op>
+    __device__ __forceinline__ void wf_item(const BatchView<Item>& b, const Op& op, int local, bool wide, int32_t* s_prefix)
+    {
+        if (wide)
+        {
+            run_batch_cta(b, op, local, s_prefix);
+        }
+        else
+        {
+            run_batch_sub(b, op, local >> 2, local & 3, s_prefix);
+        }
+    }
+
     template <int DIM, int RADIUS>
     __device__ __forceinline__ void wf_chunk(const WfArgs& a, const WfJob& jb, int local, int32_t* s_prefix)
     {
@@ -1285,22 +1300,22 @@ namespace smr
                 break;
             }
             case WF_PROJ:
-                run_batch_sub(wf_view<smr_item_proj>(a.arena, jb), ProjOp<DIM>{a.src[jb.field], a.dst[jb.field]}, local >> 2, local & 3, s_prefix);
+                wf_item(wf_view<smr_item_proj>(a.arena, jb), ProjOp<DIM>{a.src[jb.field], a.dst[jb.field]}, local, jb.pad != 0, s_prefix);
                 break;
             case WF_PRED:
-                run_batch_sub(wf_view<smr_item_pred>(a.arena, jb), PredOp<DIM, RADIUS>{a.src[jb.field], a.dst[jb.field]}, local >> 2, local & 3, s_prefix);
+                wf_item(wf_view<smr_item_pred>(a.arena, jb), PredOp<DIM, RADIUS>{a.src[jb.field], a.dst[jb.field]}, local, jb.pad != 0, s_prefix);
                 break;
             case WF_DETAIL:
-                run_batch_sub(wf_view<smr_item_detail>(a.arena, jb), DetailOp<DIM, RADIUS, false>{a.dst[jb.field], a.detail + jb.field * a.n}, local >> 2, local & 3, s_prefix);
+                wf_item(wf_view<smr_item_detail>(a.arena, jb), DetailOp<DIM, RADIUS, false>{a.dst[jb.field], a.detail + jb.field * a.n}, local, jb.pad != 0, s_prefix);
                 break;
             case WF_CRITERIA:
-                run_batch_sub(wf_view<smr_item_tag>(a.arena, jb), CriteriaOp<DIM, false>{a.detail, a.tag, a.tp, a.ncomp, a.n}, local >> 2, local & 3, s_prefix);
+                wf_item(wf_view<smr_item_tag>(a.arena, jb), CriteriaOp<DIM, false>{a.detail, a.tag, a.tp, a.ncomp, a.n}, local, jb.pad != 0, s_prefix);
                 break;
             case WF_MAXIMUM:
-                run_batch_sub(wf_view<smr_item_tag>(a.arena, jb), MaximumOp<DIM, false>{a.tag}, local >> 2, local & 3, s_prefix);
+                wf_item(wf_view<smr_item_tag>(a.arena, jb), MaximumOp<DIM, false>{a.tag}, local, jb.pad != 0, s_prefix);
                 break;
             case WF_KEEP:
-                run_batch_sub(wf_view<smr_item_fv>(a.arena, jb), KeepLeavesOpT<false>{a.tag, a.mask_all}, local >> 2, local & 3, s_prefix);
+                wf_item(wf_view<smr_item_fv>(a.arena, jb), KeepLeavesOpT<false>{a.tag, a.mask_all}, local, jb.pad != 0, s_prefix);
                 break;
             case WF_ZERO_DETAIL:
                 wf_zero(a.detail, jb.n_cells, local);
@@ -1309,7 +1324,7 @@ namespace smr
                 wf_zero(a.tag, jb.n_cells, local);
                 break;
             default: // WF_COPY
-                run_batch_sub(wf_view<smr_item_copy>(a.arena, jb), CopyOpT<false>{a.src[jb.field], a.dst[jb.field]}, local >> 2, local & 3, s_prefix);
+                wf_item(wf_view<smr_item_copy>(a.arena, jb), CopyOpT<false>{a.src[jb.field], a.dst[jb.field]}, local, jb.pad != 0, s_prefix);
                 break;
         }
     }
@@ -1370,7 +1385,8 @@ namespace smr
                 return;
         }
         const int32_t* cf = reinterpret_cast<const int32_t*>(a.arena + jb.cta_first);
-        const int first = cf[local >> 2], last = cf[(local >> 2) + 1];
+        const int chunk = jb.pad != 0 ? local : (local >> 2);
+        const int first = cf[chunk], last = cf[chunk + 1];
         wf_prefetch_range(a.arena + jb.prefix, static_cast<int64_t>(first) * 8, static_cast<int64_t>(last + 2) * 8);
         wf_prefetch_range(a.arena + jb.items, static_cast<int64_t>(first) * isz, static_cast<int64_t>(last + 1) * isz);
     }

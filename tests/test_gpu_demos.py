@@ -50,3 +50,21 @@ def test_other_reference_demos_run(gpu, tmp_path, demo, args, ncol):
     assert data.shape[0] > 100 and np.all(np.isfinite(data))
     u = data[:, ncol - 1] if "burgers" not in demo else data[:, 3]
     assert u.min() > -1.5 and u.max() < 1.5
+
+
+def test_cpp_heat_explicit_matches_reference_golden(gpu, tmp_path):
+    """tests/cpp/heat_explicit.cpp (the explicit branch of demos/FiniteVolume/heat.cpp written against the drop-in headers:
+    make_diffusion_order2, `unp1 = u - dt * diff(u)`, Neumann<1>, MRadaptation every step) against the reference's own
+    golden file test_finite_volume_demo_heat_explicit.h5 (tests/golden/heat_explicit.npz)."""
+    exe = os.path.join(DEMOS, "heat-explicit")
+    if not os.path.exists(exe):
+        pytest.skip("heat-explicit not built")
+    r = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "steps 25" in r.stdout
+    got = _load_csv(tmp_path / "heat_explicit.csv")
+    g = np.load(os.path.join(GOLD, "heat_explicit.npz"))
+    assert got.shape[0] == g["level"].size
+    assert np.array_equal(got[:, 0].astype(np.int64), g["level"].astype(np.int64))
+    assert np.array_equal(got[:, 1:3].astype(np.int64), g["idx"].astype(np.int64)), "mesh differs"
+    assert np.max(np.abs(got[:, 3] - g["u"])) <= 1e-15
