@@ -687,6 +687,7 @@ namespace smr
                 case WF_MAXIMUM:
                     return 2 * c + 2;
                 case WF_KEEP:
+                case WF_TAGS_CHANGE:
                     return 1;
                 case WF_COPY:
                     return 16;
@@ -1136,7 +1137,8 @@ namespace smr
         Section sec1;
         const int64_t n = mo.mesh.nref;
         mo.d_detail.ensure(static_cast<size_t>(n) * sizeof(double) * ncomp);
-        mo.d_tag.ensure(static_cast<size_t>(n));
+        const int64_t flag_at = (n + 15) & ~int64_t(15); // change flag behind the tags, copied back with them
+        mo.d_tag.ensure(static_cast<size_t>(flag_at) + 16);
         TagParams tp;
         tp.min_level = lmin;
         tp.max_level = L;
@@ -1163,6 +1165,7 @@ namespace smr
         const void* arena = mo.d_arena.p;
         const int64_t detail_limit   = mo.plan.detail_cum[std::max(std::min(L - ite, mo.mesh.nlev), 0)];
         const int64_t criteria_limit = (L - ite) >= 0 ? mo.plan.tag_cum[L - ite] : 0;
+        bool fused_flag              = false;
         if (wf_enabled())
         {
             // the whole device side of the iteration in one (two with relative detail) cooperative launch:
@@ -1171,6 +1174,7 @@ namespace smr
             wf_set_fields(a, fields);
             a.detail   = detail;
             a.tag      = tag;
+            a.change_flag = reinterpret_cast<unsigned*>(tag + flag_at);
             a.n        = n;
             a.ncomp    = ncomp;
             a.mask_all = 0;
@@ -1183,7 +1187,7 @@ namespace smr
                                     if (index == 0)
                                     {
                                         wb.add_zero(WF_ZERO_DETAIL, static_cast<int64_t>(n) * static_cast<int64_t>(sizeof(double)) * ncomp);
-                                        wb.add_zero(WF_ZERO_TAG, n);
+                                        wb.add_zero(WF_ZERO_TAG, flag_at + 16);
                                     }
                                     else if (index == 1)
                                     {
@@ -1216,7 +1220,11 @@ namespace smr
                 wb.add(WF_MAXIMUM, mo.plan.tag[level], 0);
                 wb.end_phase();
             }
+            wb.begin_phase();
+            wb.add(WF_TAGS_CHANGE, mo.plan.fv, 0);
+            wb.end_phase();
             wf_run(wb, a, arena, dim, cfg.pred_radius);
+            fused_flag = true;
         }
         else
         {
@@ -1269,8 +1277,8 @@ namespace smr
                 launch_dim<MaximumOpR, smr_item_tag>(SMR_FAM_MAXIMUM, dim, arena, mo.plan.tag[level], -1, tag);
             }
         }
-        mo.h_tag.ensure(static_cast<size_t>(n));
-        SMR_CUDA(cudaMemcpyAsync(mo.h_tag.p, tag, static_cast<size_t>(n), cudaMemcpyDeviceToHost, g.stream));
+        mo.h_tag.ensure(static_cast<size_t>(flag_at) + 16);
+        SMR_CUDA(cudaMemcpyAsync(mo.h_tag.p, tag, static_cast<size_t>(fused_flag ? flag_at + 16 : n), cudaMemcpyDeviceToHost, g.stream));
         sec1.close();
         SMR_CUDA(cudaStreamSynchronize(g.stream));
         g.stats.d2h_bytes += static_cast<uint64_t>(n);
@@ -1288,7 +1296,15 @@ namespace smr
             ts = t;
         };
         bool no_tag_changes = false;
-        CellArray ca        = cells_from_tags(mo.mesh, static_cast<const uint8_t*>(mo.h_tag.p), &no_tag_changes);
+        CellArray ca;
+        if (fused_flag && mo.graduated && *reinterpret_cast<const unsigned*>(static_cast<const uint8_t*>(mo.h_tag.p) + flag_at) == 0u)
+        {
+            no_tag_changes = true; // the device already looked at every leaf tag
+        }
+        else
+        {
+            ca = cells_from_tags(mo.mesh, static_cast<const uint8_t*>(mo.h_tag.p), &no_tag_changes);
+        }
         stage(0);
         if (no_tag_changes && mo.graduated)
         {

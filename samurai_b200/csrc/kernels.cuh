@@ -1035,6 +1035,29 @@ namespace smr
 
     using KeepLeavesOp = KeepLeavesOpT<true>;
 
+    // does update_cell_array_from_tag change anything? (algorithm/graduation.hpp:743-842: a leaf is replaced when it is
+    // tagged refine below max_level, or coarsen without keep above min_level).  Lets the host skip its scan of the tags
+    // on the iteration that finds the mesh converged.
+    struct TagsChangeOp
+    {
+        static constexpr bool two_phase = false;
+        static constexpr int min_blocks = 1;
+        static constexpr int units_per_thread = SMR_CELLS_PER_THREAD;
+
+        const uint8_t* tag;
+        unsigned* flag;
+        int min_level, max_level;
+
+        __device__ __forceinline__ void operator()(const smr_item_fv& it, int k) const
+        {
+            const uint8_t t = tag[it.c + k];
+            if (((t & 4) && it.level < max_level) || ((t & 2) && !(t & 1) && it.level > min_level))
+            {
+                *flag = 1u; // benign race: every writer stores the same value
+            }
+        }
+    };
+
     // u[cell] = (|center - c|^2 <= r^2) ? inside : outside   -- the demos' initial condition
     // (demos/FiniteVolume/advection_2d.cpp:23-45, advection_3d.cpp:32-45, scalar_burgers_2d.cpp:20-50)
     template <int DIM>
@@ -1181,7 +1204,8 @@ namespace smr
         WF_KEEP,
         WF_ZERO_DETAIL,
         WF_ZERO_TAG,
-        WF_COPY
+        WF_COPY,
+        WF_TAGS_CHANGE
     };
 
     struct WfJob
@@ -1216,6 +1240,7 @@ namespace smr
         double bc_value[SMR_WF_MAX_FIELDS];
         double* detail;
         uint8_t* tag;
+        unsigned* change_flag; // set by WF_TAGS_CHANGE (lives behind the tags, cleared by WF_ZERO_TAG)
         int64_t n; // reference cells (detail stride)
         unsigned mask_all;
         unsigned* barrier;      // grid barrier counter (monotonic across launches)
@@ -1323,6 +1348,9 @@ namespace smr
             case WF_ZERO_TAG:
                 wf_zero(a.tag, jb.n_cells, local);
                 break;
+            case WF_TAGS_CHANGE:
+                wf_item(wf_view<smr_item_fv>(a.arena, jb), TagsChangeOp{a.tag, a.change_flag, a.tp.min_level, a.tp.max_level}, local, jb.pad != 0, s_prefix);
+                break;
             default: // WF_COPY
                 wf_item(wf_view<smr_item_copy>(a.arena, jb), CopyOpT<false>{a.src[jb.field], a.dst[jb.field]}, local, jb.pad != 0, s_prefix);
                 break;
@@ -1376,6 +1404,7 @@ namespace smr
                 isz = sizeof(smr_item_tag);
                 break;
             case WF_KEEP:
+            case WF_TAGS_CHANGE:
                 isz = sizeof(smr_item_fv);
                 break;
             case WF_COPY:
