@@ -1508,7 +1508,9 @@ namespace smr
         mo.mesh          = std::move(*new_mesh);
         new_mesh.reset();
         mo.invalidate_plans();
-        static const bool overlap = std::getenv("SMR_NO_PLAN_OVERLAP") == nullptr;
+        // opt-in: with one OpenMP team per host thread the two traversals oversubscribe the cores and the step got slower
+        // on the 16-core box (6.5 -> 9.5 ms); worth it only with cores to spare
+        static const bool overlap = std::getenv("SMR_PLAN_OVERLAP") != nullptr;
         if (overlap)
         {
             update_filter(mo);

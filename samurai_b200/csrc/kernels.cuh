@@ -138,8 +138,9 @@ namespace smr
                 }
                 else if constexpr (Op::warp_uniform)
                 {
-                    // all 32 lanes of every warp are active, in the same record, on consecutive cells: the op may trade
-                    // its i-1 / i+1 loads for warp shuffles
+                    // all 32 lanes of every warp are active, in the same record, on consecutive cells: an op may trade its
+                    // i-1 / i+1 loads for warp shuffles.  Tried for the strip kernels (profiles/r01_summary.md section 8): slower
+                    // than the L1 loads at 6 CTAs/SM (4.5 vs 5.0 TB/s), so no op sets warp_uniform today.
 #pragma unroll
                     for (int k = 0; k < UPT; ++k)
                     {
@@ -363,7 +364,7 @@ namespace smr
     struct FvStripOp
     {
         static constexpr bool two_phase = false;
-        static constexpr bool warp_uniform = true;
+        static constexpr bool warp_uniform = false;
         static constexpr int min_blocks = STRIP_MIN_BLOCKS;
         static constexpr int units_per_thread = STRIP_UPT;
 
@@ -378,55 +379,6 @@ namespace smr
                 return burgers_flux(p.a[d], ul, ur);
             }
             return upwind_flux(p.half_a[d], p.half_abs_a[d], ul, ur);
-        }
-
-        // all lanes of the warp active on consecutive columns of one record: the i-1 / i+1 values come from the neighbouring
-        // lanes (same doubles, so the same bits); only lanes 0 and 31 load theirs
-        __device__ __forceinline__ void warp(const smr_item_fvstrip& it, int k) const
-        {
-            constexpr int R = SMR_STRIP_ROWS;
-            const int lane  = threadIdx.x & 31;
-            double v[R + 2];
-#pragma unroll
-            for (int r = 0; r < R + 2; ++r)
-            {
-                v[r] = u[it.row[r] + k];
-            }
-            double zm[R], zp[R];
-            if (DIM > 2)
-            {
-#pragma unroll
-                for (int r = 0; r < R; ++r)
-                {
-                    zm[r] = u[it.zm[r] + k];
-                    zp[r] = u[it.zp[r] + k];
-                }
-            }
-            double em[R], ep[R]; // edge values of the warp's 32-column window
-#pragma unroll
-            for (int r = 0; r < R; ++r)
-            {
-                em[r] = lane == 0 ? u[it.row[r + 1] + k - 1] : 0.0;
-                ep[r] = lane == 31 ? u[it.row[r + 1] + k + 1] : 0.0;
-            }
-            const double inv = p.inv_dx[it.level], dx = p.dx[it.level];
-#pragma unroll
-            for (int r = 0; r < R; ++r)
-            {
-                const double uc = v[r + 1];
-                double xm       = __shfl_up_sync(0xffffffffu, uc, 1);
-                double xp       = __shfl_down_sync(0xffffffffu, uc, 1);
-                xm              = lane == 0 ? em[r] : xm;
-                xp              = lane == 31 ? ep[r] : xp;
-                double acc      = -flux(0, xm, uc) + flux(0, uc, xp);
-                acc             = (acc + -flux(1, v[r], uc)) + flux(1, uc, v[r + 2]);
-                if (DIM > 2)
-                {
-                    acc = (acc + -flux(2, zm[r], uc)) + flux(2, uc, zp[r]);
-                }
-                const double div = p.exact_inv ? acc * inv : acc / dx;
-                mstore(out + it.row[r + 1] + k, uc - p.dt * div, static_cast<unsigned>(it.mask));
-            }
         }
 
         __device__ __forceinline__ void operator()(const smr_item_fvstrip& it, int k) const
@@ -521,48 +473,13 @@ namespace smr
     struct FluxLinHomStripOp
     {
         static constexpr bool two_phase = false;
-        static constexpr bool warp_uniform = true;
+        static constexpr bool warp_uniform = false;
         static constexpr int min_blocks = STRIP_MIN_BLOCKS;
         static constexpr int units_per_thread = STRIP_UPT;
 
         const double* __restrict__ u;
         double* __restrict__ out;
         FluxParams p;
-
-        __device__ __forceinline__ void warp(const smr_item_fvstrip& it, int k) const
-        {
-            constexpr int R = SMR_STRIP_ROWS;
-            const int lane  = threadIdx.x & 31;
-            double v[R + 2];
-#pragma unroll
-            for (int r = 0; r < R + 2; ++r)
-            {
-                v[r] = u[it.row[r] + k];
-            }
-            double em[R], ep[R];
-#pragma unroll
-            for (int r = 0; r < R; ++r)
-            {
-                em[r] = lane == 0 ? u[it.row[r + 1] + k - 1] : 0.0;
-                ep[r] = lane == 31 ? u[it.row[r + 1] + k + 1] : 0.0;
-            }
-#pragma unroll
-            for (int r = 0; r < R; ++r)
-            {
-                const double uc = v[r + 1];
-                double xm       = __shfl_up_sync(0xffffffffu, uc, 1);
-                double xp       = __shfl_down_sync(0xffffffffu, uc, 1);
-                xm              = lane == 0 ? em[r] : xm;
-                xp              = lane == 31 ? ep[r] : xp;
-                double acc      = dir_terms(0.0, 0, it.x + k, xm, uc, xp);
-                acc             = dir_terms(acc, 1, it.y + r, v[r], uc, v[r + 2]);
-                if (DIM > 2)
-                {
-                    acc = dir_terms(acc, 2, it.z, u[it.zm[r] + k], uc, u[it.zp[r] + k]);
-                }
-                mstore(out + it.row[r + 1] + k, acc, static_cast<unsigned>(it.mask));
-            }
-        }
 
         __device__ __forceinline__ double dir_terms(double acc, int d, int idx, double um, double uc, double up) const
         {
