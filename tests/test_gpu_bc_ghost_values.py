@@ -1,0 +1,133 @@
+"""Closed-form boundary ghost values, restating the reference's tests/test_bc_ghost_values.cpp for the cases on the hot path
+(Dirichlet<1> / Neumann<1> with a constant value, ghost width 1; corners): a field that the boundary reconstruction is exact
+on, so every filled ghost must hold f(ghost centre) to 1e-11 -- on uniform meshes and on an adapted mesh whose boundary
+crosses several levels (`adapted_mesh`, :56-80), in 1D, 2D and 3D.  The reference applies the BC in one direction at a time
+(`apply_field_bc(u, direction)`); here the whole update_ghost_mr runs with the same constant on every side and only the
+ghosts of the tested direction are checked, as the reference does."""
+import itertools
+
+import numpy as np
+import pytest
+
+import parity_utils as pu
+
+sb = pu.sb
+pytestmark = pytest.mark.gpu
+
+
+def _uniform(dim, level):
+    return sb.MRMesh.make_mesh([0.0] * dim, [1.0] * dim, pu.product_cfg(dim, level, level, 1))
+
+
+def _adapted(dim):
+    """test_bc_ghost_values.cpp:56-80: indicator of the ball r < 0.3 around the origin corner, levels 2..5, eps 1e-4"""
+    mesh = sb.MRMesh.make_mesh([0.0] * dim, [1.0] * dim, pu.product_cfg(dim, 2, 5, 1))
+    phi = sb.make_scalar_field("phi", mesh)
+    phi.resize()
+    phi.init_ball([0.0] * dim, 0.3)
+    sb.make_bc(phi, sb.DIRICHLET, 0.0)
+    sb.make_MRAdapt(phi)(sb.mra_config().epsilon(1e-4))
+    phi.destroy()
+    return mesh
+
+
+def _centers(mesh, lv, co):
+    h = np.array([mesh.cell_length(int(l)) for l in lv])
+    return (co + 0.5) * h[:, None]
+
+
+def _fill_leaves(mesh, u, f):
+    lv, co, off = mesh.cell_table(sb.CELLS)
+    host = np.zeros(mesh.nb_cells(sb.REFERENCE))
+    host[off] = f(_centers(mesh, lv, co))
+    u.resize()
+    u.upload(host)
+    return lv, co, off
+
+
+def _check_direction(mesh, u, axis, sign, f):
+    """ghosts one layer outside the boundary leaves of every level in direction sign * e_axis (check_ghosts, :98-126)"""
+    lv, co, _ = mesh.cell_table(sb.CELLS)
+    vals = u.download()
+    nb, levels = 0, set()
+    for level in np.unique(lv):
+        n = 1 << int(level)
+        sel = (lv == level) & (co[:, axis] == (n - 1 if sign > 0 else 0))
+        ghosts = co[sel].copy()
+        ghosts[:, axis] += sign
+        h = mesh.cell_length(int(level))
+        for g in ghosts:
+            idx = [int(v) for v in g] + [0] * (3 - len(g))
+            off = mesh.get_index(int(level), *idx)
+            expect = f(((g + 0.5) * h)[None, :])[0]
+            assert abs(vals[off] - expect) < 1e-11, f"level {level} ghost {g}: {vals[off]} vs {expect}"
+            nb += 1
+        if ghosts.shape[0]:
+            levels.add(int(level))
+    assert nb > 0
+    return levels
+
+
+@pytest.mark.parametrize("dim", [1, 2, 3])
+@pytest.mark.parametrize("kind", ["uniform", "adapted"])
+@pytest.mark.parametrize("bc", ["dirichlet", "neumann"])
+def test_constant_bc_exact_on_linear_field(gpu, dim, kind, bc):
+    """dirichlet1_constant_{1,2,3}d / neumann_constant_{1,2,3}d / dirichlet1_adapted_* / neumann_adapted_* (:544-740)"""
+    if kind == "adapted" and dim == 1:
+        pytest.skip("the reference has no 1D adapted case")
+    mesh = _uniform(dim, 4 if dim < 3 else 3) if kind == "uniform" else _adapted(dim)
+    u = sb.make_scalar_field("u", mesh)
+    crossed = set()
+    for axis, sign in itertools.product(range(dim), (-1, 1)):
+        def f(x, axis=axis):
+            return 1.0 + 3.0 * x[:, axis]
+        _fill_leaves(mesh, u, f)
+        if bc == "dirichlet":
+            face = 1.0 if sign > 0 else 0.0
+            sb.make_bc(u, sb.DIRICHLET, 1.0 + 3.0 * face)  # f on the face
+        else:
+            sb.make_bc(u, sb.NEUMANN, 3.0 * sign)  # outward normal derivative
+        sb.update_ghost_mr(u)
+        levels = _check_direction(mesh, u, axis, sign, f)
+        if sign < 0:
+            crossed |= levels
+    if kind == "adapted":
+        assert len(crossed) > 1, "the adapted boundary must cross several levels (adapted_boundary_crosses_levels_*)"
+    u.destroy()
+    mesh.destroy()
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_corner_ghosts_reflect_about_the_corner(gpu, dim):
+    """corners_{2,3}d_ghost_width_1 (:318-360, 761-780): on a uniform level-3 mesh every corner-block ghost holds the field
+    reflected about the domain corner, f = 1 + 0.5 x0^2 + sum (d+1) x_d (corner_oracle, :289-316)."""
+    level = 3
+    mesh = _uniform(dim, level)
+    u = sb.make_scalar_field("u", mesh)
+
+    def f(x):
+        p = 1.0 + 0.5 * x[:, 0] * x[:, 0]
+        for d in range(dim):
+            p = p + (d + 1) * x[:, d]
+        return p
+
+    _fill_leaves(mesh, u, f)
+    sb.make_bc(u, sb.DIRICHLET, 0.0)
+    sb.update_ghost_mr(u)
+    lv, co, off = mesh.cell_table(sb.REFERENCE)
+    vals = u.download()
+    c = _centers(mesh, lv, co)
+    outward = np.where(c < 0, -1, np.where(c > 1, 1, 0))
+    sel = (outward != 0).sum(axis=1) >= 2
+    assert sel.any()
+    for ci, oi, o in zip(c[sel], outward[sel], off[sel]):
+        first = int(np.flatnonzero(oi)[0])
+        mag = abs(ci[first] - (0.0 if oi[first] < 0 else 1.0))
+        refl = ci.copy()
+        for d in range(dim):
+            if oi[d] != 0:
+                r = 0.0 if oi[d] < 0 else 1.0
+                refl[d] = r - mag * oi[d]
+        assert abs(vals[o] - f(refl[None, :])[0]) < 1e-11, f"corner ghost at {ci}"
+    u.destroy()
+    mesh.destroy()

@@ -172,3 +172,54 @@ def test_heat_demo_reproduces_reference_golden(gpu):
     assert np.array_equal(lv, g["level"].astype(np.int64)) and np.array_equal(idx[:, :2], g["idx"].astype(np.int64)), "mesh differs"
     got = u.download()[off]
     assert np.max(np.abs(got - g["u"])) <= 1e-15
+
+
+def _two_level_mesh_2d():
+    """reference tests/test_fv_operators.cpp:965-993: coarse left half (level 3), fine right half (level 4), jump at x = 1/2"""
+    nc, nf = 8, 16
+    levels = [3] * nc + [4] * nf
+    ivl = np.zeros(nc + nf, dtype=sb.INTERVAL_DTYPE)
+    for y in range(nc):
+        ivl[y] = (y, 0, 0, nc // 2, 0)
+    for y in range(nf):
+        ivl[nc + y] = (y, 0, nf // 2, nf, 0)
+    cfg = sb.mesh_config(2, 1).min_level(3).max_level(4).max_stencil_size(2).disable_minimal_ghost_width()
+    return sb.MRMesh.from_intervals([0.0, 0.0], [1.0, 1.0], cfg, levels, ivl)
+
+
+def test_level_jump_constant_conservation(gpu):
+    """fv_operators.level_jump_constant_conservation (:1016-1052): every operator vanishes on a constant field, everywhere,
+    including the level-jump interface and the boundary (the Dirichlet value matches the constant)."""
+    mesh = _two_level_mesh_2d()
+    lv, co, off = mesh.cell_table(sb.CELLS)
+    assert set(np.unique(lv)) == {3, 4}
+    u = sb.make_scalar_field("s", mesh)
+    u.resize()
+    u.fill(2.5)
+    sb.make_bc(u, sb.DIRICHLET, 2.5)
+    for scheme in (sb.make_diffusion_order2([1.0, 1.0]), sb.make_convection_upwind([1.0, 2.0]), sb.make_convection_upwind([-1.0, -2.0])):
+        r = scheme(u).download()
+        assert np.max(np.abs(r[off])) < 1e-10, scheme.name
+
+
+def test_level_jump_linear_exactness_of_diffusion(gpu):
+    """fv_operators.level_jump_linear_exactness (:1068-1128), diffusion part: the central flux stays exact across the jump
+    because projection and prediction reproduce a linear field.  The reference imposes the linear field on the boundary
+    with a function-valued Dirichlet (not on the device path): here the BC is a constant, so the cells whose ghost
+    stencils reach the boundary (two coarse cells from it) are left out instead of only the boundary-touching ones."""
+    a, b, c = 3.0, -2.0, 1.0
+    mesh = _two_level_mesh_2d()
+    lv, co, off = mesh.cell_table(sb.CELLS)
+    h = np.array([mesh.cell_length(int(l)) for l in lv])
+    x = (co + 0.5) * h[:, None]
+    host = np.zeros(mesh.nb_cells(sb.REFERENCE))
+    host[off] = a * x[:, 0] + b * x[:, 1] + c
+    u = sb.make_scalar_field("u", mesh)
+    u.resize()
+    u.upload(host)
+    sb.make_bc(u, sb.DIRICHLET, 0.0)
+    r = sb.make_diffusion_order2([1.0, 1.0])(u).download()
+    inner = np.all((x > 0.25) & (x < 0.75), axis=1)
+    near_jump = inner & (np.abs(x[:, 0] - 0.5) < 0.13)
+    assert near_jump.sum() > 8 and set(np.unique(lv[near_jump])) == {3, 4}
+    assert np.max(np.abs(r[off][inner])) < 1e-9
