@@ -202,6 +202,11 @@ extern "C"
     /* host-side profiling aid: rebuild the sub-meshes and the index batches of the current leaves `reps` times
      * (no device work) and report the mean seconds of each stage */
     int smr_debug_host_rebuild(smr_mesh_t m, int reps, double* mesh_seconds, double* plan_seconds, int64_t* arena_bytes);
+    /* host-side testing aid (no device needed): the records of the flux-scheme batch of the current mesh, 6 ints each:
+     * level, x, y, z of the first cell, length, face kinds (2 bits per face, face = 2*d + plus side; 0 same-level leaf,
+     * 1 coarser leaf, 2 finer leaves, 3 domain boundary; the x-face kinds apply to the first / last cell only).
+     * out == NULL: only count. */
+    int smr_debug_flux_records(smr_mesh_t m, int32_t* out, int64_t capacity, int64_t* n_records);
 
     /* the demos' initial condition as a device kernel over the leaves: u = inside where |center(cell) - c|^2 <= r^2,
      * else outside (only written when overwrite_outside != 0)

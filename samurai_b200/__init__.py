@@ -109,6 +109,7 @@ SYMBOLS = {
     "smr_mg_rebalance": [_vp, _i32],
     "smr_mg_leaf_owners": [_u64, _vp, _i64],
     "smr_debug_host_rebuild": [_u64, _i32, _P(_dbl), _P(_dbl), _P(_i64)],
+    "smr_debug_flux_records": [_u64, _vp, _i64, _P(_i64)],
     "smr_profile_enable": [_i32],
     "smr_profile_get": [_i32, _P(_u64), _P(_dbl), _P(_u64)],
     "smr_profile_get_bytes": [_i32, _P(_u64)],
@@ -384,6 +385,15 @@ class MRMesh:
         a, b, n = C.c_double(), C.c_double(), C.c_int64()
         _check(load_library().smr_debug_host_rebuild(self._h, reps, C.byref(a), C.byref(b), C.byref(n)))
         return a.value, b.value, n.value
+
+    def debug_flux_records(self):
+        """[N, 6] int32: level, x, y, z, n, face kinds of every record of the flux-scheme batch (host only)."""
+        n = C.c_int64()
+        _check(load_library().smr_debug_flux_records(self._h, None, 0, C.byref(n)))
+        out = np.zeros((n.value, 6), dtype=np.int32)
+        if n.value:
+            _check(load_library().smr_debug_flux_records(self._h, out.ctypes.data, n.value, C.byref(n)))
+        return out
 
     def update_from_tags(self, tags):
         tags = np.ascontiguousarray(tags, dtype=np.uint8)

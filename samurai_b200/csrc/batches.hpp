@@ -12,6 +12,7 @@
 #include "mesh.hpp"
 
 #include <cstdio>
+#include <functional>
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -130,6 +131,8 @@ namespace smr
         int cta_units             = SMR_CTA_CELLS;
         std::vector<int> group;   // group (e.g. level) of every part, non-decreasing; empty: every part is its own group
         int n_groups = 0;
+        std::vector<size_t> part_item;  // filled by layout_batch: first record of every part ...
+        std::vector<int64_t> part_unit; // ... and the output units before it
     };
 
     template <class Item>
@@ -147,8 +150,12 @@ namespace smr
             pd.cum->assign(static_cast<size_t>(ngroups) + 1, 0);
         }
         std::vector<int64_t> per_group(static_cast<size_t>(ngroups), 0);
+        pd.part_item.assign(pd.parts.size(), 0);
+        pd.part_unit.assign(pd.parts.size(), 0);
         for (size_t k = 0; k < pd.parts.size(); ++k)
         {
+            pd.part_item[k] = n;
+            pd.part_unit[k] = c;
             int64_t cp = 0;
             for (const Item& it : *pd.parts[k])
             {
@@ -186,6 +193,52 @@ namespace smr
         b.items     = static_cast<int64_t>(arena.take(n * sizeof(Item)));
         b.prefix    = static_cast<int64_t>(arena.take((n + 1) * sizeof(int64_t)));
         b.cta_first = static_cast<int64_t>(arena.take((static_cast<size_t>(b.n_ctas) + 1) * sizeof(int32_t)));
+    }
+
+    // records and prefix entries of ONE part (parts of a batch can be filled concurrently)
+    template <class Item>
+    inline void fill_part(const Pending<Item>& pd, Arena& arena, size_t k)
+    {
+        const Batch& b = *pd.out;
+        if (b.n_items == 0 || pd.parts[k]->empty())
+        {
+            return;
+        }
+        Item* items     = reinterpret_cast<Item*>(arena.p + b.items);
+        int64_t* prefix = reinterpret_cast<int64_t*>(arena.p + b.prefix);
+        size_t i        = pd.part_item[k];
+        int64_t acc     = pd.part_unit[k];
+        std::memcpy(items + i, pd.parts[k]->data(), pd.parts[k]->size() * sizeof(Item));
+        for (const Item& it : *pd.parts[k])
+        {
+            prefix[i++] = acc;
+            acc += it.n;
+        }
+    }
+
+    // closing prefix entry and the per-CTA table, once every part is in place
+    template <class Item>
+    inline void finish_batch(const Pending<Item>& pd, Arena& arena)
+    {
+        const Batch& b = *pd.out;
+        if (b.n_items == 0)
+        {
+            return;
+        }
+        int64_t* prefix = reinterpret_cast<int64_t*>(arena.p + b.prefix);
+        int32_t* first  = reinterpret_cast<int32_t*>(arena.p + b.cta_first);
+        prefix[b.n_items] = b.n_cells;
+        size_t it = 0;
+        for (int c = 0; c < b.n_ctas; ++c)
+        {
+            const int64_t g = static_cast<int64_t>(c) * b.cta_units;
+            while (prefix[it + 1] <= g)
+            {
+                ++it;
+            }
+            first[c] = static_cast<int32_t>(it);
+        }
+        first[b.n_ctas] = b.n_items - 1;
     }
 
     template <class Item>
@@ -1807,47 +1860,42 @@ namespace smr
             layout_bc(p_bc[l], plan.arena);
         }
         plan.arena.commit();
-#pragma omp parallel for schedule(dynamic, 1)
-        for (int t = -2; t < 3 + 4 * nlev; ++t)
         {
-            if (t == -2)
+            // every (batch, part) pair is an independent copy; the per-CTA tables follow once the parts are in
+            std::vector<std::function<void()>> jobs, finish;
+            auto add = [&](auto& pd)
             {
-                fill_batch(p_fv_single, plan.arena);
-            }
-            else if (t == -1)
-            {
-                fill_batch(p_fv_strip, plan.arena);
-            }
-            else if (t == 0)
-            {
-                fill_batch(p_fv, plan.arena);
-            }
-            else if (t == 1)
-            {
-                fill_batch(p_detail, plan.arena);
-            }
-            else if (t == 2)
-            {
-                fill_batch(p_tag_all, plan.arena);
-            }
-            else
-            {
-                const int l = (t - 3) / 4;
-                switch ((t - 3) % 4)
+                for (size_t k = 0; k < pd.parts.size(); ++k)
                 {
-                    case 0:
-                        fill_batch(p_proj[l], plan.arena);
-                        break;
-                    case 1:
-                        fill_batch(p_pred[l], plan.arena);
-                        break;
-                    case 2:
-                        fill_batch(p_tag[l], plan.arena);
-                        break;
-                    default:
-                        fill_bc(p_bc[l], plan.arena);
-                        break;
+                    if (!pd.parts[k]->empty())
+                    {
+                        jobs.push_back([&pd, &plan, k] { fill_part(pd, plan.arena, k); });
+                    }
                 }
+                finish.push_back([&pd, &plan] { finish_batch(pd, plan.arena); });
+            };
+            add(p_fv_single);
+            add(p_fv_strip);
+            add(p_fv);
+            add(p_detail);
+            add(p_tag_all);
+            for (int l = 0; l < nlev; ++l)
+            {
+                add(p_proj[l]);
+                add(p_pred[l]);
+                add(p_tag[l]);
+                PendingBc* pb = &p_bc[l];
+                jobs.push_back([pb, &plan] { fill_bc(*pb, plan.arena); });
+            }
+#pragma omp parallel for schedule(dynamic, 1)
+            for (int t = 0; t < static_cast<int>(jobs.size()); ++t)
+            {
+                jobs[static_cast<size_t>(t)]();
+            }
+#pragma omp parallel for schedule(dynamic, 1)
+            for (int t = 0; t < static_cast<int>(finish.size()); ++t)
+            {
+                finish[static_cast<size_t>(t)]();
             }
         }
 #ifdef SMR_PLAN_TIMING
@@ -1868,28 +1916,49 @@ namespace smr
         const int dim = cfg.dim;
         const int nlev = old_m.nlev;
         tp.arena.clear();
-        std::vector<std::vector<smr_item_copy>> copies(nlev);
-        std::vector<std::vector<smr_item_proj>> projs(nlev);
-        std::vector<std::vector<smr_item_pred>> preds(nlev);
+        // tasks: per level the projection + prediction sets (small: only where the mesh changed) and, per row chunk of the
+        // new leaves, the copy records (the bulk)
+        struct Task
+        {
+            int kind, level;
+            size_t r0, r1;
+            std::vector<smr_item_copy> copies;
+            std::vector<smr_item_proj> projs;
+            std::vector<smr_item_pred> preds;
+        };
+        std::vector<Task> tasks;
+        for (int l = cfg.min_level; l <= cfg.max_level && l < nlev; ++l)
+        {
+            if (!new_m.cells[l].empty() && !old_m.ref[l].empty())
+            {
+                const std::vector<size_t> cut = chunk_rows(new_m.cells[l], 3000, 16);
+                for (size_t c = 0; c + 1 < cut.size(); ++c)
+                {
+                    tasks.push_back(Task{0, l, cut[c], cut[c + 1], {}, {}, {}});
+                }
+            }
+            if (l > cfg.min_level)
+            {
+                tasks.push_back(Task{1, l, 0, 0, {}, {}, {}});
+            }
+        }
         std::string error;
 #pragma omp parallel for schedule(dynamic, 1)
-        for (int t = 2 * nlev - 1; t >= 0; --t)
+        for (int t = static_cast<int>(tasks.size()) - 1; t >= 0; --t)
         {
-            const int kind = t / nlev, l = t % nlev;
-            if (l < cfg.min_level || l > cfg.max_level)
-            {
-                continue;
-            }
+            Task& tk    = tasks[static_cast<size_t>(t)];
+            const int l = tk.level;
             try
             {
-                if (kind == 0)
+                if (tk.kind == 0)
                 {
-                    LevelSet s = set_inter(old_m.ref[l], new_m.cells[l]);
+                    LevelSet s = set_inter(old_m.ref[l], slice_rows(new_m.cells[l], tk.r0, tk.r1));
                     if (!s.empty())
                     {
                         LevelSet so = s;
                         locate(s, new_m.ref[l]);
                         locate(so, old_m.ref[l]);
+                        tk.copies.reserve(s.n_intervals());
                         for (size_t r = 0; r < s.rows(); ++r)
                         {
                             const int y = key_y(s.key[r]), z = key_z(s.key[r]);
@@ -1900,22 +1969,22 @@ namespace smr
                             const int mask = static_cast<int>(flt.mask(l, y, z));
                             for (int q = s.ptr[r]; q < s.ptr[r + 1]; ++q)
                             {
-                                copies[l].push_back({s.off[q], so.off[q], s.xe[q] - s.xs[q], mask});
+                                tk.copies.push_back({s.off[q], so.off[q], s.xe[q] - s.xs[q], mask});
                             }
                         }
                     }
                 }
-                else if (l > cfg.min_level)
+                else
                 {
                     LevelSet sc = set_inter(coarsen(old_m.cells[l], 1, dim), new_m.cells[l - 1]);
-                    proj_items(dim, sc, l - 1, new_m.ref[l - 1], old_m.ref[l], flt, projs[l]);
+                    proj_items(dim, sc, l - 1, new_m.ref[l - 1], old_m.ref[l], flt, tk.projs);
                     // set_refine = (new cells[l] ∩ old cells[l-1]).on(l-1); every coarse cell fills all its children
                     LevelSet sr = set_inter(coarsen(new_m.cells[l], 1, dim), old_m.cells[l - 1]);
                     if (!sr.empty())
                     {
                         LevelSet fine = refine(sr, 1, dim);
                         locate(fine, new_m.ref[l]);
-                        pred_items(dim, cfg.pred_radius, l, fine, old_m.ref[l - 1], flt, preds[l]);
+                        pred_items(dim, cfg.pred_radius, l, fine, old_m.ref[l - 1], flt, tk.preds);
                     }
                 }
             }
@@ -1932,11 +2001,17 @@ namespace smr
         Pending<smr_item_copy> p_copy{&tp.copy, B_COPY, -1, {}, nullptr, false};
         Pending<smr_item_proj> p_proj{&tp.proj, B_PROJ, -1, {}, nullptr, false};
         Pending<smr_item_pred> p_pred{&tp.pred, B_PRED, -1, {}, nullptr, false};
-        for (int l = 0; l < nlev; ++l)
+        for (const Task& tk : tasks)
         {
-            p_copy.parts.push_back(&copies[l]);
-            p_proj.parts.push_back(&projs[l]);
-            p_pred.parts.push_back(&preds[l]);
+            if (tk.kind == 0)
+            {
+                p_copy.parts.push_back(&tk.copies);
+            }
+            else
+            {
+                p_proj.parts.push_back(&tk.projs);
+                p_pred.parts.push_back(&tk.preds);
+            }
         }
         layout_batch(p_copy, tp.arena);
         layout_batch(p_proj, tp.arena);

@@ -2563,6 +2563,42 @@ extern "C"
             });
     }
 
+    int smr_debug_flux_records(smr_mesh_t m, int32_t* out, int64_t capacity, int64_t* n_records)
+    {
+        return guarded(
+            [&]
+            {
+                MeshObj& mo = get_mesh(m);
+                FluxPlan fp;
+                build_flux_plan(mo.mesh, fp);
+                *n_records = fp.items.n_items;
+                if (out == nullptr)
+                {
+                    return;
+                }
+                if (capacity < fp.items.n_items)
+                {
+                    throw std::invalid_argument("output array too small");
+                }
+                const smr_item_flux* it = reinterpret_cast<const smr_item_flux*>(fp.arena.p + fp.items.items);
+                const Mesh& mesh        = mo.mesh;
+                for (int i = 0; i < fp.items.n_items; ++i)
+                {
+                    // the record stores offsets, not coordinates: recover (x, y, z) of its first cell from the reference mesh
+                    const LevelSet& ref = mesh.ref[it[i].level];
+                    const auto pos      = std::upper_bound(ref.off.begin(), ref.off.end(), it[i].c) - ref.off.begin() - 1;
+                    const auto row      = std::upper_bound(ref.ptr.begin(), ref.ptr.end(), static_cast<int32_t>(pos)) - ref.ptr.begin() - 1;
+                    int32_t* o          = out + 6 * static_cast<int64_t>(i);
+                    o[0]                = it[i].level;
+                    o[1]                = ref.xs[static_cast<size_t>(pos)] + static_cast<int32_t>(it[i].c - ref.off[static_cast<size_t>(pos)]);
+                    o[2]                = key_y(ref.key[static_cast<size_t>(row)]);
+                    o[3]                = key_z(ref.key[static_cast<size_t>(row)]);
+                    o[4]                = it[i].n;
+                    o[5]                = it[i].kinds;
+                }
+            });
+    }
+
     int smr_adapt_last_size(smr_mesh_t m, int64_t* out)
     {
         return guarded(

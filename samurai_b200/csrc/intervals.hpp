@@ -992,7 +992,8 @@ namespace smr
     inline void locate(LevelSet& sub, const LevelSet& ref)
     {
         sub.off.assign(sub.xs.size(), -1);
-        size_t rr = 0;
+        // start at the first row of `sub` (chunked callers locate a small slice in a big set)
+        size_t rr = sub.rows() ? static_cast<size_t>(std::lower_bound(ref.key.begin(), ref.key.end(), sub.key[0]) - ref.key.begin()) : 0;
         for (size_t r = 0; r < sub.rows(); ++r)
         {
             while (rr < ref.rows() && ref.key[rr] < sub.key[r])

@@ -86,3 +86,55 @@ def test_invalid_configs_raise():
         sb.MRMesh.make_mesh([0, 0], [1, 1], sb.mesh_config(2, 1).min_level(5).max_level(3).disable_minimal_ghost_width())
     with pytest.raises(ValueError):  # ghost width 2 is not implemented: must fail loudly, not silently differ
         sb.MRMesh.make_mesh([0, 0], [1, 1], sb.mesh_config(2, 1).min_level(2).max_level(4))
+
+
+@pytest.mark.parametrize("dim,lmin,lmax", [(1, 2, 7), (2, 2, 6), (3, 1, 4)])
+def test_flux_face_classification_matches_interface_sets(dim, lmin, lmax):
+    """Host half of the flux-based schemes (csrc/batches.hpp: flux_items) against the reference's interface sets restated
+    by the oracle (interface.hpp:35-306, boundary.hpp:6-33): the records tile the leaves exactly, and for every cell and
+    every face the neighbour kind is: same-level leaf / coarser leaf / finer leaves / domain boundary."""
+    ocfg = pu.oracle_cfg(dim, lmin, lmax, 1)
+    om = so.Mesh.uniform(ocfg)
+    om, _ = so.adapt(om, so.init_disc(om, [0.3] * dim, 0.2), so.Bc(), 2e-4, 1.0)
+    assert len(om.leaf_levels()) > 1
+    levels, ivl = [], []
+    for l in om.leaf_levels():
+        c = so.unpack(om.cells[l], dim)
+        full = np.zeros((c.shape[0], 3), dtype=np.int64)
+        full[:, :dim] = c
+        for x, y, z in full:  # one single-cell interval per leaf: the product merges them
+            levels.append(l)
+            ivl.append((y, z, x, x + 1, 0))
+    pm = sb.MRMesh.from_intervals([0.0] * dim, [1.0] * dim, pu.product_cfg(dim, lmin, lmax, 1), levels, np.array(ivl, dtype=sb.INTERVAL_DTYPE))
+    pu.assert_same_mesh(pm, om)
+    rec = pm.debug_flux_records()
+    seen = {l: [] for l in om.leaf_levels()}
+    SAME, COARSE, FINE, BDRY = 0, 1, 2, 3
+    for level, x, y, z, n, kinds in rec:
+        xs = np.arange(x, x + n)
+        coords = np.stack([xs, np.full(n, y), np.full(n, z)], axis=1)[:, :dim]
+        keys = so.pack(coords)
+        seen[int(level)].append(keys)
+        for d in range(dim):
+            for plus in (0, 1):
+                e = [0] * dim
+                e[d] = 1 if plus else -1
+                nb = so.translate(keys, e)
+                is_same = np.isin(nb, om.cells[level])
+                is_bdry = ~om.in_domain(level, nb)
+                is_coarse = np.isin(so.pack(so.unpack(nb, dim) >> 1), om.cells[level - 1]) & ~is_bdry if level > 0 else np.zeros(n, bool)
+                is_fine = np.isin(so.pack(so.unpack(nb, dim) << 1), om.cells[level + 1]) & ~is_bdry
+                truth = np.select([is_same, is_bdry, is_coarse, is_fine], [SAME, BDRY, COARSE, FINE], default=-1)
+                assert np.all(truth >= 0)
+                kind = (int(kinds) >> (2 * (2 * d + plus))) & 3
+                if d == 0:
+                    # x faces: interior faces of a record are same-level; the record's kind applies to its end cell
+                    inner = truth[1:] if not plus else truth[:-1]
+                    assert np.all(inner == SAME)
+                    assert kind == (truth[-1] if plus else truth[0])
+                else:
+                    assert np.all(truth == kind), f"level {level} row ({y},{z}) x {x}+{n} face d={d} plus={plus}: {truth} vs {kind}"
+    for l in om.leaf_levels():
+        got = np.sort(np.concatenate(seen[l]))
+        assert np.array_equal(got, om.cells[l]), f"level {l}: the records do not tile the leaves"
+    pm.destroy()
