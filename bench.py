@@ -463,6 +463,24 @@ def run_product(args):
                      "diffusion_order2": {"ms_per_apply": 1e3 * d_u, "note": "rhs = make_diffusion_order2(K)(u): fill(0) + gather, 8 B zero-fill + 8 B read + 8 B write per cell",
                                           "achieved": 24.0 * n_u / d_u / 1e9, "frac": 24.0 * n_u / d_u / 1e9 / peak_gbs}}
 
+        # ---- flux-based scheme on the same adapted mesh (a8-a10): rhs = diffusion(u); unp1 = u - dt * rhs ----------------
+        flux = None
+        try:
+            diff = sb.make_diffusion_order2([1.0] * args.dim)
+            rhs = diff(sim.u)  # builds the face-classified batch of this mesh (host) and applies once
+            st0 = sb.stats(reset=True)
+            sb.profile_enable(True)
+            for _ in range(5):
+                diff.apply(rhs, sim.u)
+            n_f, s_f, c_f = sb.profile_get()["fv"]
+            sb.profile_enable(False)
+            flux = {"scheme": "make_diffusion_order2 across level jumps (FluxGenOp)", "leaves": leaves_now, "us_per_apply": 1e6 * s_f / max(n_f, 1),
+                    "GBps": 16.0 * c_f / s_f / 1e9 if s_f > 0 else None,
+                    "note": "gather kernel alone (8 B read + 8 B write per leaf); the adapted mesh is L2 resident, see uniform_sweep.diffusion_order2 for the HBM-bound shape"}
+            rhs.destroy()
+        except Exception as e:  # noqa: BLE001
+            flux = {"error": str(e)}
+
         # ---- cpu baseline: oracle port on a bounded sample of the same state ----------------------------------------
         cpu = None
         if not args.no_cpu_baseline:
@@ -495,6 +513,7 @@ def run_product(args):
             "kernel_families_fused": fused,
             "kernel_families_per_sweep_launches": families,
             "uniform_sweep": sweep,
+            "flux_scheme_on_adapted_mesh": flux,
             "cpu_baseline": cpu,
             "clocks": clocks,
         }

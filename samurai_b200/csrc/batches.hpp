@@ -108,7 +108,7 @@ namespace smr
             if (size > cap)
             {
                 release();
-                cap = size + size / 4 + 4096;
+                cap = 2 * size + 4096; // pinned when the C ABI installs alloc_fn: regrowing is expensive, so double
                 p   = static_cast<uint8_t*>(alloc_fn ? alloc_fn(cap) : std::malloc(cap));
                 if (!p)
                 {

@@ -100,7 +100,9 @@ namespace smr
             if (bytes > cap)
             {
                 release();
-                size_t want = bytes + bytes / 4 + 4096;
+                // every regrowth is a cudaFree + cudaMalloc (a device synchronisation and up to milliseconds): grow
+                // geometrically, generously outside the fixed multi-GPU pool
+                size_t want = bytes + ((shared && g_pool_on) ? bytes / 4 : bytes / 2) + 4096;
                 if (shared && g_pool_on)
                 {
                     want = (want + 255) & ~size_t(255);
@@ -167,7 +169,7 @@ namespace smr
                 {
                     cudaFreeHost(p);
                 }
-                size_t want = bytes + bytes / 4 + 4096;
+                size_t want = 2 * bytes + 4096; // pinning pages costs ~10 ms per 10 MB: regrow rarely
                 SMR_CUDA(cudaHostAlloc(&p, want, cudaHostAllocDefault));
                 cap = want;
             }

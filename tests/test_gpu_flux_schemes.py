@@ -223,3 +223,44 @@ def test_level_jump_linear_exactness_of_diffusion(gpu):
     near_jump = inner & (np.abs(x[:, 0] - 0.5) < 0.13)
     assert near_jump.sum() > 8 and set(np.unique(lv[near_jump])) == {3, 4}
     assert np.max(np.abs(r[off][inner])) < 1e-9
+
+
+@pytest.mark.parametrize("dim,lo,hi,kind", [(1, 2, 8, "burgers"), (2, 2, 6, "burgers"), (2, 2, 6, "diffusion"), (3, 1, 4, "convection")])
+def test_flux_scheme_time_loop_matches_oracle(gpu, dim, lo, hi, kind):
+    """`MRadaptation; unp1 = u - dt * scheme(u); swap` for several steps (the loop of demos/FiniteVolume/burgers_mra.cpp:142-160 and
+    heat.cpp:196-222) on the GPU and on the oracle: meshes identical at every step, leaves bit-identical."""
+    pmesh = sb.MRMesh.make_mesh([0.0] * dim, [1.0] * dim, pu.product_cfg(dim, lo, hi, 1))
+    omesh = so.Mesh.uniform(pu.oracle_cfg(dim, lo, hi, 1))
+    bc = so.Bc("dirichlet", 0.0)
+    ou = so.init_disc(omesh, [0.3] * dim, 0.2)
+    u = sb.make_scalar_field("u", pmesh)
+    u.resize()
+    u.upload(ou)
+    unp1 = sb.make_scalar_field("unp1", pmesh)
+    sb.make_bc(u, sb.DIRICHLET, 0.0)
+    sb.make_bc(unp1, sb.DIRICHLET, 0.0)
+    vel, K = [1.0, 0.5, -0.25][:dim], [1.0] * dim
+    if kind == "burgers":
+        scheme, dt = 0.5 * sb.make_convection_upwind(), 0.5 * pmesh.min_cell_length()
+        apply_o = lambda m, f: so.flux_nonlin_apply(m, f, so.burgers_upwind_flux(0.5))
+    elif kind == "diffusion":
+        scheme, dt = sb.make_diffusion_order2(K), 0.2 * pmesh.min_cell_length() ** 2
+        apply_o = lambda m, f: so.flux_linhom_apply(m, f, so.diffusion_order2_coeffs(K))
+    else:
+        scheme, dt = sb.make_convection_upwind(vel), 0.25 * pmesh.min_cell_length()
+        apply_o = lambda m, f: so.flux_linhom_apply(m, f, so.convection_upwind_coeffs(vel))
+    adapt = sb.make_MRAdapt(u)
+    mra = sb.mra_config().epsilon(2e-4)
+    for step in range(4):
+        adapt(mra)
+        omesh, ou = so.adapt(omesh, ou, bc, 2e-4, 1.0)
+        pu.assert_same_mesh(pmesh, omesh)
+        unp1.resize()
+        sb.lincomb(unp1, 1.0, u, -dt, scheme(u))
+        sb.swap(u, unp1)
+        so.update_ghost_mr(omesh, ou, bc)
+        ou = so.lincomb_leaves(omesh, 1.0, ou, -dt, apply_o(omesh, ou))
+        _, _, leaf = omesh.leaf_table()
+        got = u.download()
+        assert np.array_equal(got[leaf], ou[leaf]), f"step {step}: max diff {np.max(np.abs(got[leaf] - ou[leaf])):.3e}"
+    assert len(omesh.leaf_levels()) > 1
