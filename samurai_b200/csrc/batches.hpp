@@ -60,6 +60,7 @@ namespace smr
         size_t size = 0;
 
         static inline void* (*alloc_fn)(size_t) = nullptr;
+        static inline size_t min_pinned_cap    = size_t(48) << 20;
         static inline void (*free_fn)(void*)    = nullptr;
 
         Arena()                        = default;
@@ -108,7 +109,9 @@ namespace smr
             if (size > cap)
             {
                 release();
-                cap = 2 * size + 4096; // pinned when the C ABI installs alloc_fn: regrowing is expensive, so double
+                // pinned when the C ABI installs alloc_fn: pinning pages (and mapping them for every GPU of the box) was
+                // measured at ~300 ms per regrowth, so start generously and double
+                cap = std::max<size_t>(2 * size + 4096, alloc_fn ? min_pinned_cap : 0);
                 p   = static_cast<uint8_t*>(alloc_fn ? alloc_fn(cap) : std::malloc(cap));
                 if (!p)
                 {

@@ -169,7 +169,7 @@ namespace smr
                 {
                     cudaFreeHost(p);
                 }
-                size_t want = 2 * bytes + 4096; // pinning pages costs ~10 ms per 10 MB: regrow rarely
+                size_t want = std::max<size_t>(2 * bytes + 4096, size_t(8) << 20); // pinning is slow (~300 ms per regrowth measured): regrow rarely
                 SMR_CUDA(cudaHostAlloc(&p, want, cudaHostAllocDefault));
                 cap = want;
             }
