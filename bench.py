@@ -506,7 +506,11 @@ def run_product(args):
             "e2e": {"value": e2e_cells / e2e_secs, "unit": UNIT, "h2d_bytes_per_step": int(st_e2e["h2d_bytes"] / args.steps),
                     "d2h_bytes_per_step": int(st_e2e["d2h_bytes"] / args.steps), "ms_per_step": 1e3 * e2e_secs / args.steps},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
-                         "traffic": None, "peak_source": peak_src, "share_of_device_time": fam_time[dom] / total_prof,
+                         # dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` of two steady-state harten
+                         # launches of this workload (18.6 MB and 34.4 MB; profiles/r01_summary.md section 6): below the algorithmic
+                         # bytes because the adapted working set stays in L2 between the sweeps.  Not re-measured by this run.
+                         "traffic": 26.5e6 if (dom == "wavefront" and args.dim == 2 and args.max_level == 14) else None,
+                         "peak_source": peak_src, "share_of_device_time": fam_time[dom] / total_prof,
                          "launches": n_l, "us_per_launch": 1e6 * s_l / n_l, "algorithmic_bytes_per_launch": dom_bytes / n_l,
                          "note": "adapted-mesh step: ~1e6 cells over ~40 dependent level sweeps per launch (grid barrier between sweeps): latency bound, "
                                  "the working set lives in L2; see uniform_sweep for the HBM-bound shape"},
