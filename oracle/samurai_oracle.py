@@ -601,15 +601,23 @@ def mr_criteria(mesh: Mesh, detail, tag, level, eps, regularity):
     c = unpack(coarse, dim)
     ci = mesh.index(level - 1, coarse)
     fi = [mesh.index(level, pack(2 * c + np.array(ch, dtype=np.int64))) for ch in _children_offsets(dim)]
+    # several adapted fields / components: coarsen needs every component below its threshold, refine needs any above
+    # (mr/criteria.hpp:33-37, 49-53, 81-85: loops over n_comp)
+    comps = detail if isinstance(detail, (list, tuple)) else [detail]
     if level > cfg.min_level:
-        cond = ~(np.abs(detail[ci]) > coarse_eps)
-        for i in fi:
-            cond &= ~(np.abs(detail[i]) > eps_l)
+        cond = np.ones(coarse.size, dtype=bool)
+        for dc in comps:
+            cond &= ~(np.abs(dc[ci]) > coarse_eps)
+            for i in fi:
+                cond &= ~(np.abs(dc[i]) > eps_l)
         for i in fi:
             tag[i[cond]] = COARSEN
     if level < cfg.max_level:
         for i in fi:
-            tag[i] |= (np.abs(detail[i]) > fine_eps).astype(np.uint8) * np.uint8(REFINE)
+            ref = np.zeros(coarse.size, dtype=bool)
+            for dc in comps:
+                ref |= np.abs(dc[i]) > fine_eps
+            tag[i] |= ref.astype(np.uint8) * np.uint8(REFINE)
 
 
 def maximum(mesh: Mesh, tag, level):
@@ -772,6 +780,38 @@ def adapt(mesh: Mesh, f, bc: Bc, eps=1e-4, regularity=1.0, trace=None, relative_
         f = update_fields(mesh, new_mesh, f)
         mesh = new_mesh
     return mesh, f
+
+
+def adapt_fields(mesh: Mesh, fields, bcs, eps=1e-4, regularity=1.0):
+    """make_MRAdapt(u, v, ...)(mra_config): several fields adapted together (mr/adapt.hpp:103-107, 148-195, 277-389 with a
+    Field_tuple: one detail array per field, one tag array).  Returns (mesh, [fields])."""
+    cfg = mesh.cfg
+    lmin, L = cfg.min_level, cfg.max_level
+    fields = list(fields)
+    if lmin == L:
+        return mesh, fields
+    for ite in range(L - lmin):
+        details = [np.zeros(mesh.nref) for _ in fields]
+        tag = np.zeros(mesh.nref, dtype=np.uint8)
+        for l in mesh.leaf_levels():
+            tag[mesh.index(l, mesh.cells[l])] = KEEP
+        for f, bc in zip(fields, bcs):
+            update_ghost_mr(mesh, f, bc)
+        for level in range(max(lmin - 1, 0), L - ite):
+            for f, d in zip(fields, details):
+                compute_detail(mesh, f, d, level, detail_set(mesh, level))
+        for level in range(lmin, L - ite + 1):
+            mr_criteria(mesh, details, tag, level, eps, regularity)
+        for level in range(L, 0, -1):
+            maximum(mesh, tag, level)
+        new_ca = update_cell_array_from_tag(mesh, tag)
+        new_ca = make_graduation(cfg, new_ca)
+        if mesh.same_cells(new_ca):
+            break
+        new_mesh = Mesh(cfg, {l: new_ca[l] for l in range(len(new_ca)) if new_ca[l].size})
+        fields = [update_fields(mesh, new_mesh, f) for f in fields]
+        mesh = new_mesh
+    return mesh, fields
 
 
 # ----------------------------------------------------------------------------

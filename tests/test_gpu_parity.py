@@ -67,3 +67,47 @@ def test_fused_and_per_sweep_paths_are_bit_identical(gpu):
     assert all(np.array_equal(x, y) for x, y in zip(ta, tb))
     leaves_and_ghosts = ta[2]
     assert np.array_equal(fa[leaves_and_ghosts], fb[leaves_and_ghosts])
+
+
+@pytest.mark.parametrize("dim,lmin,lmax", [(2, 2, 7), (3, 1, 4)])
+def test_two_fields_adapted_together_match_oracle(gpu, dim, lmin, lmax):
+    """make_MRAdapt(u, v): one mesh driven by the details of both fields (coarsen only where every field allows it, refine
+    where any asks for it: mr/criteria.hpp loops over the components), different boundary conditions per field."""
+    sb, so = pu.sb, pu.so
+    ocfg = pu.oracle_cfg(dim, lmin, lmax, 1)
+    omesh = so.Mesh.uniform(ocfg)
+    ou = so.init_disc(omesh, [0.3] * dim, 0.2)
+    ov = 0.5 * so.init_disc(omesh, [0.7] * dim, 0.15)
+    bcs = [so.Bc("dirichlet", 0.0), so.Bc("neumann", 0.0)]
+    pmesh = sb.MRMesh.make_mesh([0.0] * dim, [1.0] * dim, pu.product_cfg(dim, lmin, lmax, 1))
+    u = sb.make_scalar_field("u", pmesh)
+    v = sb.make_scalar_field("v", pmesh)
+    for f, host in ((u, ou), (v, ov)):
+        f.resize()
+        f.upload(host)
+    sb.make_bc(u, sb.DIRICHLET, 0.0)
+    sb.make_bc(v, sb.NEUMANN, 0.0)
+    unp1 = sb.make_scalar_field("unp1", pmesh)
+    vnp1 = sb.make_scalar_field("vnp1", pmesh)
+    adapt = sb.make_MRAdapt(u, v)
+    mra = sb.mra_config().epsilon(2e-4)
+    dt = (0.5 if dim == 2 else 0.25) * pmesh.min_cell_length()
+    a, b = [1.0] * dim, [-1.0] * dim
+    only_u = so.adapt(so.Mesh.uniform(ocfg), so.init_disc(omesh, [0.3] * dim, 0.2), bcs[0], 2e-4, 1.0)[0]
+    for step in range(3):
+        adapt(mra)
+        omesh, (ou, ov) = so.adapt_fields(omesh, [ou, ov], bcs, 2e-4, 1.0)
+        pu.assert_same_mesh(pmesh, omesh)
+        if step == 0:
+            assert omesh.nb_cells() > only_u.nb_cells(), "the second field must really influence the mesh"
+        for f, nf, of, vel, bc in ((u, unp1, ou, a, bcs[0]), (v, vnp1, ov, b, bcs[1])):
+            sb.update_ghost_mr(f)
+            so.update_ghost_mr(omesh, of, bc)
+            nf.resize()
+            sb.upwind_step(nf, f, vel, dt)
+        ou, ov = so.fv_step(omesh, ou, a, dt), so.fv_step(omesh, ov, b, dt)
+        sb.swap(u, unp1)
+        sb.swap(v, vnp1)
+        _, _, leaf = omesh.leaf_table()
+        pu.assert_fields_close(u.download()[leaf], ou[leaf], f"u step {step}")
+        pu.assert_fields_close(v.download()[leaf], ov[leaf], f"v step {step}")
