@@ -474,24 +474,74 @@ def make_scalar_field(name, mesh):
     return ScalarField(name, mesh)
 
 
-def make_bc(field: ScalarField, kind, value):
-    """samurai::make_bc<Dirichlet<1>>(u, v) / make_bc<Neumann<1>>(u, v) (bc/bc.hpp:751-815)."""
-    _check(load_library().smr_field_set_bc(field._h, kind, float(value)))
+class VectorField:
+    """samurai::VectorField<mesh_t, double, n_comp> (field/vector_field.hpp) on the device: one SoA array per component
+    (BASELINE north_star), i.e. n_comp scalar device fields that are ghost-updated, adapted and advanced together.  The
+    reference's host layout is AoS `[cell][comp]`; upload()/download() convert."""
+
+    def __init__(self, name, mesh: MRMesh, n_comp):
+        self.name, self.mesh, self.n_comp = name, mesh, n_comp
+        self.components = [ScalarField(f"{name}_{c}", mesh) for c in range(n_comp)]
+
+    def resize(self):
+        for f in self.components:
+            f.resize()
+
+    def fill(self, v):
+        for f in self.components:
+            f.fill(v)
+
+    def upload(self, aos):
+        """aos: [nb_cells(reference), n_comp]"""
+        aos = np.asarray(aos, dtype=np.float64)
+        for c, f in enumerate(self.components):
+            f.upload(np.ascontiguousarray(aos[:, c]))
+
+    def download(self):
+        return np.stack([f.download() for f in self.components], axis=1)
+
+    def destroy(self):
+        for f in self.components:
+            f.destroy()
 
 
-def swap(a: ScalarField, b: ScalarField):
+def make_vector_field(name, mesh, n_comp):
+    return VectorField(name, mesh, n_comp)
+
+
+def _scalars(field):
+    return field.components if isinstance(field, VectorField) else [field]
+
+
+def make_bc(field, kind, *values):
+    """samurai::make_bc<Dirichlet<1>>(u, v...) / make_bc<Neumann<1>>(u, v...) (bc/bc.hpp:751-815): one constant per component."""
+    comps = _scalars(field)
+    if len(values) == 1 and len(comps) > 1:
+        values = values * len(comps)
+    if len(values) != len(comps):
+        raise ValueError("one boundary value per component")
+    for f, v in zip(comps, values):
+        _check(load_library().smr_field_set_bc(f._h, kind, float(v)))
+
+
+def swap(a, b):
     """std::swap(u.array(), unp1.array())."""
-    _check(load_library().smr_field_swap(a._h, b._h))
+    for x, y in zip(_scalars(a), _scalars(b)):
+        _check(load_library().smr_field_swap(x._h, y._h))
 
 
-def update_ghost_mr(field: ScalarField):
-    _check(load_library().smr_update_ghost_mr(field._h))
+def update_ghost_mr(*fields):
+    """update_ghost_mr(fields...) (algorithm/update_ghost_mr.hpp:260-270)"""
+    for field in fields:
+        for f in _scalars(field):
+            _check(load_library().smr_update_ghost_mr(f._h))
 
 
-def upwind_step(unp1: ScalarField, u: ScalarField, a, dt):
-    """unp1 = u - dt * samurai::upwind(a, u)."""
+def upwind_step(unp1, u, a, dt):
+    """unp1 = u - dt * samurai::upwind(a, u) (every component of a vector field is transported by the same velocity)."""
     a = np.ascontiguousarray(a, dtype=np.float64)
-    _check(load_library().smr_fv_upwind(unp1._h, u._h, a.ctypes.data, float(dt)))
+    for x, y in zip(_scalars(unp1), _scalars(u)):
+        _check(load_library().smr_fv_upwind(x._h, y._h, a.ctypes.data, float(dt)))
 
 
 def upwind_scalar_burgers_step(unp1: ScalarField, u: ScalarField, k, dt):
@@ -563,7 +613,8 @@ class MRAdapt:
     """samurai::make_MRAdapt(fields...) (mr/adapt.hpp:391-397)."""
 
     def __init__(self, *fields):
-        self.fields = fields
+        self.fields = [f for field in fields for f in _scalars(field)]  # a vector field contributes all its components
+        fields = self.fields
         self._arr = (C.c_uint64 * len(fields))(*[f._h for f in fields])
 
     def __call__(self, cfg: mra_config):

@@ -111,3 +111,39 @@ def test_two_fields_adapted_together_match_oracle(gpu, dim, lmin, lmax):
         _, _, leaf = omesh.leaf_table()
         pu.assert_fields_close(u.download()[leaf], ou[leaf], f"u step {step}")
         pu.assert_fields_close(v.download()[leaf], ov[leaf], f"v step {step}")
+
+
+def test_vector_field_soa_components_match_oracle(gpu):
+    """make_vector_field<double, 2>: two SoA device arrays ghost-updated, adapted (make_MRAdapt(vec): the criteria loop over
+    the components, mr/criteria.hpp:33-85) and advanced together; host layout AoS [cell][comp] as in the reference."""
+    sb, so = pu.sb, pu.so
+    dim, lmin, lmax = 2, 2, 7
+    omesh = so.Mesh.uniform(pu.oracle_cfg(dim, lmin, lmax, 1))
+    o0 = so.init_disc(omesh, [0.3, 0.3], 0.2)
+    o1 = -2.0 * so.init_disc(omesh, [0.6, 0.4], 0.1)
+    bcs = [so.Bc("dirichlet", 0.0), so.Bc("dirichlet", 0.0)]
+    pmesh = sb.MRMesh.make_mesh([0.0] * dim, [1.0] * dim, pu.product_cfg(dim, lmin, lmax, 1))
+    vec = sb.make_vector_field("v", pmesh, 2)
+    vnp1 = sb.make_vector_field("vnp1", pmesh, 2)
+    vec.resize()
+    vec.upload(np.stack([o0, o1], axis=1))
+    sb.make_bc(vec, sb.DIRICHLET, 0.0, 0.0)
+    adapt = sb.make_MRAdapt(vec)
+    mra = sb.mra_config().epsilon(2e-4)
+    a, dt = [1.0, 0.5], 0.5 * pmesh.min_cell_length()
+    for step in range(3):
+        adapt(mra)
+        omesh, (o0, o1) = so.adapt_fields(omesh, [o0, o1], bcs, 2e-4, 1.0)
+        pu.assert_same_mesh(pmesh, omesh)
+        sb.update_ghost_mr(vec)
+        for of in (o0, o1):
+            so.update_ghost_mr(omesh, of, bcs[0])
+        vnp1.resize()
+        sb.upwind_step(vnp1, vec, a, dt)
+        sb.swap(vec, vnp1)
+        o0, o1 = so.fv_step(omesh, o0, a, dt), so.fv_step(omesh, o1, a, dt)
+        _, _, leaf = omesh.leaf_table()
+        got = vec.download()
+        assert got.shape == (omesh.nref, 2)
+        pu.assert_fields_close(got[leaf, 0], o0[leaf], f"component 0 step {step}")
+        pu.assert_fields_close(got[leaf, 1], o1[leaf], f"component 1 step {step}")
