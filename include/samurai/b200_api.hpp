@@ -304,6 +304,25 @@ namespace samurai
             }
         }
 
+        // `Box<double, 2> box({0., 0.}, {1., 1.})` (README.md:96, demos/FiniteVolume/burgers_mra.cpp:265)
+        Box(std::initializer_list<value_t> min_corner, std::initializer_list<value_t> max_corner)
+        {
+            if (min_corner.size() != dim || max_corner.size() != dim)
+            {
+                throw std::invalid_argument("Box corners must have `dim` coordinates");
+            }
+            std::size_t d = 0;
+            for (auto v : min_corner)
+            {
+                m_min[d++] = v;
+            }
+            d = 0;
+            for (auto v : max_corner)
+            {
+                m_max[d++] = v;
+            }
+        }
+
         const point_t& min_corner() const
         {
             return m_min;
@@ -1104,6 +1123,14 @@ namespace samurai
     template <class value_t, class mesh_t>
     auto make_scalar_field(const std::string& name, mesh_t& mesh) // field/scalar_field.hpp:171-215
     {
+        return ScalarField<mesh_t, value_t>(name, mesh);
+    }
+
+    // `make_field<T, n>` only survives in the reference's README (README.md:104,132); kept as an alias of the scalar field
+    template <class value_t, std::size_t n_comp, class mesh_t>
+    auto make_field(const std::string& name, mesh_t& mesh)
+    {
+        static_assert(n_comp == 1, "the device path stores scalar fields (one SoA array per component)");
         return ScalarField<mesh_t, value_t>(name, mesh);
     }
 

@@ -53,3 +53,46 @@ int main(int argc, char** argv) {
     assert r.returncode == 0, r.stderr[-3000:]
     r = subprocess.run([str(exe), "--Tf", "0.01", "--velocity", "2", "3", "--min-corner", "0", "-1"], capture_output=True, text=True, timeout=60)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_scheme_objects_and_readme_spellings_compile(lib, tmp_path):
+    """<samurai/schemes/fv.hpp>: make_convection_upwind (linear and non-linear), make_diffusion_order2, scalar * scheme,
+    rhs = scheme(u), scheme.apply(out, in), unp1 = u - dt * scheme(u); README spellings make_field<double, 1> and
+    Box({..}, {..}); plus tests/cpp/heat_explicit.cpp (the explicit branch of demos/FiniteVolume/heat.cpp)."""
+    code = r'''
+#include <samurai/mr/adapt.hpp>
+#include <samurai/mr/mesh.hpp>
+#include <samurai/samurai.hpp>
+#include <samurai/schemes/fv.hpp>
+int main(int argc, char** argv) {
+    samurai::initialize("schemes", argc, argv);
+    constexpr std::size_t dim = 2;
+    const samurai::Box<double, dim> box({0., 0.}, {1., 1.});
+    auto cfg  = samurai::mesh_config<dim>().min_level(2).max_level(5).max_stencil_size(2).disable_minimal_ghost_width();
+    auto mesh = samurai::mra::make_mesh(box, cfg);
+    auto u    = samurai::make_field<double, 1>("u", mesh);
+    auto unp1 = samurai::make_scalar_field<double>("unp1", mesh);
+    auto rhs  = samurai::make_scalar_field<double>("rhs", mesh);
+    samurai::make_bc<samurai::Dirichlet<1>>(u, 0.);
+    samurai::VelocityVector<dim> velocity;
+    velocity.fill(1);
+    samurai::DiffCoeff<dim> K;
+    K.fill(0.5);
+    auto conv    = samurai::make_convection_upwind<decltype(u)>(velocity);
+    auto burgers = 0.5 * samurai::make_convection_upwind<decltype(u)>();
+    auto diff    = samurai::make_diffusion_order2<decltype(u)>(K);
+    double dt    = 1e-3;
+    rhs          = conv(u);
+    diff.apply(rhs, u);
+    unp1 = u - dt * burgers(u);
+    unp1 = u - dt * diff(u);
+    samurai::finalize();
+    return 0;
+}'''
+    src = tmp_path / "schemes.cpp"
+    src.write_text(code)
+    link = ["-L" + os.path.join(ROOT, "samurai_b200"), "-lsamurai_b200", "-Wl,-rpath," + os.path.join(ROOT, "samurai_b200")]
+    for s, exe in ((src, tmp_path / "schemes"), (os.path.join(ROOT, "tests", "cpp", "heat_explicit.cpp"), tmp_path / "heat")):
+        r = subprocess.run(["g++", "-std=c++20", "-O1", "-I" + os.path.join(ROOT, "include"), "-o", str(exe), str(s)] + link,
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-4000:]
