@@ -94,6 +94,7 @@ namespace smr
         size_t cap  = 0;
         bool shared = false; // peers store into it: must live in the pool when running multi-GPU
         bool pooled = false;
+        size_t min_cap = 0; // first allocation at least this big (index-batch buffers: a regrowth is a cudaFree + cudaMalloc stall)
 
         void ensure(size_t bytes)
         {
@@ -102,7 +103,9 @@ namespace smr
                 release();
                 // every regrowth is a cudaFree + cudaMalloc (a device synchronisation and up to milliseconds): grow
                 // geometrically, generously outside the fixed multi-GPU pool
-                size_t want = bytes + ((shared && g_pool_on) ? bytes / 4 : bytes / 2) + 4096;
+                // (measured: smr_field_resize spent 90-490 ms in cudaFree + cudaMalloc when a 5-12 MB field buffer regrew).
+                // Outside the pool: at least 64 MB (or min_cap) and double, so steady-state runs never reallocate.
+                size_t want = (shared && g_pool_on) ? bytes + bytes / 4 + 4096 : std::max(2 * bytes + 4096, std::max(min_cap, size_t(64) << 20));
                 if (shared && g_pool_on)
                 {
                     want = (want + 255) & ~size_t(255);
@@ -209,6 +212,7 @@ namespace smr
 
         MeshObj()
         {
+            d_arena.min_cap = size_t(48) << 20;
             d_detail.shared = true;
             d_tag.shared    = true;
             d_relmax.shared = true;
@@ -1027,7 +1031,6 @@ namespace smr
         }
         a.barrier      = g.wf_barrier;
         a.barrier_base = g.wf_barrier_at;
-        g.wf_barrier_at += n_barriers * static_cast<unsigned>(grid); // wraps modulo 2^32 like the device counter
         static void* d_trace = nullptr;
         if (trace)
         {
@@ -1059,6 +1062,8 @@ namespace smr
                 wf_launch_t<3, 1>(a, grid, pbytes + jbytes);
                 break;
         }
+        // only a launch that was accepted advances the expected counter value (wraps modulo 2^32 like the device counter)
+        g.wf_barrier_at += n_barriers * static_cast<unsigned>(grid);
         SMR_CUDA(cudaEventRecord(g.wf_done[slot], g.stream));
         ++g.stats.kernel_launches;
         if (g.profile)
@@ -1530,6 +1535,7 @@ namespace smr
         stage(4);
         g.stats.host_batch_seconds += now() - t0;
         DevBuf& d_tr = g.d_transfer;
+        d_tr.min_cap = size_t(16) << 20;
         for (auto* f : fields)
         {
             f->spare.ensure(static_cast<size_t>(nn) * sizeof(double));

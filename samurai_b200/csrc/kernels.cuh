@@ -1292,8 +1292,14 @@ namespace smr
         {
             __threadfence();
             atomicAdd(counter, 1u);
-            while (static_cast<int>(*reinterpret_cast<volatile unsigned*>(counter) - target) < 0)
+            // bounded: a launch whose CTAs were not co-resident (it is launched cooperatively, so this cannot happen) or a
+            // host/device disagreement on the barrier count must not hang the GPU
+            for (long long spins = 0; static_cast<int>(*reinterpret_cast<volatile unsigned*>(counter) - target) < 0; ++spins)
             {
+                if (spins > (1LL << 28))
+                {
+                    break;
+                }
             }
             __threadfence();
         }
