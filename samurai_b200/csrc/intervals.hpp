@@ -7,6 +7,7 @@
 // (row key, x_start, x_end, storage offset) is what gets uploaded to the device.
 #pragma once
 #include <algorithm>
+#include <cstdlib>
 #include <limits>
 #include <cassert>
 #include <cstdint>
@@ -771,6 +772,13 @@ namespace smr
     // row boundaries of at most `max_chunks` chunks holding about `target` intervals each
     inline std::vector<size_t> chunk_rows(const LevelSet& a, size_t target, size_t max_chunks)
     {
+        // tuning knobs (environment, read once): scale the chunk size / the chunk count limit of every caller
+        // (measured on the 16-core box: half the callers' nominal chunk size and twice their chunk count is ~3 % faster per step
+        // than the nominal values, a quarter / four times is slower)
+        static const double target_scale = std::getenv("SMR_CHUNK_SCALE") ? std::atof(std::getenv("SMR_CHUNK_SCALE")) : 0.5;
+        static const long max_override   = std::getenv("SMR_CHUNK_MAX") ? std::atol(std::getenv("SMR_CHUNK_MAX")) : 0;
+        target     = std::max<size_t>(1, static_cast<size_t>(static_cast<double>(target) * target_scale));
+        max_chunks = max_override > 0 ? static_cast<size_t>(max_override) : 2 * max_chunks;
         std::vector<size_t> cut{0};
         const size_t n = a.n_intervals();
         size_t chunks  = std::min(max_chunks, std::max<size_t>(1, n / std::max<size_t>(target, 1)));
