@@ -462,6 +462,30 @@ namespace samurai
             return *this;
         }
 
+        // mesh_config.hpp:224-253.  Periodic meshes are not on the device path yet: the flags are kept
+        // so that demos which expose `--periodic` compile, and a periodic mesh is refused when it is built.
+        auto& periodic(bool p)
+        {
+            m_periodic.fill(p);
+            return *this;
+        }
+
+        auto& periodic(const std::array<bool, dim_>& p)
+        {
+            m_periodic = p;
+            return *this;
+        }
+
+        const std::array<bool, dim_>& periodic() const
+        {
+            return m_periodic;
+        }
+
+        bool periodic(std::size_t d) const
+        {
+            return m_periodic[d];
+        }
+
         void parse_args() // mesh_config.hpp:358-396
         {
             if (!m_disable_args_parse)
@@ -510,6 +534,7 @@ namespace samurai
         double m_scaling_factor        = 0;
         bool m_disable_args_parse          = false;
         bool m_disable_minimal_ghost_width = false;
+        std::array<bool, dim_> m_periodic{};
     };
 
     // ---- mr/mesh.hpp:25-34 ---------------------------------------------------------------------------------------------
@@ -590,6 +615,13 @@ namespace samurai
         MRMesh(const Box<double, dim>& b, const Config& cfg)
             : m_cfg(cfg)
         {
+            for (std::size_t d = 0; d < dim; ++d)
+            {
+                if (cfg.periodic(d))
+                {
+                    throw std::invalid_argument("periodic meshes are not implemented on the device path (update_ghost_periodic, DESIGN.md section 7)");
+                }
+            }
             smr_mesh_config c{};
             c.dim                = static_cast<int32_t>(dim);
             c.min_level          = static_cast<int32_t>(cfg.min_level());
@@ -1027,9 +1059,16 @@ namespace samurai
                 throw std::invalid_argument("only `u - dt * op(a, u)` with the same field u is recognised on the device path");
             }
             double a[3] = {0, 0, 0};
-            for (std::size_t d = 0; d < dim; ++d)
+            if constexpr (std::is_arithmetic_v<A>) // 1D: `upwind(a, u)` with a scalar velocity (advection_1d.cpp:148)
             {
-                a[d] = e.rhs.op.a[d];
+                a[0] = e.rhs.op.a;
+            }
+            else
+            {
+                for (std::size_t d = 0; d < dim; ++d)
+                {
+                    a[d] = e.rhs.op.a[d];
+                }
             }
             const smr_field_t in = e.u->device();
             b200::check(smr_field_resize(handle()));
@@ -1142,10 +1181,60 @@ namespace samurai
     }
 
     // ---- bc/bc.hpp:751-815 -----------------------------------------------------------------------------------------------
+    // make_bc returns a Bc*; `->on(directions...)` restricts it to boundary regions (bc/bc.hpp:326-363, 490-560).  The device
+    // path applies one constant condition on the whole boundary: `on()` is accepted when the directions cover it.
+    template <std::size_t dim>
+    class BcHandle
+    {
+      public:
+
+        BcHandle* operator->()
+        {
+            return this;
+        }
+
+        template <class... Directions>
+        BcHandle& on(const Directions&... directions)
+        {
+            std::array<bool, 2 * dim> seen{};
+            auto mark = [&](const auto& dir)
+            {
+                std::size_t axis = dim;
+                int sign         = 0;
+                for (std::size_t d = 0; d < dim; ++d)
+                {
+                    if (dir[d] != 0)
+                    {
+                        if (axis != dim)
+                        {
+                            throw std::invalid_argument("make_bc(...)->on(): only Cartesian directions are supported on the device path");
+                        }
+                        axis = d;
+                        sign = dir[d] > 0 ? 1 : 0;
+                    }
+                }
+                if (axis != dim)
+                {
+                    seen[2 * axis + static_cast<std::size_t>(sign)] = true;
+                }
+            };
+            (mark(directions), ...);
+            for (bool b : seen)
+            {
+                if (!b)
+                {
+                    throw std::invalid_argument("make_bc(...)->on(): the device path applies one condition on the whole boundary; list every direction");
+                }
+            }
+            return *this;
+        }
+    };
+
     template <class BcType, class Field>
-    void make_bc(Field& u, double value)
+    auto make_bc(Field& u, double value)
     {
         u.attach_bc(BcType::type, value);
+        return BcHandle<Field::dim>();
     }
 
     // ---- stencil_field.hpp:175-179, 245-249 ------------------------------------------------------------------------------

@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = "/root/reference/demos/FiniteVolume"
 
 
-@pytest.mark.parametrize("demo", ["advection_2d", "advection_3d", "scalar_burgers_2d"])
+@pytest.mark.parametrize("demo", ["advection_1d", "advection_2d", "advection_3d", "scalar_burgers_2d"])
 def test_reference_demo_compiles_unchanged(lib, tmp_path, demo):
     src = os.path.join(REF, demo + ".cpp")
     if not os.path.exists(src):

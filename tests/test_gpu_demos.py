@@ -68,3 +68,28 @@ def test_cpp_heat_explicit_matches_reference_golden(gpu, tmp_path):
     assert np.array_equal(got[:, 0].astype(np.int64), g["level"].astype(np.int64))
     assert np.array_equal(got[:, 1:3].astype(np.int64), g["idx"].astype(np.int64)), "mesh differs"
     assert np.max(np.abs(got[:, 3] - g["u"])) <= 1e-15
+
+
+def test_reference_advection_1d_demo_unchanged_matches_oracle(gpu, tmp_path):
+    """demos/FiniteVolume/advection_1d.cpp compiled unchanged (scalar velocity, `make_bc<Dirichlet<1>>(u, 0.)->on(left, right)`,
+    `mesh_config().periodic(false)`), run with the reference test's `--Tf 0.1` (tests/test_demo_finite_volume.py:21-52) and
+    compared with the oracle's run of the same loop: box [-2, 2], levels 6-12, eps 2e-4, cfl 0.95, a = 1."""
+    import sys
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import samurai_oracle as so
+
+    exe = os.path.join(DEMOS, "finite-volume-advection-1d")
+    if not os.path.exists(exe):
+        pytest.skip("demo binary not built (needs /root/reference at build time)")
+    r = subprocess.run([exe, "--path", str(tmp_path), "--filename", "adv1d", "--Tf", "0.1"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert os.path.exists(tmp_path / "adv1d.csv"), os.listdir(tmp_path)
+    got = _load_csv(tmp_path / "adv1d.csv")
+    cfg = so.MeshConfig(dim=1, min_level=6, max_level=12, pred_radius=1, origin=(-2.0,), scaling=4.0)
+    res = so.run_advection(cfg, Tf=0.1, eps=2e-4, a=[1.0], cfl=0.95, center=[0.0], radius=0.2)
+    mesh, u = res["final"]
+    lv, co, ix = mesh.leaf_table()
+    assert got.shape[0] == lv.size, f"{got.shape[0]} cells vs oracle {lv.size}"
+    assert np.array_equal(got[:, 0].astype(np.int64), lv) and np.array_equal(got[:, 1].astype(np.int64), co[:, 0]), "mesh differs"
+    assert np.max(np.abs(got[:, 2] - u[ix])) <= 1e-13  # columns: level, i, u, level
