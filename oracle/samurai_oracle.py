@@ -12,8 +12,11 @@ element-wise arithmetic (no FMA, IEEE round-to-nearest), written in the
 reference's operation order so results are bit-comparable.
 
 Parity pin: `tests/test_oracle_golden.py` checks this oracle against the
-reference's golden HDF5 files (advection_2d, prediction radius 0 and 1, initial
-and final meshes + fields) -- see tests/golden/make_golden.py.
+reference's golden HDF5 files -- advection_2d (prediction radius 0 and 1, initial
+and final meshes + fields) for the field-expression path, and heat.cpp --explicit
+(test_finite_volume_demo_heat_explicit.h5) for the flux-based schemes across level
+jumps -- see tests/golden/make_golden.py.  Unpinned (no golden in the snapshot):
+upwind_scalar_burgers, the non-linear flux scheme, everything 3D.
 
 Reference (hpc-maths/samurai v0.33.0, paths relative to include/samurai/):
   mesh construction      mesh.hpp:326-341,426-439,894-911,1160-1262  mr/mesh.hpp:222-455
@@ -24,6 +27,9 @@ Reference (hpc-maths/samurai v0.33.0, paths relative to include/samurai/):
   mesh from tags         algorithm/graduation.hpp:245-330,573-842
   field transfer         algorithm/update_fields.hpp:27-54
   FV operators           stencil_field.hpp:16-243
+  flux-based schemes     schemes/fv/flux_based/{flux_based_scheme,explicit_flux_based_scheme}__{lin_hom,nonlin}.hpp
+                         interface.hpp:35-306,440-509  schemes/fv/operators/{convection_lin,convection_nonlin,diffusion}.hpp
+  relative detail        mr/rel_detail.hpp:73-112
 Supported scope: non-periodic box domains, scalar fp64 fields, ghost width 1
 (max_stencil_radius = 1, prediction radius 0 or 1), Dirichlet<1>/Neumann<1>
 constant BCs -- exactly what BASELINE.json's configs use.
