@@ -178,9 +178,8 @@ extern "C"
         uint64_t ghost_updates_skipped; /* smr_update_ghost_mr calls answered by the ghosts_updated flag            */
         uint64_t harten_iterations;     /* iterations of the adaptation loop (mr/adapt.hpp:277-389)                  */
         /* host stages: 0 tags -> new leaves, 1 mesh equality tests, 2 make_graduation, 3 sub-mesh construction,
-         * 4 field-transfer batches, 5 per-mesh batches (the part not hidden behind stage 4), 6 waiting for the device before a host stage, 7 releasing the old mesh */
+         * 4 field-transfer batches, 5 per-mesh batches, 6 waiting for the device before a host stage, 7 releasing the old mesh */
         double host_stage_seconds[8];
-        double plan_overlap_seconds; /* batch building of a new mesh that ran on the worker thread behind the field transfer */
     } smr_stats;
 
     int smr_stats_get(smr_stats* out); /* synchronises the stream to resolve device_seconds */

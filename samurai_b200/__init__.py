@@ -56,7 +56,6 @@ class StatsC(C.Structure):
         ("ghost_updates_skipped", C.c_uint64),
         ("harten_iterations", C.c_uint64),
         ("host_stage_seconds", C.c_double * 8),
-        ("plan_overlap_seconds", C.c_double),
     ]
 
 

@@ -5,9 +5,6 @@
 #include "kernels.cuh"
 
 #include <chrono>
-#include <condition_variable>
-#include <mutex>
-#include <thread>
 #include <cmath>
 #include <memory>
 #include <string>
@@ -194,19 +191,12 @@ namespace smr
         Mesh mesh;
         MeshPlan plan;
         bool plan_ready = false;
-        bool plan_pending = false; // the batches are being built by the plan worker
-        bool plan_built   = false; // ... and are ready in the host arena, not uploaded yet
         double plan_seconds = 0;
         DevBuf d_arena;
         FluxPlan flux; // flux-based schemes on multi-level meshes, built on first use
         DevBuf d_flux, d_fluxtab;
 
-        void invalidate_plans(); // waits for a build in flight, then marks every plan stale
-
-        ~MeshObj()
-        {
-            invalidate_plans();
-        }
+        void invalidate_plans();
         DevBuf d_detail, d_tag, d_relmax;
         PlanFilter filter; // multi-GPU slab ownership for this mesh (identity when world == 1)
 
@@ -406,8 +396,6 @@ namespace smr
         }
     }
 
-    static void settle_plan(MeshObj& mo); // waits for the batches a worker thread may still be building for this mesh
-
     static MeshObj& get_mesh(smr_mesh_t h)
     {
         auto it = g.meshes.find(h);
@@ -415,7 +403,6 @@ namespace smr
         {
             throw std::invalid_argument("invalid mesh handle");
         }
-        settle_plan(*it->second);
         return *it->second;
     }
 
@@ -426,7 +413,6 @@ namespace smr
         {
             throw std::invalid_argument("invalid field handle");
         }
-        settle_plan(*it->second->mesh);
         return *it->second;
     }
 
@@ -528,133 +514,9 @@ namespace smr
         mo.plan_seconds = now() - t0;
     }
 
-    // After an adaptation the batches of the new mesh are built on a second host thread while the calling thread builds
-    // the field-transfer batches and queues the transfer: the two traversals are independent (both only read the meshes).
-    struct PlanWorker
-    {
-        std::thread th;
-        std::mutex m;
-        std::condition_variable cv;
-        MeshObj* job = nullptr;
-        bool busy    = false;
-        bool quit    = false;
-        std::string error;
-
-        void loop()
-        {
-            if (g.device)
-            {
-                cudaSetDevice(g.dev); // the arena grows through cudaHostAlloc
-            }
-            std::unique_lock<std::mutex> lk(m);
-            for (;;)
-            {
-                cv.wait(lk, [&] { return job != nullptr || quit; });
-                if (quit)
-                {
-                    return;
-                }
-                MeshObj* mo = job;
-                lk.unlock();
-                std::string err;
-                try
-                {
-                    build_plan_host(*mo);
-                }
-                catch (const std::exception& e)
-                {
-                    err = e.what();
-                    if (err.empty())
-                    {
-                        err = "plan build failed";
-                    }
-                }
-                lk.lock();
-                error = err;
-                job   = nullptr;
-                busy  = false;
-                cv.notify_all();
-            }
-        }
-
-        void start(MeshObj* mo)
-        {
-            std::unique_lock<std::mutex> lk(m);
-            if (!th.joinable())
-            {
-                th = std::thread([this] { loop(); });
-            }
-            cv.wait(lk, [&] { return !busy; });
-            error.clear();
-            job  = mo;
-            busy = true;
-            cv.notify_all();
-        }
-
-        void wait()
-        {
-            std::unique_lock<std::mutex> lk(m);
-            cv.wait(lk, [&] { return !busy; });
-            if (!error.empty())
-            {
-                const std::string e = error;
-                error.clear();
-                throw std::out_of_range(e);
-            }
-        }
-
-        ~PlanWorker()
-        {
-            stop();
-        }
-
-        void stop()
-        {
-            {
-                std::unique_lock<std::mutex> lk(m);
-                cv.wait(lk, [&] { return !busy; });
-                quit = true;
-                cv.notify_all();
-            }
-            if (th.joinable())
-            {
-                th.join();
-            }
-            quit = false;
-        }
-    };
-
-    static PlanWorker g_plan_worker;
-
-    static void settle_plan(MeshObj& mo)
-    {
-        if (mo.plan_pending)
-        {
-            const double tw0 = now();
-            mo.plan_pending  = false;
-            g_plan_worker.wait(); // rethrows a failure of the build
-            mo.plan_built = true;
-            g.stats.host_stage_seconds[5] += now() - tw0; // only the part the caller had to wait for
-            g.stats.host_batch_seconds += now() - tw0;
-            g.stats.plan_overlap_seconds += std::max(0.0, mo.plan_seconds - (now() - tw0));
-        }
-    }
-
     void MeshObj::invalidate_plans()
     {
-        if (plan_pending)
-        {
-            plan_pending = false;
-            try
-            {
-                g_plan_worker.wait();
-            }
-            catch (...)
-            {
-            }
-        }
         plan_ready = false;
-        plan_built = false;
         flux.ready = false;
     }
 
@@ -664,15 +526,10 @@ namespace smr
         {
             return;
         }
-        settle_plan(mo);
-        if (!mo.plan_built)
-        {
-            update_filter(mo);
-            build_plan_host(mo);
-            g.stats.host_batch_seconds += mo.plan_seconds;
-            g.stats.host_stage_seconds[5] += mo.plan_seconds;
-        }
-        mo.plan_built = false;
+        update_filter(mo);
+        build_plan_host(mo);
+        g.stats.host_batch_seconds += mo.plan_seconds;
+        g.stats.host_stage_seconds[5] += mo.plan_seconds;
         // the previous arena may still be in use by queued kernels: stream-ordered, so a sync is needed before reuse
         const double tw = now();
         SMR_CUDA(cudaStreamSynchronize(g.stream));
@@ -1509,22 +1366,13 @@ namespace smr
         g.stats.host_mesh_seconds += now() - t0;
         ++g.stats.mesh_rebuilds;
 
-        // the new mesh takes its place; its batches are built on the worker thread while this thread builds the transfer
+        // the new mesh takes its place (building its batches on a second host thread behind the transfer was tried: two OpenMP
+        // teams on the 16-core box made the step slower, 6.2 -> 10.8 ms, also with the cores split between the teams)
         const int64_t nn = new_mesh->nref;
         Mesh old_mesh    = std::move(mo.mesh);
         mo.mesh          = std::move(*new_mesh);
         new_mesh.reset();
         mo.invalidate_plans();
-        // opt-in: with one OpenMP team per host thread the two traversals oversubscribe the cores and the step got slower
-        // on the 16-core box (6.5 -> 9.5 ms); worth it only with cores to spare
-        static const bool overlap = std::getenv("SMR_PLAN_OVERLAP") != nullptr;
-        if (overlap)
-        {
-            update_filter(mo);
-            mo.plan_pending = true;
-            g_plan_worker.start(&mo);
-        }
-
         // update_fields (algorithm/update_fields.hpp:27-54,101-127)
         t0 = now();
         TransferPlan& tpn = g.transfer;
