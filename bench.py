@@ -123,6 +123,13 @@ class ClockSampler:
             self._stop.set()
             self.t.join(timeout=2)
             n = self.nvml
+            try:  # one more reading right at the end of the timed region (short runs may fit between two periodic samples)
+                rs = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.samples.append((float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)),
+                                     float(n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)), int(rs)))
+            except Exception:
+                pass
             names = (("hw_slowdown", getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8)),
                      ("hw_thermal_slowdown", getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40)),
                      ("sw_thermal_slowdown", getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20)),
