@@ -2,7 +2,8 @@
 // No CPU fallback: every compute entry point requires a device and fails loudly otherwise.
 #include "../../include/samurai_b200.h"
 #include "batches.hpp"
-#include "kernels.cuh"
+#define SMR_MISC_KERNELS
+#include "launch.hpp"
 
 #include <chrono>
 #include <cmath>
@@ -257,6 +258,7 @@ namespace smr
         void* wf_dev       = nullptr;
         unsigned* wf_barrier   = nullptr;
         unsigned wf_barrier_at = 0;
+        unsigned* wf_error_host = nullptr; // pinned copy of the wavefront error word (kernels.cuh: SMR_WF_ERROR_WORD)
         int wf_next        = 0;
         cudaEvent_t wf_done[16] = {};
         // multi-GPU
@@ -271,6 +273,31 @@ namespace smr
     };
 
     static Ctx g;
+
+    // every kernel translation unit holds its own copy of the __constant__ peer table (kernels.cuh: g_peers)
+    static std::vector<PeerSetter>& peer_setters()
+    {
+        static std::vector<PeerSetter> v;
+        return v;
+    }
+
+    void register_peer_setter(PeerSetter f)
+    {
+        peer_setters().push_back(f);
+    }
+
+    cudaError_t set_peer_table(const PeerTable& t)
+    {
+        cudaError_t e = cudaMemcpyToSymbol(g_peers, &t, sizeof(t)); // this unit's copy (mg_barrier_kernel, publish_slot_kernel)
+        for (PeerSetter f : peer_setters())
+        {
+            if (e == cudaSuccess)
+            {
+                e = f(t);
+            }
+        }
+        return e;
+    }
 
     static double now()
     {
@@ -316,7 +343,34 @@ namespace smr
                 cudaEventRecord(ev.second, g.stream);
                 g.pending.push_back(ev);
                 ev.first = nullptr;
+                if (g.pending.size() > 64)
+                {
+                    retire_finished();
+                }
             }
+        }
+
+        // a program that never polls the statistics must not accumulate events: fold the sections the device has already
+        // finished into the total and recycle their events (no synchronisation)
+        static void retire_finished()
+        {
+            size_t keep = 0;
+            for (size_t i = 0; i < g.pending.size(); ++i)
+            {
+                auto& p = g.pending[i];
+                float ms = 0;
+                if (cudaEventQuery(p.second) == cudaSuccess && cudaEventElapsedTime(&ms, p.first, p.second) == cudaSuccess)
+                {
+                    g.stats.device_seconds += ms * 1e-3;
+                    g.pool.push_back(p);
+                }
+                else
+                {
+                    g.pending[keep++] = p;
+                }
+            }
+            g.pending.resize(keep);
+            (void) cudaGetLastError(); // cudaErrorNotReady from the queries is not an error
         }
 
         ~Section()
@@ -564,8 +618,7 @@ namespace smr
             throw std::logic_error("batch laid out for a different CTA size than its kernel");
         }
         const int n_ctas = static_cast<int>((n_cells + b.cta_units - 1) / b.cta_units);
-        batch_kernel<Item, Op><<<n_ctas, SMR_CTA_THREADS, 0, g.stream>>>(view_of<Item>(arena, b, n_cells), op);
-        SMR_CUDA(cudaGetLastError());
+        SMR_CUDA((launch_batch<Item, Op>(n_ctas, g.stream, view_of<Item>(arena, b, n_cells), op)));
         ++g.stats.kernel_launches;
         prof_end(fam, n_cells);
         mg_barrier();
@@ -593,19 +646,7 @@ namespace smr
         }
         const int grid = ph.bc.n_ctas + ph.proj.n_ctas;
         prof_begin();
-        switch (dim)
-        {
-            case 1:
-                ghost_phase_kernel<1><<<grid, SMR_CTA_THREADS, 0, g.stream>>>(bc, ph.bc.n_ctas, pv, f);
-                break;
-            case 2:
-                ghost_phase_kernel<2><<<grid, SMR_CTA_THREADS, 0, g.stream>>>(bc, ph.bc.n_ctas, pv, f);
-                break;
-            default:
-                ghost_phase_kernel<3><<<grid, SMR_CTA_THREADS, 0, g.stream>>>(bc, ph.bc.n_ctas, pv, f);
-                break;
-        }
-        SMR_CUDA(cudaGetLastError());
+        SMR_CUDA(launch_ghost_phase_kernel(dim, grid, g.stream, bc, ph.bc.n_ctas, pv, f));
         ++g.stats.kernel_launches;
         prof_end(ph.proj.n_cells >= ph.bc.n_items ? SMR_FAM_PROJ : SMR_FAM_BC, ph.proj.n_cells + ph.bc.n_items);
         mg_barrier();
@@ -783,17 +824,40 @@ namespace smr
     template <int DIM, int RADIUS>
     static void wf_launch_t(WfArgs& a, int grid, size_t smem)
     {
-        void* args[] = {&a};
-        SMR_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(&wavefront_kernel<DIM, RADIUS>), dim3(static_cast<unsigned>(grid)),
-                                             dim3(SMR_CTA_THREADS), args, smem, g.stream));
+        SMR_CUDA((wf_launch_inst<DIM, RADIUS>(a, grid, smem, g.stream)));
     }
 
     template <int DIM, int RADIUS>
     static int wf_occupancy()
     {
-        int per_sm = 0;
-        SMR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wavefront_kernel<DIM, RADIUS>, SMR_CTA_THREADS, WF_SLOT_BYTES));
+        const int per_sm = wf_occupancy_inst<DIM, RADIUS>(WF_SLOT_BYTES);
+        if (per_sm < 0)
+        {
+            throw CudaError("cudaOccupancyMaxActiveBlocksPerMultiprocessor(wavefront_kernel) failed");
+        }
         return per_sm;
+    }
+
+    // queue the read-back of the wavefront error word; wf_check_error() after the next stream synchronisation throws if a
+    // grid barrier timed out (the launch then left its outputs incomplete)
+    static void wf_fetch_error()
+    {
+        if (g.wf_barrier != nullptr)
+        {
+            SMR_CUDA(cudaMemcpyAsync(g.wf_error_host, g.wf_barrier + SMR_WF_ERROR_WORD, sizeof(unsigned), cudaMemcpyDeviceToHost, g.stream));
+        }
+    }
+
+    static void wf_check_error()
+    {
+        if (g.wf_error_host != nullptr && *g.wf_error_host != 0u)
+        {
+            const unsigned at = *g.wf_error_host;
+            *g.wf_error_host  = 0;
+            cudaMemsetAsync(g.wf_barrier, 0, 256, g.stream);
+            g.wf_barrier_at = 0;
+            throw CudaError("fused wavefront: grid barrier timed out (target " + std::to_string(at) + "); results of that launch are invalid");
+        }
     }
 
     // run the phases of `wb` (offsets relative to `arena`) in one cooperative launch
@@ -810,6 +874,8 @@ namespace smr
             SMR_CUDA(cudaMalloc(&g.wf_dev, WF_SLOTS * WF_SLOT_BYTES));
             SMR_CUDA(cudaMalloc(&g.wf_barrier, 256));
             SMR_CUDA(cudaMemset(g.wf_barrier, 0, 256));
+            SMR_CUDA(cudaMallocHost(reinterpret_cast<void**>(&g.wf_error_host), 64));
+            *g.wf_error_host = 0;
             for (int i = 0; i < WF_SLOTS; ++i)
             {
                 SMR_CUDA(cudaEventCreateWithFlags(&g.wf_done[i], cudaEventDisableTiming));
@@ -996,6 +1062,10 @@ namespace smr
         }
         for (size_t i = 0; i < fields.size(); ++i)
         {
+            if (fields[i]->bc_type < 0)
+            {
+                throw std::invalid_argument("field '" + fields[i]->name + "' has no boundary condition attached (make_bc)");
+            }
             a.dst[i]      = static_cast<double*>(fields[i]->data.p);
             a.src[i]      = a.dst[i];
             a.bc_type[i]  = fields[i]->bc_type;
@@ -1302,7 +1372,9 @@ namespace smr
         mo.h_tag.ensure(static_cast<size_t>(flag_at) + 16);
         SMR_CUDA(cudaMemcpyAsync(mo.h_tag.p, tag, static_cast<size_t>(fused_flag ? flag_at + 16 : n), cudaMemcpyDeviceToHost, g.stream));
         sec1.close();
+        wf_fetch_error();
         SMR_CUDA(cudaStreamSynchronize(g.stream));
+        wf_check_error();
         g.stats.d2h_bytes += static_cast<uint64_t>(n);
         mo.last_size  = n;
         mo.last_ncomp = ncomp;
@@ -1587,7 +1659,9 @@ extern "C"
             [&]
             {
                 require_device();
+                wf_fetch_error();
                 SMR_CUDA(cudaStreamSynchronize(g.stream));
+                wf_check_error();
             });
     }
 
@@ -1937,6 +2011,10 @@ extern "C"
                 if (bc_type != SMR_BCTYPE_DIRICHLET && bc_type != SMR_BCTYPE_NEUMANN)
                 {
                     throw std::invalid_argument("unknown boundary condition type");
+                }
+                if (f.bc_type != bc_type || f.bc_value != value)
+                {
+                    f.ghosts_valid = false; // the boundary ghosts depend on the condition: the next update must not be skipped
                 }
                 f.bc_type  = bc_type;
                 f.bc_value = value;
@@ -2300,7 +2378,7 @@ extern "C"
                     }
                     t.delta[p] = static_cast<long long>(static_cast<char*>(g.mg_peer_base[p]) - static_cast<char*>(g.mg_pool));
                 }
-                SMR_CUDA(cudaMemcpyToSymbol(g_peers, &t, sizeof(t)));
+                SMR_CUDA(set_peer_table(t));
                 g.mg_connected = true;
             });
     }

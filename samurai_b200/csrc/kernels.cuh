@@ -55,6 +55,7 @@ namespace smr
         }
     }
 
+#ifdef SMR_MISC_KERNELS // non-template kernels: compiled by capi.cu only
     // all ranks have finished everything queued before this kernel (and their peer stores have landed) once it returns
     __global__ void mg_barrier_kernel(unsigned long long epoch)
     {
@@ -78,6 +79,7 @@ namespace smr
             }
         }
     }
+#endif
 
     // Field pointers of an op: __restrict__ (read-only data path, loads hoisted above stores) when the op runs as its own
     // launch; plain when it runs inside the fused wavefront kernel, where other phases of the same launch write the arrays
@@ -1009,6 +1011,7 @@ namespace smr
         }
     };
 
+#ifdef SMR_MISC_KERNELS
     // publish this rank's slot into every peer's table (multi-GPU), one thread per peer
     __global__ void publish_slot_kernel(unsigned long long* slots)
     {
@@ -1038,6 +1041,7 @@ namespace smr
             detail[i] *= inv;
         }
     }
+#endif
 
     // tag[leaf] = keep (mr/adapt.hpp:286-290), driven by the FV leaf batch
     template <bool RESTRICT = true>
@@ -1251,6 +1255,7 @@ namespace smr
     };
 
     #define SMR_WF_MAX_FIELDS 8
+    #define SMR_WF_ERROR_WORD 16 /* word index (from the barrier counter) of the launch error word */
     #define SMR_WF_ZERO_BYTES 16384 /* bytes cleared by one CTA-chunk of a WF_ZERO_* job */
 
     struct WfArgs
@@ -1285,8 +1290,11 @@ namespace smr
 
     // Grid-wide barrier of the cooperative launch (all CTAs co-resident): one atomic arrival per CTA on a monotonic
     // counter, thread 0 spins until the whole grid has arrived.  Lighter than cooperative_groups' grid.sync().
-    __device__ __forceinline__ void wf_grid_barrier(unsigned* counter, unsigned target)
+    // Returns false when the wait timed out: the caller raises the launch's error word (counter[SMR_WF_ERROR_WORD]) and
+    // every CTA leaves the kernel instead of running on unsynchronised.
+    __device__ __forceinline__ bool wf_grid_barrier(unsigned* counter, unsigned target)
     {
+        __shared__ int s_ok;
         __syncthreads();
         if (threadIdx.x == 0)
         {
@@ -1296,14 +1304,17 @@ namespace smr
             // host/device disagreement on the barrier count must not hang the GPU
             for (long long spins = 0; static_cast<int>(*reinterpret_cast<volatile unsigned*>(counter) - target) < 0; ++spins)
             {
-                if (spins > (1LL << 28))
+                if (spins > (1LL << 28) || *reinterpret_cast<volatile unsigned*>(counter + SMR_WF_ERROR_WORD) != 0u)
                 {
+                    atomicExch(counter + SMR_WF_ERROR_WORD, target | 1u); // sticky: the host throws at its next synchronisation
                     break;
                 }
             }
+            s_ok = *reinterpret_cast<volatile unsigned*>(counter + SMR_WF_ERROR_WORD) == 0u;
             __threadfence();
         }
         __syncthreads();
+        return s_ok != 0;
     }
 
     template <class Item>
@@ -1521,7 +1532,10 @@ namespace smr
                 else
                 {
                     ++barriers;
-                    wf_grid_barrier(a.barrier, a.barrier_base + barriers * gridDim.x);
+                    if (!wf_grid_barrier(a.barrier, a.barrier_base + barriers * gridDim.x))
+                    {
+                        return; // barrier timed out: error word raised, results are invalid and the host will throw
+                    }
                 }
             }
         }
