@@ -75,17 +75,66 @@ def assert_fields_close(a, b, what, tol=REL_TOL, finite_only=False):
     return err
 
 
+def init_square(omesh, half=0.1):
+    """README.md:111-118: u = 1 where every |center_d - 0.5| <= 0.5 * 0.2."""
+    u = np.zeros(omesh.nref)
+    for l in omesh.leaf_levels():
+        k = omesh.cells[l]
+        c = omesh.cell_centers(l, k)
+        u[omesh.index(l, k)] = np.where(np.all(np.abs(c - 0.5) <= half, axis=1), 1.0, 0.0)
+    return u
+
+
+def adapt_both(adapt, mcfg, pmesh, omesh, ou, bc, eps, regularity, relative_detail=False, trace_tags=False, what=""):
+    """One MRadaptation call on both sides.  With trace_tags the product runs iteration by iteration (smr_adapt_iteration)
+    and the tag array (uint8, every reference cell) and the detail array (fp64, every reference cell) of EVERY harten
+    iteration are compared with the oracle's: tags bit-exact (north_star), details within REL_TOL (observed: bit-exact)."""
+    if not trace_tags:
+        adapt(mcfg)
+        return so.adapt(omesh, ou, bc, eps, regularity, relative_detail=relative_detail)
+    trace = []
+    omesh2, ou2 = so.adapt(omesh, ou, bc, eps, regularity, trace=trace, relative_detail=relative_detail)
+    cfg = omesh.cfg
+    n_ite = 0
+    for ite in range(cfg.max_level - cfg.min_level):
+        unchanged = adapt.iteration(mcfg, ite)
+        n_ite += 1
+        assert ite < len(trace), f"{what}: product ran more harten iterations than the oracle ({len(trace)})"
+        ref = trace[ite]
+        tags = adapt.last_tags()
+        assert tags.size == ref["tag"].size, f"{what} ite {ite}: tag array size {tags.size} vs {ref['tag'].size}"
+        bad = np.flatnonzero(tags != ref["tag"])
+        assert bad.size == 0, f"{what} ite {ite}: {bad.size} tag bytes differ (first at {bad[:5]}: {tags[bad[:5]]} vs {ref['tag'][bad[:5]]})"
+        det = adapt.last_detail()
+        assert det.size == ref["detail"].size
+        assert_fields_close(det, ref["detail"], f"{what} ite {ite} detail")
+        if unchanged:
+            break
+    assert n_ite == len(trace), f"{what}: {n_ite} harten iterations vs {len(trace)} in the oracle"
+    return omesh2, ou2
+
+
 def run_advection_parity(dim=2, min_level=2, max_level=6, pred_radius=1, steps=3, eps=2e-4, regularity=1.0, device=0, verbose=False,
-                         scheme="upwind", relative_detail=False, amplitude=1.0):
+                         scheme="upwind", relative_detail=False, amplitude=1.0, init="disc", trace_tags=False, a=None, cfl=None,
+                         discs=None, check_ghosts=True):
     """demos/FiniteVolume/advection_2d.cpp time loop on the GPU, checked against the oracle at every step:
-    meshes bit-identical (cells + all ghosts + storage offsets), fields within 1e-12 relative."""
+    meshes bit-identical (cells + all ghosts + storage offsets), fields within 1e-12 relative; with trace_tags also the
+    tag and detail arrays of every harten iteration.  `discs`: [(center, radius, value)] initial condition
+    (scalar_burgers_2d.cpp:20-50); init="square": README.md:111-118."""
     if not sb.initialize(device):
         raise sb.SamuraiError("a CUDA device is required")
     ocfg = oracle_cfg(dim, min_level, max_level, pred_radius)
     bc = so.Bc("dirichlet", 0.0)
     omesh = so.Mesh.uniform(ocfg)
-    center, radius = [0.3] * dim, 0.2
-    ou = so.init_disc(omesh, center, radius) * amplitude
+    if discs is not None:
+        ou = np.zeros(omesh.nref)
+        for center, radius, value in discs:
+            m = so.init_disc(omesh, center, radius)
+            ou = np.where(m != 0, value, ou)
+    elif init == "square":
+        ou = init_square(omesh) * amplitude
+    else:
+        ou = so.init_disc(omesh, [0.3] * dim, 0.2) * amplitude
 
     pmesh = sb.MRMesh.make_mesh([0.0] * dim, [1.0] * dim, product_cfg(dim, min_level, max_level, pred_radius))
     assert_same_mesh(pmesh, omesh)
@@ -96,28 +145,32 @@ def run_advection_parity(dim=2, min_level=2, max_level=6, pred_radius=1, steps=3
     unp1 = sb.make_scalar_field("unp1", pmesh)
     adapt = sb.make_MRAdapt(u)
     mcfg = sb.mra_config().epsilon(eps).regularity(regularity).relative_detail(relative_detail)
-    a = [1.0] * dim
-    dt = 0.5 * pmesh.min_cell_length() if dim == 2 else 0.25 * pmesh.min_cell_length()
+    a = [1.0] * dim if a is None else list(a)
+    if cfl is None:
+        cfl = 0.5 if dim == 2 else 0.25
+    dt = cfl * pmesh.min_cell_length()
+    worst = 0.0
 
     def check(tag):
+        nonlocal worst
         assert_same_mesh(pmesh, omesh)
         _, _, leaf_idx = omesh.leaf_table()
         pu = u.download()
         err = assert_fields_close(pu[leaf_idx], ou[leaf_idx], tag)
+        worst = max(worst, err)
         if verbose:
             print(f"{tag}: leaves {omesh.nb_cells()} ref {omesh.nref} max rel err {err:.2e}")
 
-    adapt(mcfg)
-    omesh, ou = so.adapt(omesh, ou, bc, eps, regularity, relative_detail=relative_detail)
+    omesh, ou = adapt_both(adapt, mcfg, pmesh, omesh, ou, bc, eps, regularity, relative_detail, trace_tags and not relative_detail, "initial adaptation")
     check("initial adaptation")
     for it in range(steps):
-        adapt(mcfg)
-        omesh, ou = so.adapt(omesh, ou, bc, eps, regularity, relative_detail=relative_detail)
+        omesh, ou = adapt_both(adapt, mcfg, pmesh, omesh, ou, bc, eps, regularity, relative_detail, trace_tags and not relative_detail, f"step {it}")
         sb.update_ghost_mr(u)
         so.update_ghost_mr(omesh, ou, bc)
-        # after the ghost update every reference cell the oracle defines must agree
-        pu = u.download()
-        assert_fields_close(pu, ou, f"step {it} ghosts", finite_only=True)
+        if check_ghosts:
+            # after the ghost update every reference cell the oracle defines must agree
+            pu = u.download()
+            assert_fields_close(pu, ou, f"step {it} ghosts", finite_only=True)
         unp1.resize()
         if scheme == "upwind":
             sb.upwind_step(unp1, u, a, dt)
@@ -126,6 +179,8 @@ def run_advection_parity(dim=2, min_level=2, max_level=6, pred_radius=1, steps=3
         ou = so.fv_step(omesh, ou, a, dt, scheme=scheme)
         sb.swap(u, unp1)
         check(f"step {it}")
+    leaves = omesh.nb_cells()
     u.destroy()
     unp1.destroy()
     pmesh.destroy()
+    return dict(leaves=leaves, max_rel_err=worst)
