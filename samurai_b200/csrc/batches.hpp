@@ -61,6 +61,7 @@ namespace smr
 
         static inline void* (*alloc_fn)(size_t) = nullptr;
         static inline size_t min_pinned_cap    = size_t(48) << 20;
+        size_t min_cap = 0; // this arena's own floor (0: min_pinned_cap when pinned)
         static inline void (*free_fn)(void*)    = nullptr;
 
         Arena()                        = default;
@@ -89,9 +90,43 @@ namespace smr
             cap = 0;
         }
 
+        // Device-only region: records the device derives itself (derive.cuh) are laid out behind the uploaded bytes; the
+        // host buffer never holds them.  take_dev() hands out offsets relative to the region, close_layout() turns them
+        // into arena offsets once the size of the uploaded part is known.
+        size_t dev_size = 0;
+        size_t dev_base = 0;
+        std::vector<int64_t*> dev_fixups;
+
         void clear()
         {
-            size = 0;
+            size     = 0;
+            dev_size = 0;
+            dev_base = 0;
+            dev_fixups.clear();
+        }
+
+        void take_dev(size_t bytes, int64_t* where)
+        {
+            dev_size = (dev_size + 15) & ~size_t(15);
+            *where   = static_cast<int64_t>(dev_size);
+            dev_size += bytes;
+            dev_fixups.push_back(where);
+        }
+
+        void close_layout()
+        {
+            dev_base = (size + 255) & ~size_t(255);
+            for (int64_t* w : dev_fixups)
+            {
+                *w += static_cast<int64_t>(dev_base);
+            }
+            dev_fixups.clear();
+        }
+
+        // bytes the device buffer needs (uploaded part + derived records)
+        size_t device_bytes() const
+        {
+            return dev_size ? dev_base + dev_size : size;
         }
 
         // layout pass: reserve `bytes` (16-byte aligned) and return their offset
@@ -111,7 +146,7 @@ namespace smr
                 release();
                 // pinned when the C ABI installs alloc_fn: pinning pages (and mapping them for every GPU of the box) was
                 // measured at ~300 ms per regrowth, so start generously and double
-                cap = std::max<size_t>(2 * size + 4096, alloc_fn ? min_pinned_cap : 0);
+                cap = std::max<size_t>(2 * size + 4096, alloc_fn ? (min_cap ? min_cap : min_pinned_cap) : 0);
                 p   = static_cast<uint8_t*>(alloc_fn ? alloc_fn(cap) : std::malloc(cap));
                 if (!p)
                 {
@@ -281,6 +316,203 @@ namespace smr
             first[c] = static_cast<int32_t>(it);
         }
         first[b.n_ctas] = b.n_items - 1;
+    }
+
+    // ---------------------------------------------------------------------------------------------------------
+    // Batches whose records the DEVICE derives (derive.cuh): the host lays out seeds + prefix + per-CTA table in the
+    // uploaded part of the arena and reserves the records in the device-only part.
+    // ---------------------------------------------------------------------------------------------------------
+    struct DeriveList
+    {
+        std::vector<smr_derive_job> jobs;
+        int64_t jobs_off = -1; // uploaded copy of `jobs`
+        int blocks       = 0;  // CTAs of the derive launch
+
+        void clear()
+        {
+            jobs.clear();
+            jobs_off = -1;
+            blocks   = 0;
+        }
+    };
+
+    struct PendingSeeds
+    {
+        Batch* out       = nullptr;
+        int kind         = -1; // B_*
+        int derive       = -1; // SMR_DERIVE_*
+        int level        = -1;
+        size_t item_size = 0;
+        std::vector<const std::vector<smr_seed>*> parts;
+        std::vector<int64_t>* cum = nullptr; // optional per-group cumulative output-cell counts
+        bool inclusive            = false;
+        int cta_units             = SMR_CTA_CELLS;
+        std::vector<int> group; // group (e.g. level) of every part, non-decreasing; empty: every part is its own group
+        int n_groups = 0;
+        // records shared with another batch (the per-level tag batches are slices of tag_all): no seeds, no derive job
+        const PendingSeeds* alias = nullptr;
+        size_t alias_part0        = 0;
+        std::vector<size_t> part_item;
+        std::vector<int64_t> part_unit;
+        int64_t seeds = -1;
+    };
+
+    inline void layout_seeds(PendingSeeds& pd, Arena& arena, DeriveList& dl)
+    {
+        Batch& b  = *pd.out;
+        b         = Batch();
+        b.kind    = pd.kind;
+        b.level   = pd.level;
+        size_t n  = 0;
+        int64_t c = 0;
+        const int ngroups = pd.n_groups > 0 ? pd.n_groups : static_cast<int>(pd.parts.size());
+        if (pd.cum)
+        {
+            pd.cum->assign(static_cast<size_t>(ngroups) + 1, 0);
+        }
+        std::vector<int64_t> per_group(static_cast<size_t>(ngroups), 0);
+        pd.part_item.assign(pd.parts.size(), 0);
+        pd.part_unit.assign(pd.parts.size(), 0);
+        for (size_t k = 0; k < pd.parts.size(); ++k)
+        {
+            pd.part_item[k] = n;
+            pd.part_unit[k] = c;
+            int64_t cp = 0;
+            for (const smr_seed& sd : *pd.parts[k])
+            {
+                cp += sd.n;
+            }
+            c += cp;
+            per_group[static_cast<size_t>(pd.n_groups > 0 ? pd.group[k] : static_cast<int>(k))] += cp;
+            n += pd.parts[k]->size();
+        }
+        if (pd.cum)
+        {
+            int64_t acc = 0;
+            for (int gi = 0; gi < ngroups; ++gi)
+            {
+                if (!pd.inclusive)
+                {
+                    (*pd.cum)[static_cast<size_t>(gi)] = acc;
+                }
+                acc += per_group[static_cast<size_t>(gi)];
+                if (pd.inclusive)
+                {
+                    (*pd.cum)[static_cast<size_t>(gi)] = acc;
+                }
+            }
+            (*pd.cum)[static_cast<size_t>(ngroups)] = acc;
+        }
+        b.n_items = static_cast<int>(n);
+        if (n == 0)
+        {
+            return;
+        }
+        b.n_cells   = c;
+        b.cta_units = pd.cta_units;
+        b.n_ctas    = static_cast<int>((c + pd.cta_units - 1) / pd.cta_units);
+        b.prefix    = static_cast<int64_t>(arena.take((n + 1) * sizeof(int64_t)));
+        b.cta_first = static_cast<int64_t>(arena.take((static_cast<size_t>(b.n_ctas) + 1) * sizeof(int32_t)));
+        if (pd.alias != nullptr)
+        {
+            // still relative to the device-only region: fixed up together with the aliased batch
+            b.items = pd.alias->out->items + static_cast<int64_t>(pd.alias->part_item[pd.alias_part0] * pd.item_size);
+            arena.dev_fixups.push_back(&b.items);
+            return;
+        }
+        pd.seeds = static_cast<int64_t>(arena.take(n * sizeof(smr_seed)));
+        arena.take_dev(n * pd.item_size, &b.items);
+        smr_derive_job jb{};
+        jb.kind        = pd.derive;
+        jb.n           = static_cast<int32_t>(n);
+        jb.first_block = dl.blocks;
+        jb.seeds       = pd.seeds;
+        jb.items       = b.items; // relative: close_derive adds the base
+        dl.jobs.push_back(jb);
+        dl.blocks += static_cast<int>((n + SMR_CTA_THREADS - 1) / SMR_CTA_THREADS);
+    }
+
+    // after every layout_seeds / layout_bc of the arena: place the job table, fix the device-only offsets, get the memory
+    inline void close_derive(Arena& arena, DeriveList& dl)
+    {
+        dl.jobs_off = static_cast<int64_t>(arena.take(std::max<size_t>(dl.jobs.size(), 1) * sizeof(smr_derive_job)));
+        arena.close_layout();
+        for (smr_derive_job& jb : dl.jobs)
+        {
+            jb.items += static_cast<int64_t>(arena.dev_base);
+        }
+        arena.commit();
+        if (!dl.jobs.empty())
+        {
+            std::memcpy(arena.p + dl.jobs_off, dl.jobs.data(), dl.jobs.size() * sizeof(smr_derive_job));
+        }
+    }
+
+    // seeds and prefix entries of ONE part (parts of a batch can be filled concurrently)
+    inline void fill_seeds_part(const PendingSeeds& pd, Arena& arena, size_t k)
+    {
+        const Batch& b = *pd.out;
+        if (b.n_items == 0 || pd.parts[k]->empty())
+        {
+            return;
+        }
+        int64_t* prefix = reinterpret_cast<int64_t*>(arena.p + b.prefix);
+        size_t i        = pd.part_item[k];
+        int64_t acc     = pd.part_unit[k];
+        if (pd.alias == nullptr)
+        {
+            std::memcpy(reinterpret_cast<smr_seed*>(arena.p + pd.seeds) + i, pd.parts[k]->data(), pd.parts[k]->size() * sizeof(smr_seed));
+        }
+        for (const smr_seed& sd : *pd.parts[k])
+        {
+            prefix[i++] = acc;
+            acc += sd.n;
+        }
+    }
+
+    // closing prefix entry and the per-CTA table, once every part is in place
+    inline void finish_seeds(const PendingSeeds& pd, Arena& arena)
+    {
+        const Batch& b = *pd.out;
+        if (b.n_items == 0)
+        {
+            return;
+        }
+        int64_t* prefix = reinterpret_cast<int64_t*>(arena.p + b.prefix);
+        int32_t* first  = reinterpret_cast<int32_t*>(arena.p + b.cta_first);
+        prefix[b.n_items] = b.n_cells;
+        size_t it = 0;
+        for (int c = 0; c < b.n_ctas; ++c)
+        {
+            const int64_t g = static_cast<int64_t>(c) * b.cta_units;
+            while (prefix[it + 1] <= g)
+            {
+                ++it;
+            }
+            first[c] = static_cast<int32_t>(it);
+        }
+        first[b.n_ctas] = b.n_items - 1;
+    }
+
+    inline void fill_seeds(const PendingSeeds& pd, Arena& arena)
+    {
+        for (size_t k = 0; k < pd.parts.size(); ++k)
+        {
+            fill_seeds_part(pd, arena, k);
+        }
+        finish_seeds(pd, arena);
+    }
+
+    inline PendingSeeds pending_seeds(Batch* out, int kind, int derive, int level, size_t item_size, int cta_units = SMR_CTA_CELLS)
+    {
+        PendingSeeds pd;
+        pd.out       = out;
+        pd.kind      = kind;
+        pd.derive    = derive;
+        pd.level     = level;
+        pd.item_size = item_size;
+        pd.cta_units = cta_units;
+        return pd;
     }
 
     struct PendingBc
@@ -479,116 +711,63 @@ namespace smr
     }
 
     // ---------------------------------------------------------------------------------------------------------
-    // per-interval item builders
+    // per-interval seed builders: the storage offsets are looked up on the device (derive.cuh)
     // ---------------------------------------------------------------------------------------------------------
-    inline void fv_items(const Mesh& m, int l, const PlanFilter& flt, std::vector<smr_item_fv>& out, size_t row_begin = 0, size_t row_end = ~size_t(0))
+    inline smr_seed mk_seed(int level, int y, int z, int s, int e, unsigned mask)
     {
-        const int dim = m.cfg.dim;
-        const LevelSet& c   = m.cells[l];
-        const LevelSet& ref = m.ref[l];
-        Probe pc(ref), pym(ref), pyp(ref), pzm(ref), pzp(ref);
-        row_end = std::min(row_end, c.rows());
-        out.reserve(out.size() + static_cast<size_t>(c.ptr[row_end] - c.ptr[row_begin]));
+        return smr_seed{s, e - s, y, z, level | static_cast<int>(mask << 8), 0};
+    }
+
+    // one seed per x-interval of rows [row_begin, row_end) of `cs` (a set at `level`) whose row this rank owns
+    inline void set_seeds(const LevelSet& cs, int level, const PlanFilter& flt, bool to_all, std::vector<smr_seed>& out, size_t row_begin = 0,
+                          size_t row_end = ~size_t(0))
+    {
+        row_end = std::min(row_end, cs.rows());
+        if (row_begin >= row_end)
+        {
+            return;
+        }
+        out.reserve(out.size() + static_cast<size_t>(cs.ptr[row_end] - cs.ptr[row_begin]));
         for (size_t r = row_begin; r < row_end; ++r)
         {
-            const int y = key_y(c.key[r]), z = key_z(c.key[r]);
-            if (!flt.owns(l, y, z))
+            const int y = key_y(cs.key[r]), z = key_z(cs.key[r]);
+            if (!flt.owns(level, y, z))
             {
                 continue;
             }
-            const int mask = static_cast<int>(flt.mask(l, y, z));
-            pc.seek(c.key[r]);
-            if (dim > 1)
+            const unsigned mask = to_all ? flt.mask_all() : flt.mask(level, y, z);
+            for (int q = cs.ptr[r]; q < cs.ptr[r + 1]; ++q)
             {
-                pym.seek(mk_key(y - 1, z));
-                pyp.seek(mk_key(y + 1, z));
-            }
-            if (dim > 2)
-            {
-                pzm.seek(mk_key(y, z - 1));
-                pzp.seek(mk_key(y, z + 1));
-            }
-            for (int q = c.ptr[r]; q < c.ptr[r + 1]; ++q)
-            {
-                const int s = c.xs[q], e = c.xe[q];
-                smr_item_fv it;
-                it.c  = need(pc, "fv x", l, y, z, s - 1, e) + 1;
-                it.ym = it.yp = it.zm = it.zp = it.c;
-                if (dim > 1)
-                {
-                    it.ym = need(pym, "fv y-1", l, y - 1, z, s, e - 1);
-                    it.yp = need(pyp, "fv y+1", l, y + 1, z, s, e - 1);
-                }
-                if (dim > 2)
-                {
-                    it.zm = need(pzm, "fv z-1", l, y, z - 1, s, e - 1);
-                    it.zp = need(pzp, "fv z+1", l, y, z + 1, s, e - 1);
-                }
-                it.n     = e - s;
-                it.level = l;
-                it.x     = s;
-                it.y     = y;
-                it.z     = z;
-                it.mask  = mask;
-                out.push_back(it);
+                out.push_back(mk_seed(level, y, z, cs.xs[q], cs.xe[q], mask));
             }
         }
     }
 
+    inline void fv_seeds(const Mesh& m, int l, const PlanFilter& flt, std::vector<smr_seed>& out, size_t row_begin = 0, size_t row_end = ~size_t(0))
+    {
+        set_seeds(m.cells[l], l, flt, false, out, row_begin, row_end);
+    }
+
     // Leaves of level l split for the FV kernels: strips of SMR_STRIP_ROWS consecutive rows sharing an x-range, and the
     // single-row remainder.  Every leaf cell lands in exactly one of the two lists.
-    inline void fv_split_items(const Mesh& m, int l, const PlanFilter& flt, std::vector<smr_item_fvstrip>& strips, std::vector<smr_item_fv>& singles,
+    inline void fv_split_seeds(const Mesh& m, int l, const PlanFilter& flt, std::vector<smr_seed>& strips, std::vector<smr_seed>& singles,
                                size_t row_begin = 0, size_t row_end = ~size_t(0))
     {
         constexpr int R = SMR_STRIP_ROWS;
         const int dim   = m.cfg.dim;
-        const LevelSet& c   = m.cells[l];
-        const LevelSet& ref = m.ref[l];
+        const LevelSet& c = m.cells[l];
         if (dim < 2)
         {
-            fv_items(m, l, flt, singles, row_begin, row_end);
+            fv_seeds(m, l, flt, singles, row_begin, row_end);
             return;
         }
-        Probe prow[R + 2], pzm[R], pzp[R];
-        for (auto& x : prow)
-        {
-            x = Probe(ref);
-        }
-        for (int r = 0; r < R; ++r)
-        {
-            pzm[r] = Probe(ref);
-            pzp[r] = Probe(ref);
-        }
-        Probe ps_c(ref), ps_ym(ref), ps_yp(ref), ps_zm(ref), ps_zp(ref);
         std::vector<std::pair<int, int>> common, tmp;
         auto single = [&](int y, int z, int s, int e)
         {
-            if (!flt.owns(l, y, z))
+            if (flt.owns(l, y, z))
             {
-                return;
+                singles.push_back(mk_seed(l, y, z, s, e, flt.mask(l, y, z)));
             }
-            smr_item_fv it;
-            ps_c.seek(mk_key(y, z));
-            ps_ym.seek(mk_key(y - 1, z));
-            ps_yp.seek(mk_key(y + 1, z));
-            it.c  = need(ps_c, "fv x", l, y, z, s - 1, e) + 1;
-            it.ym = need(ps_ym, "fv y-1", l, y - 1, z, s, e - 1);
-            it.yp = need(ps_yp, "fv y+1", l, y + 1, z, s, e - 1);
-            it.zm = it.zp = it.c;
-            if (dim > 2)
-            {
-                ps_zm.seek(mk_key(y, z - 1));
-                ps_zp.seek(mk_key(y, z + 1));
-                it.zm = need(ps_zm, "fv z-1", l, y, z - 1, s, e - 1);
-                it.zp = need(ps_zp, "fv z+1", l, y, z + 1, s, e - 1);
-            }
-            it.n     = e - s;
-            it.level = l;
-            it.x     = s;
-            it.y     = y;
-            it.z     = z;
-            it.mask  = static_cast<int>(flt.mask(l, y, z));
-            singles.push_back(it);
         };
         size_t r0 = row_begin;
         const size_t nrows = std::min(row_end, c.rows());
@@ -649,46 +828,17 @@ namespace smr
                 }
             }
             common.swap(tmp);
-            for (int r = 0; r < R + 2; ++r)
+            if (flt.owns(l, y0, z0))
             {
-                prow[r].seek(mk_key(y0 - 1 + r, z0));
-            }
-            if (dim > 2)
-            {
-                for (int r = 0; r < R; ++r)
+                const unsigned mask = flt.dim > 2 ? flt.mask(l, y0, z0) : flt.mask(l, y0, z0, R);
+                for (auto& iv : common)
                 {
-                    pzm[r].seek(mk_key(y0 + r, z0 - 1));
-                    pzp[r].seek(mk_key(y0 + r, z0 + 1));
+                    strips.push_back(mk_seed(l, y0, z0, iv.first, iv.second, mask));
                 }
             }
-            const bool own_strip = flt.owns(l, y0, z0);
-            for (auto& iv : common)
+            else
             {
-                if (!own_strip)
-                {
-                    break;
-                }
-                const int s = iv.first, e = iv.second;
-                smr_item_fvstrip it;
-                std::memset(&it, 0, sizeof(it));
-                it.row[0]     = need(prow[0], "fv strip y-1", l, y0 - 1, z0, s, e - 1);
-                it.row[R + 1] = need(prow[R + 1], "fv strip y+R", l, y0 + R, z0, s, e - 1);
-                for (int r = 0; r < R; ++r)
-                {
-                    it.row[r + 1] = need(prow[r + 1], "fv strip x", l, y0 + r, z0, s - 1, e) + 1;
-                    if (dim > 2)
-                    {
-                        it.zm[r] = need(pzm[r], "fv strip z-1", l, y0 + r, z0 - 1, s, e - 1);
-                        it.zp[r] = need(pzp[r], "fv strip z+1", l, y0 + r, z0 + 1, s, e - 1);
-                    }
-                }
-                it.n     = e - s;
-                it.level = l;
-                it.mask  = static_cast<int>(flt.dim > 2 ? flt.mask(l, y0, z0) : flt.mask(l, y0, z0, R));
-                it.x     = s;
-                it.y     = y0;
-                it.z     = z0;
-                strips.push_back(it);
+                // another rank runs the strips of this group (ownership is decided on the first row)
             }
             // remainder of every row
             for (int r = 0; r < R; ++r)
@@ -723,7 +873,6 @@ namespace smr
         }
     }
 
-    // coarse set `cs` at level lc (dst offsets from dst_ref) <- children rows in src_ref (level lc+1)
     // ---------------------------------------------------------------------------------------------------------
     // flux-based schemes on multi-level meshes: the reference enumerates interfaces (interface.hpp:35-306, 440-509) and
     // scatters both sides' contributions; here every leaf gathers its own contributions, so the host classifies what
@@ -1018,239 +1167,6 @@ namespace smr
         plan.ready = true;
     }
 
-    inline void proj_items(int dim, const LevelSet& cs, int lc, const LevelSet& dst_ref, const LevelSet& src_ref, const PlanFilter& flt, std::vector<smr_item_proj>& out)
-    {
-        Probe pd(dst_ref);
-        Probe ps[4] = {Probe(src_ref), Probe(src_ref), Probe(src_ref), Probe(src_ref)};
-        const int ny = dim > 1 ? 2 : 1, nz = dim > 2 ? 2 : 1;
-        out.reserve(out.size() + cs.n_intervals());
-        for (size_t r = 0; r < cs.rows(); ++r)
-        {
-            const int y = key_y(cs.key[r]), z = key_z(cs.key[r]);
-            if (!flt.owns(lc, y, z))
-            {
-                continue;
-            }
-            const int mask = static_cast<int>(flt.mask(lc, y, z));
-            pd.seek(cs.key[r]);
-            for (int cz = 0; cz < nz; ++cz)
-            {
-                for (int cy = 0; cy < ny; ++cy)
-                {
-                    ps[cy + 2 * cz].seek(mk_key(dim > 1 ? 2 * y + cy : 0, dim > 2 ? 2 * z + cz : 0));
-                }
-            }
-            for (int q = cs.ptr[r]; q < cs.ptr[r + 1]; ++q)
-            {
-                const int s = cs.xs[q], e = cs.xe[q];
-                smr_item_proj it;
-                it.dst = need(pd, "projection dst", lc, y, z, s, e - 1);
-                for (int k = 0; k < 4; ++k)
-                {
-                    it.src[k] = 0;
-                }
-                for (int cz = 0; cz < nz; ++cz)
-                {
-                    for (int cy = 0; cy < ny; ++cy)
-                    {
-                        it.src[cy + 2 * cz] = need(ps[cy + 2 * cz], "projection src", lc + 1, 2 * y + cy, 2 * z + cz, 2 * s, 2 * e - 1);
-                    }
-                }
-                it.n    = e - s;
-                it.mask = mask;
-                out.push_back(it);
-            }
-        }
-    }
-
-    // Fine set `fs` at level lf (must carry .off = destination offsets) predicted from src_ref (level lf-1).
-    struct PredBuilder
-    {
-        int dim, radius, lf;
-        Probe p[9];
-        int ry_, rz_;
-
-        PredBuilder(int dim_, int radius_, int lf_, const LevelSet& src_ref)
-            : dim(dim_)
-            , radius(radius_)
-            , lf(lf_)
-        {
-            for (auto& x : p)
-            {
-                x = Probe(src_ref);
-            }
-            ry_ = dim > 1 ? radius : 0;
-            rz_ = dim > 2 ? radius : 0;
-        }
-
-        void seek_row(int y, int z)
-        {
-            const int yc = y >> 1, zc = z >> 1;
-            for (int rz = -rz_; rz <= rz_; ++rz)
-            {
-                for (int ry = -ry_; ry <= ry_; ++ry)
-                {
-                    p[(ry + 1) + 3 * (rz + 1)].seek(mk_key(yc + ry, zc + rz));
-                }
-            }
-        }
-
-        void add(int y, int z, int s, int e, int64_t dst, unsigned mask, std::vector<smr_item_pred>& out)
-        {
-            smr_item_pred it;
-            it.dst = dst;
-            it.n   = e - s;
-            it.par = (s & 1) | ((dim > 1 ? (y & 1) : 0) << 1) | ((dim > 2 ? (z & 1) : 0) << 2) | static_cast<int>(mask << 8);
-            const int sc = s >> 1, ec = (e - 1) >> 1;
-            for (int k = 0; k < 9; ++k)
-            {
-                it.src[k] = 0;
-            }
-            for (int rz = -rz_; rz <= rz_; ++rz)
-            {
-                for (int ry = -ry_; ry <= ry_; ++ry)
-                {
-                    const int k = (ry + 1) + 3 * (rz + 1);
-                    it.src[k]   = need(p[k], "prediction src", lf - 1, (y >> 1) + ry, (z >> 1) + rz, sc - radius, ec + radius) + radius;
-                }
-            }
-            out.push_back(it);
-        }
-    };
-
-    inline void pred_items(int dim, int radius, int lf, const LevelSet& fs, const LevelSet& src_ref, const PlanFilter& flt, std::vector<smr_item_pred>& out)
-    {
-        PredBuilder pb(dim, radius, lf, src_ref);
-        out.reserve(out.size() + fs.n_intervals());
-        for (size_t r = 0; r < fs.rows(); ++r)
-        {
-            const int y = key_y(fs.key[r]), z = key_z(fs.key[r]);
-            if (!flt.owns(lf, y, z))
-            {
-                continue;
-            }
-            const unsigned mask = flt.mask(lf, y, z);
-            pb.seek_row(y, z);
-            for (int q = fs.ptr[r]; q < fs.ptr[r + 1]; ++q)
-            {
-                pb.add(y, z, fs.xs[q], fs.xe[q], fs.off[q], mask, out);
-            }
-        }
-    }
-
-    inline void detail_items(const Mesh& m, int level, const LevelSet& cs, const PlanFilter& flt, std::vector<smr_item_detail>& out)
-    {
-        const int dim = m.cfg.dim, radius = m.cfg.pred_radius;
-        const LevelSet& rc = m.ref[level];
-        const LevelSet& rf = m.ref[level + 1];
-        const int ry_ = dim > 1 ? radius : 0, rz_ = dim > 2 ? radius : 0;
-        const int ny = dim > 1 ? 2 : 1, nz = dim > 2 ? 2 : 1;
-        Probe pc[9], pf[4];
-        for (auto& x : pc)
-        {
-            x = Probe(rc);
-        }
-        for (auto& x : pf)
-        {
-            x = Probe(rf);
-        }
-        out.reserve(out.size() + cs.n_intervals());
-        for (size_t r = 0; r < cs.rows(); ++r)
-        {
-            const int y = key_y(cs.key[r]), z = key_z(cs.key[r]);
-            if (!flt.owns(level, y, z))
-            {
-                continue;
-            }
-            const int mask = static_cast<int>(flt.mask(level, y, z));
-            for (int rz = -rz_; rz <= rz_; ++rz)
-            {
-                for (int ry = -ry_; ry <= ry_; ++ry)
-                {
-                    pc[(ry + 1) + 3 * (rz + 1)].seek(mk_key(y + ry, z + rz));
-                }
-            }
-            for (int cz = 0; cz < nz; ++cz)
-            {
-                for (int cy = 0; cy < ny; ++cy)
-                {
-                    pf[cy + 2 * cz].seek(mk_key(dim > 1 ? 2 * y + cy : 0, dim > 2 ? 2 * z + cz : 0));
-                }
-            }
-            for (int q = cs.ptr[r]; q < cs.ptr[r + 1]; ++q)
-            {
-                const int s = cs.xs[q], e = cs.xe[q];
-                smr_item_detail it;
-                std::memset(&it, 0, sizeof(it));
-                for (int rz = -rz_; rz <= rz_; ++rz)
-                {
-                    for (int ry = -ry_; ry <= ry_; ++ry)
-                    {
-                        const int k  = (ry + 1) + 3 * (rz + 1);
-                        it.coarse[k] = need(pc[k], "detail coarse", level, y + ry, z + rz, s - radius, e - 1 + radius) + radius;
-                    }
-                }
-                for (int cz = 0; cz < nz; ++cz)
-                {
-                    for (int cy = 0; cy < ny; ++cy)
-                    {
-                        it.fine[cy + 2 * cz] = need(pf[cy + 2 * cz], "detail fine", level + 1, 2 * y + cy, 2 * z + cz, 2 * s, 2 * e - 1);
-                    }
-                }
-                it.n    = e - s;
-                it.mask = mask;
-                out.push_back(it);
-            }
-        }
-    }
-
-    inline void tag_items(const Mesh& m, int fine_level, const LevelSet& cs, const PlanFilter& flt, std::vector<smr_item_tag>& out)
-    {
-        const int dim = m.cfg.dim;
-        const LevelSet& rc = m.ref[fine_level - 1];
-        const LevelSet& rf = m.ref[fine_level];
-        const int ny = dim > 1 ? 2 : 1, nz = dim > 2 ? 2 : 1;
-        Probe pc(rc), pf[4];
-        for (auto& x : pf)
-        {
-            x = Probe(rf);
-        }
-        out.reserve(out.size() + cs.n_intervals());
-        for (size_t r = 0; r < cs.rows(); ++r)
-        {
-            const int y = key_y(cs.key[r]), z = key_z(cs.key[r]);
-            if (!flt.owns(fine_level - 1, y, z))
-            {
-                continue;
-            }
-            pc.seek(cs.key[r]);
-            for (int cz = 0; cz < nz; ++cz)
-            {
-                for (int cy = 0; cy < ny; ++cy)
-                {
-                    pf[cy + 2 * cz].seek(mk_key(dim > 1 ? 2 * y + cy : 0, dim > 2 ? 2 * z + cz : 0));
-                }
-            }
-            for (int q = cs.ptr[r]; q < cs.ptr[r + 1]; ++q)
-            {
-                const int s = cs.xs[q], e = cs.xe[q];
-                smr_item_tag it;
-                std::memset(&it, 0, sizeof(it));
-                it.coarse = need(pc, "tag coarse", fine_level - 1, y, z, s, e - 1);
-                for (int cz = 0; cz < nz; ++cz)
-                {
-                    for (int cy = 0; cy < ny; ++cy)
-                    {
-                        it.fine[cy + 2 * cz] = need(pf[cy + 2 * cz], "tag fine", fine_level, 2 * y + cy, 2 * z + cz, 2 * s, 2 * e - 1);
-                    }
-                }
-                it.n     = e - s;
-                it.level = fine_level | static_cast<int>(flt.mask_all() << 8); // tags are replicated on every rank
-                out.push_back(it);
-            }
-        }
-    }
-
     // ---------------------------------------------------------------------------------------------------------
     // directions (reference stencil.hpp:299-357)
     // ---------------------------------------------------------------------------------------------------------
@@ -1325,7 +1241,8 @@ namespace smr
         std::vector<int64_t> detail_cum; // detail_cum[k] = output cells of detail records with coarse level < k
         Batch tag_all;                // criteria: all fine levels, ascending
         std::vector<int64_t> tag_cum; // tag_cum[k] = output cells of tag records with fine level <= k
-        std::vector<Batch> tag;       // per fine level, for the sequential keep propagation
+        std::vector<Batch> tag;       // per fine level, for the sequential keep propagation (records shared with tag_all)
+        DeriveList derive;            // what the device has to derive after the upload (all batches above except the bc ones)
         double build_seconds = 0;
     };
 
@@ -1436,7 +1353,7 @@ namespace smr
     struct PhaseItems
     {
         BcBuilder bc;
-        std::vector<smr_item_proj> proj;
+        std::vector<smr_seed> proj; // seeds at the coarse level
     };
 
     // project_corner_below(src_level) (update_outer_ghost.hpp:267-336): copies of the corner ghost of src_level into
@@ -1634,7 +1551,7 @@ namespace smr
         if (level > 0 && !ref.empty())
         {
             LevelSet ps = set_inter(coarsen(ref, 1, dim), m.proj[level - 1]);
-            proj_items(dim, ps, level - 1, m.ref[level - 1], ref, flt, out.proj);
+            set_seeds(ps, level - 1, flt, false, out.proj);
         }
     }
 
@@ -1703,10 +1620,6 @@ namespace smr
                         if (level >= 1 && level <= L)
                         {
                             predset[level] = prediction_set(m, level);
-                            if (!predset[level].empty())
-                            {
-                                locate(predset[level], m.ref[level]);
-                            }
                         }
                         break;
                     case 1:
@@ -1737,11 +1650,7 @@ namespace smr
         {
             int kind, level;
             size_t r0, r1;
-            std::vector<smr_item_fv> fv, fv_single;
-            std::vector<smr_item_fvstrip> fv_strip;
-            std::vector<smr_item_pred> pred;
-            std::vector<smr_item_detail> detail;
-            std::vector<smr_item_tag> tag;
+            std::vector<smr_seed> seeds, strips; // strips: kind 4 only (seeds = the single-row remainder)
         };
         std::vector<Chunk> chunks;
         // chunk lists per kind, levels ascending, so that the concatenation below keeps level order
@@ -1757,7 +1666,7 @@ namespace smr
                 const std::vector<size_t> cut = chunk_rows(src, 2500, 16);
                 for (size_t c = 0; c + 1 < cut.size(); ++c)
                 {
-                    chunks.push_back(Chunk{kind, level, cut[c], cut[c + 1], {}, {}, {}, {}, {}, {}});
+                    chunks.push_back(Chunk{kind, level, cut[c], cut[c + 1], {}, {}});
                 }
             }
         }
@@ -1773,19 +1682,20 @@ namespace smr
                 switch (ck.kind)
                 {
                     case 4:
-                        fv_split_items(m, ck.level, flt, ck.fv_strip, ck.fv_single, ck.r0, ck.r1);
+                        fv_split_seeds(m, ck.level, flt, ck.strips, ck.seeds, ck.r0, ck.r1);
                         break;
                     case 3:
-                        fv_items(m, ck.level, flt, ck.fv, ck.r0, ck.r1);
+                        fv_seeds(m, ck.level, flt, ck.seeds, ck.r0, ck.r1);
                         break;
                     case 2:
-                        pred_items(dim, cfg.pred_radius, ck.level, slice_rows(predset[ck.level], ck.r0, ck.r1, true), m.ref[ck.level - 1], flt, ck.pred);
+                        set_seeds(predset[ck.level], ck.level, flt, false, ck.seeds, ck.r0, ck.r1);
                         break;
                     case 1:
-                        detail_items(m, ck.level, slice_rows(detailset[ck.level], ck.r0, ck.r1), flt, ck.detail);
+                        set_seeds(detailset[ck.level], ck.level, flt, false, ck.seeds, ck.r0, ck.r1);
                         break;
                     default:
-                        tag_items(m, ck.level, slice_rows(tagset[ck.level], ck.r0, ck.r1), flt, ck.tag);
+                        // tagset[l] lives at the coarse level l - 1; tags are replicated on every rank
+                        set_seeds(tagset[ck.level], ck.level - 1, flt, true, ck.seeds, ck.r0, ck.r1);
                         break;
                 }
             }
@@ -1807,21 +1717,24 @@ namespace smr
         plan.pred.assign(nlev, Batch());
         plan.tag.assign(nlev, Batch());
         // layout (serial, cheap) then fill (parallel) straight into the staging arena
-        Pending<smr_item_fv> p_fv{&plan.fv, B_FV, -1, {}, nullptr, false};
-        Pending<smr_item_fv> p_fv_single{&plan.fv_single, B_FV, -1, {}, nullptr, false};
-        Pending<smr_item_fvstrip> p_fv_strip{&plan.fv_strip, B_FV, -1, {}, nullptr, false, SMR_CTA_THREADS * STRIP_UPT};
-        Pending<smr_item_detail> p_detail{&plan.detail, B_DETAIL, -1, {}, &plan.detail_cum, false};
-        Pending<smr_item_tag> p_tag_all{&plan.tag_all, B_TAG, -1, {}, &plan.tag_cum, true};
+        plan.derive.clear();
+        PendingSeeds p_fv        = pending_seeds(&plan.fv, B_FV, SMR_DERIVE_FV, -1, sizeof(smr_item_fv));
+        PendingSeeds p_fv_single = pending_seeds(&plan.fv_single, B_FV, SMR_DERIVE_FV, -1, sizeof(smr_item_fv));
+        PendingSeeds p_fv_strip  = pending_seeds(&plan.fv_strip, B_FV, SMR_DERIVE_FVSTRIP, -1, sizeof(smr_item_fvstrip), SMR_CTA_THREADS * STRIP_UPT);
+        PendingSeeds p_detail    = pending_seeds(&plan.detail, B_DETAIL, SMR_DERIVE_DETAIL, -1, sizeof(smr_item_detail));
+        PendingSeeds p_tag_all   = pending_seeds(&plan.tag_all, B_TAG, SMR_DERIVE_TAG, -1, sizeof(smr_item_tag));
+        p_detail.cum             = &plan.detail_cum;
+        p_tag_all.cum            = &plan.tag_cum;
+        p_tag_all.inclusive      = true;
         p_detail.n_groups = p_tag_all.n_groups = nlev; // cumulative counts are indexed by level
-        std::vector<Pending<smr_item_proj>> p_proj(nlev);
-        std::vector<Pending<smr_item_pred>> p_pred(nlev);
-        std::vector<Pending<smr_item_tag>> p_tag(nlev);
+        std::vector<PendingSeeds> p_proj(nlev), p_pred(nlev), p_tag(nlev);
         std::vector<PendingBc> p_bc(nlev);
         for (int l = 0; l < nlev; ++l)
         {
-            p_proj[l] = Pending<smr_item_proj>{&plan.down[l].proj, B_PROJ, l, {&phases[l].proj}, nullptr, false};
-            p_pred[l] = Pending<smr_item_pred>{&plan.pred[l], B_PRED, l, {}, nullptr, false};
-            p_tag[l]  = Pending<smr_item_tag>{&plan.tag[l], B_TAG, l, {}, nullptr, false};
+            p_proj[l] = pending_seeds(&plan.down[l].proj, B_PROJ, SMR_DERIVE_PROJ, l, sizeof(smr_item_proj));
+            p_proj[l].parts.push_back(&phases[l].proj);
+            p_pred[l] = pending_seeds(&plan.pred[l], B_PRED, SMR_DERIVE_PRED, l, sizeof(smr_item_pred));
+            p_tag[l]  = pending_seeds(&plan.tag[l], B_TAG, SMR_DERIVE_TAG, l, sizeof(smr_item_tag));
             p_bc[l]   = PendingBc{&plan.down[l].bc, l, &phases[l].bc.items, &phases[l].bc.srcs};
         }
         for (const Chunk& ck : chunks)
@@ -1829,53 +1742,58 @@ namespace smr
             switch (ck.kind)
             {
                 case 4:
-                    p_fv_single.parts.push_back(&ck.fv_single);
-                    p_fv_strip.parts.push_back(&ck.fv_strip);
+                    p_fv_single.parts.push_back(&ck.seeds);
+                    p_fv_strip.parts.push_back(&ck.strips);
                     break;
                 case 3:
-                    p_fv.parts.push_back(&ck.fv);
+                    p_fv.parts.push_back(&ck.seeds);
                     break;
                 case 2:
-                    p_pred[ck.level].parts.push_back(&ck.pred);
+                    p_pred[ck.level].parts.push_back(&ck.seeds);
                     break;
                 case 1:
-                    p_detail.parts.push_back(&ck.detail);
+                    p_detail.parts.push_back(&ck.seeds);
                     p_detail.group.push_back(ck.level);
                     break;
                 default:
-                    p_tag_all.parts.push_back(&ck.tag);
+                    if (p_tag[ck.level].parts.empty())
+                    {
+                        p_tag[ck.level].alias       = &p_tag_all;
+                        p_tag[ck.level].alias_part0 = p_tag_all.parts.size();
+                    }
+                    p_tag_all.parts.push_back(&ck.seeds);
                     p_tag_all.group.push_back(ck.level);
-                    p_tag[ck.level].parts.push_back(&ck.tag);
+                    p_tag[ck.level].parts.push_back(&ck.seeds);
                     break;
             }
         }
-        layout_batch(p_fv, plan.arena);
-        layout_batch(p_fv_single, plan.arena);
-        layout_batch(p_fv_strip, plan.arena);
+        layout_seeds(p_fv, plan.arena, plan.derive);
+        layout_seeds(p_fv_single, plan.arena, plan.derive);
+        layout_seeds(p_fv_strip, plan.arena, plan.derive);
         plan.fv_strip_cells = plan.fv_strip.n_cells * SMR_STRIP_ROWS;
-        layout_batch(p_detail, plan.arena);
-        layout_batch(p_tag_all, plan.arena);
+        layout_seeds(p_detail, plan.arena, plan.derive);
+        layout_seeds(p_tag_all, plan.arena, plan.derive);
         for (int l = 0; l < nlev; ++l)
         {
-            layout_batch(p_proj[l], plan.arena);
-            layout_batch(p_pred[l], plan.arena);
-            layout_batch(p_tag[l], plan.arena);
+            layout_seeds(p_proj[l], plan.arena, plan.derive);
+            layout_seeds(p_pred[l], plan.arena, plan.derive);
+            layout_seeds(p_tag[l], plan.arena, plan.derive);
             layout_bc(p_bc[l], plan.arena);
         }
-        plan.arena.commit();
+        close_derive(plan.arena, plan.derive);
         {
             // every (batch, part) pair is an independent copy; the per-CTA tables follow once the parts are in
             std::vector<std::function<void()>> jobs, finish;
-            auto add = [&](auto& pd)
+            auto add = [&](PendingSeeds& pd)
             {
                 for (size_t k = 0; k < pd.parts.size(); ++k)
                 {
                     if (!pd.parts[k]->empty())
                     {
-                        jobs.push_back([&pd, &plan, k] { fill_part(pd, plan.arena, k); });
+                        jobs.push_back([&pd, &plan, k] { fill_seeds_part(pd, plan.arena, k); });
                     }
                 }
-                finish.push_back([&pd, &plan] { finish_batch(pd, plan.arena); });
+                finish.push_back([&pd, &plan] { finish_seeds(pd, plan.arena); });
             };
             add(p_fv_single);
             add(p_fv_strip);
@@ -1911,6 +1829,7 @@ namespace smr
     {
         Arena arena;
         Batch copy, proj, pred;
+        DeriveList derive; // copy: dst in the new mesh, src in the old one; proj / pred likewise (empty for build_broadcast)
     };
 
     inline void build_transfer(const Mesh& old_m, const Mesh& new_m, TransferPlan& tp, const PlanFilter& flt = PlanFilter())
@@ -1925,9 +1844,7 @@ namespace smr
         {
             int kind, level;
             size_t r0, r1;
-            std::vector<smr_item_copy> copies;
-            std::vector<smr_item_proj> projs;
-            std::vector<smr_item_pred> preds;
+            std::vector<smr_seed> copies, projs, preds;
         };
         std::vector<Task> tasks;
         for (int l = cfg.min_level; l <= cfg.max_level && l < nlev; ++l)
@@ -1956,38 +1873,17 @@ namespace smr
                 if (tk.kind == 0)
                 {
                     LevelSet s = set_inter(old_m.ref[l], slice_rows(new_m.cells[l], tk.r0, tk.r1));
-                    if (!s.empty())
-                    {
-                        LevelSet so = s;
-                        locate(s, new_m.ref[l]);
-                        locate(so, old_m.ref[l]);
-                        tk.copies.reserve(s.n_intervals());
-                        for (size_t r = 0; r < s.rows(); ++r)
-                        {
-                            const int y = key_y(s.key[r]), z = key_z(s.key[r]);
-                            if (!flt.owns(l, y, z))
-                            {
-                                continue;
-                            }
-                            const int mask = static_cast<int>(flt.mask(l, y, z));
-                            for (int q = s.ptr[r]; q < s.ptr[r + 1]; ++q)
-                            {
-                                tk.copies.push_back({s.off[q], so.off[q], s.xe[q] - s.xs[q], mask});
-                            }
-                        }
-                    }
+                    set_seeds(s, l, flt, false, tk.copies);
                 }
                 else
                 {
                     LevelSet sc = set_inter(coarsen(old_m.cells[l], 1, dim), new_m.cells[l - 1]);
-                    proj_items(dim, sc, l - 1, new_m.ref[l - 1], old_m.ref[l], flt, tk.projs);
+                    set_seeds(sc, l - 1, flt, false, tk.projs);
                     // set_refine = (new cells[l] ∩ old cells[l-1]).on(l-1); every coarse cell fills all its children
                     LevelSet sr = set_inter(coarsen(new_m.cells[l], 1, dim), old_m.cells[l - 1]);
                     if (!sr.empty())
                     {
-                        LevelSet fine = refine(sr, 1, dim);
-                        locate(fine, new_m.ref[l]);
-                        pred_items(dim, cfg.pred_radius, l, fine, old_m.ref[l - 1], flt, tk.preds);
+                        set_seeds(refine(sr, 1, dim), l, flt, false, tk.preds);
                     }
                 }
             }
@@ -2001,9 +1897,10 @@ namespace smr
         {
             throw std::out_of_range(error);
         }
-        Pending<smr_item_copy> p_copy{&tp.copy, B_COPY, -1, {}, nullptr, false};
-        Pending<smr_item_proj> p_proj{&tp.proj, B_PROJ, -1, {}, nullptr, false};
-        Pending<smr_item_pred> p_pred{&tp.pred, B_PRED, -1, {}, nullptr, false};
+        tp.derive.clear();
+        PendingSeeds p_copy = pending_seeds(&tp.copy, B_COPY, SMR_DERIVE_COPY, -1, sizeof(smr_item_copy));
+        PendingSeeds p_proj = pending_seeds(&tp.proj, B_PROJ, SMR_DERIVE_PROJ, -1, sizeof(smr_item_proj));
+        PendingSeeds p_pred = pending_seeds(&tp.pred, B_PRED, SMR_DERIVE_PRED, -1, sizeof(smr_item_pred));
         for (const Task& tk : tasks)
         {
             if (tk.kind == 0)
@@ -2016,18 +1913,18 @@ namespace smr
                 p_pred.parts.push_back(&tk.preds);
             }
         }
-        layout_batch(p_copy, tp.arena);
-        layout_batch(p_proj, tp.arena);
-        layout_batch(p_pred, tp.arena);
-        tp.arena.commit();
+        layout_seeds(p_copy, tp.arena, tp.derive);
+        layout_seeds(p_proj, tp.arena, tp.derive);
+        layout_seeds(p_pred, tp.arena, tp.derive);
+        close_derive(tp.arena, tp.derive);
 #pragma omp parallel sections
         {
 #pragma omp section
-            fill_batch(p_copy, tp.arena);
+            fill_seeds(p_copy, tp.arena);
 #pragma omp section
-            fill_batch(p_proj, tp.arena);
+            fill_seeds(p_proj, tp.arena);
 #pragma omp section
-            fill_batch(p_pred, tp.arena);
+            fill_seeds(p_pred, tp.arena);
         }
     }
 
@@ -2036,6 +1933,7 @@ namespace smr
     inline void build_broadcast(const Mesh& m, const PlanFilter& flt, TransferPlan& tp)
     {
         tp.arena.clear();
+        tp.derive.clear();
         std::vector<std::vector<smr_item_copy>> copies(1);
         const int mask = static_cast<int>(flt.mask_all());
         for (int l = 0; l < m.nlev; ++l)
@@ -2059,5 +1957,59 @@ namespace smr
         layout_batch(p_copy, tp.arena);
         tp.arena.commit();
         fill_batch(p_copy, tp.arena);
+    }
+
+    // The reference sub-mesh as the device sees it (items.h: smr_csr_table): per level the CSR arrays of Mesh::ref, back to
+    // back in one staging buffer.  16 B per interval + 12 B per row: 1-2 MB for a 10^6-cell adapted mesh.
+    struct CsrImage
+    {
+        Arena arena;
+        smr_csr_table tab;
+
+        CsrImage()
+        {
+            arena.min_cap = size_t(8) << 20;
+        }
+    };
+
+    inline void build_csr(const Mesh& m, CsrImage& img)
+    {
+        img.arena.clear();
+        std::memset(&img.tab, 0, sizeof(img.tab));
+        if (m.nlev > SMR_MAX_LEVELS)
+        {
+            throw std::invalid_argument("more levels than SMR_MAX_LEVELS");
+        }
+        for (int l = 0; l < m.nlev; ++l)
+        {
+            const LevelSet& r = m.ref[l];
+            if (r.empty())
+            {
+                continue;
+            }
+            smr_csr_level& lv = img.tab.lv[l];
+            lv.rows = static_cast<int32_t>(r.rows());
+            lv.key  = static_cast<int64_t>(img.arena.take(r.rows() * sizeof(int64_t)));
+            lv.ptr  = static_cast<int64_t>(img.arena.take((r.rows() + 1) * sizeof(int32_t)));
+            lv.xs   = static_cast<int64_t>(img.arena.take(r.n_intervals() * sizeof(int32_t)));
+            lv.xe   = static_cast<int64_t>(img.arena.take(r.n_intervals() * sizeof(int32_t)));
+            lv.off  = static_cast<int64_t>(img.arena.take(r.n_intervals() * sizeof(int64_t)));
+        }
+        img.arena.commit();
+#pragma omp parallel for schedule(dynamic, 1)
+        for (int l = m.nlev - 1; l >= 0; --l)
+        {
+            const LevelSet& r       = m.ref[l];
+            const smr_csr_level& lv = img.tab.lv[l];
+            if (lv.rows == 0)
+            {
+                continue;
+            }
+            std::memcpy(img.arena.p + lv.key, r.key.data(), r.rows() * sizeof(int64_t));
+            std::memcpy(img.arena.p + lv.ptr, r.ptr.data(), (r.rows() + 1) * sizeof(int32_t));
+            std::memcpy(img.arena.p + lv.xs, r.xs.data(), r.n_intervals() * sizeof(int32_t));
+            std::memcpy(img.arena.p + lv.xe, r.xe.data(), r.n_intervals() * sizeof(int32_t));
+            std::memcpy(img.arena.p + lv.off, r.off.data(), r.n_intervals() * sizeof(int64_t));
+        }
     }
 } // namespace smr

@@ -204,11 +204,40 @@ namespace smr
         MeshObj()
         {
             d_arena.min_cap = size_t(48) << 20;
+            d_csr.min_cap = d_csr_old.min_cap = size_t(8) << 20;
             d_detail.shared = true;
             d_tag.shared    = true;
             d_relmax.shared = true;
         }
+        // the reference sub-mesh on the device (items.h: smr_csr_table), read by derive_kernel; the previous mesh's copy is
+        // kept for the field transfer old -> new
+        CsrImage h_csr[2];
+        cudaEvent_t h_csr_done[2] = {nullptr, nullptr};
+        int h_csr_next  = 0;
+        DevBuf d_csr, d_csr_old;
+        smr_csr_table csr_tab{}, csr_tab_old{};
+        bool csr_ready = false;
+
+        void retire_csr() // the mesh is about to be replaced
+        {
+            d_csr.swap(d_csr_old);
+            csr_tab_old = csr_tab;
+            csr_ready   = false;
+        }
+
+        ~MeshObj()
+        {
+            for (cudaEvent_t e : h_csr_done)
+            {
+                if (e != nullptr)
+                {
+                    cudaEventDestroy(e);
+                }
+            }
+        }
+
         PinnedBuf h_tag;
+        bool h_tag_valid    = false; // h_tag holds the tags of the last harten iteration (else they are still in d_tag only)
         int64_t last_size   = 0;
         int last_ncomp      = 0;
         bool graduated      = false; // true once the leaves are known to be a fixed point of make_graduation
@@ -261,6 +290,8 @@ namespace smr
         unsigned* wf_error_host = nullptr; // pinned copy of the wavefront error word (kernels.cuh: SMR_WF_ERROR_WORD)
         int wf_next        = 0;
         cudaEvent_t wf_done[16] = {};
+        unsigned* derive_error      = nullptr; // device: sticky error words of derive_kernel (derive.cuh)
+        unsigned* derive_error_host = nullptr; // pinned copy
         // multi-GPU
         int mg_rank = 0, mg_world = 1;
         void* mg_pool            = nullptr;
@@ -539,9 +570,65 @@ namespace smr
         {
             return;
         }
-        d.ensure(a.size);
+        d.ensure(a.device_bytes());
         SMR_CUDA(cudaMemcpyAsync(d.p, a.p, a.size, cudaMemcpyHostToDevice, g.stream));
         g.stats.h2d_bytes += a.size;
+    }
+
+    // upload the reference sub-mesh CSR of the current mesh (once per mesh)
+    static void ensure_csr(MeshObj& mo)
+    {
+        if (mo.csr_ready)
+        {
+            return;
+        }
+        const int k   = mo.h_csr_next;
+        mo.h_csr_next = k ^ 1;
+        if (mo.h_csr_done[k] == nullptr)
+        {
+            SMR_CUDA(cudaEventCreateWithFlags(&mo.h_csr_done[k], cudaEventDisableTiming));
+        }
+        SMR_CUDA(cudaEventSynchronize(mo.h_csr_done[k])); // the copy that last read this staging buffer has finished
+        const double t0 = now();
+        build_csr(mo.mesh, mo.h_csr[k]);
+        const double dt = now() - t0;
+        g.stats.host_batch_seconds += dt;
+        g.stats.host_stage_seconds[5] += dt;
+        upload_arena(mo.h_csr[k].arena, mo.d_csr);
+        SMR_CUDA(cudaEventRecord(mo.h_csr_done[k], g.stream));
+        mo.csr_tab   = mo.h_csr[k].tab;
+        mo.csr_ready = true;
+    }
+
+    // one launch turns the seeds of an uploaded arena into records (derive.cuh).  `from_old`: sources are looked up in the
+    // previous mesh (field transfer), destinations always in the current one.
+    static void run_derive(DevBuf& d_arena, const DeriveList& dl, MeshObj& mo, bool from_old)
+    {
+        if (dl.jobs.empty() || dl.blocks == 0)
+        {
+            return;
+        }
+        if (g.derive_error == nullptr)
+        {
+            SMR_CUDA(cudaMalloc(reinterpret_cast<void**>(&g.derive_error), 64));
+            SMR_CUDA(cudaMemsetAsync(g.derive_error, 0, 64, g.stream));
+            SMR_CUDA(cudaMallocHost(reinterpret_cast<void**>(&g.derive_error_host), 64));
+            std::memset(g.derive_error_host, 0, 64);
+        }
+        DeriveArgs a;
+        a.arena     = static_cast<const char*>(d_arena.p);
+        a.arena_out = static_cast<char*>(d_arena.p);
+        a.jobs      = reinterpret_cast<const smr_derive_job*>(a.arena + dl.jobs_off);
+        a.n_jobs    = static_cast<int>(dl.jobs.size());
+        a.dim       = mo.mesh.cfg.dim;
+        a.radius    = mo.mesh.cfg.pred_radius;
+        a.csr_dst   = static_cast<const char*>(mo.d_csr.p);
+        a.tab_dst   = mo.csr_tab;
+        a.csr_src   = static_cast<const char*>(from_old ? mo.d_csr_old.p : mo.d_csr.p);
+        a.tab_src   = from_old ? mo.csr_tab_old : mo.csr_tab;
+        a.error     = g.derive_error;
+        SMR_CUDA(launch_derive(dl.blocks, g.stream, a));
+        ++g.stats.kernel_launches;
     }
 
     // host half of ensure_plan: slab cuts + traversal of the mesh into index batches (no CUDA calls except the pinned arena)
@@ -588,7 +675,9 @@ namespace smr
         const double tw = now();
         SMR_CUDA(cudaStreamSynchronize(g.stream));
         g.stats.host_stage_seconds[6] += now() - tw;
+        ensure_csr(mo);
         upload_arena(mo.plan.arena, mo.d_arena);
+        run_derive(mo.d_arena, mo.plan.derive, mo, false);
         mo.plan_ready = true;
     }
 
@@ -842,6 +931,10 @@ namespace smr
     // grid barrier timed out (the launch then left its outputs incomplete)
     static void wf_fetch_error()
     {
+        if (g.derive_error != nullptr)
+        {
+            SMR_CUDA(cudaMemcpyAsync(g.derive_error_host, g.derive_error, 32, cudaMemcpyDeviceToHost, g.stream));
+        }
         if (g.wf_barrier != nullptr)
         {
             SMR_CUDA(cudaMemcpyAsync(g.wf_error_host, g.wf_barrier + SMR_WF_ERROR_WORD, sizeof(unsigned), cudaMemcpyDeviceToHost, g.stream));
@@ -850,6 +943,18 @@ namespace smr
 
     static void wf_check_error()
     {
+        if (g.derive_error_host != nullptr && g.derive_error_host[0] != 0u)
+        {
+            static const char* kinds[] = {"fv", "fv strip", "projection", "prediction", "detail", "tag", "copy"};
+            const unsigned* e  = g.derive_error_host;
+            const unsigned k   = e[0] - 1;
+            std::string msg    = std::string("interval not found in the reference mesh (") + (k < 7 ? kinds[k] : "?") + " record) at level "
+                              + std::to_string(static_cast<int>(e[1])) + ", i = " + std::to_string(static_cast<int>(e[2]))
+                              + ", index = " + std::to_string(static_cast<int>(e[3])) + " " + std::to_string(static_cast<int>(e[4]));
+            g.derive_error_host[0] = 0;
+            cudaMemsetAsync(g.derive_error, 0, 64, g.stream);
+            throw std::out_of_range(msg);
+        }
         if (g.wf_error_host != nullptr && *g.wf_error_host != 0u)
         {
             const unsigned at = *g.wf_error_host;
@@ -1370,12 +1475,32 @@ namespace smr
             }
         }
         mo.h_tag.ensure(static_cast<size_t>(flag_at) + 16);
-        SMR_CUDA(cudaMemcpyAsync(mo.h_tag.p, tag, static_cast<size_t>(fused_flag ? flag_at + 16 : n), cudaMemcpyDeviceToHost, g.stream));
-        sec1.close();
-        wf_fetch_error();
-        SMR_CUDA(cudaStreamSynchronize(g.stream));
-        wf_check_error();
-        g.stats.d2h_bytes += static_cast<uint64_t>(n);
+        // Tags go back to the host for the graduation (1 B per reference cell).  The fused launch leaves a "some leaf changes"
+        // flag behind the tags: it is fetched first, and when it is clear on a graduated mesh the mesh is a fixed point and the
+        // tag array itself stays on the device (smr_adapt_last_tags fetches it on demand).
+        bool flag_clear = false;
+        if (fused_flag && mo.graduated)
+        {
+            SMR_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(mo.h_tag.p) + flag_at, tag + flag_at, 16, cudaMemcpyDeviceToHost, g.stream));
+            sec1.close();
+            wf_fetch_error();
+            SMR_CUDA(cudaStreamSynchronize(g.stream));
+            wf_check_error();
+            g.stats.d2h_bytes += 16;
+            flag_clear = *reinterpret_cast<const unsigned*>(static_cast<const uint8_t*>(mo.h_tag.p) + flag_at) == 0u;
+        }
+        mo.h_tag_valid = !flag_clear;
+        if (!flag_clear)
+        {
+            Section sec_tags;
+            SMR_CUDA(cudaMemcpyAsync(mo.h_tag.p, tag, static_cast<size_t>(fused_flag ? flag_at + 16 : n), cudaMemcpyDeviceToHost, g.stream));
+            sec_tags.close();
+            sec1.close();
+            wf_fetch_error();
+            SMR_CUDA(cudaStreamSynchronize(g.stream));
+            wf_check_error();
+            g.stats.d2h_bytes += static_cast<uint64_t>(n);
+        }
         mo.last_size  = n;
         mo.last_ncomp = ncomp;
 
@@ -1391,7 +1516,7 @@ namespace smr
         };
         bool no_tag_changes = false;
         CellArray ca;
-        if (fused_flag && mo.graduated && *reinterpret_cast<const unsigned*>(static_cast<const uint8_t*>(mo.h_tag.p) + flag_at) == 0u)
+        if (flag_clear)
         {
             no_tag_changes = true; // the device already looked at every leaf tag
         }
@@ -1445,6 +1570,7 @@ namespace smr
         mo.mesh          = std::move(*new_mesh);
         new_mesh.reset();
         mo.invalidate_plans();
+        mo.retire_csr();
         // update_fields (algorithm/update_fields.hpp:27-54,101-127)
         t0 = now();
         TransferPlan& tpn = g.transfer;
@@ -1461,7 +1587,9 @@ namespace smr
             f->spare.ensure(static_cast<size_t>(nn) * sizeof(double));
         }
         Section sec2;
+        ensure_csr(mo);
         upload_arena(tpn.arena, d_tr);
+        run_derive(d_tr, tpn.derive, mo, true);
         if (wf_enabled() && fields.size() <= SMR_WF_MAX_FIELDS)
         {
             // copy / projection / prediction of every field: independent jobs of one phase, one launch
@@ -2292,6 +2420,7 @@ extern "C"
                     nm.init_from_cells(mo.mesh.cfg, std::move(ca));
                     mo.mesh       = std::move(nm);
                     mo.invalidate_plans();
+                    mo.retire_csr();
                     ++g.stats.mesh_rebuilds;
                 }
                 g.stats.host_mesh_seconds += now() - t0;
@@ -2551,6 +2680,13 @@ extern "C"
                 if (n != mo.last_size || n == 0)
                 {
                     throw std::invalid_argument("size does not match the last adaptation's reference size");
+                }
+                if (!mo.h_tag_valid)
+                {
+                    require_device();
+                    SMR_CUDA(cudaMemcpyAsync(mo.h_tag.p, mo.d_tag.p, static_cast<size_t>(n), cudaMemcpyDeviceToHost, g.stream));
+                    SMR_CUDA(cudaStreamSynchronize(g.stream));
+                    mo.h_tag_valid = true;
                 }
                 std::memcpy(host, mo.h_tag.p, static_cast<size_t>(n));
             });

@@ -148,4 +148,58 @@ typedef struct
     int64_t src_first; /* index into the batch's int64 source-offset array */
 } smr_item_bc;
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Device-side record derivation.  The host no longer looks up storage offsets: it uploads the reference sub-mesh as a
+ * per-level CSR (row keys, row pointers, interval starts / ends / storage offsets) plus one 24-byte *seed* per record
+ * (the x-interval of the subset and its row), and derive_kernel (kernels.cuh) turns every seed into the record above
+ * by searching the CSR -- the row lookups of the reference's `mesh[mesh_id_t::reference][level][interval, index]`
+ * accessors (cell_array.hpp, level_cell_array.hpp:find).
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct
+{
+    int32_t xs; /* first x of the interval (output resolution of the record) */
+    int32_t n;  /* output cells */
+    int32_t y, z;
+    int32_t level; /* bits 0-7: level the record is written for; bits 8-15: multi-GPU peer mask */
+    int32_t pad;
+} smr_seed;
+
+/* one level of the reference sub-mesh on the device: byte offsets into the CSR buffer */
+typedef struct
+{
+    int64_t key;  /* int64 [rows]    (y, z) packed like intervals.hpp: mk_key */
+    int64_t ptr;  /* int32 [rows+1]  */
+    int64_t xs;   /* int32 [nivl]    */
+    int64_t xe;   /* int32 [nivl]    */
+    int64_t off;  /* int64 [nivl]    storage offset of cell xs */
+    int32_t rows; /* 0: level absent */
+    int32_t pad;
+} smr_csr_level;
+
+typedef struct
+{
+    smr_csr_level lv[SMR_MAX_LEVELS];
+} smr_csr_table;
+
+enum
+{
+    SMR_DERIVE_FV = 0,
+    SMR_DERIVE_FVSTRIP,
+    SMR_DERIVE_PROJ,   /* seed at the coarse level `level`: dst in csr_dst[level], children in csr_src[level+1] */
+    SMR_DERIVE_PRED,   /* seed at the fine level: dst in csr_dst[level], parents in csr_src[level-1] */
+    SMR_DERIVE_DETAIL, /* seed at the coarse level */
+    SMR_DERIVE_TAG,    /* seed at the coarse level `level`, record level = level + 1 */
+    SMR_DERIVE_COPY    /* dst in csr_dst[level], src in csr_src[level] */
+};
+
+typedef struct
+{
+    int32_t kind;
+    int32_t n;           /* seeds */
+    int32_t first_block; /* first CTA of the derive launch that works on this job */
+    int32_t pad;
+    int64_t seeds; /* byte offset into the arena */
+    int64_t items; /* byte offset into the arena (device-only region) */
+} smr_derive_job;
+
 #endif

@@ -2,6 +2,7 @@
 // (k_fv.cu, k_flux.cu, k_mr.cu and one k_wf.cu object per <dim, prediction radius>) so the library builds in parallel;
 // capi.cu only sees these declarations and never instantiates a kernel itself.
 #pragma once
+#include "derive.cuh"
 #include "kernels.cuh"
 
 namespace smr
@@ -11,6 +12,9 @@ namespace smr
     cudaError_t launch_batch(int grid, cudaStream_t st, const BatchView<Item>& v, const Op& op);
 
     cudaError_t launch_ghost_phase_kernel(int dim, int grid, cudaStream_t st, const BcView& bc, int bc_ctas, const BatchView<smr_item_proj>& pv, double* f);
+
+    // records from seeds + CSR (derive.cuh, k_derive.cu)
+    cudaError_t launch_derive(int grid, cudaStream_t st, const DeriveArgs& a);
 
     // fused wavefront, one instantiation per (dim, radius)
     template <int DIM, int RADIUS>
