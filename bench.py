@@ -313,6 +313,68 @@ def uniform_sweep(sb, torch, level, iters=20):
     return n, secs, gsecs, dsecs
 
 
+def uniform_full_step(sb, torch, dim, level, iters=10):
+    """The WHOLE step on a uniform level-`level` mesh with min_level = level - 1 (BASELINE.json configs[4] shapes): MRadaptation
+    (zero fill, keep tags, ghost update = projection level -> level-1 + BC, detail, criteria, keep propagation, change flag),
+    update_ghost_mr, unp1 = u - dt * upwind(a, u), swap.  epsilon < 0 makes every detail significant, so nothing coarsens and the
+    mesh stays uniform while all the multiresolution work is done; the change flag stays clear, so no tag leaves the device.
+    Returns the device time per step (CUDA events) and the algorithmic bytes the step moves."""
+    cfg = sb.mesh_config(dim, 1).min_level(level - 1).max_level(level).max_stencil_size(2).disable_minimal_ghost_width()
+    mesh = sb.MRMesh.make_mesh([0.0] * dim, [1.0] * dim, cfg)
+    u = sb.make_scalar_field("u", mesh)
+    u.resize()
+    u.fill(0.0)
+    u.init_ball([0.3] * dim, 0.2)
+    sb.make_bc(u, sb.DIRICHLET, 0.0)
+    v = sb.make_scalar_field("v", mesh)
+    v.resize()
+    adapt = sb.make_MRAdapt(u)
+    mra = sb.mra_config().epsilon(-1.0)
+    a = [1.0] * dim
+    dt = (0.5 if dim == 2 else 0.25) * mesh.min_cell_length()
+
+    def step():
+        adapt(mra)
+        sb.update_ghost_mr(u)
+        sb.upwind_step(v, u, a, dt)
+        sb.swap(u, v)
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    n, nref = mesh.nb_cells(), mesh.nb_cells(sb.REFERENCE)
+    assert n == (1 << (dim * level)), "the mesh must have stayed uniform"
+    st0 = sb.stats(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    secs = e0.elapsed_time(e1) * 1e-3 / iters
+    st = sb.stats()
+    nc = 1 << dim
+    # algorithmic bytes per step, N = leaves, nref = reference cells (levels L, L-1 and the L-2 prediction ghosts):
+    parts = {
+        "zero_fill_detail_tag": 9.0 * nref,              # mr/adapt.hpp:165-168
+        "keep_tags": 1.0 * n,
+        "projection": 8.0 * n + 8.0 * n / nc,            # ghost update: level -> level-1 (read children, write parents)
+        "detail": 8.0 * n + 8.0 * n / nc + 8.0 * n,      # children + parents read once, details written
+        "criteria": 8.0 * n + 8.0 * n / nc + 2.0 * n,    # details of children and parents, tags read + written
+        "keep_propagation": 2.0 * n + 2.0 * n / nc,      # tags of children r/w, parents r/w
+        "change_flag": 1.0 * n,
+        "fv": 16.0 * n,
+    }
+    total = sum(parts.values())
+    u.destroy()
+    v.destroy()
+    mesh.destroy()
+    return {"dim": dim, "level": level, "cells": n, "reference_cells": nref, "ms_per_step": 1e3 * secs, "device_ms_per_step": 1e3 * st["device_seconds"] / iters,
+            "algorithmic_bytes": total, "bytes_per_cell": total / n, "parts_bytes_per_cell": {k: x / n for k, x in parts.items()},
+            "achieved_GBps": total / secs / 1e9, "cell_updates_per_s": n / secs, "launches_per_step": st["kernel_launches"] / iters,
+            "d2h_bytes_per_step": st["d2h_bytes"] / iters, "harten_iterations_per_step": st["harten_iterations"] / iters}
+
+
 def run_product(args):
     import torch
     import torch.distributed as dist

@@ -43,6 +43,7 @@ namespace smr
         int cta_units   = SMR_CTA_CELLS; // output units per CTA (256 x the kernel's units per thread)
         // byte offsets into the arena
         int64_t items = -1, prefix = -1, cta_first = -1, aux = -1;
+        int64_t seeds = -1; // device-derived batches: the uploaded seeds the records come from
         int level     = -1;
 
         bool empty() const
@@ -417,10 +418,12 @@ namespace smr
         {
             // still relative to the device-only region: fixed up together with the aliased batch
             b.items = pd.alias->out->items + static_cast<int64_t>(pd.alias->part_item[pd.alias_part0] * pd.item_size);
+            b.seeds = pd.alias->seeds + static_cast<int64_t>(pd.alias->part_item[pd.alias_part0] * sizeof(smr_seed));
             arena.dev_fixups.push_back(&b.items);
             return;
         }
         pd.seeds = static_cast<int64_t>(arena.take(n * sizeof(smr_seed)));
+        b.seeds  = pd.seeds;
         arena.take_dev(n * pd.item_size, &b.items);
         smr_derive_job jb{};
         jb.kind        = pd.derive;

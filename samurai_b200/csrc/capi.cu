@@ -965,14 +965,8 @@ namespace smr
         }
     }
 
-    // run the phases of `wb` (offsets relative to `arena`) in one cooperative launch
-    static void wf_run(WfBuilder& wb, WfArgs& a, const void* arena, int dim, int radius)
+    static void wf_init()
     {
-        wb.end_phase();
-        if (wb.phases.empty())
-        {
-            return;
-        }
         if (g.wf_host == nullptr)
         {
             SMR_CUDA(cudaMallocHost(&g.wf_host, WF_SLOTS * WF_SLOT_BYTES));
@@ -997,9 +991,221 @@ namespace smr
             }
             g.wf_grid = prop.multiProcessorCount * per_sm;
         }
+    }
+
+    // One job of a throughput-bound phase as its own launch at full occupancy.  The cooperative kernel keeps 2 CTAs of 256
+    // threads per SM (it is sized for the latency-bound level sweeps of adapted meshes); a phase with hundreds of chunks per
+    // CTA (uniform and near-uniform levels) streams 2-3x faster from a plain launch of the same operator
+    // (profiles/r02_summary.md: uniform level-13 step 3.0 -> 1.3 ms).  Per-cell arithmetic is the same functor.
+    static void wf_job_standalone(const WfArgs& a, const WfJob& jb, const void* arena, int dim, int radius)
+    {
+        const char* base = static_cast<const char*>(arena);
+        auto view = [&](auto tag_item)
+        {
+            using Item = decltype(tag_item);
+            return BatchView<Item>{reinterpret_cast<const Item*>(base + jb.items), reinterpret_cast<const int64_t*>(base + jb.prefix),
+                                   reinterpret_cast<const int32_t*>(base + jb.cta_first), jb.n_cells};
+        };
+        const int n_ctas = static_cast<int>((jb.n_cells + SMR_CTA_CELLS - 1) / SMR_CTA_CELLS);
+        int fam          = SMR_FAM_WAVEFRONT;
+        prof_begin();
+        switch (jb.op)
+        {
+            case WF_BC:
+            {
+                BcView bc{reinterpret_cast<const smr_item_bc*>(base + jb.items), reinterpret_cast<const int64_t*>(base + jb.aux), static_cast<int>(jb.n_cells),
+                          a.bc_type[jb.field], a.bc_value[jb.field]};
+                const int ctas = static_cast<int>((jb.n_cells + SMR_CTA_THREADS - 1) / SMR_CTA_THREADS);
+                SMR_CUDA(launch_ghost_phase_kernel(dim, ctas, g.stream, bc, ctas, BatchView<smr_item_proj>{nullptr, nullptr, nullptr, 0}, a.dst[jb.field]));
+                fam = SMR_FAM_BC;
+                break;
+            }
+            case WF_PROJ:
+                fam = SMR_FAM_PROJ;
+                switch (dim)
+                {
+                    case 1:
+                        SMR_CUDA((launch_batch<smr_item_proj, ProjOp<1>>(n_ctas, g.stream, view(smr_item_proj{}), ProjOp<1>{a.src[jb.field], a.dst[jb.field]})));
+                        break;
+                    case 2:
+                        SMR_CUDA((launch_batch<smr_item_proj, ProjOp<2>>(n_ctas, g.stream, view(smr_item_proj{}), ProjOp<2>{a.src[jb.field], a.dst[jb.field]})));
+                        break;
+                    default:
+                        SMR_CUDA((launch_batch<smr_item_proj, ProjOp<3>>(n_ctas, g.stream, view(smr_item_proj{}), ProjOp<3>{a.src[jb.field], a.dst[jb.field]})));
+                        break;
+                }
+                break;
+            case WF_PRED:
+                fam = SMR_FAM_PRED;
+#define SMR_WF_PRED_CASE(D, R)                                                                                                                    \
+    SMR_CUDA((launch_batch<smr_item_pred, PredOp<D, R>>(n_ctas, g.stream, view(smr_item_pred{}), PredOp<D, R>{a.src[jb.field], a.dst[jb.field]})))
+                switch (dim * 2 + (radius ? 1 : 0))
+                {
+                    case 2:
+                        SMR_WF_PRED_CASE(1, 0);
+                        break;
+                    case 3:
+                        SMR_WF_PRED_CASE(1, 1);
+                        break;
+                    case 4:
+                        SMR_WF_PRED_CASE(2, 0);
+                        break;
+                    case 5:
+                        SMR_WF_PRED_CASE(2, 1);
+                        break;
+                    case 6:
+                        SMR_WF_PRED_CASE(3, 0);
+                        break;
+                    default:
+                        SMR_WF_PRED_CASE(3, 1);
+                        break;
+                }
+#undef SMR_WF_PRED_CASE
+                break;
+            case WF_DETAIL:
+                fam = SMR_FAM_DETAIL;
+#define SMR_WF_DETAIL_CASE(D, R)                                                                                          \
+    SMR_CUDA((launch_batch<smr_item_detail, DetailOp<D, R>>(n_ctas, g.stream, view(smr_item_detail{}), \
+                                                             DetailOp<D, R>{a.dst[jb.field], a.detail + jb.field * a.n})))
+                switch (dim * 2 + (radius ? 1 : 0))
+                {
+                    case 2:
+                        SMR_WF_DETAIL_CASE(1, 0);
+                        break;
+                    case 3:
+                        SMR_WF_DETAIL_CASE(1, 1);
+                        break;
+                    case 4:
+                        SMR_WF_DETAIL_CASE(2, 0);
+                        break;
+                    case 5:
+                        SMR_WF_DETAIL_CASE(2, 1);
+                        break;
+                    case 6:
+                        SMR_WF_DETAIL_CASE(3, 0);
+                        break;
+                    default:
+                        SMR_WF_DETAIL_CASE(3, 1);
+                        break;
+                }
+#undef SMR_WF_DETAIL_CASE
+                break;
+            case WF_CRITERIA:
+                fam = SMR_FAM_CRITERIA;
+                switch (dim)
+                {
+                    case 1:
+                        SMR_CUDA((launch_batch<smr_item_tag, CriteriaOp<1>>(n_ctas, g.stream, view(smr_item_tag{}), CriteriaOp<1>{a.detail, a.tag, a.tp, a.ncomp, a.n})));
+                        break;
+                    case 2:
+                        SMR_CUDA((launch_batch<smr_item_tag, CriteriaOp<2>>(n_ctas, g.stream, view(smr_item_tag{}), CriteriaOp<2>{a.detail, a.tag, a.tp, a.ncomp, a.n})));
+                        break;
+                    default:
+                        SMR_CUDA((launch_batch<smr_item_tag, CriteriaOp<3>>(n_ctas, g.stream, view(smr_item_tag{}), CriteriaOp<3>{a.detail, a.tag, a.tp, a.ncomp, a.n})));
+                        break;
+                }
+                break;
+            case WF_MAXIMUM:
+                fam = SMR_FAM_MAXIMUM;
+                switch (dim)
+                {
+                    case 1:
+                        SMR_CUDA((launch_batch<smr_item_tag, MaximumOp<1, true>>(n_ctas, g.stream, view(smr_item_tag{}), MaximumOp<1, true>{a.tag})));
+                        break;
+                    case 2:
+                        SMR_CUDA((launch_batch<smr_item_tag, MaximumOp<2, true>>(n_ctas, g.stream, view(smr_item_tag{}), MaximumOp<2, true>{a.tag})));
+                        break;
+                    default:
+                        SMR_CUDA((launch_batch<smr_item_tag, MaximumOp<3, true>>(n_ctas, g.stream, view(smr_item_tag{}), MaximumOp<3, true>{a.tag})));
+                        break;
+                }
+                break;
+            case WF_KEEP:
+                fam = SMR_FAM_KEEP;
+                SMR_CUDA((launch_batch<smr_item_fv, KeepLeavesOp>(n_ctas, g.stream, view(smr_item_fv{}), KeepLeavesOp{a.tag, a.mask_all})));
+                break;
+            case WF_TAGS_CHANGE:
+                fam = SMR_FAM_KEEP;
+                SMR_CUDA((launch_batch<smr_item_fv, TagsChangeOp>(n_ctas, g.stream, view(smr_item_fv{}),
+                                                                  TagsChangeOp{a.tag, a.change_flag, a.tp.min_level, a.tp.max_level})));
+                break;
+            case WF_ZERO_DETAIL:
+                fam = SMR_FAM_INIT;
+                SMR_CUDA(cudaMemsetAsync(a.detail, 0, static_cast<size_t>(jb.n_cells), g.stream));
+                break;
+            case WF_ZERO_TAG:
+                fam = SMR_FAM_INIT;
+                SMR_CUDA(cudaMemsetAsync(a.tag, 0, static_cast<size_t>(jb.n_cells), g.stream));
+                break;
+            default: // WF_COPY
+                fam = SMR_FAM_COPY;
+                SMR_CUDA((launch_batch<smr_item_copy, CopyOp>(n_ctas, g.stream, view(smr_item_copy{}), CopyOp{a.src[jb.field], a.dst[jb.field]})));
+                break;
+        }
+        ++g.stats.kernel_launches;
+        prof_end(fam, jb.n_cells);
+    }
+
+    static void wf_run_fused(WfBuilder& wb, WfArgs& a, const void* arena, int dim, int radius);
+
+    // run the phases of `wb` (offsets relative to `arena`): runs of latency-bound phases go into one cooperative launch each,
+    // throughput-bound phases (far more chunks than the cooperative grid has CTAs) are launched job by job at full occupancy
+    static void wf_run(WfBuilder& wb, WfArgs& a, const void* arena, int dim, int radius)
+    {
+        wb.end_phase();
+        if (wb.phases.empty())
+        {
+            return;
+        }
+        wf_init();
+        static const bool no_split = std::getenv("SMR_WF_NO_SPLIT") != nullptr;
+        const int wide_at = WF_WIDE_FACTOR * g.wf_grid;
+        size_t p = 0;
+        while (p < wb.phases.size())
+        {
+            if (!no_split && wb.phases[p].total_ctas > wide_at)
+            {
+                const WfPhase& ph = wb.phases[p];
+                for (int j = ph.first_job; j < ph.first_job + ph.n_jobs; ++j)
+                {
+                    wf_job_standalone(a, wb.jobs[static_cast<size_t>(j)], arena, dim, radius);
+                }
+                ++p;
+                continue;
+            }
+            size_t q = p;
+            while (q < wb.phases.size() && (no_split || wb.phases[q].total_ctas <= wide_at))
+            {
+                ++q;
+            }
+            if (p == 0 && q == wb.phases.size())
+            {
+                wf_run_fused(wb, a, arena, dim, radius); // the usual case: nothing to split
+                return;
+            }
+            WfBuilder sub;
+            sub.dim = wb.dim;
+            for (size_t k = p; k < q; ++k)
+            {
+                const WfPhase& ph = wb.phases[k];
+                sub.begin_phase();
+                for (int j = ph.first_job; j < ph.first_job + ph.n_jobs; ++j)
+                {
+                    sub.push(wb.jobs[static_cast<size_t>(j)]);
+                }
+                sub.end_phase();
+            }
+            wf_run_fused(sub, a, arena, dim, radius);
+            p = q;
+        }
+    }
+
+    static void wf_run_fused(WfBuilder& wb, WfArgs& a, const void* arena, int dim, int radius)
+    {
         for (WfPhase& ph : wb.phases)
         {
             // a phase with far more quarter chunks than CTAs is throughput bound: switch its batch jobs to full chunks
+            // (only reached with SMR_WF_NO_SPLIT: wf_run launches such phases on their own)
             if (g.wf_grid > 0 && ph.total_ctas > WF_WIDE_FACTOR * g.wf_grid)
             {
                 int total = 0;

@@ -16,6 +16,7 @@ SMR_MR_DIM(2)
 SMR_MR_DIM(3)
 SMR_INST_BATCH(smr_item_fv, smr::AbsMaxOp)
 SMR_INST_BATCH(smr_item_fv, smr::KeepLeavesOp)
+SMR_INST_BATCH(smr_item_fv, smr::TagsChangeOp)
 SMR_INST_BATCH(smr_item_copy, smr::CopyOp)
 
 namespace smr

@@ -16,6 +16,23 @@
 #ifndef STRIP_MIN_BLOCKS
 #define STRIP_MIN_BLOCKS 6
 #endif
+// resident CTAs per SM the streaming operators are compiled for (register cap = 65536 / (256 * blocks)); measured on the
+// uniform level-13 step (profiles/r02_summary.md)
+#ifndef SMR_MB_DETAIL
+#define SMR_MB_DETAIL 1
+#endif
+#ifndef SMR_MB_CRITERIA
+#define SMR_MB_CRITERIA 1
+#endif
+#ifndef SMR_MB_MAXIMUM
+#define SMR_MB_MAXIMUM 1
+#endif
+#ifndef SMR_MB_COPY
+#define SMR_MB_COPY 1
+#endif
+#ifndef SMR_MB_PROJ
+#define SMR_MB_PROJ 1
+#endif
 
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
@@ -103,6 +120,19 @@ namespace smr
         int64_t n_cells;
     };
 
+    // ops may offer span(it, k0, count): the whole CTA processes `count` consecutive units of ONE record cooperatively
+    // (byte-granular ops on long records: vector accesses instead of one byte per thread)
+    template <class Op, class = void>
+    struct HasSpan
+    {
+        static constexpr bool value = false;
+    };
+    template <class Op>
+    struct HasSpan<Op, decltype(void(Op::has_span))>
+    {
+        static constexpr bool value = Op::has_span;
+    };
+
     // body of one CTA of a batch: output units [cta * U, (cta + 1) * U) ∩ [0, n_cells), U = 256 * Op::units_per_thread
     // `s_prefix`: shared staging for SMR_CTA_THREADS * Op::units_per_thread + 2 entries, owned by the calling kernel
     template <class Item, class Op>
@@ -119,6 +149,13 @@ namespace smr
             // the whole CTA lies inside one record (long intervals: uniform or nearly uniform levels): no staging,
             // no search, the record is read once and every access is base pointer + small immediate
             const Item it = b.items[first];
+            if constexpr (HasSpan<Op>::value)
+            {
+                if (op.span(it, static_cast<int>(base - b.prefix[first]), static_cast<int>(left >= UNITS ? UNITS : left)))
+                {
+                    return;
+                }
+            }
             const int k0  = static_cast<int>(base - b.prefix[first]) + threadIdx.x;
             if (left >= UNITS)
             {
@@ -685,7 +722,7 @@ namespace smr
     {
         static constexpr bool two_phase = false;
         static constexpr bool warp_uniform = false;
-        static constexpr int min_blocks = 1;
+        static constexpr int min_blocks = SMR_MB_PROJ;
         static constexpr int units_per_thread = SMR_CELLS_PER_THREAD;
 
         const double* src; // may alias dst (ghost update projects inside one field)
@@ -772,7 +809,7 @@ namespace smr
     {
         static constexpr bool two_phase = false;
         static constexpr bool warp_uniform = false;
-        static constexpr int min_blocks = 1;
+        static constexpr int min_blocks = SMR_MB_DETAIL;
         static constexpr int units_per_thread = SMR_CELLS_PER_THREAD;
 
         typename PtrOf<const double, RESTRICT>::type f;
@@ -859,9 +896,9 @@ namespace smr
     template <int DIM, bool RESTRICT = true>
     struct CriteriaOp
     {
-        static constexpr bool two_phase = false;
+        static constexpr bool two_phase = true; // all detail loads of a thread's units are issued before its first tag store
         static constexpr bool warp_uniform = false;
-        static constexpr int min_blocks = 1;
+        static constexpr int min_blocks = SMR_MB_CRITERIA;
         static constexpr int units_per_thread = SMR_CELLS_PER_THREAD;
 
         typename PtrOf<const double, RESTRICT>::type detail; // ncomp arrays of `stride` entries (one per adapted field)
@@ -870,12 +907,16 @@ namespace smr
         int ncomp;
         int64_t stride;
 
-        __device__ __forceinline__ void operator()(const smr_item_tag& it, int k) const
+        struct Vals
+        {
+            unsigned bits; // bit 0: the sibling group may coarsen; bit 1 + 2 r + x: child (r, x) must refine
+        };
+
+        __device__ __forceinline__ Vals load(const smr_item_tag& it, int k) const
         {
             constexpr int NR = 1 << (DIM - 1);
-            const int fl        = it.level & 0xff;
-            const unsigned mask = static_cast<unsigned>(it.level) >> 8;
-            bool coarsen_ok     = fl > p.min_level;
+            const int fl    = it.level & 0xff;
+            bool coarsen_ok = fl > p.min_level;
             bool refine[NR][2];
 #pragma unroll
             for (int r = 0; r < NR; ++r)
@@ -907,6 +948,30 @@ namespace smr
                     }
                 }
             }
+            Vals out{coarsen_ok ? 1u : 0u};
+#pragma unroll
+            for (int r = 0; r < NR; ++r)
+            {
+#pragma unroll
+                for (int x = 0; x < 2; ++x)
+                {
+                    out.bits |= refine[r][x] ? (2u << (2 * r + x)) : 0u;
+                }
+            }
+            return out;
+        }
+
+        __device__ __forceinline__ void operator()(const smr_item_tag& it, int k) const
+        {
+            finish(it, k, load(it, k));
+        }
+
+        __device__ __forceinline__ void finish(const smr_item_tag& it, int k, const Vals& v) const
+        {
+            constexpr int NR = 1 << (DIM - 1);
+            const int fl          = it.level & 0xff;
+            const unsigned mask   = static_cast<unsigned>(it.level) >> 8;
+            const bool coarsen_ok = (v.bits & 1u) != 0u;
             if (coarsen_ok)
             {
 #pragma unroll
@@ -924,7 +989,7 @@ namespace smr
 #pragma unroll
                     for (int x = 0; x < 2; ++x)
                     {
-                        if (refine[r][x])
+                        if (v.bits & (2u << (2 * r + x)))
                         {
                             uint8_t* t = tag + it.fine[r] + 2 * k + x;
                             // the coarsen store above (if any) went to the same peers, so the local value is theirs too
@@ -939,50 +1004,82 @@ namespace smr
     template <int DIM, bool RESTRICT = true>
     struct MaximumOp
     {
-        static constexpr bool two_phase = false;
+        static constexpr bool two_phase = true; // the tag loads of a thread's units are issued before its first store
         static constexpr bool warp_uniform = false;
-        static constexpr int min_blocks = 1;
+        static constexpr int min_blocks = SMR_MB_MAXIMUM;
         static constexpr int units_per_thread = SMR_CELLS_PER_THREAD;
 
         typename PtrOf<uint8_t, RESTRICT>::type tag;
 
-        __device__ __forceinline__ void operator()(const smr_item_tag& it, int k) const
+        // Every tag this unit touches (its 2^dim children and their parent) is written by this unit alone during the sweep of
+        // one fine level, so the values may be read up front and a store that would not change the byte may be dropped.
+        struct Vals
+        {
+            uint8_t t[1 << (DIM - 1)][2];
+            uint8_t tc;
+        };
+
+        __device__ __forceinline__ Vals load(const smr_item_tag& it, int k) const
+        {
+            constexpr int NR = 1 << (DIM - 1);
+            Vals v;
+#pragma unroll
+            for (int r = 0; r < NR; ++r)
+            {
+                v.t[r][0] = tag[it.fine[r] + 2 * k];
+                v.t[r][1] = tag[it.fine[r] + 2 * k + 1];
+            }
+            v.tc = tag[it.coarse + k];
+            return v;
+        }
+
+        __device__ __forceinline__ void put(uint8_t* where, uint8_t old_value, uint8_t new_value, unsigned mask) const
+        {
+            if (new_value != old_value || mask != 0u)
+            {
+                mstore(where, new_value, mask);
+            }
+        }
+
+        __device__ __forceinline__ void finish(const smr_item_tag& it, int k, const Vals& v) const
         {
             constexpr int NR    = 1 << (DIM - 1);
             const unsigned mask = static_cast<unsigned>(it.level) >> 8;
-            uint8_t t[NR][2];
             uint8_t any = 0, all = 0xff;
 #pragma unroll
             for (int r = 0; r < NR; ++r)
             {
-                t[r][0] = tag[it.fine[r] + 2 * k];
-                t[r][1] = tag[it.fine[r] + 2 * k + 1];
-                any |= t[r][0] | t[r][1];
-                all &= t[r][0] & t[r][1];
+                any |= v.t[r][0] | v.t[r][1];
+                all &= v.t[r][0] & v.t[r][1];
             }
             if (any & 1)
             {
 #pragma unroll
                 for (int r = 0; r < NR; ++r)
                 {
-                    mstore(tag + it.fine[r] + 2 * k, static_cast<uint8_t>(t[r][0] | 1), mask);
-                    mstore(tag + it.fine[r] + 2 * k + 1, static_cast<uint8_t>(t[r][1] | 1), mask);
+                    put(tag + it.fine[r] + 2 * k, v.t[r][0], static_cast<uint8_t>(v.t[r][0] | 1), mask);
+                    put(tag + it.fine[r] + 2 * k + 1, v.t[r][1], static_cast<uint8_t>(v.t[r][1] | 1), mask);
                 }
-                mstore(tag + it.coarse + k, static_cast<uint8_t>(tag[it.coarse + k] | 1), mask);
+                put(tag + it.coarse + k, v.tc, static_cast<uint8_t>(v.tc | 1), mask);
             }
             else if (all & 2)
             {
-                mstore(tag + it.coarse + k, static_cast<uint8_t>(tag[it.coarse + k] | 1), mask);
+                put(tag + it.coarse + k, v.tc, static_cast<uint8_t>(v.tc | 1), mask);
             }
             else
             {
 #pragma unroll
                 for (int r = 0; r < NR; ++r)
                 {
-                    mstore(tag + it.fine[r] + 2 * k, static_cast<uint8_t>(t[r][0] & ~2), mask);
-                    mstore(tag + it.fine[r] + 2 * k + 1, static_cast<uint8_t>(t[r][1] & ~2), mask);
+                    put(tag + it.fine[r] + 2 * k, v.t[r][0], static_cast<uint8_t>(v.t[r][0] & ~2), mask);
+                    put(tag + it.fine[r] + 2 * k + 1, v.t[r][1], static_cast<uint8_t>(v.t[r][1] & ~2), mask);
                 }
             }
+        }
+
+        __device__ __forceinline__ void operator()(const smr_item_tag& it, int k) const
+        {
+            finish(it, k, load(it, k));
         }
     };
 
@@ -1059,6 +1156,36 @@ namespace smr
         {
             mstore(tag + it.c + k, static_cast<uint8_t>(1), mask_all);
         }
+
+        // long leaf intervals: a memset of `count` bytes with 16-byte stores (one byte store per thread was measured at
+        // 0.1 TB/s on the uniform level-13 mesh: partial-sector writes)
+        static constexpr bool has_span = true;
+        __device__ __forceinline__ bool span(const smr_item_fv& it, int k0, int count) const
+        {
+            if (mask_all != 0u)
+            {
+                return false;
+            }
+            uint8_t* p     = tag + it.c + k0;
+            const int head = min(count, static_cast<int>((16u - (static_cast<unsigned>(reinterpret_cast<uintptr_t>(p)) & 15u)) & 15u));
+            const int nvec = (count - head) >> 4;
+            const int tail = count - head - (nvec << 4);
+            const int t    = threadIdx.x;
+            if (t < head)
+            {
+                p[t] = 1;
+            }
+            uint4* v = reinterpret_cast<uint4*>(p + head);
+            for (int i = t; i < nvec; i += SMR_CTA_THREADS)
+            {
+                v[i] = make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);
+            }
+            if (t < tail)
+            {
+                p[head + (nvec << 4) + t] = 1;
+            }
+            return true;
+        }
     };
 
     using KeepLeavesOp = KeepLeavesOpT<true>;
@@ -1084,6 +1211,43 @@ namespace smr
             {
                 *flag = 1u; // benign race: every writer stores the same value
             }
+        }
+
+        // long leaf intervals: 16 tags per load, the two conditions evaluated on packed bytes
+        static constexpr bool has_span = true;
+        __device__ __forceinline__ bool span(const smr_item_fv& it, int k0, int count) const
+        {
+            const uint8_t* p = tag + it.c + k0;
+            const int head   = min(count, static_cast<int>((16u - (static_cast<unsigned>(reinterpret_cast<uintptr_t>(p)) & 15u)) & 15u));
+            const int nvec   = (count - head) >> 4;
+            const int tail   = count - head - (nvec << 4);
+            const int t      = threadIdx.x;
+            const unsigned refine_on  = it.level < max_level ? 0x04040404u : 0u;
+            const unsigned coarsen_on = it.level > min_level ? 0x02020202u : 0u;
+            unsigned hit = 0;
+            auto test = [&](unsigned w) { hit |= (w & refine_on) | (w & coarsen_on & ~((w & 0x01010101u) << 1)); };
+            if (t < head)
+            {
+                test(p[t]);
+            }
+            const uint4* v = reinterpret_cast<const uint4*>(p + head);
+            for (int i = t; i < nvec; i += SMR_CTA_THREADS)
+            {
+                const uint4 w = v[i];
+                test(w.x);
+                test(w.y);
+                test(w.z);
+                test(w.w);
+            }
+            if (t < tail)
+            {
+                test(p[head + (nvec << 4) + t]);
+            }
+            if (hit != 0u)
+            {
+                *flag = 1u;
+            }
+            return true;
         }
     };
 
@@ -1134,7 +1298,7 @@ namespace smr
     {
         static constexpr bool two_phase = false;
         static constexpr bool warp_uniform = false;
-        static constexpr int min_blocks = 1;
+        static constexpr int min_blocks = SMR_MB_COPY;
         static constexpr int units_per_thread = SMR_CELLS_PER_THREAD;
 
         typename PtrOf<const double, RESTRICT>::type src;
