@@ -199,31 +199,62 @@ def oracle_steps(so, cfg, bc, mesh, u, n_steps, dt):
     return cells, time.perf_counter() - t0, mesh, u
 
 
+def workload_string(args):
+    return (f"advection_{args.dim}d min_level={args.min_level} max_level={args.max_level} eps={args.eps} pred_radius=1 Dirichlet(0) "
+            f"ball r=0.2@(0.3,..), a=(1,..), cfl={0.5 if args.dim == 2 else 0.25}; one step = MRadaptation + update_ghost_mr + upwind + swap")
+
+
+def cpu_adapted_sim(args):
+    """The workload's adapted start state built by the compiled CPU path alone (bottom-up: uniform coarse level, refine to
+    max_level re-imposing the exact initial condition, like the demo's initial MRadaptation from the other side)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import cpu_path
+
+    start = min(8 if args.dim == 2 else 5, args.max_level)
+    sim = cpu_path.CpuSim(args.dim, args.min_level, args.max_level, 1, eps=args.eps, regularity=1.0, start_level=start)
+    sim.init_ball([0.3] * args.dim, 0.2)
+    for _ in range(args.max_level - args.min_level + 2):
+        n0 = sim.nb_cells()
+        sim.adapt()
+        sim.init_ball([0.3] * args.dim, 0.2)
+        if sim.nb_cells() == n0:
+            break
+    return cpu_path, sim
+
+
 def run_reference(args):
+    """The CPU arm: the reference library itself cannot be built in this image, so this times the
+    compiled all-cores CPU path (oracle/cpu_path.cpp, `kind: port`, bit-identical to the numpy oracle that is pinned on the
+    reference's golden files) on the SAME workload as the product arm, all host threads."""
     rank, _, world = dist_env()
     if rank != 0:
         return
+    os.environ.pop("OMP_NUM_THREADS", None)  # torchrun pins it to 1; this arm runs alone on rank 0 with every host core
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import samurai_oracle as so
+    import cpu_path
 
-    # bounded sample: the numpy port advances ~9e4 cell-updates/s and the adapted mesh holds ~1.2e5 * 2^(L-12) leaves,
-    # so pick the largest max_level <= the product's whose (steps + warmup) fit in ~150 s of CPU work
-    sample_level = min(args.max_level, args.ref_max_level)
-    while sample_level > args.min_level + 2 and (args.steps + args.warmup) * 1.3 * 2.0 ** (sample_level - 12) > 150.0:
-        sample_level -= 1
-    cfg, bc, mesh, u = oracle_adapted_state(so, args.min_level, sample_level, args.eps)
-    dt = 0.5 * cfg.cell_length(sample_level)
-    _, _, mesh, u = oracle_steps(so, cfg, bc, mesh, u, args.warmup, dt)
-    cells, secs, mesh, u = oracle_steps(so, cfg, bc, mesh, u, args.steps, dt)
+    cpu_path.CpuSim.set_threads(os.cpu_count() or 1)
+    cpu_path, sim = cpu_adapted_sim(args)
+    a = [1.0] * args.dim
+    dt = (0.5 if args.dim == 2 else 0.25) / (1 << args.max_level)
+    sim.steps(args.warmup, a, dt)
+    sim.times(reset=True)
+    t0 = time.perf_counter()
+    cells = sim.steps(args.steps, a, dt)
+    secs = time.perf_counter() - t0
     value = cells / secs
-    sample = (f"{args.steps} steps of advection_2d on the oracle's own adapted mesh, levels {args.min_level}-{sample_level} "
-              f"({mesh.nb_cells()} leaves); numpy port, 1 thread")
+    tm = sim.times()
+    cores = cpu_path.CpuSim.threads()
+    sample = (f"{args.steps} steps of the full workload ({sim.nb_cells()} leaves, {sim.nb_cells(True)} reference cells at the end); compiled C++/OpenMP port "
+              f"(oracle/cpu_path.cpp, -O3 -march=x86-64-v3 -ffp-contract=off), {cores} threads")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"advection_2d min_level={args.min_level} max_level={sample_level} eps={args.eps} (CPU sample of the max_level={args.max_level} case)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+        "config": {"workload": workload_string(args), "leaves": sim.nb_cells(), "reference_cells": sim.nb_cells(True)},
+        "split_ms_per_step": {"fp_loops": 1e3 * tm["fp_s"] / args.steps, "host_mesh": 1e3 * tm["host_mesh_s"] / args.steps,
+                              "host_batches": 1e3 * tm["host_batches_s"] / args.steps},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -392,7 +423,7 @@ def run_product(args):
     if world > 1:
         # every field / detail / tag buffer lives in a per-rank pool mapped into the peers: size it for the uniform
         # max_level start mesh (reference cells ~ 4/3 * 4^L; u, its transfer twin, unp1, detail, tags) with slack
-        nref0 = int(4 ** args.max_level * 1.35)
+        nref0 = int((2 ** args.dim) ** args.max_level * (1.35 if args.dim == 2 else 1.16))
         pool = int(nref0 * (8 * 4 + 1) * 1.6) + (1 << 28)
         ok = sb.initialize_multi(rank, world, device=local_rank, pool_bytes=pool)
     else:
@@ -473,14 +504,18 @@ def run_product(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         secs, e2e_secs = t.tolist()  # cells / e2e_cells already count the GLOBAL leaves (every rank holds the whole mesh)
 
+    # ---- parity against the CPU path + cpu baseline (collective: every rank steps the product) -------------------------------
+    cpu = parity = None
+    if not args.no_cpu_baseline:
+        cpu, parity = parity_and_cpu_baseline(sb, sim, args, rank, world, barrier)
+
     line = None
     if rank == 0 and world > 1:
         line = {
             "metric": METRIC, "value": cells / secs, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"advection_{args.dim}d min_level={args.min_level} max_level={args.max_level} eps={args.eps} pred_radius=1 Dirichlet(0) "
-                                   f"ball r=0.2@(0.3,..), a=(1,..), cfl={0.5 if args.dim == 2 else 0.25}; one step = MRadaptation + update_ghost_mr + upwind + swap",
+            "config": {"workload": workload_string(args),
                        "leaves": leaves_now, "reference_cells": ref_now,
                        "parallelism": f"{world} leaf-balanced slabs (one per GPU), halo values stored into the peers by the producing kernels over "
                                       f"NVLink (CUDA IPC), flag barrier per phase, tags replicated; same global problem as N=1"},
@@ -490,7 +525,7 @@ def run_product(args):
             "initial_adaptation_s": init_secs,
             "e2e": {"value": e2e_cells / e2e_secs, "unit": UNIT, "h2d_bytes_per_step": int(st_e2e["h2d_bytes"] / args.steps),
                     "d2h_bytes_per_step": int(st_e2e["d2h_bytes"] / args.steps), "ms_per_step": 1e3 * e2e_secs / args.steps},
-            "roofline": None, "cpu_baseline": None, "clocks": clocks,
+            "roofline": None, "cpu_baseline": cpu, "parity": parity, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
     elif rank == 0:
@@ -550,17 +585,27 @@ def run_product(args):
         except Exception as e:  # noqa: BLE001
             flux = {"error": str(e)}
 
-        # ---- cpu baseline: oracle port on a bounded sample of the same state ----------------------------------------
-        cpu = None
-        if not args.no_cpu_baseline:
-            cpu = cpu_baseline_from_state(sb, sim, args)
+        # ---- the whole step on uniform meshes (configs[4] shapes): the HBM-bound form of the metric ---------------------
+        ustep = None
+        if args.sweep_level > 0:
+            ustep = {}
+            for d, lvl in ((2, args.sweep_level), (3, args.sweep_level_3d)):
+                if lvl <= 0:
+                    continue
+                r = uniform_full_step(sb, torch, d, lvl)
+                r.update({"bound": "hbm", "achieved": r["achieved_GBps"], "peak": peak_gbs, "unit": "GB/s", "frac": r["achieved_GBps"] / peak_gbs})
+                ustep[f"{d}d_level{lvl}"] = r
+
+        # ---- the numpy oracle itself on the full-size mesh (the checker pinned on the reference's golden files) --------
+        np_parity = None
+        if not args.no_cpu_baseline and args.numpy_parity_steps > 0:
+            np_parity = numpy_oracle_parity(sb, sim, args, args.numpy_parity_steps)
 
         line = {
             "metric": METRIC, "value": cells / secs, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"advection_{args.dim}d min_level={args.min_level} max_level={args.max_level} eps={args.eps} pred_radius=1 Dirichlet(0) "
-                                   f"ball r=0.2@(0.3,..), a=(1,..), cfl={0.5 if args.dim == 2 else 0.25}; one step = MRadaptation + update_ghost_mr + upwind + swap",
+            "config": {"workload": workload_string(args),
                        "leaves": leaves_now, "reference_cells": ref_now, "parallelism": f"replicas x{world}" if world > 1 else "single GPU",
                        "l2_policy": "every kernel is launched once per mesh state; between timed steps the mesh and all index batches change; "
                                     "the uniform sweep uses a working set > L2"},
@@ -586,8 +631,11 @@ def run_product(args):
             "kernel_families_fused": fused,
             "kernel_families_per_sweep_launches": families,
             "uniform_sweep": sweep,
+            "uniform_full_step": ustep,
             "flux_scheme_on_adapted_mesh": flux,
             "cpu_baseline": cpu,
+            "parity": parity,
+            "parity_numpy_oracle": np_parity,
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
@@ -596,9 +644,70 @@ def run_product(args):
         dist.destroy_process_group()
 
 
-def cpu_baseline_from_state(sb, sim, args):
-    """Oracle port timed on the product's current adapted mesh (same leaves, same field): a bounded sample of the
-    same workload, and a full-size parity check of the step at the same time."""
+def product_leaves(sb, sim, max_level):
+    """Leaf intervals (level, y, z, xs, xe) and leaf values of the product, in for_each_cell order."""
+    rows, offs = [], []
+    for level in range(max_level + 1):
+        iv = sim.mesh.intervals(sb.CELLS, level)
+        if iv.size == 0:
+            continue
+        rows.append(np.stack([np.full(iv.size, level), iv["y"], iv["z"], iv["start"], iv["end"]], axis=1).astype(np.int32))
+        n = (iv["end"] - iv["start"]).astype(np.int64)
+        rep = np.repeat(np.arange(iv.size), n)
+        offs.append(iv["offset"][rep] + (np.arange(int(n.sum())) - np.repeat(np.cumsum(n) - n, n)))
+    u = sim.u.download()
+    return np.concatenate(rows), u[np.concatenate(offs)]
+
+
+def parity_and_cpu_baseline(sb, sim, args, rank, world, barrier):
+    """Every rank calls this.  Rank 0 hands the product's current state (leaves + leaf values) to the compiled CPU path
+    (oracle/cpu_path.cpp, bit-identical to the numpy oracle), times `--cpu-steps` steps of it on all host cores (the
+    cpu_baseline: a bounded sample of the same workload), then all ranks advance the product by the same steps and rank 0
+    compares: leaves bit-identical, leaf values within 1e-12 relative (north_star).  At N > 1 this is the check that the
+    N-GPU run equals the single-process result (the reference CI's procedure, .github/workflows/ci.yml:298-330)."""
+    n_steps = args.cpu_steps
+    if world > 1:
+        sb.mg_broadcast(sim.u)
+    cpu = parity = None
+    cs = None
+    if rank == 0:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import cpu_path
+
+        saved = cpu_path.CpuSim.set_threads(os.cpu_count() or 1)  # the other ranks wait at the barrier below
+        iv, vals = product_leaves(sb, sim, args.max_level)
+        cs = cpu_path.CpuSim(args.dim, args.min_level, args.max_level, 1, eps=args.eps, regularity=1.0, leaves=iv, leaf_values=vals)
+        a = [1.0] * args.dim
+        cs.steps(1, a, sim.dt)  # warm-up (first-touch of the arenas)
+        t0 = time.perf_counter()
+        done = cs.steps(n_steps, a, sim.dt)
+        secs = time.perf_counter() - t0
+        tm = cs.times()
+        cores = cpu_path.CpuSim.threads()
+        cpu_path.CpuSim.set_threads(saved)
+        cpu = {"value": done / secs, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{n_steps} steps from the product's own adapted state ({cs.nb_cells()} leaves); compiled C++/OpenMP port oracle/cpu_path.cpp "
+                         f"(-O3 -march=x86-64-v3 -ffp-contract=off), all host threads" + (f"; {world} ranks were idle meanwhile" if world > 1 else ""),
+               "ms_per_step": 1e3 * secs / n_steps}
+    barrier()
+    for _ in range(n_steps + 1):
+        sim.step()
+    if world > 1:
+        sb.mg_broadcast(sim.u)
+    if rank == 0:
+        iv2, vals2 = product_leaves(sb, sim, args.max_level)
+        civ, cvals = cs.leaves()
+        same = bool(iv2.shape == civ.shape and np.array_equal(iv2, civ))
+        err = float(np.max(np.abs(vals2 - cvals) / np.maximum(np.abs(cvals), 1.0))) if same else None
+        parity = {"against": "compiled CPU path started from the same state (bit-identical to the numpy oracle, tests/test_cpu_path.py)",
+                  "steps": n_steps + 1, "mesh_identical": same, "max_rel_err": err, "leaves": int(vals2.size),
+                  "leaf_sum_product": float(np.sum(vals2)), "leaf_sum_cpu": float(np.sum(cvals))}
+        cs.close()
+    return cpu, parity
+
+
+def numpy_oracle_parity(sb, sim, args, n_steps):
+    """The numpy oracle (the checker pinned on the reference's golden files) on the product's current full-size mesh."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import samurai_oracle as so
 
@@ -613,9 +722,7 @@ def cpu_baseline_from_state(sb, sim, args):
     assert np.array_equal(olv, lv) and np.array_equal(oco, co)
     ou[oix] = pu[off]
     bc = so.Bc("dirichlet", 0.0)
-    n_steps = args.cpu_steps
     cells_done, secs, omesh, ou = oracle_steps(so, cfg, bc, omesh, ou, n_steps, sim.dt)
-    # parity at full size: advance the product by the same steps and compare
     for _ in range(n_steps):
         sim.step()
     lv2, co2, off2 = sim.mesh.cell_table(sb.CELLS)
@@ -623,9 +730,8 @@ def cpu_baseline_from_state(sb, sim, args):
     same_mesh = bool(np.array_equal(olv, lv2) and np.array_equal(oco, co2))
     pu2 = sim.u.download()
     err = float(np.max(np.abs(pu2[off2] - ou[oix]) / np.maximum(np.abs(ou[oix]), 1.0))) if same_mesh else None
-    return {"value": cells_done / secs, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"{n_steps} steps on the same adapted mesh ({omesh.nb_cells()} leaves), numpy oracle, 1 thread",
-            "parity_mesh_identical": same_mesh, "parity_max_rel_err": err}
+    return {"steps": n_steps, "leaves": int(omesh.nb_cells()), "mesh_identical": same_mesh, "max_rel_err": err,
+            "numpy_oracle_cell_updates_per_s": cells_done / secs}
 
 
 def main():
@@ -640,7 +746,9 @@ def main():
     ap.add_argument("--max-level", type=int, default=14)
     ap.add_argument("--eps", type=float, default=2e-4)
     ap.add_argument("--sweep-level", type=int, default=13)
-    ap.add_argument("--cpu-steps", type=int, default=2)
+    ap.add_argument("--cpu-steps", type=int, default=10, help="steps of the compiled CPU path timed as cpu_baseline (and compared with the product)")
+    ap.add_argument("--numpy-parity-steps", type=int, default=1, help="steps of the numpy oracle compared with the product at full size (N=1)")
+    ap.add_argument("--sweep-level-3d", type=int, default=9, help="level of the 3D uniform full-step measurement (0: skip)")
     ap.add_argument("--ref-max-level", type=int, default=14, help="largest max_level the CPU reference arm samples")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--clock-period", type=float, default=0.1, help="seconds between NVML clock samples during the timed region")

@@ -781,6 +781,18 @@ extern "C"
         return omp_get_max_threads();
     }
 
+    // the OpenMP runtime is shared with whatever else the process loaded (torchrun pins OMP_NUM_THREADS=1): let the caller
+    // give this arm all host cores and restore the previous setting afterwards
+    int cpu_sim_set_threads(int n)
+    {
+        const int before = omp_get_max_threads();
+        if (n > 0)
+        {
+            omp_set_num_threads(n);
+        }
+        return before;
+    }
+
     int cpu_sim_init_ball(void* h, const double* center, double radius, double inside, double outside)
     {
         Sim* S = static_cast<Sim*>(h);

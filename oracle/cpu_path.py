@@ -34,6 +34,8 @@ def load():
     L.cpu_sim_create_from_leaves.argtypes = [i32, i32, i32, i32, f64, f64, i32, f64, vp, i64, vp]
     L.cpu_sim_destroy.argtypes = [vp]
     L.cpu_sim_threads.restype = i32
+    L.cpu_sim_set_threads.restype = i32
+    L.cpu_sim_set_threads.argtypes = [i32]
     L.cpu_sim_init_ball.argtypes = [vp, vp, f64, f64, f64]
     L.cpu_sim_adapt.argtypes = [vp]
     L.cpu_sim_update_ghost.argtypes = [vp]
@@ -82,6 +84,11 @@ class CpuSim:
     @staticmethod
     def threads():
         return load().cpu_sim_threads()
+
+    @staticmethod
+    def set_threads(n):
+        """returns the previous setting"""
+        return load().cpu_sim_set_threads(int(n))
 
     def _ok(self, rc):
         if rc != 0:

@@ -877,7 +877,7 @@ namespace smr
             j.items     = b.items;
             j.prefix    = b.prefix;
             j.cta_first = b.cta_first;
-            j.aux       = b.aux;
+            j.aux       = op == WF_BC ? b.aux : static_cast<int64_t>(b.n_items); // bc: source offsets; batch jobs: number of records
             j.field     = field;
             push(j);
         }
@@ -1122,12 +1122,13 @@ namespace smr
                 break;
             case WF_KEEP:
                 fam = SMR_FAM_KEEP;
-                SMR_CUDA((launch_batch<smr_item_fv, KeepLeavesOp>(n_ctas, g.stream, view(smr_item_fv{}), KeepLeavesOp{a.tag, a.mask_all})));
+                SMR_CUDA((launch_records<smr_item_fv, KeepLeavesOp>(g.stream, reinterpret_cast<const smr_item_fv*>(base + jb.items), static_cast<int>(jb.aux),
+                                                                    KeepLeavesOp{a.tag, a.mask_all})));
                 break;
             case WF_TAGS_CHANGE:
                 fam = SMR_FAM_KEEP;
-                SMR_CUDA((launch_batch<smr_item_fv, TagsChangeOp>(n_ctas, g.stream, view(smr_item_fv{}),
-                                                                  TagsChangeOp{a.tag, a.change_flag, a.tp.min_level, a.tp.max_level})));
+                SMR_CUDA((launch_records<smr_item_fv, TagsChangeOp>(g.stream, reinterpret_cast<const smr_item_fv*>(base + jb.items), static_cast<int>(jb.aux),
+                                                                    TagsChangeOp{a.tag, a.change_flag, a.tp.min_level, a.tp.max_level})));
                 break;
             case WF_ZERO_DETAIL:
                 fam = SMR_FAM_INIT;

@@ -17,6 +17,8 @@ SMR_MR_DIM(3)
 SMR_INST_BATCH(smr_item_fv, smr::AbsMaxOp)
 SMR_INST_BATCH(smr_item_fv, smr::KeepLeavesOp)
 SMR_INST_BATCH(smr_item_fv, smr::TagsChangeOp)
+SMR_INST_RECORDS(smr_item_fv, smr::KeepLeavesOp)
+SMR_INST_RECORDS(smr_item_fv, smr::TagsChangeOp)
 SMR_INST_BATCH(smr_item_copy, smr::CopyOp)
 
 namespace smr

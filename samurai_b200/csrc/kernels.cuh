@@ -19,19 +19,19 @@
 // resident CTAs per SM the streaming operators are compiled for (register cap = 65536 / (256 * blocks)); measured on the
 // uniform level-13 step (profiles/r02_summary.md)
 #ifndef SMR_MB_DETAIL
-#define SMR_MB_DETAIL 1
+#define SMR_MB_DETAIL 6
 #endif
 #ifndef SMR_MB_CRITERIA
-#define SMR_MB_CRITERIA 1
+#define SMR_MB_CRITERIA 6
 #endif
 #ifndef SMR_MB_MAXIMUM
-#define SMR_MB_MAXIMUM 1
+#define SMR_MB_MAXIMUM 6
 #endif
 #ifndef SMR_MB_COPY
-#define SMR_MB_COPY 1
+#define SMR_MB_COPY 6
 #endif
 #ifndef SMR_MB_PROJ
-#define SMR_MB_PROJ 1
+#define SMR_MB_PROJ 6
 #endif
 
 #include <cooperative_groups.h>
@@ -279,6 +279,19 @@ namespace smr
                 }
             }
             op(b.items[first + lo], g - s_prefix[lo]);
+        }
+    }
+
+    // One warp per record: byte-granular operators over the leaf intervals (keep tags, change flag) when they run as their
+    // own launch.  A 1024-cell chunk is 1 KB of tags, so the chunked kernel spends its time on the per-CTA index chain
+    // (measured 140-190 us for 67 MB on the uniform level-13 mesh); a warp streams its whole record with 16-byte accesses.
+    template <class Item, class Op>
+    __global__ void __launch_bounds__(SMR_CTA_THREADS) record_kernel(const Item* __restrict__ items, int n_items, Op op)
+    {
+        const int r = static_cast<int>(blockIdx.x) * (SMR_CTA_THREADS / 32) + static_cast<int>(threadIdx.x >> 5);
+        if (r < n_items)
+        {
+            op.record(items[r], static_cast<int>(threadIdx.x & 31));
         }
     }
 
@@ -809,7 +822,7 @@ namespace smr
     {
         static constexpr bool two_phase = false;
         static constexpr bool warp_uniform = false;
-        static constexpr int min_blocks = SMR_MB_DETAIL;
+        static constexpr int min_blocks = DIM > 2 ? 2 : SMR_MB_DETAIL;
         static constexpr int units_per_thread = SMR_CELLS_PER_THREAD;
 
         typename PtrOf<const double, RESTRICT>::type f;
@@ -898,7 +911,7 @@ namespace smr
     {
         static constexpr bool two_phase = true; // all detail loads of a thread's units are issued before its first tag store
         static constexpr bool warp_uniform = false;
-        static constexpr int min_blocks = SMR_MB_CRITERIA;
+        static constexpr int min_blocks = DIM > 2 ? 4 : SMR_MB_CRITERIA;
         static constexpr int units_per_thread = SMR_CELLS_PER_THREAD;
 
         typename PtrOf<const double, RESTRICT>::type detail; // ncomp arrays of `stride` entries (one per adapted field)
@@ -1006,7 +1019,7 @@ namespace smr
     {
         static constexpr bool two_phase = true; // the tag loads of a thread's units are issued before its first store
         static constexpr bool warp_uniform = false;
-        static constexpr int min_blocks = SMR_MB_MAXIMUM;
+        static constexpr int min_blocks = DIM > 2 ? 4 : SMR_MB_MAXIMUM;
         static constexpr int units_per_thread = SMR_CELLS_PER_THREAD;
 
         typename PtrOf<uint8_t, RESTRICT>::type tag;
@@ -1186,6 +1199,28 @@ namespace smr
             }
             return true;
         }
+
+        // the whole record by one warp (record_kernel)
+        __device__ __forceinline__ void record(const smr_item_fv& it, int lane) const
+        {
+            uint8_t* p     = tag + it.c;
+            const int head = min(it.n, static_cast<int>((16u - (static_cast<unsigned>(reinterpret_cast<uintptr_t>(p)) & 15u)) & 15u));
+            const int nvec = (it.n - head) >> 4;
+            const int tail = it.n - head - (nvec << 4);
+            if (lane < head)
+            {
+                p[lane] = 1;
+            }
+            uint4* v = reinterpret_cast<uint4*>(p + head);
+            for (int i = lane; i < nvec; i += 32)
+            {
+                v[i] = make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);
+            }
+            if (lane < tail)
+            {
+                p[head + (nvec << 4) + lane] = 1;
+            }
+        }
     };
 
     using KeepLeavesOp = KeepLeavesOpT<true>;
@@ -1248,6 +1283,41 @@ namespace smr
                 *flag = 1u;
             }
             return true;
+        }
+
+        // the whole record by one warp (record_kernel)
+        __device__ __forceinline__ void record(const smr_item_fv& it, int lane) const
+        {
+            const uint8_t* p = tag + it.c;
+            const int head   = min(it.n, static_cast<int>((16u - (static_cast<unsigned>(reinterpret_cast<uintptr_t>(p)) & 15u)) & 15u));
+            const int nvec   = (it.n - head) >> 4;
+            const int tail   = it.n - head - (nvec << 4);
+            const unsigned refine_on  = it.level < max_level ? 0x04040404u : 0u;
+            const unsigned coarsen_on = it.level > min_level ? 0x02020202u : 0u;
+            unsigned hit = 0;
+            auto test = [&](unsigned w) { hit |= (w & refine_on) | (w & coarsen_on & ~((w & 0x01010101u) << 1)); };
+            if (lane < head)
+            {
+                test(p[lane]);
+            }
+            const uint4* v = reinterpret_cast<const uint4*>(p + head);
+#pragma unroll 4
+            for (int i = lane; i < nvec; i += 32)
+            {
+                const uint4 w = v[i];
+                test(w.x);
+                test(w.y);
+                test(w.z);
+                test(w.w);
+            }
+            if (lane < tail)
+            {
+                test(p[head + (nvec << 4) + lane]);
+            }
+            if (hit != 0u)
+            {
+                *flag = 1u;
+            }
         }
     };
 

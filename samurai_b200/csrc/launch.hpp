@@ -11,6 +11,10 @@ namespace smr
     template <class Item, class Op>
     cudaError_t launch_batch(int grid, cudaStream_t st, const BatchView<Item>& v, const Op& op);
 
+    // record_kernel<Item, Op><<<ceil(n_items / 8), 256>>>: one warp per record
+    template <class Item, class Op>
+    cudaError_t launch_records(cudaStream_t st, const Item* items, int n_items, const Op& op);
+
     cudaError_t launch_ghost_phase_kernel(int dim, int grid, cudaStream_t st, const BcView& bc, int bc_ctas, const BatchView<smr_item_proj>& pv, double* f);
 
     // records from seeds + CSR (derive.cuh, k_derive.cu)

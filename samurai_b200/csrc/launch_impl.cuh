@@ -11,6 +11,13 @@ namespace smr
         return cudaGetLastError();
     }
 
+    template <class Item, class Op>
+    cudaError_t launch_records(cudaStream_t st, const Item* items, int n_items, const Op& op)
+    {
+        record_kernel<Item, Op><<<(n_items + SMR_CTA_THREADS / 32 - 1) / (SMR_CTA_THREADS / 32), SMR_CTA_THREADS, 0, st>>>(items, n_items, op);
+        return cudaGetLastError();
+    }
+
     template <int DIM, int RADIUS>
     cudaError_t wf_launch_inst(WfArgs& a, int grid, size_t smem, cudaStream_t st)
     {
@@ -42,4 +49,5 @@ namespace smr
     }
 } // namespace smr
 
+#define SMR_INST_RECORDS(Item, ...) template cudaError_t smr::launch_records<Item, __VA_ARGS__>(cudaStream_t, const Item*, int, const __VA_ARGS__&);
 #define SMR_INST_BATCH(Item, ...) template cudaError_t smr::launch_batch<Item, __VA_ARGS__>(int, cudaStream_t, const smr::BatchView<Item>&, const __VA_ARGS__&);
