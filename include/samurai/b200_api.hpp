@@ -561,6 +561,220 @@ namespace samurai
         }
     };
 
+    // interval.hpp:262-300: translation of an interval (`i - 1`, `i + 1` in stencil expressions)
+    inline Interval operator+(Interval i, int s)
+    {
+        i.start += s;
+        i.end += s;
+        i.index -= s; // the same storage cells are no longer addressed: callers re-resolve the row (ScalarField::operator())
+        return i;
+    }
+
+    inline Interval operator-(Interval i, int s)
+    {
+        return i + (-s);
+    }
+
+    // ---- host-side row expressions -----------------------------------------------------------------------------------------
+    // `u(level, i, j)` (field/access_base.hpp:69-103) is a view of one x-interval of the field; the reference combines such views
+    // with xtensor expression templates inside user lambdas (README.md:144-151).  This is the HOST path of the drop-in: the views
+    // address the field's host mirror (downloaded once after the device last wrote the field, uploaded before the device next reads
+    // it).  The device kernels never go through it.
+    namespace rowx
+    {
+        template <class E>
+        struct expr
+        {
+            const E& self() const
+            {
+                return static_cast<const E&>(*this);
+            }
+        };
+
+        struct scalar : expr<scalar>
+        {
+            double v;
+
+            explicit scalar(double x)
+                : v(x)
+            {
+            }
+
+            double operator[](std::size_t) const
+            {
+                return v;
+            }
+
+            std::size_t size() const
+            {
+                return 0;
+            }
+        };
+
+        template <class A, class B, class Op>
+        struct binary : expr<binary<A, B, Op>>
+        {
+            A a;
+            B b;
+
+            binary(const A& a_, const B& b_)
+                : a(a_)
+                , b(b_)
+            {
+            }
+
+            double operator[](std::size_t k) const
+            {
+                return Op::apply(a[k], b[k]);
+            }
+
+            std::size_t size() const
+            {
+                return std::max(a.size(), b.size());
+            }
+        };
+
+        struct add
+        {
+            static double apply(double x, double y)
+            {
+                return x + y;
+            }
+        };
+
+        struct sub
+        {
+            static double apply(double x, double y)
+            {
+                return x - y;
+            }
+        };
+
+        struct mul
+        {
+            static double apply(double x, double y)
+            {
+                return x * y;
+            }
+        };
+
+        struct div
+        {
+            static double apply(double x, double y)
+            {
+                return x / y;
+            }
+        };
+
+        struct view : expr<view>
+        {
+            double* p     = nullptr;
+            std::size_t n = 0;
+
+            view(double* p_, std::size_t n_)
+                : p(p_)
+                , n(n_)
+            {
+            }
+
+            view(const view&) = default;
+
+            double operator[](std::size_t k) const
+            {
+                return p[k];
+            }
+
+            double& operator[](std::size_t k)
+            {
+                return p[k];
+            }
+
+            std::size_t size() const
+            {
+                return n;
+            }
+
+            template <class E>
+            view& operator=(const expr<E>& e)
+            {
+                const E& x = e.self();
+                for (std::size_t k = 0; k < n; ++k)
+                {
+                    p[k] = x[k];
+                }
+                return *this;
+            }
+
+            view& operator=(const view& o)
+            {
+                for (std::size_t k = 0; k < n; ++k)
+                {
+                    p[k] = o.p[k];
+                }
+                return *this;
+            }
+
+            view& operator=(double v)
+            {
+                for (std::size_t k = 0; k < n; ++k)
+                {
+                    p[k] = v;
+                }
+                return *this;
+            }
+
+            template <class E>
+            view& operator+=(const expr<E>& e)
+            {
+                const E& x = e.self();
+                for (std::size_t k = 0; k < n; ++k)
+                {
+                    p[k] += x[k];
+                }
+                return *this;
+            }
+
+            template <class E>
+            view& operator-=(const expr<E>& e)
+            {
+                const E& x = e.self();
+                for (std::size_t k = 0; k < n; ++k)
+                {
+                    p[k] -= x[k];
+                }
+                return *this;
+            }
+        };
+
+#define SMR_ROWX_OP(SYM, NAME)                                                             \
+    template <class A, class B>                                                            \
+    auto operator SYM(const expr<A>& a, const expr<B>& b)                                  \
+    {                                                                                      \
+        return binary<A, B, NAME>(a.self(), b.self());                                     \
+    }                                                                                      \
+    template <class A, class S, class = std::enable_if_t<std::is_arithmetic_v<S>>>         \
+    auto operator SYM(const expr<A>& a, S b)                                               \
+    {                                                                                      \
+        return binary<A, scalar, NAME>(a.self(), scalar(static_cast<double>(b)));          \
+    }                                                                                      \
+    template <class B, class S, class = std::enable_if_t<std::is_arithmetic_v<S>>>         \
+    auto operator SYM(S a, const expr<B>& b)                                               \
+    {                                                                                      \
+        return binary<scalar, B, NAME>(scalar(static_cast<double>(a)), b.self());          \
+    }
+        SMR_ROWX_OP(+, add)
+        SMR_ROWX_OP(-, sub)
+        SMR_ROWX_OP(*, mul)
+        SMR_ROWX_OP(/, div)
+#undef SMR_ROWX_OP
+
+        template <class A>
+        auto operator-(const expr<A>& a)
+        {
+            return binary<scalar, A, sub>(scalar(0.0), a.self());
+        }
+    } // namespace rowx
+
     template <std::size_t dim_>
     struct Cell
     {
@@ -666,6 +880,22 @@ namespace samurai
             m_owner->h = h;
         }
 
+        // `samurai::MRMesh<Config> mesh(box, min_level, max_level);` -- the constructor the reference's README still shows
+        // (README.md:96-100); stencil width 1, no minimal ghost width, starts uniform at max_level
+        MRMesh(const Box<double, dim>& b, std::size_t min_level, std::size_t max_level)
+            : MRMesh(b, legacy_config(min_level, max_level))
+        {
+        }
+
+        static Config legacy_config(std::size_t min_level, std::size_t max_level)
+        {
+            Config cfg;
+            cfg.min_level(min_level).max_level(max_level).max_stencil_radius(1).disable_minimal_ghost_width();
+            cfg.parse_args();
+            cfg.start_level() = cfg.max_level();
+            return cfg;
+        }
+
         // Copies share the library mesh (the demos copy a mesh to iterate over it, scalar_burgers_2d.cpp:23);
         // `mesh = samurai::mra::make_mesh(box, config);` (advection_2d.cpp:107) rebinds this object, and the fields that
         // point at it follow.
@@ -755,6 +985,10 @@ namespace samurai
         Config m_cfg;
         smr_mesh_config m_c{};
     };
+
+    // README.md:90: `using Config = samurai::MRConfig<dim>;`
+    template <std::size_t dim_, std::size_t max_stencil_width_ = 1, std::size_t graduation_width_ = 1, std::size_t prediction_order_ = 1>
+    using MRConfig = mesh_config<dim_, static_cast<int>(prediction_order_)>;
 
     namespace mra
     {
@@ -901,6 +1135,19 @@ namespace samurai
         scaled_scheme_expr<Field> rhs;
     };
 
+    // general field expressions (field/field_expression.hpp:62-141), evaluated on the device: see namespace fx below
+    namespace fx
+    {
+        template <class E>
+        struct node
+        {
+            const E& self() const
+            {
+                return static_cast<const E&>(*this);
+            }
+        };
+    }
+
     template <class mesh_t_, class value_t = double>
     class ScalarField
     {
@@ -1025,6 +1272,37 @@ namespace samurai
             }
         }
 
+        // host access: u(level, i), u(level, i, j), u(level, i, j, k), u(level, i, index)  (field/access_base.hpp:69-103).
+        // The interval may be translated (`i - 1`), the row too (`j - 1`): the storage offset is looked up in the reference
+        // sub-mesh (ghosts included), an absent row throws like the reference's debug build does.
+        rowx::view operator()(std::size_t level, const Interval& i, int j = 0, int k = 0)
+        {
+            static_assert(on_device, "u(level, i, ...) needs a double field");
+            pull_host();
+            m_storage.host_dirty = true;
+            return rowx::view(m_storage.host.data() + row_offset(level, i, j, k), i.size());
+        }
+
+        rowx::view operator()(std::size_t level, const Interval& i, int j = 0, int k = 0) const
+        {
+            static_assert(on_device, "u(level, i, ...) needs a double field");
+            auto* self = const_cast<ScalarField*>(this);
+            self->pull_host();
+            return rowx::view(self->m_storage.host.data() + row_offset(level, i, j, k), i.size());
+        }
+
+        template <std::size_t N>
+        rowx::view operator()(std::size_t level, const Interval& i, const xt::xtensor_fixed<int, xt::xshape<N>>& index)
+        {
+            return (*this)(level, i, dim > 1 ? index[0] : 0, (dim > 2 && N > 1) ? index[N > 1 ? 1 : 0] : 0);
+        }
+
+        template <std::size_t N>
+        rowx::view operator()(std::size_t level, const Interval& i, const xt::xtensor_fixed<int, xt::xshape<N>>& index) const
+        {
+            return (*this)(level, i, dim > 1 ? index[0] : 0, (dim > 2 && N > 1) ? index[N > 1 ? 1 : 0] : 0);
+        }
+
         // device handle with pending host writes flushed and the boundary condition attached
         smr_field_t device() const
         {
@@ -1104,6 +1382,15 @@ namespace samurai
             return *this;
         }
 
+        // `unp1 = 1./3 * u + 2./3 * (u2 - dt * conv(u2))` and friends: any tree of +, -, scalar * over fields and scheme(u)
+        template <class E>
+        ScalarField& operator=(const fx::node<E>& e)
+        {
+            static_assert(on_device, "field expressions need a double field");
+            e.self().assign_to(*this);
+            return *this;
+        }
+
         std::vector<double> leaf_values() const
         {
             const_cast<ScalarField*>(this)->pull_host();
@@ -1111,6 +1398,20 @@ namespace samurai
         }
 
       private:
+
+        std::size_t row_offset(std::size_t level, const Interval& i, int j, int k) const
+        {
+            int64_t first = -1, last = -1;
+            if (smr_mesh_get_index(p_mesh->handle(), static_cast<int>(level), i.start, j, k, &first) != SMR_OK || first < 0
+                || smr_mesh_get_index(p_mesh->handle(), static_cast<int>(level), i.end - 1, j, k, &last) != SMR_OK
+                || last - first != static_cast<int64_t>(i.size()) - 1)
+            {
+                throw std::out_of_range("field '" + m_name + "': interval [" + std::to_string(i.start) + ", " + std::to_string(i.end) + ") of row ("
+                                        + std::to_string(j) + ", " + std::to_string(k) + ") at level " + std::to_string(level)
+                                        + " is not in the reference mesh");
+            }
+            return static_cast<std::size_t>(first);
+        }
 
         smr_field_t handle()
         {
@@ -1378,6 +1679,240 @@ namespace samurai
     auto operator-(const ScalarField<mesh_t, double>& v, const scaled_scheme_expr<ScalarField<mesh_t, double>>& rhs)
     {
         return scheme_step_expr<ScalarField<mesh_t, double>>{&v, rhs};
+    }
+
+    // ---- general field expressions (field/field_expression.hpp:62-141, field/field_base.hpp:230-242) -----------------------
+    // The reference evaluates `unp1 = 1./3 * u + 2./3 * (u2 - dt * conv(u2))` lazily, cell by cell over the leaves.  Here the
+    // tree is walked once per assignment and every `a * X + b * Y` node becomes one LinCombOp launch over the leaves
+    // (smr_field_lincomb: a * x + b * y, no FMA contraction), so each cell sees the same operations in the same order as the
+    // reference's expression template.  scheme(u) leaves are applied into temporaries first (explicit_FV_scheme.hpp), like
+    // the reference's `make_field_operator_function` does.  Temporaries come from a small per-mesh pool.
+    namespace fx
+    {
+        template <class Field>
+        struct pool
+        {
+            static std::vector<std::unique_ptr<Field>>& fields(typename Field::mesh_t* mesh)
+            {
+                static std::map<typename Field::mesh_t*, std::vector<std::unique_ptr<Field>>> m;
+                return m[mesh];
+            }
+
+            static int& used()
+            {
+                static int n = 0;
+                return n;
+            }
+
+            static Field& take(typename Field::mesh_t& mesh)
+            {
+                auto& v = fields(&mesh);
+                if (static_cast<int>(v.size()) <= used())
+                {
+                    v.push_back(std::make_unique<Field>("tmp" + std::to_string(v.size()), mesh));
+                }
+                Field& f = *v[static_cast<std::size_t>(used()++)];
+                f.resize();
+                return f;
+            }
+        };
+
+        template <class Field>
+        struct term // value = c * f
+        {
+            double c;
+            Field* f;
+        };
+
+        template <class Field>
+        struct leaf : node<leaf<Field>>
+        {
+            using field_t = Field;
+            Field* f;
+
+            term<Field> eval() const
+            {
+                return {1.0, f};
+            }
+
+            void assign_to(Field& out) const
+            {
+                if (&out != f)
+                {
+                    b200::check(smr_field_resize(out.device()));
+                    b200::check(smr_field_lincomb(out.device(), 1.0, f->device(), 0.0, f->device()));
+                    out.device_written();
+                }
+            }
+        };
+
+        template <class Field>
+        struct scheme_node : node<scheme_node<Field>> // scheme(u)
+        {
+            using field_t = Field;
+            FluxBasedScheme<Field> scheme;
+            Field* u;
+
+            term<Field> eval() const
+            {
+                Field& tmp = pool<Field>::take(u->mesh());
+                scheme.apply(tmp, *u);
+                return {1.0, &tmp};
+            }
+
+            void assign_to(Field& out) const
+            {
+                scheme.apply(out, *u);
+            }
+        };
+
+        template <class E>
+        struct scaled : node<scaled<E>>
+        {
+            using field_t = typename E::field_t;
+            double c;
+            E e;
+
+            term<field_t> eval() const
+            {
+                term<field_t> t = e.eval();
+                if (t.c != 1.0) // c * (t.c * f): materialise the inner product so the roundings stay where the expression has them
+                {
+                    field_t& tmp = pool<field_t>::take(t.f->mesh());
+                    b200::check(smr_field_lincomb(tmp.device(), t.c, t.f->device(), 0.0, t.f->device()));
+                    tmp.device_written();
+                    t = {1.0, &tmp};
+                }
+                return {c, t.f};
+            }
+
+            void assign_to(field_t& out) const
+            {
+                const int mark = pool<field_t>::used();
+                term<field_t> t = eval();
+                b200::check(smr_field_resize(out.device()));
+                b200::check(smr_field_lincomb(out.device(), t.c, t.f->device(), 0.0, t.f->device()));
+                out.device_written();
+                pool<field_t>::used() = mark;
+            }
+        };
+
+        template <class A, class B>
+        struct sum : node<sum<A, B>> // a + sign * b
+        {
+            using field_t = typename A::field_t;
+            A a;
+            B b;
+            double sign;
+
+            void into(field_t& out) const
+            {
+                term<field_t> ta = a.eval();
+                term<field_t> tb = b.eval();
+                b200::check(smr_field_resize(out.device()));
+                b200::check(smr_field_lincomb(out.device(), ta.c, ta.f->device(), sign * tb.c, tb.f->device()));
+                out.device_written();
+            }
+
+            term<field_t> eval() const
+            {
+                term<field_t> ta = a.eval();
+                term<field_t> tb = b.eval();
+                field_t& tmp     = pool<field_t>::take(ta.f->mesh());
+                b200::check(smr_field_lincomb(tmp.device(), ta.c, ta.f->device(), sign * tb.c, tb.f->device()));
+                tmp.device_written();
+                return {1.0, &tmp};
+            }
+
+            void assign_to(field_t& out) const
+            {
+                const int mark = pool<field_t>::used();
+                into(out);
+                pool<field_t>::used() = mark;
+            }
+        };
+
+        // operands: fields, scheme(u), dt * scheme(u), v - dt * scheme(u), and nodes
+        template <class mesh_t>
+        auto as_node(const ScalarField<mesh_t, double>& f)
+        {
+            return leaf<ScalarField<mesh_t, double>>{{}, const_cast<ScalarField<mesh_t, double>*>(&f)};
+        }
+
+        template <class Field>
+        auto as_node(const scheme_expr<Field>& e)
+        {
+            return scheme_node<Field>{{}, e.scheme, e.u};
+        }
+
+        template <class Field>
+        auto as_node(const scaled_scheme_expr<Field>& e)
+        {
+            return scaled<scheme_node<Field>>{{}, e.factor, as_node(e.e)};
+        }
+
+        template <class Field>
+        auto as_node(const scheme_step_expr<Field>& e)
+        {
+            return sum<leaf<Field>, scaled<scheme_node<Field>>>{{}, as_node(*e.v), as_node(e.rhs), -1.0};
+        }
+
+        template <class E>
+        const E& as_node(const node<E>& e)
+        {
+            return e.self();
+        }
+
+        template <class T, class = void>
+        struct is_operand : std::false_type
+        {
+        };
+
+        template <class mesh_t>
+        struct is_operand<ScalarField<mesh_t, double>> : std::true_type
+        {
+        };
+
+        template <class Field>
+        struct is_operand<scheme_expr<Field>> : std::true_type
+        {
+        };
+
+        template <class Field>
+        struct is_operand<scaled_scheme_expr<Field>> : std::true_type
+        {
+        };
+
+        template <class Field>
+        struct is_operand<scheme_step_expr<Field>> : std::true_type
+        {
+        };
+
+        template <class T>
+        struct is_operand<T, std::enable_if_t<std::is_base_of_v<node<T>, T>>> : std::true_type
+        {
+        };
+
+        template <class T>
+        using node_of = std::decay_t<decltype(as_node(std::declval<const T&>()))>;
+    } // namespace fx
+
+    template <class A, class B, class = std::enable_if_t<fx::is_operand<A>::value && fx::is_operand<B>::value>>
+    auto operator+(const A& a, const B& b)
+    {
+        return fx::sum<fx::node_of<A>, fx::node_of<B>>{{}, fx::as_node(a), fx::as_node(b), 1.0};
+    }
+
+    template <class A, class B, class = std::enable_if_t<fx::is_operand<A>::value && fx::is_operand<B>::value>, class = void>
+    auto operator-(const A& a, const B& b)
+    {
+        return fx::sum<fx::node_of<A>, fx::node_of<B>>{{}, fx::as_node(a), fx::as_node(b), -1.0};
+    }
+
+    template <class S, class B, class = std::enable_if_t<std::is_arithmetic_v<S> && fx::is_operand<B>::value>, class = void, class = void>
+    auto operator*(S c, const B& b)
+    {
+        return fx::scaled<fx::node_of<B>>{{}, static_cast<double>(c), fx::as_node(b)};
     }
 
     // ---- algorithm/update_ghost_mr.hpp:260-270 ---------------------------------------------------------------------------

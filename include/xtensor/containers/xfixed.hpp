@@ -5,6 +5,7 @@
 #include <cstddef>
 #include <initializer_list>
 #include <ostream>
+#include <type_traits>
 
 namespace xt
 {
@@ -105,6 +106,100 @@ namespace xt
 
         std::array<T, N> m_data;
     };
+
+    // element-wise arithmetic and comparisons, enough for expressions like
+    //   xt::all(xt::abs(cell.center() - 0.5) <= 0.5 * length)      (README.md:111-118, tests/test_periodic.cpp:36)
+#define XFIXED_BINARY(OP)                                                                                              \
+    template <class T, std::size_t N>                                                                                  \
+    auto operator OP(const xtensor_fixed<T, xshape<N>>& a, const xtensor_fixed<T, xshape<N>>& b)                       \
+    {                                                                                                                  \
+        xtensor_fixed<decltype(T{} OP T{}), xshape<N>> r;                                                              \
+        for (std::size_t i = 0; i < N; ++i)                                                                            \
+        {                                                                                                              \
+            r[i] = a[i] OP b[i];                                                                                       \
+        }                                                                                                              \
+        return r;                                                                                                      \
+    }                                                                                                                  \
+    template <class T, std::size_t N, class S, class = std::enable_if_t<std::is_arithmetic_v<S>>>                      \
+    auto operator OP(const xtensor_fixed<T, xshape<N>>& a, S b)                                                        \
+    {                                                                                                                  \
+        xtensor_fixed<decltype(T{} OP S{}), xshape<N>> r;                                                              \
+        for (std::size_t i = 0; i < N; ++i)                                                                            \
+        {                                                                                                              \
+            r[i] = a[i] OP b;                                                                                          \
+        }                                                                                                              \
+        return r;                                                                                                      \
+    }                                                                                                                  \
+    template <class T, std::size_t N, class S, class = std::enable_if_t<std::is_arithmetic_v<S>>>                      \
+    auto operator OP(S a, const xtensor_fixed<T, xshape<N>>& b)                                                        \
+    {                                                                                                                  \
+        xtensor_fixed<decltype(S{} OP T{}), xshape<N>> r;                                                              \
+        for (std::size_t i = 0; i < N; ++i)                                                                            \
+        {                                                                                                              \
+            r[i] = a OP b[i];                                                                                          \
+        }                                                                                                              \
+        return r;                                                                                                      \
+    }
+    XFIXED_BINARY(+)
+    XFIXED_BINARY(-)
+    XFIXED_BINARY(*)
+    XFIXED_BINARY(/)
+    XFIXED_BINARY(<=)
+    XFIXED_BINARY(<)
+    XFIXED_BINARY(>=)
+    XFIXED_BINARY(>)
+    XFIXED_BINARY(==)
+    XFIXED_BINARY(<<)
+    XFIXED_BINARY(>>)
+#undef XFIXED_BINARY
+
+    template <class T, std::size_t N>
+    auto abs(const xtensor_fixed<T, xshape<N>>& a)
+    {
+        xtensor_fixed<T, xshape<N>> r;
+        for (std::size_t i = 0; i < N; ++i)
+        {
+            r[i] = a[i] < T{} ? -a[i] : a[i];
+        }
+        return r;
+    }
+
+    template <class T, std::size_t N>
+    bool all(const xtensor_fixed<T, xshape<N>>& a)
+    {
+        for (std::size_t i = 0; i < N; ++i)
+        {
+            if (!a[i])
+            {
+                return false;
+            }
+        }
+        return true;
+    }
+
+    template <class T, std::size_t N>
+    bool any(const xtensor_fixed<T, xshape<N>>& a)
+    {
+        for (std::size_t i = 0; i < N; ++i)
+        {
+            if (a[i])
+            {
+                return true;
+            }
+        }
+        return false;
+    }
+
+    template <class T, std::size_t N>
+    T sum(const xtensor_fixed<T, xshape<N>>& a)
+    {
+        T s{};
+        for (std::size_t i = 0; i < N; ++i)
+        {
+            s += a[i];
+        }
+        return s;
+    }
 
     template <class T, std::size_t N>
     std::ostream& operator<<(std::ostream& os, const xtensor_fixed<T, xshape<N>>& v)

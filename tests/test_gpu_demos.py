@@ -93,3 +93,104 @@ def test_reference_advection_1d_demo_unchanged_matches_oracle(gpu, tmp_path):
     assert got.shape[0] == lv.size, f"{got.shape[0]} cells vs oracle {lv.size}"
     assert np.array_equal(got[:, 0].astype(np.int64), lv) and np.array_equal(got[:, 1].astype(np.int64), co[:, 0]), "mesh differs"
     assert np.max(np.abs(got[:, 2] - u[ix])) <= 1e-13  # columns: level, i, u, level
+
+
+def test_readme_example_user_lambda_matches_oracle(gpu):
+    """The reference's README example (README.md:84-155) assembled statement for statement in tests/cpp/readme_advection.cpp:
+    legacy constructor MRMesh<Config>(box, 2, 8), make_field<double, 1>, u[cell], MRadaptation(1e-4, 2), and the upwind scheme as
+    the USER lambda over u(level, i, j) row views (the drop-in's host path, field/access_base.hpp:69-103).  Compared with the
+    oracle driven through the same loop, the stencil evaluated in the lambda's operation order: mesh identical, values bit-equal."""
+    import sys
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import samurai_oracle as so
+    from parity_utils import init_square
+
+    exe = os.path.join(DEMOS, "readme-advection")
+    if not os.path.exists(exe):
+        pytest.skip("readme-advection not built")
+    steps = 50
+    r = subprocess.run([exe, str(steps)], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    lines = r.stdout.strip().splitlines()
+    k = next(i for i, ln in enumerate(lines) if ln.startswith("leaves "))
+    got = np.array([[float(x) for x in ln.split()] for ln in lines[k + 1:]])
+    cfg = so.MeshConfig(dim=2, min_level=2, max_level=8, pred_radius=1)
+    bc = so.Bc("dirichlet", 0.0)
+    mesh = so.Mesh.uniform(cfg)
+    u = init_square(mesh)
+    dt = 0.5 * cfg.cell_length(8)
+    for _ in range(steps):
+        mesh, u = so.adapt(mesh, u, bc, 1e-4, 2.0)
+        so.update_ghost_mr(mesh, u, bc)
+        unp1 = np.full(mesh.nref, np.nan)
+        for l in mesh.leaf_levels():
+            keys = mesh.cells[l]
+            ic = mesh.index(l, keys)
+            uc = u[ic]
+            uxm = u[mesh.index(l, so.translate(keys, [-1, 0]))]
+            uym = u[mesh.index(l, so.translate(keys, [0, -1]))]
+            dx = cfg.cell_length(l)
+            unp1[ic] = uc - dt / dx * (uc - uxm + uc - uym)
+        u = unp1
+    lv, co, ix = mesh.leaf_table()
+    assert got.shape[0] == lv.size, f"{got.shape[0]} leaves vs oracle {lv.size}"
+    assert np.array_equal(got[:, 0].astype(np.int64), lv) and np.array_equal(got[:, 1:3].astype(np.int64), co), "mesh differs"
+    assert np.array_equal(got[:, 3], u[ix]), f"max abs diff {np.max(np.abs(got[:, 3] - u[ix])):.3e}"
+
+
+def test_rk3_general_field_expressions_match_oracle(gpu):
+    """tests/cpp/rk3_expressions.cpp: SSP-RK3 stages written as general field expressions (`3./4 * u + 1./4 * (u1 - dt * diff(u1))`,
+    field/field_expression.hpp:62-141, burgers.cpp:262-269), evaluated on the device node by node.  The oracle evaluates the same
+    trees element-wise in numpy: mesh identical, leaf values bit-equal."""
+    import sys
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import samurai_oracle as so
+
+    exe = os.path.join(DEMOS, "rk3-expressions")
+    if not os.path.exists(exe):
+        pytest.skip("rk3-expressions not built")
+    steps = 10
+    r = subprocess.run([exe, str(steps)], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    lines = r.stdout.strip().splitlines()
+    k = next(i for i, ln in enumerate(lines) if ln.startswith("leaves "))
+    got = np.array([[float(x) for x in ln.split()] for ln in lines[k + 1:]])
+
+    K, cfl = 1.0, 0.5
+    cfg = so.MeshConfig(dim=2, min_level=3, max_level=6, pred_radius=1, origin=(-4.0, -4.0), scaling=8.0)
+    bc = so.Bc("neumann", 0.0)
+    mesh = so.Mesh.uniform(cfg)
+    u = np.zeros(mesh.nref)
+    L = cfg.max_level
+    u[mesh.index(L, mesh.cells[L])] = so.heat_exact(mesh.cell_centers(L, mesh.cells[L]), 1e-2, K)
+    dx = cfg.cell_length(L)
+    dt = cfl * (dx * dx) / (pow(2, 2) * K)
+    coeffs = so.diffusion_order2_coeffs([K, K])
+    mesh, u = so.adapt(mesh, u, bc, 1e-4, 1.0)
+
+    def S(v):
+        so.update_ghost_mr(mesh, v, bc)
+        return so.flux_linhom_apply(mesh, v, coeffs)
+
+    def leaves_expr(fn):
+        out = np.full(mesh.nref, np.nan)
+        for l in mesh.leaf_levels():
+            i = mesh.index(l, mesh.cells[l])
+            out[i] = fn(i)
+        return out
+
+    for _ in range(steps):
+        mesh, u = so.adapt(mesh, u, bc, 1e-4, 1.0)
+        r0 = S(u)
+        u1 = leaves_expr(lambda i: u[i] - dt * r0[i])
+        r1 = S(u1)
+        u2 = leaves_expr(lambda i: 3. / 4 * u[i] + 1. / 4 * (u1[i] - dt * r1[i]))
+        r2 = S(u2)
+        u = leaves_expr(lambda i: 1. / 3 * u[i] + 2. / 3 * (u2[i] - dt * r2[i]))
+    lv, co, ix = mesh.leaf_table()
+    assert got.shape[0] == lv.size, f"{got.shape[0]} leaves vs oracle {lv.size}"
+    assert np.array_equal(got[:, 0].astype(np.int64), lv) and np.array_equal(got[:, 1:3].astype(np.int64), co), "mesh differs"
+    assert np.array_equal(got[:, 3], u[ix]), f"max abs diff {np.max(np.abs(got[:, 3] - u[ix])):.3e}"
