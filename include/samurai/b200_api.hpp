@@ -1164,6 +1164,24 @@ namespace samurai
         {
         }
 
+        // component of a vector field: same object, storage owned by the caller
+        ScalarField(std::string name, mesh_t& mesh, FieldStorage* external)
+            : m_name(std::move(name))
+            , p_mesh(&mesh)
+            , p_ext(external)
+        {
+        }
+
+        FieldStorage& st()
+        {
+            return p_ext ? *p_ext : m_storage;
+        }
+
+        const FieldStorage& st() const
+        {
+            return p_ext ? *p_ext : m_storage;
+        }
+
         ScalarField(const ScalarField&)            = delete;
         ScalarField& operator=(const ScalarField&) = delete;
 
@@ -1180,9 +1198,9 @@ namespace samurai
 
         ~ScalarField()
         {
-            if (m_storage.handle)
+            if (st().handle)
             {
-                smr_field_destroy(m_storage.handle);
+                smr_field_destroy(st().handle);
             }
         }
 
@@ -1203,7 +1221,7 @@ namespace samurai
 
         FieldStorage& array()
         {
-            return m_storage;
+            return st();
         }
 
         std::size_t size() const
@@ -1217,7 +1235,7 @@ namespace samurai
             {
                 push_host();
                 b200::check(smr_field_resize(handle()));
-                m_storage.host_valid = false;
+                st().host_valid = false;
             }
             else
             {
@@ -1231,8 +1249,8 @@ namespace samurai
             {
                 b200::check(smr_field_resize(handle()));
                 b200::check(smr_field_fill(handle(), v));
-                m_storage.host_valid = false;
-                m_storage.host_dirty = false;
+                st().host_valid = false;
+                st().host_dirty = false;
             }
             else
             {
@@ -1246,8 +1264,8 @@ namespace samurai
             if constexpr (on_device)
             {
                 pull_host();
-                m_storage.host_dirty = true;
-                return m_storage.host[static_cast<std::size_t>(cell.index)];
+                st().host_dirty = true;
+                return st().host[static_cast<std::size_t>(cell.index)];
             }
             else
             {
@@ -1264,7 +1282,7 @@ namespace samurai
             if constexpr (on_device)
             {
                 const_cast<ScalarField*>(this)->pull_host();
-                return m_storage.host[static_cast<std::size_t>(cell.index)];
+                return st().host[static_cast<std::size_t>(cell.index)];
             }
             else
             {
@@ -1279,8 +1297,8 @@ namespace samurai
         {
             static_assert(on_device, "u(level, i, ...) needs a double field");
             pull_host();
-            m_storage.host_dirty = true;
-            return rowx::view(m_storage.host.data() + row_offset(level, i, j, k), i.size());
+            st().host_dirty = true;
+            return rowx::view(st().host.data() + row_offset(level, i, j, k), i.size());
         }
 
         rowx::view operator()(std::size_t level, const Interval& i, int j = 0, int k = 0) const
@@ -1288,7 +1306,7 @@ namespace samurai
             static_assert(on_device, "u(level, i, ...) needs a double field");
             auto* self = const_cast<ScalarField*>(this);
             self->pull_host();
-            return rowx::view(self->m_storage.host.data() + row_offset(level, i, j, k), i.size());
+            return rowx::view(self->st().host.data() + row_offset(level, i, j, k), i.size());
         }
 
         template <std::size_t N>
@@ -1317,8 +1335,8 @@ namespace samurai
 
         void device_written()
         {
-            m_storage.host_valid = false;
-            m_storage.host_dirty = false;
+            st().host_valid = false;
+            st().host_dirty = false;
         }
 
         void attach_bc(int type, double value)
@@ -1394,7 +1412,7 @@ namespace samurai
         std::vector<double> leaf_values() const
         {
             const_cast<ScalarField*>(this)->pull_host();
-            return m_storage.host;
+            return st().host;
         }
 
       private:
@@ -1415,50 +1433,284 @@ namespace samurai
 
         smr_field_t handle()
         {
-            if (!m_storage.handle)
+            if (!st().handle)
             {
                 if (!p_mesh->handle())
                 {
                     throw std::runtime_error("field '" + m_name + "' used before its mesh was built");
                 }
-                b200::check(smr_field_create(p_mesh->handle(), m_name.c_str(), &m_storage.handle));
+                b200::check(smr_field_create(p_mesh->handle(), m_name.c_str(), &st().handle));
             }
-            return m_storage.handle;
+            return st().handle;
         }
 
         void pull_host()
         {
             const std::size_t n = size();
-            if (!m_storage.host_valid || m_storage.host.size() != n)
+            if (!st().host_valid || st().host.size() != n)
             {
                 int64_t fs_ = 0;
                 b200::check(smr_field_resize(handle()));
                 b200::check(smr_field_size(handle(), &fs_));
-                m_storage.host.resize(n);
-                b200::check(smr_field_download(handle(), m_storage.host.data(), static_cast<int64_t>(n)));
-                m_storage.host_valid = true;
-                m_storage.host_dirty = false;
+                st().host.resize(n);
+                b200::check(smr_field_download(handle(), st().host.data(), static_cast<int64_t>(n)));
+                st().host_valid = true;
+                st().host_dirty = false;
             }
         }
 
         void push_host()
         {
-            if (m_storage.host_dirty)
+            if (st().host_dirty)
             {
-                b200::check(smr_field_upload(handle(), m_storage.host.data(), static_cast<int64_t>(m_storage.host.size())));
+                b200::check(smr_field_upload(handle(), st().host.data(), static_cast<int64_t>(st().host.size())));
                 b200::check(smr_synchronize());
-                m_storage.host_dirty = false;
-                m_storage.host_valid = true;
+                st().host_dirty = false;
+                st().host_valid = true;
             }
         }
 
         std::string m_name;
         mesh_t* p_mesh;
         FieldStorage m_storage;
+        FieldStorage* p_ext = nullptr; // component of a VectorField: the storage lives in the vector field (so that swapping its array() swaps every component)
         std::vector<value_t> m_plain; // non-double fields are host-only (e.g. the `level` field the demos save)
         int m_bc_type     = -1;
         double m_bc_value = 0;
     };
+
+    // ---- field/vector_field.hpp:234 ------------------------------------------------------------------------------------------
+    // A vector field is stored as n_comp scalar components (SoA: one device array per component, as north_star asks), each
+    // with the reference's storage numbering.  The host view the user code sees is the reference's: `u[cell]` is a small
+    // vector (u[cell][c], u[cell] = {..}), `u(c, level, i, j)` the row of one component.  All components are adapted together
+    // (one tag array, the criteria takes the max over the components: mr/operators.hpp:623-677, mr/criteria.hpp) and share the
+    // ghost update.
+    template <class mesh_t_, class value_t, std::size_t n_comp_>
+    class VectorField
+    {
+      public:
+
+        using mesh_t                        = mesh_t_;
+        using cell_t                        = typename mesh_t::cell_t;
+        using component_t                   = ScalarField<mesh_t, value_t>;
+        static constexpr std::size_t dim    = mesh_t::dim;
+        static constexpr std::size_t n_comp = n_comp_;
+
+        VectorField(std::string name, mesh_t& mesh)
+            : m_name(std::move(name))
+            , p_mesh(&mesh)
+        {
+            for (std::size_t c = 0; c < n_comp; ++c)
+            {
+                m_comp[c] = std::make_unique<component_t>(m_name + "_" + std::to_string(c), mesh, &m_storage.s[c]);
+            }
+        }
+
+        VectorField(const VectorField&)            = delete; // the components point into m_storage
+        VectorField& operator=(const VectorField&) = delete;
+
+        const std::string& name() const
+        {
+            return m_name;
+        }
+
+        mesh_t& mesh()
+        {
+            return *p_mesh;
+        }
+
+        const mesh_t& mesh() const
+        {
+            return *p_mesh;
+        }
+
+        component_t& component(std::size_t c)
+        {
+            return *m_comp[c];
+        }
+
+        const component_t& component(std::size_t c) const
+        {
+            return *m_comp[c];
+        }
+
+        void resize()
+        {
+            for (auto& f : m_comp)
+            {
+                f->resize();
+            }
+        }
+
+        void fill(value_t v)
+        {
+            for (auto& f : m_comp)
+            {
+                f->fill(v);
+            }
+        }
+
+        // what `u.array()` returns: std::swap(u.array(), unp1.array()) exchanges every component's device buffer and host mirror
+        struct Storage
+        {
+            std::array<FieldStorage, n_comp> s;
+        };
+
+        Storage& array()
+        {
+            return m_storage;
+        }
+
+        // u[cell]: proxy over the n_comp values of one cell
+        struct CellRef
+        {
+            VectorField* f;
+            const cell_t* cell;
+
+            value_t& operator[](std::size_t c)
+            {
+                return (*f->m_comp[c])[*cell];
+            }
+
+            value_t& operator()(std::size_t c)
+            {
+                return (*f->m_comp[c])[*cell];
+            }
+
+            CellRef& operator=(value_t v)
+            {
+                for (std::size_t c = 0; c < n_comp; ++c)
+                {
+                    (*f->m_comp[c])[*cell] = v;
+                }
+                return *this;
+            }
+
+            CellRef& operator=(const xt::xtensor_fixed<value_t, xt::xshape<n_comp>>& v)
+            {
+                for (std::size_t c = 0; c < n_comp; ++c)
+                {
+                    (*f->m_comp[c])[*cell] = v[c];
+                }
+                return *this;
+            }
+
+            CellRef& operator=(std::initializer_list<value_t> v)
+            {
+                std::size_t c = 0;
+                for (const value_t& x : v)
+                {
+                    if (c < n_comp)
+                    {
+                        (*f->m_comp[c++])[*cell] = x;
+                    }
+                }
+                return *this;
+            }
+
+            operator xt::xtensor_fixed<value_t, xt::xshape<n_comp>>() const
+            {
+                xt::xtensor_fixed<value_t, xt::xshape<n_comp>> r;
+                for (std::size_t c = 0; c < n_comp; ++c)
+                {
+                    r[c] = (*f->m_comp[c])[*cell];
+                }
+                return r;
+            }
+        };
+
+        CellRef operator[](const cell_t& cell)
+        {
+            return CellRef{this, &cell};
+        }
+
+        xt::xtensor_fixed<value_t, xt::xshape<n_comp>> operator[](const cell_t& cell) const
+        {
+            xt::xtensor_fixed<value_t, xt::xshape<n_comp>> r;
+            for (std::size_t c = 0; c < n_comp; ++c)
+            {
+                r[c] = (*m_comp[c])[cell];
+            }
+            return r;
+        }
+
+        // u(c, level, i, j...): one component's row (field/access_base.hpp:117-160)
+        template <class... Index>
+        auto operator()(std::size_t c, std::size_t level, const Interval& i, const Index&... index)
+        {
+            return (*m_comp[c])(level, i, index...);
+        }
+
+        template <class... Index>
+        auto operator()(std::size_t c, std::size_t level, const Interval& i, const Index&... index) const
+        {
+            return static_cast<const component_t&>(*m_comp[c])(level, i, index...);
+        }
+
+        void attach_bc(int type, const std::array<double, n_comp>& values)
+        {
+            for (std::size_t c = 0; c < n_comp; ++c)
+            {
+                m_comp[c]->attach_bc(type, values[c]);
+            }
+        }
+
+        // `unp1 = u - dt * upwind(a, u)`: every component is transported by the same velocity (stencil_field.hpp:83-173)
+        template <class A>
+        VectorField& operator=(const fv_step_expr<A, VectorField>& e)
+        {
+            for (std::size_t c = 0; c < n_comp; ++c)
+            {
+                const component_t& uc = e.u->component(c);
+                *m_comp[c] = fv_step_expr<A, component_t>{&uc, scaled_upwind_expr<A, component_t>{e.rhs.dt, upwind_expr<A, component_t>{e.rhs.op.a, &uc, e.rhs.op.burgers}}};
+            }
+            return *this;
+        }
+
+      private:
+
+        std::string m_name;
+        mesh_t* p_mesh;
+        Storage m_storage; // declared before the components: destroyed after them
+        std::array<std::unique_ptr<component_t>, n_comp> m_comp;
+    };
+
+    template <class value_t, std::size_t n_comp, class mesh_t>
+    auto make_vector_field(const std::string& name, mesh_t& mesh) // field/vector_field.hpp:234-300
+    {
+        return VectorField<mesh_t, value_t, n_comp>(name, mesh);
+    }
+
+    template <std::size_t n_comp, class mesh_t>
+    auto make_vector_field(const std::string& name, mesh_t& mesh)
+    {
+        return VectorField<mesh_t, double, n_comp>(name, mesh);
+    }
+
+    template <class mesh_t, class T, std::size_t n>
+    void swap(VectorField<mesh_t, T, n>& a, VectorField<mesh_t, T, n>& b)
+    {
+        std::swap(a.array(), b.array());
+    }
+
+    namespace b200
+    {
+        // every scalar component behind a field argument, in order
+        template <class mesh_t, class T, class F>
+        void for_each_component(ScalarField<mesh_t, T>& f, F&& fn)
+        {
+            fn(f);
+        }
+
+        template <class mesh_t, class T, std::size_t n, class F>
+        void for_each_component(VectorField<mesh_t, T, n>& f, F&& fn)
+        {
+            for (std::size_t c = 0; c < n; ++c)
+            {
+                fn(f.component(c));
+            }
+        }
+    }
 
     template <class value_t, class mesh_t>
     auto make_scalar_field(const std::string& name, mesh_t& mesh) // field/scalar_field.hpp:171-215
@@ -1534,7 +1786,26 @@ namespace samurai
     template <class BcType, class Field>
     auto make_bc(Field& u, double value)
     {
-        u.attach_bc(BcType::type, value);
+        if constexpr (requires { Field::n_comp; })
+        {
+            std::array<double, Field::n_comp> v;
+            v.fill(value);
+            u.attach_bc(BcType::type, v);
+        }
+        else
+        {
+            u.attach_bc(BcType::type, value);
+        }
+        return BcHandle<Field::dim>();
+    }
+
+    // make_bc<Dirichlet<1>>(u, v0, v1, ...): one constant per component of a vector field (bc/bc.hpp:751-815)
+    template <class BcType, class Field, class... Values>
+        requires(sizeof...(Values) >= 1 && requires { Field::n_comp; })
+    auto make_bc(Field& u, double v0, Values... vs)
+    {
+        static_assert(sizeof...(Values) + 1 == Field::n_comp, "one boundary value per component");
+        u.attach_bc(BcType::type, std::array<double, Field::n_comp>{v0, static_cast<double>(vs)...});
         return BcHandle<Field::dim>();
     }
 
@@ -1561,6 +1832,12 @@ namespace samurai
     auto operator-(const ScalarField<mesh_t, double>& u, const scaled_upwind_expr<A, ScalarField<mesh_t, double>>& rhs)
     {
         return fv_step_expr<A, ScalarField<mesh_t, double>>{&u, rhs};
+    }
+
+    template <class A, class mesh_t, std::size_t n>
+    auto operator-(const VectorField<mesh_t, double, n>& u, const scaled_upwind_expr<A, VectorField<mesh_t, double, n>>& rhs)
+    {
+        return fv_step_expr<A, VectorField<mesh_t, double, n>>{&u, rhs};
     }
 
     // ---- schemes/fv/operators/{convection_lin,convection_nonlin,diffusion}.hpp ------------------------------------------------
@@ -1916,11 +2193,19 @@ namespace samurai
     }
 
     // ---- algorithm/update_ghost_mr.hpp:260-270 ---------------------------------------------------------------------------
-    template <class Field>
-    void update_ghost_mr(Field& u)
+    template <class Field, class... Fields>
+    void update_ghost_mr(Field& u, Fields&... others)
     {
-        b200::check(smr_update_ghost_mr(u.device()));
-        u.device_written();
+        b200::for_each_component(u,
+                                 [](auto& f)
+                                 {
+                                     b200::check(smr_update_ghost_mr(f.device()));
+                                     f.device_written();
+                                 });
+        if constexpr (sizeof...(Fields) > 0)
+        {
+            update_ghost_mr(others...);
+        }
     }
 
     // ---- mr/config.hpp:10-68 -----------------------------------------------------------------------------------------------
@@ -2006,10 +2291,12 @@ namespace samurai
         template <std::size_t... I>
         void call(double eps, double reg, bool rel, std::index_sequence<I...>)
         {
-            smr_field_t h[] = {std::get<I>(m_fields)->device()...};
-            int it          = 0;
-            b200::check(smr_adapt_ex(h, static_cast<int>(sizeof...(Fields)), eps, reg, rel ? 1 : 0, &it));
-            (std::get<I>(m_fields)->device_written(), ...);
+            // scalar fields and the components of vector fields, in argument order: one detail array each, one tag array
+            std::vector<smr_field_t> h;
+            (b200::for_each_component(*std::get<I>(m_fields), [&](auto& f) { h.push_back(f.device()); }), ...);
+            int it = 0;
+            b200::check(smr_adapt_ex(h.data(), static_cast<int>(h.size()), eps, reg, rel ? 1 : 0, &it));
+            (b200::for_each_component(*std::get<I>(m_fields), [](auto& f) { f.device_written(); }), ...);
         }
 
         std::tuple<Fields*...> m_fields;

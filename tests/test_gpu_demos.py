@@ -194,3 +194,47 @@ def test_rk3_general_field_expressions_match_oracle(gpu):
     assert got.shape[0] == lv.size, f"{got.shape[0]} leaves vs oracle {lv.size}"
     assert np.array_equal(got[:, 0].astype(np.int64), lv) and np.array_equal(got[:, 1:3].astype(np.int64), co), "mesh differs"
     assert np.array_equal(got[:, 3], u[ix]), f"max abs diff {np.max(np.abs(got[:, 3] - u[ix])):.3e}"
+
+
+def test_cpp_vector_field_matches_oracle(gpu):
+    """tests/cpp/vector_advection.cpp: make_vector_field<double, 2> (field/vector_field.hpp:234) through the drop-in headers --
+    u[cell][c], one Dirichlet value per component, both components adapted together by make_MRAdapt(u) (one tag array, criteria over
+    all components: mr/operators.hpp:623-677), `unp1 = u - dt * upwind(a, u)`, std::swap(u.array(), unp1.array()).  Against the
+    oracle's adapt_fields + per-component upwind: mesh identical, both components bit-equal."""
+    import sys
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import samurai_oracle as so
+
+    exe = os.path.join(DEMOS, "vector-advection")
+    if not os.path.exists(exe):
+        pytest.skip("vector-advection not built")
+    steps = 10
+    r = subprocess.run([exe, str(steps)], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    lines = r.stdout.strip().splitlines()
+    k = next(i for i, ln in enumerate(lines) if ln.startswith("leaves "))
+    got = np.array([[float(x) for x in ln.split()] for ln in lines[k + 1:]])
+
+    cfg = so.MeshConfig(dim=2, min_level=2, max_level=7, pred_radius=1)
+    bcs = [so.Bc("dirichlet", 0.0), so.Bc("dirichlet", 0.0)]
+    mesh = so.Mesh.uniform(cfg)
+    L = cfg.max_level
+    c = mesh.cell_centers(L, mesh.cells[L])
+    ix = mesh.index(L, mesh.cells[L])
+    u0, u1 = np.zeros(mesh.nref), np.zeros(mesh.nref)
+    u0[ix] = np.where((c[:, 0] - 0.3) * (c[:, 0] - 0.3) + (c[:, 1] - 0.3) * (c[:, 1] - 0.3) <= 0.2 * 0.2, 1.0, 0.0)
+    u1[ix] = np.where((c[:, 0] - 0.6) * (c[:, 0] - 0.6) + (c[:, 1] - 0.5) * (c[:, 1] - 0.5) <= 0.15 * 0.15, 2.0, 0.0)
+    fields = [u0, u1]
+    dt = 0.5 * cfg.cell_length(L)
+    mesh, fields = so.adapt_fields(mesh, fields, bcs, 2e-4, 1.0)
+    for _ in range(steps):
+        mesh, fields = so.adapt_fields(mesh, fields, bcs, 2e-4, 1.0)
+        for f, bc in zip(fields, bcs):
+            so.update_ghost_mr(mesh, f, bc)
+        fields = [so.fv_step(mesh, f, [1.0, 1.0], dt) for f in fields]
+    lv, co, ix = mesh.leaf_table()
+    assert got.shape[0] == lv.size, f"{got.shape[0]} leaves vs oracle {lv.size}"
+    assert np.array_equal(got[:, 0].astype(np.int64), lv) and np.array_equal(got[:, 1:3].astype(np.int64), co), "mesh differs"
+    for comp in range(2):
+        assert np.array_equal(got[:, 3 + comp], fields[comp][ix]), f"component {comp}: max abs diff {np.max(np.abs(got[:, 3 + comp] - fields[comp][ix])):.3e}"
