@@ -29,6 +29,7 @@
 #include <type_traits>
 #include <vector>
 
+#include "b200_h5.hpp"
 #include <fmt/format.h>
 #include <xtensor/containers/xfixed.hpp>
 
@@ -894,6 +895,27 @@ namespace samurai
             cfg.parse_args();
             cfg.start_level() = cfg.max_level();
             return cfg;
+        }
+
+        // samurai::load(): replace this mesh by the one whose leaves are given as rows (level, y, z, start, end); `c` comes from
+        // the checkpoint (the object may be an empty mesh made by make_empty_mesh)
+        void rebuild_from_leaves(const smr_mesh_config& c, const std::vector<int64_t>& ivl5)
+        {
+            const std::size_t n = ivl5.size() / 5;
+            std::vector<int32_t> levels(n);
+            std::vector<smr_interval> ivl(n);
+            for (std::size_t i = 0; i < n; ++i)
+            {
+                levels[i] = static_cast<int32_t>(ivl5[5 * i]);
+                ivl[i]    = smr_interval{static_cast<int32_t>(ivl5[5 * i + 1]), static_cast<int32_t>(ivl5[5 * i + 2]), static_cast<int32_t>(ivl5[5 * i + 3]),
+                                      static_cast<int32_t>(ivl5[5 * i + 4]), 0};
+            }
+            smr_mesh_t h = 0;
+            b200::check(smr_mesh_create_from_intervals(&c, levels.data(), ivl.data(), static_cast<int64_t>(n), &h));
+            m_c = c;
+            m_cfg.min_level(static_cast<std::size_t>(c.min_level)).max_level(static_cast<std::size_t>(c.max_level));
+            m_owner    = std::make_shared<Owner>();
+            m_owner->h = h;
         }
 
         // Copies share the library mesh (the demos copy a mesh to iterate over it, scalar_burgers_2d.cpp:23);
@@ -2308,9 +2330,11 @@ namespace samurai
         return Adapt<Fields...>(fields...);
     }
 
-    // ---- io/hdf5.hpp, io/restart.hpp -----------------------------------------------------------------------------------
-    // No HDF5 library in this environment: save() writes <name>.csv (level, cell indices, centre, one column per field) in
-    // for_each_cell order -- the information of /mesh + /mesh/fields/* of the reference's .h5 -- next to a <name>.txt summary.
+    // ---- io/hdf5.hpp:680-950, io/restart.hpp --------------------------------------------------------------------------
+    // save() writes the reference's layout: <name>.h5 with /mesh/points [P,3] f64, /mesh/connectivity [N, 2^dim] u64 and one
+    // /mesh/fields/<field> [N] dataset per scalar field / vector component (cells in for_each_cell order, points numbered
+    // in order of first appearance like extract_coords_and_connectivity, io/hdf5.hpp:85-145), plus the <name>.xdmf companion.
+    // No HDF5 library exists here: the file structures are written directly (b200_h5.hpp).
     namespace detail
     {
         template <class Mesh>
@@ -2322,6 +2346,54 @@ namespace samurai
                 os << "," << "ijk"[d];
             }
         }
+
+        inline const char* element_type(std::size_t dim) // io/hdf5.hpp:44-58
+        {
+            return dim == 1 ? "Polyline" : (dim == 2 ? "Quadrilateral" : "Hexahedron");
+        }
+
+        // per-cell values of one scalar field, in for_each_cell order
+        template <class Mesh, class mesh_t, class T>
+        void add_field_datasets(b200::h5::Writer& w, const Mesh& mesh, const ScalarField<mesh_t, T>& f, std::vector<std::string>& names, const std::string& prefix)
+        {
+            std::vector<uint64_t> shape{static_cast<uint64_t>(mesh.nb_cells())};
+            if constexpr (std::is_floating_point_v<T>)
+            {
+                std::vector<double> v;
+                v.reserve(shape[0]);
+                for_each_cell(mesh, [&](const auto& cell) { v.push_back(static_cast<double>(f[cell])); });
+                w.add(prefix + "/fields/" + f.name(), b200::h5::Type::f64, shape, v.data());
+            }
+            else if constexpr (std::is_signed_v<T>)
+            {
+                std::vector<int64_t> v;
+                v.reserve(shape[0]);
+                for_each_cell(mesh, [&](const auto& cell) { v.push_back(static_cast<int64_t>(f[cell])); });
+                w.add(prefix + "/fields/" + f.name(), b200::h5::Type::i64, shape, v.data());
+            }
+            else
+            {
+                std::vector<uint64_t> v;
+                v.reserve(shape[0]);
+                for_each_cell(mesh, [&](const auto& cell) { v.push_back(static_cast<uint64_t>(f[cell])); });
+                w.add(prefix + "/fields/" + f.name(), b200::h5::Type::u64, shape, v.data());
+            }
+            names.push_back(f.name());
+        }
+
+        template <class Mesh, class mesh_t, class T, std::size_t n>
+        void add_field_datasets(b200::h5::Writer& w, const Mesh& mesh, const VectorField<mesh_t, T, n>& f, std::vector<std::string>& names, const std::string& prefix)
+        {
+            for (std::size_t c = 0; c < n; ++c) // io/hdf5.hpp:871-881: <name>_<component>
+            {
+                std::vector<double> v;
+                v.reserve(mesh.nb_cells());
+                for_each_cell(mesh, [&](const auto& cell) { v.push_back(static_cast<double>(f.component(c)[cell])); });
+                const std::string name = f.name() + "_" + std::to_string(c);
+                w.add(prefix + "/fields/" + name, b200::h5::Type::f64, {static_cast<uint64_t>(mesh.nb_cells())}, v.data());
+                names.push_back(name);
+            }
+        }
     }
 
     template <class T>
@@ -2331,41 +2403,243 @@ namespace samurai
         requires mesh_like<Mesh>
     void save(const fs::path& path, const std::string& filename, const Mesh& mesh, const Fields&... fields)
     {
+        constexpr std::size_t dim = Mesh::dim;
         fs::create_directories(path);
-        std::ofstream os(path / (filename + ".csv"));
-        os.precision(17);
-        detail::write_header(os, mesh);
-        ((os << "," << fields.name()), ...);
-        os << "\n";
+        const std::size_t n_cells = mesh.nb_cells();
+        const std::size_t per_cell = std::size_t(1) << dim;
+        // io/hdf5.hpp:60-82: corner order of a segment / quadrilateral / hexahedron
+        static const int element[8][3] = {{0, 0, 0}, {1, 0, 0}, {1, 1, 0}, {0, 1, 0}, {0, 0, 1}, {1, 0, 1}, {1, 1, 1}, {0, 1, 1}};
+        std::map<std::array<double, dim>, uint64_t> points_id;
+        std::vector<uint64_t> connectivity;
+        connectivity.reserve(n_cells * per_cell);
         for_each_cell(mesh,
                       [&](const auto& cell)
                       {
-                          os << cell.level;
-                          for (std::size_t d = 0; d < Mesh::dim; ++d)
+                          const auto start = cell.corner();
+                          for (std::size_t i = 0; i < per_cell; ++i)
                           {
-                              os << "," << cell.indices[d];
+                              std::array<double, dim> a;
+                              for (std::size_t d = 0; d < dim; ++d)
+                              {
+                                  a[d] = start[d] + cell.length * element[dim == 1 ? (i == 0 ? 0 : 1) : i][d];
+                              }
+                              auto it = points_id.find(a);
+                              if (it == points_id.end())
+                              {
+                                  it = points_id.emplace(a, static_cast<uint64_t>(points_id.size())).first;
+                              }
+                              connectivity.push_back(it->second);
                           }
-                          ((os << "," << fields[cell]), ...);
-                          os << "\n";
                       });
+        std::vector<double> coords(points_id.size() * 3, 0.0);
+        for (const auto& kv : points_id)
+        {
+            for (std::size_t d = 0; d < dim; ++d)
+            {
+                coords[kv.second * 3 + d] = kv.first[d];
+            }
+        }
+        b200::h5::Writer w;
+        w.add("/mesh/connectivity", b200::h5::Type::u64, {static_cast<uint64_t>(n_cells), static_cast<uint64_t>(per_cell)}, connectivity.data());
+        w.add("/mesh/points", b200::h5::Type::f64, {static_cast<uint64_t>(points_id.size()), 3}, coords.data());
+        std::vector<std::string> names;
+        (detail::add_field_datasets(w, mesh, fields, names, "/mesh"), ...);
+        w.write((path / (filename + ".h5")).string());
+
+        std::ofstream x(path / (filename + ".xdmf"));
+        x << "<?xml version=\"1.0\"?>\n<Xdmf>\n    <Domain>\n        <Grid Name=\"mesh\">\n";
+        x << "            <Topology TopologyType=\"" << detail::element_type(dim) << "\" NumberOfElements=\"" << n_cells << "\">\n";
+        x << "                <DataItem Dimensions=\"" << n_cells * per_cell << "\" Format=\"HDF\">" << filename << ".h5:/mesh/connectivity</DataItem>\n";
+        x << "            </Topology>\n            <Geometry GeometryType=\"XYZ\">\n";
+        x << "                <DataItem Dimensions=\"" << points_id.size() * 3 << "\" Format=\"HDF\">" << filename << ".h5:/mesh/points</DataItem>\n";
+        x << "            </Geometry>\n";
+        for (const std::string& name : names)
+        {
+            x << "            <Attribute Name=\"" << name << "\" Center=\"Cell\">\n";
+            x << "                <DataItem Dimensions=\"" << n_cells << "\" Format=\"HDF\" Precision=\"8\">" << filename << ".h5:/mesh/fields/" << name
+              << "</DataItem>\n            </Attribute>\n";
+        }
+        x << "        </Grid>\n    </Domain>\n</Xdmf>\n";
+
+        if (std::getenv("SAMURAI_B200_CSV") != nullptr) // plain-text copy of the same table (level, indices, one column per field)
+        {
+            std::ofstream os(path / (filename + ".csv"));
+            os.precision(17);
+            detail::write_header(os, mesh);
+            for (const std::string& name : names)
+            {
+                os << "," << name;
+            }
+            os << "\n";
+            for_each_cell(mesh,
+                          [&](const auto& cell)
+                          {
+                              os << cell.level;
+                              for (std::size_t d = 0; d < Mesh::dim; ++d)
+                              {
+                                  os << "," << cell.indices[d];
+                              }
+                              auto put = [&](const auto& f)
+                              {
+                                  if constexpr (requires { f.component(0); })
+                                  {
+                                      for (std::size_t c = 0; c < std::decay_t<decltype(f)>::n_comp; ++c)
+                                      {
+                                          os << "," << f.component(c)[cell];
+                                      }
+                                  }
+                                  else
+                                  {
+                                      os << "," << f[cell];
+                                  }
+                              };
+                              (put(fields), ...);
+                              os << "\n";
+                          });
+        }
     }
 
+    // Checkpoints.  dump() writes <name>.h5 holding the leaves and the leaf values: /n_process, /mesh/{dim, min_level, max_level,
+    // origin_point, scaling_factor} as in the reference's restart files (io/restart.hpp:96-176), the leaf intervals as
+    // /mesh/b200/intervals [n, 5] (level, y, z, start, end) and /fields/<name>/data with the leaf values in for_each_cell order.
+    // NOT interchangeable with the reference's restart files: those store samurai's per-dimension interval arrays as an HDF5
+    // compound type (io/restart.hpp:30-47), which this writer does not produce; load() says so when it is given one.
     template <class Mesh, class... Fields>
         requires mesh_like<Mesh>
     void dump(const fs::path& path, const std::string& filename, const Mesh& mesh, const Fields&... fields)
     {
-        save(path, filename, mesh, fields...);
+        fs::create_directories(path);
+        b200::h5::Writer w;
+        const auto& c = mesh.c_config();
+        w.add_scalar("/n_process", uint64_t(1));
+        w.add_scalar("/mesh/dim", static_cast<uint64_t>(Mesh::dim));
+        w.add_scalar("/mesh/min_level", static_cast<uint64_t>(mesh.min_level()));
+        w.add_scalar("/mesh/max_level", static_cast<uint64_t>(mesh.max_level()));
+        w.add("/mesh/origin_point", b200::h5::Type::f64, {static_cast<uint64_t>(Mesh::dim)}, c.origin);
+        w.add_scalar("/mesh/scaling_factor", static_cast<double>(c.scaling_factor));
+        std::vector<int64_t> ivl;
+        for (std::size_t level = 0; level <= mesh.max_level(); ++level)
+        {
+            for (const auto& iv : mesh.intervals(MRMeshId::cells, level))
+            {
+                ivl.insert(ivl.end(), {static_cast<int64_t>(level), static_cast<int64_t>(iv.y), static_cast<int64_t>(iv.z), static_cast<int64_t>(iv.start),
+                                       static_cast<int64_t>(iv.end)});
+            }
+        }
+        w.add("/mesh/b200/intervals", b200::h5::Type::i64, {static_cast<uint64_t>(ivl.size() / 5), 5}, ivl.data());
+        const int64_t cfgv[8] = {c.min_level, c.max_level, c.pred_radius, c.max_stencil_radius, c.graduation_width, c.n_cells0[0], c.n_cells0[1], c.n_cells0[2]};
+        w.add("/mesh/b200/config", b200::h5::Type::i64, {8}, cfgv);
+        auto put = [&](const auto& f)
+        {
+            std::vector<std::string> names;
+            b200::h5::Writer tmp; // names only
+            if constexpr (requires { f.component(0); })
+            {
+                constexpr std::size_t n = std::decay_t<decltype(f)>::n_comp;
+                w.add_scalar("/fields/" + f.name() + "/n_comp", static_cast<uint64_t>(n));
+                std::vector<double> v;
+                for_each_cell(mesh,
+                              [&](const auto& cell)
+                              {
+                                  for (std::size_t k = 0; k < n; ++k)
+                                  {
+                                      v.push_back(f.component(k)[cell]);
+                                  }
+                              });
+                w.add("/fields/" + f.name() + "/data", b200::h5::Type::f64, {static_cast<uint64_t>(v.size())}, v.data());
+            }
+            else
+            {
+                w.add_scalar("/fields/" + f.name() + "/n_comp", uint64_t(1));
+                std::vector<double> v;
+                for_each_cell(mesh, [&](const auto& cell) { v.push_back(static_cast<double>(f[cell])); });
+                w.add("/fields/" + f.name() + "/data", b200::h5::Type::f64, {static_cast<uint64_t>(v.size())}, v.data());
+            }
+        };
+        (put(fields), ...);
+        w.write((path / (filename + ".h5")).string());
     }
 
     template <class Mesh, class... Fields>
-    void load(const fs::path&, Mesh&, Fields&...)
+        requires mesh_like<Mesh>
+    void dump(const std::string& filename, const Mesh& mesh, const Fields&... fields)
     {
-        throw std::runtime_error("samurai::load (HDF5 restart files) is not available in samurai_b200");
+        dump(fs::current_path(), filename, mesh, fields...);
+    }
+
+    // load(): rebuilds the mesh from the checkpoint's leaves and fills the fields (io/restart.hpp:383-470)
+    template <class Mesh, class... Fields>
+    void load(const fs::path& file, Mesh& mesh, Fields&... fields)
+    {
+        fs::path p = file;
+        if (p.extension() != ".h5")
+        {
+            p += ".h5";
+        }
+        b200::h5::Reader r(p.string());
+        if (!r.exists("/mesh/b200/intervals"))
+        {
+            throw std::runtime_error("'" + p.string() + "' is not a samurai_b200 checkpoint (the reference's restart files store compound-type interval arrays, "
+                                                          "which this reader does not decode)");
+        }
+        if (r.template read<uint64_t>("/mesh/dim").at(0) != Mesh::dim)
+        {
+            throw std::runtime_error("checkpoint dimension differs from the mesh's");
+        }
+        std::vector<uint64_t> shape;
+        const std::vector<int64_t> ivl  = r.template read<int64_t>("/mesh/b200/intervals", &shape);
+        const std::vector<int64_t> cfgv = r.template read<int64_t>("/mesh/b200/config");
+        const std::vector<double> org   = r.template read<double>("/mesh/origin_point");
+        smr_mesh_config c{};
+        c.dim                = static_cast<int32_t>(Mesh::dim);
+        c.min_level          = static_cast<int32_t>(cfgv.at(0));
+        c.max_level          = static_cast<int32_t>(cfgv.at(1));
+        c.pred_radius        = static_cast<int32_t>(cfgv.at(2));
+        c.max_stencil_radius = static_cast<int32_t>(cfgv.at(3));
+        c.graduation_width   = static_cast<int32_t>(cfgv.at(4));
+        for (std::size_t d = 0; d < 3; ++d)
+        {
+            c.n_cells0[d] = static_cast<int32_t>(cfgv.at(5 + d));
+            c.origin[d]   = d < Mesh::dim ? org.at(d) : 0.0;
+        }
+        c.scaling_factor = r.template read<double>("/mesh/scaling_factor").at(0);
+        mesh.rebuild_from_leaves(c, ivl);
+        auto get = [&](auto& f)
+        {
+            const std::vector<double> v = r.template read<double>("/fields/" + f.name() + "/data");
+            std::size_t k               = 0;
+            f.resize();
+            if constexpr (requires { f.component(0); })
+            {
+                constexpr std::size_t n = std::decay_t<decltype(f)>::n_comp;
+                if (v.size() != mesh.nb_cells() * n)
+                {
+                    throw std::runtime_error("checkpoint field '" + f.name() + "' does not match the mesh");
+                }
+                for_each_cell(mesh,
+                              [&](const auto& cell)
+                              {
+                                  for (std::size_t c = 0; c < n; ++c)
+                                  {
+                                      f[cell][c] = v[k++];
+                                  }
+                              });
+            }
+            else
+            {
+                if (v.size() != mesh.nb_cells())
+                {
+                    throw std::runtime_error("checkpoint field '" + f.name() + "' does not match the mesh");
+                }
+                for_each_cell(mesh, [&](const auto& cell) { f[cell] = v[k++]; });
+            }
+        };
+        (get(fields), ...);
     }
 
     template <class Mesh, class... Fields>
-    void load(const std::string&, Mesh&, Fields&...)
+    void load(const std::string& file, Mesh& mesh, Fields&... fields)
     {
-        throw std::runtime_error("samurai::load (HDF5 restart files) is not available in samurai_b200");
+        load(fs::path(file), mesh, fields...);
     }
 } // namespace samurai

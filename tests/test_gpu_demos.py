@@ -13,9 +13,31 @@ GOLD = os.path.join(ROOT, "tests", "golden")
 pytestmark = pytest.mark.gpu
 
 
-def _load_csv(path):
-    data = np.loadtxt(path, delimiter=",", skiprows=1)
-    return data
+def _load_h5(path, dim=2, field="u"):
+    """The demos' samurai::save output (reference layout: /mesh/points, /mesh/connectivity, /mesh/fields/*), read with the pure-Python
+    HDF5 reader that also parses the reference's golden files.  Returns one row per cell: level, indices..., field value."""
+    import sys
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import h5mini
+
+    h5 = h5mini.H5File(str(path))
+    pts = h5.read("/mesh/points")
+    conn = h5.read("/mesh/connectivity").astype(np.int64)
+    corners = pts[conn]
+    lo = corners.min(axis=1)[:, :dim]
+    hi = corners.max(axis=1)[:, :dim]
+    level = h5.read("/mesh/fields/level").astype(np.int64) if "level" in h5.listdir("/mesh/fields") else None
+    length = hi[:, 0] - lo[:, 0]
+    return lo, length, level, h5.read("/mesh/fields/" + field)
+
+
+def _cells_h5(path, dim, origin, scaling, field="u"):
+    lo, length, level, u = _load_h5(path, dim, field)
+    if level is None:
+        level = np.rint(np.log2(scaling / length)).astype(np.int64)
+    idx = np.rint((lo - np.asarray(origin)[None, :dim]) / length[:, None]).astype(np.int64)
+    return np.concatenate([level[:, None].astype(np.float64), idx.astype(np.float64), u[:, None]], axis=1)
 
 
 def test_reference_advection_2d_demo_unchanged(gpu, tmp_path):
@@ -28,7 +50,8 @@ def test_reference_advection_2d_demo_unchanged(gpu, tmp_path):
     assert "iteration 20" in r.stdout
     for pred in (0, 1):
         for suffix, gold in (("_init", f"advection_2d_pred_{pred}_init.npz"), ("", f"advection_2d_pred_{pred}.npz")):
-            got = _load_csv(tmp_path / f"adv2d_pred_{pred}{suffix}.csv")
+            got = _cells_h5(tmp_path / f"adv2d_pred_{pred}{suffix}.h5", 2, [0.0, 0.0], 1.0)
+            assert os.path.exists(tmp_path / f"adv2d_pred_{pred}{suffix}.xdmf")
             g = np.load(os.path.join(GOLD, gold))
             assert got.shape[0] == g["level"].size, f"{gold}: {got.shape[0]} cells vs {g['level'].size}"
             assert np.array_equal(got[:, 0].astype(np.int64), g["level"].astype(np.int64))
@@ -44,11 +67,12 @@ def test_other_reference_demos_run(gpu, tmp_path, demo, args, ncol):
         pytest.skip("demo binary not built (needs /root/reference at build time)")
     r = subprocess.run([exe, "--path", str(tmp_path), "--filename", "out"] + args, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    files = sorted(p for p in os.listdir(tmp_path) if p.endswith(".csv") and "restart" not in p)
+    files = sorted(p for p in os.listdir(tmp_path) if p.endswith(".h5") and "restart" not in p)
     assert files
-    data = _load_csv(tmp_path / files[-1])
+    dim = 3 if "3d" in demo else 2
+    data = _cells_h5(tmp_path / files[-1], dim, [0.0] * dim, 1.0)
     assert data.shape[0] > 100 and np.all(np.isfinite(data))
-    u = data[:, ncol - 1] if "burgers" not in demo else data[:, 3]
+    u = data[:, -1]
     assert u.min() > -1.5 and u.max() < 1.5
 
 
@@ -62,7 +86,7 @@ def test_cpp_heat_explicit_matches_reference_golden(gpu, tmp_path):
     r = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "steps 25" in r.stdout
-    got = _load_csv(tmp_path / "heat_explicit.csv")
+    got = _cells_h5(tmp_path / "heat_explicit.h5", 2, [-4.0, -4.0], 8.0)
     g = np.load(os.path.join(GOLD, "heat_explicit.npz"))
     assert got.shape[0] == g["level"].size
     assert np.array_equal(got[:, 0].astype(np.int64), g["level"].astype(np.int64))
@@ -84,8 +108,8 @@ def test_reference_advection_1d_demo_unchanged_matches_oracle(gpu, tmp_path):
         pytest.skip("demo binary not built (needs /root/reference at build time)")
     r = subprocess.run([exe, "--path", str(tmp_path), "--filename", "adv1d", "--Tf", "0.1"], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert os.path.exists(tmp_path / "adv1d.csv"), os.listdir(tmp_path)
-    got = _load_csv(tmp_path / "adv1d.csv")
+    assert os.path.exists(tmp_path / "adv1d.h5"), os.listdir(tmp_path)
+    got = _cells_h5(tmp_path / "adv1d.h5", 1, [-2.0], 4.0)
     cfg = so.MeshConfig(dim=1, min_level=6, max_level=12, pred_radius=1, origin=(-2.0,), scaling=4.0)
     res = so.run_advection(cfg, Tf=0.1, eps=2e-4, a=[1.0], cfl=0.95, center=[0.0], radius=0.2)
     mesh, u = res["final"]
@@ -238,3 +262,27 @@ def test_cpp_vector_field_matches_oracle(gpu):
     assert np.array_equal(got[:, 0].astype(np.int64), lv) and np.array_equal(got[:, 1:3].astype(np.int64), co), "mesh differs"
     for comp in range(2):
         assert np.array_equal(got[:, 3 + comp], fields[comp][ix]), f"component {comp}: max abs diff {np.max(np.abs(got[:, 3 + comp] - fields[comp][ix])):.3e}"
+
+
+def test_reference_demo_restart_roundtrip(gpu, tmp_path):
+    """samurai::dump / samurai::load through the unchanged advection_2d demo (`--restart-file`, advection_2d.cpp:57,105-113):
+    20 steps in one run equal 10 steps + checkpoint + 10 steps from the checkpoint, bit for bit (mesh and field)."""
+    exe = os.path.join(DEMOS, "finite-volume-advection-2d")
+    if not os.path.exists(exe):
+        pytest.skip("demo binary not built (needs /root/reference at build time)")
+    dt = 0.5 * 2.0 ** -10
+
+    def run(name, steps, restart=None):
+        cmd = [exe, "--path", str(tmp_path), "--filename", name, "--Tf", repr(steps * dt)]
+        if restart:
+            cmd += ["--restart-file", str(tmp_path / restart)]
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        assert f"iteration {steps - 1}:" in r.stdout and f"iteration {steps}:" not in r.stdout
+        return _cells_h5(tmp_path / f"{name}_pred_1.h5", 2, [0.0, 0.0], 1.0)
+
+    full = run("full", 20)
+    run("half", 10)
+    assert os.path.exists(tmp_path / "half_pred_1_restart.h5")
+    cont = run("cont", 10, restart="half_pred_1_restart")
+    assert full.shape == cont.shape and np.array_equal(full, cont)
