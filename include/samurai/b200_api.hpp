@@ -830,14 +830,11 @@ namespace samurai
         MRMesh(const Box<double, dim>& b, const Config& cfg)
             : m_cfg(cfg)
         {
+            smr_mesh_config c{};
             for (std::size_t d = 0; d < dim; ++d)
             {
-                if (cfg.periodic(d))
-                {
-                    throw std::invalid_argument("periodic meshes are not implemented on the device path (update_ghost_periodic, DESIGN.md section 7)");
-                }
+                c.periodic[d] = cfg.periodic(d) ? 1 : 0;
             }
-            smr_mesh_config c{};
             c.dim                = static_cast<int32_t>(dim);
             c.min_level          = static_cast<int32_t>(cfg.min_level());
             c.max_level          = static_cast<int32_t>(cfg.max_level());
@@ -929,6 +926,45 @@ namespace samurai
         smr_mesh_t handle() const
         {
             return m_owner ? m_owner->h : 0;
+        }
+
+        // mesh[mesh_id_t::cells]: one of the five sub-meshes as an iterable (mesh.hpp:560-580): for_each_interval / for_each_cell
+        struct SubMesh
+        {
+            static constexpr std::size_t dim = Config::dim;
+            using cell_t                     = Cell<Config::dim>;
+            const MRMesh* mesh;
+            MRMeshId id;
+
+            std::size_t max_level() const
+            {
+                return mesh->max_level() + 2;
+            }
+
+            auto intervals(MRMeshId, std::size_t level) const
+            {
+                return mesh->intervals(id, level);
+            }
+
+            std::size_t nb_cells() const
+            {
+                return mesh->nb_cells(id);
+            }
+
+            double cell_length(std::size_t level) const
+            {
+                return mesh->cell_length(level);
+            }
+
+            const smr_mesh_config& c_config() const
+            {
+                return mesh->c_config();
+            }
+        };
+
+        SubMesh operator[](MRMeshId id) const
+        {
+            return SubMesh{this, id};
         }
 
         std::size_t min_level() const
@@ -1483,6 +1519,13 @@ namespace samurai
 
         void push_host()
         {
+            if (st().host_dirty && st().host.size() != size())
+            {
+                // the mirror was taken on a previous mesh (a field that was only read through u(level, i, ...) or that is about to be
+                // resized): nothing of it addresses the current numbering
+                st().host_dirty = false;
+                st().host_valid = false;
+            }
             if (st().host_dirty)
             {
                 b200::check(smr_field_upload(handle(), st().host.data(), static_cast<int64_t>(st().host.size())));

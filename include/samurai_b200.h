@@ -55,6 +55,8 @@ extern "C"
         int32_t n_cells0[3];        /* box size in level-0 cells: length / scaling_factor          */
         double origin[3];           /* Box::min_corner                                             */
         double scaling_factor;      /* LevelCellArray::scaling_factor (box.hpp:280-, approximate_box) */
+        int32_t periodic[3];        /* mesh_config::periodic(d) (mesh_config.hpp:171-196)           */
+        int32_t reserved;
     } smr_mesh_config;
 
     /* one x-interval of a sub-mesh: LevelCellArray entry (interval.hpp:50-64) flattened with its (y, z) */

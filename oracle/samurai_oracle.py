@@ -173,14 +173,32 @@ class MeshConfig:
     n_cells0: tuple = None  # domain size in level-0 cells per dim (default 1 each)
     origin: tuple = None
     scaling: float = 1.0
+    periodic: tuple = None  # mesh_config::periodic(d) (mesh_config.hpp:171-196)
 
     def __post_init__(self):
         if self.n_cells0 is None:
             self.n_cells0 = (1,) * self.dim
         if self.origin is None:
             self.origin = (0.0,) * self.dim
-        assert self.max_stencil_radius == 1, "oracle restates ghost width 1 only"
+        if self.periodic is None:
+            self.periodic = (False,) * self.dim
+        self.periodic = tuple(bool(p) for p in self.periodic)
+        # ghost width 2 is restated for fully periodic meshes only: no boundary extrapolation (bc/apply_field_bc.hpp:499-563) and
+        # no contiguous-boundary graduation rule (graduation.hpp:372-500) are involved there
+        assert self.max_stencil_radius == 1 or (self.max_stencil_radius == 2 and all(self.periodic)), "oracle restates ghost width 1 (2 if periodic)"
         assert self.pred_radius in (0, 1)
+
+    def periodic_directions(self, level):
+        """get_periodic_directions (mesh.hpp:45-81, graduation.hpp:37-76): every combination of -N_d, 0, +N_d over the periodic
+        dimensions except the null vector, N_d = number of cells of the domain at `level`."""
+        choices = [((-(n << level)), 0, (n << level)) if p else (0,) for n, p in zip(self.n_cells0, self.periodic)]
+        out = []
+        import itertools
+
+        for v in itertools.product(*choices):
+            if any(v):
+                out.append(list(v))
+        return out
 
     @property
     def ghost_width(self):
@@ -263,6 +281,14 @@ class Mesh:
         # cells_and_ghosts (mr/mesh.hpp:240-253)
         self.cag = [expand(self.cells[l], msr, dim) for l in range(nlev)]
         cl = [self.cag[l] for l in range(nlev)]
+        periodic = any(cfg.periodic)
+        if periodic:
+            # ghosts of the periodic images (mr/mesh.hpp:276-331): translate the leaves, expand, keep what lies in the expanded domain
+            for l in range(nlev):
+                if self.cells[l].size and l <= L:
+                    for d in cfg.periodic_directions(l):
+                        s = expand(translate(self.cells[l], d), msr, dim)
+                        cl[l] = union(cl[l], self.expanded_domain_inter(l, s, msr))
         self.proj = [EMPTY] * nlev
         if cfg.max_level != cfg.min_level:
             # prediction ghosts one and two levels below (mr/mesh.hpp:329-359)
@@ -274,6 +300,14 @@ class Mesh:
                 if l - 1 > 0:
                     s2 = expand(coarsen(self.cells[l], 2, dim), pr, dim)
                     cl[l - 2] = union(cl[l - 2], s2)
+                if periodic:
+                    # periodic part (mr/mesh.hpp:366-380): same sets for the translated leaves, inside the domain only
+                    for d in cfg.periodic_directions(l):
+                        p1 = expand(coarsen(translate(self.cag[l], d), 1, dim), pr, dim)
+                        cl[l - 1] = union(cl[l - 1], self.domain_inter(l - 1, p1))
+                        if l - 1 > 0:
+                            p2 = expand(coarsen(translate(self.cells[l], d), 2, dim), pr, dim)
+                            cl[l - 2] = union(cl[l - 2], self.domain_inter(l - 2, p2))
             ref = list(cl)
             # children of projected ghosts, coarse -> fine cascade (mr/mesh.hpp:415-452);
             # for_each_level re-evaluates max_level() every iteration and skips empty levels
@@ -453,6 +487,8 @@ def update_outer_ghosts(mesh: Mesh, f, bc: Bc, level):
     L, lmin = cfg.max_level, cfg.min_level
     if dim > 1 and lmin <= level <= L:
         for direction in diagonal_directions(dim):
+            if any(direction[d] != 0 and cfg.periodic[d] for d in range(dim)):
+                continue  # a periodic direction has no corner ghost (update_outer_ghost.hpp:352-366)
             corner = mesh.corner_cell(level, direction)
             # update_outer_corners_by_polynomial_extrapolation, stencil size 2:
             # u[corner + direction] = u[corner]   (bc/polynomial_extrapolation.hpp:63-66)
@@ -475,6 +511,8 @@ def update_outer_ghosts(mesh: Mesh, f, bc: Bc, level):
                     if proj_level == 0:
                         break
     for direction in cartesian_directions(dim):
+        if any(direction[d] != 0 and cfg.periodic[d] for d in range(dim)):
+            continue  # update_outer_ghost.hpp:372-375
         if level < L:
             _project_bc(mesh, f, level, direction)
         if level >= lmin:
@@ -564,17 +602,79 @@ def prediction_set(mesh: Mesh, level):
     return e[mesh.contains(level - 1, parent)]
 
 
+def periodic_pairs(mesh: Mesh, level, d):
+    """iterate_over_periodic_ghosts for dimension d (algorithm/update_periodic.hpp:34-125): returns (ghost keys, source keys).
+    Ghosts within ghost_width beyond the upper boundary mirror the cells just inside the lower boundary (set1), ghosts before the
+    lower boundary mirror the cells just inside the upper one (set2); in the other dimensions the slabs span the domain grown by
+    ghost_width; a pair exists where both cells are in the reference sub-mesh."""
+    cfg, dim = mesh.cfg, mesh.cfg.dim
+    ref = mesh.ref[level]
+    if ref.size == 0:
+        return EMPTY, EMPTY
+    gw = cfg.ghost_width
+    c = unpack(ref, dim)
+    n = [cfg.n_cells0[k] << level for k in range(dim)]
+    inside_others = np.ones(ref.size, dtype=bool)
+    for k in range(dim):
+        if k != d:
+            inside_others &= (c[:, k] >= -gw) & (c[:, k] < n[k] + gw)
+    shift = [0] * dim
+    shift[d] = n[d]
+    ghosts, sources = [], []
+    # set1: translate(ref & lca_min_p, +shift) & (ref & lca_max_p)
+    src = ref[inside_others & (c[:, d] >= 0) & (c[:, d] < gw)]
+    dst = ref[inside_others & (c[:, d] >= n[d]) & (c[:, d] < n[d] + gw)]
+    g = inter(translate(src, shift), dst)
+    ghosts.append(g)
+    sources.append(translate(g, [-s for s in shift]))
+    # set2: translate(ref & lca_max_m, -shift) & (ref & lca_min_m)
+    src = ref[inside_others & (c[:, d] >= n[d] - gw) & (c[:, d] < n[d])]
+    dst = ref[inside_others & (c[:, d] >= -gw) & (c[:, d] < 0)]
+    g = inter(translate(src, [-s for s in shift]), dst)
+    ghosts.append(g)
+    sources.append(translate(g, shift))
+    return np.concatenate(ghosts), np.concatenate(sources)
+
+
+def update_ghost_periodic(mesh: Mesh, f, level):
+    """update_ghost_periodic(level, field) (algorithm/update_periodic.hpp:23-32): dimension after dimension."""
+    for d in range(mesh.cfg.dim):
+        if mesh.cfg.periodic[d]:
+            g, s = periodic_pairs(mesh, level, d)
+            if g.size:
+                f[mesh.index(level, g)] = f[mesh.index(level, s)]
+
+
+def update_tag_periodic(mesh: Mesh, tag, level):
+    """update_tag_periodic (algorithm/update_periodic.hpp:211-300): a ghost and its mirrored cell take the OR of their tags."""
+    for d in range(mesh.cfg.dim):
+        if mesh.cfg.periodic[d]:
+            g, s = periodic_pairs(mesh, level, d)
+            if g.size:
+                gi, si = mesh.index(level, g), mesh.index(level, s)
+                v = tag[gi] | tag[si]
+                tag[gi] = v
+                tag[si] = v
+
+
 def update_ghost_mr(mesh: Mesh, f, bc: Bc):
-    """update_ghost_mr_aggregated (algorithm/update_ghost_mr.hpp:194-237), serial, non-periodic."""
+    """update_ghost_mr_aggregated (algorithm/update_ghost_mr.hpp:194-237), serial."""
     L = mesh.cfg.max_level
+    periodic = any(mesh.cfg.periodic)
     for level in range(L, -1, -1):
+        if periodic:
+            update_ghost_periodic(mesh, f, level)
         update_outer_ghosts(mesh, f, bc, level)
+        if periodic:
+            update_ghost_periodic(mesh, f, level)
         if level > 0:
             projection(mesh, f, level - 1, projection_set(mesh, level))
     for level in range(1, L + 1):
         e = prediction_set(mesh, level)
         if e.size:
             f[mesh.index(level, e)] = predict_values(mesh, f, mesh, level, e)
+        if periodic:
+            update_ghost_periodic(mesh, f, level)
 
 
 # ----------------------------------------------------------------------------
@@ -692,17 +792,19 @@ def make_graduation(cfg: MeshConfig, ca):
         for fine in range(hi, lo + 1, -1):  # fine_level = max_level ... min_level+2
             if ca[fine].size == 0:
                 continue
-            proj = coarsen(expand(ca[fine], 2 * w, dim), 2, dim)
-            coarse_level = fine - 2
-            while True:
-                if proj.size:
-                    r = inter(proj, ca[coarse_level])
-                    if r.size:
-                        out[coarse_level].append(r)
-                if coarse_level == lo or proj.size == 0:
-                    break
-                proj = coarsen(proj, 1, dim)
-                coarse_level -= 1
+            # the fine cells and, on periodic meshes, their images (graduation.hpp:309-320)
+            for fine_set in [ca[fine]] + [translate(ca[fine], d) for d in cfg.periodic_directions(fine)]:
+                proj = coarsen(expand(fine_set, 2 * w, dim), 2, dim)
+                coarse_level = fine - 2
+                while True:
+                    if proj.size:
+                        r = inter(proj, ca[coarse_level])
+                        if r.size:
+                            out[coarse_level].append(r)
+                    if coarse_level == lo or proj.size == 0:
+                        break
+                    proj = coarsen(proj, 1, dim)
+                    coarse_level -= 1
         if not any(out):
             return ca
         rem = [union(*o) if o else EMPTY for o in out]
@@ -775,6 +877,7 @@ def adapt(mesh: Mesh, f, bc: Bc, eps=1e-4, regularity=1.0, trace=None, relative_
         for level in range(lmin, L - ite + 1):
             mr_criteria(mesh, detail, tag, level, eps, regularity)
         for level in range(L, 0, -1):
+            update_tag_periodic(mesh, tag, level)  # mr/adapt.hpp:353
             maximum(mesh, tag, level)
         if trace is not None:
             trace.append(dict(ite=ite, mesh=mesh, field=f.copy(), detail=detail, tag=tag.copy()))
@@ -809,6 +912,7 @@ def adapt_fields(mesh: Mesh, fields, bcs, eps=1e-4, regularity=1.0):
         for level in range(lmin, L - ite + 1):
             mr_criteria(mesh, details, tag, level, eps, regularity)
         for level in range(L, 0, -1):
+            update_tag_periodic(mesh, tag, level)
             maximum(mesh, tag, level)
         new_ca = update_cell_array_from_tag(mesh, tag)
         new_ca = make_graduation(cfg, new_ca)

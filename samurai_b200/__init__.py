@@ -34,6 +34,8 @@ class MeshConfigC(C.Structure):
         ("n_cells0", C.c_int32 * 3),
         ("origin", C.c_double * 3),
         ("scaling_factor", C.c_double),
+        ("periodic", C.c_int32 * 3),
+        ("reserved", C.c_int32),
     ]
 
 
@@ -266,6 +268,7 @@ class mesh_config:
         self._max_stencil_radius = 1
         self._graduation_width = 1
         self._disable_minimal_ghost_width = False
+        self._periodic = [False, False, False]
 
     def min_level(self, v):
         self._min_level = v
@@ -291,6 +294,16 @@ class mesh_config:
         self._disable_minimal_ghost_width = True
         return self
 
+    def periodic(self, *flags):
+        """mesh_config::periodic(bool) / periodic(array) (mesh_config.hpp:171-196)"""
+        if len(flags) == 1 and isinstance(flags[0], (list, tuple)):
+            flags = tuple(flags[0])
+        if len(flags) == 1:
+            flags = flags * self.dim
+        for d in range(self.dim):
+            self._periodic[d] = bool(flags[d])
+        return self
+
     def to_c(self, box_min, box_max):
         msr = self._max_stencil_radius
         if not self._disable_minimal_ghost_width:
@@ -298,6 +311,8 @@ class mesh_config:
         c = MeshConfigC()
         c.dim, c.min_level, c.max_level = self.dim, self._min_level, self._max_level
         c.pred_radius, c.max_stencil_radius, c.graduation_width = self.pred_radius, msr, self._graduation_width
+        for d in range(3):
+            c.periodic[d] = 1 if (d < self.dim and self._periodic[d]) else 0
         lengths = [float(box_max[d]) - float(box_min[d]) for d in range(self.dim)]
         # approximate_box (box.hpp:280-360) for boxes whose lengths are integer multiples of the smallest one
         scaling = min(lengths)

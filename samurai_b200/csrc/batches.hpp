@@ -1228,8 +1228,10 @@ namespace smr
     //   * the projection chain never reads an outside ghost, so it shares the launch.
     struct GhostPhase
     {
-        Batch bc;   // extrapolated corners(level) + corner copies from level+1 + project_bc(level) + BC values(level, level+1 children)
-        Batch proj; // projection level -> level-1
+        Batch bc;     // extrapolated corners(level) + corner copies from level+1 + project_bc(level) + BC values(level, level+1 children)
+        Batch proj;   // projection level -> level-1
+        Batch per[3]; // periodic ghosts of the level, one batch per periodic dimension (update_ghost_periodic: the dimensions are
+                      // processed one after the other, the later ones copy ghosts the earlier ones filled)
     };
 
     struct MeshPlan
@@ -1357,7 +1359,62 @@ namespace smr
     {
         BcBuilder bc;
         std::vector<smr_seed> proj; // seeds at the coarse level
+        std::vector<smr_item_copy> per[3];
     };
+
+    // update_ghost_periodic(level) for dimension d (algorithm/update_periodic.hpp:34-125): the ghosts within ghost_width beyond the
+    // upper boundary copy the cells just inside the lower one and vice versa, wherever both exist in the reference sub-mesh.  In the
+    // other dimensions the slabs span the domain grown by ghost_width, so that corner ghosts are reached dimension after dimension.
+    inline void periodic_items(const Mesh& m, int level, int d, const PlanFilter& flt, std::vector<smr_item_copy>& out)
+    {
+        const MeshConfig& cfg = m.cfg;
+        const LevelSet& ref   = m.ref[level];
+        if (ref.empty() || level > cfg.max_level)
+        {
+            return;
+        }
+        const int dim = cfg.dim, gw = cfg.ghost_width();
+        const int N = cfg.n0[d] << level;
+        int lo[3], hi[3];
+        for (int side = 0; side < 2; ++side)
+        {
+            m.domain_box(level, gw, lo, hi);
+            // side 0: ghosts in [N, N + gw) <- cells in [0, gw) ; side 1: ghosts in [-gw, 0) <- cells in [N - gw, N)
+            const int shift = side == 0 ? N : -N;
+            lo[d] = side == 0 ? 0 : N - gw;
+            hi[d] = side == 0 ? gw : N;
+            const LevelSet src = clip_box(ref, dim, lo, hi);
+            lo[d] += shift;
+            hi[d] += shift;
+            const LevelSet dst = clip_box(ref, dim, lo, hi);
+            if (src.empty() || dst.empty())
+            {
+                continue;
+            }
+            int sv[3] = {0, 0, 0};
+            sv[d]     = shift;
+            const LevelSet set = set_inter(translate(src, sv[0], sv[1], sv[2]), dst);
+            for (size_t r = 0; r < set.rows(); ++r)
+            {
+                const int y = key_y(set.key[r]), z = key_z(set.key[r]);
+                if (!flt.owns(level, y, z))
+                {
+                    continue;
+                }
+                const int mask = static_cast<int>(flt.mask(level, y, z));
+                for (int q = set.ptr[r]; q < set.ptr[r + 1]; ++q)
+                {
+                    const int s = set.xs[q], e = set.xe[q];
+                    smr_item_copy it;
+                    it.dst  = need(ref, "periodic ghost", level, y, z, s, e - 1);
+                    it.src  = need(ref, "periodic source", level, y - sv[1], z - sv[2], s - sv[0], e - 1 - sv[0]);
+                    it.n    = e - s;
+                    it.mask = mask;
+                    out.push_back(it);
+                }
+            }
+        }
+    }
 
     // project_corner_below(src_level) (update_outer_ghost.hpp:267-336): copies of the corner ghost of src_level into
     // the corner ghosts one (dl = 1) and two (dl = 2) levels below, where the corner-most child exists
@@ -1408,11 +1465,33 @@ namespace smr
         {
             return;
         }
+        auto touches_periodic = [&](const Dir& d)
+        {
+            for (int k = 0; k < dim; ++k)
+            {
+                if (d.v[k] != 0 && cfg.periodic[k])
+                {
+                    return true;
+                }
+            }
+            return false;
+        };
+        for (int k = 0; k < dim; ++k)
+        {
+            if (cfg.periodic[k])
+            {
+                periodic_items(m, level, k, flt, out.per[k]);
+            }
+        }
         std::vector<int64_t> extrap_dst;
         if (dim > 1)
         {
             for (const Dir& d : diagonal_directions(dim))
             {
+                if (touches_periodic(d))
+                {
+                    continue; // a periodic direction has no boundary, hence no corner ghost (update_outer_ghost.hpp:352-366)
+                }
                 if (level >= lmin && level <= L && !ref.empty())
                 {
                     // update_outer_corners_by_polynomial_extrapolation, ghost width 1: u[c + d] = u[c]
@@ -1432,6 +1511,10 @@ namespace smr
             std::sort(extrap_dst.begin(), extrap_dst.end());
             for (const Dir& d : diagonal_directions(dim))
             {
+                if (touches_periodic(d))
+                {
+                    continue;
+                }
                 // records of project_corner_below(level + 1): written in this phase, after phase level+1 produced their source
                 if (level + 1 >= lmin && level + 1 <= L)
                 {
@@ -1454,6 +1537,10 @@ namespace smr
         }
         for (const Dir& d : cartesian_directions(dim))
         {
+            if (touches_periodic(d))
+            {
+                continue; // update_outer_ghost.hpp:372-375
+            }
             if (level < L && !ref.empty())
             {
                 // project_bc, layer 1
@@ -1732,8 +1819,13 @@ namespace smr
         p_detail.n_groups = p_tag_all.n_groups = nlev; // cumulative counts are indexed by level
         std::vector<PendingSeeds> p_proj(nlev), p_pred(nlev), p_tag(nlev);
         std::vector<PendingBc> p_bc(nlev);
+        std::vector<Pending<smr_item_copy>> p_per(static_cast<size_t>(3 * nlev));
         for (int l = 0; l < nlev; ++l)
         {
+            for (int k = 0; k < 3; ++k)
+            {
+                p_per[static_cast<size_t>(3 * l + k)] = Pending<smr_item_copy>{&plan.down[l].per[k], B_COPY, l, {&phases[l].per[k]}, nullptr, false};
+            }
             p_proj[l] = pending_seeds(&plan.down[l].proj, B_PROJ, SMR_DERIVE_PROJ, l, sizeof(smr_item_proj));
             p_proj[l].parts.push_back(&phases[l].proj);
             p_pred[l] = pending_seeds(&plan.pred[l], B_PRED, SMR_DERIVE_PRED, l, sizeof(smr_item_pred));
@@ -1782,6 +1874,10 @@ namespace smr
             layout_seeds(p_pred[l], plan.arena, plan.derive);
             layout_seeds(p_tag[l], plan.arena, plan.derive);
             layout_bc(p_bc[l], plan.arena);
+            for (int k = 0; k < 3; ++k)
+            {
+                layout_batch(p_per[static_cast<size_t>(3 * l + k)], plan.arena);
+            }
         }
         close_derive(plan.arena, plan.derive);
         {
@@ -1810,6 +1906,14 @@ namespace smr
                 add(p_tag[l]);
                 PendingBc* pb = &p_bc[l];
                 jobs.push_back([pb, &plan] { fill_bc(*pb, plan.arena); });
+                for (int k = 0; k < 3; ++k)
+                {
+                    Pending<smr_item_copy>* pp = &p_per[static_cast<size_t>(3 * l + k)];
+                    if (!phases[l].per[k].empty())
+                    {
+                        jobs.push_back([pp, &plan] { fill_batch(*pp, plan.arena); });
+                    }
+                }
             }
 #pragma omp parallel for schedule(dynamic, 1)
             for (int t = 0; t < static_cast<int>(jobs.size()); ++t)

@@ -519,9 +519,17 @@ namespace smr
         {
             throw std::invalid_argument("max_level too large (max_refinement_level is 20, samurai_config.hpp:50)");
         }
-        if (c->max_stencil_radius != 1)
+        bool all_periodic = true;
+        for (int d = 0; d < c->dim; ++d)
         {
-            throw std::invalid_argument("only max_stencil_radius == 1 (ghost width 1) is implemented");
+            all_periodic = all_periodic && c->periodic[d] != 0;
+        }
+        if (c->max_stencil_radius < 1 || c->max_stencil_radius > 2 || (c->max_stencil_radius == 2 && !all_periodic))
+        {
+            // ghost width 2 needs the further-ghost extrapolation at non-periodic boundaries (bc/apply_field_bc.hpp:499-563) and the
+            // contiguous-boundary graduation rule (graduation.hpp:372-500), which are not built; a fully periodic mesh has neither
+            throw std::invalid_argument("max_stencil_radius must be 1 (or 2 on a mesh periodic in every direction): call "
+                                        "max_stencil_size(2) / disable_minimal_ghost_width() on the mesh_config");
         }
         if (c->pred_radius < 0 || c->pred_radius > 1)
         {
@@ -543,6 +551,10 @@ namespace smr
             }
         }
         out.scaling = c->scaling_factor;
+        for (int d = 0; d < 3; ++d)
+        {
+            out.periodic[d] = d < c->dim && c->periodic[d] != 0;
+        }
     }
 
     // ---------------------------------------------------------------------------------------------------------
@@ -840,6 +852,8 @@ namespace smr
                 case WF_KEEP:
                 case WF_TAGS_CHANGE:
                     return 1;
+                case WF_TAG_OR:
+                    return 4;
                 case WF_COPY:
                     return 16;
                 default:
@@ -1138,6 +1152,10 @@ namespace smr
                 fam = SMR_FAM_INIT;
                 SMR_CUDA(cudaMemsetAsync(a.tag, 0, static_cast<size_t>(jb.n_cells), g.stream));
                 break;
+            case WF_TAG_OR:
+                fam = SMR_FAM_MAXIMUM;
+                SMR_CUDA((launch_batch<smr_item_copy, TagOrOp>(n_ctas, g.stream, view(smr_item_copy{}), TagOrOp{a.tag, a.mask_all})));
+                break;
             default: // WF_COPY
                 fam = SMR_FAM_COPY;
                 SMR_CUDA((launch_batch<smr_item_copy, CopyOp>(n_ctas, g.stream, view(smr_item_copy{}), CopyOp{a.src[jb.field], a.dst[jb.field]})));
@@ -1222,7 +1240,8 @@ namespace smr
                 }
                 ph.total_ctas = total;
             }
-            ph.pad = ph.total_ctas <= WF_SERIAL_CTAS ? 1 : 0;
+            static const bool no_serial = std::getenv("SMR_WF_NO_SERIAL") != nullptr;
+            ph.pad = (!no_serial && ph.total_ctas <= WF_SERIAL_CTAS) ? 1 : 0;
         }
         static const bool trace = std::getenv("SMR_WF_TRACE") != nullptr;
         if (trace)
@@ -1327,35 +1346,69 @@ namespace smr
     {
         const MeshConfig& cfg = mo.mesh.cfg;
         int index             = 0;
+        const bool periodic = cfg.any_periodic();
+        // update_ghost_periodic(level): one phase per periodic dimension (the later dimensions copy ghosts of the earlier ones)
+        auto periodic_phases = [&](int level)
+        {
+            for (int k = 0; k < cfg.dim; ++k)
+            {
+                const Batch& b = mo.plan.down[level].per[k];
+                if (cfg.periodic[k] && !b.empty())
+                {
+                    wb.begin_phase();
+                    for (int f = 0; f < nfields; ++f)
+                    {
+                        wb.add(WF_COPY, b, f);
+                    }
+                    wb.end_phase();
+                }
+            }
+        };
         for (int level = cfg.max_level; level >= 0; --level)
         {
             const GhostPhase& ph = mo.plan.down[level];
-            if (ph.bc.empty() && ph.proj.empty())
+            // algorithm/update_ghost_mr.hpp:204-222: periodic ghosts, outer ghosts, periodic ghosts again, projection.  Both passes
+            // are needed even without outer ghosts: a corner ghost whose mirror along the last dimension is absent from the mesh is
+            // filled along the first one, from a ghost the first pass has just written (measured: a single pass leaves such corners
+            // stale).  The projection only touches cells inside the domain, so it shares the phase of the outer ghosts.
+            if (periodic)
             {
-                continue;
+                periodic_phases(level);
             }
-            wb.begin_phase();
-            extra(index++);
-            for (int f = 0; f < nfields; ++f)
+            if (!(ph.bc.empty() && ph.proj.empty()))
             {
-                wb.add(WF_BC, ph.bc, f);
-                wb.add(WF_PROJ, ph.proj, f);
+                wb.begin_phase();
+                extra(index++);
+                for (int f = 0; f < nfields; ++f)
+                {
+                    wb.add(WF_BC, ph.bc, f);
+                    wb.add(WF_PROJ, ph.proj, f);
+                }
+                wb.end_phase();
             }
-            wb.end_phase();
+            if (periodic)
+            {
+                periodic_phases(level);
+            }
         }
         for (int level = 1; level <= cfg.max_level; ++level)
         {
-            if (mo.plan.pred[level].empty())
+            if (!mo.plan.pred[level].empty())
             {
-                continue;
+                wb.begin_phase();
+                extra(index++);
+                for (int f = 0; f < nfields; ++f)
+                {
+                    wb.add(WF_PRED, mo.plan.pred[level], f);
+                }
+                wb.end_phase();
             }
-            wb.begin_phase();
-            extra(index++);
-            for (int f = 0; f < nfields; ++f)
+            if (periodic)
             {
-                wb.add(WF_PRED, mo.plan.pred[level], f);
+                // also without prediction ghosts at this level: predict_bc(level) wrote boundary ghosts of this level after its
+                // top-down periodic passes (update_outer_ghost.hpp:396-400), and the mirrored corners must see them
+                periodic_phases(level);
             }
-            wb.end_phase();
         }
         // phases the caller still owes its extras to
         for (; index < 2; ++index)
@@ -1374,7 +1427,7 @@ namespace smr
         }
         for (size_t i = 0; i < fields.size(); ++i)
         {
-            if (fields[i]->bc_type < 0)
+            if (fields[i]->bc_type < 0 && !fields[i]->mesh->mesh.cfg.all_periodic())
             {
                 throw std::invalid_argument("field '" + fields[i]->name + "' has no boundary condition attached (make_bc)");
             }
@@ -1397,7 +1450,7 @@ namespace smr
     {
         MeshObj& mo = *f.mesh;
         check_field_ready(f);
-        if (f.bc_type < 0)
+        if (f.bc_type < 0 && !mo.mesh.cfg.all_periodic())
         {
             throw std::invalid_argument("field '" + f.name + "' has no boundary condition attached (make_bc)");
         }
@@ -1417,13 +1470,26 @@ namespace smr
             f.ghosts_valid = true;
             return;
         }
+        auto periodic_copies = [&](int level)
+        {
+            for (int k = 0; k < cfg.dim; ++k)
+            {
+                if (cfg.periodic[k])
+                {
+                    launch<smr_item_copy>(SMR_FAM_COPY, arena, mo.plan.down[level].per[k], CopyOp{u, u});
+                }
+            }
+        };
         for (int level = cfg.max_level; level >= 0; --level)
         {
+            periodic_copies(level);
             launch_ghost_phase(cfg.dim, arena, mo.plan.down[level], u, f.bc_type, f.bc_value);
+            periodic_copies(level);
         }
         for (int level = 1; level <= cfg.max_level; ++level)
         {
             launch_pred(cfg.dim, cfg.pred_radius, arena, mo.plan.pred[level], u, u);
+            periodic_copies(level);
         }
         f.ghosts_valid = true;
     }
@@ -1620,6 +1686,15 @@ namespace smr
             wb.end_phase();
             for (int level = L; level >= 1; --level)
             {
+                for (int k = 0; k < dim; ++k) // update_tag_periodic(level), mr/adapt.hpp:353
+                {
+                    if (cfg.periodic[k] && !mo.plan.down[level].per[k].empty())
+                    {
+                        wb.begin_phase();
+                        wb.add(WF_TAG_OR, mo.plan.down[level].per[k], 0);
+                        wb.end_phase();
+                    }
+                }
                 wb.begin_phase();
                 wb.add(WF_MAXIMUM, mo.plan.tag[level], 0);
                 wb.end_phase();
@@ -1678,6 +1753,13 @@ namespace smr
             }
             for (int level = L; level >= 1; --level)
             {
+                for (int k = 0; k < dim; ++k)
+                {
+                    if (cfg.periodic[k])
+                    {
+                        launch<smr_item_copy>(SMR_FAM_MAXIMUM, arena, mo.plan.down[level].per[k], TagOrOp{tag, mo.filter.mask_all()});
+                    }
+                }
                 launch_dim<MaximumOpR, smr_item_tag>(SMR_FAM_MAXIMUM, dim, arena, mo.plan.tag[level], -1, tag);
             }
         }
@@ -2088,6 +2170,11 @@ extern "C"
                     out->origin[d]   = c.origin[d];
                 }
                 out->scaling_factor = c.scaling;
+                for (int d = 0; d < 3; ++d)
+                {
+                    out->periodic[d] = c.periodic[d] ? 1 : 0;
+                }
+                out->reserved = 0;
             });
     }
 
@@ -2412,6 +2499,11 @@ extern "C"
                 if (kind != SMR_SCHEME_CONVECTION_UPWIND && kind != SMR_SCHEME_DIFFUSION_ORDER2 && kind != SMR_SCHEME_CONVECTION_UPWIND_NONLINEAR)
                 {
                     throw std::invalid_argument("unknown scheme kind");
+                }
+                if (cfg.any_periodic())
+                {
+                    // the interface enumeration (interface.hpp) across a periodic boundary is not built: fail loudly, never approximate
+                    throw std::invalid_argument("flux-based schemes are not implemented on periodic meshes (field expressions with upwind() are)");
                 }
                 const bool nonlin = kind == SMR_SCHEME_CONVECTION_UPWIND_NONLINEAR;
                 static const bool force_general = std::getenv("SMR_FLUX_GENERAL") != nullptr;

@@ -20,6 +20,7 @@ SMR_INST_BATCH(smr_item_fv, smr::TagsChangeOp)
 SMR_INST_RECORDS(smr_item_fv, smr::KeepLeavesOp)
 SMR_INST_RECORDS(smr_item_fv, smr::TagsChangeOp)
 SMR_INST_BATCH(smr_item_copy, smr::CopyOp)
+SMR_INST_BATCH(smr_item_copy, smr::TagOrOp)
 
 namespace smr
 {

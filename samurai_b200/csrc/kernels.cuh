@@ -1382,6 +1382,26 @@ namespace smr
 
     using CopyOp = CopyOpT<true>;
 
+    // update_tag_periodic (algorithm/update_periodic.hpp:211-300): a periodic ghost and the cell it mirrors end up with the OR
+    // of their tags; driven by the same records as the periodic ghost copy of the fields (dst = ghost, src = mirrored cell)
+    struct TagOrOp
+    {
+        static constexpr bool two_phase = false;
+        static constexpr bool warp_uniform = false;
+        static constexpr int min_blocks = 1;
+        static constexpr int units_per_thread = SMR_CELLS_PER_THREAD;
+
+        uint8_t* tag;
+        unsigned mask_all;
+
+        __device__ __forceinline__ void operator()(const smr_item_copy& it, int k) const
+        {
+            const uint8_t v = static_cast<uint8_t>(tag[it.dst + k] | tag[it.src + k]);
+            mstore(tag + it.dst + k, v, mask_all);
+            mstore(tag + it.src + k, v, mask_all);
+        }
+    };
+
     // ------------------------------------------------------------------------------------------------------------
     // boundary ghosts: one thread per ghost cell (update_outer_ghost.hpp, bc/dirichlet.hpp:29, bc/neumann.hpp:27-28)
     // ------------------------------------------------------------------------------------------------------------
@@ -1470,7 +1490,8 @@ namespace smr
         WF_ZERO_DETAIL,
         WF_ZERO_TAG,
         WF_COPY,
-        WF_TAGS_CHANGE
+        WF_TAGS_CHANGE,
+        WF_TAG_OR
     };
 
     struct WfJob
@@ -1629,6 +1650,9 @@ namespace smr
             case WF_TAGS_CHANGE:
                 wf_item(wf_view<smr_item_fv>(a.arena, jb), TagsChangeOp{a.tag, a.change_flag, a.tp.min_level, a.tp.max_level}, local, jb.pad != 0, s_prefix);
                 break;
+            case WF_TAG_OR:
+                wf_item(wf_view<smr_item_copy>(a.arena, jb), TagOrOp{a.tag, a.mask_all}, local, jb.pad != 0, s_prefix);
+                break;
             default: // WF_COPY
                 wf_item(wf_view<smr_item_copy>(a.arena, jb), CopyOpT<false>{a.src[jb.field], a.dst[jb.field]}, local, jb.pad != 0, s_prefix);
                 break;
@@ -1686,6 +1710,7 @@ namespace smr
                 isz = sizeof(smr_item_fv);
                 break;
             case WF_COPY:
+            case WF_TAG_OR:
                 isz = sizeof(smr_item_copy);
                 break;
             default:

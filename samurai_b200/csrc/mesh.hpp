@@ -46,6 +46,58 @@ namespace smr
         int n0[3]              = {1, 1, 1}; // domain size in level-0 cells
         double origin[3]       = {0, 0, 0};
         double scaling         = 1.0;
+        bool periodic[3]       = {false, false, false}; // mesh_config::periodic(d)
+
+        bool any_periodic() const
+        {
+            return periodic[0] || periodic[1] || periodic[2];
+        }
+
+        bool all_periodic() const
+        {
+            for (int d = 0; d < dim; ++d)
+            {
+                if (!periodic[d])
+                {
+                    return false;
+                }
+            }
+            return true;
+        }
+
+        // translations that map the domain onto its periodic images at `level` (mesh.hpp:45-81 get_periodic_directions):
+        // every combination of {-N_d, 0, +N_d} over the periodic dimensions except the null one
+        std::vector<std::array<int, 3>> periodic_directions(int level) const
+        {
+            std::vector<std::array<int, 3>> out;
+            if (!any_periodic())
+            {
+                return out;
+            }
+            for (int cz = -1; cz <= 1; ++cz)
+            {
+                for (int cy = -1; cy <= 1; ++cy)
+                {
+                    for (int cx = -1; cx <= 1; ++cx)
+                    {
+                        const int c[3] = {cx, cy, cz};
+                        bool ok = (cx | cy | cz) != 0;
+                        for (int d = 0; d < 3; ++d)
+                        {
+                            if (c[d] != 0 && (d >= dim || !periodic[d]))
+                            {
+                                ok = false;
+                            }
+                        }
+                        if (ok)
+                        {
+                            out.push_back({cx * (n0[0] << level), cy * (n0[1] << level), cz * (n0[2] << level)});
+                        }
+                    }
+                }
+            }
+            return out;
+        }
 
         int ghost_width() const
         {
@@ -200,9 +252,29 @@ namespace smr
                 int level;
                 size_t r0, r1;
                 LevelSet cag, add1, add2;
+                LevelSet per0, per1, per2; // periodic images of the three sets above (mr/mesh.hpp:276-331, 366-380)
             };
             std::vector<Task> tasks;
             std::vector<std::pair<int, int>> level_tasks(nlev, {0, 0});
+            const bool periodic = cfg.any_periodic();
+            // union over the periodic directions of translate(s, direction(level)) clipped to the domain grown by `grow`
+            auto images = [&](const LevelSet& s, int level, int grow)
+            {
+                LevelSet acc;
+                if (s.empty() || level < 0)
+                {
+                    return acc;
+                }
+                for (const auto& dv : cfg.periodic_directions(level))
+                {
+                    LevelSet t = in_domain(translate(s, dv[0], dv[1], dv[2]), level, grow);
+                    if (!t.empty())
+                    {
+                        acc = acc.empty() ? std::move(t) : set_union(acc, t);
+                    }
+                }
+                return acc;
+            };
             for (int l = 0; l < nlev; ++l)
             {
                 level_tasks[l].first = static_cast<int>(tasks.size());
@@ -211,7 +283,7 @@ namespace smr
                     const std::vector<size_t> cut = chunk_rows(cells[l], 3000, 16);
                     for (size_t c = 0; c + 1 < cut.size(); ++c)
                     {
-                        tasks.push_back(Task{l, cut[c], cut[c + 1], {}, {}, {}});
+                        tasks.push_back(Task{l, cut[c], cut[c + 1], {}, {}, {}, {}, {}, {}});
                     }
                 }
                 level_tasks[l].second = static_cast<int>(tasks.size());
@@ -244,12 +316,26 @@ namespace smr
                 }
                 const LevelSet& part = whole ? cells[l] : part_storage;
                 tk.cag               = expand(part, msr, dim);
+                if (periodic)
+                {
+                    // ghost cells of the periodic images: expand(translate(cells, d), msr) inside the domain grown by msr
+                    tk.per0 = images(tk.cag, l, msr);
+                }
                 if (multi && l >= 1)
                 {
-                    tk.add1 = in_domain(expand(coarsen(tk.cag, 1, dim), pr, dim), l - 1, pr);
+                    LevelSet below = expand(coarsen(tk.cag, 1, dim), pr, dim);
+                    if (periodic)
+                    {
+                        tk.per1 = images(below, l - 1, 0); // prediction ghosts of the images, inside the domain only
+                    }
+                    tk.add1 = in_domain(below, l - 1, pr);
                     if (l - 1 > 0)
                     {
                         tk.add2 = expand(coarsen(part, 2, dim), pr, dim);
+                        if (periodic)
+                        {
+                            tk.per2 = images(tk.add2, l - 2, 0);
+                        }
                     }
                 }
 #ifdef SMR_PLAN_TIMING
@@ -257,23 +343,46 @@ namespace smr
                 tlev[l] += omp_get_wtime() - tl0;
 #endif
             }
+            std::vector<LevelSet> per0(nlev), per1(nlev), per2(nlev);
 #pragma omp parallel for schedule(dynamic, 1)
-            for (int t = 3 * nlev - 1; t >= 0; --t)
+            for (int t = 6 * nlev - 1; t >= 0; --t)
             {
-                const int l = t / 3, what = t % 3;
+                const int l = t / 6, what = t % 6;
+                if (what >= 3 && !periodic)
+                {
+                    continue;
+                }
+                auto member = [what](Task& tk) -> LevelSet&
+                {
+                    switch (what)
+                    {
+                        case 0:
+                            return tk.cag;
+                        case 1:
+                            return tk.add1;
+                        case 2:
+                            return tk.add2;
+                        case 3:
+                            return tk.per0;
+                        case 4:
+                            return tk.per1;
+                        default:
+                            return tk.per2;
+                    }
+                };
+                LevelSet& dst = what == 0 ? cag[l] : (what == 1 ? add1[l] : (what == 2 ? add2[l] : (what == 3 ? per0[l] : (what == 4 ? per1[l] : per2[l]))));
                 std::vector<const LevelSet*> parts;
                 for (int k = level_tasks[l].first; k < level_tasks[l].second; ++k)
                 {
-                    parts.push_back(what == 0 ? &tasks[k].cag : (what == 1 ? &tasks[k].add1 : &tasks[k].add2));
+                    parts.push_back(&member(tasks[static_cast<size_t>(k)]));
                 }
                 if (parts.size() == 1)
                 {
-                    LevelSet& src = what == 0 ? tasks[level_tasks[l].first].cag : (what == 1 ? tasks[level_tasks[l].first].add1 : tasks[level_tasks[l].first].add2);
-                    (what == 0 ? cag[l] : (what == 1 ? add1[l] : add2[l])) = std::move(src);
+                    dst = std::move(member(tasks[static_cast<size_t>(level_tasks[l].first)]));
                 }
                 else if (!parts.empty())
                 {
-                    (what == 0 ? cag[l] : (what == 1 ? add1[l] : add2[l])) = union_all(parts);
+                    dst = union_all(parts);
                 }
             }
 #ifdef SMR_PLAN_TIMING
@@ -291,6 +400,21 @@ namespace smr
                 if (l + 2 < nlev && !add2[l + 2].empty())
                 {
                     r = set_union(r, add2[l + 2]);
+                }
+                if (periodic)
+                {
+                    if (!per0[l].empty())
+                    {
+                        r = set_union(r, per0[l]);
+                    }
+                    if (l + 1 < nlev && !per1[l + 1].empty())
+                    {
+                        r = set_union(r, per1[l + 1]);
+                    }
+                    if (l + 2 < nlev && !per2[l + 2].empty())
+                    {
+                        r = set_union(r, per2[l + 2]);
+                    }
                 }
                 ref[l] = std::move(r);
             }
@@ -665,6 +789,17 @@ namespace smr
                 // multiples of 4, so the halo test x in [4c-2w, 4c+3+2w] is exactly (x>>1) in [2c-w, 2c+1+w]; coarsening
                 // first halves the rows the expansion has to merge
                 LevelSet p = coarsen(expand(coarsen(slice_rows(ca[fine], tk.r0, tk.r1), 1, dim), w, dim), 1, dim);
+                if (cfg.any_periodic() && !p.empty())
+                {
+                    // the periodic images of the fine cells graduate the other side of the domain too (graduation.hpp:309-320):
+                    // translate(fine, N(fine)) expanded and coarsened twice == translate(p, N(fine - 2)), N(fine) being a multiple of 4
+                    LevelSet all = p;
+                    for (const auto& dv : cfg.periodic_directions(fine - 2))
+                    {
+                        all = set_union(all, translate(p, dv[0], dv[1], dv[2]));
+                    }
+                    p = std::move(all);
+                }
                 for (int cl = fine - 2;; --cl)
                 {
                     if (!p.empty() && !ca[cl].empty())

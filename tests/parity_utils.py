@@ -14,12 +14,17 @@ import samurai_oracle as so  # noqa: E402
 REL_TOL = 1e-12  # BASELINE.json north_star: fields within 1e-12 relative in fp64
 
 
-def oracle_cfg(dim, min_level, max_level, pred_radius):
-    return so.MeshConfig(dim=dim, min_level=min_level, max_level=max_level, pred_radius=pred_radius)
+def oracle_cfg(dim, min_level, max_level, pred_radius, periodic=None, msr=1):
+    return so.MeshConfig(dim=dim, min_level=min_level, max_level=max_level, pred_radius=pred_radius, periodic=periodic, max_stencil_radius=msr)
 
 
-def product_cfg(dim, min_level, max_level, pred_radius):
-    return (sb.mesh_config(dim, pred_radius).min_level(min_level).max_level(max_level).max_stencil_size(2).disable_minimal_ghost_width())
+def product_cfg(dim, min_level, max_level, pred_radius, periodic=None, msr=1):
+    cfg = sb.mesh_config(dim, pred_radius).min_level(min_level).max_level(max_level)
+    if msr == 1:
+        cfg = cfg.max_stencil_size(2).disable_minimal_ghost_width()
+    if periodic is not None:
+        cfg = cfg.periodic(list(periodic))
+    return cfg
 
 
 def oracle_sub(omesh, mesh_id):
@@ -116,14 +121,14 @@ def adapt_both(adapt, mcfg, pmesh, omesh, ou, bc, eps, regularity, relative_deta
 
 def run_advection_parity(dim=2, min_level=2, max_level=6, pred_radius=1, steps=3, eps=2e-4, regularity=1.0, device=0, verbose=False,
                          scheme="upwind", relative_detail=False, amplitude=1.0, init="disc", trace_tags=False, a=None, cfl=None,
-                         discs=None, check_ghosts=True):
+                         discs=None, check_ghosts=True, periodic=None, msr=1):
     """demos/FiniteVolume/advection_2d.cpp time loop on the GPU, checked against the oracle at every step:
     meshes bit-identical (cells + all ghosts + storage offsets), fields within 1e-12 relative; with trace_tags also the
     tag and detail arrays of every harten iteration.  `discs`: [(center, radius, value)] initial condition
     (scalar_burgers_2d.cpp:20-50); init="square": README.md:111-118."""
     if not sb.initialize(device):
         raise sb.SamuraiError("a CUDA device is required")
-    ocfg = oracle_cfg(dim, min_level, max_level, pred_radius)
+    ocfg = oracle_cfg(dim, min_level, max_level, pred_radius, periodic, msr)
     bc = so.Bc("dirichlet", 0.0)
     omesh = so.Mesh.uniform(ocfg)
     if discs is not None:
@@ -136,12 +141,13 @@ def run_advection_parity(dim=2, min_level=2, max_level=6, pred_radius=1, steps=3
     else:
         ou = so.init_disc(omesh, [0.3] * dim, 0.2) * amplitude
 
-    pmesh = sb.MRMesh.make_mesh([0.0] * dim, [1.0] * dim, product_cfg(dim, min_level, max_level, pred_radius))
+    pmesh = sb.MRMesh.make_mesh([0.0] * dim, [1.0] * dim, product_cfg(dim, min_level, max_level, pred_radius, periodic, msr))
     assert_same_mesh(pmesh, omesh)
     u = sb.make_scalar_field("u", pmesh)
     u.resize()
     u.upload(ou)
-    sb.make_bc(u, sb.DIRICHLET, 0.0)
+    if periodic is None or not all(periodic):
+        sb.make_bc(u, sb.DIRICHLET, 0.0)
     unp1 = sb.make_scalar_field("unp1", pmesh)
     adapt = sb.make_MRAdapt(u)
     mcfg = sb.mra_config().epsilon(eps).regularity(regularity).relative_detail(relative_detail)
