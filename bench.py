@@ -406,6 +406,54 @@ def uniform_full_step(sb, torch, dim, level, iters=10):
             "d2h_bytes_per_step": st["d2h_bytes"] / iters, "harten_iterations_per_step": st["harten_iterations"] / iters}
 
 
+def config4_3d(sb, torch, dist, args, world, barrier):
+    """BASELINE.json configs[3]: advection_3d (levels 4-`--level-3d`, eps 2e-4, ball r=0.2 at 0.3, a=(1,1,1), cfl 0.25), the case
+    the multi-GPU efficiency target is stated on.  Same loop and same timing rules as the headline; every rank calls this."""
+    class A3:
+        pass
+
+    a3 = A3()
+    a3.dim, a3.min_level, a3.max_level, a3.eps = 3, args.min_level, args.level_3d, args.eps
+    t0 = time.perf_counter()
+    sim = Sim(sb, a3)
+    sim.adapt(sim.mra)
+    sb.synchronize()
+    init_secs = time.perf_counter() - t0
+    if world > 1:
+        sb.mg_rebalance(sim.u)
+    for _ in range(3):
+        sim.step()
+    if world > 1:
+        sb.mg_rebalance(sim.u)
+    sb.stats(reset=True)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    cells = 0
+    steps = args.steps_3d
+    for _ in range(steps):
+        cells += sim.step()
+    e1.record()
+    barrier()
+    secs = e0.elapsed_time(e1) * 1e-3
+    st = sb.stats()
+    if world > 1:
+        t = torch.tensor([secs], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        secs = t.item()
+    out = {"workload": f"advection_3d min_level={a3.min_level} max_level={a3.max_level} eps={a3.eps} pred_radius=1 Dirichlet(0) ball r=0.2@(0.3,..), "
+                       f"a=(1,1,1), cfl=0.25; one step = MRadaptation + update_ghost_mr + upwind + swap",
+           "n_gpus": world, "steps": steps, "value": cells / secs, "unit": UNIT, "ms_per_step": 1e3 * secs / steps,
+           "leaves": sim.mesh.nb_cells(), "reference_cells": sim.mesh.nb_cells(sb.REFERENCE), "initial_adaptation_s": init_secs,
+           "split_ms_per_step": {"device": 1e3 * st["device_seconds"] / steps, "host_mesh": 1e3 * st["host_mesh_seconds"] / steps,
+                                 "host_batches": 1e3 * st["host_batch_seconds"] / steps},
+           "gpu_launches_per_step": st["kernel_launches"] / steps}
+    sim.u.destroy()
+    sim.unp1.destroy()
+    sim.mesh.destroy()
+    return out
+
+
 def run_product(args):
     import torch
     import torch.distributed as dist
@@ -424,6 +472,8 @@ def run_product(args):
         # every field / detail / tag buffer lives in a per-rank pool mapped into the peers: size it for the uniform
         # max_level start mesh (reference cells ~ 4/3 * 4^L; u, its transfer twin, unp1, detail, tags) with slack
         nref0 = int((2 ** args.dim) ** args.max_level * (1.35 if args.dim == 2 else 1.16))
+        if args.level_3d > 0:
+            nref0 = max(nref0, int(8 ** args.level_3d * 1.16))
         pool = int(nref0 * (8 * 4 + 1) * 1.6) + (1 << 28)
         ok = sb.initialize_multi(rank, world, device=local_rank, pool_bytes=pool)
     else:
@@ -509,6 +559,32 @@ def run_product(args):
     if not args.no_cpu_baseline:
         cpu, parity = parity_and_cpu_baseline(sb, sim, args, rank, world, barrier)
 
+    # ---- dominant kernel of the loop, measured live (collective at N > 1: every rank launches the same sequence) ----------------
+    mg_prof = None
+    if world > 1:
+        sb.profile_enable(True)
+        for _ in range(3):
+            sim.step()
+        prof = sb.profile_get()
+        wf_bytes = sb.profile_bytes("wavefront")
+        sb.profile_enable(False)
+        fam_time = {k: v[1] for k, v in prof.items() if v[0]}
+        if fam_time:
+            total_prof = sum(fam_time.values())
+            dom = max(fam_time, key=fam_time.get)
+            n_l, s_l, c_l = prof[dom]
+            dom_bytes = wf_bytes if dom == "wavefront" else alg_bytes_per_cell(dom, args.dim) * c_l
+            mg_prof = {"bound": "hbm", "kernel": dom, "achieved": dom_bytes / s_l / 1e9, "peak": peak_gbs, "unit": "GB/s", "frac": dom_bytes / s_l / 1e9 / peak_gbs,
+                       "traffic": None, "peak_source": peak_src, "share_of_device_time": fam_time[dom] / total_prof, "launches": n_l,
+                       "us_per_launch": 1e6 * s_l / n_l, "algorithmic_bytes_per_launch": dom_bytes / n_l,
+                       "note": "rank 0's share of the phases (its slab); the launch spans the cross-GPU phase barriers, so its duration includes "
+                               "waiting for the slowest rank; latency bound like the single-GPU launch"}
+
+    # ---- BASELINE configs[3]: the 3D case (every rank) -----------------------------------------------------------------------
+    c4 = None
+    if args.level_3d > 0:
+        c4 = config4_3d(sb, torch, dist if world > 1 else None, args, world, barrier)
+
     line = None
     if rank == 0 and world > 1:
         line = {
@@ -518,14 +594,16 @@ def run_product(args):
             "config": {"workload": workload_string(args),
                        "leaves": leaves_now, "reference_cells": ref_now,
                        "parallelism": f"{world} leaf-balanced slabs (one per GPU), halo values stored into the peers by the producing kernels over "
-                                      f"NVLink (CUDA IPC), flag barrier per phase, tags replicated; same global problem as N=1"},
+                                      f"NVLink (CUDA IPC); one fused cooperative launch per ghost update / harten iteration on every GPU, its phase "
+                                      f"barrier exchanging flags with the peers; tags replicated; host mesh work replicated on every rank "
+                                      f"({max(1, (os.cpu_count() or 1) // world)} host threads per rank); same global problem as N=1"},
             "split_ms_per_step": {"device": 1e3 * st["device_seconds"] / args.steps, "host_mesh": 1e3 * st["host_mesh_seconds"] / args.steps,
                                   "host_batches": 1e3 * st["host_batch_seconds"] / args.steps},
             "gpu_launches": int(st["kernel_launches"]),
             "initial_adaptation_s": init_secs,
             "e2e": {"value": e2e_cells / e2e_secs, "unit": UNIT, "h2d_bytes_per_step": int(st_e2e["h2d_bytes"] / args.steps),
                     "d2h_bytes_per_step": int(st_e2e["d2h_bytes"] / args.steps), "ms_per_step": 1e3 * e2e_secs / args.steps},
-            "roofline": None, "cpu_baseline": cpu, "parity": parity, "clocks": clocks,
+            "roofline": mg_prof, "cpu_baseline": cpu, "parity": parity, "config4_3d": c4, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
     elif rank == 0:
@@ -632,6 +710,7 @@ def run_product(args):
             "kernel_families_per_sweep_launches": families,
             "uniform_sweep": sweep,
             "uniform_full_step": ustep,
+            "config4_3d": c4,
             "flux_scheme_on_adapted_mesh": flux,
             "cpu_baseline": cpu,
             "parity": parity,
@@ -748,6 +827,8 @@ def main():
     ap.add_argument("--sweep-level", type=int, default=13)
     ap.add_argument("--cpu-steps", type=int, default=10, help="steps of the compiled CPU path timed as cpu_baseline (and compared with the product)")
     ap.add_argument("--numpy-parity-steps", type=int, default=1, help="steps of the numpy oracle compared with the product at full size (N=1)")
+    ap.add_argument("--level-3d", type=int, default=9, help="max_level of the 3D advection block (BASELINE configs[3]; 0: skip)")
+    ap.add_argument("--steps-3d", type=int, default=20)
     ap.add_argument("--sweep-level-3d", type=int, default=9, help="level of the 3D uniform full-step measurement (0: skip)")
     ap.add_argument("--ref-max-level", type=int, default=14, help="largest max_level the CPU reference arm samples")
     ap.add_argument("--no-cpu-baseline", action="store_true")

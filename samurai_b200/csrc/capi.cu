@@ -287,6 +287,7 @@ namespace smr
         void* wf_dev       = nullptr;
         unsigned* wf_barrier   = nullptr;
         unsigned wf_barrier_at = 0;
+        unsigned wf_release_at = 0; // counter[1]: multi-GPU release word (kernels.cuh: wf_mg_barrier)
         unsigned* wf_error_host = nullptr; // pinned copy of the wavefront error word (kernels.cuh: SMR_WF_ERROR_WORD)
         int wf_next        = 0;
         cudaEvent_t wf_done[16] = {};
@@ -815,6 +816,7 @@ namespace smr
         uint64_t bytes = 0;
         int dim       = 2;
         bool open     = false;
+        bool keep_empty = false; // multi-GPU: phases without local work still count (every rank crosses the same barriers)
 
         void begin_phase()
         {
@@ -824,7 +826,7 @@ namespace smr
 
         void end_phase()
         {
-            if (open && phases.back().n_jobs == 0)
+            if (open && phases.back().n_jobs == 0 && !keep_empty)
             {
                 phases.pop_back();
             }
@@ -919,9 +921,17 @@ namespace smr
         }
     };
 
+    // multi-GPU: every rank walks the SAME phase list (empty phases are kept, nothing is run serially or split off), the phase
+    // barrier exchanges flags with the peers (kernels.cuh: wf_mg_barrier); SMR_WF_MG=0 falls back to one launch per sweep
+    static bool wf_multi()
+    {
+        return g.mg_world > 1 && g.mg_connected;
+    }
+
     static bool wf_enabled()
     {
-        return g.fuse && g.mg_world == 1;
+        static const bool mg_off = std::getenv("SMR_WF_MG") != nullptr && std::getenv("SMR_WF_MG")[0] == '0';
+        return g.fuse && (g.mg_world == 1 || (g.mg_connected && !mg_off));
     }
 
     template <int DIM, int RADIUS>
@@ -975,6 +985,7 @@ namespace smr
             *g.wf_error_host  = 0;
             cudaMemsetAsync(g.wf_barrier, 0, 256, g.stream);
             g.wf_barrier_at = 0;
+            g.wf_release_at = 0;
             throw CudaError("fused wavefront: grid barrier timed out (target " + std::to_string(at) + "); results of that launch are invalid");
         }
     }
@@ -1177,7 +1188,8 @@ namespace smr
             return;
         }
         wf_init();
-        static const bool no_split = std::getenv("SMR_WF_NO_SPLIT") != nullptr;
+        static const bool no_split_env = std::getenv("SMR_WF_NO_SPLIT") != nullptr;
+        const bool no_split            = no_split_env || wf_multi();
         const int wide_at = WF_WIDE_FACTOR * g.wf_grid;
         size_t p = 0;
         while (p < wb.phases.size())
@@ -1241,7 +1253,7 @@ namespace smr
                 ph.total_ctas = total;
             }
             static const bool no_serial = std::getenv("SMR_WF_NO_SERIAL") != nullptr;
-            ph.pad = (!no_serial && ph.total_ctas <= WF_SERIAL_CTAS) ? 1 : 0;
+            ph.pad = (!no_serial && !wf_multi() && ph.total_ctas <= WF_SERIAL_CTAS) ? 1 : 0;
         }
         static const bool trace = std::getenv("SMR_WF_TRACE") != nullptr;
         if (trace)
@@ -1285,6 +1297,9 @@ namespace smr
         }
         a.barrier      = g.wf_barrier;
         a.barrier_base = g.wf_barrier_at;
+        a.mg_world     = wf_multi() ? g.mg_world : 1;
+        a.release_base = g.wf_release_at;
+        a.mg_epoch_base = g.epoch;
         static void* d_trace = nullptr;
         if (trace)
         {
@@ -1318,6 +1333,11 @@ namespace smr
         }
         // only a launch that was accepted advances the expected counter value (wraps modulo 2^32 like the device counter)
         g.wf_barrier_at += n_barriers * static_cast<unsigned>(grid);
+        if (wf_multi())
+        {
+            g.wf_release_at += n_barriers;
+            g.epoch += n_barriers; // the kernel used epochs g.epoch + 1 ... g.epoch + n_barriers on every rank
+        }
         SMR_CUDA(cudaEventRecord(g.wf_done[slot], g.stream));
         ++g.stats.kernel_launches;
         if (g.profile)
@@ -1325,6 +1345,7 @@ namespace smr
             g.prof_bytes[SMR_FAM_WAVEFRONT] += wb.bytes;
         }
         prof_end(SMR_FAM_WAVEFRONT, wb.units);
+        mg_barrier(); // multi-GPU: the last phase's peer stores have landed everywhere before anything else is queued
         if (trace)
         {
             std::vector<unsigned long long> t(wb.phases.size() + 1);
@@ -1353,7 +1374,7 @@ namespace smr
             for (int k = 0; k < cfg.dim; ++k)
             {
                 const Batch& b = mo.plan.down[level].per[k];
-                if (cfg.periodic[k] && !b.empty())
+                if (cfg.periodic[k] && (!b.empty() || wb.keep_empty))
                 {
                     wb.begin_phase();
                     for (int f = 0; f < nfields; ++f)
@@ -1375,7 +1396,7 @@ namespace smr
             {
                 periodic_phases(level);
             }
-            if (!(ph.bc.empty() && ph.proj.empty()))
+            if (!(ph.bc.empty() && ph.proj.empty()) || wb.keep_empty)
             {
                 wb.begin_phase();
                 extra(index++);
@@ -1393,7 +1414,7 @@ namespace smr
         }
         for (int level = 1; level <= cfg.max_level; ++level)
         {
-            if (!mo.plan.pred[level].empty())
+            if (!mo.plan.pred[level].empty() || wb.keep_empty)
             {
                 wb.begin_phase();
                 extra(index++);
@@ -1462,6 +1483,7 @@ namespace smr
         {
             WfBuilder wb;
             wb.dim = cfg.dim;
+            wb.keep_empty = wf_multi();
             WfArgs a{};
             std::vector<FieldObj*> one{&f};
             wf_set_fields(a, one);
@@ -1647,10 +1669,11 @@ namespace smr
             a.change_flag = reinterpret_cast<unsigned*>(tag + flag_at);
             a.n        = n;
             a.ncomp    = ncomp;
-            a.mask_all = 0;
+            a.mask_all = mo.filter.mask_all();
             a.tp       = tp;
             WfBuilder wb;
             wb.dim = dim;
+            wb.keep_empty = wf_multi();
             wf_add_ghost_phases(wb, mo, ncomp,
                                 [&](int index)
                                 {
@@ -1679,6 +1702,7 @@ namespace smr
                 wf_run(wb, a, arena, dim, cfg.pred_radius);
                 wb = WfBuilder();
                 wb.dim = dim;
+            wb.keep_empty = wf_multi();
                 relative_detail_pass(mo, fields, detail, n);
             }
             wb.begin_phase();
@@ -1688,7 +1712,7 @@ namespace smr
             {
                 for (int k = 0; k < dim; ++k) // update_tag_periodic(level), mr/adapt.hpp:353
                 {
-                    if (cfg.periodic[k] && !mo.plan.down[level].per[k].empty())
+                    if (cfg.periodic[k] && (!mo.plan.down[level].per[k].empty() || wb.keep_empty))
                     {
                         wb.begin_phase();
                         wb.add(WF_TAG_OR, mo.plan.down[level].per[k], 0);
@@ -1885,6 +1909,7 @@ namespace smr
             WfArgs a{};
             WfBuilder wb;
             wb.dim = dim;
+            wb.keep_empty = wf_multi();
             wb.begin_phase();
             for (size_t i = 0; i < fields.size(); ++i)
             {

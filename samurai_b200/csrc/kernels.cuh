@@ -1238,13 +1238,14 @@ namespace smr
         const uint8_t* tag;
         unsigned* flag;
         int min_level, max_level;
+        unsigned mask_all = 0; // multi-GPU: every rank scans its own leaves and raises the flag on all ranks
 
         __device__ __forceinline__ void operator()(const smr_item_fv& it, int k) const
         {
             const uint8_t t = tag[it.c + k];
             if (((t & 4) && it.level < max_level) || ((t & 2) && !(t & 1) && it.level > min_level))
             {
-                *flag = 1u; // benign race: every writer stores the same value
+                mstore(flag, 1u, mask_all); // benign race: every writer stores the same value
             }
         }
 
@@ -1280,7 +1281,7 @@ namespace smr
             }
             if (hit != 0u)
             {
-                *flag = 1u;
+                mstore(flag, 1u, mask_all);
             }
             return true;
         }
@@ -1316,7 +1317,7 @@ namespace smr
             }
             if (hit != 0u)
             {
-                *flag = 1u;
+                mstore(flag, 1u, mask_all);
             }
         }
     };
@@ -1532,6 +1533,11 @@ namespace smr
         unsigned mask_all;
         unsigned* barrier;      // grid barrier counter (monotonic across launches)
         unsigned barrier_base;  // its value when this launch starts
+        // multi-GPU: every phase boundary is also a barrier across the ranks (all run the same phase list).  CTA 0 exchanges
+        // flags with the peers once the local grid has arrived, then releases the local grid through counter[1].
+        int mg_world;                      // 1: single GPU
+        unsigned release_base;             // value of counter[1] when this launch starts
+        unsigned long long mg_epoch_base;  // flag value of this launch's k-th barrier is mg_epoch_base + k
         unsigned long long* trace; // optional: CTA 0 stamps %globaltimer at the start of every phase and at the end
         TagParams tp;
     };
@@ -1570,6 +1576,87 @@ namespace smr
         }
         __syncthreads();
         return s_ok != 0;
+    }
+
+    // Phase boundary across GPUs: local arrival as above; CTA 0 then tells every peer "my rank has finished barrier k" by storing
+    // the epoch into the peer's flag table over NVLink, waits for the same word from every peer, and releases the local grid.
+    // Every thread fences at system scope first, so the halo values it stored into the peers' pools are visible there before the
+    // flag is.  All waits are bounded: a rank that stopped raises the error words instead of hanging the GPUs.
+    __device__ __forceinline__ bool wf_mg_barrier(const WfArgs& a, unsigned k)
+    {
+        __shared__ int s_ok_mg;
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            unsigned* counter     = a.barrier;
+            const unsigned target = a.barrier_base + k * gridDim.x;
+            const unsigned rel    = a.release_base + k;
+            volatile unsigned* vc = reinterpret_cast<volatile unsigned*>(counter);
+            atomicAdd(counter, 1u);
+            bool ok = true;
+            if (blockIdx.x == 0)
+            {
+                for (long long spins = 0; static_cast<int>(vc[0] - target) < 0; ++spins)
+                {
+                    if (spins > (1LL << 28) || vc[SMR_WF_ERROR_WORD] != 0u)
+                    {
+                        ok = false;
+                        break;
+                    }
+                }
+                const unsigned long long epoch = a.mg_epoch_base + k;
+                __threadfence_system();
+                for (int p = 0; ok && p < g_peers.world; ++p)
+                {
+                    if (p != g_peers.rank)
+                    {
+                        volatile unsigned long long* remote = reinterpret_cast<volatile unsigned long long*>(
+                            reinterpret_cast<char*>(g_peers.flags) + g_peers.delta[p]);
+                        remote[g_peers.rank] = epoch;
+                    }
+                }
+                __threadfence_system();
+                volatile unsigned long long* mine = g_peers.flags;
+                for (int p = 0; ok && p < g_peers.world; ++p)
+                {
+                    if (p == g_peers.rank)
+                    {
+                        continue;
+                    }
+                    for (long long spins = 0; mine[p] < epoch; ++spins)
+                    {
+                        if (spins > 400000000LL) // ~ a second
+                        {
+                            *g_peers.error = epoch;
+                            ok             = false;
+                            break;
+                        }
+                    }
+                }
+                if (!ok)
+                {
+                    atomicExch(counter + SMR_WF_ERROR_WORD, target | 1u);
+                }
+                __threadfence_system();
+                atomicExch(counter + 1, rel); // release the local grid (also on failure: the others then see the error word)
+            }
+            else
+            {
+                for (long long spins = 0; static_cast<int>(vc[1] - rel) < 0; ++spins)
+                {
+                    if (spins > (1LL << 30) || vc[SMR_WF_ERROR_WORD] != 0u)
+                    {
+                        atomicExch(counter + SMR_WF_ERROR_WORD, target | 1u);
+                        break;
+                    }
+                }
+            }
+            s_ok_mg = vc[SMR_WF_ERROR_WORD] == 0u;
+            __threadfence_system();
+        }
+        __syncthreads();
+        return s_ok_mg != 0;
     }
 
     template <class Item>
@@ -1648,7 +1735,7 @@ namespace smr
                 wf_zero(a.tag, jb.n_cells, local);
                 break;
             case WF_TAGS_CHANGE:
-                wf_item(wf_view<smr_item_fv>(a.arena, jb), TagsChangeOp{a.tag, a.change_flag, a.tp.min_level, a.tp.max_level}, local, jb.pad != 0, s_prefix);
+                wf_item(wf_view<smr_item_fv>(a.arena, jb), TagsChangeOp{a.tag, a.change_flag, a.tp.min_level, a.tp.max_level, a.mask_all}, local, jb.pad != 0, s_prefix);
                 break;
             case WF_TAG_OR:
                 wf_item(wf_view<smr_item_copy>(a.arena, jb), TagOrOp{a.tag, a.mask_all}, local, jb.pad != 0, s_prefix);
@@ -1791,7 +1878,7 @@ namespace smr
                 else
                 {
                     ++barriers;
-                    if (!wf_grid_barrier(a.barrier, a.barrier_base + barriers * gridDim.x))
+                    if (!(a.mg_world > 1 ? wf_mg_barrier(a, barriers) : wf_grid_barrier(a.barrier, a.barrier_base + barriers * gridDim.x)))
                     {
                         return; // barrier timed out: error word raised, results are invalid and the host will throw
                     }
