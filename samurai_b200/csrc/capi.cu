@@ -1920,6 +1920,7 @@ namespace smr
                 wb.add(WF_PROJ, tpn.proj, static_cast<int>(i));
                 wb.add(WF_PRED, tpn.pred, static_cast<int>(i));
             }
+            mg_barrier(); // multi-GPU: every rank has zeroed its new buffers before any peer stores halo values into them
             wf_run(wb, a, d_tr.p, dim, cfg.pred_radius);
         }
         else
