@@ -764,7 +764,8 @@ def parity_and_cpu_baseline(sb, sim, args, rank, world, barrier):
         tm = cs.times()
         cores = cpu_path.CpuSim.threads()
         cpu_path.CpuSim.set_threads(saved)
-        cpu = {"value": done / secs, "unit": UNIT, "cores": cores, "kind": "port",
+        # at N > 1 the run is only the parity reference (torchrun pins the ranks' host threads, its timing means nothing)
+        cpu = None if world > 1 else {"value": done / secs, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{n_steps} steps from the product's own adapted state ({cs.nb_cells()} leaves); compiled C++/OpenMP port oracle/cpu_path.cpp "
                          f"(-O3 -march=x86-64-v3 -ffp-contract=off), all host threads" + (f"; {world} ranks were idle meanwhile" if world > 1 else ""),
                "ms_per_step": 1e3 * secs / n_steps}
