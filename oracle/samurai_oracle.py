@@ -183,9 +183,10 @@ class MeshConfig:
         if self.periodic is None:
             self.periodic = (False,) * self.dim
         self.periodic = tuple(bool(p) for p in self.periodic)
-        # ghost width 2 is restated for fully periodic meshes only: no boundary extrapolation (bc/apply_field_bc.hpp:499-563) and
-        # no contiguous-boundary graduation rule (graduation.hpp:372-500) are involved there
-        assert self.max_stencil_radius == 1 or (self.max_stencil_radius == 2 and all(self.periodic)), "oracle restates ghost width 1 (2 if periodic)"
+        # ghost width 2: further-ghost extrapolation (bc/apply_field_bc.hpp:499-563), the two-layer corner block (:313-466) and the
+        # contiguous-boundary graduation rule (graduation.hpp:372-500) are restated for boundary conditions that fill ONE layer
+        # (Dirichlet<1> / Neumann<1>); larger widths are not
+        assert self.max_stencil_radius in (1, 2), "oracle restates ghost widths 1 and 2"
         assert self.pred_radius in (0, 1)
 
     def periodic_directions(self, level):
@@ -495,6 +496,8 @@ def update_outer_ghosts(mesh: Mesh, f, bc: Bc, level):
             cc = inter(mesh.cells[level], corner)
             if cc.size:
                 f[mesh.index(level, translate(cc, direction))] = f[mesh.index(level, cc)]
+            if cfg.ghost_width == 2 and cc.size:
+                _corner_block_width2(mesh, f, level, direction, cc)
             # project_corner_below (update_outer_ghost.hpp:267-336)
             if level > 0:
                 for delta_l in (1, 2):
@@ -519,6 +522,73 @@ def update_outer_ghosts(mesh: Mesh, f, bc: Bc, level):
             _apply_field_bc(mesh, f, bc, level, direction)
         if lmin <= level < L:
             _predict_bc(mesh, f, level + 1, direction)
+    # the B.C. fills one ghost layer: the farther ones by polynomial extrapolation (update_outer_ghost.hpp:412-423)
+    if level >= lmin and cfg.ghost_width > 1:
+        for direction in cartesian_directions(dim):
+            if any(direction[d] != 0 and cfg.periodic[d] for d in range(dim)):
+                continue
+            _further_ghosts(mesh, f, level, direction)
+
+
+def _extrapolate4(mesh: Mesh, f, level, centres, direction, target_offset=None):
+    """PolynomialExtrapolation<4> (bc/polynomial_extrapolation.hpp:67-70) on the line stencil -1, 0, 1, 2 along `direction`
+    (stencil.hpp:211-231 rotated by convert_for_direction): u[c + 2 d] = u[c - d] - u[c] * 3 + u[c + d] * 3."""
+    if centres.size == 0:
+        return
+    d = list(direction)
+    u0 = f[mesh.index(level, translate(centres, [-x for x in d]))]
+    u1 = f[mesh.index(level, centres)]
+    u2 = f[mesh.index(level, translate(centres, d))]
+    f[mesh.index(level, translate(centres, [2 * x for x in d]))] = u0 - u1 * 3.0 + u2 * 3.0
+
+
+def _further_ghosts(mesh: Mesh, f, level, direction):
+    """update_further_ghosts_by_polynomial_extrapolation (bc/apply_field_bc.hpp:499-563), ghost width 2, B.C. of stencil 2."""
+    dim = mesh.cfg.dim
+    ref = mesh.ref[level]
+    if ref.size == 0:
+        return
+    d = list(direction)
+    has2 = translate(ref, [-2 * x for x in d])  # cells c with c + 2 d in the reference mesh
+    has1 = translate(ref, [-x for x in d])
+    # 1. beyond the boundary leaves (apply_extrapolation_bc_cells<4>, :125-150)
+    _extrapolate4(mesh, f, level, inter(_bdry_leaves(mesh, level, direction), has2), direction)
+    # 2. beyond the inner ghosts of the boundary layer that lie under finer cells (apply_extrapolation_bc_ghosts<4>, :220-242)
+    inside = ref[mesh.in_domain(level, ref)]
+    layer = inside[~mesh.in_domain(level, translate(inside, d))]  # domain \ translate(domain, -direction)
+    cand = inter(inter(inter(layer, has2), has1), mesh.union[level])
+    _extrapolate4(mesh, f, level, diff(cand, mesh.cells[level]), direction)
+
+
+def _corner_block_width2(mesh: Mesh, f, level, direction, cc):
+    """update_outer_corners_by_polynomial_extrapolation for ghost width 2 (bc/apply_field_bc.hpp:313-466): the second diagonal ghost
+    by the 4-point extrapolation along the diagonal, then the off-diagonal ghosts of the corner block copied from the diagonal ones."""
+    dim = mesh.cfg.dim
+    d = list(direction)
+    ref = mesh.ref[level]
+    # step 1, layer 2: needs the farthest ghost (apply_extrapolation_bc_cells<4>)
+    c2 = inter(cc, translate(ref, [-2 * x for x in d]))
+    _extrapolate4(mesh, f, level, c2, direction)
+    # step 2: for layer k the diagonal ghost corner + k d is copied to the block cells whose offsets along the other non-zero
+    # dimensions are g_p - (k - 1), g_p in {0, 1}, not all equal to k - 1
+    nz = [k for k in range(dim) if d[k] != 0]
+    if len(nz) < 2:
+        return
+    gw = 2
+    for k in (1, 2):
+        src = translate(cc, [k * x for x in d])
+        for combo in itertools.product(range(gw), repeat=len(nz) - 1):
+            # the reference enumerates g_1 fastest (combo index modulo ghost_width first)
+            g = list(reversed(combo))
+            delta = [0] * dim
+            for p in range(1, len(nz)):
+                delta[nz[p]] += (g[p - 1] - (k - 1)) * d[nz[p]]
+            if not any(delta):
+                continue
+            dst = translate(src, delta)
+            ok = mesh.contains(level, dst) & mesh.contains(level, src)
+            if ok.any():
+                f[mesh.index(level, dst[ok])] = f[mesh.index(level, src[ok])]
 
 
 def _project_bc(mesh: Mesh, f, level, direction):
@@ -805,6 +875,25 @@ def make_graduation(cfg: MeshConfig, ca):
                         break
                     proj = coarsen(proj, 1, dim)
                     coarse_level -= 1
+        # cells two steps inward of a boundary leaf must not lie in a coarser leaf (graduation.hpp:372-455, max_stencil_radius 2:
+        # n_contiguous_boundary_cells = max(2, 2 * (2 - 2)) = 2; the level -> level + 1 part only exists for radius > 2)
+        if cfg.max_stencil_radius == 2:
+            for direction in cartesian_directions(dim):
+                if any(direction[k] != 0 and cfg.periodic[k] for k in range(dim)):
+                    continue
+                for level in range(hi, lo, -1):
+                    if ca[level].size == 0 or ca[level - 1].size == 0:
+                        continue
+                    k = ca[level]
+                    c = unpack(translate(k, direction), dim)
+                    outside = np.zeros(k.size, dtype=bool)
+                    for a in range(dim):
+                        outside |= (c[:, a] < 0) | (c[:, a] >= (cfg.n_cells0[a] << level))
+                    bdry = k[outside]
+                    if bdry.size:
+                        r = inter(coarsen(translate(bdry, [-2 * x for x in direction]), 1, dim), ca[level - 1])
+                        if r.size:
+                            out[level - 1].append(r)
         if not any(out):
             return ca
         rem = [union(*o) if o else EMPTY for o in out]

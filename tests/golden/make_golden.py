@@ -37,3 +37,18 @@ if __name__ == "__main__":
     out = os.path.join(HERE, "heat_explicit.npz")
     np.savez_compressed(out, level=level.astype(np.int8), idx=idx.astype(np.int32), u=h5.read("/mesh/fields/u"))
     print(out, len(level), os.path.getsize(out))
+
+    # burgers_mra.cpp --nfiles=1 --min-level=2 --max-level=9 --init-sol=hat --mr-eps=1e-5 (tests/test_demo_finite_volume.py:191-207): 1D,
+    # box [-2, 3], max_stencil_radius 2 (ghost width 2), graduation width 2, Dirichlet<1>(0), regularity 0, scheme = 0.5 * make_convection_upwind
+    # (non-linear), cfl 0.95, Tf 0.1; the file without the max-level-flux option
+    h5 = h5mini.H5File(REF + "test_finite_volume_demo_mra_burgers_hat.h5")
+    pts = h5.read("/mesh/points")
+    conn = h5.read("/mesh/connectivity").reshape(-1, 2).astype(np.int64)
+    lo = pts[conn].min(axis=1)[:, 0]
+    level = h5.read("/mesh/fields/level").astype(np.int64)
+    length = 5.0 / (1 << level)
+    idx = np.rint((lo + 2.0) / length).astype(np.int64)
+    assert np.allclose(pts[conn].max(axis=1)[:, 0] - lo, length)
+    out = os.path.join(HERE, "mra_burgers_hat.npz")
+    np.savez_compressed(out, level=level.astype(np.int8), idx=idx.astype(np.int32)[:, None], u=h5.read("/mesh/fields/u"))
+    print(out, len(level), os.path.getsize(out))

@@ -117,3 +117,52 @@ def test_flux_schemes_on_adapted_meshes(dim, lo, hi):
     for out in (so.flux_linhom_apply(mesh, u, so.diffusion_order2_coeffs([1.0] * dim)),
                 so.flux_nonlin_apply(mesh, u, so.burgers_upwind_flux(0.5))):
         assert abs(np.sum(out[leaves] * vol)) < 1e-12 * max(1.0, np.max(np.abs(out[leaves])))
+
+
+def test_oracle_matches_reference_mra_burgers_hat_golden():
+    """demos/FiniteVolume/burgers_mra.cpp with the reference test's arguments (tests/test_demo_finite_volume.py:191-207:
+    --nfiles=1 --min-level=2 --max-level=9 --init-sol=hat --mr-eps=1e-5): 1D, box [-2, 3], max_stencil_radius 2 (the library's
+    default ghost width: further-ghost polynomial extrapolation, contiguous-boundary graduation rule), graduation width 2,
+    Dirichlet<1>(0), regularity 0, `unp1 = u - dt * scheme(u)` with scheme = 0.5 * make_convection_upwind<Field>() (the NON-LINEAR
+    flux-based scheme), cfl 0.95, Tf 0.1.  Against the reference's own test_finite_volume_demo_mra_burgers_hat.h5
+    (tests/golden/mra_burgers_hat.npz): mesh identical, values within 1e-15."""
+    g = np.load(os.path.join(GOLD, "mra_burgers_hat.npz"))
+
+    def hat(x):  # hat_exact_solution(x, 0), burgers_mra.cpp:17-47
+        out = np.zeros_like(x)
+        m1 = (x > -1) & (x < 0)
+        out[m1] = (1.0 / (0.0 - -1.0)) * (x[m1] - -1.0)
+        m2 = (x >= 0) & (x < 1)
+        out[m2] = (-1.0 / (1.0 - 0.0)) * (x[m2] - 0.0) + 1.0
+        return out
+
+    cfg = so.MeshConfig(dim=1, min_level=2, max_level=9, pred_radius=1, max_stencil_radius=2, graduation_width=2, origin=(-2.0,), scaling=5.0)
+    bc = so.Bc("dirichlet", 0.0)
+    mesh = so.Mesh.uniform(cfg)
+    L = cfg.max_level
+    u = np.zeros(mesh.nref)
+    u[mesh.index(L, mesh.cells[L])] = hat(mesh.cell_centers(L, mesh.cells[L])[:, 0])
+    eps, reg = 1e-5, 0.0
+    dt = 0.95 * cfg.cell_length(L)
+    Tf = 0.1
+    mesh, u = so.adapt(mesh, u, bc, eps, reg)
+    flux = so.burgers_upwind_flux(0.5)
+    t, nt = 0.0, 0
+    while t != Tf:
+        t += dt
+        if t > Tf:
+            dt += Tf - t
+            t = Tf
+        mesh, u = so.adapt(mesh, u, bc, eps, reg)
+        so.update_ghost_mr(mesh, u, bc)
+        rhs = so.flux_nonlin_apply(mesh, u, flux)
+        unp1 = np.full(mesh.nref, np.nan)
+        for l in mesh.leaf_levels():
+            i = mesh.index(l, mesh.cells[l])
+            unp1[i] = u[i] - dt * rhs[i]
+        u = unp1
+        nt += 1
+    assert nt == 11
+    lv, co, ix = mesh.leaf_table()
+    assert lv.size == g["level"].size and np.array_equal(lv, g["level"]) and np.array_equal(co, g["idx"]), "mesh differs from the reference golden"
+    assert np.max(np.abs(u[ix] - g["u"])) <= 1e-15
