@@ -484,6 +484,10 @@ namespace
             {
                 f[it.dst] = S.bc_type == SMR_BCTYPE_DIRICHLET ? 2 * S.bc_value - f[s[0]] : it.coef * S.bc_value + f[s[0]];
             }
+            else if (kind == SMR_BC_EXTRAP4) // bc/polynomial_extrapolation.hpp:67-70
+            {
+                f[it.dst] = f[s[0]] - f[s[1]] * 3.0 + f[s[2]] * 3.0;
+            }
             else
             {
                 double sum = 0.0;
@@ -523,6 +527,7 @@ namespace
             const GhostPhase& ph = S.plan.down[level];
             boundary(S, ph.bc, f);
             projection(S.mesh, S.mesh, dim, seeds_of(S.plan.arena, ph.proj), f, f);
+            boundary(S, ph.bc2, f); // second ghost layer (ghost width 2): reads the first layer
         }
         for (int level = 1; level <= S.cfg.max_level; ++level)
         {

@@ -1229,6 +1229,7 @@ namespace smr
     struct GhostPhase
     {
         Batch bc;     // extrapolated corners(level) + corner copies from level+1 + project_bc(level) + BC values(level, level+1 children)
+        Batch bc2;    // ghost width 2: second ghost layer by polynomial extrapolation and the rest of the corner block; reads what `bc` wrote
         Batch proj;   // projection level -> level-1
         Batch per[3]; // periodic ghosts of the level, one batch per periodic dimension (update_ghost_periodic: the dimensions are
                       // processed one after the other, the later ones copy ghosts the earlier ones filled)
@@ -1286,6 +1287,14 @@ namespace smr
         {
             items.push_back({dst, coef, SMR_BC_VALUE | cur_mask, 1, static_cast<int64_t>(srcs.size())});
             srcs.push_back(src);
+        }
+
+        void extrap4(int64_t dst, int64_t s0, int64_t s1, int64_t s2)
+        {
+            items.push_back({dst, 0.0, SMR_BC_EXTRAP4 | cur_mask, 3, static_cast<int64_t>(srcs.size())});
+            srcs.push_back(s0);
+            srcs.push_back(s1);
+            srcs.push_back(s2);
         }
 
         void begin_avg(int64_t dst)
@@ -1358,6 +1367,7 @@ namespace smr
     struct PhaseItems
     {
         BcBuilder bc;
+        BcBuilder bc2;
         std::vector<smr_seed> proj; // seeds at the coarse level
         std::vector<smr_item_copy> per[3];
     };
@@ -1453,6 +1463,81 @@ namespace smr
         }
     }
 
+    // Ghost width 2, corner leaf (x, y, z) of diagonal direction d (bc/apply_field_bc.hpp:313-466): the second diagonal ghost by the
+    // 4-point extrapolation along the diagonal, then the off-diagonal ghosts of the corner block copied from the diagonal ghost of
+    // their layer.  The copies of layer 2 repeat the extrapolation (same operands, same result) instead of reading the diagonal ghost,
+    // which the same phase writes.
+    inline void corner_block_width2(const Mesh& m, int level, const Dir& d, int x, int y, int z, const PlanFilter& flt, BcBuilder& g)
+    {
+        const int dim       = m.cfg.dim;
+        const LevelSet& ref = m.ref[level];
+        g.flt               = &flt;
+        auto off = [&](int cx, int cy, int cz) { return ref.offset_of(mk_key(cy, cz), cx, cx); };
+        const int64_t sm = off(x - d.v[0], y - d.v[1], z - d.v[2]);
+        const int64_t s0 = off(x, y, z);
+        const int64_t s1 = off(x + d.v[0], y + d.v[1], z + d.v[2]);
+        const int64_t s2 = off(x + 2 * d.v[0], y + 2 * d.v[1], z + 2 * d.v[2]);
+        const bool layer2 = s2 >= 0; // apply_extrapolation_bc_cells<4>: only where the farthest ghost exists
+        if (layer2 && (sm < 0 || s0 < 0 || s1 < 0))
+        {
+            missing("corner extrapolation stencil", level, x, y, z);
+        }
+        if (layer2 && g.target(level, y + 2 * d.v[1], z + 2 * d.v[2]))
+        {
+            g.extrap4(s2, sm, s0, s1);
+        }
+        int nz[3], n_nz = 0;
+        for (int k = 0; k < dim; ++k)
+        {
+            if (d.v[k] != 0)
+            {
+                nz[n_nz++] = k;
+            }
+        }
+        if (n_nz < 2)
+        {
+            return;
+        }
+        const int combos = n_nz == 2 ? 2 : 4; // ghost_width^(n_nz - 1)
+        for (int k = 1; k <= 2; ++k)
+        {
+            if (k == 2 && !layer2)
+            {
+                continue;
+            }
+            const int sx = x + k * d.v[0], sy = y + k * d.v[1], sz = z + k * d.v[2];
+            for (int combo = 0; combo < combos; ++combo)
+            {
+                int delta[3] = {0, 0, 0};
+                int tmp      = combo;
+                for (int p = 1; p < n_nz; ++p)
+                {
+                    const int gp = tmp % 2;
+                    tmp /= 2;
+                    delta[nz[p]] += (gp - (k - 1)) * d.v[nz[p]];
+                }
+                if (delta[0] == 0 && delta[1] == 0 && delta[2] == 0)
+                {
+                    continue;
+                }
+                const int tx = sx + delta[0], ty = sy + delta[1], tz = sz + delta[2];
+                const int64_t dst = off(tx, ty, tz);
+                if (dst < 0 || !g.target(level, ty, tz))
+                {
+                    continue;
+                }
+                if (k == 1)
+                {
+                    g.copy(dst, s1);
+                }
+                else
+                {
+                    g.extrap4(dst, sm, s0, s1);
+                }
+            }
+        }
+    }
+
     inline void build_ghost_phase(const Mesh& m, int level, const PlanFilter& flt, PhaseItems& out)
     {
         const MeshConfig& cfg = m.cfg;
@@ -1504,6 +1589,10 @@ namespace smr
                                       if (g.target(level, y + d.v[1], z + d.v[2]))
                                       {
                                           g.copy(dst, need(ref, "corner cell", level, y, z, x, x));
+                                      }
+                                      if (cfg.ghost_width() == 2)
+                                      {
+                                          corner_block_width2(m, level, d, x, y, z, flt, out.bc2);
                                       }
                                   });
                 }
@@ -1636,6 +1725,50 @@ namespace smr
                         }
                     }
                 }
+            }
+        }
+        // the boundary condition fills one ghost layer, the second one is extrapolated (update_outer_ghost.hpp:412-423,
+        // bc/apply_field_bc.hpp:499-563); these records read the first layer and therefore run one phase later (GhostPhase::bc2)
+        if (cfg.ghost_width() == 2 && level >= lmin && !ref.empty())
+        {
+            out.bc2.flt = &flt;
+            for (const Dir& d : cartesian_directions(dim))
+            {
+                if (touches_periodic(d))
+                {
+                    continue;
+                }
+                const LevelSet has1 = translate(ref, -d.v[0], -d.v[1], -d.v[2]);
+                const LevelSet has2 = translate(ref, -2 * d.v[0], -2 * d.v[1], -2 * d.v[2]);
+                auto emit = [&](const LevelSet& centres)
+                {
+                    for_each_cell(centres,
+                                  [&](int x, int y, int z)
+                                  {
+                                      const int gx = x + 2 * d.v[0], gy = y + 2 * d.v[1], gz = z + 2 * d.v[2];
+                                      if (!out.bc2.target(level, gy, gz))
+                                      {
+                                          return;
+                                      }
+                                      out.bc2.extrap4(need(ref, "second ghost", level, gy, gz, gx, gx),
+                                                      need(ref, "extrapolation stencil -1", level, y - d.v[1], z - d.v[2], x - d.v[0], x - d.v[0]),
+                                                      need(ref, "extrapolation stencil 0", level, y, z, x, x),
+                                                      need(ref, "extrapolation stencil +1", level, y + d.v[1], z + d.v[2], x + d.v[0], x + d.v[0]));
+                                  });
+                };
+                // 1. beyond the boundary leaves (apply_extrapolation_bc_cells<4>)
+                emit(set_inter(boundary_leaves(m, level, d), has2));
+                // 2. beyond the cells of the boundary layer that lie under finer leaves (apply_extrapolation_bc_ghosts<4>)
+                int lo[3], hi[3];
+                m.domain_box(level, 0, lo, hi);
+                for (int k = 0; k < 3; ++k)
+                {
+                    lo[k] -= d.v[k];
+                    hi[k] -= d.v[k];
+                }
+                LevelSet layer = minus_box(m.in_domain(ref, level), dim, lo, hi); // domain \ translate(domain, -d)
+                LevelSet cand  = set_inter(set_inter(set_inter(layer, has2), has1), m.uni[level]);
+                emit(set_diff(cand, m.cells[level]));
             }
         }
         if (level > 0 && !ref.empty())
@@ -1818,7 +1951,7 @@ namespace smr
         p_tag_all.inclusive      = true;
         p_detail.n_groups = p_tag_all.n_groups = nlev; // cumulative counts are indexed by level
         std::vector<PendingSeeds> p_proj(nlev), p_pred(nlev), p_tag(nlev);
-        std::vector<PendingBc> p_bc(nlev);
+        std::vector<PendingBc> p_bc(nlev), p_bc2(nlev);
         std::vector<Pending<smr_item_copy>> p_per(static_cast<size_t>(3 * nlev));
         for (int l = 0; l < nlev; ++l)
         {
@@ -1831,6 +1964,7 @@ namespace smr
             p_pred[l] = pending_seeds(&plan.pred[l], B_PRED, SMR_DERIVE_PRED, l, sizeof(smr_item_pred));
             p_tag[l]  = pending_seeds(&plan.tag[l], B_TAG, SMR_DERIVE_TAG, l, sizeof(smr_item_tag));
             p_bc[l]   = PendingBc{&plan.down[l].bc, l, &phases[l].bc.items, &phases[l].bc.srcs};
+            p_bc2[l]  = PendingBc{&plan.down[l].bc2, l, &phases[l].bc2.items, &phases[l].bc2.srcs};
         }
         for (const Chunk& ck : chunks)
         {
@@ -1874,6 +2008,7 @@ namespace smr
             layout_seeds(p_pred[l], plan.arena, plan.derive);
             layout_seeds(p_tag[l], plan.arena, plan.derive);
             layout_bc(p_bc[l], plan.arena);
+            layout_bc(p_bc2[l], plan.arena);
             for (int k = 0; k < 3; ++k)
             {
                 layout_batch(p_per[static_cast<size_t>(3 * l + k)], plan.arena);
@@ -1906,6 +2041,8 @@ namespace smr
                 add(p_tag[l]);
                 PendingBc* pb = &p_bc[l];
                 jobs.push_back([pb, &plan] { fill_bc(*pb, plan.arena); });
+                PendingBc* pb2 = &p_bc2[l];
+                jobs.push_back([pb2, &plan] { fill_bc(*pb2, plan.arena); });
                 for (int k = 0; k < 3; ++k)
                 {
                     Pending<smr_item_copy>* pp = &p_per[static_cast<size_t>(3 * l + k)];

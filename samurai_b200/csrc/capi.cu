@@ -520,17 +520,12 @@ namespace smr
         {
             throw std::invalid_argument("max_level too large (max_refinement_level is 20, samurai_config.hpp:50)");
         }
-        bool all_periodic = true;
-        for (int d = 0; d < c->dim; ++d)
+        if (c->max_stencil_radius < 1 || c->max_stencil_radius > 2)
         {
-            all_periodic = all_periodic && c->periodic[d] != 0;
-        }
-        if (c->max_stencil_radius < 1 || c->max_stencil_radius > 2 || (c->max_stencil_radius == 2 && !all_periodic))
-        {
-            // ghost width 2 needs the further-ghost extrapolation at non-periodic boundaries (bc/apply_field_bc.hpp:499-563) and the
-            // contiguous-boundary graduation rule (graduation.hpp:372-500), which are not built; a fully periodic mesh has neither
-            throw std::invalid_argument("max_stencil_radius must be 1 (or 2 on a mesh periodic in every direction): call "
-                                        "max_stencil_size(2) / disable_minimal_ghost_width() on the mesh_config");
+            // ghost width 2 (the library default, mesh_config.hpp:388-393) is built for boundary conditions that fill one layer:
+            // further-ghost extrapolation (bc/apply_field_bc.hpp:499-563), two-layer corner block (:313-466), contiguous-boundary
+            // graduation rule (graduation.hpp:372-455).  Wider stencils (WENO5: radius 3) are not.
+            throw std::invalid_argument("max_stencil_radius must be 1 or 2");
         }
         if (c->pred_radius < 0 || c->pred_radius > 1)
         {
@@ -1407,6 +1402,16 @@ namespace smr
                 }
                 wb.end_phase();
             }
+            if (cfg.ghost_width() == 2 && !cfg.all_periodic() && (!ph.bc2.empty() || wb.keep_empty))
+            {
+                // second ghost layer: extrapolated from the first one, which the phase above wrote
+                wb.begin_phase();
+                for (int f = 0; f < nfields; ++f)
+                {
+                    wb.add(WF_BC, ph.bc2, f);
+                }
+                wb.end_phase();
+            }
             if (periodic)
             {
                 periodic_phases(level);
@@ -1506,6 +1511,12 @@ namespace smr
         {
             periodic_copies(level);
             launch_ghost_phase(cfg.dim, arena, mo.plan.down[level], u, f.bc_type, f.bc_value);
+            if (cfg.ghost_width() == 2 && !cfg.all_periodic())
+            {
+                GhostPhase second;
+                second.bc = mo.plan.down[level].bc2;
+                launch_ghost_phase(cfg.dim, arena, second, u, f.bc_type, f.bc_value);
+            }
             periodic_copies(level);
         }
         for (int level = 1; level <= cfg.max_level; ++level)

@@ -136,7 +136,8 @@ enum
 {
     SMR_BC_COPY  = 0, /* f[dst] = f[src[0]]                            corner extrapolation / projection, predict_bc */
     SMR_BC_VALUE = 1, /* Dirichlet: 2*v - f[src[0]] ; Neumann: coef*v + f[src[0]]   (coef = dx)                     */
-    SMR_BC_AVG   = 2  /* f[dst] = (0 + f[src[0]] + ... ) / n_src ; 0 if n_src == 0   project_bc                     */
+    SMR_BC_AVG   = 2, /* f[dst] = (0 + f[src[0]] + ... ) / n_src ; 0 if n_src == 0   project_bc                     */
+    SMR_BC_EXTRAP4 = 3 /* f[dst] = f[src[0]] - f[src[1]] * 3 + f[src[2]] * 3   PolynomialExtrapolation<4>, second ghost layer */
 };
 
 typedef struct

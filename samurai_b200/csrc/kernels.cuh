@@ -1440,6 +1440,11 @@ namespace smr
                 mstore(f + it.dst, it.coef * v.bc_value + f[s[0]], mask);
             }
         }
+        else if (kind == SMR_BC_EXTRAP4)
+        {
+            // bc/polynomial_extrapolation.hpp:67-70: u[cells[0]] - u[cells[1]] * 3.0 + u[cells[2]] * 3.0
+            mstore(f + it.dst, f[s[0]] - f[s[1]] * 3.0 + f[s[2]] * 3.0, mask);
+        }
         else
         {
             double sum = 0.0;

@@ -830,6 +830,48 @@ namespace smr
                     any     = true;
                 }
             }
+            // max_stencil_radius 2: the cell two steps inward of a boundary leaf must not lie in a coarser leaf, so that the stencil of
+            // the coarser level never reaches outside the domain (list_interval_to_refine_for_contiguous_boundary_cells,
+            // graduation.hpp:372-455: n_contiguous_boundary_cells = max(2, 2 * (2 - 2)) = 2; its second part needs radius > 2)
+            if (cfg.max_stencil_radius == 2)
+            {
+                for (int k = 0; k < dim; ++k)
+                {
+                    if (cfg.periodic[k])
+                    {
+                        continue;
+                    }
+                    for (int sgn = 1; sgn >= -1; sgn -= 2)
+                    {
+                        int dv[3] = {0, 0, 0};
+                        dv[k]     = sgn;
+                        for (int level = hi; level > lo; --level)
+                        {
+                            if (ca[level].empty() || ca[level - 1].empty())
+                            {
+                                continue;
+                            }
+                            int blo[3], bhi[3];
+                            for (int a = 0; a < 3; ++a)
+                            {
+                                blo[a] = -dv[a]; // translate(domain, -direction)
+                                bhi[a] = (cfg.n0[a] << level) - dv[a];
+                            }
+                            const LevelSet bdry = minus_box(ca[level], dim, blo, bhi);
+                            if (bdry.empty())
+                            {
+                                continue;
+                            }
+                            LevelSet r = set_inter(coarsen(translate(bdry, -2 * dv[0], -2 * dv[1], -2 * dv[2]), 1, dim), ca[level - 1]);
+                            if (!r.empty())
+                            {
+                                out[level - 1] = out[level - 1].empty() ? std::move(r) : set_union(out[level - 1], r);
+                                any            = true;
+                            }
+                        }
+                    }
+                }
+            }
             if (!any)
             {
                 return nit;

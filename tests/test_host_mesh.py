@@ -84,8 +84,24 @@ def test_from_intervals_roundtrip_and_get_index():
 def test_invalid_configs_raise():
     with pytest.raises(ValueError):
         sb.MRMesh.make_mesh([0, 0], [1, 1], sb.mesh_config(2, 1).min_level(5).max_level(3).disable_minimal_ghost_width())
-    with pytest.raises(ValueError):  # ghost width 2 is not implemented: must fail loudly, not silently differ
-        sb.MRMesh.make_mesh([0, 0], [1, 1], sb.mesh_config(2, 1).min_level(2).max_level(4))
+    with pytest.raises(ValueError):  # ghost width 3 (WENO5 stencils) is not implemented: must fail loudly, not silently differ
+        sb.MRMesh.make_mesh([0, 0], [1, 1], sb.mesh_config(2, 1).min_level(2).max_level(4).max_stencil_radius(3))
+
+
+@pytest.mark.parametrize("dim,lmin,lmax", [(1, 2, 8), (2, 2, 6), (3, 1, 4)])
+def test_default_ghost_width_2_mesh_matches_oracle(dim, lmin, lmax):
+    """the library's default mesh_config (max_stencil_radius 2, mesh_config.hpp:388-393) on the host: sub-meshes, storage offsets and the
+    graduation with the contiguous-boundary rule (graduation.hpp:372-455), driven by the oracle's tag arrays"""
+    ocfg = pu.oracle_cfg(dim, lmin, lmax, 1, None, 2)
+    om = so.Mesh.uniform(ocfg)
+    pm = sb.MRMesh.make_mesh([0.0] * dim, [1.0] * dim, pu.product_cfg(dim, lmin, lmax, 1, None, 2))
+    pu.assert_same_mesh(pm, om)
+    trace = []
+    om2, _ = so.adapt(om, so.init_disc(om, [0.3] * dim, 0.2), so.Bc("dirichlet", 0.0), 2e-4, 1.0, trace=trace)
+    for t in trace:
+        pm.update_from_tags(t["tag"])
+    pu.assert_same_mesh(pm, om2)
+    assert len(om2.leaf_levels()) > 1
 
 
 @pytest.mark.parametrize("dim,lmin,lmax", [(1, 2, 7), (2, 2, 6), (3, 1, 4)])
