@@ -331,13 +331,7 @@ def uniform_sweep(sb, torch, level, iters=20):
     torch.cuda.synchronize()
     dsecs = e0.elapsed_time(e1) * 1e-3 / iters
     rhs.destroy()
-    # ghost update on the same mesh (BC only on a uniform mesh)
-    e0.record()
-    for _ in range(iters):
-        sb.update_ghost_mr(u)
-    e1.record()
-    torch.cuda.synchronize()
-    gsecs = e0.elapsed_time(e1) * 1e-3 / iters
+    gsecs = None  # the ghost update of a uniform mesh is part of uniform_full_step (timing it here only hit the ghosts_updated skip path)
     u.destroy()
     v.destroy()
     mesh.destroy()
@@ -641,7 +635,7 @@ def run_product(args):
             n_u, s_u, g_u, d_u = uniform_sweep(sb, torch, args.sweep_level)
             sweep = {"workload": f"uniform 2D level {args.sweep_level} upwind sweep, {n_u} cells, working set {16 * n_u / 1e6:.0f} MB > L2",
                      "cell_updates_per_s": n_u / s_u, "ms_per_sweep": 1e3 * s_u, "bound": "hbm", "achieved": 16.0 * n_u / s_u / 1e9,
-                     "peak": peak_gbs, "unit": "GB/s", "frac": 16.0 * n_u / s_u / 1e9 / peak_gbs, "ghost_update_ms": 1e3 * g_u,
+                     "peak": peak_gbs, "unit": "GB/s", "frac": 16.0 * n_u / s_u / 1e9 / peak_gbs,
                      "diffusion_order2": {"ms_per_apply": 1e3 * d_u, "note": "rhs = make_diffusion_order2(K)(u): fill(0) + gather, 8 B zero-fill + 8 B read + 8 B write per cell",
                                           "achieved": 24.0 * n_u / d_u / 1e9, "frac": 24.0 * n_u / d_u / 1e9 / peak_gbs}}
 
@@ -699,9 +693,9 @@ def run_product(args):
                     "d2h_bytes_per_step": int(st_e2e["d2h_bytes"] / args.steps), "ms_per_step": 1e3 * e2e_secs / args.steps},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
                          # dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` of two steady-state harten
-                         # launches of this workload (18.6 MB and 34.4 MB; profiles/r01_summary.md section 6): below the algorithmic
+                         # launches of this workload (30.4 MB and 31.4 MB; profiles/r02_ncu_wavefront.md): below the algorithmic
                          # bytes because the adapted working set stays in L2 between the sweeps.  Not re-measured by this run.
-                         "traffic": 26.5e6 if (dom == "wavefront" and args.dim == 2 and args.max_level == 14) else None,
+                         "traffic": 30.9e6 if (dom == "wavefront" and args.dim == 2 and args.max_level == 14) else None,
                          "peak_source": peak_src, "share_of_device_time": fam_time[dom] / total_prof,
                          "launches": n_l, "us_per_launch": 1e6 * s_l / n_l, "algorithmic_bytes_per_launch": dom_bytes / n_l,
                          "note": "adapted-mesh step: ~1e6 cells over ~40 dependent level sweeps per launch (grid barrier between sweeps): latency bound, "
