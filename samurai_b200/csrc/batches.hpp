@@ -1633,7 +1633,15 @@ namespace smr
             if (level < L && !ref.empty())
             {
                 // project_bc, layer 1
-                LevelSet ghosts = set_inter(m.outside_domain(translate(m.uni[level], d.v[0], d.v[1], d.v[2]), level), ref);
+                // only the boundary layer of the union can leave the domain: clip before translating (the levels are large)
+                int blo[3], bhi[3];
+                m.domain_box(level, 0, blo, bhi);
+                for (int k = 0; k < 3; ++k)
+                {
+                    blo[k] -= d.v[k];
+                    bhi[k] -= d.v[k];
+                }
+                LevelSet ghosts = set_inter(translate(minus_box(m.uni[level], dim, blo, bhi), d.v[0], d.v[1], d.v[2]), ref);
                 locate(ghosts, ref);
                 for (size_t r = 0; r < ghosts.rows(); ++r)
                 {
@@ -1773,8 +1781,9 @@ namespace smr
         }
         if (level > 0 && !ref.empty())
         {
-            LevelSet ps = set_inter(coarsen(ref, 1, dim), m.proj[level - 1]);
-            set_seeds(ps, level - 1, flt, false, out.proj);
+            // projection targets: proj_cells[level - 1] ∩ coarsen(reference[level]) (update_ghost_mr.hpp:219) == proj_cells[level - 1]:
+            // the mesh construction adds the children of every projection cell to the reference (mr/mesh.hpp:415-452)
+            set_seeds(m.proj[level - 1], level - 1, flt, false, out.proj);
         }
     }
 
@@ -1785,12 +1794,14 @@ namespace smr
         {
             return LevelSet();
         }
-        LevelSet pg = m.in_domain(set_diff(m.ref[level], set_union(m.cells[level], m.proj[level])), level);
+        LevelSet pg = m.in_domain(set_diff(set_diff(m.ref[level], m.cells[level]), m.proj[level]), level);
         if (pg.empty())
         {
             return pg;
         }
-        return set_inter(pg, refine(m.ref[level - 1], 1, dim));
+        // "... whose parent exists in all_cells[level - 1]": test the parents of the (few) candidates instead of refining the whole
+        // coarser level (pg ∩ refine(ref[l-1]) == pg ∩ refine(coarsen(pg) ∩ ref[l-1]))
+        return set_inter(pg, refine(set_inter(coarsen(pg, 1, dim), m.ref[level - 1]), 1, dim));
     }
 
     inline LevelSet detail_set(const Mesh& m, int level)
