@@ -186,7 +186,8 @@ class MeshConfig:
         # ghost width 2: further-ghost extrapolation (bc/apply_field_bc.hpp:499-563), the two-layer corner block (:313-466) and the
         # contiguous-boundary graduation rule (graduation.hpp:372-500) are restated for boundary conditions that fill ONE layer
         # (Dirichlet<1> / Neumann<1>); larger widths are not
-        assert self.max_stencil_radius in (1, 2), "oracle restates ghost widths 1 and 2"
+        # (fully periodic meshes have no boundary: any width, e.g. 3 for the WENO5 stencil)
+        assert self.max_stencil_radius in (1, 2) or all(self.periodic), "oracle restates ghost widths 1 and 2 at non-periodic boundaries"
         assert self.pred_radius in (0, 1)
 
     def periodic_directions(self, level):
@@ -1204,11 +1205,45 @@ def burgers_upwind_flux(scale=1.0):
     return fn
 
 
-def flux_nonlin_apply(mesh: Mesh, u, flux_fn):
+def weno5_flux(velocity):
+    """make_convection_weno5 for a scalar field (schemes/fv/operators/convection_lin.hpp:95-178): per direction d a function of the six
+    stencil values u[-2..3]; f = velocity[d] * (u0..u4) if velocity[d] >= 0 else velocity[d] * (u5..u1); Jiang & Shu WENO5
+    (schemes/fv/operators/weno_impl.hpp:26-63, same operation order; pow(x, 2) taken as x * x)."""
+    def make(d):
+        v = float(velocity[d])
+
+        def fn(u0, u1, u2, u3, u4, u5):
+            f = [u0 * v, u1 * v, u2 * v, u3 * v, u4 * v] if v >= 0 else [u5 * v, u4 * v, u3 * v, u2 * v, u1 * v]
+            j = 2
+            q0 = 1. / 3 * f[j - 2] - 7. / 6 * f[j - 1] + 11. / 6 * f[j]
+            q1 = -1. / 6 * f[j - 1] + 5. / 6 * f[j] + 1. / 3 * f[j + 1]
+            q2 = 1. / 3 * f[j] + 5. / 6 * f[j + 1] - 1. / 6 * f[j + 2]
+            sq = lambda x: x * x
+            IS0 = 13. / 12 * sq(f[j - 2] - 2 * f[j - 1] + f[j]) + 1. / 4 * sq(f[j - 2] - 4 * f[j - 1] + 3 * f[j])
+            IS1 = 13. / 12 * sq(f[j - 1] - 2 * f[j] + f[j + 1]) + 1. / 4 * sq(f[j - 1] - f[j + 1])
+            IS2 = 13. / 12 * sq(f[j] - 2 * f[j + 1] + f[j + 2]) + 1. / 4 * sq(3 * f[j] - 4 * f[j + 1] + f[j + 2])
+            eps = 1e-6
+            a0 = 0.1 / sq(eps + IS0)
+            a1 = 0.6 / sq(eps + IS1)
+            a2 = 0.3 / sq(eps + IS2)
+            sa = a0 + a1 + a2
+            return (a0 / sa) * q0 + (a1 / sa) * q1 + (a2 / sa) * q2
+        return fn
+    return [make(d) for d in range(len(velocity))]
+
+
+WENO5_OFFSETS = (-2, -1, 0, 1, 2, 3)  # line_stencil<dim, d>(-2, -1, 0, 1, 2, 3), convection_lin.hpp:115
+
+
+def flux_nonlin_apply(mesh: Mesh, u, flux_fn, offsets=(0, 1)):
     """Explicit<FluxBasedScheme<NonLinear>>::apply with finer_level_flux disabled, sequential order
     (flux_based/explicit_flux_based_scheme__nonlin.hpp:35-85; flux_based_scheme__nonlin.hpp:334-364 interior,
     :366-402 boundary, :407-520 level loop and factors; fluxes[1] = -fluxes[0]: flux_definition.hpp:125-136).
-    Per interface cell, in interval order: out[left] += flux*left_factor, then out[right] += (-flux)*right_factor."""
+    Per interface cell, in interval order: out[left] += flux*left_factor, then out[right] += (-flux)*right_factor.
+    `offsets`: the line stencil of the flux (cells origin + o * e_d, origin = the cell left of the interface at the level the flux
+    is computed on); `flux_fn`: one function of the stencil values, or one per direction.  Periodic directions add the interfaces
+    through the boundary, seen once from each side (interface.hpp:83-92, 179-189, 280-290), and have no boundary interfaces
+    (flux_based_scheme__nonlin.hpp:537-540)."""
     cfg, dim = mesh.cfg, mesh.cfg.dim
     out = np.zeros(mesh.nref)
     leaf_lv = mesh.leaf_levels()
@@ -1218,48 +1253,68 @@ def flux_nonlin_apply(mesh: Mesh, u, flux_fn):
     def hfac(h_face, h_cell):
         return pow(h_face, dim - 1) / pow(h_cell, dim)
 
-    def scatter(run_left, run_right, st0, st1, lf, rf):
-        # sequential per-cell accumulation (several fine cells may hit the same coarse cell: np.add.at keeps order)
-        fl = flux_fn(u[st0], u[st1])
-        a = fl * lf
-        b = (-fl) * rf
-        for k in range(run_left.size):
-            out[run_left[k]] = out[run_left[k]] + a[k]
-            out[run_right[k]] = out[run_right[k]] + b[k]
-
     for d in range(dim):
+        fn = flux_fn[d] if isinstance(flux_fn, (list, tuple)) else flux_fn
         e = [0] * dim
         e[d] = 1
         me = [-v for v in e]
+
+        def scatter(slevel, origin, run_left, run_right, lf, rf):
+            # sequential per-cell accumulation (several fine cells may hit the same coarse cell)
+            vals = [u[mesh.index(slevel, translate(origin, [o * x for x in e]))] for o in offsets]
+            fl = fn(*vals)
+            a = fl * lf
+            b = (-fl) * rf
+            for k in range(run_left.size):
+                out[run_left[k]] = out[run_left[k]] + a[k]
+                out[run_right[k]] = out[run_right[k]] + b[k]
+
+        def shift_of(level, sign):
+            sh = [0] * dim
+            sh[d] = sign * (cfg.n_cells0[d] << level)
+            return sh
+
         for level in range(lo, hi + 1):
             cells = mesh.cells[level]
             if cells.size == 0:
                 continue
             h = cfg.cell_length(level)
             f = hfac(h, h)
-            iface = cells[np.isin(translate(cells, e), cells)]
-            for run in _runs(iface, dim):
-                li = mesh.index(level, run)
-                ri = mesh.index(level, translate(run, e))
-                scatter(li, ri, li, ri, f, f)
+            pairs = [(cells, cells)]
+            if cfg.periodic[d]:
+                pairs += [(cells, translate(cells, shift_of(level, 1))), (translate(cells, shift_of(level, -1)), cells)]
+            for left_set, right_set in pairs:
+                iface = inter(left_set, translate(right_set, me))
+                for run in _runs(iface, dim):
+                    li = mesh.index(level, run)
+                    ri = mesh.index(level, translate(run, e))
+                    scatter(level, run, li, ri, f, f)
         for level in range(lo, hi):
             coarse, fine = mesh.cells[level], mesh.cells[level + 1]
             if coarse.size == 0 or fine.size == 0:
                 continue
             h_l, h_f = cfg.cell_length(level), cfg.cell_length(level + 1)
-            rcoarse = refine(coarse, 1, dim)
-            ghosts = inter(rcoarse, translate(fine, me))
-            for run in _runs(ghosts, dim):
-                st0 = mesh.index(level + 1, run)
-                st1 = mesh.index(level + 1, translate(run, e))
-                left = mesh.index(level, pack(unpack(run, dim) >> 1))
-                scatter(left, st1, st0, st1, hfac(h_f, h_l), hfac(h_f, h_f))
-            ghosts = inter(rcoarse, translate(fine, e))
-            for run in _runs(ghosts, dim):
-                st0 = mesh.index(level + 1, translate(run, me))
-                st1 = mesh.index(level + 1, run)
-                right = mesh.index(level, pack(unpack(run, dim) >> 1))
-                scatter(st0, right, st0, st1, hfac(h_f, h_f), hfac(h_f, h_l))
+            pairs = [(coarse, fine)]
+            if cfg.periodic[d]:
+                pairs += [(coarse, translate(fine, shift_of(level + 1, 1))), (translate(coarse, shift_of(level, -1)), fine)]
+            for cs, fs in pairs:
+                ghosts = inter(refine(cs, 1, dim), translate(fs, me))
+                for run in _runs(ghosts, dim):
+                    st1 = mesh.index(level + 1, translate(run, e))
+                    left = mesh.index(level, pack(unpack(run, dim) >> 1))
+                    scatter(level + 1, run, left, st1, hfac(h_f, h_l), hfac(h_f, h_f))
+            pairs = [(coarse, fine)]
+            if cfg.periodic[d]:
+                pairs += [(coarse, translate(fine, shift_of(level + 1, -1))), (translate(coarse, shift_of(level, 1)), fine)]
+            for cs, fs in pairs:
+                ghosts = inter(refine(cs, 1, dim), translate(fs, e))
+                for run in _runs(ghosts, dim):
+                    st0 = mesh.index(level + 1, translate(run, me))
+                    right = mesh.index(level, pack(unpack(run, dim) >> 1))
+                    scatter(level + 1, translate(run, me), st0, right, hfac(h_f, h_f), hfac(h_f, h_l))
+        if cfg.periodic[d]:
+            continue
+        assert tuple(offsets) == (0, 1), "boundary interfaces are restated for two-cell stencils"
         for level in leaf_lv:
             cells = mesh.cells[level]
             h = cfg.cell_length(level)
@@ -1267,12 +1322,12 @@ def flux_nonlin_apply(mesh: Mesh, u, flux_fn):
             bd = cells[~mesh.in_domain(level, translate(cells, e))]
             for run in _runs(bd, dim):
                 bi = mesh.index(level, run)
-                fl = flux_fn(u[bi], u[mesh.index(level, translate(run, e))])
+                fl = fn(u[bi], u[mesh.index(level, translate(run, e))])
                 out[bi] = out[bi] + fl * f
             bd = cells[~mesh.in_domain(level, translate(cells, me))]
             for run in _runs(bd, dim):
                 bi = mesh.index(level, run)
-                fl = flux_fn(u[mesh.index(level, translate(run, me))], u[bi])
+                fl = fn(u[mesh.index(level, translate(run, me))], u[bi])
                 out[bi] = out[bi] + (-fl) * f  # flux_values[1] *= -(-factor)
     return out
 
@@ -1370,6 +1425,62 @@ def run_heat(cfg: MeshConfig, Tf=0.1, K=1.0, cfl=0.95, eps=1e-4, regularity=1.0,
             i = mesh.index(l, mesh.cells[l])
             unp1[i] = u[i] - dt * rhs[i]
         u = unp1
+        nt += 1
+        if on_step is not None:
+            on_step(nt, mesh, u)
+        if max_steps is not None and nt >= max_steps:
+            break
+    return dict(init=init_state, final=(mesh, u), steps=nt)
+
+
+def run_linear_convection(cfg: MeshConfig, Tf=0.1, cfl=0.95, eps=1e-4, regularity=1.0, velocity=None, max_steps=None, on_step=None):
+    """demos/FiniteVolume/linear_convection.cpp, explicit branch (:84-222): fully periodic box, u0 = 1 in [-0.8, -0.3] x [0.3, 0.8]
+    (1D: [-0.8, -0.3]) else 0, velocity (1, -1), conv = make_convection_weno5 (six-cell line stencil: max_stencil_size(6), ghost
+    width 3), dt = cfl * dx / sum|v|; per step MRadaptation then TVD-RK3:
+        u1 = u - dt*conv(u);  u2 = 3/4 u + 1/4 (u1 - dt*conv(u1));  unp1 = 1/3 u + 2/3 (u2 - dt*conv(u2))."""
+    dim = cfg.dim
+    if velocity is None:
+        velocity = [1.0] * dim
+        if dim == 2:
+            velocity[1] = -1.0
+    bc = Bc("neumann", 0.0)  # never applied: no boundary on a fully periodic mesh
+    mesh = Mesh.uniform(cfg)
+    L = cfg.max_level
+    c = mesh.cell_centers(L, mesh.cells[L])
+    inside = (c[:, 0] >= -0.8) & (c[:, 0] <= -0.3)
+    if dim == 2:
+        inside &= (c[:, 1] >= 0.3) & (c[:, 1] <= 0.8)
+    u = np.zeros(mesh.nref)
+    u[mesh.index(L, mesh.cells[L])] = np.where(inside, 1.0, 0.0)
+    dt = cfl * cfg.cell_length(L) / sum(abs(v) for v in velocity)
+    flux = weno5_flux(velocity)
+
+    def conv(mesh, f):
+        update_ghost_mr(mesh, f, bc)
+        return flux_nonlin_apply(mesh, f, flux, WENO5_OFFSETS)
+
+    def leaves_expr(mesh, fn):
+        out = np.full(mesh.nref, np.nan)
+        for l in mesh.leaf_levels():
+            i = mesh.index(l, mesh.cells[l])
+            out[i] = fn(i)
+        return out
+
+    mesh, u = adapt(mesh, u, bc, eps, regularity)
+    init_state = (mesh, u.copy())
+    t, nt = 0.0, 0
+    while t != Tf:
+        t += dt
+        if t > Tf:
+            dt += Tf - t
+            t = Tf
+        mesh, u = adapt(mesh, u, bc, eps, regularity)
+        c0 = conv(mesh, u)
+        u1 = leaves_expr(mesh, lambda i: u[i] - dt * c0[i])
+        c1 = conv(mesh, u1)
+        u2 = leaves_expr(mesh, lambda i: 3. / 4 * u[i] + 1. / 4 * (u1[i] - dt * c1[i]))
+        c2 = conv(mesh, u2)
+        u = leaves_expr(mesh, lambda i: 1. / 3 * u[i] + 2. / 3 * (u2[i] - dt * c2[i]))
         nt += 1
         if on_step is not None:
             on_step(nt, mesh, u)

@@ -52,3 +52,18 @@ if __name__ == "__main__":
     out = os.path.join(HERE, "mra_burgers_hat.npz")
     np.savez_compressed(out, level=level.astype(np.int8), idx=idx.astype(np.int32)[:, None], u=h5.read("/mesh/fields/u"))
     print(out, len(level), os.path.getsize(out))
+
+    # linear_convection.cpp --nfiles=1 --min-level=1 --max-level=6 --Tf=0.1 (tests/test_demo_finite_volume.py:280-298, explicit): 2D,
+    # box [-1, 1]^2 periodic in both directions, max_stencil_size(6) (ghost width 3), make_convection_weno5 (NON-LINEAR flux scheme,
+    # six-cell line stencil), velocity (1, -1), TVD-RK3, cfl 0.95, default mra_config (eps 1e-4, regularity 1)
+    h5 = h5mini.H5File(REF + "test_finite_volume_demo_linear_convection_explicit.h5")
+    pts = h5.read("/mesh/points")
+    conn = h5.read("/mesh/connectivity").reshape(-1, 4).astype(np.int64)
+    lo = pts[conn].min(axis=1)[:, :2]
+    level = h5.read("/mesh/fields/level").astype(np.int64)
+    length = 2.0 / (1 << level)
+    idx = np.rint((lo + 1.0) / length[:, None]).astype(np.int64)
+    assert np.allclose(pts[conn].max(axis=1)[:, 0] - lo[:, 0], length)
+    out = os.path.join(HERE, "linear_convection_explicit.npz")
+    np.savez_compressed(out, level=level.astype(np.int8), idx=idx.astype(np.int32), u=h5.read("/mesh/fields/u"))
+    print(out, len(level), os.path.getsize(out))

@@ -166,3 +166,21 @@ def test_oracle_matches_reference_mra_burgers_hat_golden():
     lv, co, ix = mesh.leaf_table()
     assert lv.size == g["level"].size and np.array_equal(lv, g["level"]) and np.array_equal(co, g["idx"]), "mesh differs from the reference golden"
     assert np.max(np.abs(u[ix] - g["u"])) <= 1e-15
+
+
+def test_oracle_matches_reference_linear_convection_weno5_golden():
+    """demos/FiniteVolume/linear_convection.cpp with the reference test's arguments (tests/test_demo_finite_volume.py:280-298, explicit:
+    --min-level=1 --max-level=6 --Tf=0.1): 2D box [-1, 1]^2 periodic in both directions, max_stencil_size(6) (ghost width 3),
+    `make_convection_weno5` (NON-LINEAR flux scheme with a six-cell line stencil, level jumps through predicted fine
+    ghosts, interfaces through the periodic boundary), TVD-RK3 field expressions, default mra_config.  Against the reference's own
+    test_finite_volume_demo_linear_convection_explicit.h5 (tests/golden/linear_convection_explicit.npz): mesh identical, values
+    within 1e-13 (the reference's own tolerance is rel 1e-14 / abs 1e-7, tests/conftest.py:121-122)."""
+    g = np.load(os.path.join(GOLD, "linear_convection_explicit.npz"))
+    cfg = so.MeshConfig(dim=2, min_level=1, max_level=6, pred_radius=1, max_stencil_radius=3, graduation_width=1, origin=(-1.0, -1.0),
+                        scaling=2.0, periodic=(True, True))
+    r = so.run_linear_convection(cfg, Tf=0.1)
+    assert r["steps"] == 7
+    mesh, u = r["final"]
+    lv, co, ix = mesh.leaf_table()
+    assert lv.size == g["level"].size and np.array_equal(lv, g["level"]) and np.array_equal(co, g["idx"]), "mesh differs from the reference golden"
+    assert np.max(np.abs(u[ix] - g["u"])) <= 1e-13
