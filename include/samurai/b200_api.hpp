@@ -1980,6 +1980,17 @@ namespace samurai
     }
 
     template <class Field>
+    auto make_convection_weno5(const VelocityVector<Field::dim>& velocity) // operators/convection_lin.hpp:95-178 (WENO5, Jiang & Shu)
+    {
+        double v[3] = {0, 0, 0};
+        for (std::size_t d = 0; d < Field::dim; ++d)
+        {
+            v[d] = velocity(d);
+        }
+        return FluxBasedScheme<Field>(SMR_SCHEME_CONVECTION_WENO5, v, "convection");
+    }
+
+    template <class Field>
     auto make_convection_upwind() // operators/convection_nonlin.hpp:24-76 (scalar field: Burgers)
     {
         const double v[3] = {0, 0, 0};

@@ -111,6 +111,7 @@ SYMBOLS = {
     "smr_mg_leaf_owners": [_u64, _vp, _i64],
     "smr_debug_host_rebuild": [_u64, _i32, _P(_dbl), _P(_dbl), _P(_i64)],
     "smr_debug_flux_records": [_u64, _vp, _i64, _P(_i64)],
+    "smr_debug_fluxw_apply": [_u64, _vp, _vp, _dbl, _vp],
     "smr_profile_enable": [_i32],
     "smr_profile_get": [_i32, _P(_u64), _P(_dbl), _P(_u64)],
     "smr_profile_get_bytes": [_i32, _P(_u64)],
@@ -409,6 +410,14 @@ class MRMesh:
             _check(load_library().smr_debug_flux_records(self._h, out.ctypes.data, n.value, C.byref(n)))
         return out
 
+    def debug_fluxw_apply(self, u, velocity, scale=1.0):
+        """Host evaluation of the WENO5 flux records (tests only; ghosts of `u` must be up to date)."""
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        v = np.ascontiguousarray(list(velocity) + [0.0] * (3 - len(velocity)), dtype=np.float64)
+        out = np.zeros_like(u)
+        _check(load_library().smr_debug_fluxw_apply(self._h, u.ctypes.data, v.ctypes.data, float(scale), out.ctypes.data))
+        return out
+
     def update_from_tags(self, tags):
         tags = np.ascontiguousarray(tags, dtype=np.uint8)
         unchanged = C.c_int()
@@ -564,7 +573,7 @@ def upwind_scalar_burgers_step(unp1: ScalarField, u: ScalarField, k, dt):
     _check(load_library().smr_fv_upwind_burgers(unp1._h, u._h, k.ctypes.data, float(dt)))
 
 
-CONVECTION_UPWIND, DIFFUSION_ORDER2, CONVECTION_UPWIND_NONLINEAR = 0, 1, 2
+CONVECTION_UPWIND, DIFFUSION_ORDER2, CONVECTION_UPWIND_NONLINEAR, CONVECTION_WENO5 = 0, 1, 2, 3
 
 
 class FluxScheme:
@@ -592,6 +601,13 @@ def make_convection_upwind(velocity=None):
     if velocity is None:
         return FluxScheme(CONVECTION_UPWIND_NONLINEAR, [0.0, 0.0, 0.0], "convection(u)")
     return FluxScheme(CONVECTION_UPWIND, velocity, "convection")
+
+
+def make_convection_weno5(velocity):
+    """samurai::make_convection_weno5<Field>(velocity) (schemes/fv/operators/convection_lin.hpp:95-178): WENO5 (Jiang & Shu) linear
+    convection, a non-linear flux scheme with a six-cell line stencil; fully periodic meshes with max_stencil_size(6)."""
+    v = list(velocity) + [0.0] * (3 - len(velocity))
+    return FluxScheme(CONVECTION_WENO5, v, "convection")
 
 
 def make_diffusion_order2(K):

@@ -1101,6 +1101,228 @@ namespace smr
         }
     }
 
+    // Six-cell line stencil {-2 .. 3} (WENO5, operators/convection_lin.hpp:95-178) on a fully periodic mesh: the same face
+    // classification, with the neighbour across a periodic boundary looked up at the wrapped position (interface.hpp:83-92 same level,
+    // :179-189 and :280-290 level jumps) while the stencil values are the periodic ghosts at the unwrapped one.
+    inline void fluxw_items(const Mesh& m, int l, const PlanFilter& flt, std::vector<smr_item_fluxw>& out, std::vector<int64_t>& aux)
+    {
+        const int dim       = m.cfg.dim;
+        const LevelSet& c   = m.cells[l];
+        const LevelSet& ref = m.ref[l];
+        const LevelSet* cc  = l > 0 ? &m.cells[l - 1] : nullptr;
+        const LevelSet* cf  = l + 1 < m.nlev ? &m.cells[l + 1] : nullptr;
+        const LevelSet* rf  = l + 1 < m.nlev ? &m.ref[l + 1] : nullptr;
+        const int nfaces    = 2 * dim;
+        int nl[3];
+        for (int d = 0; d < 3; ++d)
+        {
+            nl[d] = m.cfg.n0[d] << l;
+        }
+        auto wrap = [&](int d, int v) { return ((v % nl[d]) + nl[d]) % nl[d]; };
+        struct Seg
+        {
+            int a, b, kind;
+        };
+        std::vector<Seg> segs[6];
+        std::vector<int> cuts;
+        auto has = [](const LevelSet* s, int y, int z, int x)
+        {
+            return s != nullptr && s->contains(mk_key(y, z), x);
+        };
+        out.reserve(out.size() + static_cast<size_t>(c.ptr[c.rows()]));
+        for (size_t r = 0; r < c.rows(); ++r)
+        {
+            const int y = key_y(c.key[r]), z = key_z(c.key[r]);
+            if (!flt.owns(l, y, z))
+            {
+                continue;
+            }
+            const int mask = static_cast<int>(flt.mask(l, y, z));
+            const int py = dim > 1 ? (y >> 1) : 0, pz = dim > 2 ? (z >> 1) : 0; // parent row
+            auto cy_ = [&](int a) { return dim > 1 ? 2 * y + a : 0; };             // child rows
+            auto cz_ = [&](int a) { return dim > 2 ? 2 * z + a : 0; };
+            for (int q = c.ptr[r]; q < c.ptr[r + 1]; ++q)
+            {
+                const int s = c.xs[q], e = c.xe[q];
+                cuts.clear();
+                cuts.push_back(s);
+                cuts.push_back(e);
+                int swap_bits = 0;
+                for (int f = 2; f < nfaces; ++f)
+                {
+                    segs[f].clear();
+                    const int d = f >> 1, sgn = (f & 1) ? 1 : -1;
+                    int yy = y + (d == 1 ? sgn : 0), zz = z + (d == 2 ? sgn : 0);
+                    const int j        = d == 1 ? yy : zz;
+                    const bool through = j < 0 || j >= nl[d];
+                    if (through)
+                    {
+                        (d == 1 ? yy : zz) = wrap(d, j);
+                    }
+                    const int rS = c.find_row(mk_key(yy, zz));
+                    const int rC = cc ? cc->find_row(mk_key(dim > 1 ? (yy >> 1) : 0, dim > 2 ? (zz >> 1) : 0)) : -1;
+                    // the child row of the neighbour position that touches this leaf
+                    const int fy = d == 1 ? 2 * yy + (sgn < 0 ? 1 : 0) : 2 * yy;
+                    const int fz = dim > 2 ? (d == 2 ? 2 * zz + (sgn < 0 ? 1 : 0) : 2 * zz) : 0;
+                    const int rF = cf ? cf->find_row(mk_key(fy, fz)) : -1;
+                    int pos = s;
+                    while (pos < e)
+                    {
+                        int i, end, kind;
+                        if (rS >= 0 && (i = c.find_ivl(rS, pos)) >= 0)
+                        {
+                            end  = std::min(e, c.xe[i]);
+                            kind = SMR_FACE_SAME;
+                            if (through && sgn < 0)
+                            {
+                                swap_bits |= 1 << (SMR_FLUXW_SWAP_SHIFT + d); // whole interval or none: see the cut below
+                            }
+                        }
+                        else if (rC >= 0 && (i = cc->find_ivl(rC, pos >> 1)) >= 0)
+                        {
+                            end  = std::min(e, 2 * cc->xe[i]);
+                            kind = SMR_FACE_COARSE;
+                        }
+                        else if (rF >= 0 && (i = cf->find_ivl(rF, 2 * pos)) >= 0)
+                        {
+                            end  = std::min(e, (cf->xe[i] + 1) >> 1);
+                            kind = SMR_FACE_FINE;
+                        }
+                        else
+                        {
+                            missing("wide flux: neighbour leaf", l, pos, yy, zz);
+                        }
+                        segs[f].push_back({pos, end, kind});
+                        cuts.push_back(end);
+                        pos = end;
+                    }
+                }
+                std::sort(cuts.begin(), cuts.end());
+                cuts.erase(std::unique(cuts.begin(), cuts.end()), cuts.end());
+                size_t cur[6] = {0, 0, 0, 0, 0, 0};
+                for (size_t ci = 0; ci + 1 < cuts.size(); ++ci)
+                {
+                    const int a = cuts[ci], b = cuts[ci + 1];
+                    int kinds     = 0;
+                    bool any_fine = false;
+                    // x faces: the neighbour cells a - 1 and b, wrapped through the periodic boundary
+                    int kx[2];
+                    for (int side = 0; side < 2; ++side)
+                    {
+                        const bool inside = side == 0 ? a > s : b < e;
+                        if (inside)
+                        {
+                            kx[side] = SMR_FACE_SAME;
+                            continue;
+                        }
+                        const int xn       = side == 0 ? a - 1 : b;
+                        const bool through = xn < 0 || xn >= nl[0];
+                        const int xw       = wrap(0, xn);
+                        if (through && has(&c, y, z, xw))
+                        {
+                            kx[side] = SMR_FACE_SAME;
+                            if (side == 0)
+                            {
+                                kinds |= 1 << SMR_FLUXW_SWAP_SHIFT;
+                            }
+                        }
+                        else if (has(cc, py, pz, xw >> 1))
+                        {
+                            kx[side] = SMR_FACE_COARSE;
+                        }
+                        else if (has(cf, cy_(0), cz_(0), side == 0 ? 2 * xw + 1 : 2 * xw))
+                        {
+                            kx[side] = SMR_FACE_FINE;
+                        }
+                        else
+                        {
+                            missing("wide flux: x neighbour leaf", l, xn, y, z);
+                        }
+                    }
+                    kinds |= kx[0] | (kx[1] << 2);
+                    any_fine = kx[0] == SMR_FACE_FINE || kx[1] == SMR_FACE_FINE;
+                    for (int f = 2; f < nfaces; ++f)
+                    {
+                        while (segs[f][cur[f]].b <= a)
+                        {
+                            ++cur[f];
+                        }
+                        const int kind = segs[f][cur[f]].kind;
+                        kinds |= kind << (2 * f);
+                        any_fine = any_fine || kind == SMR_FACE_FINE;
+                        if (kind == SMR_FACE_SAME && !(f & 1))
+                        {
+                            kinds |= swap_bits & (1 << (SMR_FLUXW_SWAP_SHIFT + (f >> 1)));
+                        }
+                    }
+                    smr_item_fluxw it;
+                    it.c = need(ref, "wide flux x", l, y, z, a - 3, b + 2) + 3;
+                    for (int k = 0; k < 12; ++k)
+                    {
+                        it.nb[k] = it.c;
+                    }
+                    for (int d = 1; d < dim; ++d)
+                    {
+                        for (int o = -3; o <= 3; ++o)
+                        {
+                            if (o != 0)
+                            {
+                                it.nb[6 * (d - 1) + (o < 0 ? o + 3 : o + 2)] = need(ref, "wide flux transverse row", l, y + (d == 1 ? o : 0),
+                                                                                    z + (d == 2 ? o : 0), a, b - 1);
+                            }
+                        }
+                    }
+                    it.fine = 0;
+                    if (any_fine)
+                    {
+                        it.fine = static_cast<int64_t>(aux.size());
+                        aux.resize(aux.size() + SMR_FLUXW_AUX_SLOTS, 0);
+                        int64_t* fx  = aux.data() + it.fine;
+                        const int nr = 1 << (dim - 1);
+                        for (int side = 0; side < 2; ++side)
+                        {
+                            if (kx[side] == SMR_FACE_FINE)
+                            {
+                                // stencil origin at level+1 (unwrapped): x-: the fine leaf 2a-1 (ghost 2a); x+: the ghost 2b-1 (fine leaf 2b)
+                                const int x0 = side == 0 ? 2 * a - 1 : 2 * b - 1;
+                                for (int rr = 0; rr < nr; ++rr)
+                                {
+                                    fx[side * 4 + rr] = need(*rf, "wide flux fine x rows", l + 1, cy_(rr & 1), cz_(rr >> 1), x0 - 2, x0 + 3) + 2;
+                                }
+                            }
+                        }
+                        for (int f = 2; f < nfaces; ++f)
+                        {
+                            if (((kinds >> (2 * f)) & 3) != SMR_FACE_FINE)
+                            {
+                                continue;
+                            }
+                            const int d = f >> 1, sgn = (f & 1) ? 1 : -1;
+                            const int base     = d == 1 ? 2 * y : 2 * z;
+                            const int origin   = sgn < 0 ? base - 1 : base + 1; // minus: the fine leaf row; plus: the ghost row
+                            const int nb_other = dim > 2 ? 2 : 1;
+                            for (int bb = 0; bb < nb_other; ++bb)
+                            {
+                                for (int st = 0; st < 6; ++st)
+                                {
+                                    const int row = origin - 2 + st;
+                                    const int ry  = d == 1 ? row : cy_(bb);
+                                    const int rz  = d == 2 ? row : cz_(bb);
+                                    fx[8 + ((f - 2) * 2 + bb) * 6 + st] = need(*rf, "wide flux fine transverse rows", l + 1, ry, rz, 2 * a, 2 * b - 1);
+                                }
+                            }
+                        }
+                    }
+                    it.n     = b - a;
+                    it.level = l;
+                    it.kinds = kinds;
+                    it.mask  = mask;
+                    out.push_back(it);
+                }
+            }
+        }
+    }
+
     // batches for the flux-based schemes on multi-level meshes, built on first use for a mesh (flux schemes only)
     struct FluxPlan
     {
@@ -1109,10 +1331,11 @@ namespace smr
         bool ready = false;
     };
 
-    inline void build_flux_plan(const Mesh& m, FluxPlan& plan, const PlanFilter& flt = PlanFilter())
+    template <class Item, class ItemsFn>
+    inline void build_flux_plan_t(const Mesh& m, FluxPlan& plan, ItemsFn&& items_fn)
     {
         const int nlev = m.nlev;
-        std::vector<std::vector<smr_item_flux>> items(nlev);
+        std::vector<std::vector<Item>> items(nlev);
         std::vector<std::vector<int64_t>> aux(nlev);
         std::string error;
 #pragma omp parallel for schedule(dynamic, 1)
@@ -1122,7 +1345,7 @@ namespace smr
             {
                 if (!m.cells[l].empty())
                 {
-                    flux_items(m, l, flt, items[l], aux[l]);
+                    items_fn(l, items[l], aux[l]);
                 }
             }
             catch (const std::exception& e)
@@ -1141,7 +1364,7 @@ namespace smr
         {
             if (base != 0)
             {
-                for (smr_item_flux& it : items[l])
+                for (Item& it : items[l])
                 {
                     it.fine += base;
                 }
@@ -1149,7 +1372,7 @@ namespace smr
             base += static_cast<int64_t>(aux[l].size());
         }
         plan.arena.clear();
-        Pending<smr_item_flux> pd{&plan.items, B_FV, -1, {}, nullptr, false};
+        Pending<Item> pd{&plan.items, B_FV, -1, {}, nullptr, false};
         for (int l = 0; l < nlev; ++l)
         {
             pd.parts.push_back(&items[l]);
@@ -1168,6 +1391,17 @@ namespace smr
             }
         }
         plan.ready = true;
+    }
+
+    inline void build_flux_plan(const Mesh& m, FluxPlan& plan, const PlanFilter& flt = PlanFilter())
+    {
+        build_flux_plan_t<smr_item_flux>(m, plan, [&](int l, std::vector<smr_item_flux>& it, std::vector<int64_t>& aux) { flux_items(m, l, flt, it, aux); });
+    }
+
+    // six-cell line stencils (WENO5) on fully periodic meshes
+    inline void build_fluxw_plan(const Mesh& m, FluxPlan& plan, const PlanFilter& flt = PlanFilter())
+    {
+        build_flux_plan_t<smr_item_fluxw>(m, plan, [&](int l, std::vector<smr_item_fluxw>& it, std::vector<int64_t>& aux) { fluxw_items(m, l, flt, it, aux); });
     }
 
     // ---------------------------------------------------------------------------------------------------------

@@ -194,8 +194,9 @@ namespace smr
         bool plan_ready = false;
         double plan_seconds = 0;
         DevBuf d_arena;
-        FluxPlan flux; // flux-based schemes on multi-level meshes, built on first use
-        DevBuf d_flux, d_fluxtab;
+        FluxPlan flux;  // flux-based schemes on multi-level meshes, built on first use
+        FluxPlan fluxw; // the same for six-cell line stencils (WENO5)
+        DevBuf d_flux, d_fluxw, d_fluxtab;
 
         void invalidate_plans();
         DevBuf d_detail, d_tag, d_relmax;
@@ -520,12 +521,18 @@ namespace smr
         {
             throw std::invalid_argument("max_level too large (max_refinement_level is 20, samurai_config.hpp:50)");
         }
-        if (c->max_stencil_radius < 1 || c->max_stencil_radius > 2)
+        bool all_periodic = true;
+        for (int d = 0; d < c->dim; ++d)
+        {
+            all_periodic = all_periodic && c->periodic[d] != 0;
+        }
+        // a fully periodic mesh has no boundary: any ghost width up to 3 (max_stencil_size(6), the WENO5 stencil)
+        if (c->max_stencil_radius < 1 || c->max_stencil_radius > (all_periodic ? 3 : 2))
         {
             // ghost width 2 (the library default, mesh_config.hpp:388-393) is built for boundary conditions that fill one layer:
             // further-ghost extrapolation (bc/apply_field_bc.hpp:499-563), two-layer corner block (:313-466), contiguous-boundary
             // graduation rule (graduation.hpp:372-455).  Wider stencils (WENO5: radius 3) are not.
-            throw std::invalid_argument("max_stencil_radius must be 1 or 2");
+            throw std::invalid_argument("max_stencil_radius must be 1 or 2 (up to 3 on a fully periodic mesh)");
         }
         if (c->pred_radius < 0 || c->pred_radius > 1)
         {
@@ -666,7 +673,8 @@ namespace smr
     void MeshObj::invalidate_plans()
     {
         plan_ready = false;
-        flux.ready = false;
+        flux.ready  = false;
+        fluxw.ready = false;
     }
 
     static void ensure_plan(MeshObj& mo)
@@ -2533,9 +2541,71 @@ extern "C"
                 MeshObj& mo = *in.mesh;
                 check_field_ready(in);
                 const MeshConfig& cfg = mo.mesh.cfg;
-                if (kind != SMR_SCHEME_CONVECTION_UPWIND && kind != SMR_SCHEME_DIFFUSION_ORDER2 && kind != SMR_SCHEME_CONVECTION_UPWIND_NONLINEAR)
+                if (kind != SMR_SCHEME_CONVECTION_UPWIND && kind != SMR_SCHEME_DIFFUSION_ORDER2 && kind != SMR_SCHEME_CONVECTION_UPWIND_NONLINEAR
+                    && kind != SMR_SCHEME_CONVECTION_WENO5)
                 {
                     throw std::invalid_argument("unknown scheme kind");
+                }
+                if (kind == SMR_SCHEME_CONVECTION_WENO5)
+                {
+                    // six-cell line stencil: needs ghost width 3; boundary conditions that fill three layers (Dirichlet<3>) are not
+                    // built, so the scheme runs on fully periodic meshes (demos/FiniteVolume/linear_convection.cpp)
+                    if (!cfg.all_periodic() || cfg.ghost_width() < 3)
+                    {
+                        throw std::invalid_argument("make_convection_weno5 needs a fully periodic mesh with max_stencil_size(6)");
+                    }
+                    ensure_plan(mo);
+                    if (!in.ghosts_valid)
+                    {
+                        do_update_ghost(in);
+                    }
+                    if (!mo.fluxw.ready)
+                    {
+                        const double t0 = now();
+                        build_fluxw_plan(mo.mesh, mo.fluxw, mo.filter);
+                        g.stats.host_batch_seconds += now() - t0;
+                        SMR_CUDA(cudaStreamSynchronize(g.stream));
+                        upload_arena(mo.fluxw.arena, mo.d_fluxw);
+                    }
+                    if (static_cast<size_t>(mo.mesh.nref) * sizeof(double) > out.data.cap)
+                    {
+                        SMR_CUDA(cudaStreamSynchronize(g.stream));
+                    }
+                    out.data.ensure(static_cast<size_t>(mo.mesh.nref) * sizeof(double));
+                    out.n = mo.mesh.nref;
+                    Section sec;
+                    out.ghosts_valid = false;
+                    mg_barrier();
+                    SMR_CUDA(cudaMemsetAsync(out.data.p, 0, static_cast<size_t>(out.n) * sizeof(double), g.stream)); // output.fill(0)
+                    mg_barrier();
+                    static thread_local std::vector<double> wtab;
+                    wtab.assign(2 * SMR_MAX_LEVELS * 6, 0.0);
+                    for (int l = 0; l <= cfg.max_level && l < SMR_MAX_LEVELS; ++l)
+                    {
+                        const double h = cfg.cell_length(l), hf = cfg.cell_length(l + 1);
+                        wtab[static_cast<size_t>(l) * 6]                    = h_factor(cfg.dim, h, h);
+                        wtab[static_cast<size_t>(SMR_MAX_LEVELS + l) * 6] = h_factor(cfg.dim, hf, h);
+                    }
+                    mo.d_fluxtab.ensure(wtab.size() * sizeof(double));
+                    SMR_CUDA(cudaMemcpyAsync(mo.d_fluxtab.p, wtab.data(), wtab.size() * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+                    const double* u    = static_cast<const double*>(in.data.p);
+                    double* o          = static_cast<double*>(out.data.p);
+                    const int64_t* aux = reinterpret_cast<const int64_t*>(static_cast<const char*>(mo.d_fluxw.p) + mo.fluxw.items.aux);
+                    const double* tab  = static_cast<const double*>(mo.d_fluxtab.p);
+                    const double v[3]  = {params[0], cfg.dim > 1 ? params[1] : 0.0, cfg.dim > 2 ? params[2] : 0.0};
+                    switch (cfg.dim)
+                    {
+                        case 1:
+                            launch<smr_item_fluxw>(SMR_FAM_FV, mo.d_fluxw.p, mo.fluxw.items, FluxWenoOp<1>{u, o, aux, tab, {v[0], v[1], v[2]}, scale});
+                            break;
+                        case 2:
+                            launch<smr_item_fluxw>(SMR_FAM_FV, mo.d_fluxw.p, mo.fluxw.items, FluxWenoOp<2>{u, o, aux, tab, {v[0], v[1], v[2]}, scale});
+                            break;
+                        default:
+                            launch<smr_item_fluxw>(SMR_FAM_FV, mo.d_fluxw.p, mo.fluxw.items, FluxWenoOp<3>{u, o, aux, tab, {v[0], v[1], v[2]}, scale});
+                            break;
+                    }
+                    return;
                 }
                 if (cfg.any_periodic())
                 {
@@ -2994,6 +3064,55 @@ extern "C"
                     o[3]                = key_z(ref.key[static_cast<size_t>(row)]);
                     o[4]                = it[i].n;
                     o[5]                = it[i].kinds;
+                }
+            });
+    }
+
+    int smr_debug_fluxw_apply(smr_mesh_t m, const double* u, const double* velocity, double scale, double* out)
+    {
+        return guarded(
+            [&]
+            {
+                MeshObj& mo           = get_mesh(m);
+                const MeshConfig& cfg = mo.mesh.cfg;
+                if (!cfg.all_periodic() || cfg.ghost_width() < 3)
+                {
+                    throw std::invalid_argument("make_convection_weno5 needs a fully periodic mesh with max_stencil_size(6)");
+                }
+                FluxPlan fp;
+                build_fluxw_plan(mo.mesh, fp);
+                std::vector<double> tab(2 * SMR_MAX_LEVELS * 6, 0.0);
+                for (int l = 0; l <= cfg.max_level && l < SMR_MAX_LEVELS; ++l)
+                {
+                    const double h = cfg.cell_length(l), hf = cfg.cell_length(l + 1);
+                    tab[static_cast<size_t>(l) * 6]                    = h_factor(cfg.dim, h, h);
+                    tab[static_cast<size_t>(SMR_MAX_LEVELS + l) * 6] = h_factor(cfg.dim, hf, h);
+                }
+                const smr_item_fluxw* it = reinterpret_cast<const smr_item_fluxw*>(fp.arena.p + fp.items.items);
+                const int64_t* aux       = reinterpret_cast<const int64_t*>(fp.arena.p + fp.items.aux);
+                const double v[3]        = {velocity[0], cfg.dim > 1 ? velocity[1] : 0.0, cfg.dim > 2 ? velocity[2] : 0.0};
+                auto run = [&](auto op)
+                {
+                    for (int i = 0; i < fp.items.n_items; ++i)
+                    {
+                        for (int k = 0; k < it[i].n; ++k)
+                        {
+                            out[it[i].c + k] = op.compute(it[i], k);
+                        }
+                    }
+                };
+                std::fill(out, out + mo.mesh.nref, 0.0);
+                switch (cfg.dim)
+                {
+                    case 1:
+                        run(FluxWenoOp<1>{u, out, aux, tab.data(), {v[0], v[1], v[2]}, scale});
+                        break;
+                    case 2:
+                        run(FluxWenoOp<2>{u, out, aux, tab.data(), {v[0], v[1], v[2]}, scale});
+                        break;
+                    default:
+                        run(FluxWenoOp<3>{u, out, aux, tab.data(), {v[0], v[1], v[2]}, scale});
+                        break;
                 }
             });
     }

@@ -87,6 +87,26 @@ typedef struct
     int32_t mask;
 } smr_item_flux;
 
+/* leaf sub-interval for flux schemes with a six-cell line stencil {-2 .. 3} (make_convection_weno5, operators/convection_lin.hpp:95-178)
+ * on fully periodic meshes: like smr_item_flux, with the three own-level rows on each side of every transverse direction.  A face on a
+ * periodic boundary is classified by the leaf found at the wrapped position (interface.hpp:83-92, 179-189, 280-290) and reads the
+ * periodic ghosts at the unwrapped one. */
+#define SMR_FLUXW_AUX_SLOTS 56 /* x faces: [face*4 + cy + 2*cz] = offset of the stencil origin (cell left of the interface) in child
+                                  row (2y+cy, 2z+cz); transverse face f = 2..5: [8 + ((f-2)*2 + b)*6 + st] = offset of x = 2*start
+                                  in stencil row st (origin row - 2 + st) of the b-th child row of the other transverse direction */
+#define SMR_FLUXW_SWAP_SHIFT 12 /* kinds bit (12 + d): the minus face of direction d is a same-level interface through the periodic
+                                   boundary: the reference visits it after the regular same-level interfaces, i.e. after the plus face */
+typedef struct
+{
+    int64_t c;      /* offset of the first cell in its own row */
+    int64_t nb[12]; /* same x in rows y-3, y-2, y-1, y+1, y+2, y+3 [0..5] and z-3 .. z+3 [6..11] of the cell's own level */
+    int64_t fine;   /* first of this record's SMR_FLUXW_AUX_SLOTS aux entries (only if a face is FINE) */
+    int32_t n;
+    int32_t level;
+    int32_t kinds;  /* 2 bits per face as in smr_item_flux + the swap bits */
+    int32_t mask;
+} smr_item_fluxw;
+
 /* coarse interval filled by projection (numeric/projection.hpp:22-64) */
 typedef struct
 {

@@ -7,3 +7,6 @@ SMR_INST_BATCH(smr_item_flux, smr::FluxGenOp<3, 0>)
 SMR_INST_BATCH(smr_item_flux, smr::FluxGenOp<1, 1>)
 SMR_INST_BATCH(smr_item_flux, smr::FluxGenOp<2, 1>)
 SMR_INST_BATCH(smr_item_flux, smr::FluxGenOp<3, 1>)
+SMR_INST_BATCH(smr_item_fluxw, smr::FluxWenoOp<1>)
+SMR_INST_BATCH(smr_item_fluxw, smr::FluxWenoOp<2>)
+SMR_INST_BATCH(smr_item_fluxw, smr::FluxWenoOp<3>)

@@ -705,6 +705,150 @@ namespace smr
         }
     };
 
+    // make_convection_weno5<Field>(velocity) on a scalar field (operators/convection_lin.hpp:95-178, weno_impl.hpp:26-63): non-linear
+    // flux scheme with the line stencil {-2 .. 3}, gather form as above.  Fully periodic meshes only: a face on the periodic boundary
+    // reads the periodic ghosts; a same-level minus face through the boundary comes after the plus face (swap bit, items.h).
+    // `tab`: [0][l][0] = h_factor(h_l, h_l), [1][l][0] = h_factor(h_{l+1}, h_l).
+    template <int DIM>
+    struct FluxWenoOp
+    {
+        static constexpr bool two_phase = false;
+        static constexpr bool warp_uniform = false;
+        static constexpr int min_blocks = 1;
+        static constexpr int units_per_thread = SMR_CELLS_PER_THREAD;
+
+        const double* __restrict__ u;
+        double* __restrict__ out;
+        const int64_t* __restrict__ aux;
+        const double* __restrict__ tab;
+        double vel[3];
+        double scale; // `scale * scheme` (flux_based/algebraic_operators.hpp:38-46)
+
+        // compute_weno5_flux (Jiang & Shu) of f = v * {s0..s4} (v >= 0) or v * {s5..s1}; pow(x, 2) as x * x
+        static __host__ __device__ __forceinline__ double weno(double v, double s0, double s1, double s2, double s3, double s4, double s5)
+        {
+            double f0, f1, f2, f3, f4;
+            if (v >= 0)
+            {
+                f0 = s0 * v, f1 = s1 * v, f2 = s2 * v, f3 = s3 * v, f4 = s4 * v;
+            }
+            else
+            {
+                f0 = s5 * v, f1 = s4 * v, f2 = s3 * v, f3 = s2 * v, f4 = s1 * v;
+            }
+            const double q0 = 1. / 3 * f0 - 7. / 6 * f1 + 11. / 6 * f2;
+            const double q1 = -1. / 6 * f1 + 5. / 6 * f2 + 1. / 3 * f3;
+            const double q2 = 1. / 3 * f2 + 5. / 6 * f3 - 1. / 6 * f4;
+            const double a0 = f0 - 2 * f1 + f2, b0 = f0 - 4 * f1 + 3 * f2;
+            const double a1 = f1 - 2 * f2 + f3, b1 = f1 - f3;
+            const double a2 = f2 - 2 * f3 + f4, b2 = 3 * f2 - 4 * f3 + f4;
+            const double IS0 = 13. / 12 * (a0 * a0) + 1. / 4 * (b0 * b0);
+            const double IS1 = 13. / 12 * (a1 * a1) + 1. / 4 * (b1 * b1);
+            const double IS2 = 13. / 12 * (a2 * a2) + 1. / 4 * (b2 * b2);
+            const double eps = 1e-6;
+            const double e0 = eps + IS0, e1 = eps + IS1, e2 = eps + IS2;
+            const double al0 = 0.1 / (e0 * e0);
+            const double al1 = 0.6 / (e1 * e1);
+            const double al2 = 0.3 / (e2 * e2);
+            const double sa  = al0 + al1 + al2;
+            return (al0 / sa) * q0 + (al1 / sa) * q1 + (al2 / sa) * q2;
+        }
+
+        __host__ __device__ __forceinline__ double flux(double v, double s0, double s1, double s2, double s3, double s4, double s5) const
+        {
+            const double f = weno(v, s0, s1, s2, s3, s4, s5);
+            return scale != 1 ? f * scale : f;
+        }
+
+        // value of the own-level cell o steps along d from cell k of the record
+        __host__ __device__ __forceinline__ double val(const smr_item_fluxw& it, const double* c, int k, int d, int o) const
+        {
+            if (d == 0)
+            {
+                return c[o];
+            }
+            return o == 0 ? c[0] : u[it.nb[6 * (d - 1) + (o < 0 ? o + 3 : o + 2)] + k];
+        }
+
+        __host__ __device__ __forceinline__ double side(double acc, const smr_item_fluxw& it, int k, int d, int plus, int kind, const double* c,
+                                               double cs, double cj) const
+        {
+            const double sg = plus ? 1.0 : -1.0; // fluxes[1] = -fluxes[0] (flux_definition.hpp:125-136)
+            const double v  = vel[d];
+            if (kind != SMR_FACE_FINE)
+            {
+                const int o    = plus ? 0 : -1; // stencil origin = the cell left of the interface
+                const double f = flux(v, val(it, c, k, d, o - 2), val(it, c, k, d, o - 1), val(it, c, k, d, o), val(it, c, k, d, o + 1),
+                                      val(it, c, k, d, o + 2), val(it, c, k, d, o + 3));
+                return acc + (sg * f) * cs;
+            }
+            if (d == 0)
+            {
+                const int64_t* fx = aux + it.fine + plus * 4;
+#pragma unroll
+                for (int r = 0; r < (1 << (DIM - 1)); ++r)
+                {
+                    const double* s = u + fx[r];
+                    acc             = acc + (sg * flux(v, s[-2], s[-1], s[0], s[1], s[2], s[3])) * cj;
+                }
+                return acc;
+            }
+            const int64_t* fx = aux + it.fine + 8 + ((2 * d + plus) - 2) * 12;
+#pragma unroll
+            for (int b = 0; b < (DIM > 2 ? 2 : 1); ++b)
+            {
+                const int64_t* rows = fx + 6 * b;
+#pragma unroll
+                for (int x = 0; x < 2; ++x)
+                {
+                    const int64_t j = 2 * k + x;
+                    acc = acc + (sg * flux(v, u[rows[0] + j], u[rows[1] + j], u[rows[2] + j], u[rows[3] + j], u[rows[4] + j], u[rows[5] + j])) * cj;
+                }
+            }
+            return acc;
+        }
+
+        // the value of cell k of the record (host-callable: smr_debug_fluxw_apply evaluates the records without a device in the CPU tests)
+        __host__ __device__ __forceinline__ double compute(const smr_item_fluxw& it, int k) const
+        {
+            const double* c = u + it.c + k;
+            const double cs = tab[it.level * 6];
+            const double cj = tab[(SMR_MAX_LEVELS + it.level) * 6];
+            double acc      = 0.0;
+#pragma unroll
+            for (int d = 0; d < DIM; ++d)
+            {
+                int km = (it.kinds >> (4 * d)) & 3, kp = (it.kinds >> (4 * d + 2)) & 3;
+                bool swap = ((it.kinds >> (SMR_FLUXW_SWAP_SHIFT + d)) & 1) != 0;
+                if (d == 0)
+                {
+                    swap = swap && k == 0;
+                    km   = k != 0 ? SMR_FACE_SAME : km;
+                    kp   = k != it.n - 1 ? SMR_FACE_SAME : kp;
+                }
+                // pass numbers x2 as in FluxGenOp; a same-level minus face through the periodic boundary: 3
+                const int pm = km == SMR_FACE_SAME ? (swap ? 3 : 2) : (km == SMR_FACE_COARSE ? 4 : 7);
+                const int pp = kp == SMR_FACE_SAME ? 2 : (kp == SMR_FACE_COARSE ? 5 : 6);
+                if (pm <= pp)
+                {
+                    acc = side(acc, it, k, d, 0, km, c, cs, cj);
+                    acc = side(acc, it, k, d, 1, kp, c, cs, cj);
+                }
+                else
+                {
+                    acc = side(acc, it, k, d, 1, kp, c, cs, cj);
+                    acc = side(acc, it, k, d, 0, km, c, cs, cj);
+                }
+            }
+            return acc;
+        }
+
+        __device__ __forceinline__ void operator()(const smr_item_fluxw& it, int k) const
+        {
+            mstore(out + it.c + k, compute(it, k), static_cast<unsigned>(it.mask));
+        }
+    };
+
     // out = a * x + b * y on the leaves (the field-expression tail `u - dt * S(u)` is a = 1, b = -dt)
     struct LinCombOp
     {
