@@ -112,6 +112,11 @@ namespace CLI
                 auto it = m_options.find(key);
                 if (it == m_options.end())
                 {
+                    if (m_allow_extras) // CLI::App::allow_extras(): unknown arguments are left alone (PETSc options in the demos)
+                    {
+                        ++i;
+                        continue;
+                    }
                     throw std::invalid_argument("The following argument was not expected: " + key);
                 }
                 if (!inline_val.empty())
@@ -125,6 +130,12 @@ namespace CLI
                     i += 1 + it->second->parse(args, i + 1);
                 }
             }
+        }
+
+        App* allow_extras(bool allow = true)
+        {
+            m_allow_extras = allow;
+            return this;
         }
 
         std::string description;
@@ -192,6 +203,7 @@ namespace CLI
         }
 
         std::map<std::string, std::unique_ptr<Option>> m_options;
+        bool m_allow_extras = false;
     };
 }
 
@@ -1781,6 +1793,29 @@ namespace samurai
     auto make_scalar_field(const std::string& name, mesh_t& mesh) // field/scalar_field.hpp:171-215
     {
         return ScalarField<mesh_t, value_t>(name, mesh);
+    }
+
+    template <class value_t, class mesh_t>
+    auto make_scalar_field(const std::string& name, mesh_t& mesh, value_t init_value) // field/scalar_field.hpp:178-185
+    {
+        auto field = ScalarField<mesh_t, value_t>(name, mesh);
+        field.fill(init_value);
+        return field;
+    }
+
+    // initial value from a function of the cell centre (field/scalar_field.hpp:201-215)
+    template <class value_t, class mesh_t, class Func>
+        requires std::is_invocable_v<Func, typename Cell<mesh_t::dim>::coords_t>
+    auto make_scalar_field(const std::string& name, mesh_t& mesh, Func&& f)
+    {
+        auto field = ScalarField<mesh_t, value_t>(name, mesh);
+        field.fill(0);
+        for_each_cell(mesh,
+                      [&](const auto& cell)
+                      {
+                          field[cell] = f(cell.center());
+                      });
+        return field;
     }
 
     // `make_field<T, n>` only survives in the reference's README (README.md:104,132); kept as an alias of the scalar field

@@ -94,6 +94,26 @@ def test_cpp_heat_explicit_matches_reference_golden(gpu, tmp_path):
     assert np.max(np.abs(got[:, 3] - g["u"])) <= 1e-15
 
 
+def test_cpp_linear_convection_weno5_matches_reference_golden(gpu, tmp_path):
+    """tests/cpp/linear_convection_explicit.cpp (the explicit branch of demos/FiniteVolume/linear_convection.cpp kept statement for
+    statement: fully periodic box, max_stencil_size(6), make_convection_weno5, TVD-RK3 as field expressions, MRadaptation every step) with
+    the reference test's arguments (tests/test_demo_finite_volume.py:280-298) against the reference's own golden file
+    test_finite_volume_demo_linear_convection_explicit.h5 (tests/golden/linear_convection_explicit.npz)."""
+    exe = os.path.join(DEMOS, "linear-convection-explicit")
+    if not os.path.exists(exe):
+        pytest.skip("linear-convection-explicit not built")
+    r = subprocess.run([exe, "--path", str(tmp_path), "--filename", "lc", "--nfiles=1", "--min-level=1", "--max-level=6", "--Tf=0.1"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "steps 7" in r.stdout
+    got = _cells_h5(tmp_path / "lc.h5", 2, [-1.0, -1.0], 2.0)
+    g = np.load(os.path.join(GOLD, "linear_convection_explicit.npz"))
+    assert got.shape[0] == g["level"].size
+    assert np.array_equal(got[:, 0].astype(np.int64), g["level"].astype(np.int64))
+    assert np.array_equal(got[:, 1:3].astype(np.int64), g["idx"].astype(np.int64)), "mesh differs"
+    assert np.max(np.abs(got[:, 3] - g["u"])) <= 1e-13
+
+
 def test_reference_advection_1d_demo_unchanged_matches_oracle(gpu, tmp_path):
     """demos/FiniteVolume/advection_1d.cpp compiled unchanged (scalar velocity, `make_bc<Dirichlet<1>>(u, 0.)->on(left, right)`,
     `mesh_config().periodic(false)`), run with the reference test's `--Tf 0.1` (tests/test_demo_finite_volume.py:21-52) and
