@@ -1744,6 +1744,26 @@ namespace samurai
             return *this;
         }
 
+        // `rhs = scheme(u)` and `unp1 = v - dt * scheme(u)` for vector fields (make_convection_upwind<VectorField>() couples the components)
+        VectorField& operator=(const scheme_expr<VectorField>& e)
+        {
+            e.scheme.apply(*this, *e.u);
+            return *this;
+        }
+
+        VectorField& operator=(const scheme_step_expr<VectorField>& e)
+        {
+            VectorField tmp(e.rhs.e.scheme.name() + "(" + e.rhs.e.u->name() + ")", *p_mesh);
+            e.rhs.e.scheme.apply(tmp, *e.rhs.e.u);
+            for (std::size_t c = 0; c < n_comp; ++c)
+            {
+                b200::check(smr_field_resize(m_comp[c]->device()));
+                b200::check(smr_field_lincomb(m_comp[c]->device(), 1.0, e.v->component(c).device(), -e.rhs.factor, tmp.component(c).device()));
+                m_comp[c]->device_written();
+            }
+            return *this;
+        }
+
       private:
 
         std::string m_name;
@@ -1982,9 +2002,38 @@ namespace samurai
         // scheme.apply(out, in) (schemes/fv/FV_scheme.hpp:212-238): ghosts of `in` are updated if needed, out.fill(0), then the fluxes
         void apply(Field& out, Field& in) const
         {
-            b200::check(smr_scheme_apply(out.device(), in.device(), m_kind, m_params, m_scale));
-            out.device_written();
-            in.device_written(); // its ghosts may just have been updated on the device
+            if constexpr (requires { Field::n_comp; }) // VectorField: SoA component fields on one mesh
+            {
+                constexpr std::size_t n = Field::n_comp;
+                if (m_kind == SMR_SCHEME_CONVECTION_UPWIND_NONLINEAR) // couples the components: flux u(d) * u (convection_nonlin.hpp:24-76)
+                {
+                    smr_field_t oh[n], ih[n];
+                    for (std::size_t c = 0; c < n; ++c)
+                    {
+                        oh[c] = out.component(c).device();
+                        ih[c] = in.component(c).device();
+                    }
+                    b200::check(smr_scheme_apply_vector(oh, ih, static_cast<int>(n), m_kind, m_params, m_scale));
+                }
+                else // the linear schemes act on every component separately
+                {
+                    for (std::size_t c = 0; c < n; ++c)
+                    {
+                        b200::check(smr_scheme_apply(out.component(c).device(), in.component(c).device(), m_kind, m_params, m_scale));
+                    }
+                }
+                for (std::size_t c = 0; c < n; ++c)
+                {
+                    out.component(c).device_written();
+                    in.component(c).device_written();
+                }
+            }
+            else
+            {
+                b200::check(smr_scheme_apply(out.device(), in.device(), m_kind, m_params, m_scale));
+                out.device_written();
+                in.device_written(); // its ghosts may just have been updated on the device
+            }
         }
 
         FluxBasedScheme scaled(double s) const // flux_based/algebraic_operators.hpp:7-82
@@ -2061,6 +2110,12 @@ namespace samurai
     auto operator*(double dt, const scheme_expr<Field>& e)
     {
         return scaled_scheme_expr<Field>{dt, e};
+    }
+
+    template <class mesh_t, std::size_t n>
+    auto operator-(const VectorField<mesh_t, double, n>& v, const scaled_scheme_expr<VectorField<mesh_t, double, n>>& rhs)
+    {
+        return scheme_step_expr<VectorField<mesh_t, double, n>>{&v, rhs};
     }
 
     template <class mesh_t>

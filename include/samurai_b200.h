@@ -139,6 +139,10 @@ extern "C"
     };
 
     int smr_scheme_apply(smr_field_t out, smr_field_t u, int kind, const double* params, double scale);
+    /* the same for a vector field stored as n_comp SoA component fields on one mesh: out[c] = S(u)[c].  Vector schemes:
+     * SMR_SCHEME_CONVECTION_UPWIND_NONLINEAR = make_convection_upwind<VectorField>() with n_comp == dim (flux u(d) * u upwinded by the
+     * mean of component d, operators/convection_nonlin.hpp:24-76).  The linear schemes act per component: call smr_scheme_apply. */
+    int smr_scheme_apply_vector(const smr_field_t* out, const smr_field_t* u, int n_comp, int kind, const double* params, double scale);
     /* out = a * x + b * y over the leaves: the field-expression tail `unp1 = u - dt * scheme(u)` is (1, u, -dt, rhs) */
     int smr_field_lincomb(smr_field_t out, double a, smr_field_t x, double b, smr_field_t y);
 

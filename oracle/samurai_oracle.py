@@ -1205,6 +1205,21 @@ def burgers_upwind_flux(scale=1.0):
     return fn
 
 
+def burgers_upwind_flux_vector(dim, scale=1.0):
+    """`scale * make_convection_upwind<VectorField>()`, n_comp == dim (schemes/fv/operators/convection_nonlin.hpp:24-76): in direction d,
+    v = .5*(uL[d]+uR[d]); flux = v >= 0 ? uL[d]*uL : uR[d]*uR (every component)."""
+    def make(d):
+        def fn(ul, ur):
+            v = 0.5 * (ul[d] + ur[d])
+            out = []
+            for c in range(len(ul)):
+                f = np.where(v >= 0, ul[d] * ul[c], ur[d] * ur[c])
+                out.append(f * scale if scale != 1 else f)
+            return out
+        return fn
+    return [make(d) for d in range(dim)]
+
+
 def weno5_flux(velocity):
     """make_convection_weno5 for a scalar field (schemes/fv/operators/convection_lin.hpp:95-178): per direction d a function of the six
     stencil values u[-2..3]; f = velocity[d] * (u0..u4) if velocity[d] >= 0 else velocity[d] * (u5..u1); Jiang & Shu WENO5
@@ -1245,7 +1260,9 @@ def flux_nonlin_apply(mesh: Mesh, u, flux_fn, offsets=(0, 1)):
     through the boundary, seen once from each side (interface.hpp:83-92, 179-189, 280-290), and have no boundary interfaces
     (flux_based_scheme__nonlin.hpp:537-540)."""
     cfg, dim = mesh.cfg, mesh.cfg.dim
-    out = np.zeros(mesh.nref)
+    vector = isinstance(u, (list, tuple))  # vector field: one array per component; the flux functions get/return per-component lists
+    outs = [np.zeros(mesh.nref) for _ in (u if vector else [u])]
+    out = outs[0]
     leaf_lv = mesh.leaf_levels()
     lo = max(cfg.min_level, leaf_lv[0] - 1)
     hi = min(cfg.max_level, leaf_lv[-1] + 1)
@@ -1261,13 +1278,17 @@ def flux_nonlin_apply(mesh: Mesh, u, flux_fn, offsets=(0, 1)):
 
         def scatter(slevel, origin, run_left, run_right, lf, rf):
             # sequential per-cell accumulation (several fine cells may hit the same coarse cell)
-            vals = [u[mesh.index(slevel, translate(origin, [o * x for x in e]))] for o in offsets]
-            fl = fn(*vals)
-            a = fl * lf
-            b = (-fl) * rf
-            for k in range(run_left.size):
-                out[run_left[k]] = out[run_left[k]] + a[k]
-                out[run_right[k]] = out[run_right[k]] + b[k]
+            idx = [mesh.index(slevel, translate(origin, [o * x for x in e])) for o in offsets]
+            if vector:
+                fls = fn(*[[uc[i] for uc in u] for i in idx])  # one flux array per component
+            else:
+                fls = [fn(*[u[i] for i in idx])]
+            for oc, fl in zip(outs, fls):
+                a = fl * lf
+                b = (-fl) * rf
+                for k in range(run_left.size):
+                    oc[run_left[k]] = oc[run_left[k]] + a[k]
+                    oc[run_right[k]] = oc[run_right[k]] + b[k]
 
         def shift_of(level, sign):
             sh = [0] * dim
@@ -1322,14 +1343,18 @@ def flux_nonlin_apply(mesh: Mesh, u, flux_fn, offsets=(0, 1)):
             bd = cells[~mesh.in_domain(level, translate(cells, e))]
             for run in _runs(bd, dim):
                 bi = mesh.index(level, run)
-                fl = fn(u[bi], u[mesh.index(level, translate(run, e))])
-                out[bi] = out[bi] + fl * f
+                ni = mesh.index(level, translate(run, e))
+                fls = fn([uc[bi] for uc in u], [uc[ni] for uc in u]) if vector else [fn(u[bi], u[ni])]
+                for oc, fl in zip(outs, fls):
+                    oc[bi] = oc[bi] + fl * f
             bd = cells[~mesh.in_domain(level, translate(cells, me))]
             for run in _runs(bd, dim):
                 bi = mesh.index(level, run)
-                fl = fn(u[mesh.index(level, translate(run, me))], u[bi])
-                out[bi] = out[bi] + (-fl) * f  # flux_values[1] *= -(-factor)
-    return out
+                ni = mesh.index(level, translate(run, me))
+                fls = fn([uc[ni] for uc in u], [uc[bi] for uc in u]) if vector else [fn(u[ni], u[bi])]
+                for oc, fl in zip(outs, fls):
+                    oc[bi] = oc[bi] + (-fl) * f  # flux_values[1] *= -(-factor)
+    return outs if vector else out
 
 
 def lincomb_leaves(mesh: Mesh, a, x, b, y):

@@ -94,6 +94,7 @@ SYMBOLS = {
     "smr_fv_upwind": [_u64, _u64, _vp, _dbl],
     "smr_fv_upwind_burgers": [_u64, _u64, _vp, _dbl],
     "smr_scheme_apply": [_u64, _u64, _i32, _vp, _dbl],
+    "smr_scheme_apply_vector": [_vp, _vp, _i32, _i32, _vp, _dbl],
     "smr_field_lincomb": [_u64, _dbl, _u64, _dbl, _u64],
     "smr_adapt": [_vp, _i32, _dbl, _dbl, _P(_i32)],
     "smr_adapt_ex": [_vp, _i32, _dbl, _dbl, _i32, _P(_i32)],
@@ -583,14 +584,27 @@ class FluxScheme:
     def __init__(self, kind, params, name, scale=1.0):
         self.kind, self.params, self.name, self.scale = kind, np.ascontiguousarray(params, dtype=np.float64), name, float(scale)
 
-    def apply(self, out: ScalarField, u: ScalarField):
+    def apply(self, out, u):
+        if isinstance(u, VectorField):
+            if self.kind == CONVECTION_UPWIND_NONLINEAR:  # the one scheme that couples the components (flux u(d) * u)
+                n = u.n_comp
+                oh = (C.c_uint64 * n)(*[f._h for f in out.components])
+                uh = (C.c_uint64 * n)(*[f._h for f in u.components])
+                _check(load_library().smr_scheme_apply_vector(oh, uh, n, self.kind, self.params.ctypes.data, self.scale))
+            else:  # linear schemes act on every component separately
+                for o, f in zip(out.components, u.components):
+                    _check(load_library().smr_scheme_apply(o._h, f._h, self.kind, self.params.ctypes.data, self.scale))
+            return
         _check(load_library().smr_scheme_apply(out._h, u._h, self.kind, self.params.ctypes.data, self.scale))
 
     def __rmul__(self, scalar):
         return FluxScheme(self.kind, self.params, f"{scalar} * {self.name}", self.scale * float(scalar))
 
-    def __call__(self, u: ScalarField):
-        out = ScalarField(f"{self.name}({u.name})", u.mesh)
+    def __call__(self, u):
+        if isinstance(u, VectorField):
+            out = VectorField(f"{self.name}({u.name})", u.mesh, u.n_comp)
+        else:
+            out = ScalarField(f"{self.name}({u.name})", u.mesh)
         self.apply(out, u)
         return out
 

@@ -2712,6 +2712,116 @@ extern "C"
             });
     }
 
+    int smr_scheme_apply_vector(const smr_field_t* outh, const smr_field_t* inh, int n_comp, int kind, const double* params, double scale)
+    {
+        (void) params;
+        return guarded(
+            [&]
+            {
+                require_device();
+                if (kind != SMR_SCHEME_CONVECTION_UPWIND_NONLINEAR)
+                {
+                    throw std::invalid_argument("vector fields: only make_convection_upwind<VectorField>() is a vector scheme; apply the linear schemes per component");
+                }
+                if (n_comp < 2 || n_comp > 3)
+                {
+                    throw std::invalid_argument("make_convection_upwind() needs n_comp == dim (convection_nonlin.hpp:39-40)");
+                }
+                std::vector<FieldObj*> in, out;
+                for (int c = 0; c < n_comp; ++c)
+                {
+                    in.push_back(&get_field(inh[c]));
+                    out.push_back(&get_field(outh[c]));
+                }
+                MeshObj& mo           = *in[0]->mesh;
+                const MeshConfig& cfg = mo.mesh.cfg;
+                if (n_comp != cfg.dim)
+                {
+                    throw std::invalid_argument("make_convection_upwind() needs n_comp == dim (convection_nonlin.hpp:39-40)");
+                }
+                for (int c = 0; c < n_comp; ++c)
+                {
+                    if (in[c]->mesh != &mo || out[c]->mesh != &mo)
+                    {
+                        throw std::invalid_argument("scheme output must be a different field on the same mesh");
+                    }
+                    for (int k = 0; k < n_comp; ++k)
+                    {
+                        if (out[c] == in[k] || (k != c && out[c] == out[k]))
+                        {
+                            throw std::invalid_argument("scheme output must be a different field on the same mesh");
+                        }
+                    }
+                    check_field_ready(*in[c]);
+                }
+                if (cfg.any_periodic())
+                {
+                    throw std::invalid_argument("flux-based schemes with two-cell stencils are not implemented on periodic meshes");
+                }
+                ensure_plan(mo);
+                for (int c = 0; c < n_comp; ++c)
+                {
+                    if (!in[c]->ghosts_valid)
+                    {
+                        do_update_ghost(*in[c]);
+                    }
+                }
+                if (!mo.flux.ready)
+                {
+                    const double t0 = now();
+                    build_flux_plan(mo.mesh, mo.flux, mo.filter);
+                    g.stats.host_batch_seconds += now() - t0;
+                    SMR_CUDA(cudaStreamSynchronize(g.stream));
+                    upload_arena(mo.flux.arena, mo.d_flux);
+                }
+                const size_t bytes = static_cast<size_t>(mo.mesh.nref) * sizeof(double);
+                for (int c = 0; c < n_comp; ++c)
+                {
+                    if (bytes > out[c]->data.cap)
+                    {
+                        SMR_CUDA(cudaStreamSynchronize(g.stream));
+                    }
+                    out[c]->data.ensure(bytes);
+                    out[c]->n            = mo.mesh.nref;
+                    out[c]->ghosts_valid = false;
+                }
+                Section sec;
+                mg_barrier();
+                for (int c = 0; c < n_comp; ++c)
+                {
+                    SMR_CUDA(cudaMemsetAsync(out[c]->data.p, 0, bytes, g.stream)); // output.fill(0)
+                }
+                mg_barrier();
+                static thread_local std::vector<double> vtab;
+                vtab.assign(2 * SMR_MAX_LEVELS * 6, 0.0);
+                for (int l = 0; l <= cfg.max_level && l < SMR_MAX_LEVELS; ++l)
+                {
+                    const double h = cfg.cell_length(l), hf = cfg.cell_length(l + 1);
+                    vtab[static_cast<size_t>(l) * 6]                    = h_factor(cfg.dim, h, h);
+                    vtab[static_cast<size_t>(SMR_MAX_LEVELS + l) * 6] = h_factor(cfg.dim, hf, h);
+                }
+                mo.d_fluxtab.ensure(vtab.size() * sizeof(double));
+                SMR_CUDA(cudaMemcpyAsync(mo.d_fluxtab.p, vtab.data(), vtab.size() * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+                const int64_t* aux = reinterpret_cast<const int64_t*>(static_cast<const char*>(mo.d_flux.p) + mo.flux.items.aux);
+                const double* tab  = static_cast<const double*>(mo.d_fluxtab.p);
+                const double* up[3] = {nullptr, nullptr, nullptr};
+                double* op[3]       = {nullptr, nullptr, nullptr};
+                for (int c = 0; c < n_comp; ++c)
+                {
+                    up[c] = static_cast<const double*>(in[c]->data.p);
+                    op[c] = static_cast<double*>(out[c]->data.p);
+                }
+                if (cfg.dim == 2)
+                {
+                    launch<smr_item_flux>(SMR_FAM_FV, mo.d_flux.p, mo.flux.items, FluxVecOp<2>{{up[0], up[1], up[2]}, {op[0], op[1], op[2]}, aux, tab, scale});
+                }
+                else
+                {
+                    launch<smr_item_flux>(SMR_FAM_FV, mo.d_flux.p, mo.flux.items, FluxVecOp<3>{{up[0], up[1], up[2]}, {op[0], op[1], op[2]}, aux, tab, scale});
+                }
+            });
+    }
+
     int smr_field_lincomb(smr_field_t outh, double a, smr_field_t xh, double b, smr_field_t yh)
     {
         return guarded(

@@ -10,3 +10,5 @@ SMR_INST_BATCH(smr_item_flux, smr::FluxGenOp<3, 1>)
 SMR_INST_BATCH(smr_item_fluxw, smr::FluxWenoOp<1>)
 SMR_INST_BATCH(smr_item_fluxw, smr::FluxWenoOp<2>)
 SMR_INST_BATCH(smr_item_fluxw, smr::FluxWenoOp<3>)
+SMR_INST_BATCH(smr_item_flux, smr::FluxVecOp<2>)
+SMR_INST_BATCH(smr_item_flux, smr::FluxVecOp<3>)

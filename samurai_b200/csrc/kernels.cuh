@@ -705,6 +705,107 @@ namespace smr
         }
     };
 
+    // scale * make_convection_upwind<VectorField>() with n_comp == dim (operators/convection_nonlin.hpp:24-76): in direction d the
+    // interface flux is the whole vector  v >= 0 ? uL[d] * uL : uR[d] * uR,  v = .5 * (uL[d] + uR[d]).  Same records and term order
+    // as FluxGenOp<DIM, 1>; the components are separate SoA arrays on the same mesh, so one record serves all of them.
+    template <int DIM>
+    struct FluxVecOp
+    {
+        static constexpr bool two_phase = false;
+        static constexpr bool warp_uniform = false;
+        static constexpr int min_blocks = 1;
+        static constexpr int units_per_thread = SMR_CELLS_PER_THREAD;
+
+        const double* u[3];
+        double* out[3];
+        const int64_t* __restrict__ aux;
+        const double* __restrict__ tab;
+        double scale;
+
+        // acc[c] += (sg * flux_c(left cell at offset l, right cell at offset r)) * coef
+        __device__ __forceinline__ void add(double* acc, int d, int64_t l, int64_t r, double sg, double coef) const
+        {
+            const double uld = u[d][l], urd = u[d][r];
+            const bool up    = 0.5 * (uld + urd) >= 0;
+#pragma unroll
+            for (int c = 0; c < DIM; ++c)
+            {
+                double f = up ? uld * u[c][l] : urd * u[c][r];
+                f        = scale != 1 ? f * scale : f;
+                acc[c]   = acc[c] + (sg * f) * coef;
+            }
+        }
+
+        __device__ __forceinline__ void side(double* acc, const smr_item_flux& it, int k, int d, int plus, int kind, double cs, double cj) const
+        {
+            const double sg = plus ? 1.0 : -1.0;
+            const int64_t i = it.c + k;
+            if (kind != SMR_FACE_FINE)
+            {
+                const int64_t n = d == 0 ? i + (plus ? 1 : -1) : it.nb[2 * (d - 1) + plus] + k;
+                add(acc, d, plus ? i : n, plus ? n : i, sg, cs);
+                return;
+            }
+            const int64_t* fx = aux + it.fine + (2 * d + plus) * 4;
+            if (d == 0)
+            {
+#pragma unroll
+                for (int r = 0; r < (1 << (DIM - 1)); ++r)
+                {
+                    add(acc, d, fx[r], fx[r] + 1, sg, cj);
+                }
+                return;
+            }
+#pragma unroll
+            for (int b = 0; b < (DIM > 2 ? 2 : 1); ++b)
+            {
+                const int64_t r0 = fx[2 * b] + 2 * k, r1 = fx[2 * b + 1] + 2 * k;
+                add(acc, d, r0, r1, sg, cj);
+                add(acc, d, r0 + 1, r1 + 1, sg, cj);
+            }
+        }
+
+        __device__ __forceinline__ void operator()(const smr_item_flux& it, int k) const
+        {
+            const double cs = tab[it.level * 6];
+            const double cj = tab[(SMR_MAX_LEVELS + it.level) * 6];
+            double acc[DIM];
+#pragma unroll
+            for (int c = 0; c < DIM; ++c)
+            {
+                acc[c] = 0.0;
+            }
+#pragma unroll
+            for (int d = 0; d < DIM; ++d)
+            {
+                int km = (it.kinds >> (4 * d)) & 3, kp = (it.kinds >> (4 * d + 2)) & 3;
+                if (d == 0)
+                {
+                    km = k != 0 ? SMR_FACE_SAME : km;
+                    kp = k != it.n - 1 ? SMR_FACE_SAME : kp;
+                }
+                // pass numbers x2 as in FluxGenOp: minus {2, 4, 7, 9}, plus {2, 5, 6, 8}
+                const int pm = km == SMR_FACE_SAME ? 2 : (km == SMR_FACE_COARSE ? 4 : (km == SMR_FACE_FINE ? 7 : 9));
+                const int pp = kp == SMR_FACE_SAME ? 2 : (kp == SMR_FACE_COARSE ? 5 : (kp == SMR_FACE_FINE ? 6 : 8));
+                if (pm <= pp)
+                {
+                    side(acc, it, k, d, 0, km, cs, cj);
+                    side(acc, it, k, d, 1, kp, cs, cj);
+                }
+                else
+                {
+                    side(acc, it, k, d, 1, kp, cs, cj);
+                    side(acc, it, k, d, 0, km, cs, cj);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < DIM; ++c)
+            {
+                mstore(out[c] + it.c + k, acc[c], static_cast<unsigned>(it.mask));
+            }
+        }
+    };
+
     // make_convection_weno5<Field>(velocity) on a scalar field (operators/convection_lin.hpp:95-178, weno_impl.hpp:26-63): non-linear
     // flux scheme with the line stencil {-2 .. 3}, gather form as above.  Fully periodic meshes only: a face on the periodic boundary
     // reads the periodic ghosts; a same-level minus face through the boundary comes after the plus face (swap bit, items.h).

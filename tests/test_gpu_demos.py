@@ -284,6 +284,62 @@ def test_cpp_vector_field_matches_oracle(gpu):
         assert np.array_equal(got[:, 3 + comp], fields[comp][ix]), f"component {comp}: max abs diff {np.max(np.abs(got[:, 3 + comp] - fields[comp][ix])):.3e}"
 
 
+def test_cpp_vector_burgers_upwind_matches_oracle(gpu):
+    """tests/cpp/vector_burgers.cpp: `make_convection_upwind<VectorField>()` (vector form: flux u(d) * u upwinded by the
+    mean of component d, operators/convection_nonlin.hpp:24-76) in `unp1 = u - dt * conv(u)` through the drop-in headers, both
+    components adapted together.  Against the oracle's adapt_fields + flux_nonlin_apply on the component list: mesh identical,
+    both components bit-equal."""
+    import sys
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import samurai_oracle as so
+
+    exe = os.path.join(DEMOS, "vector-burgers")
+    if not os.path.exists(exe):
+        pytest.skip("vector-burgers not built")
+    steps = 10
+    r = subprocess.run([exe, str(steps)], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    lines = r.stdout.strip().splitlines()
+    k = next(i for i, ln in enumerate(lines) if ln.startswith("leaves "))
+    got = np.array([[float(x) for x in ln.split()] for ln in lines[k + 1:]])
+
+    cfg = so.MeshConfig(dim=2, min_level=2, max_level=6, pred_radius=1, origin=(-1.0, -1.0), scaling=2.0)
+    bcs = [so.Bc("dirichlet", 0.0), so.Bc("dirichlet", 0.0)]
+    mesh = so.Mesh.uniform(cfg)
+    L = cfg.max_level
+    c = mesh.cell_centers(L, mesh.cells[L])
+    ix = mesh.index(L, mesh.cells[L])
+    u0, u1 = np.zeros(mesh.nref), np.zeros(mesh.nref)
+    r0 = np.maximum(np.abs(c[:, 0]), np.abs(c[:, 1]))
+    r1 = np.maximum(np.abs(c[:, 0] - 0.25), np.abs(c[:, 1] + 0.25))
+    u0[ix] = np.where(r0 < 0.5, 1.0 - 2.0 * r0, 0.0)
+    u1[ix] = np.where(r1 < 0.4, -(1.0 - 2.5 * r1), 0.0)
+    fields = [u0, u1]
+    dt = 0.4 * cfg.cell_length(L)
+    flux = so.burgers_upwind_flux_vector(2)
+    mesh, fields = so.adapt_fields(mesh, fields, bcs, 1e-3, 1.0)
+    for _ in range(steps):
+        mesh, fields = so.adapt_fields(mesh, fields, bcs, 1e-3, 1.0)
+        for f, bc in zip(fields, bcs):
+            so.update_ghost_mr(mesh, f, bc)
+        rhs = so.flux_nonlin_apply(mesh, fields, flux)
+        new = []
+        for f, rh in zip(fields, rhs):
+            out = np.full(mesh.nref, np.nan)
+            for l in mesh.leaf_levels():
+                i = mesh.index(l, mesh.cells[l])
+                out[i] = f[i] - dt * rh[i]
+            new.append(out)
+        fields = new
+    lv, co, ix = mesh.leaf_table()
+    assert len(mesh.leaf_levels()) > 1
+    assert got.shape[0] == lv.size, f"{got.shape[0]} leaves vs oracle {lv.size}"
+    assert np.array_equal(got[:, 0].astype(np.int64), lv) and np.array_equal(got[:, 1:3].astype(np.int64), co), "mesh differs"
+    for comp in range(2):
+        assert np.array_equal(got[:, 3 + comp], fields[comp][ix]), f"component {comp}: max abs diff {np.max(np.abs(got[:, 3 + comp] - fields[comp][ix])):.3e}"
+
+
 def test_reference_demo_restart_roundtrip(gpu, tmp_path):
     """samurai::dump / samurai::load through the unchanged advection_2d demo (`--restart-file`, advection_2d.cpp:57,105-113):
     20 steps in one run equal 10 steps + checkpoint + 10 steps from the checkpoint, bit for bit (mesh and field)."""

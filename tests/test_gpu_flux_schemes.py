@@ -264,3 +264,39 @@ def test_flux_scheme_time_loop_matches_oracle(gpu, dim, lo, hi, kind):
         got = u.download()
         assert np.array_equal(got[leaf], ou[leaf]), f"step {step}: max diff {np.max(np.abs(got[leaf] - ou[leaf])):.3e}"
     assert len(omesh.leaf_levels()) > 1
+
+
+@pytest.mark.parametrize("dim,lo,hi", [(2, 2, 6), (2, 3, 7), (3, 2, 5)])
+@pytest.mark.parametrize("bc", [("dirichlet", 0.3), ("neumann", -0.2)])
+def test_vector_convection_upwind_across_level_jumps_bitwise(gpu, dim, lo, hi, bc):
+    """a9, vector form: make_convection_upwind<VectorField>() with n_comp == dim (flux u(d) * u upwinded by the mean of component d,
+    operators/convection_nonlin.hpp:24-76) on adapted meshes: every component of every leaf bit-identical to the oracle's restatement
+    of the reference's scatter loops (same-level, both jump orientations, boundary), with and without a scalar factor."""
+    pmesh, omesh, u0, ou0, obc, leaves = _adapted(dim, lo, hi, bc)
+    assert len(omesh.leaf_levels()) > 1
+    rng = np.random.default_rng(23)
+    v = sb.make_vector_field("v", pmesh, dim)
+    v.resize()
+    comps = []
+    for c in range(dim):
+        oc = ou0.copy()
+        oc[leaves] += 0.3 * rng.standard_normal(leaves.size) - 0.2 * c  # both signs of the upwinding velocity occur
+        comps.append(oc)
+    v.upload(np.stack(comps, axis=1))
+    sb.make_bc(v, sb.DIRICHLET if bc[0] == "dirichlet" else sb.NEUMANN, *([bc[1]] * dim))
+    og = [c.copy() for c in comps]
+    for c in og:
+        so.update_ghost_mr(omesh, c, obc)
+    for scale in (1.0, 0.5):
+        scheme = sb.make_convection_upwind() if scale == 1.0 else scale * sb.make_convection_upwind()
+        want = so.flux_nonlin_apply(omesh, og, so.burgers_upwind_flux_vector(dim, scale))
+        rhs = scheme(v)
+        got = rhs.download()
+        for c in range(dim):
+            bad = np.flatnonzero(got[leaves, c] != want[c][leaves])
+            assert bad.size == 0, (f"scale {scale} component {c}: {bad.size} of {leaves.size} leaves differ, "
+                                   f"max {np.max(np.abs(got[leaves, c] - want[c][leaves])):.3e}")
+        rhs.destroy()
+    v.destroy()
+    u0.destroy()
+    pmesh.destroy()
