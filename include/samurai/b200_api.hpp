@@ -2005,7 +2005,7 @@ namespace samurai
             if constexpr (requires { Field::n_comp; }) // VectorField: SoA component fields on one mesh
             {
                 constexpr std::size_t n = Field::n_comp;
-                if (m_kind == SMR_SCHEME_CONVECTION_UPWIND_NONLINEAR) // couples the components: flux u(d) * u (convection_nonlin.hpp:24-76)
+                if (m_kind == SMR_SCHEME_CONVECTION_UPWIND_NONLINEAR || m_kind == SMR_SCHEME_CONVECTION_WENO5_NONLINEAR) // flux u(d) * u couples the components
                 {
                     smr_field_t oh[n], ih[n];
                     for (std::size_t c = 0; c < n; ++c)
@@ -2072,6 +2072,13 @@ namespace samurai
             v[d] = velocity(d);
         }
         return FluxBasedScheme<Field>(SMR_SCHEME_CONVECTION_WENO5, v, "convection");
+    }
+
+    template <class Field>
+    auto make_convection_weno5() // operators/convection_nonlin.hpp:162-233 (f = u * u or u(d) * u, WENO5)
+    {
+        const double v[3] = {0, 0, 0};
+        return FluxBasedScheme<Field>(SMR_SCHEME_CONVECTION_WENO5_NONLINEAR, v, "convection(u)");
     }
 
     template <class Field>

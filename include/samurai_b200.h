@@ -132,16 +132,21 @@ extern "C"
         SMR_SCHEME_DIFFUSION_ORDER2  = 1, /* make_diffusion_order2<Field>(K),         operators/diffusion.hpp:123-175;     params = K[dim]        */
         SMR_SCHEME_CONVECTION_UPWIND_NONLINEAR = 2, /* make_convection_upwind<Field>() on a scalar field (Burgers, flux u*u upwinded by the
                                                        mean velocity), operators/convection_nonlin.hpp:24-76; params unused */
-        SMR_SCHEME_CONVECTION_WENO5 = 3 /* make_convection_weno5<Field>(velocity) on a scalar field: non-linear flux scheme with the line
+        SMR_SCHEME_CONVECTION_WENO5 = 3, /* make_convection_weno5<Field>(velocity) on a scalar field: non-linear flux scheme with the line
                                            stencil {-2 .. 3}, operators/convection_lin.hpp:95-178 + weno_impl.hpp:26-63; params = velocity[dim];
                                            fully periodic meshes with max_stencil_size(6) (interfaces through the periodic boundary:
                                            interface.hpp:83-92, 179-189, 280-290) */
+        SMR_SCHEME_CONVECTION_WENO5_NONLINEAR = 4 /* make_convection_weno5<Field>(): WENO5 of f(u) = u * u (scalar field) or u(d) * u
+                                                     (vector field with n_comp == dim, through smr_scheme_apply_vector), upwinded by the mean
+                                                     of the two cells next to the interface, operators/convection_nonlin.hpp:162-233;
+                                                     params unused; same mesh requirements as SMR_SCHEME_CONVECTION_WENO5 */
     };
 
     int smr_scheme_apply(smr_field_t out, smr_field_t u, int kind, const double* params, double scale);
     /* the same for a vector field stored as n_comp SoA component fields on one mesh: out[c] = S(u)[c].  Vector schemes:
      * SMR_SCHEME_CONVECTION_UPWIND_NONLINEAR = make_convection_upwind<VectorField>() with n_comp == dim (flux u(d) * u upwinded by the
-     * mean of component d, operators/convection_nonlin.hpp:24-76).  The linear schemes act per component: call smr_scheme_apply. */
+     * mean of component d, operators/convection_nonlin.hpp:24-76) and SMR_SCHEME_CONVECTION_WENO5_NONLINEAR.  The linear schemes act
+     * per component: call smr_scheme_apply. */
     int smr_scheme_apply_vector(const smr_field_t* out, const smr_field_t* u, int n_comp, int kind, const double* params, double scale);
     /* out = a * x + b * y over the leaves: the field-expression tail `unp1 = u - dt * scheme(u)` is (1, u, -dt, rhs) */
     int smr_field_lincomb(smr_field_t out, double a, smr_field_t x, double b, smr_field_t y);
@@ -216,11 +221,12 @@ extern "C"
      * 1 coarser leaf, 2 finer leaves, 3 domain boundary; the x-face kinds apply to the first / last cell only).
      * out == NULL: only count. */
     int smr_debug_flux_records(smr_mesh_t m, int32_t* out, int64_t capacity, int64_t* n_records);
-    /* host-side testing aid (no device needed, tests only): evaluates the records of the six-cell-stencil flux batch (WENO5,
-     * SMR_SCHEME_CONVECTION_WENO5) of the current mesh on the host with the kernel's own per-cell function; `u` and `out` are host
-     * arrays of nb_cells(reference) doubles, ghosts of `u` already updated.  Checks the host-built records and the operation order
-     * against the oracle where no GPU is present; it is not a compute path (single-threaded, rebuilds the records at every call). */
-    int smr_debug_fluxw_apply(smr_mesh_t m, const double* u, const double* velocity, double scale, double* out);
+    /* host-side testing aid (no device needed, tests only): evaluates the records of the six-cell-stencil flux batch (kinds
+     * SMR_SCHEME_CONVECTION_WENO5 / _WENO5_NONLINEAR) of the current mesh on the host with the kernel's own per-cell function; `u` and
+     * `out` are host arrays of n_comp x nb_cells(reference) doubles (one component after the other), ghosts of `u` already updated.
+     * Checks the host-built records and the operation order against the oracle where no GPU is present; it is not a compute path
+     * (single-threaded, rebuilds the records at every call). */
+    int smr_debug_fluxw_apply(smr_mesh_t m, const double* u, int n_comp, int kind, const double* velocity, double scale, double* out);
 
     /* the demos' initial condition as a device kernel over the leaves: u = inside where |center(cell) - c|^2 <= r^2,
      * else outside (only written when overwrite_outside != 0)

@@ -1220,34 +1220,76 @@ def burgers_upwind_flux_vector(dim, scale=1.0):
     return [make(d) for d in range(dim)]
 
 
+def _weno5(f):
+    """compute_weno5_flux (schemes/fv/operators/weno_impl.hpp:26-63, Jiang & Shu 1996) of the five flux values f[0..4], same
+    operation order; pow(x, 2) taken as x * x."""
+    j = 2
+    q0 = 1. / 3 * f[j - 2] - 7. / 6 * f[j - 1] + 11. / 6 * f[j]
+    q1 = -1. / 6 * f[j - 1] + 5. / 6 * f[j] + 1. / 3 * f[j + 1]
+    q2 = 1. / 3 * f[j] + 5. / 6 * f[j + 1] - 1. / 6 * f[j + 2]
+    sq = lambda x: x * x
+    IS0 = 13. / 12 * sq(f[j - 2] - 2 * f[j - 1] + f[j]) + 1. / 4 * sq(f[j - 2] - 4 * f[j - 1] + 3 * f[j])
+    IS1 = 13. / 12 * sq(f[j - 1] - 2 * f[j] + f[j + 1]) + 1. / 4 * sq(f[j - 1] - f[j + 1])
+    IS2 = 13. / 12 * sq(f[j] - 2 * f[j + 1] + f[j + 2]) + 1. / 4 * sq(3 * f[j] - 4 * f[j + 1] + f[j + 2])
+    eps = 1e-6
+    a0 = 0.1 / sq(eps + IS0)
+    a1 = 0.6 / sq(eps + IS1)
+    a2 = 0.3 / sq(eps + IS2)
+    sa = a0 + a1 + a2
+    return (a0 / sa) * q0 + (a1 / sa) * q1 + (a2 / sa) * q2
+
+
 def weno5_flux(velocity):
     """make_convection_weno5 for a scalar field (schemes/fv/operators/convection_lin.hpp:95-178): per direction d a function of the six
-    stencil values u[-2..3]; f = velocity[d] * (u0..u4) if velocity[d] >= 0 else velocity[d] * (u5..u1); Jiang & Shu WENO5
-    (schemes/fv/operators/weno_impl.hpp:26-63, same operation order; pow(x, 2) taken as x * x)."""
+    stencil values u[-2..3]; f = velocity[d] * (u0..u4) if velocity[d] >= 0 else velocity[d] * (u5..u1), then WENO5."""
     def make(d):
         v = float(velocity[d])
 
         def fn(u0, u1, u2, u3, u4, u5):
-            f = [u0 * v, u1 * v, u2 * v, u3 * v, u4 * v] if v >= 0 else [u5 * v, u4 * v, u3 * v, u2 * v, u1 * v]
-            j = 2
-            q0 = 1. / 3 * f[j - 2] - 7. / 6 * f[j - 1] + 11. / 6 * f[j]
-            q1 = -1. / 6 * f[j - 1] + 5. / 6 * f[j] + 1. / 3 * f[j + 1]
-            q2 = 1. / 3 * f[j] + 5. / 6 * f[j + 1] - 1. / 6 * f[j + 2]
-            sq = lambda x: x * x
-            IS0 = 13. / 12 * sq(f[j - 2] - 2 * f[j - 1] + f[j]) + 1. / 4 * sq(f[j - 2] - 4 * f[j - 1] + 3 * f[j])
-            IS1 = 13. / 12 * sq(f[j - 1] - 2 * f[j] + f[j + 1]) + 1. / 4 * sq(f[j - 1] - f[j + 1])
-            IS2 = 13. / 12 * sq(f[j] - 2 * f[j + 1] + f[j + 2]) + 1. / 4 * sq(3 * f[j] - 4 * f[j + 1] + f[j + 2])
-            eps = 1e-6
-            a0 = 0.1 / sq(eps + IS0)
-            a1 = 0.6 / sq(eps + IS1)
-            a2 = 0.3 / sq(eps + IS2)
-            sa = a0 + a1 + a2
-            return (a0 / sa) * q0 + (a1 / sa) * q1 + (a2 / sa) * q2
+            return _weno5([u0 * v, u1 * v, u2 * v, u3 * v, u4 * v] if v >= 0 else [u5 * v, u4 * v, u3 * v, u2 * v, u1 * v])
         return fn
     return [make(d) for d in range(len(velocity))]
 
 
+def weno5_flux_nonlinear(dim, n_comp=1, scale=1.0):
+    """`scale * make_convection_weno5<Field>()` (schemes/fv/operators/convection_nonlin.hpp:162-233): f(u) = u * u (scalar) or
+    u(d) * u (vector, n_comp == dim); upwinded by v = .5 * (u[2] + u[3]) (component d for vectors): WENO5 of f(u0..u4) if v >= 0
+    else of f(u5..u1), component by component."""
+    def make(d):
+        def fn(*u):
+            if n_comp == 1:
+                v = 0.5 * (u[2] + u[3])
+                f = [x * x for x in u]
+                out = np.where(v >= 0, _weno5(f[0:5]), _weno5([f[5], f[4], f[3], f[2], f[1]]))
+                return out * scale if scale != 1 else out
+            v = 0.5 * (u[2][d] + u[3][d])
+            outs = []
+            for c in range(n_comp):
+                f = [x[d] * x[c] for x in u]
+                o = np.where(v >= 0, _weno5(f[0:5]), _weno5([f[5], f[4], f[3], f[2], f[1]]))
+                outs.append(o * scale if scale != 1 else o)
+            return outs
+        return fn
+    return [make(d) for d in range(dim)]
+
+
 WENO5_OFFSETS = (-2, -1, 0, 1, 2, 3)  # line_stencil<dim, d>(-2, -1, 0, 1, 2, 3), convection_lin.hpp:115
+
+
+def _scatter_pairs(out, left, a, right, b):
+    """for k: out[left[k]] += a[k]; out[right[k]] += b[k] -- the reference's sequential scatter, vectorised where that keeps every
+    cell's order of additions: disjoint sides (np.add.at is sequential per index), or the x-direction run right == left + 1 with
+    unique cells, where a cell first receives b (as the right cell of interface k - 1) and then a (as the left cell of interface k)."""
+    if left.size > 1 and np.array_equal(right[:-1], left[1:]) and np.all(np.diff(left) == 1):
+        out[right] += b
+        out[left] += a
+    elif left.size == 1 or not np.intersect1d(left, right).size:
+        np.add.at(out, left, a)
+        np.add.at(out, right, b)
+    else:
+        for k in range(left.size):
+            out[left[k]] = out[left[k]] + a[k]
+            out[right[k]] = out[right[k]] + b[k]
 
 
 def flux_nonlin_apply(mesh: Mesh, u, flux_fn, offsets=(0, 1)):
@@ -1286,9 +1328,7 @@ def flux_nonlin_apply(mesh: Mesh, u, flux_fn, offsets=(0, 1)):
             for oc, fl in zip(outs, fls):
                 a = fl * lf
                 b = (-fl) * rf
-                for k in range(run_left.size):
-                    oc[run_left[k]] = oc[run_left[k]] + a[k]
-                    oc[run_right[k]] = oc[run_right[k]] + b[k]
+                _scatter_pairs(oc, run_left, a, run_right, b)
 
         def shift_of(level, sign):
             sh = [0] * dim

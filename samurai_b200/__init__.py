@@ -112,7 +112,7 @@ SYMBOLS = {
     "smr_mg_leaf_owners": [_u64, _vp, _i64],
     "smr_debug_host_rebuild": [_u64, _i32, _P(_dbl), _P(_dbl), _P(_i64)],
     "smr_debug_flux_records": [_u64, _vp, _i64, _P(_i64)],
-    "smr_debug_fluxw_apply": [_u64, _vp, _vp, _dbl, _vp],
+    "smr_debug_fluxw_apply": [_u64, _vp, _i32, _i32, _vp, _dbl, _vp],
     "smr_profile_enable": [_i32],
     "smr_profile_get": [_i32, _P(_u64), _P(_dbl), _P(_u64)],
     "smr_profile_get_bytes": [_i32, _P(_u64)],
@@ -411,13 +411,17 @@ class MRMesh:
             _check(load_library().smr_debug_flux_records(self._h, out.ctypes.data, n.value, C.byref(n)))
         return out
 
-    def debug_fluxw_apply(self, u, velocity, scale=1.0):
-        """Host evaluation of the WENO5 flux records (tests only; ghosts of `u` must be up to date)."""
-        u = np.ascontiguousarray(u, dtype=np.float64)
-        v = np.ascontiguousarray(list(velocity) + [0.0] * (3 - len(velocity)), dtype=np.float64)
-        out = np.zeros_like(u)
-        _check(load_library().smr_debug_fluxw_apply(self._h, u.ctypes.data, v.ctypes.data, float(scale), out.ctypes.data))
-        return out
+    def debug_fluxw_apply(self, u, velocity=None, scale=1.0):
+        """Host evaluation of the WENO5 flux records (tests only; ghosts of `u` must be up to date).  `u`: one array, or a list of
+        component arrays; without a velocity the non-linear form make_convection_weno5<Field>()."""
+        comps = list(u) if isinstance(u, (list, tuple)) else [u]
+        soa = np.ascontiguousarray(np.stack([np.asarray(c, dtype=np.float64) for c in comps]))
+        kind = CONVECTION_WENO5 if velocity is not None else CONVECTION_WENO5_NONLINEAR
+        v = np.ascontiguousarray(list(velocity if velocity is not None else []) + [0.0] * (3 - len(velocity if velocity is not None else [])),
+                                 dtype=np.float64)
+        out = np.zeros_like(soa)
+        _check(load_library().smr_debug_fluxw_apply(self._h, soa.ctypes.data, len(comps), kind, v.ctypes.data, float(scale), out.ctypes.data))
+        return [out[c] for c in range(len(comps))] if isinstance(u, (list, tuple)) else out[0]
 
     def update_from_tags(self, tags):
         tags = np.ascontiguousarray(tags, dtype=np.uint8)
@@ -574,7 +578,7 @@ def upwind_scalar_burgers_step(unp1: ScalarField, u: ScalarField, k, dt):
     _check(load_library().smr_fv_upwind_burgers(unp1._h, u._h, k.ctypes.data, float(dt)))
 
 
-CONVECTION_UPWIND, DIFFUSION_ORDER2, CONVECTION_UPWIND_NONLINEAR, CONVECTION_WENO5 = 0, 1, 2, 3
+CONVECTION_UPWIND, DIFFUSION_ORDER2, CONVECTION_UPWIND_NONLINEAR, CONVECTION_WENO5, CONVECTION_WENO5_NONLINEAR = 0, 1, 2, 3, 4
 
 
 class FluxScheme:
@@ -586,7 +590,7 @@ class FluxScheme:
 
     def apply(self, out, u):
         if isinstance(u, VectorField):
-            if self.kind == CONVECTION_UPWIND_NONLINEAR:  # the one scheme that couples the components (flux u(d) * u)
+            if self.kind in (CONVECTION_UPWIND_NONLINEAR, CONVECTION_WENO5_NONLINEAR):  # the schemes that couple the components (flux u(d) * u)
                 n = u.n_comp
                 oh = (C.c_uint64 * n)(*[f._h for f in out.components])
                 uh = (C.c_uint64 * n)(*[f._h for f in u.components])
@@ -617,9 +621,12 @@ def make_convection_upwind(velocity=None):
     return FluxScheme(CONVECTION_UPWIND, velocity, "convection")
 
 
-def make_convection_weno5(velocity):
+def make_convection_weno5(velocity=None):
     """samurai::make_convection_weno5<Field>(velocity) (schemes/fv/operators/convection_lin.hpp:95-178): WENO5 (Jiang & Shu) linear
-    convection, a non-linear flux scheme with a six-cell line stencil; fully periodic meshes with max_stencil_size(6)."""
+    convection, a non-linear flux scheme with a six-cell line stencil; fully periodic meshes with max_stencil_size(6).  Without a
+    velocity the Burgers form make_convection_weno5<Field>() (operators/convection_nonlin.hpp:162-233; scalar or n_comp == dim)."""
+    if velocity is None:
+        return FluxScheme(CONVECTION_WENO5_NONLINEAR, [0.0, 0.0, 0.0], "convection(u)")
     v = list(velocity) + [0.0] * (3 - len(velocity))
     return FluxScheme(CONVECTION_WENO5, v, "convection")
 

@@ -2016,6 +2016,102 @@ namespace smr
         }
     }
 
+    static void wide_tab(const MeshConfig& cfg, std::vector<double>& tab)
+    {
+        tab.assign(2 * SMR_MAX_LEVELS * 6, 0.0);
+        for (int l = 0; l <= cfg.max_level && l < SMR_MAX_LEVELS; ++l)
+        {
+            const double h = cfg.cell_length(l), hf = cfg.cell_length(l + 1);
+            tab[static_cast<size_t>(l) * 6]                    = h_factor(cfg.dim, h, h);
+            tab[static_cast<size_t>(SMR_MAX_LEVELS + l) * 6] = h_factor(cfg.dim, hf, h);
+        }
+    }
+
+    // calls fn(op) with the FluxWenoOp instantiation of (dim, kind, n_comp)
+    template <class Fn>
+    static void with_weno_op(int dim, int kind, int nc, const double* const* u, double* const* o, const int64_t* aux, const double* tab,
+                             const double* params, double scale, Fn&& fn)
+    {
+        const double v[3] = {params ? params[0] : 0.0, params && dim > 1 ? params[1] : 0.0, params && dim > 2 ? params[2] : 0.0};
+        const bool nonlin = kind == SMR_SCHEME_CONVECTION_WENO5_NONLINEAR;
+#define SMR_WENO_CASE(D, N, C)                                                                                             \
+    if (dim == D && nonlin == (N != 0) && nc == C)                                                                         \
+    {                                                                                                                      \
+        fn(FluxWenoOp<D, N, C>{{u[0], C > 1 ? u[1] : nullptr, C > 2 ? u[2] : nullptr}, {o[0], C > 1 ? o[1] : nullptr, C > 2 ? o[2] : nullptr}, \
+                               aux, tab, {v[0], v[1], v[2]}, scale});                                                       \
+        return;                                                                                                            \
+    }
+        SMR_WENO_CASE(1, 0, 1)
+        SMR_WENO_CASE(2, 0, 1)
+        SMR_WENO_CASE(3, 0, 1)
+        SMR_WENO_CASE(1, 1, 1)
+        SMR_WENO_CASE(2, 1, 1)
+        SMR_WENO_CASE(3, 1, 1)
+        SMR_WENO_CASE(2, 1, 2)
+        SMR_WENO_CASE(3, 1, 3)
+#undef SMR_WENO_CASE
+        throw std::invalid_argument("make_convection_weno5: scalar fields, or (without a velocity) vector fields with n_comp == dim");
+    }
+
+    // WENO5 schemes (six-cell line stencil): ghost width 3; boundary conditions that fill three layers (Dirichlet<3>) are not built, so
+    // they run on fully periodic meshes (demos/FiniteVolume/linear_convection.cpp)
+    static void apply_wide_scheme(MeshObj& mo, FieldObj* const* in, FieldObj* const* out, int nc, int kind, const double* params, double scale)
+    {
+        const MeshConfig& cfg = mo.mesh.cfg;
+        if (!cfg.all_periodic() || cfg.ghost_width() < 3)
+        {
+            throw std::invalid_argument("make_convection_weno5 needs a fully periodic mesh with max_stencil_size(6)");
+        }
+        ensure_plan(mo);
+        for (int c = 0; c < nc; ++c)
+        {
+            if (!in[c]->ghosts_valid)
+            {
+                do_update_ghost(*in[c]);
+            }
+        }
+        if (!mo.fluxw.ready)
+        {
+            const double t0 = now();
+            build_fluxw_plan(mo.mesh, mo.fluxw, mo.filter);
+            g.stats.host_batch_seconds += now() - t0;
+            SMR_CUDA(cudaStreamSynchronize(g.stream));
+            upload_arena(mo.fluxw.arena, mo.d_fluxw);
+        }
+        const size_t bytes = static_cast<size_t>(mo.mesh.nref) * sizeof(double);
+        for (int c = 0; c < nc; ++c)
+        {
+            if (bytes > out[c]->data.cap)
+            {
+                SMR_CUDA(cudaStreamSynchronize(g.stream));
+            }
+            out[c]->data.ensure(bytes);
+            out[c]->n            = mo.mesh.nref;
+            out[c]->ghosts_valid = false;
+        }
+        Section sec;
+        mg_barrier();
+        for (int c = 0; c < nc; ++c)
+        {
+            SMR_CUDA(cudaMemsetAsync(out[c]->data.p, 0, bytes, g.stream)); // output.fill(0)
+        }
+        mg_barrier();
+        static thread_local std::vector<double> wtab;
+        wide_tab(cfg, wtab);
+        mo.d_fluxtab.ensure(wtab.size() * sizeof(double));
+        SMR_CUDA(cudaMemcpyAsync(mo.d_fluxtab.p, wtab.data(), wtab.size() * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+        const double* up[3] = {nullptr, nullptr, nullptr};
+        double* op[3]       = {nullptr, nullptr, nullptr};
+        for (int c = 0; c < nc; ++c)
+        {
+            up[c] = static_cast<const double*>(in[c]->data.p);
+            op[c] = static_cast<double*>(out[c]->data.p);
+        }
+        const int64_t* aux = reinterpret_cast<const int64_t*>(static_cast<const char*>(mo.d_fluxw.p) + mo.fluxw.items.aux);
+        with_weno_op(cfg.dim, kind, nc, up, op, aux, static_cast<const double*>(mo.d_fluxtab.p), params, scale,
+                     [&](const auto& opr) { launch<smr_item_fluxw>(SMR_FAM_FV, mo.d_fluxw.p, mo.fluxw.items, opr); });
+    }
+
     template <class F>
     static int guarded(F&& f)
     {
@@ -2542,69 +2638,15 @@ extern "C"
                 check_field_ready(in);
                 const MeshConfig& cfg = mo.mesh.cfg;
                 if (kind != SMR_SCHEME_CONVECTION_UPWIND && kind != SMR_SCHEME_DIFFUSION_ORDER2 && kind != SMR_SCHEME_CONVECTION_UPWIND_NONLINEAR
-                    && kind != SMR_SCHEME_CONVECTION_WENO5)
+                    && kind != SMR_SCHEME_CONVECTION_WENO5 && kind != SMR_SCHEME_CONVECTION_WENO5_NONLINEAR)
                 {
                     throw std::invalid_argument("unknown scheme kind");
                 }
-                if (kind == SMR_SCHEME_CONVECTION_WENO5)
+                if (kind == SMR_SCHEME_CONVECTION_WENO5 || kind == SMR_SCHEME_CONVECTION_WENO5_NONLINEAR)
                 {
-                    // six-cell line stencil: needs ghost width 3; boundary conditions that fill three layers (Dirichlet<3>) are not
-                    // built, so the scheme runs on fully periodic meshes (demos/FiniteVolume/linear_convection.cpp)
-                    if (!cfg.all_periodic() || cfg.ghost_width() < 3)
-                    {
-                        throw std::invalid_argument("make_convection_weno5 needs a fully periodic mesh with max_stencil_size(6)");
-                    }
-                    ensure_plan(mo);
-                    if (!in.ghosts_valid)
-                    {
-                        do_update_ghost(in);
-                    }
-                    if (!mo.fluxw.ready)
-                    {
-                        const double t0 = now();
-                        build_fluxw_plan(mo.mesh, mo.fluxw, mo.filter);
-                        g.stats.host_batch_seconds += now() - t0;
-                        SMR_CUDA(cudaStreamSynchronize(g.stream));
-                        upload_arena(mo.fluxw.arena, mo.d_fluxw);
-                    }
-                    if (static_cast<size_t>(mo.mesh.nref) * sizeof(double) > out.data.cap)
-                    {
-                        SMR_CUDA(cudaStreamSynchronize(g.stream));
-                    }
-                    out.data.ensure(static_cast<size_t>(mo.mesh.nref) * sizeof(double));
-                    out.n = mo.mesh.nref;
-                    Section sec;
-                    out.ghosts_valid = false;
-                    mg_barrier();
-                    SMR_CUDA(cudaMemsetAsync(out.data.p, 0, static_cast<size_t>(out.n) * sizeof(double), g.stream)); // output.fill(0)
-                    mg_barrier();
-                    static thread_local std::vector<double> wtab;
-                    wtab.assign(2 * SMR_MAX_LEVELS * 6, 0.0);
-                    for (int l = 0; l <= cfg.max_level && l < SMR_MAX_LEVELS; ++l)
-                    {
-                        const double h = cfg.cell_length(l), hf = cfg.cell_length(l + 1);
-                        wtab[static_cast<size_t>(l) * 6]                    = h_factor(cfg.dim, h, h);
-                        wtab[static_cast<size_t>(SMR_MAX_LEVELS + l) * 6] = h_factor(cfg.dim, hf, h);
-                    }
-                    mo.d_fluxtab.ensure(wtab.size() * sizeof(double));
-                    SMR_CUDA(cudaMemcpyAsync(mo.d_fluxtab.p, wtab.data(), wtab.size() * sizeof(double), cudaMemcpyHostToDevice, g.stream));
-                    const double* u    = static_cast<const double*>(in.data.p);
-                    double* o          = static_cast<double*>(out.data.p);
-                    const int64_t* aux = reinterpret_cast<const int64_t*>(static_cast<const char*>(mo.d_fluxw.p) + mo.fluxw.items.aux);
-                    const double* tab  = static_cast<const double*>(mo.d_fluxtab.p);
-                    const double v[3]  = {params[0], cfg.dim > 1 ? params[1] : 0.0, cfg.dim > 2 ? params[2] : 0.0};
-                    switch (cfg.dim)
-                    {
-                        case 1:
-                            launch<smr_item_fluxw>(SMR_FAM_FV, mo.d_fluxw.p, mo.fluxw.items, FluxWenoOp<1>{u, o, aux, tab, {v[0], v[1], v[2]}, scale});
-                            break;
-                        case 2:
-                            launch<smr_item_fluxw>(SMR_FAM_FV, mo.d_fluxw.p, mo.fluxw.items, FluxWenoOp<2>{u, o, aux, tab, {v[0], v[1], v[2]}, scale});
-                            break;
-                        default:
-                            launch<smr_item_fluxw>(SMR_FAM_FV, mo.d_fluxw.p, mo.fluxw.items, FluxWenoOp<3>{u, o, aux, tab, {v[0], v[1], v[2]}, scale});
-                            break;
-                    }
+                    FieldObj* ip[1] = {&in};
+                    FieldObj* op[1] = {&out};
+                    apply_wide_scheme(mo, ip, op, 1, kind, params, scale);
                     return;
                 }
                 if (cfg.any_periodic())
@@ -2714,14 +2756,13 @@ extern "C"
 
     int smr_scheme_apply_vector(const smr_field_t* outh, const smr_field_t* inh, int n_comp, int kind, const double* params, double scale)
     {
-        (void) params;
         return guarded(
             [&]
             {
                 require_device();
-                if (kind != SMR_SCHEME_CONVECTION_UPWIND_NONLINEAR)
+                if (kind != SMR_SCHEME_CONVECTION_UPWIND_NONLINEAR && kind != SMR_SCHEME_CONVECTION_WENO5_NONLINEAR)
                 {
-                    throw std::invalid_argument("vector fields: only make_convection_upwind<VectorField>() is a vector scheme; apply the linear schemes per component");
+                    throw std::invalid_argument("vector fields: make_convection_upwind<VectorField>() and make_convection_weno5<VectorField>() are the vector schemes; apply the linear schemes per component");
                 }
                 if (n_comp < 2 || n_comp > 3)
                 {
@@ -2753,6 +2794,11 @@ extern "C"
                         }
                     }
                     check_field_ready(*in[c]);
+                }
+                if (kind == SMR_SCHEME_CONVECTION_WENO5_NONLINEAR)
+                {
+                    apply_wide_scheme(mo, in.data(), out.data(), n_comp, kind, params, scale);
+                    return;
                 }
                 if (cfg.any_periodic())
                 {
@@ -3178,7 +3224,7 @@ extern "C"
             });
     }
 
-    int smr_debug_fluxw_apply(smr_mesh_t m, const double* u, const double* velocity, double scale, double* out)
+    int smr_debug_fluxw_apply(smr_mesh_t m, const double* u, int n_comp, int kind, const double* velocity, double scale, double* out)
     {
         return guarded(
             [&]
@@ -3189,41 +3235,40 @@ extern "C"
                 {
                     throw std::invalid_argument("make_convection_weno5 needs a fully periodic mesh with max_stencil_size(6)");
                 }
+                if (n_comp < 1 || n_comp > 3)
+                {
+                    throw std::invalid_argument("n_comp must be 1, 2 or 3");
+                }
                 FluxPlan fp;
                 build_fluxw_plan(mo.mesh, fp);
-                std::vector<double> tab(2 * SMR_MAX_LEVELS * 6, 0.0);
-                for (int l = 0; l <= cfg.max_level && l < SMR_MAX_LEVELS; ++l)
-                {
-                    const double h = cfg.cell_length(l), hf = cfg.cell_length(l + 1);
-                    tab[static_cast<size_t>(l) * 6]                    = h_factor(cfg.dim, h, h);
-                    tab[static_cast<size_t>(SMR_MAX_LEVELS + l) * 6] = h_factor(cfg.dim, hf, h);
-                }
+                std::vector<double> tab;
+                wide_tab(cfg, tab);
                 const smr_item_fluxw* it = reinterpret_cast<const smr_item_fluxw*>(fp.arena.p + fp.items.items);
                 const int64_t* aux       = reinterpret_cast<const int64_t*>(fp.arena.p + fp.items.aux);
-                const double v[3]        = {velocity[0], cfg.dim > 1 ? velocity[1] : 0.0, cfg.dim > 2 ? velocity[2] : 0.0};
-                auto run = [&](auto op)
+                const double* up[3]      = {nullptr, nullptr, nullptr};
+                double* op[3]            = {nullptr, nullptr, nullptr};
+                for (int c = 0; c < n_comp; ++c)
                 {
-                    for (int i = 0; i < fp.items.n_items; ++i)
-                    {
-                        for (int k = 0; k < it[i].n; ++k)
-                        {
-                            out[it[i].c + k] = op.compute(it[i], k);
-                        }
-                    }
-                };
-                std::fill(out, out + mo.mesh.nref, 0.0);
-                switch (cfg.dim)
-                {
-                    case 1:
-                        run(FluxWenoOp<1>{u, out, aux, tab.data(), {v[0], v[1], v[2]}, scale});
-                        break;
-                    case 2:
-                        run(FluxWenoOp<2>{u, out, aux, tab.data(), {v[0], v[1], v[2]}, scale});
-                        break;
-                    default:
-                        run(FluxWenoOp<3>{u, out, aux, tab.data(), {v[0], v[1], v[2]}, scale});
-                        break;
+                    up[c] = u + static_cast<int64_t>(c) * mo.mesh.nref;
+                    op[c] = out + static_cast<int64_t>(c) * mo.mesh.nref;
                 }
+                std::fill(out, out + static_cast<int64_t>(n_comp) * mo.mesh.nref, 0.0);
+                with_weno_op(cfg.dim, kind, n_comp, up, op, aux, tab.data(), velocity, scale,
+                             [&](const auto& opr)
+                             {
+                                 double acc[3];
+                                 for (int i = 0; i < fp.items.n_items; ++i)
+                                 {
+                                     for (int k = 0; k < it[i].n; ++k)
+                                     {
+                                         opr.compute(it[i], k, acc);
+                                         for (int c = 0; c < n_comp; ++c)
+                                         {
+                                             op[c][it[i].c + k] = acc[c];
+                                         }
+                                     }
+                                 }
+                             });
             });
     }
 

@@ -806,11 +806,14 @@ namespace smr
         }
     };
 
-    // make_convection_weno5<Field>(velocity) on a scalar field (operators/convection_lin.hpp:95-178, weno_impl.hpp:26-63): non-linear
-    // flux scheme with the line stencil {-2 .. 3}, gather form as above.  Fully periodic meshes only: a face on the periodic boundary
-    // reads the periodic ghosts; a same-level minus face through the boundary comes after the plus face (swap bit, items.h).
+    // WENO5 convection (Jiang & Shu, weno_impl.hpp:26-63) as non-linear flux schemes with the line stencil {-2 .. 3}, gather form as
+    // above, on fully periodic meshes (a face on the periodic boundary reads the periodic ghosts; a same-level minus face through the
+    // boundary comes after the plus face: swap bit, items.h).
+    //   NONLIN = 0, NC = 1: make_convection_weno5<Field>(velocity)   (operators/convection_lin.hpp:95-178): f = velocity[d] * u
+    //   NONLIN = 1:         make_convection_weno5<Field>()           (operators/convection_nonlin.hpp:162-233): f = u * u (NC = 1) or
+    //                       u(d) * u (NC = DIM, SoA components), upwinded by the mean of the two cells next to the interface
     // `tab`: [0][l][0] = h_factor(h_l, h_l), [1][l][0] = h_factor(h_{l+1}, h_l).
-    template <int DIM>
+    template <int DIM, int NONLIN = 0, int NC = 1>
     struct FluxWenoOp
     {
         static constexpr bool two_phase = false;
@@ -818,25 +821,16 @@ namespace smr
         static constexpr int min_blocks = 1;
         static constexpr int units_per_thread = SMR_CELLS_PER_THREAD;
 
-        const double* __restrict__ u;
-        double* __restrict__ out;
+        const double* u[3];
+        double* out[3];
         const int64_t* __restrict__ aux;
         const double* __restrict__ tab;
         double vel[3];
         double scale; // `scale * scheme` (flux_based/algebraic_operators.hpp:38-46)
 
-        // compute_weno5_flux (Jiang & Shu) of f = v * {s0..s4} (v >= 0) or v * {s5..s1}; pow(x, 2) as x * x
-        static __host__ __device__ __forceinline__ double weno(double v, double s0, double s1, double s2, double s3, double s4, double s5)
+        // compute_weno5_flux of the five flux values; pow(x, 2) as x * x
+        static __host__ __device__ __forceinline__ double weno5(double f0, double f1, double f2, double f3, double f4)
         {
-            double f0, f1, f2, f3, f4;
-            if (v >= 0)
-            {
-                f0 = s0 * v, f1 = s1 * v, f2 = s2 * v, f3 = s3 * v, f4 = s4 * v;
-            }
-            else
-            {
-                f0 = s5 * v, f1 = s4 * v, f2 = s3 * v, f3 = s2 * v, f4 = s1 * v;
-            }
             const double q0 = 1. / 3 * f0 - 7. / 6 * f1 + 11. / 6 * f2;
             const double q1 = -1. / 6 * f1 + 5. / 6 * f2 + 1. / 3 * f3;
             const double q2 = 1. / 3 * f2 + 5. / 6 * f3 - 1. / 6 * f4;
@@ -855,33 +849,68 @@ namespace smr
             return (al0 / sa) * q0 + (al1 / sa) * q1 + (al2 / sa) * q2;
         }
 
-        __host__ __device__ __forceinline__ double flux(double v, double s0, double s1, double s2, double s3, double s4, double s5) const
+        // acc[c] += (sg * flux_c) * coef for the interface whose six stencil cells sit at the storage offsets i[0..5]
+        __host__ __device__ __forceinline__ void add(double* acc, int d, const int64_t* i, double sg, double coef) const
         {
-            const double f = weno(v, s0, s1, s2, s3, s4, s5);
-            return scale != 1 ? f * scale : f;
-        }
-
-        // value of the own-level cell o steps along d from cell k of the record
-        __host__ __device__ __forceinline__ double val(const smr_item_fluxw& it, const double* c, int k, int d, int o) const
-        {
-            if (d == 0)
+            if (NONLIN == 0)
             {
-                return c[o];
+                const double v  = vel[d];
+                const double* p = u[0];
+                double f        = v >= 0 ? weno5(p[i[0]] * v, p[i[1]] * v, p[i[2]] * v, p[i[3]] * v, p[i[4]] * v)
+                                         : weno5(p[i[5]] * v, p[i[4]] * v, p[i[3]] * v, p[i[2]] * v, p[i[1]] * v);
+                f               = scale != 1 ? f * scale : f;
+                acc[0]          = acc[0] + (sg * f) * coef;
+                return;
             }
-            return o == 0 ? c[0] : u[it.nb[6 * (d - 1) + (o < 0 ? o + 3 : o + 2)] + k];
+            const double* pd = u[NC == 1 ? 0 : d];
+            double ud[6];
+#pragma unroll
+            for (int k = 0; k < 6; ++k)
+            {
+                ud[k] = pd[i[k]];
+            }
+            const bool up = 0.5 * (ud[2] + ud[3]) >= 0;
+#pragma unroll
+            for (int c = 0; c < NC; ++c)
+            {
+                const double* pc = u[c];
+                double g[6];
+#pragma unroll
+                for (int k = 0; k < 6; ++k)
+                {
+                    g[k] = ud[k] * pc[i[k]];
+                }
+                double f = up ? weno5(g[0], g[1], g[2], g[3], g[4]) : weno5(g[5], g[4], g[3], g[2], g[1]);
+                f        = scale != 1 ? f * scale : f;
+                acc[c]   = acc[c] + (sg * f) * coef;
+            }
         }
 
-        __host__ __device__ __forceinline__ double side(double acc, const smr_item_fluxw& it, int k, int d, int plus, int kind, const double* c,
-                                               double cs, double cj) const
+        // storage offset of the own-level cell o steps along d from cell k of the record
+        __host__ __device__ __forceinline__ int64_t off(const smr_item_fluxw& it, int k, int d, int o) const
+        {
+            if (d == 0 || o == 0)
+            {
+                return it.c + k + (d == 0 ? o : 0);
+            }
+            return it.nb[6 * (d - 1) + (o < 0 ? o + 3 : o + 2)] + k;
+        }
+
+        __host__ __device__ __forceinline__ void side(double* acc, const smr_item_fluxw& it, int k, int d, int plus, int kind, double cs,
+                                                      double cj) const
         {
             const double sg = plus ? 1.0 : -1.0; // fluxes[1] = -fluxes[0] (flux_definition.hpp:125-136)
-            const double v  = vel[d];
+            int64_t i[6];
             if (kind != SMR_FACE_FINE)
             {
-                const int o    = plus ? 0 : -1; // stencil origin = the cell left of the interface
-                const double f = flux(v, val(it, c, k, d, o - 2), val(it, c, k, d, o - 1), val(it, c, k, d, o), val(it, c, k, d, o + 1),
-                                      val(it, c, k, d, o + 2), val(it, c, k, d, o + 3));
-                return acc + (sg * f) * cs;
+                const int o = plus ? 0 : -1; // stencil origin = the cell left of the interface
+#pragma unroll
+                for (int s = 0; s < 6; ++s)
+                {
+                    i[s] = off(it, k, d, o - 2 + s);
+                }
+                add(acc, d, i, sg, cs);
+                return;
             }
             if (d == 0)
             {
@@ -889,10 +918,14 @@ namespace smr
 #pragma unroll
                 for (int r = 0; r < (1 << (DIM - 1)); ++r)
                 {
-                    const double* s = u + fx[r];
-                    acc             = acc + (sg * flux(v, s[-2], s[-1], s[0], s[1], s[2], s[3])) * cj;
+#pragma unroll
+                    for (int s = 0; s < 6; ++s)
+                    {
+                        i[s] = fx[r] - 2 + s;
+                    }
+                    add(acc, d, i, sg, cj);
                 }
-                return acc;
+                return;
             }
             const int64_t* fx = aux + it.fine + 8 + ((2 * d + plus) - 2) * 12;
 #pragma unroll
@@ -902,20 +935,26 @@ namespace smr
 #pragma unroll
                 for (int x = 0; x < 2; ++x)
                 {
-                    const int64_t j = 2 * k + x;
-                    acc = acc + (sg * flux(v, u[rows[0] + j], u[rows[1] + j], u[rows[2] + j], u[rows[3] + j], u[rows[4] + j], u[rows[5] + j])) * cj;
+#pragma unroll
+                    for (int s = 0; s < 6; ++s)
+                    {
+                        i[s] = rows[s] + 2 * k + x;
+                    }
+                    add(acc, d, i, sg, cj);
                 }
             }
-            return acc;
         }
 
-        // the value of cell k of the record (host-callable: smr_debug_fluxw_apply evaluates the records without a device in the CPU tests)
-        __host__ __device__ __forceinline__ double compute(const smr_item_fluxw& it, int k) const
+        // the values of cell k of the record (host-callable: smr_debug_fluxw_apply evaluates the records without a device in the CPU tests)
+        __host__ __device__ __forceinline__ void compute(const smr_item_fluxw& it, int k, double* acc) const
         {
-            const double* c = u + it.c + k;
             const double cs = tab[it.level * 6];
             const double cj = tab[(SMR_MAX_LEVELS + it.level) * 6];
-            double acc      = 0.0;
+#pragma unroll
+            for (int c = 0; c < NC; ++c)
+            {
+                acc[c] = 0.0;
+            }
 #pragma unroll
             for (int d = 0; d < DIM; ++d)
             {
@@ -932,21 +971,26 @@ namespace smr
                 const int pp = kp == SMR_FACE_SAME ? 2 : (kp == SMR_FACE_COARSE ? 5 : 6);
                 if (pm <= pp)
                 {
-                    acc = side(acc, it, k, d, 0, km, c, cs, cj);
-                    acc = side(acc, it, k, d, 1, kp, c, cs, cj);
+                    side(acc, it, k, d, 0, km, cs, cj);
+                    side(acc, it, k, d, 1, kp, cs, cj);
                 }
                 else
                 {
-                    acc = side(acc, it, k, d, 1, kp, c, cs, cj);
-                    acc = side(acc, it, k, d, 0, km, c, cs, cj);
+                    side(acc, it, k, d, 1, kp, cs, cj);
+                    side(acc, it, k, d, 0, km, cs, cj);
                 }
             }
-            return acc;
         }
 
         __device__ __forceinline__ void operator()(const smr_item_fluxw& it, int k) const
         {
-            mstore(out + it.c + k, compute(it, k), static_cast<unsigned>(it.mask));
+            double acc[NC];
+            compute(it, k, acc);
+#pragma unroll
+            for (int c = 0; c < NC; ++c)
+            {
+                mstore(out[c] + it.c + k, acc[c], static_cast<unsigned>(it.mask));
+            }
         }
     };
 
@@ -1830,15 +1874,19 @@ namespace smr
 
     // Phase boundary across GPUs: local arrival as above; CTA 0 then tells every peer "my rank has finished barrier k" by storing
     // the epoch into the peer's flag table over NVLink, waits for the same word from every peer, and releases the local grid.
-    // Every thread fences at system scope first, so the halo values it stored into the peers' pools are visible there before the
-    // flag is.  All waits are bounded: a rank that stopped raises the error words instead of hanging the GPUs.
+    // Thread 0 of every CTA releases at device scope after the CTA barrier and CTA 0 fences at system scope before sending the flags, so
+    // the halo values the grid stored into the peers' pools are visible there before the flag is.  All waits are bounded: a rank that stopped raises the error words instead of hanging the GPUs.
     __device__ __forceinline__ bool wf_mg_barrier(const WfArgs& a, unsigned k)
     {
         __shared__ int s_ok_mg;
-        __threadfence_system();
         __syncthreads();
         if (threadIdx.x == 0)
         {
+            // Fences are cumulative (PTX memory model): the CTA barrier orders every thread's peer stores before this device-scope
+            // release, CTA 0 acquires all arrivals and issues ONE system-scope fence before it sends the flags, so the stores of the
+            // whole grid are visible to the peers before the flag is.  A system-scope fence costs ~4 us on this path (measured: five of
+            // them in sequence made a phase boundary 21 us); the barrier now has two on its critical path, both in CTA 0.
+            __threadfence();
             unsigned* counter     = a.barrier;
             const unsigned target = a.barrier_base + k * gridDim.x;
             const unsigned rel    = a.release_base + k;
@@ -1866,7 +1914,6 @@ namespace smr
                         remote[g_peers.rank] = epoch;
                     }
                 }
-                __threadfence_system();
                 volatile unsigned long long* mine = g_peers.flags;
                 for (int p = 0; ok && p < g_peers.world; ++p)
                 {
@@ -1888,7 +1935,7 @@ namespace smr
                 {
                     atomicExch(counter + SMR_WF_ERROR_WORD, target | 1u);
                 }
-                __threadfence_system();
+                __threadfence_system(); // acquire: the peers' halo stores (made visible before their flags) are visible to this grid
                 atomicExch(counter + 1, rel); // release the local grid (also on failure: the others then see the error word)
             }
             else
@@ -1903,7 +1950,7 @@ namespace smr
                 }
             }
             s_ok_mg = vc[SMR_WF_ERROR_WORD] == 0u;
-            __threadfence_system();
+            __threadfence(); // the halo values live in this GPU's memory: a device-scope acquire after CTA 0's system-scope one
         }
         __syncthreads();
         return s_ok_mg != 0;

@@ -124,3 +124,66 @@ def test_linear_convection_demo_matches_oracle_and_reference_golden(gpu):
     lv, idx, off = pmesh.cell_table(sb.CELLS)
     assert np.array_equal(lv, g["level"].astype(np.int64)) and np.array_equal(idx[:, :2], g["idx"].astype(np.int64)), "mesh differs from the golden"
     assert np.max(np.abs(u.download()[off] - g["u"])) <= 1e-13
+
+
+@pytest.mark.parametrize("dim,lo,hi,n_comp", [(1, 2, 8, 1), (2, 1, 6, 1), (2, 1, 6, 2), (3, 1, 4, 3)])
+def test_nonlinear_weno5_burgers_steps_match_oracle(gpu, dim, lo, hi, n_comp):
+    """make_convection_weno5<Field>() (Burgers form, scalar and vector: operators/convection_nonlin.hpp:162-233) in
+    `unp1 = u - dt * conv(u)` with MRadaptation at every step on a fully periodic mesh: meshes identical to the oracle's at every step,
+    leaves within 1e-12 (bit-equal expected)."""
+    pcfg, ocfg = _cfgs(dim, lo, hi)
+    pmesh = sb.MRMesh.make_mesh([-1.0] * dim, [1.0] * dim, pcfg)
+    om = so.Mesh.uniform(ocfg)
+    c = om.cell_centers(hi, om.cells[hi])
+    ix = om.index(hi, om.cells[hi])
+    r = np.max(np.abs(c + 0.4), axis=1)
+    comps = []
+    for k in range(n_comp):
+        f = np.zeros(om.nref)
+        f[ix] = np.where(r < 0.5, (1.0 - 2.0 * r) * (1.0 if k % 2 == 0 else -0.7), 0.0)  # hats of both signs, touching the periodic boundary
+        comps.append(f)
+    bcs = [so.Bc("neumann", 0.0)] * n_comp
+    if n_comp == 1:
+        u, unp1 = sb.make_scalar_field("u", pmesh), sb.make_scalar_field("unp1", pmesh)
+        u.resize()
+        u.upload(comps[0])
+    else:
+        u, unp1 = sb.make_vector_field("u", pmesh, n_comp), sb.make_vector_field("unp1", pmesh, n_comp)
+        u.resize()
+        u.upload(np.stack(comps, axis=1))
+    conv = sb.make_convection_weno5()
+    flux = so.weno5_flux_nonlinear(dim, n_comp)
+    dt = 0.3 * pmesh.cell_length(hi)
+    adapt = sb.make_MRAdapt(u)
+    mra = sb.mra_config()
+    adapt(mra)
+    om, comps = so.adapt_fields(om, comps, bcs, 1e-4, 1.0)
+    pu.assert_same_mesh(pmesh, om)
+    worst = 0.0
+    for step in range(6):
+        adapt(mra)
+        om, comps = so.adapt_fields(om, comps, bcs, 1e-4, 1.0)
+        pu.assert_same_mesh(pmesh, om)
+        unp1.resize()
+        rhs = conv(u)
+        for a, b, cc in zip(sb._scalars(unp1), sb._scalars(u), sb._scalars(rhs)):
+            sb.lincomb(a, 1.0, b, -dt, cc)
+        rhs.destroy()
+        sb.swap(u, unp1)
+        for f, bc in zip(comps, bcs):
+            so.update_ghost_mr(om, f, bc)
+        orhs = so.flux_nonlin_apply(om, comps if n_comp > 1 else comps[0], flux, so.WENO5_OFFSETS)
+        orhs = orhs if n_comp > 1 else [orhs]
+        leaves = _leaves(om)
+        new = []
+        for f, rh in zip(comps, orhs):
+            o = np.full(om.nref, np.nan)
+            o[leaves] = f[leaves] - dt * rh[leaves]
+            new.append(o)
+        comps = new
+        got = u.download()
+        got = got if n_comp > 1 else got[:, None]
+        for k in range(n_comp):
+            worst = max(worst, float(np.max(np.abs(got[leaves, k] - comps[k][leaves]))))
+    assert len(om.leaf_levels()) > 1
+    assert worst <= pu.REL_TOL, f"max abs difference to the oracle: {worst:.3e}"

@@ -50,3 +50,27 @@ def test_weno5_records_match_oracle(dim, lo, hi, vel):
     bad = np.flatnonzero(got[leaves] != want[leaves])
     assert bad.size == 0, f"{bad.size} of {leaves.size} leaves differ, max {np.max(np.abs(got[leaves] - want[leaves])):.3e}"
     pm.destroy()
+
+
+@pytest.mark.parametrize("dim,lo,hi,n_comp", [(1, 2, 8, 1), (2, 1, 6, 1), (2, 1, 6, 2), (3, 1, 4, 3)])
+def test_nonlinear_weno5_records_match_oracle(dim, lo, hi, n_comp):
+    """make_convection_weno5<Field>() (operators/convection_nonlin.hpp:162-233): f = u * u for a scalar field, u(d) * u for a vector
+    field with n_comp == dim, upwinded by the mean next to the interface; with and without a scalar factor."""
+    pm, om, ou, bc = adapted_periodic(dim, lo, hi)
+    leaves = np.concatenate([om.index(l, om.cells[l]) for l in om.leaf_levels()])
+    rng = np.random.default_rng(7)
+    comps = []
+    for c in range(n_comp):
+        oc = ou.copy()
+        oc[leaves] += 0.4 * rng.standard_normal(leaves.size) - 0.3 * c  # both upwinding signs occur
+        so.update_ghost_mr(om, oc, bc)
+        comps.append(oc)
+    arg = comps if n_comp > 1 else comps[0]
+    for scale in (1.0, 0.5):
+        want = so.flux_nonlin_apply(om, arg, so.weno5_flux_nonlinear(dim, n_comp, scale), so.WENO5_OFFSETS)
+        got = pm.debug_fluxw_apply(arg, None, scale)
+        for c in range(n_comp):
+            g, w = (got[c], want[c]) if n_comp > 1 else (got, want)
+            bad = np.flatnonzero(g[leaves] != w[leaves])
+            assert bad.size == 0, f"scale {scale} component {c}: {bad.size} of {leaves.size} leaves differ, max {np.max(np.abs(g[leaves] - w[leaves])):.3e}"
+    pm.destroy()
