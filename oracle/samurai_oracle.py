@@ -1111,6 +1111,12 @@ def flux_linhom_apply(mesh: Mesh, u, coeff_fn):
         e = [0] * dim
         e[d] = 1
         me = [-v for v in e]
+
+        def shift_of(level, sign):
+            sh = [0] * dim
+            sh[d] = sign * (cfg.n_cells0[d] << level)
+            return sh
+
         # ---- same level
         for level in range(lo, hi + 1):
             cells = mesh.cells[level]
@@ -1121,14 +1127,18 @@ def flux_linhom_apply(mesh: Mesh, u, coeff_fn):
             f = hfac(h, h)
             lc = (f * fc[0], f * fc[1])
             rc = (-lc[0], -lc[1])
-            iface = cells[np.isin(translate(cells, e), cells)]
-            for run in _runs(iface, dim):
-                li = mesh.index(level, run)
-                ri = mesh.index(level, translate(run, e))
-                st = (li, ri)
-                for cc in range(2):
-                    out[li] = out[li] + lc[cc] * u[st[cc]]
-                    out[ri] = out[ri] + rc[cc] * u[st[cc]]
+            pairs = [(cells, cells)]
+            if cfg.periodic[d]:  # interfaces through the periodic boundary, seen once from each side (interface.hpp:83-92)
+                pairs += [(cells, translate(cells, shift_of(level, 1))), (translate(cells, shift_of(level, -1)), cells)]
+            for left_set, right_set in pairs:
+                iface = inter(left_set, translate(right_set, me))
+                for run in _runs(iface, dim):
+                    li = mesh.index(level, run)
+                    ri = mesh.index(level, translate(run, e))
+                    st = (li, ri)
+                    for cc in range(2):
+                        out[li] = out[li] + lc[cc] * u[st[cc]]
+                        out[ri] = out[ri] + rc[cc] * u[st[cc]]
         # ---- level jumps level -> level+1
         for level in range(lo, hi):
             coarse, fine = mesh.cells[level], mesh.cells[level + 1]
@@ -1140,40 +1150,51 @@ def flux_linhom_apply(mesh: Mesh, u, coeff_fn):
             # orientation A: coarse on the left, fine on the right
             lcA = tuple(hfac(h_f, h_l) * v for v in fc)
             rcA = tuple(-hfac(h_f, h_f) * v for v in fc)
-            ghosts = inter(rcoarse, translate(fine, me))
-            for run in _runs(ghosts, dim):
-                st = (mesh.index(level + 1, run), mesh.index(level + 1, translate(run, e)))
-                right = st[1]
-                if run.size == 1 or d == 0:
-                    left = mesh.index(level, pack(unpack(run, dim) >> 1))
-                    for cc in range(2):
-                        out[left] = out[left] + lcA[cc] * u[st[cc]]
-                        out[right] = out[right] + rcA[cc] * u[st[cc]]
-                else:
-                    assert run.size % 2 == 0
-                    left = mesh.index(level, pack(unpack(run[0::2], dim) >> 1))
-                    for cc in range(2):
-                        out[left] = out[left] + (lcA[cc] * u[st[cc][0::2]] + lcA[cc] * u[st[cc][1::2]])
-                        out[right] = out[right] + rcA[cc] * u[st[cc]]
+            pairsA = [(coarse, fine)]
+            if cfg.periodic[d]:  # interface.hpp:179-189
+                pairsA += [(coarse, translate(fine, shift_of(level + 1, 1))), (translate(coarse, shift_of(level, -1)), fine)]
+            for cs_, fs_ in pairsA:
+                ghosts = inter(refine(cs_, 1, dim), translate(fs_, me))
+                for run in _runs(ghosts, dim):
+                    st = (mesh.index(level + 1, run), mesh.index(level + 1, translate(run, e)))
+                    right = st[1]
+                    if run.size == 1 or d == 0:
+                        left = mesh.index(level, pack(unpack(run, dim) >> 1))
+                        for cc in range(2):
+                            out[left] = out[left] + lcA[cc] * u[st[cc]]
+                            out[right] = out[right] + rcA[cc] * u[st[cc]]
+                    else:
+                        assert run.size % 2 == 0
+                        left = mesh.index(level, pack(unpack(run[0::2], dim) >> 1))
+                        for cc in range(2):
+                            out[left] = out[left] + (lcA[cc] * u[st[cc][0::2]] + lcA[cc] * u[st[cc][1::2]])
+                            out[right] = out[right] + rcA[cc] * u[st[cc]]
             # orientation B: fine on the left, coarse on the right; stencil {-dir, 0} around the ghost child
             lcB = tuple(hfac(h_f, h_f) * v for v in fc)
             rcB = tuple(-hfac(h_f, h_l) * v for v in fc)
-            ghosts = inter(rcoarse, translate(fine, e))
-            for run in _runs(ghosts, dim):
-                st = (mesh.index(level + 1, translate(run, me)), mesh.index(level + 1, run))
-                left = st[0]
-                if run.size == 1 or d == 0:
-                    right = mesh.index(level, pack(unpack(run, dim) >> 1))
-                    for cc in range(2):
-                        out[left] = out[left] + lcB[cc] * u[st[cc]]
-                        out[right] = out[right] + rcB[cc] * u[st[cc]]
-                else:
-                    assert run.size % 2 == 0
-                    right = mesh.index(level, pack(unpack(run[0::2], dim) >> 1))
-                    for cc in range(2):
-                        out[left] = out[left] + lcB[cc] * u[st[cc]]
-                        out[right] = out[right] + (rcB[cc] * u[st[cc][0::2]] + rcB[cc] * u[st[cc][1::2]])
-        # ---- boundary interfaces: per level, direction then opposite direction
+            pairsB = [(coarse, fine)]
+            if cfg.periodic[d]:  # interface.hpp:280-290
+                pairsB += [(coarse, translate(fine, shift_of(level + 1, -1))), (translate(coarse, shift_of(level, 1)), fine)]
+            for cs_, fs_ in pairsB:
+                ghosts = inter(refine(cs_, 1, dim), translate(fs_, e))
+                for run in _runs(ghosts, dim):
+                    st = (mesh.index(level + 1, translate(run, me)), mesh.index(level + 1, run))
+                    left = st[0]
+                    if run.size == 1 or d == 0:
+                        right = mesh.index(level, pack(unpack(run, dim) >> 1))
+                        for cc in range(2):
+                            out[left] = out[left] + lcB[cc] * u[st[cc]]
+                            out[right] = out[right] + rcB[cc] * u[st[cc]]
+                    else:
+                        assert run.size % 2 == 0
+                        right = mesh.index(level, pack(unpack(run[0::2], dim) >> 1))
+                        for cc in range(2):
+                            out[left] = out[left] + lcB[cc] * u[st[cc]]
+                            out[right] = out[right] + (rcB[cc] * u[st[cc][0::2]] + rcB[cc] * u[st[cc][1::2]])
+        # ---- boundary interfaces: per level, direction then opposite direction (none in a periodic direction,
+        # flux_based_scheme__lin_hom.hpp:189-192)
+        if cfg.periodic[d]:
+            continue
         for level in leaf_lv:
             cells = mesh.cells[level]
             h = cfg.cell_length(level)

@@ -897,6 +897,9 @@ namespace smr
         {
             nl[d] = m.cfg.n0[d] << l;
         }
+        // a face on a periodic boundary is classified by the leaf at the wrapped position (interface.hpp:83-92, 179-189, 280-290) and
+        // reads the periodic ghosts at the unwrapped one; the other boundaries keep their boundary interfaces
+        auto wrap = [&](int d, int v) { return ((v % nl[d]) + nl[d]) % nl[d]; };
         struct Seg
         {
             int a, b, kind;
@@ -930,15 +933,20 @@ namespace smr
                 {
                     segs[f].clear();
                     const int d = f >> 1, sgn = (f & 1) ? 1 : -1;
-                    const int yy = y + (d == 1 ? sgn : 0), zz = z + (d == 2 ? sgn : 0);
-                    const int j = d == 1 ? yy : zz;
-                    if (j < 0 || j >= nl[d])
+                    int yy = y + (d == 1 ? sgn : 0), zz = z + (d == 2 ? sgn : 0);
+                    const int j        = d == 1 ? yy : zz;
+                    const bool through = j < 0 || j >= nl[d];
+                    if (through && !m.cfg.periodic[d])
                     {
                         segs[f].push_back({s, e, SMR_FACE_BDRY});
                         continue;
                     }
+                    if (through)
+                    {
+                        (d == 1 ? yy : zz) = wrap(d, j);
+                    }
                     const int rS = c.find_row(mk_key(yy, zz));
-                    const int rC = cc ? cc->find_row(mk_key(yy >> 1, dim > 2 ? (zz >> 1) : 0)) : -1;
+                    const int rC = cc ? cc->find_row(mk_key(dim > 1 ? (yy >> 1) : 0, dim > 2 ? (zz >> 1) : 0)) : -1;
                     // the child row of the neighbour position that touches this leaf
                     const int fy = d == 1 ? 2 * yy + (sgn < 0 ? 1 : 0) : 2 * yy;
                     const int fz = dim > 2 ? (d == 2 ? 2 * zz + (sgn < 0 ? 1 : 0) : 2 * zz) : 0;
@@ -950,7 +958,7 @@ namespace smr
                         if (rS >= 0 && (i = c.find_ivl(rS, pos)) >= 0)
                         {
                             end  = std::min(e, c.xe[i]);
-                            kind = SMR_FACE_SAME;
+                            kind = SMR_FACE_SAME | (through ? 4 : 0); // bit 2 (segments only): through the periodic boundary
                         }
                         else if (rC >= 0 && (i = cc->find_ivl(rC, pos >> 1)) >= 0)
                         {
@@ -979,47 +987,40 @@ namespace smr
                     const int a = cuts[ci], b = cuts[ci + 1];
                     int kinds  = 0;
                     bool any_fine = false;
-                    // x faces
+                    // x faces: the neighbour cells a - 1 and b (wrapped through a periodic boundary)
                     int kx[2];
-                    if (a > s)
+                    for (int side = 0; side < 2; ++side)
                     {
-                        kx[0] = SMR_FACE_SAME;
-                    }
-                    else if (a == 0)
-                    {
-                        kx[0] = SMR_FACE_BDRY;
-                    }
-                    else if (has(cc, py, pz, (a - 1) >> 1))
-                    {
-                        kx[0] = SMR_FACE_COARSE;
-                    }
-                    else if (has(cf, cy_(0), cz_(0), 2 * a - 1))
-                    {
-                        kx[0] = SMR_FACE_FINE;
-                    }
-                    else
-                    {
-                        missing("flux: x- neighbour leaf", l, a - 1, y, z);
-                    }
-                    if (b < e)
-                    {
-                        kx[1] = SMR_FACE_SAME;
-                    }
-                    else if (b == nl[0])
-                    {
-                        kx[1] = SMR_FACE_BDRY;
-                    }
-                    else if (has(cc, py, pz, b >> 1))
-                    {
-                        kx[1] = SMR_FACE_COARSE;
-                    }
-                    else if (has(cf, cy_(0), cz_(0), 2 * b))
-                    {
-                        kx[1] = SMR_FACE_FINE;
-                    }
-                    else
-                    {
-                        missing("flux: x+ neighbour leaf", l, b, y, z);
+                        if (side == 0 ? a > s : b < e)
+                        {
+                            kx[side] = SMR_FACE_SAME;
+                            continue;
+                        }
+                        const int xn       = side == 0 ? a - 1 : b;
+                        const bool through = xn < 0 || xn >= nl[0];
+                        if (through && !m.cfg.periodic[0])
+                        {
+                            kx[side] = SMR_FACE_BDRY;
+                            continue;
+                        }
+                        const int xw = through ? wrap(0, xn) : xn;
+                        if (through && has(&c, y, z, xw))
+                        {
+                            kx[side] = SMR_FACE_SAME;
+                            kinds |= 1 << ((side == 0 ? SMR_FLUXW_SWAP_SHIFT : SMR_FLUX_PLUS_THROUGH_SHIFT) + 0);
+                        }
+                        else if (has(cc, py, pz, xw >> 1))
+                        {
+                            kx[side] = SMR_FACE_COARSE;
+                        }
+                        else if (has(cf, cy_(0), cz_(0), side == 0 ? 2 * xw + 1 : 2 * xw))
+                        {
+                            kx[side] = SMR_FACE_FINE;
+                        }
+                        else
+                        {
+                            missing("flux: x neighbour leaf", l, xn, y, z);
+                        }
                     }
                     kinds |= kx[0] | (kx[1] << 2);
                     any_fine = kx[0] == SMR_FACE_FINE || kx[1] == SMR_FACE_FINE;
@@ -1029,9 +1030,13 @@ namespace smr
                         {
                             ++cur[f];
                         }
-                        const int kind = segs[f][cur[f]].kind;
+                        const int kind = segs[f][cur[f]].kind & 3;
                         kinds |= kind << (2 * f);
                         any_fine = any_fine || kind == SMR_FACE_FINE;
+                        if (segs[f][cur[f]].kind & 4) // same-level interface through the periodic boundary
+                        {
+                            kinds |= 1 << (((f & 1) ? SMR_FLUX_PLUS_THROUGH_SHIFT : SMR_FLUXW_SWAP_SHIFT) + (f >> 1));
+                        }
                     }
                     smr_item_flux it;
                     it.c = ref.offset_of(c.key[r], a - 1, b);

@@ -2649,15 +2649,12 @@ extern "C"
                     apply_wide_scheme(mo, ip, op, 1, kind, params, scale);
                     return;
                 }
-                if (cfg.any_periodic())
-                {
-                    // the interface enumeration (interface.hpp) across a periodic boundary is not built: fail loudly, never approximate
-                    throw std::invalid_argument("flux-based schemes are not implemented on periodic meshes (field expressions with upwind() are)");
-                }
                 const bool nonlin = kind == SMR_SCHEME_CONVECTION_UPWIND_NONLINEAR;
                 static const bool force_general = std::getenv("SMR_FLUX_GENERAL") != nullptr;
                 const int level    = mo.mesh.min_leaf_level();
-                const bool general = nonlin || force_general || level != mo.mesh.max_leaf_level();
+                // periodic meshes: the interfaces through the boundary (interface.hpp:83-92, 179-189, 280-290) are classified in the
+                // general records; the uniform-level strip kernels know boundaries only
+                const bool general = nonlin || force_general || level != mo.mesh.max_leaf_level() || cfg.any_periodic();
                 // update_ghosts_if_needed (schemes/fv/FV_scheme.hpp:187-197)
                 ensure_plan(mo);
                 if (!in.ghosts_valid)
@@ -2799,10 +2796,6 @@ extern "C"
                 {
                     apply_wide_scheme(mo, in.data(), out.data(), n_comp, kind, params, scale);
                     return;
-                }
-                if (cfg.any_periodic())
-                {
-                    throw std::invalid_argument("flux-based schemes with two-cell stencils are not implemented on periodic meshes");
                 }
                 ensure_plan(mo);
                 for (int c = 0; c < n_comp; ++c)

@@ -94,6 +94,8 @@ typedef struct
 #define SMR_FLUXW_AUX_SLOTS 56 /* x faces: [face*4 + cy + 2*cz] = offset of the stencil origin (cell left of the interface) in child
                                   row (2y+cy, 2z+cz); transverse face f = 2..5: [8 + ((f-2)*2 + b)*6 + st] = offset of x = 2*start
                                   in stencil row st (origin row - 2 + st) of the b-th child row of the other transverse direction */
+#define SMR_FLUX_PLUS_THROUGH_SHIFT 16 /* kinds bit (16 + d): the plus face of direction d is a same-level interface through the periodic
+                                         boundary (linear schemes: its x-interface is not in the cell's own interface interval) */
 #define SMR_FLUXW_SWAP_SHIFT 12 /* kinds bit (12 + d): the minus face of direction d is a same-level interface through the periodic
                                    boundary: the reference visits it after the regular same-level interfaces, i.e. after the plus face */
 typedef struct

@@ -678,7 +678,15 @@ namespace smr
                     km = k != 0 ? SMR_FACE_SAME : km;
                     kp = k != it.n - 1 ? SMR_FACE_SAME : kp;
                 }
-                if (!NONLIN && d == 0 && km == SMR_FACE_SAME && kp == SMR_FACE_SAME)
+                // same-level interfaces through a periodic boundary come after the regular ones (interface.hpp:83-92): first the one
+                // seen from the cell left of the boundary (its plus face), then the one seen from the cell right of it (its minus face)
+                bool m_thr = ((it.kinds >> (SMR_FLUXW_SWAP_SHIFT + d)) & 1) != 0, p_thr = ((it.kinds >> (SMR_FLUX_PLUS_THROUGH_SHIFT + d)) & 1) != 0;
+                if (d == 0)
+                {
+                    m_thr = m_thr && k == 0;
+                    p_thr = p_thr && k == it.n - 1;
+                }
+                if (!NONLIN && d == 0 && km == SMR_FACE_SAME && kp == SMR_FACE_SAME && !m_thr && !p_thr)
                 {
                     // one interface interval holds both x-interfaces of the cell: for c = 0, 1 the left-cell loop runs
                     // before the right-cell loop (explicit_flux_based_scheme__lin_hom.hpp:63-76)
@@ -687,10 +695,10 @@ namespace smr
                     acc = (((acc + tLc) + tRm) + tLp) + tRc;
                     continue;
                 }
-                // pass numbers x2: minus {2, 4, 7, 9}, plus {2, 5, 6, 8}
-                const int pm = km == SMR_FACE_SAME ? 2 : (km == SMR_FACE_COARSE ? 4 : (km == SMR_FACE_FINE ? 7 : 9));
-                const int pp = kp == SMR_FACE_SAME ? 2 : (kp == SMR_FACE_COARSE ? 5 : (kp == SMR_FACE_FINE ? 6 : 8));
-                if (pm <= pp)
+                // pass numbers x2: minus {2, 4, 7, 9}, plus {2, 5, 6, 8}; through the periodic boundary: plus 3, minus 3 after it
+                const int pm = km == SMR_FACE_SAME ? (m_thr ? 3 : 2) : (km == SMR_FACE_COARSE ? 4 : (km == SMR_FACE_FINE ? 7 : 9));
+                const int pp = kp == SMR_FACE_SAME ? (p_thr ? 3 : 2) : (kp == SMR_FACE_COARSE ? 5 : (kp == SMR_FACE_FINE ? 6 : 8));
+                if (pm <= pp && !(m_thr && p_thr))
                 {
                     acc = side(acc, it, k, d, 0, km, c, cs, cj);
                     acc = side(acc, it, k, d, 1, kp, c, cs, cj);
@@ -784,10 +792,16 @@ namespace smr
                     km = k != 0 ? SMR_FACE_SAME : km;
                     kp = k != it.n - 1 ? SMR_FACE_SAME : kp;
                 }
-                // pass numbers x2 as in FluxGenOp: minus {2, 4, 7, 9}, plus {2, 5, 6, 8}
-                const int pm = km == SMR_FACE_SAME ? 2 : (km == SMR_FACE_COARSE ? 4 : (km == SMR_FACE_FINE ? 7 : 9));
-                const int pp = kp == SMR_FACE_SAME ? 2 : (kp == SMR_FACE_COARSE ? 5 : (kp == SMR_FACE_FINE ? 6 : 8));
-                if (pm <= pp)
+                bool m_thr = ((it.kinds >> (SMR_FLUXW_SWAP_SHIFT + d)) & 1) != 0, p_thr = ((it.kinds >> (SMR_FLUX_PLUS_THROUGH_SHIFT + d)) & 1) != 0;
+                if (d == 0)
+                {
+                    m_thr = m_thr && k == 0;
+                    p_thr = p_thr && k == it.n - 1;
+                }
+                // pass numbers x2 as in FluxGenOp: minus {2, 4, 7, 9}, plus {2, 5, 6, 8}; through the periodic boundary: plus 3, then minus
+                const int pm = km == SMR_FACE_SAME ? (m_thr ? 3 : 2) : (km == SMR_FACE_COARSE ? 4 : (km == SMR_FACE_FINE ? 7 : 9));
+                const int pp = kp == SMR_FACE_SAME ? (p_thr ? 3 : 2) : (kp == SMR_FACE_COARSE ? 5 : (kp == SMR_FACE_FINE ? 6 : 8));
+                if (pm <= pp && !(m_thr && p_thr))
                 {
                     side(acc, it, k, d, 0, km, cs, cj);
                     side(acc, it, k, d, 1, kp, cs, cj);

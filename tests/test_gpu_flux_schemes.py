@@ -300,3 +300,63 @@ def test_vector_convection_upwind_across_level_jumps_bitwise(gpu, dim, lo, hi, b
     v.destroy()
     u0.destroy()
     pmesh.destroy()
+
+
+@pytest.mark.parametrize("dim,lo,hi,msr", [(1, 2, 7, 1), (2, 2, 6, 1), (2, 2, 6, 2), (3, 2, 4, 1)])
+def test_schemes_on_periodic_meshes_bitwise(gpu, dim, lo, hi, msr):
+    """a10, periodic variants (interface.hpp:83-92 same level, :179-189 and :280-290 level jumps): the two-cell flux schemes on a fully
+    periodic adapted mesh whose refined region touches the boundary, so that same-level interfaces and level jumps go through it.
+    Linear homogeneous (upwind convection, diffusion), non-linear scalar (Burgers) and vector (u(d) * u): every leaf bit-identical to
+    the oracle's restatement of the reference's scatter loops (no boundary interfaces in a periodic direction)."""
+    periodic = (True,) * dim
+    pmesh = sb.MRMesh.make_mesh([0.0] * dim, [1.0] * dim, pu.product_cfg(dim, lo, hi, 1, periodic, msr))
+    u = sb.make_scalar_field("u", pmesh)
+    u.resize()
+    u.init_ball([0.1] * dim, 0.2)  # crosses the lower boundaries: its periodic images matter
+    sb.make_MRAdapt(u)(sb.mra_config().epsilon(2e-4))
+    ocfg = pu.oracle_cfg(dim, lo, hi, 1, periodic, msr)
+    obc = so.Bc("neumann", 0.0)
+    omesh = so.Mesh.uniform(ocfg)
+    omesh, ou = so.adapt(omesh, so.init_disc(omesh, [0.1] * dim, 0.2), obc, eps=2e-4)
+    pu.assert_same_mesh(pmesh, omesh)
+    assert len(omesh.leaf_levels()) > 1
+    rng = np.random.default_rng(31)
+    leaves = np.concatenate([omesh.index(l, omesh.cells[l]) for l in omesh.leaf_levels()])
+    ou[leaves] += 0.2 * rng.standard_normal(leaves.size) - 0.05
+    u.upload(ou)
+    og = ou.copy()
+    so.update_ghost_mr(omesh, og, obc)
+    vel, K = [1.0, -0.5, 0.25][:dim], [1.0, 2.0, 0.5][:dim]
+    cases = [(sb.make_convection_upwind(vel), so.flux_linhom_apply(omesh, og, so.convection_upwind_coeffs(vel))),
+             (sb.make_convection_upwind([-v for v in vel]), so.flux_linhom_apply(omesh, og, so.convection_upwind_coeffs([-v for v in vel]))),
+             (sb.make_diffusion_order2(K), so.flux_linhom_apply(omesh, og, so.diffusion_order2_coeffs(K))),
+             (sb.make_convection_upwind(), so.flux_nonlin_apply(omesh, og, so.burgers_upwind_flux())),
+             (0.5 * sb.make_convection_upwind(), so.flux_nonlin_apply(omesh, og, so.burgers_upwind_flux(0.5)))]
+    for scheme, ref in cases:
+        rhs = scheme(u)
+        got = rhs.download()
+        bad = np.flatnonzero(got[leaves] != ref[leaves])
+        assert bad.size == 0, f"{scheme.name}: {bad.size} of {leaves.size} leaves differ, max {np.max(np.abs(got[leaves] - ref[leaves])):.3e}"
+        rhs.destroy()
+    if dim > 1:
+        v = sb.make_vector_field("v", pmesh, dim)
+        v.resize()
+        comps = []
+        for c in range(dim):
+            oc = ou.copy()
+            oc[leaves] += 0.3 * rng.standard_normal(leaves.size) - 0.2 * c
+            comps.append(oc)
+        v.upload(np.stack(comps, axis=1))
+        ogv = [c.copy() for c in comps]
+        for c in ogv:
+            so.update_ghost_mr(omesh, c, obc)
+        want = so.flux_nonlin_apply(omesh, ogv, so.burgers_upwind_flux_vector(dim))
+        rhsv = sb.make_convection_upwind()(v)
+        got = rhsv.download()
+        for c in range(dim):
+            bad = np.flatnonzero(got[leaves, c] != want[c][leaves])
+            assert bad.size == 0, f"vector component {c}: {bad.size} of {leaves.size} leaves differ"
+        rhsv.destroy()
+        v.destroy()
+    u.destroy()
+    pmesh.destroy()
