@@ -822,7 +822,7 @@ def main():
     ap.add_argument("--sweep-level", type=int, default=13)
     ap.add_argument("--cpu-steps", type=int, default=10, help="steps of the compiled CPU path timed as cpu_baseline (and compared with the product)")
     ap.add_argument("--numpy-parity-steps", type=int, default=1, help="steps of the numpy oracle compared with the product at full size (N=1)")
-    ap.add_argument("--level-3d", type=int, default=9, help="max_level of the 3D advection block (BASELINE configs[3]; 0: skip)")
+    ap.add_argument("--level-3d", type=int, default=10, help="max_level of the 3D advection block (BASELINE configs[3]; 0: skip)")
     ap.add_argument("--steps-3d", type=int, default=20)
     ap.add_argument("--sweep-level-3d", type=int, default=9, help="level of the 3D uniform full-step measurement (0: skip)")
     ap.add_argument("--ref-max-level", type=int, default=14, help="largest max_level the CPU reference arm samples")
