@@ -1125,7 +1125,7 @@ namespace smr
     {
         static constexpr bool two_phase = false;
         static constexpr bool warp_uniform = false;
-        static constexpr int min_blocks = DIM > 2 ? 2 : SMR_MB_DETAIL; // 3D radius 1 holds 16 accumulators + 27 coarse values (a one-child-row-at-a-time variant with 64 registers was measured slower: 933 vs 759 us at level 9)
+        static constexpr int min_blocks = DIM > 2 ? 2 : SMR_MB_DETAIL; // 3D radius 1 holds 16 accumulators + 27 coarse values (measured slower at level 9: a one-child-row-at-a-time variant with 64 registers, 933 vs 759 us; one unit per thread with four CTAs per chunk, 1029 us)
         static constexpr int units_per_thread = SMR_CELLS_PER_THREAD;
 
         typename PtrOf<const double, RESTRICT>::type f;
