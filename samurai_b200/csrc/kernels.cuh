@@ -21,6 +21,15 @@
 #ifndef SMR_MB_DETAIL
 #define SMR_MB_DETAIL 6
 #endif
+#ifndef SMR_MB_DETAIL3D
+#define SMR_MB_DETAIL3D 4 /* 64 registers, no spills: 759 -> 550 us at level 9 (2: 128 registers, 24 % occupancy, latency bound; 5 and 6 spill) */
+#endif
+#ifndef SMR_MB_CRIT3D
+#define SMR_MB_CRIT3D 6 /* 3D criteria: 249 (4) / 239 (6) / 273 us (8 CTAs per SM) at level 9 */
+#endif
+#ifndef SMR_MB_MAX3D
+#define SMR_MB_MAX3D 8 /* 3D keep propagation: 211 (4) / 158 (6) / 141 us (8) */
+#endif
 #ifndef SMR_MB_CRITERIA
 #define SMR_MB_CRITERIA 6
 #endif
@@ -1125,7 +1134,7 @@ namespace smr
     {
         static constexpr bool two_phase = false;
         static constexpr bool warp_uniform = false;
-        static constexpr int min_blocks = DIM > 2 ? 2 : SMR_MB_DETAIL; // 3D radius 1 holds 16 accumulators + 27 coarse values (measured slower at level 9: a one-child-row-at-a-time variant with 64 registers, 933 vs 759 us; one unit per thread with four CTAs per chunk, 1029 us)
+        static constexpr int min_blocks = DIM > 2 ? SMR_MB_DETAIL3D : SMR_MB_DETAIL; // 3D radius 1 holds 16 accumulators + 27 coarse values (measured slower at level 9: a one-child-row-at-a-time variant with 64 registers, 933 vs 759 us; one unit per thread with four CTAs per chunk, 1029 us)
         static constexpr int units_per_thread = SMR_CELLS_PER_THREAD;
 
         typename PtrOf<const double, RESTRICT>::type f;
@@ -1214,7 +1223,7 @@ namespace smr
     {
         static constexpr bool two_phase = true; // all detail loads of a thread's units are issued before its first tag store
         static constexpr bool warp_uniform = false;
-        static constexpr int min_blocks = DIM > 2 ? 4 : SMR_MB_CRITERIA;
+        static constexpr int min_blocks = DIM > 2 ? SMR_MB_CRIT3D : SMR_MB_CRITERIA;
         static constexpr int units_per_thread = SMR_CELLS_PER_THREAD;
 
         typename PtrOf<const double, RESTRICT>::type detail; // ncomp arrays of `stride` entries (one per adapted field)
@@ -1322,7 +1331,7 @@ namespace smr
     {
         static constexpr bool two_phase = true; // the tag loads of a thread's units are issued before its first store
         static constexpr bool warp_uniform = false;
-        static constexpr int min_blocks = DIM > 2 ? 4 : SMR_MB_MAXIMUM;
+        static constexpr int min_blocks = DIM > 2 ? SMR_MB_MAX3D : SMR_MB_MAXIMUM;
         static constexpr int units_per_thread = SMR_CELLS_PER_THREAD;
 
         typename PtrOf<uint8_t, RESTRICT>::type tag;
