@@ -338,6 +338,35 @@ def uniform_sweep(sb, torch, level, iters=20):
     return n, secs, gsecs, dsecs
 
 
+def weno5_sweep(sb, torch, level, iters=10):
+    """rhs = make_convection_weno5(velocity)(u) on a uniform, fully periodic 2D level-`level` mesh with max_stencil_size(6)
+    (demos/FiniteVolume/linear_convection.cpp's operator, row f1): per cell four WENO5 fluxes of ~60 fp64 operations each without FMA
+    contraction, so the fp64 pipe bounds it, not HBM (8 B zero-fill + 8 B read + 8 B write per cell)."""
+    cfg = sb.mesh_config(2, 1).min_level(level).max_level(level).periodic([True, True]).max_stencil_size(6)
+    mesh = sb.MRMesh.make_mesh([-1.0, -1.0], [1.0, 1.0], cfg)
+    u = sb.make_scalar_field("u", mesh)
+    u.resize()
+    u.fill(0.0)
+    u.init_ball([-0.5, 0.5], 0.3)
+    rhs = sb.make_scalar_field("rhs", mesh)
+    conv = sb.make_convection_weno5([1.0, -1.0])
+    n = mesh.nb_cells()
+    for _ in range(3):
+        conv.apply(rhs, u)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        conv.apply(rhs, u)
+    e1.record()
+    torch.cuda.synchronize()
+    secs = e0.elapsed_time(e1) * 1e-3 / iters
+    for f in (rhs, u):
+        f.destroy()
+    mesh.destroy()
+    return n, secs
+
+
 def uniform_full_step(sb, torch, dim, level, iters=10):
     """The WHOLE step on a uniform level-`level` mesh with min_level = level - 1 (BASELINE.json configs[4] shapes): MRadaptation
     (zero fill, keep tags, ghost update = projection level -> level-1 + BC, detail, criteria, keep propagation, change flag),
@@ -638,6 +667,15 @@ def run_product(args):
                      "peak": peak_gbs, "unit": "GB/s", "frac": 16.0 * n_u / s_u / 1e9 / peak_gbs,
                      "diffusion_order2": {"ms_per_apply": 1e3 * d_u, "note": "rhs = make_diffusion_order2(K)(u): fill(0) + gather, 8 B zero-fill + 8 B read + 8 B write per cell",
                                           "achieved": 24.0 * n_u / d_u / 1e9, "frac": 24.0 * n_u / d_u / 1e9 / peak_gbs}}
+
+            try:
+                n_w, s_w = weno5_sweep(sb, torch, max(args.sweep_level - 1, 2))
+                sweep["weno5"] = {"workload": f"rhs = make_convection_weno5(a)(u), uniform periodic 2D level {max(args.sweep_level - 1, 2)}, {n_w} cells",
+                                  "ms_per_apply": 1e3 * s_w, "cells_per_s": n_w / s_w, "achieved": 24.0 * n_w / s_w / 1e9, "unit": "GB/s",
+                                  "frac": 24.0 * n_w / s_w / 1e9 / peak_gbs,
+                                  "note": "fp64-pipe bound (four WENO5 fluxes per cell, no FMA contraction for bit-exactness), not HBM bound"}
+            except sb.SamuraiError as e:
+                sweep["weno5"] = {"error": str(e)}
 
         # ---- flux-based scheme on the same adapted mesh (a8-a10): rhs = diffusion(u); unp1 = u - dt * rhs ----------------
         flux = None
