@@ -95,8 +95,8 @@ def test_cpp_heat_explicit_matches_reference_golden(gpu, tmp_path):
 
 
 def test_cpp_linear_convection_weno5_matches_reference_golden(gpu, tmp_path):
-    """tests/cpp/linear_convection_explicit.cpp (the explicit branch of demos/FiniteVolume/linear_convection.cpp kept statement for
-    statement: fully periodic box, max_stencil_size(6), make_convection_weno5, TVD-RK3 as field expressions, MRadaptation every step) with
+    """tests/cpp/linear_convection_explicit.cpp (the explicit mode of demos/FiniteVolume/linear_convection.cpp written with the same
+    API calls: fully periodic box, max_stencil_size(6), make_convection_weno5, TVD-RK3 as field expressions, MRadaptation every step) with
     the reference test's arguments (tests/test_demo_finite_volume.py:280-298) against the reference's own golden file
     test_finite_volume_demo_linear_convection_explicit.h5 (tests/golden/linear_convection_explicit.npz)."""
     exe = os.path.join(DEMOS, "linear-convection-explicit")
