@@ -1,5 +1,5 @@
 """Closed-form boundary ghost values, restating the reference's tests/test_bc_ghost_values.cpp for the cases on the hot path
-(Dirichlet<1> / Neumann<1> with a constant value, ghost width 1; corners): a field that the boundary reconstruction is exact
+(Dirichlet<1> / Neumann<1> with a constant value, ghost widths 1 and 2 -- the second layer by polynomial extrapolation --; corners): a field that the boundary reconstruction is exact
 on, so every filled ghost must hold f(ghost centre) to 1e-11 -- on uniform meshes and on an adapted mesh whose boundary
 crosses several levels (`adapted_mesh`, :56-80), in 1D, 2D and 3D.  The reference applies the BC in one direction at a time
 (`apply_field_bc(u, direction)`); here the whole update_ghost_mr runs with the same constant on every side and only the
@@ -45,24 +45,25 @@ def _fill_leaves(mesh, u, f):
     return lv, co, off
 
 
-def _check_direction(mesh, u, axis, sign, f):
-    """ghosts one layer outside the boundary leaves of every level in direction sign * e_axis (check_ghosts, :98-126)"""
+def _check_direction(mesh, u, axis, sign, f, layers=1):
+    """ghosts `layers` layers outside the boundary leaves of every level in direction sign * e_axis (check_ghosts, :98-126)"""
     lv, co, _ = mesh.cell_table(sb.CELLS)
     vals = u.download()
     nb, levels = 0, set()
     for level in np.unique(lv):
         n = 1 << int(level)
         sel = (lv == level) & (co[:, axis] == (n - 1 if sign > 0 else 0))
-        ghosts = co[sel].copy()
-        ghosts[:, axis] += sign
         h = mesh.cell_length(int(level))
-        for g in ghosts:
-            idx = [int(v) for v in g] + [0] * (3 - len(g))
-            off = mesh.get_index(int(level), *idx)
-            expect = f(((g + 0.5) * h)[None, :])[0]
-            assert abs(vals[off] - expect) < 1e-11, f"level {level} ghost {g}: {vals[off]} vs {expect}"
-            nb += 1
-        if ghosts.shape[0]:
+        for k in range(1, layers + 1):
+            ghosts = co[sel].copy()
+            ghosts[:, axis] += k * sign
+            for g in ghosts:
+                idx = [int(v) for v in g] + [0] * (3 - len(g))
+                off = mesh.get_index(int(level), *idx)
+                expect = f(((g + 0.5) * h)[None, :])[0]
+                assert abs(vals[off] - expect) < 1e-11, f"level {level} layer {k} ghost {g}: {vals[off]} vs {expect}"
+                nb += 1
+        if sel.any():
             levels.add(int(level))
     assert nb > 0
     return levels
@@ -129,5 +130,46 @@ def test_corner_ghosts_reflect_about_the_corner(gpu, dim):
                 r = 0.0 if oi[d] < 0 else 1.0
                 refl[d] = r - mag * oi[d]
         assert abs(vals[o] - f(refl[None, :])[0]) < 1e-11, f"corner ghost at {ci}"
+    u.destroy()
+    mesh.destroy()
+
+
+def _mesh_width2(dim, kind):
+    """the library's default mesh_config (no disable_minimal_ghost_width(): max_stencil_radius 2, mesh_config.hpp:388-393)"""
+    if kind == "uniform":
+        level = 4 if dim < 3 else 3
+        return sb.MRMesh.make_mesh([0.0] * dim, [1.0] * dim, sb.mesh_config(dim, 1).min_level(level).max_level(level))
+    mesh = sb.MRMesh.make_mesh([0.0] * dim, [1.0] * dim, sb.mesh_config(dim, 1).min_level(2).max_level(5))
+    phi = sb.make_scalar_field("phi", mesh)
+    phi.resize()
+    phi.init_ball([0.0] * dim, 0.3)
+    sb.make_bc(phi, sb.DIRICHLET, 0.0)
+    sb.make_MRAdapt(phi)(sb.mra_config().epsilon(1e-4))
+    phi.destroy()
+    return mesh
+
+
+@pytest.mark.parametrize("dim", [1, 2, 3])
+@pytest.mark.parametrize("kind", ["uniform", "adapted"])
+@pytest.mark.parametrize("bc", ["dirichlet", "neumann"])
+def test_further_ghosts_exact_on_linear_field(gpu, dim, kind, bc):
+    """further_ghosts_dirichlet1_{uniform,adapted}_{2,3}d / further_ghosts_neumann_uniform_{2,3}d (:386-440, 917-960): with ghost width 2
+    a Dirichlet<1> / Neumann<1> condition fills the first layer and update_further_ghosts_by_polynomial_extrapolation the second
+    (bc/apply_field_bc.hpp:499-563); on a field that is linear along the normal both layers hold f(ghost centre).  The reference drives
+    the case with a function B.C.; with the constant one of this path the field is linear in the normal coordinate only."""
+    if kind == "adapted" and dim == 1:
+        pytest.skip("the reference has no 1D adapted case")
+    mesh = _mesh_width2(dim, kind)
+    u = sb.make_scalar_field("u", mesh)
+    for axis, sign in itertools.product(range(dim), (-1, 1)):
+        def f(x, axis=axis):
+            return 1.0 + 3.0 * x[:, axis]
+        _fill_leaves(mesh, u, f)
+        if bc == "dirichlet":
+            sb.make_bc(u, sb.DIRICHLET, 1.0 + 3.0 * (1.0 if sign > 0 else 0.0))
+        else:
+            sb.make_bc(u, sb.NEUMANN, 3.0 * sign)
+        sb.update_ghost_mr(u)
+        _check_direction(mesh, u, axis, sign, f, layers=2)
     u.destroy()
     mesh.destroy()
