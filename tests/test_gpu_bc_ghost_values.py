@@ -99,11 +99,15 @@ def test_constant_bc_exact_on_linear_field(gpu, dim, kind, bc):
 
 
 @pytest.mark.parametrize("dim", [2, 3])
-def test_corner_ghosts_reflect_about_the_corner(gpu, dim):
-    """corners_{2,3}d_ghost_width_1 (:318-360, 761-780): on a uniform level-3 mesh every corner-block ghost holds the field
+@pytest.mark.parametrize("width", [1, 2])
+def test_corner_ghosts_reflect_about_the_corner(gpu, dim, width):
+    """corners_{2,3}d_ghost_width_{1,2} (:318-360, 761-780): on a uniform level-3 mesh every corner-block ghost holds the field
     reflected about the domain corner, f = 1 + 0.5 x0^2 + sum (d+1) x_d (corner_oracle, :289-316)."""
     level = 3
-    mesh = _uniform(dim, level)
+    if width == 1:
+        mesh = _uniform(dim, level)
+    else:
+        mesh = sb.MRMesh.make_mesh([0.0] * dim, [1.0] * dim, sb.mesh_config(dim, 1).min_level(level).max_level(level))
     u = sb.make_scalar_field("u", mesh)
 
     def f(x):
