@@ -243,6 +243,8 @@ namespace samurai
         inline double epsilon               = std::numeric_limits<double>::infinity();
         inline double regularity            = std::numeric_limits<double>::infinity();
         inline bool timers                  = false;
+        inline bool rel_detail              = false;
+        inline bool refine_boundary         = false;
     }
 
     // ---- samurai.hpp:22-114 --------------------------------------------------------------------------------------------
@@ -259,6 +261,8 @@ namespace samurai
         app.add_option("--mr-eps", args::epsilon, "The epsilon used by the multiresolution to adapt the mesh");
         app.add_option("--mr-reg", args::regularity, "The regularity criteria used by the multiresolution to adapt the mesh");
         app.add_flag("--timers", args::timers, "Print timers at the end of the program");
+        app.add_flag("--mr-rel-detail", args::rel_detail, "Use relative detail instead of absolute detail");
+        app.add_flag("--refine-boundary", args::refine_boundary, "Keep the boundary refined at max_level");
         int device = 0;
         if (const char* e = std::getenv("SAMURAI_B200_DEVICE"))
         {
@@ -852,6 +856,7 @@ namespace samurai
             c.max_level          = static_cast<int32_t>(cfg.max_level());
             c.pred_radius        = Config::prediction_stencil_radius;
             c.max_stencil_radius = cfg.max_stencil_radius();
+            c.refine_boundary    = args::refine_boundary ? 1 : 0;
             c.graduation_width   = static_cast<int32_t>(cfg.graduation_width());
             // approximate_box (box.hpp:280-360) for boxes whose edge lengths are integer multiples of the smallest one
             const auto len = b.length();
@@ -2428,6 +2433,10 @@ namespace samurai
             if (std::isfinite(args::regularity))
             {
                 m_reg = args::regularity;
+            }
+            if (args::rel_detail) // mr/config.hpp:57-60
+            {
+                m_rel = true;
             }
         }
 

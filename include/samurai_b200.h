@@ -56,7 +56,8 @@ extern "C"
         double origin[3];           /* Box::min_corner                                             */
         double scaling_factor;      /* LevelCellArray::scaling_factor (box.hpp:280-, approximate_box) */
         int32_t periodic[3];        /* mesh_config::periodic(d) (mesh_config.hpp:171-196)           */
-        int32_t reserved;
+        int32_t refine_boundary;    /* args::refine_boundary (`--refine-boundary`): keep_boundary_refined after the criteria,
+                                       mr/adapt.hpp:245-274, 340-345 */
     } smr_mesh_config;
 
     /* one x-interval of a sub-mesh: LevelCellArray entry (interval.hpp:50-64) flattened with its (y, z) */

@@ -948,7 +948,24 @@ def compute_relative_detail(mesh: Mesh, f, detail):
     detail *= 1.0 / m
 
 
-def adapt(mesh: Mesh, f, bc: Bc, eps=1e-4, regularity=1.0, trace=None, relative_detail=False):
+def keep_boundary_refined(mesh: Mesh, tag):
+    """keep_boundary_refined (mr/adapt.hpp:245-274, `--refine-boundary`): after the criteria, the leaves of max_level within
+    max_stencil_radius cells of the domain boundary, direction after direction (boundary.hpp:6-22: cells minus translate(domain, -w * dir)),
+    get tag = keep (assignment)."""
+    cfg, dim, L = mesh.cfg, mesh.cfg.dim, mesh.cfg.max_level
+    cells = mesh.cells[L]
+    if cells.size == 0:
+        return
+    w = cfg.max_stencil_radius
+    c = unpack(cells, dim)
+    for d in range(dim):
+        n = cfg.n_cells0[d] << L
+        for sel in (c[:, d] >= n - w, c[:, d] < w):  # direction +e_d, then -e_d
+            if sel.any():
+                tag[mesh.index(L, cells[sel])] = KEEP
+
+
+def adapt(mesh: Mesh, f, bc: Bc, eps=1e-4, regularity=1.0, trace=None, relative_detail=False, refine_boundary=False):
     """Adapt::operator() + harten (mr/adapt.hpp:148-195, 277-389). Returns (mesh, field)."""
     cfg = mesh.cfg
     lmin, L = cfg.min_level, cfg.max_level
@@ -966,6 +983,8 @@ def adapt(mesh: Mesh, f, bc: Bc, eps=1e-4, regularity=1.0, trace=None, relative_
             compute_relative_detail(mesh, f, detail)
         for level in range(lmin, L - ite + 1):
             mr_criteria(mesh, detail, tag, level, eps, regularity)
+        if refine_boundary:  # mr/adapt.hpp:340-345
+            keep_boundary_refined(mesh, tag)
         for level in range(L, 0, -1):
             update_tag_periodic(mesh, tag, level)  # mr/adapt.hpp:353
             maximum(mesh, tag, level)

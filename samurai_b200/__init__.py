@@ -35,7 +35,7 @@ class MeshConfigC(C.Structure):
         ("origin", C.c_double * 3),
         ("scaling_factor", C.c_double),
         ("periodic", C.c_int32 * 3),
-        ("reserved", C.c_int32),
+        ("refine_boundary", C.c_int32),
     ]
 
 
@@ -296,6 +296,11 @@ class mesh_config:
         self._disable_minimal_ghost_width = True
         return self
 
+    def refine_boundary(self, on=True):
+        """args::refine_boundary (`--refine-boundary`, arguments.hpp:67): keep_boundary_refined after the criteria (mr/adapt.hpp:245-274)"""
+        self._refine_boundary = bool(on)
+        return self
+
     def periodic(self, *flags):
         """mesh_config::periodic(bool) / periodic(array) (mesh_config.hpp:171-196)"""
         if len(flags) == 1 and isinstance(flags[0], (list, tuple)):
@@ -315,6 +320,7 @@ class mesh_config:
         c.pred_radius, c.max_stencil_radius, c.graduation_width = self.pred_radius, msr, self._graduation_width
         for d in range(3):
             c.periodic[d] = 1 if (d < self.dim and self._periodic[d]) else 0
+        c.refine_boundary = 1 if getattr(self, "_refine_boundary", False) else 0
         lengths = [float(box_max[d]) - float(box_min[d]) for d in range(self.dim)]
         # approximate_box (box.hpp:280-360) for boxes whose lengths are integer multiples of the smallest one
         scaling = min(lengths)

@@ -1478,6 +1478,7 @@ namespace smr
     {
         Arena arena;
         Batch fv;                     // all leaves, level ascending (initialisation, keep tags)
+        Batch keep_bdry;              // `--refine-boundary`: the max_level leaves within max_stencil_radius cells of the domain boundary
         Batch fv_strip, fv_single;    // the same leaves split for the FV kernels (strips of rows + remainder)
         int64_t fv_strip_cells = 0;
         std::vector<GhostPhase> down; // indexed by level (top-down sweep uses L..0)
@@ -2192,6 +2193,23 @@ namespace smr
         // layout (serial, cheap) then fill (parallel) straight into the staging arena
         plan.derive.clear();
         PendingSeeds p_fv        = pending_seeds(&plan.fv, B_FV, SMR_DERIVE_FV, -1, sizeof(smr_item_fv));
+        // keep_boundary_refined (mr/adapt.hpp:245-274): cells[max_level] minus translate(domain, -w * direction) for every Cartesian
+        // direction (boundary.hpp:6-22) = the leaves outside the domain shrunk by w on every side; tag = keep for all of them
+        std::vector<smr_seed> bdry_seeds;
+        PendingSeeds p_bdry = pending_seeds(&plan.keep_bdry, B_FV, SMR_DERIVE_FV, -1, sizeof(smr_item_fv));
+        if (m.cfg.refine_boundary && m.cfg.max_level < nlev && !m.cells[m.cfg.max_level].empty())
+        {
+            const int Lb = m.cfg.max_level, w = m.cfg.max_stencil_radius;
+            int blo[3], bhi[3];
+            m.domain_box(Lb, 0, blo, bhi);
+            for (int k = 0; k < m.cfg.dim; ++k)
+            {
+                blo[k] += w;
+                bhi[k] -= w;
+            }
+            set_seeds(minus_box(m.cells[Lb], m.cfg.dim, blo, bhi), Lb, flt, false, bdry_seeds);
+        }
+        p_bdry.parts.push_back(&bdry_seeds);
         PendingSeeds p_fv_single = pending_seeds(&plan.fv_single, B_FV, SMR_DERIVE_FV, -1, sizeof(smr_item_fv));
         PendingSeeds p_fv_strip  = pending_seeds(&plan.fv_strip, B_FV, SMR_DERIVE_FVSTRIP, -1, sizeof(smr_item_fvstrip), SMR_CTA_THREADS * STRIP_UPT);
         PendingSeeds p_detail    = pending_seeds(&plan.detail, B_DETAIL, SMR_DERIVE_DETAIL, -1, sizeof(smr_item_detail));
@@ -2247,6 +2265,7 @@ namespace smr
             }
         }
         layout_seeds(p_fv, plan.arena, plan.derive);
+        layout_seeds(p_bdry, plan.arena, plan.derive);
         layout_seeds(p_fv_single, plan.arena, plan.derive);
         layout_seeds(p_fv_strip, plan.arena, plan.derive);
         plan.fv_strip_cells = plan.fv_strip.n_cells * SMR_STRIP_ROWS;
@@ -2282,6 +2301,7 @@ namespace smr
             add(p_fv_single);
             add(p_fv_strip);
             add(p_fv);
+            add(p_bdry);
             add(p_detail);
             add(p_tag_all);
             for (int l = 0; l < nlev; ++l)

@@ -544,6 +544,7 @@ namespace smr
         out.pred_radius        = c->pred_radius;
         out.max_stencil_radius = c->max_stencil_radius;
         out.graduation_width   = c->graduation_width;
+        out.refine_boundary    = c->refine_boundary != 0;
         for (int d = 0; d < 3; ++d)
         {
             out.n0[d]     = d < c->dim ? c->n_cells0[d] : 1;
@@ -1727,6 +1728,12 @@ namespace smr
             wb.begin_phase();
             wb.add(WF_CRITERIA, mo.plan.tag_all, 0, criteria_limit);
             wb.end_phase();
+            if (cfg.refine_boundary && (!mo.plan.keep_bdry.empty() || wb.keep_empty)) // keep_boundary_refined, mr/adapt.hpp:340-345
+            {
+                wb.begin_phase();
+                wb.add(WF_KEEP, mo.plan.keep_bdry, 0);
+                wb.end_phase();
+            }
             for (int level = L; level >= 1; --level)
             {
                 for (int k = 0; k < dim; ++k) // update_tag_periodic(level), mr/adapt.hpp:353
@@ -1793,6 +1800,10 @@ namespace smr
                         launch<smr_item_tag>(SMR_FAM_CRITERIA, arena, mo.plan.tag_all, CriteriaOp<3>{detail, tag, tp, ncomp, n}, limit);
                         break;
                 }
+            }
+            if (cfg.refine_boundary) // keep_boundary_refined, mr/adapt.hpp:340-345
+            {
+                launch<smr_item_fv>(SMR_FAM_KEEP, arena, mo.plan.keep_bdry, KeepLeavesOp{tag, mo.filter.mask_all()});
             }
             for (int level = L; level >= 1; --level)
             {
@@ -2315,7 +2326,7 @@ extern "C"
                 {
                     out->periodic[d] = c.periodic[d] ? 1 : 0;
                 }
-                out->reserved = 0;
+                out->refine_boundary = c.refine_boundary ? 1 : 0;
             });
     }
 

@@ -47,6 +47,7 @@ namespace smr
         double origin[3]       = {0, 0, 0};
         double scaling         = 1.0;
         bool periodic[3]       = {false, false, false}; // mesh_config::periodic(d)
+        bool refine_boundary   = false;                 // args::refine_boundary: keep_boundary_refined (mr/adapt.hpp:245-274)
 
         bool any_periodic() const
         {

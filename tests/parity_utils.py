@@ -90,15 +90,15 @@ def init_square(omesh, half=0.1):
     return u
 
 
-def adapt_both(adapt, mcfg, pmesh, omesh, ou, bc, eps, regularity, relative_detail=False, trace_tags=False, what=""):
+def adapt_both(adapt, mcfg, pmesh, omesh, ou, bc, eps, regularity, relative_detail=False, trace_tags=False, what="", refine_boundary=False):
     """One MRadaptation call on both sides.  With trace_tags the product runs iteration by iteration (smr_adapt_iteration)
     and the tag array (uint8, every reference cell) and the detail array (fp64, every reference cell) of EVERY harten
     iteration are compared with the oracle's: tags bit-exact (north_star), details within REL_TOL (observed: bit-exact)."""
     if not trace_tags:
         adapt(mcfg)
-        return so.adapt(omesh, ou, bc, eps, regularity, relative_detail=relative_detail)
+        return so.adapt(omesh, ou, bc, eps, regularity, relative_detail=relative_detail, refine_boundary=refine_boundary)
     trace = []
-    omesh2, ou2 = so.adapt(omesh, ou, bc, eps, regularity, trace=trace, relative_detail=relative_detail)
+    omesh2, ou2 = so.adapt(omesh, ou, bc, eps, regularity, trace=trace, relative_detail=relative_detail, refine_boundary=refine_boundary)
     cfg = omesh.cfg
     n_ite = 0
     for ite in range(cfg.max_level - cfg.min_level):
@@ -121,7 +121,7 @@ def adapt_both(adapt, mcfg, pmesh, omesh, ou, bc, eps, regularity, relative_deta
 
 def run_advection_parity(dim=2, min_level=2, max_level=6, pred_radius=1, steps=3, eps=2e-4, regularity=1.0, device=0, verbose=False,
                          scheme="upwind", relative_detail=False, amplitude=1.0, init="disc", trace_tags=False, a=None, cfl=None,
-                         discs=None, check_ghosts=True, periodic=None, msr=1):
+                         discs=None, check_ghosts=True, periodic=None, msr=1, refine_boundary=False):
     """demos/FiniteVolume/advection_2d.cpp time loop on the GPU, checked against the oracle at every step:
     meshes bit-identical (cells + all ghosts + storage offsets), fields within 1e-12 relative; with trace_tags also the
     tag and detail arrays of every harten iteration.  `discs`: [(center, radius, value)] initial condition
@@ -141,7 +141,10 @@ def run_advection_parity(dim=2, min_level=2, max_level=6, pred_radius=1, steps=3
     else:
         ou = so.init_disc(omesh, [0.3] * dim, 0.2) * amplitude
 
-    pmesh = sb.MRMesh.make_mesh([0.0] * dim, [1.0] * dim, product_cfg(dim, min_level, max_level, pred_radius, periodic, msr))
+    pcfg = product_cfg(dim, min_level, max_level, pred_radius, periodic, msr)
+    if refine_boundary:
+        pcfg = pcfg.refine_boundary()
+    pmesh = sb.MRMesh.make_mesh([0.0] * dim, [1.0] * dim, pcfg)
     assert_same_mesh(pmesh, omesh)
     u = sb.make_scalar_field("u", pmesh)
     u.resize()
@@ -167,10 +170,12 @@ def run_advection_parity(dim=2, min_level=2, max_level=6, pred_radius=1, steps=3
         if verbose:
             print(f"{tag}: leaves {omesh.nb_cells()} ref {omesh.nref} max rel err {err:.2e}")
 
-    omesh, ou = adapt_both(adapt, mcfg, pmesh, omesh, ou, bc, eps, regularity, relative_detail, trace_tags and not relative_detail, "initial adaptation")
+    omesh, ou = adapt_both(adapt, mcfg, pmesh, omesh, ou, bc, eps, regularity, relative_detail, trace_tags and not relative_detail, "initial adaptation",
+                           refine_boundary)
     check("initial adaptation")
     for it in range(steps):
-        omesh, ou = adapt_both(adapt, mcfg, pmesh, omesh, ou, bc, eps, regularity, relative_detail, trace_tags and not relative_detail, f"step {it}")
+        omesh, ou = adapt_both(adapt, mcfg, pmesh, omesh, ou, bc, eps, regularity, relative_detail, trace_tags and not relative_detail, f"step {it}",
+                               refine_boundary)
         sb.update_ghost_mr(u)
         so.update_ghost_mr(omesh, ou, bc)
         if check_ghosts:

@@ -147,3 +147,17 @@ def test_vector_field_soa_components_match_oracle(gpu):
         assert got.shape == (omesh.nref, 2)
         pu.assert_fields_close(got[leaf, 0], o0[leaf], f"component 0 step {step}")
         pu.assert_fields_close(got[leaf, 1], o1[leaf], f"component 1 step {step}")
+
+
+@pytest.mark.parametrize("dim,min_level,max_level,msr,steps", [(1, 2, 8, 1, 6), (2, 2, 6, 1, 5), (2, 2, 6, 2, 5), (3, 1, 4, 1, 3)])
+def test_refine_boundary_matches_oracle(gpu, dim, min_level, max_level, msr, steps):
+    """`--refine-boundary` (arguments.hpp:67): keep_boundary_refined after the criteria of every harten iteration (mr/adapt.hpp:245-274,
+    340-345) keeps the max_level leaves within max_stencil_radius cells of the boundary.  Tags and details of every harten iteration,
+    all sub-meshes and the leaves at every step against the oracle."""
+    r = pu.run_advection_parity(dim=dim, min_level=min_level, max_level=max_level, pred_radius=1, steps=steps, msr=msr, trace_tags=True,
+                                refine_boundary=True, cfl=0.5 if dim < 3 else 0.25)
+    assert r["max_rel_err"] <= pu.REL_TOL
+    # the boundary stays refined: more leaves than without the flag
+    r0 = pu.run_advection_parity(dim=dim, min_level=min_level, max_level=max_level, pred_radius=1, steps=steps, msr=msr,
+                                 cfl=0.5 if dim < 3 else 0.25)
+    assert r["leaves"] > r0["leaves"]
