@@ -11,12 +11,22 @@ behind a shared implementation.  Floating-point work is plain numpy fp64
 element-wise arithmetic (no FMA, IEEE round-to-nearest), written in the
 reference's operation order so results are bit-comparable.
 
-Parity pin: `tests/test_oracle_golden.py` checks this oracle against the
-reference's golden HDF5 files -- advection_2d (prediction radius 0 and 1, initial
-and final meshes + fields) for the field-expression path, and heat.cpp --explicit
-(test_finite_volume_demo_heat_explicit.h5) for the flux-based schemes across level
-jumps -- see tests/golden/make_golden.py.  Unpinned (no golden in the snapshot):
-upwind_scalar_burgers, the non-linear flux scheme, everything 3D.
+Parity pin: `tests/test_oracle_golden.py` checks this oracle against four of the
+reference's golden HDF5 files (converted by tests/golden/make_golden.py):
+  * advection_2d, prediction radius 0 and 1, initial and final meshes + fields
+    (field-expression path, MR adaptation, ghost update, graduation);
+  * heat.cpp --explicit (test_finite_volume_demo_heat_explicit.h5): linear flux
+    schemes across level jumps, Neumann;
+  * burgers_mra.cpp (test_finite_volume_demo_mra_burgers_hat.h5): NON-LINEAR flux
+    scheme, ghost width 2 (further-ghost extrapolation, contiguous-boundary
+    graduation rule), graduation width 2;
+  * linear_convection.cpp explicit (test_finite_volume_demo_linear_convection_explicit.h5):
+    WENO5 (six-cell stencil, ghost width 3), fully periodic mesh with interfaces
+    through the boundary, TVD-RK3;
+and against the reference's own periodic test property (tests/test_periodic_oracle.py).
+Unpinned (no golden in the snapshot that this path reaches): upwind_scalar_burgers,
+the vector and WENO5 forms of the non-linear convection, `--refine-boundary`,
+everything 3D: there this file is the restatement only.
 
 Reference (hpc-maths/samurai v0.33.0, paths relative to include/samurai/):
   mesh construction      mesh.hpp:326-341,426-439,894-911,1160-1262  mr/mesh.hpp:222-455
@@ -30,9 +40,10 @@ Reference (hpc-maths/samurai v0.33.0, paths relative to include/samurai/):
   flux-based schemes     schemes/fv/flux_based/{flux_based_scheme,explicit_flux_based_scheme}__{lin_hom,nonlin}.hpp
                          interface.hpp:35-306,440-509  schemes/fv/operators/{convection_lin,convection_nonlin,diffusion}.hpp
   relative detail        mr/rel_detail.hpp:73-112
-Supported scope: non-periodic box domains, scalar fp64 fields, ghost width 1
-(max_stencil_radius = 1, prediction radius 0 or 1), Dirichlet<1>/Neumann<1>
-constant BCs -- exactly what BASELINE.json's configs use.
+Supported scope: box domains, periodic or not per direction; scalar fp64 fields
+and lists of component arrays (vector fields, several fields adapted together);
+ghost widths 1 and 2 with Dirichlet<1>/Neumann<1> constant BCs, any width on
+fully periodic meshes; prediction radius 0 or 1.
 """
 from __future__ import annotations
 
