@@ -566,8 +566,9 @@ namespace smr
     {
         int rank = 0, world = 1;
         int dim = 2, L = 0;
-        int margin = 8; // cells of the record's level: stencil reach (<= 2) + strip height (4) + slack
+        int margin = 8; // cells of the record's level: stencil reach (<= 3) + strip height (4) + slack
         std::vector<int64_t> cut2; // world + 1 cut positions in half cells of level L along the slab axis
+        bool periodic_axis = false; // the slab axis is periodic: the first and the last slab are neighbours through the boundary
 
         bool active() const
         {
@@ -627,9 +628,22 @@ namespace smr
             lo               = sh >= 0 ? (lo << sh) : (lo >> (-sh));
             hi               = sh >= 0 ? (hi << sh) : ((hi >> (-sh)) + 1);
             unsigned m       = 0;
+            // a periodic slab axis: the rows near one boundary are the sources of the periodic ghosts beyond the other one
+            // (algorithm/update_periodic.hpp:34-125) and of the stencils that reach through it, so the window also counts shifted
+            // by one period in both directions
+            const int64_t period = cut2.back();
             for (int r = 0; r < world; ++r)
             {
-                if (r != rank && cut2[r] < hi && cut2[r + 1] > lo)
+                if (r == rank)
+                {
+                    continue;
+                }
+                bool hit = cut2[r] < hi && cut2[r + 1] > lo;
+                if (periodic_axis)
+                {
+                    hit = hit || (cut2[r] < hi + period && cut2[r + 1] > lo + period) || (cut2[r] < hi - period && cut2[r + 1] > lo - period);
+                }
+                if (hit)
                 {
                     m |= 1u << r;
                 }
@@ -643,6 +657,7 @@ namespace smr
             dim = m.cfg.dim;
             L   = m.cfg.max_level;
             const int axis   = dim > 2 ? 2 : 1;
+            periodic_axis    = dim > 1 && m.cfg.periodic[axis];
             const int64_t nL = static_cast<int64_t>(m.cfg.n0[axis]) << L;
             cut2.assign(world + 1, 0);
             cut2[world] = 2 * nL;

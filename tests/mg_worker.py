@@ -137,6 +137,40 @@ def main():
         rhs.destroy()
     if rank == 0:
         print("flux schemes on", world, "GPUs OK", flush=True)
+    # WENO5 (six-cell stencils, ghost width 3) on a fully periodic adapted mesh across the slab cuts, incl. the interfaces through the
+    # periodic boundary between the first and the last slab
+    if dim < 3:
+        wl, wh = (2, 8) if dim == 1 else (1, 6)
+        pcfg = sb.mesh_config(dim, 1).min_level(wl).max_level(wh).periodic([True] * dim).max_stencil_size(6)
+        wcfg = so.MeshConfig(dim=dim, min_level=wl, max_level=wh, pred_radius=1, max_stencil_radius=3, graduation_width=1,
+                             origin=(-1.0,) * dim, scaling=2.0, periodic=(True,) * dim)
+        wmesh = sb.MRMesh.make_mesh([-1.0] * dim, [1.0] * dim, pcfg)
+        wom = so.Mesh.uniform(wcfg)
+        c = wom.cell_centers(wh, wom.cells[wh])
+        f0 = np.zeros(wom.nref)
+        f0[wom.index(wh, wom.cells[wh])] = np.where(np.all((c >= -1.0) & (c <= -0.45), axis=1), 1.0, 0.0)
+        wu = sb.make_scalar_field("wu", wmesh)
+        wu.resize()
+        wu.upload(f0)
+        sb.make_MRAdapt(wu)(sb.mra_config())
+        wbc = so.Bc("neumann", 0.0)
+        wom, wou = so.adapt(wom, f0, wbc, 1e-4, 1.0)
+        pu.assert_same_mesh(wmesh, wom)
+        wowners = sb.mg_leaf_owners(wmesh)
+        _, _, wleaf = wom.leaf_table()
+        so.update_ghost_mr(wom, wou, wbc)
+        vel = [1.0, -1.0][:dim]
+        want = so.flux_nonlin_apply(wom, wou, so.weno5_flux(vel), so.WENO5_OFFSETS)
+        rhs = sb.make_convection_weno5(vel)(wu)
+        mine = rhs.download()[wleaf]
+        parts = gather((wowners == rank, mine[wowners == rank]))
+        full = np.empty(wleaf.size)
+        for m, v in parts:
+            full[m] = v
+        bad = np.count_nonzero(full != want[wleaf])
+        assert bad == 0, f"WENO5: {bad} of {wleaf.size} owner leaves differ from the oracle on {world} GPUs"
+        if rank == 0:
+            print("WENO5 on", world, "GPUs OK", flush=True)
     st = sb.stats()
     if rank == 0:
         print("multi-GPU parity OK; launches", st["kernel_launches"], flush=True)

@@ -35,13 +35,18 @@ def test_per_sweep_launches_match_oracle_too(gpu, dim, lmin, lmax, pred):
         pu.sb.set_fused(True)
 
 
-def test_fused_and_per_sweep_paths_are_bit_identical(gpu):
-    """same run twice, fused and per-sweep: every reference cell (leaves AND ghosts) and every tag byte identical"""
+@pytest.mark.parametrize("refine_boundary", [False, True])
+def test_fused_and_per_sweep_paths_are_bit_identical(gpu, refine_boundary):
+    """same run twice, fused and per-sweep: every reference cell (leaves AND ghosts) and every tag byte identical
+    (also with `--refine-boundary`, whose keep phase sits between the criteria and the keep propagation in both paths)"""
     sb = pu.sb
     outs = []
     for fused in (True, False):
         sb.set_fused(fused)
-        mesh = sb.MRMesh.make_mesh([0.0, 0.0], [1.0, 1.0], pu.product_cfg(2, 3, 9, 1))
+        cfg = pu.product_cfg(2, 3, 9, 1)
+        if refine_boundary:
+            cfg = cfg.refine_boundary()
+        mesh = sb.MRMesh.make_mesh([0.0, 0.0], [1.0, 1.0], cfg)
         u = sb.make_scalar_field("u", mesh)
         u.resize()
         u.init_ball([0.3, 0.3], 0.2)
