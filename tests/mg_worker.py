@@ -171,6 +171,35 @@ def main():
         assert bad == 0, f"WENO5: {bad} of {wleaf.size} owner leaves differ from the oracle on {world} GPUs"
         if rank == 0:
             print("WENO5 on", world, "GPUs OK", flush=True)
+        rhs.destroy()
+        # the advection loop on the same periodic mesh (ghost width 3): periodic ghost copies, tag OR through the boundary and
+        # graduation across it, with the first and the last slab as neighbours
+        wunp1 = sb.make_scalar_field("wunp1", wmesh)
+        wadapt = sb.make_MRAdapt(wu)
+        wdt = 0.5 * wmesh.min_cell_length()
+        wa = [1.0, -1.0][:dim]
+        wou = wou.copy()
+        for it in range(3):
+            wadapt(sb.mra_config())
+            wom, wou = so.adapt(wom, wou, wbc, 1e-4, 1.0)
+            pu.assert_same_mesh(wmesh, wom)
+            sb.update_ghost_mr(wu)
+            so.update_ghost_mr(wom, wou, wbc)
+            wunp1.resize()
+            sb.upwind_step(wunp1, wu, wa, wdt)
+            wou = so.fv_step(wom, wou, wa, wdt)
+            sb.swap(wu, wunp1)
+            wowners = sb.mg_leaf_owners(wmesh)
+            _, _, wleaf = wom.leaf_table()
+            mine = wu.download()[wleaf]
+            parts = gather((wowners == rank, mine[wowners == rank]))
+            full = np.empty(wleaf.size)
+            for m, v in parts:
+                full[m] = v
+            bad = np.count_nonzero(full != wou[wleaf])
+            assert bad == 0, f"periodic advection step {it}: {bad} of {wleaf.size} owner leaves differ from the oracle on {world} GPUs"
+        if rank == 0:
+            print("periodic advection on", world, "GPUs OK", flush=True)
     st = sb.stats()
     if rank == 0:
         print("multi-GPU parity OK; launches", st["kernel_launches"], flush=True)
