@@ -50,7 +50,7 @@ extern "C"
         int32_t min_level;          /* mesh_config::min_level                                      */
         int32_t max_level;          /* mesh_config::max_level                                      */
         int32_t pred_radius;        /* template parameter prediction_stencil_radius: 0 or 1        */
-        int32_t max_stencil_radius; /* mesh_config::max_stencil_radius (only 1 is implemented)     */
+        int32_t max_stencil_radius; /* mesh_config::max_stencil_radius: 1 or 2; up to 3 on fully periodic meshes */
         int32_t graduation_width;   /* mesh_config::graduation_width                               */
         int32_t n_cells0[3];        /* box size in level-0 cells: length / scaling_factor          */
         double origin[3];           /* Box::min_corner                                             */
@@ -211,7 +211,7 @@ extern "C"
     int smr_profile_get_bytes(int family, uint64_t* bytes);
     /* 1 (default): ghost update, harten iteration and field transfer each run as ONE cooperative launch that walks the
      * level wavefront with grid-wide barriers; 0: one launch per sweep (same results bit for bit; used to profile the
-     * kernel families separately).  Multi-GPU runs always use the per-sweep launches. */
+     * kernel families separately).  Multi-GPU runs use the fused launches too: the phase barrier then also exchanges flags with the peers. */
     int smr_set_fused(int on);
 
     /* host-side profiling aid: rebuild the sub-meshes and the index batches of the current leaves `reps` times
