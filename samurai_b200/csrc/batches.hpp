@@ -2049,14 +2049,12 @@ namespace smr
         {
             return LevelSet();
         }
-        LevelSet pg = m.in_domain(set_diff(set_diff(m.ref[level], m.cells[level]), m.proj[level]), level);
+        LevelSet pg = m.in_domain(set_diff(m.ref[level], set_union(m.cells[level], m.proj[level])), level);
         if (pg.empty())
         {
             return pg;
         }
-        // "... whose parent exists in all_cells[level - 1]": test the parents of the (few) candidates instead of refining the whole
-        // coarser level (pg ∩ refine(ref[l-1]) == pg ∩ refine(coarsen(pg) ∩ ref[l-1]))
-        return set_inter(pg, refine(set_inter(coarsen(pg, 1, dim), m.ref[level - 1]), 1, dim));
+        return set_inter(pg, refine(m.ref[level - 1], 1, dim));
     }
 
     inline LevelSet detail_set(const Mesh& m, int level)
