@@ -2057,6 +2057,49 @@ namespace smr
         return set_inter(pg, refine(m.ref[level - 1], 1, dim));
     }
 
+    // the rows [row_begin, row_end) of ref[level] of prediction_set(m, level): every operation of prediction_set is row-local (the
+    // parent test needs the coarse rows (y >> 1, z >> 1) only), so the largest levels are cut into row chunks that run as separate
+    // tasks of build_plan instead of one task that was its critical path
+    inline LevelSet prediction_set_rows(const Mesh& m, int level, size_t row_begin, size_t row_end)
+    {
+        const int dim       = m.cfg.dim;
+        const LevelSet& ref = m.ref[level];
+        if (level > m.cfg.max_level || row_begin >= row_end)
+        {
+            return LevelSet();
+        }
+        const int64_t klo = ref.key[row_begin];
+        const bool last   = row_end >= ref.rows();
+        const int64_t khi = last ? 0 : ref.key[row_end];
+        auto rows_of = [&](const LevelSet& s)
+        {
+            const size_t r0 = static_cast<size_t>(std::lower_bound(s.key.begin(), s.key.end(), klo) - s.key.begin());
+            const size_t r1 = last ? s.rows() : static_cast<size_t>(std::lower_bound(s.key.begin(), s.key.end(), khi) - s.key.begin());
+            return slice_rows(s, r0, r1);
+        };
+        LevelSet pg = m.in_domain(set_diff(slice_rows(ref, row_begin, std::min(row_end, ref.rows())), set_union(rows_of(m.cells[level]), rows_of(m.proj[level]))), level);
+        if (pg.empty())
+        {
+            return pg;
+        }
+        // parent rows of the chunk: a contiguous key range of the coarse level (rows are sorted by (z, y))
+        const LevelSet& coarse = m.ref[level - 1];
+        size_t c0 = 0, c1 = coarse.rows();
+        if (dim == 2)
+        {
+            const int y0 = key_y(pg.key.front()) >> 1, y1 = key_y(pg.key.back()) >> 1;
+            c0 = static_cast<size_t>(std::partition_point(coarse.key.begin(), coarse.key.end(), [y0](int64_t k) { return key_y(k) < y0; }) - coarse.key.begin());
+            c1 = static_cast<size_t>(std::partition_point(coarse.key.begin(), coarse.key.end(), [y1](int64_t k) { return key_y(k) <= y1; }) - coarse.key.begin());
+        }
+        else if (dim == 3)
+        {
+            const int z0 = key_z(pg.key.front()) >> 1, z1 = key_z(pg.key.back()) >> 1;
+            c0 = static_cast<size_t>(std::partition_point(coarse.key.begin(), coarse.key.end(), [z0](int64_t k) { return key_z(k) < z0; }) - coarse.key.begin());
+            c1 = static_cast<size_t>(std::partition_point(coarse.key.begin(), coarse.key.end(), [z1](int64_t k) { return key_z(k) <= z1; }) - coarse.key.begin());
+        }
+        return set_inter(pg, refine(slice_rows(coarse, c0, c1), 1, dim));
+    }
+
     inline LevelSet detail_set(const Mesh& m, int level)
     {
         const int dim = m.cfg.dim;
@@ -2089,9 +2132,48 @@ namespace smr
 #ifdef SMR_PLAN_TIMING
         const double tt0 = omp_get_wtime();
 #endif
-#pragma omp parallel for schedule(dynamic, 1)
-        for (int t = 4 * nlev - 1; t >= 0; --t)
+        // prediction sets of the big levels: row chunks as extra tasks (task index >= 4 * nlev)
+        struct PredPart
         {
+            int level;
+            size_t r0, r1;
+            LevelSet res;
+        };
+        std::vector<PredPart> pred_parts;
+        std::vector<char> pred_split(static_cast<size_t>(nlev), 0);
+        for (int level = 1; level <= L && level < nlev; ++level)
+        {
+            if (m.ref[level].n_intervals() >= 8000)
+            {
+                const std::vector<size_t> cut = chunk_rows(m.ref[level], 4000, 8);
+                if (cut.size() > 2)
+                {
+                    pred_split[static_cast<size_t>(level)] = 1;
+                    for (size_t c = 0; c + 1 < cut.size(); ++c)
+                    {
+                        pred_parts.push_back(PredPart{level, cut[c], cut[c + 1], {}});
+                    }
+                }
+            }
+        }
+        const int n_extra = static_cast<int>(pred_parts.size());
+#pragma omp parallel for schedule(dynamic, 1)
+        for (int t = 4 * nlev + n_extra - 1; t >= 0; --t)
+        {
+            if (t >= 4 * nlev)
+            {
+                PredPart& pp = pred_parts[static_cast<size_t>(t - 4 * nlev)];
+                try
+                {
+                    pp.res = prediction_set_rows(m, pp.level, pp.r0, pp.r1);
+                }
+                catch (const std::exception& e)
+                {
+#pragma omp critical
+                    error = e.what();
+                }
+                continue;
+            }
             const int kind = t / nlev, level = t % nlev;
             try
             {
@@ -2104,7 +2186,7 @@ namespace smr
                         }
                         break;
                     case 2:
-                        if (level >= 1 && level <= L)
+                        if (level >= 1 && level <= L && !pred_split[static_cast<size_t>(level)])
                         {
                             predset[level] = prediction_set(m, level);
                         }
@@ -2132,6 +2214,27 @@ namespace smr
         if (!error.empty())
         {
             throw std::out_of_range(error);
+        }
+        for (int level = 1; level < nlev; ++level)
+        {
+            if (pred_split[static_cast<size_t>(level)])
+            {
+                std::vector<const LevelSet*> parts;
+                for (const PredPart& pp : pred_parts)
+                {
+                    if (pp.level == level)
+                    {
+                        parts.push_back(&pp.res);
+                    }
+                }
+                predset[level] = union_all(parts); // disjoint, ascending key ranges: bulk copies
+#ifdef SMR_CHECK_SPLIT
+                if (!predset[level].same_cells(prediction_set(m, level)))
+                {
+                    throw std::logic_error("prediction_set_rows differs from prediction_set");
+                }
+#endif
+            }
         }
         struct Chunk
         {
